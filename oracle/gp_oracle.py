@@ -1,0 +1,563 @@
+"""NumPy / torch-CPU float64 restatement of the GPJax hot path (TEST INFRASTRUCTURE).
+
+Every function cites the reference file:line (relative to the gpjax 0.13.2 tree) whose
+operation order it follows.  Values are NumPy; gradients come from two independent routes
+that the tests cross-check:
+
+* ``*_value_and_grad_autodiff`` -- a literal torch-CPU float64 restatement differentiated by
+  reverse-mode autograd (the analogue of ``jax.value_and_grad`` in ``gpjax/fit.py:160``),
+* ``*_grad_closed_form``        -- the analytic expressions the CUDA path implements.
+
+Nothing in ``gpjax_b200/`` imports this module.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import scipy.linalg as sla
+
+KINDS = {"rbf": 0, "matern32": 1, "matern52": 2}
+KIND_NAMES = {v: k for k, v in KINDS.items()}
+
+__all__ = [
+    "KINDS",
+    "KIND_NAMES",
+    "squared_distance",
+    "euclidean_distance",
+    "kernel_pair",
+    "cross_covariance",
+    "gram",
+    "add_jitter",
+    "softplus",
+    "softplus_inv",
+    "gaussian_log_prob_lu",
+    "conjugate_mll",
+    "conjugate_mll_chol",
+    "conjugate_mll_grad_closed_form",
+    "conjugate_mll_value_and_grad_autodiff",
+    "collapsed_elbo",
+    "collapsed_elbo_streamed",
+    "collapsed_elbo_grad_closed_form",
+    "collapsed_elbo_value_and_grad_autodiff",
+    "conjugate_predict",
+    "gram_longdouble",
+    "conjugate_mll_longdouble",
+]
+
+
+def _kind_id(kind) -> int:
+    if isinstance(kind, str):
+        return KINDS[kind.lower()]
+    return int(kind)
+
+
+# ----------------------------------------------------------------------------------------
+# a1: gpjax/kernels/stationary/utils.py:42-67
+# ----------------------------------------------------------------------------------------
+def squared_distance(x: np.ndarray, y: np.ndarray) -> np.floating:
+    """``jnp.sum((x - y) ** 2)`` -- gpjax/kernels/stationary/utils.py:53."""
+    return np.sum((np.asarray(x, np.float64) - np.asarray(y, np.float64)) ** 2)
+
+
+def euclidean_distance(x: np.ndarray, y: np.ndarray) -> np.floating:
+    """``sqrt(max(r2, 1e-36))`` -- gpjax/kernels/stationary/utils.py:67."""
+    return np.sqrt(np.maximum(squared_distance(x, y), 1e-36))
+
+
+def _profile(kind: int, r2: np.ndarray, variance) -> np.ndarray:
+    """Kernel profile on an array of squared scaled distances.
+
+    rbf.py:43, matern32.py:46-53 (tau via utils.py:67), matern52.py:45-52.
+    """
+    if kind == 0:
+        return variance * np.exp(-0.5 * r2)
+    tau = np.sqrt(np.maximum(r2, 1e-36))
+    if kind == 1:
+        return variance * (1.0 + np.sqrt(3.0) * tau) * np.exp(-np.sqrt(3.0) * tau)
+    if kind == 2:
+        return (
+            variance
+            * (1.0 + np.sqrt(5.0) * tau + 5.0 / 3.0 * np.square(tau))
+            * np.exp(-np.sqrt(5.0) * tau)
+        )
+    raise ValueError(f"unknown kernel kind {kind}")
+
+
+def kernel_pair(kind, x, y, lengthscale, variance) -> np.floating:
+    """Scalar ``kernel(x, y)``: scale both inputs by 1/l first (rbf.py:41-42), then a1."""
+    kind = _kind_id(kind)
+    xs = np.asarray(x, np.float64) / lengthscale
+    ys = np.asarray(y, np.float64) / lengthscale
+    return _profile(kind, squared_distance(xs, ys), variance)
+
+
+def _r2_matrix(xs: np.ndarray, zs: np.ndarray) -> np.ndarray:
+    """Direct-difference squared distances (never the |a|^2+|b|^2-2ab expansion)."""
+    n, d = xs.shape
+    r2 = np.zeros((n, zs.shape[0]), np.float64)
+    for k in range(d):
+        diff = xs[:, k : k + 1] - zs[:, k][None, :]
+        r2 += diff * diff
+    return r2
+
+
+def cross_covariance(kind, x, z, lengthscale, variance) -> np.ndarray:
+    """``vmap(vmap(kernel))`` -- gpjax/kernels/computations/dense.py:32-36."""
+    kind = _kind_id(kind)
+    x = np.atleast_2d(np.asarray(x, np.float64))
+    z = np.atleast_2d(np.asarray(z, np.float64))
+    xs = x / lengthscale
+    zs = z / lengthscale
+    return _profile(kind, _r2_matrix(xs, zs), variance)
+
+
+def gram(kind, x, lengthscale, variance) -> np.ndarray:
+    """``cross_covariance(x, x)`` -- gpjax/kernels/computations/base.py:56-72."""
+    return cross_covariance(kind, x, x, lengthscale, variance)
+
+
+def add_jitter(matrix: np.ndarray, jitter: float) -> np.ndarray:
+    """gpjax/linalg/utils.py:39-65 (same error behaviour)."""
+    if matrix.ndim != 2:
+        raise ValueError(f"Expected 2D matrix, got {matrix.ndim}D array")
+    if matrix.shape[0] != matrix.shape[1]:
+        raise ValueError(f"Expected square matrix, got shape {matrix.shape}")
+    return matrix + np.eye(matrix.shape[0]) * jitter
+
+
+# bijections: gpjax/parameters.py:140-146 (numpyro SoftplusTransform)
+def softplus(u):
+    u = np.asarray(u, np.float64)
+    return np.logaddexp(u, 0.0)
+
+
+def softplus_inv(y):
+    y = np.asarray(y, np.float64)
+    return y + np.log(-np.expm1(-y))
+
+
+# ----------------------------------------------------------------------------------------
+# a9/a10: conjugate_mll, LU formulation exactly as the reference dispatches it
+# ----------------------------------------------------------------------------------------
+def gaussian_log_prob_lu(mu: np.ndarray, sigma: np.ndarray, y: np.ndarray) -> float:
+    """gpjax/distributions.py:124-134 with Dense dispatch:
+    logdet -> slogdet (LU, linalg/operations.py:163-165), solve -> LU (operations.py:109-111)."""
+    n = mu.shape[-1]
+    diff = y - mu
+    logdet = np.linalg.slogdet(sigma)[1]
+    quad = diff @ np.linalg.solve(sigma, diff)
+    return float(-0.5 * (n * np.log(2.0 * np.pi) + logdet + quad))
+
+
+def _sigma(kind, X, lengthscale, variance, obs_stddev, jitter):
+    """objectives.py:96-102: K + jitter*I, then + eye*obs_noise (two separate adds)."""
+    obs_noise = obs_stddev**2
+    Kxx = gram(kind, X, lengthscale, variance)
+    Kxx = add_jitter(Kxx, jitter)
+    return Kxx + np.eye(Kxx.shape[0]) * obs_noise
+
+
+def conjugate_mll(kind, X, y, lengthscale, variance, obs_stddev, mean_const=0.0, jitter=1e-6):
+    """gpjax/objectives.py:93-107 (LU path, reference order)."""
+    X = np.asarray(X, np.float64)
+    y = np.asarray(y, np.float64).reshape(-1)
+    mx = np.ones(X.shape[0]) * mean_const
+    return gaussian_log_prob_lu(mx, _sigma(kind, X, lengthscale, variance, obs_stddev, jitter), y)
+
+
+def conjugate_mll_chol(kind, X, y, lengthscale, variance, obs_stddev, mean_const=0.0, jitter=1e-6):
+    """Cholesky twin of :func:`conjugate_mll` (what the CUDA path does)."""
+    X = np.asarray(X, np.float64)
+    y = np.asarray(y, np.float64).reshape(-1)
+    n = X.shape[0]
+    d = y - mean_const
+    L = np.linalg.cholesky(_sigma(kind, X, lengthscale, variance, obs_stddev, jitter))
+    w = sla.solve_triangular(L, d, lower=True)
+    return float(-0.5 * (n * np.log(2.0 * np.pi) + 2.0 * np.sum(np.log(np.diag(L))) + w @ w))
+
+
+def _dK_dr2(kind: int, r2: np.ndarray, K: np.ndarray, variance) -> np.ndarray:
+    """dK/d(r^2); zero where the 1e-36 clamp is active."""
+    if kind == 0:
+        return -0.5 * K
+    tau = np.sqrt(np.maximum(r2, 1e-36))
+    live = r2 > 1e-36
+    if kind == 1:
+        g = -1.5 * variance * np.exp(-np.sqrt(3.0) * tau)
+    else:
+        g = -(5.0 / 6.0) * variance * (1.0 + np.sqrt(5.0) * tau) * np.exp(-np.sqrt(5.0) * tau)
+    return np.where(live, g, 0.0)
+
+
+def conjugate_mll_grad_closed_form(
+    kind, X, y, lengthscale, variance, obs_stddev, mean_const=0.0, jitter=1e-6
+):
+    """Analytic gradient of conjugate_mll in constrained space.
+
+    alpha = Sigma^-1 d, W = 1/2 (alpha alpha^T - Sigma^-1);
+    d/dvar = <W,K>/var; d/dobs_stddev = 2 obs_stddev tr W; d/dc = sum alpha;
+    d/dl_d = <W, dK/dr2 * (-2 Delta_d^2 / l_d^3)>.   Returns dict of numpy values.
+    """
+    kind = _kind_id(kind)
+    X = np.asarray(X, np.float64)
+    y = np.asarray(y, np.float64).reshape(-1)
+    n, D = X.shape
+    ell = np.asarray(lengthscale, np.float64)
+    iso = ell.ndim == 0
+    ell_v = np.full(D, float(ell)) if iso else ell
+    K = gram(kind, X, ell_v, variance)
+    Sigma = add_jitter(K, jitter) + np.eye(n) * obs_stddev**2
+    Sinv = np.linalg.inv(Sigma)
+    d = y - mean_const
+    alpha = Sinv @ d
+    W = 0.5 * (np.outer(alpha, alpha) - Sinv)
+    xs = X / ell_v
+    r2 = _r2_matrix(xs, xs)
+    G = W * _dK_dr2(kind, r2, K, variance)
+    g_ell = np.zeros(D)
+    for k in range(D):
+        diff = X[:, k : k + 1] - X[:, k][None, :]
+        g_ell[k] = np.sum(G * (-2.0 * diff * diff / ell_v[k] ** 3))
+    out = {
+        "lengthscale": float(g_ell.sum()) if iso else g_ell,
+        "variance": float(np.sum(W * K) / variance),
+        "obs_stddev": float(2.0 * obs_stddev * np.trace(W)),
+        "mean_const": float(alpha.sum()),
+    }
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# torch-CPU literal restatement, differentiated by autograd (jax.value_and_grad analogue)
+# ----------------------------------------------------------------------------------------
+def _t_profile(torch, kind, r2, variance):
+    if kind == 0:
+        return variance * torch.exp(-0.5 * r2)
+    tau = torch.sqrt(torch.clamp_min(r2, 1e-36))
+    if kind == 1:
+        s3 = math.sqrt(3.0)
+        return variance * (1.0 + s3 * tau) * torch.exp(-s3 * tau)
+    s5 = math.sqrt(5.0)
+    return variance * (1.0 + s5 * tau + 5.0 / 3.0 * tau * tau) * torch.exp(-s5 * tau)
+
+
+def _t_cross(torch, kind, x, z, ell, variance):
+    xs = x / ell
+    zs = z / ell
+    diff = xs[:, None, :] - zs[None, :, :]
+    return _t_profile(torch, kind, (diff * diff).sum(-1), variance)
+
+
+def conjugate_mll_value_and_grad_autodiff(
+    kind, X, y, lengthscale, variance, obs_stddev, mean_const=0.0, jitter=1e-6, threads=None
+):
+    """Reverse-mode gradient of the literal LU-path restatement (objectives.py:93-107,
+    distributions.py:124-134, operations.py:109-111,163-165).  O(N^2 D) memory: small N only
+    unless D is small.  Returns (value, grads dict)."""
+    import torch
+
+    if threads:
+        torch.set_num_threads(threads)
+    kind = _kind_id(kind)
+    t = lambda a: torch.tensor(np.asarray(a, np.float64), dtype=torch.float64, requires_grad=True)
+    Xt = torch.tensor(np.asarray(X, np.float64))
+    yt = torch.tensor(np.asarray(y, np.float64).reshape(-1))
+    ell, var, sn, c = t(lengthscale), t(variance), t(obs_stddev), t(mean_const)
+    n = Xt.shape[0]
+    obs_noise = sn**2
+    mx = torch.ones(n, dtype=torch.float64) * c
+    Kxx = _t_cross(torch, kind, Xt, Xt, ell, var)
+    eye = torch.eye(n, dtype=torch.float64)
+    Sigma = (Kxx + eye * jitter) + eye * obs_noise
+    diff = yt - mx
+    logdet = torch.linalg.slogdet(Sigma)[1]
+    quad = diff @ torch.linalg.solve(Sigma, diff)
+    val = -0.5 * (n * math.log(2.0 * math.pi) + logdet + quad)
+    val.backward()
+    g = {
+        "lengthscale": ell.grad.numpy().copy() if ell.grad.ndim else float(ell.grad),
+        "variance": float(var.grad),
+        "obs_stddev": float(sn.grad),
+        "mean_const": float(c.grad),
+    }
+    return float(val.detach()), g
+
+
+# ----------------------------------------------------------------------------------------
+# a11: collapsed_elbo -- gpjax/objectives.py:342-416
+# ----------------------------------------------------------------------------------------
+def collapsed_elbo(kind, X, y, Z, lengthscale, variance, obs_stddev, mean_const=0.0, jitter=1e-6):
+    """Literal order of gpjax/objectives.py:342-416 (A materialised; small N only)."""
+    kind = _kind_id(kind)
+    X = np.asarray(X, np.float64)
+    y = np.asarray(y, np.float64).reshape(-1, 1)
+    Z = np.asarray(Z, np.float64)
+    n = X.shape[0]
+    m = Z.shape[0]
+    noise = obs_stddev**2
+    Kzz = add_jitter(gram(kind, Z, lengthscale, variance), jitter)  # :352-354
+    Kzx = cross_covariance(kind, Z, X, lengthscale, variance)  # :355
+    Kxx_diag = np.array(
+        [_profile(kind, np.float64(0.0), variance) for _ in range(1)]
+    ).repeat(n)  # :356 (k(x,x) = variance for every stationary kernel here)
+    mux = np.ones((n, 1)) * mean_const  # :357
+    Lz = np.linalg.cholesky(Kzz)  # :359
+    A = sla.solve_triangular(Lz, Kzx, lower=True) / np.sqrt(noise)  # :387
+    AAT = A @ A.T  # :390
+    B = np.eye(m) + AAT  # :393
+    L = np.linalg.cholesky(B)  # :396
+    log_det_B = 2.0 * np.sum(np.log(np.diag(L)))  # :399
+    diff = y - mux  # :401
+    L_inv_A_diff = sla.solve_triangular(L, A @ diff, lower=True)  # :404
+    quad = (np.sum(diff**2) - np.sum(L_inv_A_diff**2)) / noise  # :407
+    two_log_prob = -n * np.log(2.0 * np.pi * noise) - log_det_B - quad  # :410
+    two_trace = np.sum(Kxx_diag) / noise - np.trace(AAT)  # :413
+    return float((two_log_prob - two_trace) / 2.0)  # :416
+
+
+def _sgpr_stats_block(kind, Xb, db, Z, Lz, ell, variance, noise):
+    Kzx = cross_covariance(kind, Z, Xb, ell, variance)
+    A = sla.solve_triangular(Lz, Kzx, lower=True) / np.sqrt(noise)
+    return A @ A.T, A @ db, A.sum(axis=1)
+
+
+def collapsed_elbo_streamed(
+    kind, X, y, Z, lengthscale, variance, obs_stddev, mean_const=0.0, jitter=1e-6,
+    block=4096, return_stats=False,
+):
+    """Same value through row-additive statistics Phi, psi;
+    this is the formulation that is sharded over GPUs, and the CPU baseline for config 4."""
+    kind = _kind_id(kind)
+    X = np.asarray(X, np.float64)
+    y = np.asarray(y, np.float64).reshape(-1)
+    Z = np.asarray(Z, np.float64)
+    n, m = X.shape[0], Z.shape[0]
+    noise = obs_stddev**2
+    Lz = np.linalg.cholesky(add_jitter(gram(kind, Z, lengthscale, variance), jitter))
+    Phi = np.zeros((m, m))
+    psi = np.zeros(m)
+    a1 = np.zeros(m)
+    dd = 0.0
+    sd = 0.0
+    for s in range(0, n, block):
+        db = y[s : s + block] - mean_const
+        P, q, a = _sgpr_stats_block(kind, X[s : s + block], db, Z, Lz, lengthscale, variance, noise)
+        Phi += P
+        psi += q
+        a1 += a
+        dd += float(db @ db)
+        sd += float(db.sum())
+    val = _sgpr_finish(Phi, psi, dd, n, variance, noise)
+    if return_stats:
+        return val, dict(Phi=Phi, psi=psi, a1=a1, dd=dd, sd=sd, n=n, Lz=Lz)
+    return val
+
+
+def _sgpr_finish(Phi, psi, dd, n, variance, noise):
+    m = Phi.shape[0]
+    L = np.linalg.cholesky(np.eye(m) + Phi)
+    w = sla.solve_triangular(L, psi, lower=True)
+    quad = (dd - w @ w) / noise
+    two_log_prob = -n * np.log(2.0 * np.pi * noise) - 2.0 * np.sum(np.log(np.diag(L))) - quad
+    two_trace = n * variance / noise - np.trace(Phi)
+    return float((two_log_prob - two_trace) / 2.0)
+
+
+def collapsed_elbo_value_and_grad_autodiff(
+    kind, X, y, Z, lengthscale, variance, obs_stddev, mean_const=0.0, jitter=1e-6, threads=None
+):
+    """Reverse-mode gradient of the literal restatement of objectives.py:342-416.
+    Returns (value, grads) with grads for lengthscale, variance, obs_stddev, mean_const,
+    inducing_inputs."""
+    import torch
+
+    if threads:
+        torch.set_num_threads(threads)
+    kind = _kind_id(kind)
+    t = lambda a: torch.tensor(np.asarray(a, np.float64), dtype=torch.float64, requires_grad=True)
+    Xt = torch.tensor(np.asarray(X, np.float64))
+    yt = torch.tensor(np.asarray(y, np.float64).reshape(-1, 1))
+    ell, var, sn, c, Zt = t(lengthscale), t(variance), t(obs_stddev), t(mean_const), t(Z)
+    n, m = Xt.shape[0], Zt.shape[0]
+    noise = sn**2
+    eye = torch.eye(m, dtype=torch.float64)
+    Kzz = _t_cross(torch, kind, Zt, Zt, ell, var) + eye * jitter
+    Kzx = _t_cross(torch, kind, Zt, Xt, ell, var)
+    Kxx_diag = _t_profile(torch, kind, torch.zeros(n, dtype=torch.float64), var)
+    mux = torch.ones((n, 1), dtype=torch.float64) * c
+    Lz = torch.linalg.cholesky(Kzz)
+    A = torch.linalg.solve_triangular(Lz, Kzx, upper=False) / torch.sqrt(noise)
+    AAT = A @ A.T
+    L = torch.linalg.cholesky(eye + AAT)
+    log_det_B = 2.0 * torch.sum(torch.log(torch.diagonal(L)))
+    diff = yt - mux
+    L_inv_A_diff = torch.linalg.solve_triangular(L, A @ diff, upper=False)
+    quad = (torch.sum(diff**2) - torch.sum(L_inv_A_diff**2)) / noise
+    two_log_prob = -n * torch.log(2.0 * math.pi * noise) - log_det_B - quad
+    two_trace = torch.sum(Kxx_diag) / noise - torch.trace(AAT)
+    val = (two_log_prob - two_trace) / 2.0
+    val.backward()
+    g = {
+        "lengthscale": ell.grad.numpy().copy() if ell.grad.ndim else float(ell.grad),
+        "variance": float(var.grad),
+        "obs_stddev": float(sn.grad),
+        "mean_const": float(c.grad),
+        "inducing_inputs": Zt.grad.numpy().copy(),
+    }
+    return float(val.detach()), g
+
+
+def collapsed_elbo_grad_closed_form(
+    kind, X, y, Z, lengthscale, variance, obs_stddev, mean_const=0.0, jitter=1e-6, block=4096
+):
+    """Two-pass analytic gradient -- what the CUDA path implements.
+
+    Pass 1 accumulates Phi, psi, a1, dd, sd; the M x M finish yields adjoints
+    C = (2/s) Lz^-T dPhi Lz^-1, c = Lz^-T dpsi / sqrt(s), dKzz = Lz^-T (dPhi - Phi/2)... ;
+    pass 2 recomputes K_b = k(Z, X_b) and contracts dK_b = C K_b + c d_b^T with dK/dtheta.
+    """
+    kind = _kind_id(kind)
+    X = np.asarray(X, np.float64)
+    y = np.asarray(y, np.float64).reshape(-1)
+    Z = np.asarray(Z, np.float64)
+    n, D = X.shape
+    m = Z.shape[0]
+    ell = np.asarray(lengthscale, np.float64)
+    iso = ell.ndim == 0
+    ell_v = np.full(D, float(ell)) if iso else ell
+    s = obs_stddev**2
+    val, st = collapsed_elbo_streamed(
+        kind, X, y, Z, ell_v, variance, obs_stddev, mean_const, jitter, block, return_stats=True
+    )
+    Phi, psi, a1, dd, sd, Lz = st["Phi"], st["psi"], st["a1"], st["dd"], st["sd"], st["Lz"]
+    Bm = np.eye(m) + Phi
+    Binv = np.linalg.inv(Bm)
+    v = Binv @ psi
+    dPhi = 0.5 * (np.eye(m) - Binv - np.outer(v, v) / s)
+    dpsi = v / s
+    Lzinv = sla.solve_triangular(Lz, np.eye(m), lower=True)
+    C = (2.0 / s) * Lzinv.T @ dPhi @ Lzinv
+    C = 0.5 * (C + C.T)
+    cvec = Lzinv.T @ dpsi / np.sqrt(s)
+    # dELBO/dKzz from the square-root-invariant form (Q = Kzz + P/s, P = Kzx Kxz, b = Kzx d):
+    #   logdet(I+Phi) = logdet Q - logdet Kzz,  psi^T B^-1 psi = b^T Q^-1 b / s,  tr Phi = tr(Kzz^-1 P)/s
+    #   => dELBO/dKzz = Lz^-T (dPhi - Phi/2) Lz^-1.
+    dKzz = Lzinv.T @ (dPhi - 0.5 * Phi) @ Lzinv
+    dKzz = 0.5 * (dKzz + dKzz.T)
+    # -- contract with dk/dtheta -------------------------------------------------------
+    g_ell = np.zeros(D)
+    g_Z = np.zeros((m, D))
+    g_var = 0.0
+    zs = Z / ell_v
+
+    def contract(dK, Xr, Kmat, r2, z_is_both):
+        nonlocal g_ell, g_Z, g_var
+        Gm = dK * _dK_dr2(kind, r2, Kmat, variance)
+        g_var += np.sum(dK * Kmat) / variance
+        for k in range(D):
+            diff = Z[:, k : k + 1] - Xr[:, k][None, :]
+            g_ell[k] += np.sum(Gm * (-2.0 * diff * diff / ell_v[k] ** 3))
+            gz = 2.0 * Gm * diff / ell_v[k] ** 2
+            g_Z[:, k] += gz.sum(axis=1)
+            if z_is_both:
+                g_Z[:, k] -= gz.sum(axis=0)
+
+    for s0 in range(0, n, block):
+        Xb = X[s0 : s0 + block]
+        db = y[s0 : s0 + block] - mean_const
+        r2 = _r2_matrix(zs, Xb / ell_v)
+        Kb = _profile(kind, r2, variance)
+        dKb = C @ Kb + np.outer(cvec, db)
+        contract(dKb, Xb, Kb, r2, False)
+    r2zz = _r2_matrix(zs, zs)
+    Kzz0 = _profile(kind, r2zz, variance)
+    contract(dKzz, Z, Kzz0, r2zz, True)
+    g_var += -n / (2.0 * s)
+    quad_s = dd - psi @ v
+    g_s = (
+        -n / (2.0 * s)
+        + quad_s / (2.0 * s * s)
+        + n * variance / (2.0 * s * s)
+        - (2.0 * np.sum(dPhi * Phi) + dpsi @ psi) / (2.0 * s)
+    )
+    g_c = -(dpsi @ a1) * 1.0 + sd / s
+    # a1 = sum_rows A = Lz^-1 Kzx 1 / sqrt(s); psi = A d  => dpsi/dc = -a1
+    return val, {
+        "lengthscale": float(g_ell.sum()) if iso else g_ell,
+        "variance": float(g_var),
+        "obs_stddev": float(2.0 * obs_stddev * g_s),
+        "mean_const": float(g_c),
+        "inducing_inputs": g_Z,
+    }
+
+
+# ----------------------------------------------------------------------------------------
+# a15: ConjugatePosterior.predict -- gpjax/gps.py:495-526
+# ----------------------------------------------------------------------------------------
+def conjugate_predict(
+    kind, X, y, T, lengthscale, variance, obs_stddev, mean_const=0.0, jitter=1e-6,
+    prior_jitter=1e-6,
+):
+    """Returns (mean[T], cov[T,T]) of the latent function, gps.py:495-526."""
+    kind = _kind_id(kind)
+    X = np.asarray(X, np.float64)
+    y = np.asarray(y, np.float64).reshape(-1)
+    T = np.asarray(T, np.float64)
+    n = X.shape[0]
+    Sigma = gram(kind, X, lengthscale, variance) + np.eye(n) * jitter  # :505-506
+    Sigma = Sigma + np.eye(n) * obs_stddev**2  # :507-509
+    L = np.linalg.cholesky(Sigma)  # :511
+    Ktt = gram(kind, T, lengthscale, variance)  # :514
+    Kxt = cross_covariance(kind, X, T, lengthscale, variance)  # :515
+    V = sla.solve_triangular(L, Kxt, lower=True)  # :517
+    w = sla.solve_triangular(L, y - mean_const, lower=True)  # :518
+    mean = mean_const + V.T @ w  # :520
+    cov = Ktt - V.T @ V + np.eye(T.shape[0]) * prior_jitter  # :522-523
+    return mean, cov
+
+
+# ----------------------------------------------------------------------------------------
+# 80-bit adjudicators (small N only)
+# ----------------------------------------------------------------------------------------
+def gram_longdouble(kind, x, z, lengthscale, variance) -> np.ndarray:
+    kind = _kind_id(kind)
+    ld = np.longdouble
+    x = np.atleast_2d(np.asarray(x, np.float64)).astype(ld)
+    z = np.atleast_2d(np.asarray(z, np.float64)).astype(ld)
+    ell = np.asarray(lengthscale, np.float64).astype(ld)
+    xs, zs = x / ell, z / ell
+    r2 = np.zeros((x.shape[0], z.shape[0]), ld)
+    for k in range(x.shape[1]):
+        diff = xs[:, k : k + 1] - zs[:, k][None, :]
+        r2 += diff * diff
+    var = ld(variance)
+    if kind == 0:
+        return var * np.exp(ld(-0.5) * r2)
+    tau = np.sqrt(np.maximum(r2, ld(1e-36)))
+    if kind == 1:
+        s3 = np.sqrt(ld(3.0))
+        return var * (1 + s3 * tau) * np.exp(-s3 * tau)
+    s5 = np.sqrt(ld(5.0))
+    return var * (1 + s5 * tau + ld(5.0) / ld(3.0) * tau * tau) * np.exp(-s5 * tau)
+
+
+def conjugate_mll_longdouble(kind, X, y, lengthscale, variance, obs_stddev, mean_const=0.0, jitter=1e-6):
+    """Unblocked 80-bit Cholesky MLL (N <= ~400) to adjudicate LU-vs-Cholesky disagreements."""
+    ld = np.longdouble
+    X = np.asarray(X, np.float64)
+    n = X.shape[0]
+    S = gram_longdouble(kind, X, X, lengthscale, variance)
+    S = S + np.eye(n, dtype=ld) * ld(jitter)
+    S = S + np.eye(n, dtype=ld) * (ld(obs_stddev) ** 2)
+    d = np.asarray(y, np.float64).reshape(-1).astype(ld) - ld(mean_const)
+    L = np.zeros_like(S)
+    for j in range(n):
+        v = S[j:, j] - L[j:, :j] @ L[j, :j]
+        L[j, j] = np.sqrt(v[0])
+        L[j + 1 :, j] = v[1:] / L[j, j]
+    w = np.zeros(n, ld)
+    for i in range(n):
+        w[i] = (d[i] - L[i, :i] @ w[:i]) / L[i, i]
+    val = ld(-0.5) * (n * np.log(2 * ld(np.pi)) + 2 * np.sum(np.log(np.diag(L))) + w @ w)
+    return val
