@@ -1,0 +1,160 @@
+// extern "C" boundary (see include/gpjax_b200.h for the contract and the reference citations).
+#include "../../include/gpjax_b200.h"
+#include "algorithms.h"
+
+using namespace gpb;
+
+namespace {
+inline int carve(void* ws, int64_t bytes, int64_t n, int d, int potri, FactorWs* out) {
+    return factor_ws_carve(ws, bytes, n, d, potri, out);
+}
+}  // namespace
+
+extern "C" {
+
+const char* gpb_version(void) { return "gpjax_b200 0.1.0 (sm_100a, fp64 DMMA)"; }
+int gpb_max_input_dim(void) { return max_input_dim(); }
+int64_t gpb_block_size(void) { return NB; }
+
+int gpb_gram(void* stream, int kind, int64_t N, int64_t M, int D, const double* X, int64_t ldx, const double* Z,
+             int64_t ldz, const double* lengthscale, int lengthscale_is_scalar, const double* variance,
+             double diag_add, const double* diag_add_sq, int lower_only, double* K, int64_t ldk) {
+    GramDesc g;
+    g.kind = kind; g.N = N; g.M = M; g.D = D;
+    g.X = X; g.ldx = ldx; g.Z = Z; g.ldz = ldz;
+    g.ell = lengthscale; g.ell_is_scalar = lengthscale_is_scalar; g.variance = variance;
+    g.K = K; g.ldk = ldk; g.lower_only = lower_only;
+    g.diag_add = diag_add; g.diag_add_sq = diag_add_sq;
+    return gram(stream, g);
+}
+
+int64_t gpb_gram_bwd_workspace_bytes(int64_t N, int64_t M, int D) {
+    if (N < 0 || M < 0 || D <= 0) return 0;
+    return gram_bwd_partials_count(N, M, D) * (int64_t)sizeof(double);
+}
+
+int gpb_gram_bwd(void* stream, int kind, int64_t N, int64_t M, int D, const double* X, int64_t ldx,
+                 const double* Z, int64_t ldz, const double* lengthscale, int lengthscale_is_scalar,
+                 const double* variance, const double* dK, int64_t lddk, double scale, void* ws, int64_t ws_bytes,
+                 double* g_lengthscale, double* g_variance, double* g_X, int64_t ldgx, double* g_Z, int64_t ldgz) {
+    if (ws_bytes < gpb_gram_bwd_workspace_bytes(N, M, D)) return GPB_ERR_WORKSPACE;
+    GramBwdDesc d;
+    d.kind = kind; d.N = N; d.M = M; d.D = D;
+    d.X = X; d.ldx = ldx; d.Z = Z; d.ldz = ldz;
+    d.ell = lengthscale; d.ell_is_scalar = lengthscale_is_scalar; d.variance = variance;
+    d.dK = dK; d.lddk = lddk; d.scale = scale; d.partials = static_cast<double*>(ws);
+    d.g_ell = g_lengthscale; d.g_var = g_variance; d.g_X = g_X; d.ldgx = ldgx; d.g_Z = g_Z; d.ldgz = ldgz;
+    return gram_bwd(stream, d);
+}
+
+int64_t gpb_factor_workspace_bytes(int64_t ws_n, int ws_d, int ws_potri) {
+    return factor_ws_bytes(ws_n, ws_d, ws_potri);
+}
+
+int gpb_potrf_lower(void* stream, int64_t N, double* A, int64_t lda, int zero_upper, void* ws, int64_t ws_bytes,
+                    int64_t ws_n, int ws_d, int ws_potri, int* info) {
+    if (N > ws_n) return GPB_ERR_WORKSPACE;
+    FactorWs w;
+    int rc = carve(ws, ws_bytes, ws_n, ws_d, ws_potri, &w);
+    if (rc) return rc;
+    rc = potrf_lower(stream, N, A, lda, w, info);
+    if (rc) return rc;
+    if (zero_upper) return zero_triangle(stream, N, A, lda, 2);
+    return GPB_OK;
+}
+
+int gpb_diag_inverses(void* stream, int64_t N, const double* L, int64_t lda, void* ws, int64_t ws_bytes,
+                      int64_t ws_n, int ws_d, int ws_potri) {
+    if (N > ws_n) return GPB_ERR_WORKSPACE;
+    FactorWs w;
+    int rc = carve(ws, ws_bytes, ws_n, ws_d, ws_potri, &w);
+    if (rc) return rc;
+    return diag_inverses(stream, N, L, lda, w);
+}
+
+int gpb_trsv_lower(void* stream, int64_t N, const double* L, int64_t lda, int trans, double* x, void* ws,
+                   int64_t ws_bytes, int64_t ws_n, int ws_d, int ws_potri) {
+    if (N > ws_n) return GPB_ERR_WORKSPACE;
+    FactorWs w;
+    int rc = carve(ws, ws_bytes, ws_n, ws_d, ws_potri, &w);
+    if (rc) return rc;
+    return trsv_lower(stream, N, L, lda, w, x, trans);
+}
+
+int gpb_trsm_lower_left(void* stream, int64_t N, int64_t T, const double* L, int64_t lda, int trans, double* B,
+                        int64_t ldb, void* ws, int64_t ws_bytes, int64_t ws_n, int ws_d, int ws_potri) {
+    if (N > ws_n || T > ws_n) return GPB_ERR_WORKSPACE;
+    FactorWs w;
+    int rc = carve(ws, ws_bytes, ws_n, ws_d, ws_potri, &w);
+    if (rc) return rc;
+    return trsm_lower_left(stream, N, T, L, lda, w, B, ldb, trans);
+}
+
+int gpb_sum_log_diag(void* stream, int64_t N, const double* L, int64_t lda, double* out) {
+    if (N < 0 || !out || (N > 0 && !L)) return GPB_ERR_INVALID;
+    return sum_log_diag(stream, N, L, lda, out);
+}
+
+int gpb_potri_lower(void* stream, int64_t N, double* A, int64_t lda, double* out, int64_t ldo, void* ws,
+                    int64_t ws_bytes, int64_t ws_n, int ws_d, int ws_potri) {
+    if (N > ws_n || !ws_potri) return GPB_ERR_WORKSPACE;
+    FactorWs w;
+    int rc = carve(ws, ws_bytes, ws_n, ws_d, ws_potri, &w);
+    if (rc) return rc;
+    if ((rc = trtri_into_upper(stream, N, A, lda, w))) return rc;
+    if ((rc = lauum_upper(stream, N, A, lda, w))) return rc;
+    const int64_t nblk = nblocks(N);
+    for (int64_t k = 0; k < nblk; ++k) {
+        const int64_t j0 = k * NB;
+        const int64_t nbk = (N - j0) < NB ? (N - j0) : NB;
+        if ((rc = copy2d(stream, nbk, nbk, w.Sdiag + k * NB * NB, NB, out + j0 * ldo + j0, ldo))) return rc;
+        const int64_t right = N - j0 - nbk;
+        if (right > 0 && (rc = copy2d(stream, nbk, right, A + j0 * lda + j0 + nbk, lda, out + j0 * ldo + j0 + nbk, ldo)))
+            return rc;
+    }
+    return symmetrize(stream, N, out, ldo, 0);
+}
+
+int gpb_gemm(void* stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+             int a_layout, const double* B, int64_t ldb, int b_layout, double beta, double* C, int64_t ldc,
+             int mask) {
+    GemmDesc g;
+    g.M = M; g.N = N; g.K = K;
+    g.A = A; g.lda = lda; g.a_layout = a_layout;
+    g.B = B; g.ldb = ldb; g.b_layout = b_layout;
+    g.C = C; g.ldc = ldc; g.alpha = alpha; g.beta = beta; g.mask = mask;
+    return gemm(stream, g);
+}
+
+int64_t gpb_mll_workspace_bytes(int64_t N, int D) { return factor_ws_bytes(N, D, 1); }
+
+int gpb_mll_forward(void* stream, int kind, int64_t N, int D, const double* X, int64_t ldx, const double* y,
+                    const double* lengthscale, int lengthscale_is_scalar, const double* variance,
+                    const double* obs_stddev, const double* mean_const, double jitter, double* Sigma, int64_t lds,
+                    void* ws, int64_t ws_bytes, double* value_out, double* alpha_out, int* info) {
+    FactorWs w;
+    int rc = carve(ws, ws_bytes, N, D, 1, &w);
+    if (rc) return rc;
+    MllArgs a;
+    a.kind = kind; a.N = N; a.D = D; a.X = X; a.ldx = ldx; a.y = y;
+    a.ell = lengthscale; a.ell_is_scalar = lengthscale_is_scalar; a.variance = variance;
+    a.obs_stddev = obs_stddev; a.mean_const = mean_const; a.jitter = jitter; a.Sigma = Sigma; a.lds = lds;
+    return mll_forward(stream, a, w, value_out, alpha_out, info);
+}
+
+int gpb_mll_backward(void* stream, int kind, int64_t N, int D, const double* X, int64_t ldx,
+                     const double* lengthscale, int lengthscale_is_scalar, const double* variance,
+                     const double* obs_stddev, double* Sigma, int64_t lds, void* ws, int64_t ws_bytes,
+                     const double* alpha, const double* gout, double* g_lengthscale, double* g_variance,
+                     double* g_obs_stddev, double* g_mean_const) {
+    FactorWs w;
+    int rc = carve(ws, ws_bytes, N, D, 1, &w);
+    if (rc) return rc;
+    MllArgs a;
+    a.kind = kind; a.N = N; a.D = D; a.X = X; a.ldx = ldx;
+    a.ell = lengthscale; a.ell_is_scalar = lengthscale_is_scalar; a.variance = variance;
+    a.obs_stddev = obs_stddev; a.Sigma = Sigma; a.lds = lds;
+    return mll_backward(stream, a, w, alpha, gout, g_lengthscale, g_variance, g_obs_stddev, g_mean_const);
+}
+
+}  // extern "C"

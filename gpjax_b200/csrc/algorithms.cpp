@@ -1,0 +1,370 @@
+// Blocked right-looking algorithms (host orchestration only -- see algorithms.h).
+//
+// Storage convention for the exact-GP path (one N x N row-major buffer A, block size NB = 256):
+//   * lower triangle incl. the diagonal blocks : Sigma, then its Cholesky factor L (in place)
+//   * blocks strictly above the block diagonal : W = L^-T (trtri), then Sigma^-1 = W W^T (lauum)
+//   * ws.Dinv / ws.DinvT                       : inverses of the diagonal blocks of L (and transposes)
+//   * ws.Sdiag                                 : diagonal blocks of Sigma^-1
+// so a single N x N buffer carries forward AND backward (N = 100k -> 80 GB of the 180 GB HBM) and
+// L survives the backward pass.  Every O(N^3) step is a DMMA GEMM with K = NB:
+//   potrf : panel  X = P * inv(L_kk)^T,  trailing  A22 -= X X^T          (N^3/3)
+//   trtri : W[:,k] = -Acc * inv(L_kk)^T, Acc[:, k+1:] += W[:,k] L[k+1:,k]^T   (N^3/3)
+//   lauum : S[:k,:k] += W[:,k] W[:,k]^T, S[:,k] = W[:,k] inv(L_kk)       (N^3/3)
+// All operands are addressed "K-contiguous" (C = A * B^T with row-major A and B), which is what the
+// row-major lower/upper split gives for free.
+#include "algorithms.h"
+
+namespace gpb {
+
+#define GPB_TRY(expr)                 \
+    do {                              \
+        int rc__ = (expr);            \
+        if (rc__ != GPB_OK) return rc__; \
+    } while (0)
+
+// -------------------------------------------------------------------------------------------
+// workspace
+// -------------------------------------------------------------------------------------------
+namespace {
+struct WsLayout {
+    int64_t off_dinv, off_dinvt, off_sdiag, off_panel, off_small, off_vec, off_scal, off_part, total;
+    int64_t partials_count;
+};
+WsLayout ws_layout(int64_t N, int D, int with_potri) {
+    WsLayout L;
+    const int64_t blk = nblocks(N) * NB * NB;
+    int64_t o = 0;
+    auto take = [&](int64_t n) {
+        int64_t r = o;
+        o += align_up(n, 32);  // 256-byte granularity
+        return r;
+    };
+    L.off_dinv = take(blk);
+    L.off_dinvt = take(blk);
+    L.off_sdiag = take(with_potri ? blk : 0);
+    L.off_panel = take(align_up(N, NB) * NB);
+    L.off_small = take(4 * NB * NB);
+    L.off_vec = take(4 * align_up(N, NB));
+    L.off_scal = take(16);
+    L.partials_count = with_potri ? mll_bwd_partials_count(N, D > 0 ? D : 1, NB) : 0;
+    L.off_part = take(L.partials_count);
+    L.total = o;
+    return L;
+}
+}  // namespace
+
+int64_t factor_ws_bytes(int64_t N, int D, int with_potri) {
+    if (N < 0) return 0;
+    return ws_layout(N, D, with_potri).total * (int64_t)sizeof(double);
+}
+
+int factor_ws_carve(void* buf, int64_t bytes, int64_t N, int D, int with_potri, FactorWs* ws) {
+    if (!buf || !ws) return GPB_ERR_INVALID;
+    WsLayout L = ws_layout(N, D, with_potri);
+    if (bytes < L.total * (int64_t)sizeof(double)) return GPB_ERR_WORKSPACE;
+    double* b = static_cast<double*>(buf);
+    ws->Dinv = b + L.off_dinv;
+    ws->DinvT = b + L.off_dinvt;
+    ws->Sdiag = with_potri ? b + L.off_sdiag : nullptr;
+    ws->panel = b + L.off_panel;
+    ws->small = b + L.off_small;
+    ws->vec = b + L.off_vec;
+    ws->scal = b + L.off_scal;
+    ws->partials = with_potri ? b + L.off_part : nullptr;
+    ws->partials_count = L.partials_count;
+    return GPB_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// diagonal block: factor (optional) + explicit inverse, n <= NB, via two leaves and four small GEMMs
+// -------------------------------------------------------------------------------------------
+static int diag_block(stream_t s, int n, double* Ablk, int64_t lda, double* D, double* DT, double* small,
+                      int* info, int64_t row0, int factor) {
+    const int n1 = n < LEAFN ? n : (int)LEAFN;
+    const int n2 = n - n1;
+    GPB_TRY(potrf_leaf(s, n1, Ablk, lda, D, NB, DT, NB, info, row0, factor));
+    if (n2 <= 0) return GPB_OK;
+    double* t21 = small;                  // [n2 x n1], ld LEAFN : L21
+    double* tt = small + LEAFN * LEAFN;   // [n2 x n1], ld LEAFN : L21 * Dinv1
+    double* A21 = Ablk + (int64_t)n1 * lda;
+    double* A22 = A21 + n1;
+    GemmDesc g;
+    if (factor) {
+        // L21 = A21 * inv(L11)^T
+        g = GemmDesc();
+        g.M = n2; g.N = n1; g.K = n1;
+        g.A = A21; g.lda = lda; g.B = D; g.ldb = NB; g.C = t21; g.ldc = LEAFN;
+        g.krange = KR_B_LOWER;
+        GPB_TRY(gemm(s, g));
+        GPB_TRY(copy2d(s, n2, n1, t21, LEAFN, A21, lda));
+        // A22 -= L21 L21^T (lower)
+        g = GemmDesc();
+        g.M = n2; g.N = n2; g.K = n1;
+        g.A = t21; g.lda = LEAFN; g.B = t21; g.ldb = LEAFN; g.C = A22; g.ldc = lda;
+        g.alpha = -1.0; g.beta = 1.0; g.mask = MASK_LOWER;
+        GPB_TRY(gemm(s, g));
+    } else {
+        GPB_TRY(copy2d(s, n2, n1, A21, lda, t21, LEAFN));
+    }
+    double* D22 = D + (int64_t)n1 * NB + n1;
+    double* DT22 = DT + (int64_t)n1 * NB + n1;
+    GPB_TRY(potrf_leaf(s, n2, A22, lda, D22, NB, DT22, NB, info, row0 + n1, factor));
+    // tt = L21 * Dinv1          (B operand = DinvT1, upper triangular)
+    g = GemmDesc();
+    g.M = n2; g.N = n1; g.K = n1;
+    g.A = t21; g.lda = LEAFN; g.B = DT; g.ldb = NB; g.C = tt; g.ldc = LEAFN;
+    g.krange = KR_B_UPPER;
+    GPB_TRY(gemm(s, g));
+    // Dinv21 = -Dinv2 * tt      (B operand tt is N-contiguous)
+    g = GemmDesc();
+    g.M = n2; g.N = n1; g.K = n2;
+    g.A = D22; g.lda = NB; g.B = tt; g.ldb = LEAFN; g.b_layout = LAYOUT_MN;
+    g.C = D + (int64_t)n1 * NB; g.ldc = NB; g.alpha = -1.0;
+    g.krange = KR_A_LOWER;
+    GPB_TRY(gemm(s, g));
+    GPB_TRY(fill2d(s, n1, n2, D + n1, NB, 0.0));
+    GPB_TRY(transpose2d(s, n2, n1, D + (int64_t)n1 * NB, NB, DT + n1, NB));
+    GPB_TRY(fill2d(s, n2, n1, DT + (int64_t)n1 * NB, NB, 0.0));
+    return GPB_OK;
+}
+
+int potrf_lower(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& ws, int* info) {
+    if (N < 0 || (N > 0 && !A)) return GPB_ERR_INVALID;
+    const int64_t nblk = nblocks(N);
+    for (int64_t k = 0; k < nblk; ++k) {
+        const int64_t j0 = k * NB;
+        const int nbk = (int)((N - j0) < NB ? (N - j0) : NB);
+        double* Akk = A + j0 * lda + j0;
+        double* Dk = ws.Dinv + k * NB * NB;
+        double* DTk = ws.DinvT + k * NB * NB;
+        GPB_TRY(diag_block(s, nbk, Akk, lda, Dk, DTk, ws.small, info, j0, 1));
+        const int64_t rows = N - j0 - nbk;
+        if (rows <= 0) continue;
+        double* P = A + (j0 + nbk) * lda + j0;
+        // panel: X = P * inv(L_kk)^T -> contiguous copy, then back in place
+        GemmDesc g;
+        g.M = rows; g.N = nbk; g.K = nbk;
+        g.A = P; g.lda = lda; g.B = Dk; g.ldb = NB; g.C = ws.panel; g.ldc = NB;
+        g.krange = KR_B_LOWER;
+        GPB_TRY(gemm(s, g));
+        GPB_TRY(copy2d(s, rows, nbk, ws.panel, NB, P, lda));
+        // trailing update (lower triangle only): A22 -= X X^T
+        GemmDesc u;
+        u.M = rows; u.N = rows; u.K = nbk;
+        u.A = ws.panel; u.lda = NB; u.B = ws.panel; u.ldb = NB;
+        u.C = A + (j0 + nbk) * lda + (j0 + nbk); u.ldc = lda;
+        u.alpha = -1.0; u.beta = 1.0; u.mask = MASK_LOWER;
+        GPB_TRY(gemm(s, u));
+    }
+    return GPB_OK;
+}
+
+int diag_inverses(stream_t s, int64_t N, const double* L, int64_t lda, const FactorWs& ws) {
+    const int64_t nblk = nblocks(N);
+    for (int64_t k = 0; k < nblk; ++k) {
+        const int64_t j0 = k * NB;
+        const int nbk = (int)((N - j0) < NB ? (N - j0) : NB);
+        GPB_TRY(diag_block(s, nbk, const_cast<double*>(L) + j0 * lda + j0, lda, ws.Dinv + k * NB * NB,
+                           ws.DinvT + k * NB * NB, ws.small, nullptr, j0, 0));
+    }
+    return GPB_OK;
+}
+
+int trsv_lower(stream_t s, int64_t N, const double* L, int64_t lda, const FactorWs& ws, double* x, int trans) {
+    const int64_t nblk = nblocks(N);
+    double* t = ws.vec + 2 * align_up(N, NB);  // [NB] scratch
+    if (!trans) {
+        for (int64_t k = 0; k < nblk; ++k) {
+            const int64_t j0 = k * NB;
+            const int64_t nbk = (N - j0) < NB ? (N - j0) : NB;
+            GPB_TRY(gemv(s, nbk, nbk, ws.Dinv + k * NB * NB, NB, 0, x + j0, t, 1.0, 0.0));
+            const int64_t rows = N - j0 - nbk;
+            if (rows > 0) GPB_TRY(gemv(s, rows, nbk, L + (j0 + nbk) * lda + j0, lda, 0, t, x + j0 + nbk, -1.0, 1.0));
+            GPB_TRY(copy2d(s, 1, nbk, t, NB, x + j0, NB));
+        }
+    } else {
+        for (int64_t k = nblk - 1; k >= 0; --k) {
+            const int64_t j0 = k * NB;
+            const int64_t nbk = (N - j0) < NB ? (N - j0) : NB;
+            GPB_TRY(gemv(s, nbk, nbk, ws.DinvT + k * NB * NB, NB, 0, x + j0, t, 1.0, 0.0));
+            if (j0 > 0) GPB_TRY(gemv(s, nbk, j0, L + j0 * lda, lda, 1, t, x, -1.0, 1.0));
+            GPB_TRY(copy2d(s, 1, nbk, t, NB, x + j0, NB));
+        }
+    }
+    return GPB_OK;
+}
+
+int trsm_lower_left(stream_t s, int64_t N, int64_t T, const double* L, int64_t lda, const FactorWs& ws, double* B,
+                    int64_t ldb, int trans) {
+    if (N <= 0 || T <= 0) return GPB_OK;
+    const int64_t nblk = nblocks(N);
+    double* Xk = ws.panel;  // [NB x T], row stride T
+    if (!trans) {
+        for (int64_t k = 0; k < nblk; ++k) {
+            const int64_t j0 = k * NB;
+            const int64_t nbk = (N - j0) < NB ? (N - j0) : NB;
+            GemmDesc g;  // X_k = Dinv_k * B_k
+            g.M = nbk; g.N = T; g.K = nbk;
+            g.A = ws.Dinv + k * NB * NB; g.lda = NB;
+            g.B = B + j0 * ldb; g.ldb = ldb; g.b_layout = LAYOUT_MN;
+            g.C = Xk; g.ldc = T;
+            g.krange = KR_A_LOWER;
+            GPB_TRY(gemm(s, g));
+            GPB_TRY(copy2d(s, nbk, T, Xk, T, B + j0 * ldb, ldb));
+            const int64_t rows = N - j0 - nbk;
+            if (rows > 0) {
+                GemmDesc u;  // B[j0+nbk:, :] -= L[j0+nbk:, j0:j0+nbk] * X_k
+                u.M = rows; u.N = T; u.K = nbk;
+                u.A = L + (j0 + nbk) * lda + j0; u.lda = lda;
+                u.B = Xk; u.ldb = T; u.b_layout = LAYOUT_MN;
+                u.C = B + (j0 + nbk) * ldb; u.ldc = ldb; u.alpha = -1.0; u.beta = 1.0;
+                GPB_TRY(gemm(s, u));
+            }
+        }
+    } else {
+        for (int64_t k = nblk - 1; k >= 0; --k) {
+            const int64_t j0 = k * NB;
+            const int64_t nbk = (N - j0) < NB ? (N - j0) : NB;
+            GemmDesc g;  // X_k = Dinv_k^T * B_k
+            g.M = nbk; g.N = T; g.K = nbk;
+            g.A = ws.DinvT + k * NB * NB; g.lda = NB;
+            g.B = B + j0 * ldb; g.ldb = ldb; g.b_layout = LAYOUT_MN;
+            g.C = Xk; g.ldc = T;
+            g.krange = KR_A_UPPER;
+            GPB_TRY(gemm(s, g));
+            GPB_TRY(copy2d(s, nbk, T, Xk, T, B + j0 * ldb, ldb));
+            if (j0 > 0) {
+                GemmDesc u;  // B[0:j0, :] -= L[j0:j0+nbk, 0:j0]^T * X_k
+                u.M = j0; u.N = T; u.K = nbk;
+                u.A = L + j0 * lda; u.lda = lda; u.a_layout = LAYOUT_MN;
+                u.B = Xk; u.ldb = T; u.b_layout = LAYOUT_MN;
+                u.C = B; u.ldc = ldb; u.alpha = -1.0; u.beta = 1.0;
+                GPB_TRY(gemm(s, u));
+            }
+        }
+    }
+    return GPB_OK;
+}
+
+int trtri_into_upper(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& ws) {
+    const int64_t nblk = nblocks(N);
+    double* Wp = ws.panel;  // block column k of W, rows 0 .. j0+nbk, ld NB
+    for (int64_t k = 0; k < nblk; ++k) {
+        const int64_t j0 = k * NB;
+        const int64_t nbk = (N - j0) < NB ? (N - j0) : NB;
+        const double* Dk = ws.Dinv + k * NB * NB;
+        const double* DTk = ws.DinvT + k * NB * NB;
+        if (j0 > 0) {
+            // W[0:j0, k] = -Acc * inv(L_kk)^T
+            GemmDesc g;
+            g.M = j0; g.N = nbk; g.K = nbk;
+            g.A = A + j0; g.lda = lda; g.B = Dk; g.ldb = NB; g.C = Wp; g.ldc = NB;
+            g.alpha = -1.0; g.krange = KR_B_LOWER;
+            GPB_TRY(gemm(s, g));
+            GPB_TRY(copy2d(s, j0, nbk, Wp, NB, A + j0, lda));
+        }
+        const int64_t right = N - j0 - nbk;
+        if (right <= 0) continue;
+        GPB_TRY(copy2d(s, nbk, nbk, DTk, NB, Wp + j0 * NB, NB));  // W_kk = inv(L_kk)^T
+        const double* Lp = A + (j0 + nbk) * lda + j0;            // L[k+1:, k]
+        if (j0 > 0) {
+            GemmDesc u;  // Acc[0:j0, k+1:] += W[0:j0,k] * L[k+1:,k]^T
+            u.M = j0; u.N = right; u.K = nbk;
+            u.A = Wp; u.lda = NB; u.B = Lp; u.ldb = lda;
+            u.C = A + (j0 + nbk); u.ldc = lda; u.beta = 1.0;
+            GPB_TRY(gemm(s, u));
+        }
+        GemmDesc v;  // Acc[k, k+1:] = W_kk * L[k+1:,k]^T   (first write of that block row)
+        v.M = nbk; v.N = right; v.K = nbk;
+        v.A = Wp + j0 * NB; v.lda = NB; v.B = Lp; v.ldb = lda;
+        v.C = A + j0 * lda + (j0 + nbk); v.ldc = lda; v.beta = 0.0;
+        v.krange = KR_A_UPPER;
+        GPB_TRY(gemm(s, v));
+    }
+    return GPB_OK;
+}
+
+int lauum_upper(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& ws) {
+    const int64_t nblk = nblocks(N);
+    for (int64_t k = 0; k < nblk; ++k) {
+        const int64_t j0 = k * NB;
+        const int64_t nbk = (N - j0) < NB ? (N - j0) : NB;
+        const double* DTk = ws.DinvT + k * NB * NB;
+        double* P = A + j0;  // W[0:j0, k], row stride lda
+        if (j0 > 0) {
+            // S[0:j0, 0:j0] (strictly-upper blocks) += P P^T
+            GemmDesc g;
+            g.M = j0; g.N = j0; g.K = nbk;
+            g.A = P; g.lda = lda; g.B = P; g.ldb = lda; g.C = A; g.ldc = lda;
+            g.beta = 1.0; g.mask = MASK_BLOCK_STRICT_UPPER; g.mask_nb = NB;
+            GPB_TRY(gemm(s, g));
+            // diagonal blocks: Sdiag[j] += P_j P_j^T, j < k   (batched)
+            GemmDesc b;
+            b.M = NB; b.N = NB; b.K = nbk;
+            b.A = P; b.lda = lda; b.B = P; b.ldb = lda; b.C = ws.Sdiag; b.ldc = NB;
+            b.beta = 1.0; b.batch = (int)k; b.strideA = NB * lda; b.strideB = NB * lda; b.strideC = NB * NB;
+            GPB_TRY(gemm(s, b));
+            // S[0:j0, k] = W[0:j0,k] * inv(L_kk)          (B operand = DinvT_k, upper triangular)
+            GemmDesc c;
+            c.M = j0; c.N = nbk; c.K = nbk;
+            c.A = P; c.lda = lda; c.B = DTk; c.ldb = NB; c.C = ws.panel; c.ldc = NB;
+            c.krange = KR_B_UPPER;
+            GPB_TRY(gemm(s, c));
+            GPB_TRY(copy2d(s, j0, nbk, ws.panel, NB, P, lda));
+        }
+        // S_kk = inv(L_kk)^T inv(L_kk)
+        GemmDesc d;
+        d.M = nbk; d.N = nbk; d.K = nbk;
+        d.A = DTk; d.lda = NB; d.B = DTk; d.ldb = NB; d.C = ws.Sdiag + k * NB * NB; d.ldc = NB;
+        GPB_TRY(gemm(s, d));
+    }
+    return GPB_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// exact-GP objective
+// -------------------------------------------------------------------------------------------
+int mll_forward(stream_t s, const MllArgs& a, const FactorWs& ws, double* value_out, double* alpha_out, int* info) {
+    if (a.N <= 0 || a.D <= 0 || !a.X || !a.y || !a.ell || !a.variance || !a.obs_stddev || !a.Sigma || !value_out ||
+        !alpha_out || !info)
+        return GPB_ERR_INVALID;
+    const int64_t N = a.N;
+    double* dvec = ws.vec;                        // d = y - m
+    double* wvec = ws.vec + align_up(N, NB);      // w = L^-1 d
+    double* half_logdet = ws.scal;
+    double* quad = ws.scal + 1;
+    GPB_TRY(sub_scalar(s, N, a.y, a.mean_const, dvec));
+    GramDesc g;
+    g.kind = a.kind; g.N = N; g.M = N; g.D = a.D;
+    g.X = a.X; g.ldx = a.ldx; g.Z = a.X; g.ldz = a.ldx;
+    g.ell = a.ell; g.ell_is_scalar = a.ell_is_scalar; g.variance = a.variance;
+    g.K = a.Sigma; g.ldk = a.lds; g.lower_only = 1;
+    g.diag_add = a.jitter; g.diag_add_sq = a.obs_stddev;
+    GPB_TRY(gram(s, g));
+    GPB_TRY(potrf_lower(s, N, a.Sigma, a.lds, ws, info));
+    GPB_TRY(sum_log_diag(s, N, a.Sigma, a.lds, half_logdet));
+    GPB_TRY(copy2d(s, 1, N, dvec, N, wvec, N));
+    GPB_TRY(trsv_lower(s, N, a.Sigma, a.lds, ws, wvec, 0));
+    GPB_TRY(dot(s, N, wvec, wvec, quad));
+    GPB_TRY(copy2d(s, 1, N, wvec, N, alpha_out, N));
+    GPB_TRY(trsv_lower(s, N, a.Sigma, a.lds, ws, alpha_out, 1));
+    GPB_TRY(mll_value(s, N, half_logdet, quad, info, value_out));
+    return GPB_OK;
+}
+
+int mll_backward(stream_t s, const MllArgs& a, const FactorWs& ws, const double* alpha, const double* gout,
+                 double* g_ell, double* g_var, double* g_obs_stddev, double* g_mean) {
+    if (a.N <= 0 || !a.Sigma || !alpha || !ws.Sdiag || !ws.partials) return GPB_ERR_INVALID;
+    GPB_TRY(trtri_into_upper(s, a.N, a.Sigma, a.lds, ws));
+    GPB_TRY(lauum_upper(s, a.N, a.Sigma, a.lds, ws));
+    MllBwdDesc d;
+    d.kind = a.kind; d.N = a.N; d.D = a.D; d.nb = NB;
+    d.X = a.X; d.ldx = a.ldx; d.alpha = alpha;
+    d.S = a.Sigma; d.lds = a.lds; d.Sdiag = ws.Sdiag;
+    d.ell = a.ell; d.ell_is_scalar = a.ell_is_scalar; d.variance = a.variance; d.obs_stddev = a.obs_stddev;
+    d.gout = gout; d.partials = ws.partials;
+    d.g_ell = g_ell; d.g_var = g_var; d.g_obs_stddev = g_obs_stddev; d.g_mean = g_mean;
+    return mll_bwd(s, d);
+}
+
+}  // namespace gpb

@@ -1,0 +1,75 @@
+// Blocked algorithms of the hot path, written purely against primitives.h (device pointers are
+// opaque here: this file never dereferences them, so it runs unchanged on the CUDA primitives and
+// on the host model used by the CPU tests).
+#pragma once
+#include <cstdint>
+#include "primitives.h"
+
+namespace gpb {
+
+constexpr int64_t NB = 256;    // block size of every blocked algorithm
+constexpr int64_t LEAFN = 128; // leaf size handled by potrf_leaf
+
+inline int64_t nblocks(int64_t n) { return (n + NB - 1) / NB; }
+inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// ---- workspace for the exact-GP factorisation family --------------------------------------
+struct FactorWs {
+    double* Dinv = nullptr;   // nblk blocks [NB x NB], inverse of the diagonal blocks of L
+    double* DinvT = nullptr;  // their transposes
+    double* Sdiag = nullptr;  // nblk blocks [NB x NB], diagonal blocks of Sigma^-1 (potri only)
+    double* panel = nullptr;  // [N x NB] contiguous panel copy
+    double* small = nullptr;  // 4 x [NB x NB] scratch
+    double* vec = nullptr;    // 4 x [N] vectors (d, w, tmp, spare)
+    double* scal = nullptr;   // 16 scalars
+    double* partials = nullptr;
+    int64_t partials_count = 0;
+};
+// bytes needed for an N x N problem with D input dims (with_potri: include Sdiag + backward partials)
+int64_t factor_ws_bytes(int64_t N, int D, int with_potri);
+// carve `ws` out of a caller buffer; returns GPB_ERR_WORKSPACE if too small
+int factor_ws_carve(void* buf, int64_t bytes, int64_t N, int D, int with_potri, FactorWs* ws);
+
+// ---- factorisation building blocks ----------------------------------------------------------
+// In-place lower Cholesky of the lower triangle of A (strict upper never touched).  Fills
+// ws.Dinv / ws.DinvT.  *info (device) receives the first failing pivot (1-based) or stays 0.
+int potrf_lower(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& ws, int* info);
+// Only invert the diagonal blocks of an existing lower-triangular L into ws.Dinv / ws.DinvT.
+int diag_inverses(stream_t s, int64_t N, const double* L, int64_t lda, const FactorWs& ws);
+// x <- L^-1 x   /   x <- L^-T x   (vector, in place), using ws.Dinv(T) and ws.vec[2N..3N) as scratch
+int trsv_lower(stream_t s, int64_t N, const double* L, int64_t lda, const FactorWs& ws, double* x, int trans);
+// B <- L^-1 B  /  B <- L^-T B  for an N x T row-major block B (in place); scratch: ws.panel must hold
+// NB x T doubles (caller guarantees N*NB >= NB*T or provides a bigger panel)
+int trsm_lower_left(stream_t s, int64_t N, int64_t T, const double* L, int64_t lda, const FactorWs& ws, double* B,
+                    int64_t ldb, int trans);
+// W = L^-T written into the blocks strictly above the block diagonal of A (diagonal blocks of W are
+// ws.DinvT); L (lower, incl. diagonal blocks) is left intact.
+int trtri_into_upper(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& ws);
+// Sigma^-1 = W W^T: strictly-upper blocks overwrite W in A, diagonal blocks go to ws.Sdiag.
+int lauum_upper(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& ws);
+
+// ---- exact-GP objective (gpjax/objectives.py:93-107 + gpjax/distributions.py:124-134) --------
+struct MllArgs {
+    int kind = 0;
+    int64_t N = 0;
+    int D = 0;
+    const double* X = nullptr;
+    int64_t ldx = 0;
+    const double* y = nullptr;           // [N]
+    const double* ell = nullptr;         // device [D] or [1]
+    int ell_is_scalar = 0;
+    const double* variance = nullptr;    // device scalar
+    const double* obs_stddev = nullptr;  // device scalar
+    const double* mean_const = nullptr;  // device scalar or null (Zero mean)
+    double jitter = 1e-6;
+    double* Sigma = nullptr;  // N x N scratch/result buffer (lower: L; upper blocks: Sigma^-1 after bwd)
+    int64_t lds = 0;
+};
+// value_out[0] = log N(y | m, K + (jitter + obs_stddev^2) I); alpha_out[N] = Sigma^-1 (y - m)
+int mll_forward(stream_t s, const MllArgs& a, const FactorWs& ws, double* value_out, double* alpha_out, int* info);
+// gradients w.r.t. (lengthscale, variance, obs_stddev, mean_const), scaled by *gout (null -> 1).
+// Needs the Sigma buffer + ws exactly as mll_forward left them.
+int mll_backward(stream_t s, const MllArgs& a, const FactorWs& ws, const double* alpha, const double* gout,
+                 double* g_ell, double* g_var, double* g_obs_stddev, double* g_mean);
+
+}  // namespace gpb

@@ -1,0 +1,101 @@
+// Shared device helpers for the sm_100a kernels (float64 everywhere).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "primitives.h"
+
+namespace gpb {
+
+#define GPB_LAUNCH_CHECK()                                   \
+    do {                                                     \
+        cudaError_t e__ = cudaGetLastError();                \
+        if (e__ != cudaSuccess) return GPB_ERR_LAUNCH;       \
+    } while (0)
+
+static inline cudaStream_t to_stream(stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- cp.async (LDGSTS) with zero-fill -------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+    unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// ---- FP64 tensor-core MMA: D(8x8) += A(8x4) * B(4x8)  (SASS: DMMA.8x8x4) -------------------
+// fragment ownership: a = A[lane>>2][lane&3], b = B[lane&3][lane>>2],
+//                     c0/c1 = C[lane>>2][2*(lane&3) + {0,1}]
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+// ---- stationary kernel profiles (reference: gpjax/kernels/stationary/{rbf,matern32,matern52}.py) ----
+// value and d/d(r2) of g(r2) with variance folded in.  The 1e-36 clamp of
+// euclidean_distance (stationary/utils.py:67) makes the derivative vanish where r2 <= 1e-36.
+template <int KIND>
+__device__ __forceinline__ double kprofile(double r2, double var) {
+    if (KIND == KIND_RBF) {
+        return var * exp(-0.5 * r2);
+    } else if (KIND == KIND_MATERN32) {
+        const double s3 = 1.7320508075688772;
+        double tau = sqrt(fmax(r2, 1e-36));
+        return var * (1.0 + s3 * tau) * exp(-s3 * tau);
+    } else {
+        const double s5 = 2.23606797749979;
+        double tau = sqrt(fmax(r2, 1e-36));
+        return var * (1.0 + s5 * tau + (5.0 / 3.0) * (tau * tau)) * exp(-s5 * tau);
+    }
+}
+
+template <int KIND>
+__device__ __forceinline__ void kprofile_grad(double r2, double var, double& k, double& dk_dr2) {
+    if (KIND == KIND_RBF) {
+        k = var * exp(-0.5 * r2);
+        dk_dr2 = -0.5 * k;
+    } else if (KIND == KIND_MATERN32) {
+        const double s3 = 1.7320508075688772;
+        double tau = sqrt(fmax(r2, 1e-36));
+        double e = exp(-s3 * tau);
+        k = var * (1.0 + s3 * tau) * e;
+        dk_dr2 = (r2 > 1e-36) ? (-1.5 * var * e) : 0.0;
+    } else {
+        const double s5 = 2.23606797749979;
+        double tau = sqrt(fmax(r2, 1e-36));
+        double e = exp(-s5 * tau);
+        k = var * (1.0 + s5 * tau + (5.0 / 3.0) * (tau * tau)) * e;
+        dk_dr2 = (r2 > 1e-36) ? (-(5.0 / 6.0) * var * (1.0 + s5 * tau) * e) : 0.0;
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum; result valid in thread 0.  `red` needs >= 32 doubles of shared memory.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    int nw = (blockDim.x + 31) >> 5;
+    double r = 0.0;
+    if (w == 0) {
+        r = (lane < nw) ? red[lane] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+}  // namespace gpb

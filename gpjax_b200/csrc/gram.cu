@@ -1,0 +1,580 @@
+// Fused stationary-kernel Gram / cross-covariance tiles and their streamed backward contractions.
+//
+// Forward (replaces gpjax/kernels/computations/dense.py:32-36 o stationary/{rbf,matern32,matern52}.py
+// o stationary/utils.py:53,67, with add_jitter (linalg/utils.py:65) and "+ eye*obs_noise"
+// (objectives.py:101-102) folded into the epilogue so the matrix is written to HBM exactly once):
+//   K[i,j] = var * g( sum_d (x_id/l_d - z_jd/l_d)^2 )  (+ jitter + obs_stddev^2 where i == j)
+// The squared distance uses the reference's direct-difference form on inputs pre-divided by the
+// lengthscale (true division, as rbf.py:41-42) -- NOT the |a|^2+|b|^2-2ab expansion: with K-dim = D
+// the cross term is 2 DMMA k-steps while the expansion costs ~2x the rounding error near the
+// 1e-12 budget (hard part 3); on B200 the FP64 vector and tensor peaks are equal.
+//
+// Backward: <dK, dK/dtheta> contracted tile by tile with K and dK/dr2 recomputed from X -- dK/dtheta
+// is never materialised.  Two front-ends share the tile core:
+//   * gram_bwd : dK read from memory (cotangent of a Gram/cross-covariance; SGPR pass 2),
+//   * mll_bwd  : dK = W = 1/2 (alpha alpha^T - Sigma^-1) formed on the fly from alpha and the
+//                block-upper Sigma^-1 storage produced by potri (exact-GP gradient).
+#include "common.cuh"
+
+namespace gpb {
+
+namespace {
+
+constexpr int TR = 64;    // tile rows
+constexpr int TC = 128;   // tile cols
+constexpr int GT = 256;   // threads per CTA
+constexpr int RPT = 16;   // rows per thread (TR / 4)
+constexpr int MAX_D = 64;
+
+__host__ __device__ inline int pad_dim(int D, int DC) { return ((D + DC - 1) / DC) * DC; }
+
+// Load a tile of inputs divided by the lengthscale into shared memory, zero padded.
+//  ROWMAJOR: dst[r*Dp + d]   else dst[d*rows + r]
+template <bool ROWMAJOR>
+__device__ __forceinline__ void load_scaled(double* dst, const double* __restrict__ P, int64_t ld,
+                                            int64_t r0, int64_t nrows, int rows, int D, int Dp,
+                                            const double* __restrict__ ell, int ell_is_scalar) {
+    // ids run d-fastest so the global reads of one row are contiguous
+    for (int id = threadIdx.x; id < rows * Dp; id += blockDim.x) {
+        int r = id / Dp, d = id % Dp;
+        double v = 0.0;
+        int64_t gr = r0 + r;
+        if (gr < nrows && d < D) v = P[gr * ld + d] / ell[ell_is_scalar ? 0 : d];
+        dst[ROWMAJOR ? (r * Dp + d) : (d * rows + r)] = v;
+    }
+}
+
+// r2 for the thread's RPT x 2 outputs
+template <int DC>
+__device__ __forceinline__ void tile_r2(const double* __restrict__ Xs, const double* __restrict__ Zs, int Dp,
+                                        int tx, int ty, double (&r2)[RPT][2]) {
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) r2[i][0] = r2[i][1] = 0.0;
+    for (int d0 = 0; d0 < Dp; d0 += DC) {
+        double z0[DC], z1[DC];
+#pragma unroll
+        for (int d = 0; d < DC; ++d) {
+            double2 zz = *reinterpret_cast<const double2*>(Zs + (d0 + d) * TC + 2 * tx);
+            z0[d] = zz.x;
+            z1[d] = zz.y;
+        }
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            const double* xr = Xs + (ty + 4 * i) * Dp + d0;
+#pragma unroll
+            for (int d = 0; d < DC; ++d) {
+                double x = xr[d];
+                double a = x - z0[d], b = x - z1[d];
+                r2[i][0] = fma(a, a, r2[i][0]);
+                r2[i][1] = fma(b, b, r2[i][1]);
+            }
+        }
+    }
+}
+
+struct GramParams {
+    int64_t N, M;
+    int D;
+    const double* X; int64_t ldx;
+    const double* Z; int64_t ldz;
+    const double* ell; int ell_is_scalar;
+    const double* variance;
+    double* K; int64_t ldk;
+    int lower_only;
+    double diag_add;
+    const double* diag_add_sq;
+    int64_t row0, col0;
+    int64_t tiles_c;
+    int k_vec16;
+};
+
+template <int KIND, int DC>
+__global__ void __launch_bounds__(GT, 2) gram_kernel(const GramParams p) {
+    extern __shared__ __align__(16) double sm[];
+    const int Dp = pad_dim(p.D, DC);
+    double* Xs = sm;             // [TR][Dp]
+    double* Zs = sm + TR * Dp;   // [Dp][TC]
+    const int64_t tr = blockIdx.x / p.tiles_c, tc = blockIdx.x % p.tiles_c;
+    const int64_t r0 = tr * TR, c0 = tc * TC;
+    if (p.lower_only && (p.row0 + min(r0 + TR, p.N) - 1 < p.col0 + c0)) return;
+    load_scaled<true>(Xs, p.X, p.ldx, r0, p.N, TR, p.D, Dp, p.ell, p.ell_is_scalar);
+    load_scaled<false>(Zs, p.Z, p.ldz, c0, p.M, TC, p.D, Dp, p.ell, p.ell_is_scalar);
+    __syncthreads();
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    double r2[RPT][2];
+    tile_r2<DC>(Xs, Zs, Dp, tx, ty, r2);
+    const double var = *p.variance;
+    double dadd = p.diag_add;
+    if (p.diag_add_sq) { double t = *p.diag_add_sq; dadd += t * t; }
+    const int64_t c = c0 + 2 * tx;
+    if (c >= p.M) return;
+    const bool c1ok = (c + 1 < p.M);
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        int64_t r = r0 + ty + 4 * i;
+        if (r >= p.N) continue;
+        double k0 = kprofile<KIND>(r2[i][0], var);
+        double k1 = kprofile<KIND>(r2[i][1], var);
+        if (p.row0 + r == p.col0 + c) k0 += dadd;
+        if (p.row0 + r == p.col0 + c + 1) k1 += dadd;
+        double* out = p.K + r * p.ldk + c;
+        if (c1ok && p.k_vec16) {
+            *reinterpret_cast<double2*>(out) = make_double2(k0, k1);
+        } else {
+            out[0] = k0;
+            if (c1ok) out[1] = k1;
+        }
+    }
+}
+
+template <int KIND>
+int launch_gram(cudaStream_t st, const GramParams& p, int64_t ntiles) {
+    int DC = p.D <= 2 ? 2 : (p.D <= 4 ? 4 : 8);
+    int Dp = pad_dim(p.D, DC);
+    size_t smem = sizeof(double) * (size_t)(TR + TC) * Dp;
+    dim3 grid((unsigned)ntiles);
+#define GPB_GRAM_LAUNCH(DCV)                                                                         \
+    {                                                                                                \
+        auto kern = gram_kernel<KIND, DCV>;                                                          \
+        if (smem > 48 * 1024)                                                                        \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        kern<<<grid, GT, smem, st>>>(p);                                                             \
+    }
+    if (DC == 2) GPB_GRAM_LAUNCH(2)
+    else if (DC == 4) GPB_GRAM_LAUNCH(4)
+    else GPB_GRAM_LAUNCH(8)
+#undef GPB_GRAM_LAUNCH
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// backward tile core
+// ------------------------------------------------------------------------------------------
+// After r2 is known the thread turns each of its RPT x 2 outputs into
+//   G = w * dK/dr2   (w = cotangent of K at that element, symmetric weights already applied)
+// and accumulates   sum w*K  (for d/dvariance)  and, per input dimension,
+//   sum G * (xs_d - zs_d)^2   (for d/dl_d = -2/l_d * that)
+// plus, optionally, per-row / per-column   sum G * (xs_d - zs_d)   (for dX, dZ).
+template <int DC, bool WANT_X, bool WANT_Z>
+__device__ __forceinline__ void contract_dims(const double* __restrict__ Xs, const double* __restrict__ Zs,
+                                              int Dp, int tx, int ty, const double (&G)[RPT][2],
+                                              double* __restrict__ ell_acc /*[Dp] smem, atomically added*/,
+                                              double* __restrict__ gx_s /*[TR][Dp] smem*/,
+                                              double* __restrict__ gz_s /*[Dp][TC] smem*/) {
+    for (int d0 = 0; d0 < Dp; d0 += DC) {
+        double z0[DC], z1[DC], acc[DC], gz0[DC], gz1[DC];
+#pragma unroll
+        for (int d = 0; d < DC; ++d) {
+            double2 zz = *reinterpret_cast<const double2*>(Zs + (d0 + d) * TC + 2 * tx);
+            z0[d] = zz.x;
+            z1[d] = zz.y;
+            acc[d] = 0.0;
+            gz0[d] = gz1[d] = 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            const double* xr = Xs + (ty + 4 * i) * Dp + d0;
+            const double g0 = G[i][0], g1 = G[i][1];
+#pragma unroll
+            for (int d = 0; d < DC; ++d) {
+                double x = xr[d];
+                double a = x - z0[d], b = x - z1[d];
+                acc[d] = fma(g0 * a, a, acc[d]);
+                acc[d] = fma(g1 * b, b, acc[d]);
+                if (WANT_Z) {
+                    gz0[d] = fma(g0, a, gz0[d]);
+                    gz1[d] = fma(g1, b, gz1[d]);
+                }
+                if (WANT_X) {
+                    // row gradient: reduce over the 64 column-threads of this row group
+                    double gx = fma(g0, a, g1 * b);
+                    gx = warp_sum(gx);
+                    if ((threadIdx.x & 31) == 0) atomicAdd(gx_s + (ty + 4 * i) * Dp + d0 + d, gx);
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < DC; ++d) {
+            double v = warp_sum(acc[d]);
+            if ((threadIdx.x & 31) == 0) atomicAdd(ell_acc + d0 + d, v);
+            if (WANT_Z) {
+                atomicAdd(gz_s + (d0 + d) * TC + 2 * tx, gz0[d]);
+                atomicAdd(gz_s + (d0 + d) * TC + 2 * tx + 1, gz1[d]);
+            }
+        }
+    }
+}
+
+struct GramBwdParams {
+    int64_t N, M;
+    int D;
+    const double* X; int64_t ldx;
+    const double* Z; int64_t ldz;
+    const double* ell; int ell_is_scalar;
+    const double* variance;
+    const double* dK; int64_t lddk;
+    double scale;
+    double* partials;  // [ntiles][Dp + 1]
+    double* g_X; int64_t ldgx;
+    double* g_Z; int64_t ldgz;
+    int64_t tiles_c;
+};
+
+template <int KIND, int DC, bool WANT_X, bool WANT_Z>
+__global__ void __launch_bounds__(GT, (WANT_X || WANT_Z) ? 1 : 2) gram_bwd_kernel(const GramBwdParams p) {
+    extern __shared__ __align__(16) double sm[];
+    const int Dp = pad_dim(p.D, DC);
+    double* Xs = sm;                     // [TR][Dp]
+    double* Zs = Xs + TR * Dp;           // [Dp][TC]
+    double* ell_acc = Zs + Dp * TC;      // [Dp]
+    double* red = ell_acc + Dp;          // [32]
+    double* gx_s = red + 32;             // [TR][Dp]   (WANT_X)
+    double* gz_s = gx_s + (WANT_X ? TR * Dp : 0);  // [Dp][TC]   (WANT_Z)
+    const int64_t tr = blockIdx.x / p.tiles_c, tc = blockIdx.x % p.tiles_c;
+    const int64_t r0 = tr * TR, c0 = tc * TC;
+    load_scaled<true>(Xs, p.X, p.ldx, r0, p.N, TR, p.D, Dp, p.ell, p.ell_is_scalar);
+    load_scaled<false>(Zs, p.Z, p.ldz, c0, p.M, TC, p.D, Dp, p.ell, p.ell_is_scalar);
+    for (int i = threadIdx.x; i < Dp; i += GT) ell_acc[i] = 0.0;
+    if (WANT_X)
+        for (int i = threadIdx.x; i < TR * Dp; i += GT) gx_s[i] = 0.0;
+    if (WANT_Z)
+        for (int i = threadIdx.x; i < Dp * TC; i += GT) gz_s[i] = 0.0;
+    __syncthreads();
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    double r2[RPT][2];
+    tile_r2<DC>(Xs, Zs, Dp, tx, ty, r2);
+    const double var = *p.variance;
+    const int64_t c = c0 + 2 * tx;
+    double wk = 0.0;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        int64_t r = r0 + ty + 4 * i;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            double w = 0.0;
+            if (r < p.N && c + j < p.M) w = p.dK[r * p.lddk + c + j];
+            double k, dk;
+            kprofile_grad<KIND>(r2[i][j], var, k, dk);
+            wk = fma(w, k, wk);
+            r2[i][j] = w * dk;  // becomes G
+        }
+    }
+    contract_dims<DC, WANT_X, WANT_Z>(Xs, Zs, Dp, tx, ty, r2, ell_acc, gx_s, gz_s);
+    double s = block_sum(wk, red);  // contains __syncthreads -> smem atomics above are complete
+    double* out = p.partials + (int64_t)blockIdx.x * (Dp + 1);
+    if (threadIdx.x == 0) out[Dp] = s;
+    for (int i = threadIdx.x; i < Dp; i += GT) out[i] = ell_acc[i];
+    {
+        // dr2/dx_d = 2 (xs_d - zs_d) / l_d ; dr2/dz_d = -2 (xs_d - zs_d) / l_d
+        if (WANT_X && p.g_X) {
+            for (int i = threadIdx.x; i < TR * p.D; i += GT) {
+                int r = i / p.D, d = i % p.D;
+                if (r0 + r < p.N) {
+                    double l = p.ell[p.ell_is_scalar ? 0 : d];
+                    atomicAdd(p.g_X + (r0 + r) * p.ldgx + d, p.scale * 2.0 * gx_s[r * Dp + d] / l);
+                }
+            }
+        }
+        if (WANT_Z && p.g_Z) {
+            for (int i = threadIdx.x; i < TC * p.D; i += GT) {
+                int cc = i / p.D, d = i % p.D;
+                if (c0 + cc < p.M) {
+                    double l = p.ell[p.ell_is_scalar ? 0 : d];
+                    atomicAdd(p.g_Z + (c0 + cc) * p.ldgz + d, -p.scale * 2.0 * gz_s[d * TC + cc] / l);
+                }
+            }
+        }
+    }
+}
+
+// final deterministic reduction of per-tile partials: g_ell[d] += scale*(-2/l_d)*sum, g_var += scale*sum/var
+__global__ void gram_bwd_reduce_kernel(const double* __restrict__ partials, int64_t ntiles, int Dp, int D,
+                                       const double* __restrict__ ell, int ell_is_scalar,
+                                       const double* __restrict__ variance, double scale,
+                                       double* g_ell, double* g_var) {
+    __shared__ double red[32];
+    __shared__ double iso;
+    if (threadIdx.x == 0) iso = 0.0;
+    for (int d = 0; d <= D; ++d) {
+        int col = (d == D) ? Dp : d;
+        double s = 0.0;
+        for (int64_t t = threadIdx.x; t < ntiles; t += blockDim.x) s += partials[t * (Dp + 1) + col];
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) {
+            if (d == D) {
+                if (g_var) g_var[0] += scale * s / variance[0];
+            } else if (g_ell) {
+                double l = ell[ell_is_scalar ? 0 : d];
+                double v = scale * (-2.0 / l) * s;
+                if (ell_is_scalar) iso += v; else g_ell[d] += v;
+            }
+        }
+    }
+    if (threadIdx.x == 0 && ell_is_scalar && g_ell) g_ell[0] += iso;
+}
+
+// ------------------------------------------------------------------------------------------
+// exact-GP backward: W tiles from alpha and the block-upper Sigma^-1 storage
+// ------------------------------------------------------------------------------------------
+struct MllBwdParams {
+    int64_t N;
+    int D;
+    int64_t nb, nblk;
+    const double* X; int64_t ldx;
+    const double* alpha;
+    const double* S; int64_t lds;
+    const double* Sdiag;
+    const double* ell; int ell_is_scalar;
+    const double* variance;
+    double* partials;  // [ntiles][Dp + 2]  (.., sum W*K, tr W)
+    int64_t tiles_c;
+};
+
+template <int KIND, int DC>
+__global__ void __launch_bounds__(GT, 2) mll_bwd_kernel(const MllBwdParams p) {
+    extern __shared__ __align__(16) double sm[];
+    const int Dp = pad_dim(p.D, DC);
+    double* Xs = sm;
+    double* Zs = Xs + TR * Dp;
+    double* ell_acc = Zs + Dp * TC;
+    double* red = ell_acc + Dp;
+    const int64_t tr = blockIdx.x / p.tiles_c, tc = blockIdx.x % p.tiles_c;
+    const int64_t r0 = tr * TR, c0 = tc * TC;
+    double* out = p.partials + (int64_t)blockIdx.x * (Dp + 2);
+    const int64_t br = r0 / p.nb, bc = c0 / p.nb;  // tiles never straddle nb-blocks (nb % 128 == 0)
+    if (br > bc) {
+        for (int i = threadIdx.x; i < Dp + 2; i += GT) out[i] = 0.0;
+        return;
+    }
+    load_scaled<true>(Xs, p.X, p.ldx, r0, p.N, TR, p.D, Dp, p.ell, p.ell_is_scalar);
+    load_scaled<false>(Zs, p.X, p.ldx, c0, p.N, TC, p.D, Dp, p.ell, p.ell_is_scalar);
+    for (int i = threadIdx.x; i < Dp; i += GT) ell_acc[i] = 0.0;
+    __syncthreads();
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    double r2[RPT][2];
+    tile_r2<DC>(Xs, Zs, Dp, tx, ty, r2);
+    const double var = *p.variance;
+    const int64_t c = c0 + 2 * tx;
+    const bool diag_blk = (br == bc);
+    const double wgt = diag_blk ? 1.0 : 2.0;  // strictly-upper blocks stand for their mirror image too
+    const double* Sbase = diag_blk ? (p.Sdiag + br * p.nb * p.nb) : p.S;
+    const int64_t sld = diag_blk ? p.nb : p.lds;
+    const int64_t roff = diag_blk ? br * p.nb : 0;
+    double ac0 = (c < p.N) ? p.alpha[c] : 0.0, ac1 = (c + 1 < p.N) ? p.alpha[c + 1] : 0.0;
+    double wk = 0.0, trw = 0.0;
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        int64_t r = r0 + ty + 4 * i;
+        double ar = (r < p.N) ? p.alpha[r] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            double w = 0.0;
+            if (r < p.N && c + j < p.N) {
+                double sv = Sbase[(r - roff) * sld + (c + j - roff)];
+                w = 0.5 * (ar * (j ? ac1 : ac0) - sv);
+                if (r == c + j) trw += w;
+                w *= wgt;
+            }
+            double k, dk;
+            kprofile_grad<KIND>(r2[i][j], var, k, dk);
+            wk = fma(w, k, wk);
+            r2[i][j] = w * dk;
+        }
+    }
+    contract_dims<DC, false, false>(Xs, Zs, Dp, tx, ty, r2, ell_acc, nullptr, nullptr);
+    double s1 = block_sum(wk, red);
+    double s2 = block_sum(trw, red);
+    if (threadIdx.x == 0) { out[Dp] = s1; out[Dp + 1] = s2; }
+    for (int i = threadIdx.x; i < Dp; i += GT) out[i] = ell_acc[i];
+}
+
+__global__ void mll_bwd_reduce_kernel(const double* __restrict__ partials, int64_t ntiles, int Dp, int D,
+                                      const double* __restrict__ ell, int ell_is_scalar,
+                                      const double* __restrict__ variance, const double* __restrict__ obs_stddev,
+                                      const double* __restrict__ gout, const double* __restrict__ alpha, int64_t N,
+                                      double* g_ell, double* g_var, double* g_obs, double* g_mean) {
+    __shared__ double red[32];
+    __shared__ double iso;
+    if (threadIdx.x == 0) iso = 0.0;
+    const double g = gout ? gout[0] : 1.0;
+    for (int d = 0; d < D + 2; ++d) {
+        int col = (d < D) ? d : (Dp + (d - D));
+        double s = 0.0;
+        for (int64_t t = threadIdx.x; t < ntiles; t += blockDim.x) s += partials[t * (Dp + 2) + col];
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) {
+            if (d < D) {
+                if (g_ell) {
+                    double l = ell[ell_is_scalar ? 0 : d];
+                    double v = g * (-2.0 / l) * s;
+                    if (ell_is_scalar) iso += v; else g_ell[d] = v;
+                }
+            } else if (d == D) {
+                if (g_var) g_var[0] = g * s / variance[0];
+            } else {
+                if (g_obs) g_obs[0] = g * 2.0 * obs_stddev[0] * s;
+            }
+        }
+    }
+    if (threadIdx.x == 0 && ell_is_scalar && g_ell) g_ell[0] = iso;
+    if (g_mean) {
+        double s = 0.0;
+        for (int64_t i = threadIdx.x; i < N; i += blockDim.x) s += alpha[i];
+        s = block_sum(s, red);
+        if (threadIdx.x == 0) g_mean[0] = g * s;
+    }
+}
+
+inline int pick_dc(int D) { return D <= 2 ? 2 : (D <= 4 ? 4 : 8); }
+
+}  // namespace
+
+int max_input_dim() { return MAX_D; }
+
+int gram(stream_t s, const GramDesc& d) {
+    if (d.N < 0 || d.M < 0 || d.D <= 0) return GPB_ERR_INVALID;
+    if (d.D > MAX_D) return GPB_ERR_UNSUPPORTED;
+    if (d.N == 0 || d.M == 0) return GPB_OK;
+    if (!d.X || !d.Z || !d.ell || !d.variance || !d.K) return GPB_ERR_INVALID;
+    GramParams p;
+    p.N = d.N; p.M = d.M; p.D = d.D;
+    p.X = d.X; p.ldx = d.ldx; p.Z = d.Z; p.ldz = d.ldz;
+    p.ell = d.ell; p.ell_is_scalar = d.ell_is_scalar; p.variance = d.variance;
+    p.K = d.K; p.ldk = d.ldk; p.lower_only = d.lower_only;
+    p.diag_add = d.diag_add; p.diag_add_sq = d.diag_add_sq;
+    p.row0 = d.row0; p.col0 = d.col0;
+    p.tiles_c = (d.M + TC - 1) / TC;
+    p.k_vec16 = ((reinterpret_cast<uintptr_t>(d.K) & 15) == 0) && (d.ldk % 2 == 0);
+    int64_t ntiles = ((d.N + TR - 1) / TR) * p.tiles_c;
+    if (ntiles > 2147483647LL) return GPB_ERR_UNSUPPORTED;
+    cudaStream_t st = to_stream(s);
+    switch (d.kind) {
+        case KIND_RBF: return launch_gram<KIND_RBF>(st, p, ntiles);
+        case KIND_MATERN32: return launch_gram<KIND_MATERN32>(st, p, ntiles);
+        case KIND_MATERN52: return launch_gram<KIND_MATERN52>(st, p, ntiles);
+        default: return GPB_ERR_INVALID;
+    }
+}
+
+int64_t gram_bwd_partials_count(int64_t N, int64_t M, int D) {
+    int Dp = pad_dim(D, pick_dc(D));
+    return ((N + TR - 1) / TR) * ((M + TC - 1) / TC) * (Dp + 1);
+}
+
+template <int KIND, int DCV, bool WX, bool WZ>
+static int launch_gram_bwd_one(cudaStream_t st, const GramBwdParams& p, int64_t ntiles) {
+    int Dp = pad_dim(p.D, DCV);
+    size_t smem = sizeof(double) * ((size_t)(TR + TC) * Dp + (WX ? TR * Dp : 0) + (WZ ? TC * Dp : 0) + Dp + 32);
+    auto kern = gram_bwd_kernel<KIND, DCV, WX, WZ>;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<dim3((unsigned)ntiles), GT, smem, st>>>(p);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+template <int KIND, int DCV>
+static int launch_gram_bwd_dc(cudaStream_t st, const GramBwdParams& p, int64_t ntiles) {
+    bool wx = p.g_X != nullptr, wz = p.g_Z != nullptr;
+    if (wx && wz) return launch_gram_bwd_one<KIND, DCV, true, true>(st, p, ntiles);
+    if (wx) return launch_gram_bwd_one<KIND, DCV, true, false>(st, p, ntiles);
+    if (wz) return launch_gram_bwd_one<KIND, DCV, false, true>(st, p, ntiles);
+    return launch_gram_bwd_one<KIND, DCV, false, false>(st, p, ntiles);
+}
+
+template <int KIND>
+static int launch_gram_bwd(cudaStream_t st, const GramBwdParams& p, int64_t ntiles) {
+    int DC = pick_dc(p.D);
+    if (DC == 2) return launch_gram_bwd_dc<KIND, 2>(st, p, ntiles);
+    if (DC == 4) return launch_gram_bwd_dc<KIND, 4>(st, p, ntiles);
+    return launch_gram_bwd_dc<KIND, 8>(st, p, ntiles);
+}
+
+int gram_bwd(stream_t s, const GramBwdDesc& d) {
+    if (d.N < 0 || d.M < 0 || d.D <= 0) return GPB_ERR_INVALID;
+    if (d.D > MAX_D) return GPB_ERR_UNSUPPORTED;
+    if (d.N == 0 || d.M == 0) return GPB_OK;
+    if (!d.X || !d.Z || !d.ell || !d.variance || !d.dK || !d.partials) return GPB_ERR_INVALID;
+    GramBwdParams p;
+    p.N = d.N; p.M = d.M; p.D = d.D;
+    p.X = d.X; p.ldx = d.ldx; p.Z = d.Z; p.ldz = d.ldz;
+    p.ell = d.ell; p.ell_is_scalar = d.ell_is_scalar; p.variance = d.variance;
+    p.dK = d.dK; p.lddk = d.lddk; p.scale = d.scale; p.partials = d.partials;
+    p.g_X = d.g_X; p.ldgx = d.ldgx; p.g_Z = d.g_Z; p.ldgz = d.ldgz;
+    p.tiles_c = (d.M + TC - 1) / TC;
+    int64_t ntiles = ((d.N + TR - 1) / TR) * p.tiles_c;
+    if (ntiles > 2147483647LL) return GPB_ERR_UNSUPPORTED;
+    cudaStream_t st = to_stream(s);
+    int rc;
+    switch (d.kind) {
+        case KIND_RBF: rc = launch_gram_bwd<KIND_RBF>(st, p, ntiles); break;
+        case KIND_MATERN32: rc = launch_gram_bwd<KIND_MATERN32>(st, p, ntiles); break;
+        case KIND_MATERN52: rc = launch_gram_bwd<KIND_MATERN52>(st, p, ntiles); break;
+        default: return GPB_ERR_INVALID;
+    }
+    if (rc != GPB_OK) return rc;
+    int Dp = pad_dim(d.D, pick_dc(d.D));
+    gram_bwd_reduce_kernel<<<1, 1024, 0, st>>>(d.partials, ntiles, Dp, d.D, d.ell, d.ell_is_scalar, d.variance,
+                                               d.scale, d.g_ell, d.g_var);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+int64_t mll_bwd_partials_count(int64_t N, int D, int64_t nb) {
+    (void)nb;
+    int Dp = pad_dim(D, pick_dc(D));
+    return ((N + TR - 1) / TR) * ((N + TC - 1) / TC) * (Dp + 2);
+}
+
+template <int KIND>
+static int launch_mll_bwd(cudaStream_t st, const MllBwdParams& p, int64_t ntiles) {
+    int DC = pick_dc(p.D);
+    int Dp = pad_dim(p.D, DC);
+    size_t smem = sizeof(double) * ((size_t)(TR + TC) * Dp + Dp + 32);
+    dim3 grid((unsigned)ntiles);
+#define GPB_MLL_LAUNCH(DCV)                                                                          \
+    {                                                                                                \
+        auto kern = mll_bwd_kernel<KIND, DCV>;                                                       \
+        if (smem > 48 * 1024)                                                                        \
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+        kern<<<grid, GT, smem, st>>>(p);                                                             \
+    }
+    if (DC == 2) GPB_MLL_LAUNCH(2) else if (DC == 4) GPB_MLL_LAUNCH(4) else GPB_MLL_LAUNCH(8)
+#undef GPB_MLL_LAUNCH
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+int mll_bwd(stream_t s, const MllBwdDesc& d) {
+    if (d.N <= 0 || d.D <= 0) return GPB_ERR_INVALID;
+    if (d.D > MAX_D) return GPB_ERR_UNSUPPORTED;
+    if (d.nb <= 0 || d.nb % TC != 0) return GPB_ERR_INVALID;
+    if (!d.X || !d.alpha || !d.S || !d.Sdiag || !d.ell || !d.variance || !d.obs_stddev || !d.partials)
+        return GPB_ERR_INVALID;
+    MllBwdParams p;
+    p.N = d.N; p.D = d.D; p.nb = d.nb; p.nblk = (d.N + d.nb - 1) / d.nb;
+    p.X = d.X; p.ldx = d.ldx; p.alpha = d.alpha; p.S = d.S; p.lds = d.lds; p.Sdiag = d.Sdiag;
+    p.ell = d.ell; p.ell_is_scalar = d.ell_is_scalar; p.variance = d.variance;
+    p.partials = d.partials;
+    p.tiles_c = (d.N + TC - 1) / TC;
+    int64_t ntiles = ((d.N + TR - 1) / TR) * p.tiles_c;
+    if (ntiles > 2147483647LL) return GPB_ERR_UNSUPPORTED;
+    cudaStream_t st = to_stream(s);
+    int rc;
+    switch (d.kind) {
+        case KIND_RBF: rc = launch_mll_bwd<KIND_RBF>(st, p, ntiles); break;
+        case KIND_MATERN32: rc = launch_mll_bwd<KIND_MATERN32>(st, p, ntiles); break;
+        case KIND_MATERN52: rc = launch_mll_bwd<KIND_MATERN52>(st, p, ntiles); break;
+        default: return GPB_ERR_INVALID;
+    }
+    if (rc != GPB_OK) return rc;
+    int Dp = pad_dim(d.D, pick_dc(d.D));
+    mll_bwd_reduce_kernel<<<1, 1024, 0, st>>>(d.partials, ntiles, Dp, d.D, d.ell, d.ell_is_scalar, d.variance,
+                                              d.obs_stddev, d.gout, d.alpha, d.N, d.g_ell, d.g_var,
+                                              d.g_obs_stddev, d.g_mean);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+}  // namespace gpb

@@ -1,0 +1,186 @@
+// Device-primitive launcher interface.
+//
+// Everything float64, row-major.  All pointers are DEVICE pointers owned by the caller; every
+// launcher only enqueues work on `stream` (a cudaStream_t passed as void*): no allocation, no
+// synchronisation, no host reads.  The blocked algorithms in algorithms.cpp are written purely
+// against this interface, so the same orchestration code can be linked against the CUDA
+// implementation (primitives_cuda.cu -> the shipped libgpjax_b200.so) or against a plain C++
+// host model used ONLY by the CPU test-suite (tests/hostsim/primitives_host.cpp).
+#pragma once
+#include <cstdint>
+
+namespace gpb {
+
+typedef void* stream_t;
+
+enum KernelKind { KIND_RBF = 0, KIND_MATERN32 = 1, KIND_MATERN52 = 2 };
+
+// error codes (identical to include/gpjax_b200.h)
+#ifndef GPB_OK
+#define GPB_OK 0
+#define GPB_ERR_INVALID (-1)      // bad argument (null pointer, negative size, unknown kind)
+#define GPB_ERR_UNSUPPORTED (-2)  // e.g. D larger than the compiled maximum
+#define GPB_ERR_LAUNCH (-3)       // CUDA launch error
+#define GPB_ERR_WORKSPACE (-4)    // workspace too small
+#endif
+
+// Operand layouts for gemm(): element (m,k) of A / (n,k) of B lives at
+//   LAYOUT_K : ptr[m*ld + k]   (K contiguous, "row-major M x K")
+//   LAYOUT_MN: ptr[k*ld + m]   (M/N contiguous, "row-major K x M")
+enum Layout { LAYOUT_K = 0, LAYOUT_MN = 1 };
+
+// Output masks for gemm(): which C elements are written.  (r,c) are global coordinates
+// r = mask_row0 + m, c = mask_col0 + n.
+enum Mask {
+    MASK_NONE = 0,
+    MASK_LOWER = 1,               // r >= c
+    MASK_UPPER = 2,               // r <= c
+    MASK_BLOCK_STRICT_UPPER = 3,  // r / mask_nb <  c / mask_nb
+    MASK_BLOCK_STRICT_LOWER = 4   // r / mask_nb >  c / mask_nb
+};
+
+// K-range restriction exploiting triangular operands (zeros are never read).
+enum KRange {
+    KR_FULL = 0,
+    KR_B_LOWER = 1,  // B(n,k) == 0 for k > n + kr_off   -> k <  n_tile_end + kr_off
+    KR_B_UPPER = 2,  // B(n,k) == 0 for k < n + kr_off   -> k >= n_tile_begin + kr_off
+    KR_A_LOWER = 3,  // A(m,k) == 0 for k > m + kr_off
+    KR_A_UPPER = 4   // A(m,k) == 0 for k < m + kr_off
+};
+
+struct GemmDesc {
+    int64_t M = 0, N = 0, K = 0;
+    const double* A = nullptr;
+    int64_t lda = 0;
+    int a_layout = LAYOUT_K;
+    const double* B = nullptr;
+    int64_t ldb = 0;
+    int b_layout = LAYOUT_K;
+    double* C = nullptr;
+    int64_t ldc = 0;
+    double alpha = 1.0, beta = 0.0;  // C = beta*C + alpha * A * B^T   (beta == 0 never reads C)
+    int mask = MASK_NONE;
+    int64_t mask_row0 = 0, mask_col0 = 0, mask_nb = 1;
+    int krange = KR_FULL;
+    int64_t kr_off = 0;
+    int batch = 1;
+    int64_t strideA = 0, strideB = 0, strideC = 0;
+};
+
+// C = beta*C + alpha * A * B^T on the FP64 tensor pipe (DMMA).
+int gemm(stream_t s, const GemmDesc& d);
+
+struct GramDesc {
+    int kind = KIND_RBF;
+    int64_t N = 0, M = 0;  // K is N x M
+    int D = 0;
+    const double* X = nullptr;  // [N, D], row stride ldx
+    int64_t ldx = 0;
+    const double* Z = nullptr;  // [M, D], row stride ldz
+    int64_t ldz = 0;
+    const double* ell = nullptr;  // device, [D] (ARD) or [1] (isotropic)
+    int ell_is_scalar = 0;
+    const double* variance = nullptr;  // device scalar
+    double* K = nullptr;
+    int64_t ldk = 0;
+    int lower_only = 0;          // square case: write only tiles that touch r >= c
+    double diag_add = 0.0;       // host constant added where global row == col (jitter)
+    const double* diag_add_sq = nullptr;  // optional device scalar t: adds t*t on the diagonal (obs_stddev)
+    int64_t row0 = 0, col0 = 0;  // global coordinates of K[0,0] (for the diagonal test)
+};
+
+// K[i,j] = variance * g(sum_d ((x_id - z_jd)/l_d)^2) (+ diagonal terms); direct-difference form.
+int gram(stream_t s, const GramDesc& d);
+
+// Cholesky of one n x n block (n <= 128), in place in the lower triangle of A (strict upper
+// untouched).  Also writes inv(L) to Dinv (n x n, row stride ldd, upper part zero) and its
+// transpose to DinvT.  On a non-positive / NaN pivot: sets *info = global_row0 + column + 1
+// (first failure wins) and NaN-fills the block, Dinv and DinvT (JAX cholesky semantics).
+// factor == 0: A already holds a lower-triangular factor; only the inverses are produced.
+int potrf_leaf(stream_t s, int n, double* A, int64_t lda, double* Dinv, int64_t ldd, double* DinvT,
+               int64_t lddt, int* info, int64_t global_row0, int factor);
+
+// y = beta*y + alpha * op(A) x,  A is m x n (row stride lda); trans=0: y[m] ; trans=1: y[n].
+int gemv(stream_t s, int64_t m, int64_t n, const double* A, int64_t lda, int trans, const double* x,
+         double* y, double alpha, double beta);
+
+// out[0] = sum_i log(A[i*(lda+1)])            (half log-det of L L^T)
+int sum_log_diag(stream_t s, int64_t n, const double* A, int64_t lda, double* out);
+// out[0] = sum_i x[i]*y[i]
+int dot(stream_t s, int64_t n, const double* x, const double* y, double* out);
+// out[i] = a[i] - (*c)   (c device scalar, may be null -> 0)
+int sub_scalar(stream_t s, int64_t n, const double* a, const double* c, double* out);
+// strided 2-D copy: dst[i*ldd + j] = src[i*lds + j]
+int copy2d(stream_t s, int64_t rows, int64_t cols, const double* src, int64_t lds, double* dst,
+           int64_t ldd);
+// dst[j*ldd + i] = src[i*lds + j]
+int transpose2d(stream_t s, int64_t rows, int64_t cols, const double* src, int64_t lds, double* dst,
+                int64_t ldd);
+// p[i*ld + j] = v for an rows x cols rectangle
+int fill2d(stream_t s, int64_t rows, int64_t cols, double* p, int64_t ld, double v);
+// zero the strict upper (uplo=2) or strict lower (uplo=1) triangle of an n x n matrix
+int zero_triangle(stream_t s, int64_t n, double* A, int64_t lda, int uplo);
+// mirror: A[c,r] = A[r,c] for r > c (from_lower=1) or A[r,c] = A[c,r] for r > c (from_lower=0)
+int symmetrize(stream_t s, int64_t n, double* A, int64_t lda, int from_lower);
+
+// out[0] = -0.5*(n*log(2*pi) + 2*half_logdet[0] + quad[0]); NaN if *info != 0.
+int mll_value(stream_t s, int64_t n, const double* half_logdet, const double* quad, const int* info,
+              double* out);
+
+struct MllBwdDesc {
+    int kind = KIND_RBF;
+    int64_t N = 0;
+    int D = 0;
+    int64_t nb = 256;           // block size of the Sigma^-1 storage
+    const double* X = nullptr;  // [N, D]
+    int64_t ldx = 0;
+    const double* alpha = nullptr;  // [N]
+    const double* S = nullptr;      // N x N buffer: blocks strictly above the block diagonal hold Sigma^-1
+    int64_t lds = 0;
+    const double* Sdiag = nullptr;  // ceil(N/nb) blocks of nb x nb (row stride nb): diagonal blocks of Sigma^-1
+    const double* ell = nullptr;
+    int ell_is_scalar = 0;
+    const double* variance = nullptr;
+    const double* obs_stddev = nullptr;
+    const double* gout = nullptr;  // upstream cotangent (device scalar), may be null -> 1
+    double* partials = nullptr;    // workspace, mll_bwd_partials_count(...) doubles
+    double* g_ell = nullptr;       // [D] or [1]
+    double* g_var = nullptr;
+    double* g_obs_stddev = nullptr;
+    double* g_mean = nullptr;
+};
+int64_t mll_bwd_partials_count(int64_t N, int D, int64_t nb);
+// Streams W = 1/2 (alpha alpha^T - Sigma^-1) tile by tile against dK/dtheta recomputed from X.
+int mll_bwd(stream_t s, const MllBwdDesc& d);
+
+struct GramBwdDesc {
+    int kind = KIND_RBF;
+    int64_t N = 0, M = 0;
+    int D = 0;
+    const double* X = nullptr;
+    int64_t ldx = 0;
+    const double* Z = nullptr;
+    int64_t ldz = 0;
+    const double* ell = nullptr;
+    int ell_is_scalar = 0;
+    const double* variance = nullptr;
+    const double* dK = nullptr;  // cotangent, N x M
+    int64_t lddk = 0;
+    double scale = 1.0;
+    double* partials = nullptr;  // gram_bwd_partials_count(...) doubles
+    // all accumulated (+=) so several blocks / the Kzz term can add into the same gradient
+    double* g_ell = nullptr;  // [D] or [1]
+    double* g_var = nullptr;  // [1]
+    double* g_X = nullptr;    // [N, D] or null
+    int64_t ldgx = 0;
+    double* g_Z = nullptr;  // [M, D] or null
+    int64_t ldgz = 0;
+};
+int64_t gram_bwd_partials_count(int64_t N, int64_t M, int D);
+// g_theta += scale * <dK, dK/dtheta>, g_X / g_Z likewise; dK read once, K recomputed on the fly.
+int gram_bwd(stream_t s, const GramBwdDesc& d);
+
+// maximum input dimension D the compiled kernels support
+int max_input_dim();
+
+}  // namespace gpb

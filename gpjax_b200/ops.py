@@ -1,0 +1,309 @@
+"""Thin torch <-> C-ABI shim: device memory, streams and autograd plumbing only.
+
+Every function here enqueues hand-written sm_100a kernels from ``libgpjax_b200.so`` on the current
+CUDA stream through the C ABI of ``include/gpjax_b200.h``; none of them computes anything with
+torch ops.  Tensors must be float64, on the GPU and contiguous (asserted, never copied silently
+except where a ``.contiguous()`` is explicitly documented).  The ``torch.autograd.Function``
+classes are the analogue of the ``jax.custom_vjp`` registrations the north-star describes.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _abi
+from ._lib import lib, require_cuda
+
+KIND_IDS = {"RBF": 0, "Matern32": 1, "Matern52": 2, "Matérn32": 1, "Matérn52": 2}
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check_mat(t: torch.Tensor, name: str) -> None:
+    require_cuda(t)
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name} must be a 2-D float64 CUDA tensor with unit column stride")
+
+
+def _ell_args(ell: torch.Tensor, D: int):
+    require_cuda(ell)
+    if ell.numel() == 1:
+        return ell.reshape(1).contiguous(), 1
+    if ell.numel() != D:
+        raise ValueError(f"lengthscale has {ell.numel()} entries but the inputs have {D} dimensions")
+    return ell.reshape(D).contiguous(), 0
+
+
+def _scalar(t: torch.Tensor, name: str) -> torch.Tensor:
+    require_cuda(t)
+    if t.numel() != 1:
+        raise ValueError(f"{name} must hold exactly one element")
+    return t.reshape(1)
+
+
+# ------------------------------------------------------------------------------------------
+# K1: Gram / cross-covariance
+# ------------------------------------------------------------------------------------------
+def gram_forward(kind: int, X, Z, ell, variance, diag_add=0.0, diag_add_sq=None, lower_only=False, out=None):
+    _check_mat(X, "X")
+    _check_mat(Z, "Z")
+    N, D = X.shape
+    M = Z.shape[0]
+    if Z.shape[1] != D:
+        raise ValueError("X and Z must have the same number of columns")
+    ell_v, iso = _ell_args(ell, D)
+    var = _scalar(variance, "variance")
+    if out is None:
+        out = torch.empty((N, M), dtype=torch.float64, device=X.device)
+    _check_mat(out, "out")
+    rc = lib().gpb_gram(_stream(), kind, N, M, D, _p(X), X.stride(0), _p(Z), Z.stride(0), _p(ell_v), iso, _p(var),
+                        float(diag_add), _p(diag_add_sq), int(lower_only), _p(out), out.stride(0))
+    _abi.check(rc, "gpb_gram")
+    return out
+
+
+def gram_backward(kind: int, X, Z, ell, variance, dK, want_X=False, want_Z=False, scale=1.0, accum=None):
+    """Returns (g_ell, g_var, g_X, g_Z); `accum` may carry existing tensors to accumulate into."""
+    _check_mat(X, "X")
+    _check_mat(Z, "Z")
+    _check_mat(dK, "dK")
+    N, D = X.shape
+    M = Z.shape[0]
+    ell_v, iso = _ell_args(ell, D)
+    var = _scalar(variance, "variance")
+    dev = X.device
+    accum = accum or {}
+    g_ell = accum.get("ell")
+    if g_ell is None:
+        g_ell = torch.zeros(1 if iso else D, dtype=torch.float64, device=dev)
+    g_var = accum.get("var")
+    if g_var is None:
+        g_var = torch.zeros(1, dtype=torch.float64, device=dev)
+    g_X = accum.get("X")
+    if g_X is None and want_X:
+        g_X = torch.zeros((N, D), dtype=torch.float64, device=dev)
+    g_Z = accum.get("Z")
+    if g_Z is None and want_Z:
+        g_Z = torch.zeros((M, D), dtype=torch.float64, device=dev)
+    nbytes = lib().gpb_gram_bwd_workspace_bytes(N, M, D)
+    ws = torch.empty(max(nbytes // 8, 1), dtype=torch.float64, device=dev)
+    rc = lib().gpb_gram_bwd(_stream(), kind, N, M, D, _p(X), X.stride(0), _p(Z), Z.stride(0), _p(ell_v), iso,
+                            _p(var), _p(dK), dK.stride(0), float(scale), _p(ws), nbytes, _p(g_ell), _p(g_var),
+                            _p(g_X), D, _p(g_Z), D)
+    _abi.check(rc, "gpb_gram_bwd")
+    return g_ell, g_var, g_X, g_Z
+
+
+class GramFunction(torch.autograd.Function):
+    """Differentiable K(X, Z); backward never materialises dK/dtheta."""
+
+    @staticmethod
+    def forward(ctx, kind, X, Z, ell, variance, symmetric):
+        ctx.kind = kind
+        ctx.symmetric = symmetric
+        ctx.save_for_backward(X, Z, ell, variance)
+        return gram_forward(kind, X, Z, ell, variance)
+
+    @staticmethod
+    def backward(ctx, dK):
+        X, Z, ell, variance = ctx.saved_tensors
+        dK = dK.contiguous()
+        nx, nz = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        g_ell, g_var, g_X, g_Z = gram_backward(ctx.kind, X, Z, ell, variance, dK, want_X=nx, want_Z=nz)
+        g_ell = g_ell.reshape(ell.shape) if ctx.needs_input_grad[3] else None
+        g_var = g_var.reshape(variance.shape) if ctx.needs_input_grad[4] else None
+        return None, g_X, g_Z, g_ell, g_var, None
+
+
+# ------------------------------------------------------------------------------------------
+# K2-K5: factorisation family
+# ------------------------------------------------------------------------------------------
+class FactorWorkspace:
+    """Device scratch for the blocked factorisation (diagonal-block inverses, panel, partials)."""
+
+    def __init__(self, n: int, d: int = 1, potri: bool = False, device=None):
+        self.n, self.d, self.potri = int(n), int(d), int(bool(potri))
+        self.nbytes = lib().gpb_factor_workspace_bytes(self.n, self.d, self.potri)
+        self.buf = torch.empty(max(self.nbytes // 8, 1), dtype=torch.float64, device=device)
+
+    def args(self):
+        return _p(self.buf), self.nbytes, self.n, self.d, self.potri
+
+
+def potrf_lower_(A: torch.Tensor, ws: FactorWorkspace, zero_upper: bool = True) -> torch.Tensor:
+    """In-place lower Cholesky of the lower triangle of A.  Returns the device `info` word."""
+    _check_mat(A, "A")
+    n = A.shape[0]
+    info = torch.zeros(1, dtype=torch.int32, device=A.device)
+    rc = lib().gpb_potrf_lower(_stream(), n, _p(A), A.stride(0), int(zero_upper), *ws.args(), _p(info))
+    _abi.check(rc, "gpb_potrf_lower")
+    return info
+
+
+def diag_inverses(L: torch.Tensor, ws: FactorWorkspace) -> None:
+    _check_mat(L, "L")
+    rc = lib().gpb_diag_inverses(_stream(), L.shape[0], _p(L), L.stride(0), *ws.args())
+    _abi.check(rc, "gpb_diag_inverses")
+
+
+def trsv_lower_(L: torch.Tensor, x: torch.Tensor, ws: FactorWorkspace, trans: bool = False) -> torch.Tensor:
+    _check_mat(L, "L")
+    require_cuda(x)
+    assert x.dim() == 1 and x.is_contiguous()
+    rc = lib().gpb_trsv_lower(_stream(), L.shape[0], _p(L), L.stride(0), int(trans), _p(x), *ws.args())
+    _abi.check(rc, "gpb_trsv_lower")
+    return x
+
+
+def trsm_lower_left_(L: torch.Tensor, B: torch.Tensor, ws: FactorWorkspace, trans: bool = False) -> torch.Tensor:
+    _check_mat(L, "L")
+    _check_mat(B, "B")
+    rc = lib().gpb_trsm_lower_left(_stream(), L.shape[0], B.shape[1], _p(L), L.stride(0), int(trans), _p(B),
+                                   B.stride(0), *ws.args())
+    _abi.check(rc, "gpb_trsm_lower_left")
+    return B
+
+
+def sum_log_diag(L: torch.Tensor) -> torch.Tensor:
+    _check_mat(L, "L")
+    out = torch.empty(1, dtype=torch.float64, device=L.device)
+    rc = lib().gpb_sum_log_diag(_stream(), L.shape[0], _p(L), L.stride(0), _p(out))
+    _abi.check(rc, "gpb_sum_log_diag")
+    return out.reshape(())
+
+
+def potri_lower(Lbuf: torch.Tensor, ws: FactorWorkspace) -> torch.Tensor:
+    """Sigma^-1 (full symmetric) from a factor produced by potrf_lower_ with the same workspace.
+    The strict upper blocks of `Lbuf` are used as scratch."""
+    _check_mat(Lbuf, "L")
+    n = Lbuf.shape[0]
+    out = torch.empty((n, n), dtype=torch.float64, device=Lbuf.device)
+    rc = lib().gpb_potri_lower(_stream(), n, _p(Lbuf), Lbuf.stride(0), _p(out), out.stride(0), *ws.args())
+    _abi.check(rc, "gpb_potri_lower")
+    return out
+
+
+def gemm(A, B, C=None, alpha=1.0, beta=0.0, a_layout=0, b_layout=0, mask=0):
+    """C = beta*C + alpha * op(A) op(B)^T on the DMMA pipe (layout 0: [rows,K]; 1: [K,rows])."""
+    _check_mat(A, "A")
+    _check_mat(B, "B")
+    M, K = (A.shape if a_layout == 0 else (A.shape[1], A.shape[0]))
+    N, K2 = (B.shape if b_layout == 0 else (B.shape[1], B.shape[0]))
+    if K != K2:
+        raise ValueError("inner dimensions differ")
+    if C is None:
+        C = torch.empty((M, N), dtype=torch.float64, device=A.device)
+        beta = 0.0
+    _check_mat(C, "C")
+    rc = lib().gpb_gemm(_stream(), M, N, K, float(alpha), _p(A), A.stride(0), a_layout, _p(B), B.stride(0), b_layout,
+                        float(beta), _p(C), C.stride(0), mask)
+    _abi.check(rc, "gpb_gemm")
+    return C
+
+
+# ------------------------------------------------------------------------------------------
+# conjugate_mll: fused forward + analytic backward
+# ------------------------------------------------------------------------------------------
+class _MllState:
+    """Per-(device, N, D) buffers reused across iterations: the N x N Sigma/L/Sigma^-1 buffer and
+    the factorisation workspace.  `generation` guards against backward being called on a stale
+    forward (then the forward is simply replayed)."""
+
+    def __init__(self, n, d, device):
+        self.sigma = torch.empty((n, n), dtype=torch.float64, device=device)
+        self.nbytes = lib().gpb_mll_workspace_bytes(n, d)
+        self.ws = torch.empty(max(self.nbytes // 8, 1), dtype=torch.float64, device=device)
+        self.generation = 0
+
+
+_MLL_CACHE: dict = {}
+
+
+def _mll_state(n, d, device) -> _MllState:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), n, d)
+    st = _MLL_CACHE.get(key)
+    if st is None:
+        _MLL_CACHE.clear()  # one live problem size at a time: the buffer is O(N^2)
+        st = _MllState(n, d, device)
+        _MLL_CACHE[key] = st
+    return st
+
+
+def release_buffers() -> None:
+    _MLL_CACHE.clear()
+
+
+def _mll_forward_raw(st, kind, X, y, ell_v, iso, var, sn, mean, jitter):
+    N, D = X.shape
+    val = torch.empty(1, dtype=torch.float64, device=X.device)
+    alpha = torch.empty(N, dtype=torch.float64, device=X.device)
+    info = torch.zeros(1, dtype=torch.int32, device=X.device)
+    rc = lib().gpb_mll_forward(_stream(), kind, N, D, _p(X), X.stride(0), _p(y), _p(ell_v), iso, _p(var), _p(sn),
+                               _p(mean), float(jitter), _p(st.sigma), st.sigma.stride(0), _p(st.ws), st.nbytes,
+                               _p(val), _p(alpha), _p(info))
+    _abi.check(rc, "gpb_mll_forward")
+    st.generation += 1
+    return val, alpha, info
+
+
+class ConjugateMllFunction(torch.autograd.Function):
+    """log N(y | m, K + (jitter + s^2) I) with the analytic gradient
+    W = 1/2 (alpha alpha^T - Sigma^-1) : dK/dtheta  (custom_vjp analogue)."""
+
+    @staticmethod
+    def forward(ctx, kind, X, y, ell, variance, obs_stddev, mean_const, jitter):
+        _check_mat(X, "X")
+        require_cuda(y)
+        N, D = X.shape
+        y = y.reshape(-1).contiguous()
+        if y.numel() != N:
+            raise ValueError("conjugate_mll supports a single output column (y of shape [N, 1])")
+        ell_v, iso = _ell_args(ell, D)
+        var = _scalar(variance, "variance")
+        sn = _scalar(obs_stddev, "obs_stddev")
+        mean = None if mean_const is None else _scalar(mean_const, "mean constant")
+        st = _mll_state(N, D, X.device)
+        val, alpha, info = _mll_forward_raw(st, kind, X, y, ell_v, iso, var, sn, mean, jitter)
+        ctx.kind, ctx.jitter, ctx.iso = kind, jitter, iso
+        ctx.gen = st.generation
+        ctx.has_mean = mean is not None
+        ctx.shapes = (ell.shape, variance.shape, obs_stddev.shape, None if mean_const is None else mean_const.shape)
+        ctx.save_for_backward(X, y, ell_v, var, sn, mean if mean is not None else var, alpha)
+        return val.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        X, y, ell_v, var, sn, mean, alpha = ctx.saved_tensors
+        N, D = X.shape
+        st = _mll_state(N, D, X.device)
+        if st.generation != ctx.gen:  # buffer was reused by another forward: replay this one
+            _, alpha, _ = _mll_forward_raw(st, ctx.kind, X, y, ell_v, ctx.iso, var, sn,
+                                           mean if ctx.has_mean else None, ctx.jitter)
+        dev = X.device
+        g_ell = torch.empty(1 if ctx.iso else D, dtype=torch.float64, device=dev)
+        g_var = torch.empty(1, dtype=torch.float64, device=dev)
+        g_sn = torch.empty(1, dtype=torch.float64, device=dev)
+        g_mean = torch.empty(1, dtype=torch.float64, device=dev) if ctx.has_mean else None
+        g = gout.reshape(1).contiguous()
+        rc = lib().gpb_mll_backward(_stream(), ctx.kind, N, D, _p(X), X.stride(0), _p(ell_v), ctx.iso, _p(var),
+                                    _p(sn), _p(st.sigma), st.sigma.stride(0), _p(st.ws), st.nbytes, _p(alpha), _p(g),
+                                    _p(g_ell), _p(g_var), _p(g_sn), _p(g_mean))
+        _abi.check(rc, "gpb_mll_backward")
+        s_ell, s_var, s_sn, s_mean = ctx.shapes
+        return (None, None, None, g_ell.reshape(s_ell), g_var.reshape(s_var), g_sn.reshape(s_sn),
+                g_mean.reshape(s_mean) if ctx.has_mean else None, None)
+
+
+def conjugate_mll_fused(kind, X, y, ell, variance, obs_stddev, mean_const=None, jitter=1e-6):
+    return ConjugateMllFunction.apply(kind, X, y, ell, variance, obs_stddev, mean_const, jitter)
+
+
+LOG_2PI = math.log(2.0 * math.pi)

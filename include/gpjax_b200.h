@@ -1,0 +1,122 @@
+/* gpjax_b200 -- C ABI of the B200-native GPJax hot path (libgpjax_b200.so).
+ *
+ * Binding-agnostic boundary: every entry point is `extern "C"`, takes plain pointers and sizes,
+ * and is what a `jax.ffi` XLA custom-call handler (or the ctypes/torch shim shipped in
+ * gpjax_b200/_lib.py) binds for the reference call site cited next to it.  Conventions:
+ *
+ *   - float64, row-major (C order); `ld*` are row strides in elements.
+ *   - every `const double*` / `double*` is a DEVICE pointer owned by the caller, including the
+ *     hyper-parameters (lengthscale[D] or [1], variance, obs_stddev, mean constant) so a training
+ *     loop never synchronises with the host.
+ *   - `stream` is a cudaStream_t.  Calls only enqueue work: no allocation, no synchronisation,
+ *     no host read-back, no exceptions.  Re-entrant; no mutable global state.
+ *   - return value: 0 = OK, <0 = GPB_ERR_* (argument / capability / launch error).  Numerical
+ *     failure (non-positive-definite pivot) is NOT an error code: outputs are NaN-filled and the
+ *     device word `*info` receives the 1-based index of the first failing pivot, mirroring the
+ *     NaN semantics of jnp.linalg.cholesky that the reference relies on.
+ *   - scratch memory is passed in; sizes come from the companion `*_workspace_bytes` query.
+ *     Factorisation workspaces are position-dependent: pass the same (ws, ws_n, ws_d, ws_potri)
+ *     to every call that works on the same factor.
+ *   - kind: 0 = RBF (gpjax/kernels/stationary/rbf.py:40-44), 1 = Matern32 (matern32.py:41-54),
+ *           2 = Matern52 (matern52.py:42-53).
+ *
+ * Citations are file:line in the reference tree (gpjax 0.13.2).
+ */
+#ifndef GPJAX_B200_H
+#define GPJAX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPB_OK 0
+#define GPB_ERR_INVALID (-1)
+#define GPB_ERR_UNSUPPORTED (-2)
+#define GPB_ERR_LAUNCH (-3)
+#define GPB_ERR_WORKSPACE (-4)
+
+#define GPB_KIND_RBF 0
+#define GPB_KIND_MATERN32 1
+#define GPB_KIND_MATERN52 2
+
+const char* gpb_version(void);
+int gpb_max_input_dim(void); /* largest D the compiled kernels accept */
+int64_t gpb_block_size(void); /* NB of the blocked algorithms (256) */
+
+/* ---- K1: fused Gram / cross-covariance -------------------------------------------------------
+ * Replaces DenseKernelComputation._cross_covariance (gpjax/kernels/computations/dense.py:32-36),
+ * AbstractKernelComputation.gram (computations/base.py:56-72) and, through diag_add/diag_add_sq,
+ * add_jitter (gpjax/linalg/utils.py:39-65) + "eye * obs_noise" (gpjax/objectives.py:101-102).
+ * K[i,j] = variance * g(sum_d (X[i,d]/l_d - Z[j,d]/l_d)^2); where i == j (square use):
+ * += diag_add + (*diag_add_sq)^2.  lower_only: skip tiles strictly above the diagonal. */
+int gpb_gram(void* stream, int kind, int64_t N, int64_t M, int D, const double* X, int64_t ldx,
+             const double* Z, int64_t ldz, const double* lengthscale, int lengthscale_is_scalar,
+             const double* variance, double diag_add, const double* diag_add_sq, int lower_only,
+             double* K, int64_t ldk);
+
+/* Reverse mode of gpb_gram (what jax.grad derives through the double vmap, dense.py:35):
+ * g_lengthscale/g_variance/g_X/g_Z += scale * <dK, dK/d.> ; any g_* may be NULL. */
+int64_t gpb_gram_bwd_workspace_bytes(int64_t N, int64_t M, int D);
+int gpb_gram_bwd(void* stream, int kind, int64_t N, int64_t M, int D, const double* X, int64_t ldx,
+                 const double* Z, int64_t ldz, const double* lengthscale, int lengthscale_is_scalar,
+                 const double* variance, const double* dK, int64_t lddk, double scale, void* ws,
+                 int64_t ws_bytes, double* g_lengthscale, double* g_variance, double* g_X, int64_t ldgx,
+                 double* g_Z, int64_t ldgz);
+
+/* ---- K2..K5: Cholesky / triangular solves / log-determinant -------------------------------------
+ * gpb_potrf_lower  : lower_cholesky(Dense) -> jnp.linalg.cholesky (gpjax/linalg/operations.py:54-55);
+ *                    in place, reads the lower triangle only; zero_upper=1 zeroes the strict upper
+ *                    triangle as JAX returns it.
+ * gpb_diag_inverses: prepares the workspace for solves against a factor that was not produced by
+ *                    gpb_potrf_lower (a user-built Triangular).
+ * gpb_trsv_lower / gpb_trsm_lower_left : solve(Triangular, b) -> jsp.linalg.solve_triangular
+ *                    (operations.py:105-107); trans=1 solves with L^T (Triangular.T, operators.py:216-218).
+ * gpb_sum_log_diag : logdet(Triangular) = sum(log(diag)) WITHOUT the factor 2 (operations.py:142-144).
+ * gpb_potri_lower  : Sigma^-1 from the factor (TRTRI + LAUUM); result mirrored to a full symmetric
+ *                    matrix in `out` (ld ldo); what reverse-mode of slogdet/solve materialises. */
+int64_t gpb_factor_workspace_bytes(int64_t ws_n, int ws_d, int ws_potri);
+int gpb_potrf_lower(void* stream, int64_t N, double* A, int64_t lda, int zero_upper, void* ws,
+                    int64_t ws_bytes, int64_t ws_n, int ws_d, int ws_potri, int* info);
+int gpb_diag_inverses(void* stream, int64_t N, const double* L, int64_t lda, void* ws, int64_t ws_bytes,
+                      int64_t ws_n, int ws_d, int ws_potri);
+int gpb_trsv_lower(void* stream, int64_t N, const double* L, int64_t lda, int trans, double* x, void* ws,
+                   int64_t ws_bytes, int64_t ws_n, int ws_d, int ws_potri);
+int gpb_trsm_lower_left(void* stream, int64_t N, int64_t T, const double* L, int64_t lda, int trans,
+                        double* B, int64_t ldb, void* ws, int64_t ws_bytes, int64_t ws_n, int ws_d,
+                        int ws_potri);
+int gpb_sum_log_diag(void* stream, int64_t N, const double* L, int64_t lda, double* out);
+int gpb_potri_lower(void* stream, int64_t N, double* A, int64_t lda, double* out, int64_t ldo, void* ws,
+                    int64_t ws_bytes, int64_t ws_n, int ws_d, int ws_potri);
+
+/* C = beta*C + alpha * A * B^T on the FP64 tensor pipe (jnp.matmul call sites, objectives.py:390,404).
+ * layouts: 0 = operand stored [rows][K] (K contiguous), 1 = stored [K][rows]. */
+int gpb_gemm(void* stream, int64_t M, int64_t N, int64_t K, double alpha, const double* A, int64_t lda,
+             int a_layout, const double* B, int64_t ldb, int b_layout, double beta, double* C, int64_t ldc,
+             int mask);
+
+/* ---- conjugate_mll value + analytic gradient -----------------------------------------------------
+ * Forward = gpjax/objectives.py:93-107 + GaussianDistribution.log_prob (gpjax/distributions.py:124-134):
+ *   Sigma = K(X,X) + (jitter + obs_stddev^2) I,  value = -1/2 (N log 2pi + logdet Sigma + d^T Sigma^-1 d),
+ *   d = y - mean_const.  (The reference evaluates logdet/solve through LU; Cholesky is used here --
+ *   identical for SPD Sigma.)  Sigma is an N x N scratch buffer that afterwards holds L (lower).
+ * Backward = what jax.value_and_grad (gpjax/fit.py:160) returns for the constrained parameters:
+ *   W = 1/2 (alpha alpha^T - Sigma^-1) contracted with dK/dtheta tile by tile.  Must be called with
+ *   the Sigma buffer, workspace and alpha exactly as the forward left them.  mean_const may be NULL
+ *   (Zero mean); any g_* may be NULL.  gout: upstream cotangent (device scalar) or NULL (=1). */
+int64_t gpb_mll_workspace_bytes(int64_t N, int D);
+int gpb_mll_forward(void* stream, int kind, int64_t N, int D, const double* X, int64_t ldx, const double* y,
+                    const double* lengthscale, int lengthscale_is_scalar, const double* variance,
+                    const double* obs_stddev, const double* mean_const, double jitter, double* Sigma,
+                    int64_t lds, void* ws, int64_t ws_bytes, double* value_out, double* alpha_out, int* info);
+int gpb_mll_backward(void* stream, int kind, int64_t N, int D, const double* X, int64_t ldx,
+                     const double* lengthscale, int lengthscale_is_scalar, const double* variance,
+                     const double* obs_stddev, double* Sigma, int64_t lds, void* ws, int64_t ws_bytes,
+                     const double* alpha, const double* gout, double* g_lengthscale, double* g_variance,
+                     double* g_obs_stddev, double* g_mean_const);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPJAX_B200_H */

@@ -1,0 +1,311 @@
+// HOST MODEL of gpjax_b200/csrc/primitives.h -- TEST INFRASTRUCTURE ONLY.
+//
+// Plain C++ loops with the same argument semantics as the CUDA launchers, operating on host
+// pointers and ignoring the stream.  Linked with the *product's* algorithms.cpp/abi.cpp into
+// tests/hostsim/libgpjax_b200_hostsim.so so the CPU test-suite can check the blocked-algorithm
+// orchestration (block indexing, masks, workspace carving, K-range hints) against the oracle
+// without a GPU.  It is never shipped, never loaded by gpjax_b200, and is not a fallback.
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <vector>
+#include "../../gpjax_b200/csrc/primitives.h"
+
+namespace gpb {
+
+static inline double elemA(const GemmDesc& d, const double* A, int64_t m, int64_t k) {
+    return d.a_layout == LAYOUT_K ? A[m * d.lda + k] : A[k * d.lda + m];
+}
+static inline double elemB(const GemmDesc& d, const double* B, int64_t n, int64_t k) {
+    return d.b_layout == LAYOUT_K ? B[n * d.ldb + k] : B[k * d.ldb + n];
+}
+static inline bool keep(const GemmDesc& d, int64_t r, int64_t c) {
+    switch (d.mask) {
+        case MASK_LOWER: return r >= c;
+        case MASK_UPPER: return r <= c;
+        case MASK_BLOCK_STRICT_UPPER: return (r / d.mask_nb) < (c / d.mask_nb);
+        case MASK_BLOCK_STRICT_LOWER: return (r / d.mask_nb) > (c / d.mask_nb);
+        default: return true;
+    }
+}
+
+int gemm(stream_t, const GemmDesc& d) {
+    if (d.M < 0 || d.N < 0 || d.K < 0) return GPB_ERR_INVALID;
+    // Same tile geometry as the CUDA kernel so the K-range hints are exercised identically:
+    // a hint that would skip a physically non-zero element shows up as a wrong answer here too.
+    const int64_t BM = 128, BN = 64, BK = 16;
+    for (int b = 0; b < d.batch; ++b) {
+        const double* A = d.A + b * d.strideA;
+        const double* B = d.B + b * d.strideB;
+        double* C = d.C + b * d.strideC;
+        for (int64_t m0 = 0; m0 < d.M; m0 += BM)
+            for (int64_t n0 = 0; n0 < d.N; n0 += BN) {
+                int64_t mend = std::min(m0 + BM, d.M), nend = std::min(n0 + BN, d.N);
+                int64_t kbeg = 0, kend = d.K;
+                if (d.krange == KR_B_LOWER) kend = std::min(d.K, nend + d.kr_off);
+                else if (d.krange == KR_B_UPPER) kbeg = std::max<int64_t>(0, n0 + d.kr_off);
+                else if (d.krange == KR_A_LOWER) kend = std::min(d.K, mend + d.kr_off);
+                else if (d.krange == KR_A_UPPER) kbeg = std::max<int64_t>(0, m0 + d.kr_off);
+                kbeg = (kbeg / BK) * BK;
+                if (kend < kbeg) kend = kbeg;
+                for (int64_t m = m0; m < mend; ++m)
+                    for (int64_t n = n0; n < nend; ++n) {
+                        if (!keep(d, d.mask_row0 + m, d.mask_col0 + n)) continue;
+                        double acc = 0.0;
+                        for (int64_t k = kbeg; k < kend; ++k) acc += elemA(d, A, m, k) * elemB(d, B, n, k);
+                        double v = d.alpha * acc;
+                        if (d.beta != 0.0) v += d.beta * C[m * d.ldc + n];
+                        C[m * d.ldc + n] = v;
+                    }
+            }
+    }
+    return GPB_OK;
+}
+
+static double profile(int kind, double r2, double var) {
+    if (kind == KIND_RBF) return var * std::exp(-0.5 * r2);
+    double tau = std::sqrt(std::fmax(r2, 1e-36));
+    if (kind == KIND_MATERN32) return var * (1.0 + std::sqrt(3.0) * tau) * std::exp(-std::sqrt(3.0) * tau);
+    return var * (1.0 + std::sqrt(5.0) * tau + 5.0 / 3.0 * tau * tau) * std::exp(-std::sqrt(5.0) * tau);
+}
+static double dprofile(int kind, double r2, double var, double k) {
+    if (kind == KIND_RBF) return -0.5 * k;
+    if (!(r2 > 1e-36)) return 0.0;
+    double tau = std::sqrt(r2);
+    if (kind == KIND_MATERN32) return -1.5 * var * std::exp(-std::sqrt(3.0) * tau);
+    return -(5.0 / 6.0) * var * (1.0 + std::sqrt(5.0) * tau) * std::exp(-std::sqrt(5.0) * tau);
+}
+static double r2_of(const double* x, const double* z, int D, const double* ell, int iso) {
+    double r2 = 0.0;
+    for (int d = 0; d < D; ++d) {
+        double l = ell[iso ? 0 : d];
+        double a = x[d] / l - z[d] / l;
+        r2 += a * a;
+    }
+    return r2;
+}
+
+int max_input_dim() { return 64; }
+
+int gram(stream_t, const GramDesc& d) {
+    if (d.N < 0 || d.M < 0 || d.D <= 0) return GPB_ERR_INVALID;
+    if (d.D > 64) return GPB_ERR_UNSUPPORTED;
+    double var = d.variance[0];
+    double dadd = d.diag_add + (d.diag_add_sq ? d.diag_add_sq[0] * d.diag_add_sq[0] : 0.0);
+    const int64_t TR = 64, TC = 128;
+    for (int64_t i = 0; i < d.N; ++i)
+        for (int64_t j = 0; j < d.M; ++j) {
+            if (d.lower_only) {  // tile-level skip, as on the device
+                int64_t r0 = (i / TR) * TR, c0 = (j / TC) * TC;
+                if (d.row0 + std::min(r0 + TR, d.N) - 1 < d.col0 + c0) continue;
+            }
+            double k = profile(d.kind, r2_of(d.X + i * d.ldx, d.Z + j * d.ldz, d.D, d.ell, d.ell_is_scalar), var);
+            if (d.row0 + i == d.col0 + j) k += dadd;
+            d.K[i * d.ldk + j] = k;
+        }
+    return GPB_OK;
+}
+
+int potrf_leaf(stream_t, int n, double* A, int64_t lda, double* Dinv, int64_t ldd, double* DinvT, int64_t lddt,
+               int* info, int64_t global_row0, int factor) {
+    if (n < 0 || n > 128) return GPB_ERR_INVALID;
+    std::vector<double> S((size_t)n * n, 0.0);
+    for (int r = 0; r < n; ++r)
+        for (int c = 0; c <= r; ++c) S[r * n + c] = A[r * lda + c];
+    int fail = 0;
+    if (factor) {
+        for (int j = 0; j < n && !fail; ++j) {
+            double dj = S[j * n + j];
+            if (!(dj > 0.0)) { fail = j + 1; break; }
+            double p = std::sqrt(dj), inv = 1.0 / p;
+            S[j * n + j] = p;
+            for (int i = j + 1; i < n; ++i) S[i * n + j] *= inv;
+            for (int i = j + 1; i < n; ++i)
+                for (int c = j + 1; c <= i; ++c) S[i * n + c] -= S[i * n + j] * S[c * n + j];
+        }
+    }
+    if (fail) {
+        double q = std::numeric_limits<double>::quiet_NaN();
+        if (info && *info == 0) *info = (int)(global_row0 + fail);
+        for (int r = 0; r < n; ++r)
+            for (int c = 0; c < n; ++c) {
+                if (c <= r) A[r * lda + c] = q;
+                if (Dinv) Dinv[r * ldd + c] = q;
+                if (DinvT) DinvT[r * lddt + c] = q;
+            }
+        return GPB_OK;
+    }
+    if (factor)
+        for (int r = 0; r < n; ++r)
+            for (int c = 0; c <= r; ++c) A[r * lda + c] = S[r * n + c];
+    // inverse by forward substitution on unit vectors
+    std::vector<double> X((size_t)n * n, 0.0);
+    for (int j = 0; j < n; ++j)
+        for (int i = j; i < n; ++i) {
+            double acc = (i == j) ? 1.0 : 0.0;
+            for (int k = j; k < i; ++k) acc -= S[i * n + k] * X[k * n + j];
+            X[i * n + j] = acc / S[i * n + i];
+        }
+    for (int r = 0; r < n; ++r)
+        for (int c = 0; c < n; ++c) {
+            if (Dinv) Dinv[r * ldd + c] = X[r * n + c];
+            if (DinvT) DinvT[r * lddt + c] = X[c * n + r];
+        }
+    return GPB_OK;
+}
+
+int gemv(stream_t, int64_t m, int64_t n, const double* A, int64_t lda, int trans, const double* x, double* y,
+         double alpha, double beta) {
+    if (!trans) {
+        for (int64_t i = 0; i < m; ++i) {
+            double s = 0.0;
+            for (int64_t j = 0; j < n; ++j) s += A[i * lda + j] * x[j];
+            y[i] = (beta == 0.0 ? 0.0 : beta * y[i]) + alpha * s;
+        }
+    } else {
+        for (int64_t j = 0; j < n; ++j) {
+            double s = 0.0;
+            for (int64_t i = 0; i < m; ++i) s += A[i * lda + j] * x[i];
+            y[j] = (beta == 0.0 ? 0.0 : beta * y[j]) + alpha * s;
+        }
+    }
+    return GPB_OK;
+}
+
+int sum_log_diag(stream_t, int64_t n, const double* A, int64_t lda, double* out) {
+    double s = 0.0;
+    for (int64_t i = 0; i < n; ++i) s += std::log(A[i * (lda + 1)]);
+    out[0] = s;
+    return GPB_OK;
+}
+int dot(stream_t, int64_t n, const double* x, const double* y, double* out) {
+    double s = 0.0;
+    for (int64_t i = 0; i < n; ++i) s += x[i] * y[i];
+    out[0] = s;
+    return GPB_OK;
+}
+int sub_scalar(stream_t, int64_t n, const double* a, const double* c, double* out) {
+    double cv = c ? c[0] : 0.0;
+    for (int64_t i = 0; i < n; ++i) out[i] = a[i] - cv;
+    return GPB_OK;
+}
+int copy2d(stream_t, int64_t rows, int64_t cols, const double* src, int64_t lds, double* dst, int64_t ldd) {
+    for (int64_t i = 0; i < rows; ++i) std::memmove(dst + i * ldd, src + i * lds, (size_t)cols * sizeof(double));
+    return GPB_OK;
+}
+int transpose2d(stream_t, int64_t rows, int64_t cols, const double* src, int64_t lds, double* dst, int64_t ldd) {
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) dst[j * ldd + i] = src[i * lds + j];
+    return GPB_OK;
+}
+int fill2d(stream_t, int64_t rows, int64_t cols, double* p, int64_t ld, double v) {
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) p[i * ld + j] = v;
+    return GPB_OK;
+}
+int zero_triangle(stream_t, int64_t n, double* A, int64_t lda, int uplo) {
+    for (int64_t r = 0; r < n; ++r)
+        for (int64_t c = 0; c < n; ++c)
+            if ((uplo == 2 && c > r) || (uplo == 1 && c < r)) A[r * lda + c] = 0.0;
+    return GPB_OK;
+}
+int symmetrize(stream_t, int64_t n, double* A, int64_t lda, int from_lower) {
+    for (int64_t r = 0; r < n; ++r)
+        for (int64_t c = 0; c < r; ++c) {
+            if (from_lower) A[c * lda + r] = A[r * lda + c];
+            else A[r * lda + c] = A[c * lda + r];
+        }
+    return GPB_OK;
+}
+int mll_value(stream_t, int64_t n, const double* half_logdet, const double* quad, const int* info, double* out) {
+    double v = -0.5 * ((double)n * std::log(2.0 * M_PI) + 2.0 * half_logdet[0] + quad[0]);
+    if (info && info[0] != 0) v = std::numeric_limits<double>::quiet_NaN();
+    out[0] = v;
+    return GPB_OK;
+}
+
+int64_t mll_bwd_partials_count(int64_t N, int D, int64_t) {
+    int DC = D <= 2 ? 2 : (D <= 4 ? 4 : 8);
+    int Dp = (D + DC - 1) / DC * DC;
+    return ((N + 63) / 64) * ((N + 127) / 128) * (Dp + 2);
+}
+
+int mll_bwd(stream_t, const MllBwdDesc& d) {
+    if (d.nb <= 0 || d.nb % 128 != 0) return GPB_ERR_INVALID;
+    const int64_t N = d.N;
+    const double var = d.variance[0];
+    std::vector<double> acc(d.D, 0.0);
+    double wk = 0.0, trw = 0.0;
+    for (int64_t r = 0; r < N; ++r)
+        for (int64_t c = 0; c < N; ++c) {
+            int64_t br = r / d.nb, bc = c / d.nb;
+            if (br > bc) continue;
+            double sv, wgt;
+            if (br == bc) { sv = d.Sdiag[br * d.nb * d.nb + (r - br * d.nb) * d.nb + (c - br * d.nb)]; wgt = 1.0; }
+            else { sv = d.S[r * d.lds + c]; wgt = 2.0; }
+            double w = 0.5 * (d.alpha[r] * d.alpha[c] - sv);
+            if (r == c) trw += w;
+            w *= wgt;
+            double r2 = r2_of(d.X + r * d.ldx, d.X + c * d.ldx, d.D, d.ell, d.ell_is_scalar);
+            double k = profile(d.kind, r2, var), dk = dprofile(d.kind, r2, var, k);
+            wk += w * k;
+            for (int dd = 0; dd < d.D; ++dd) {
+                double l = d.ell[d.ell_is_scalar ? 0 : dd];
+                double a = d.X[r * d.ldx + dd] / l - d.X[c * d.ldx + dd] / l;
+                acc[dd] += w * dk * a * a;
+            }
+        }
+    double g = d.gout ? d.gout[0] : 1.0;
+    if (d.g_ell) {
+        if (d.ell_is_scalar) {
+            double s = 0.0;
+            for (int dd = 0; dd < d.D; ++dd) s += g * (-2.0 / d.ell[0]) * acc[dd];
+            d.g_ell[0] = s;
+        } else
+            for (int dd = 0; dd < d.D; ++dd) d.g_ell[dd] = g * (-2.0 / d.ell[dd]) * acc[dd];
+    }
+    if (d.g_var) d.g_var[0] = g * wk / var;
+    if (d.g_obs_stddev) d.g_obs_stddev[0] = g * 2.0 * d.obs_stddev[0] * trw;
+    if (d.g_mean) {
+        double s = 0.0;
+        for (int64_t i = 0; i < N; ++i) s += d.alpha[i];
+        d.g_mean[0] = g * s;
+    }
+    return GPB_OK;
+}
+
+int64_t gram_bwd_partials_count(int64_t N, int64_t M, int D) {
+    int DC = D <= 2 ? 2 : (D <= 4 ? 4 : 8);
+    int Dp = (D + DC - 1) / DC * DC;
+    return ((N + 63) / 64) * ((M + 127) / 128) * (Dp + 1);
+}
+
+int gram_bwd(stream_t, const GramBwdDesc& d) {
+    const double var = d.variance[0];
+    std::vector<double> acc(d.D, 0.0);
+    double wk = 0.0;
+    for (int64_t r = 0; r < d.N; ++r)
+        for (int64_t c = 0; c < d.M; ++c) {
+            double w = d.dK[r * d.lddk + c];
+            double r2 = r2_of(d.X + r * d.ldx, d.Z + c * d.ldz, d.D, d.ell, d.ell_is_scalar);
+            double k = profile(d.kind, r2, var), dk = dprofile(d.kind, r2, var, k);
+            wk += w * k;
+            for (int dd = 0; dd < d.D; ++dd) {
+                double l = d.ell[d.ell_is_scalar ? 0 : dd];
+                double a = d.X[r * d.ldx + dd] / l - d.Z[c * d.ldz + dd] / l;
+                acc[dd] += w * dk * a * a;
+                if (d.g_X) d.g_X[r * d.ldgx + dd] += d.scale * 2.0 * w * dk * a / l;
+                if (d.g_Z) d.g_Z[c * d.ldgz + dd] -= d.scale * 2.0 * w * dk * a / l;
+            }
+        }
+    if (d.g_ell) {
+        if (d.ell_is_scalar) {
+            for (int dd = 0; dd < d.D; ++dd) d.g_ell[0] += d.scale * (-2.0 / d.ell[0]) * acc[dd];
+        } else
+            for (int dd = 0; dd < d.D; ++dd) d.g_ell[dd] += d.scale * (-2.0 / d.ell[dd]) * acc[dd];
+    }
+    if (d.g_var) d.g_var[0] += d.scale * wk / var;
+    return GPB_OK;
+}
+
+}  // namespace gpb

@@ -1,0 +1,106 @@
+"""conjugate_mll value + gradient on the GPU vs the CPU oracle (reference formulation: LU slogdet/solve,
+reverse-mode autodiff).  Tolerance: 1e-8 relative (north-star), Gram 1e-12 is covered elsewhere."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as o
+
+pytestmark = pytest.mark.gpu
+KINDS = [(0, "rbf"), (1, "matern32"), (2, "matern52")]
+TOL = 1e-8
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+def make_data(n, d, seed):
+    """tests/test_objectives.py:25-44 of the reference, re-seeded with NumPy."""
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-2.0, 2.0, (n, d))
+    y = np.sin(X[:, :1]) + 0.1 * rng.standard_normal((n, 1))
+    return X, y
+
+
+def run_gpu(kind, X, y, ell, var, sn, c, jitter=1e-6):
+    from gpjax_b200 import ops
+
+    p = {k: dev(v).requires_grad_(True) for k, v in dict(ell=ell, var=var, sn=sn).items()}
+    mean = None if c is None else dev(c).requires_grad_(True)
+    val = ops.conjugate_mll_fused(kind, dev(X), dev(y), p["ell"], p["var"], p["sn"], mean, jitter)
+    val.backward()
+    g = dict(lengthscale=p["ell"].grad.cpu().numpy(), variance=p["var"].grad.item(), obs_stddev=p["sn"].grad.item())
+    if mean is not None:
+        g["mean_const"] = mean.grad.item()
+    return val.item(), g
+
+
+@pytest.mark.parametrize("kind,name", KINDS)
+@pytest.mark.parametrize("n,d,iso", [(1, 1, True), (2, 2, False), (10, 3, False), (100, 1, True), (300, 8, False),
+                                     (777, 2, False)])
+def test_mll_small_vs_autodiff_oracle(kind, name, n, d, iso):
+    X, y = make_data(n, d, 100 + n)
+    ell = np.array(0.9) if iso else np.linspace(0.8, 1.6, d)
+    ref, gref = o.conjugate_mll_value_and_grad_autodiff(name, X, y, ell, 1.2, 0.3, 0.1)
+    val, g = run_gpu(kind, X, y, ell, 1.2, 0.3, 0.1)
+    assert abs(val - ref) <= TOL * abs(ref)
+    for k in ("lengthscale", "variance", "obs_stddev", "mean_const"):
+        scale = max(np.max(np.abs(np.asarray(gref[k]))), 1e-3 * abs(ref))
+        assert np.max(np.abs(np.asarray(g[k]).reshape(np.shape(gref[k])) - np.asarray(gref[k]))) <= TOL * scale, k
+
+
+@pytest.mark.parametrize("kind,name", KINDS)
+def test_mll_config1_shape(kind, name):
+    """BASELINE config 1: N=1000, D=1, scalar lengthscale, Zero mean."""
+    X, y = make_data(1000, 1, 123)
+    ref = o.conjugate_mll(name, X, y, 1.0, 1.0, 0.3, 0.0)
+    gref = o.conjugate_mll_grad_closed_form(name, X, y, 1.0, 1.0, 0.3, 0.0)
+    val, g = run_gpu(kind, X, y, np.array(1.0), 1.0, 0.3, None)
+    assert abs(val - ref) <= TOL * abs(ref)
+    for k in ("lengthscale", "variance", "obs_stddev"):
+        assert rel(np.asarray(g[k]).reshape(()), gref[k]) <= TOL, k
+
+
+@pytest.mark.parametrize("kind,name,n", [(2, "matern52", 3000), (0, "rbf", 4096)])
+def test_mll_medium_vs_closed_form_oracle(kind, name, n):
+    X, y = make_data(n, 8, 20)
+    ell = np.linspace(0.8, 1.6, 8)
+    ref = o.conjugate_mll(name, X, y, ell, 1.0, 0.3, 0.0)
+    gref = o.conjugate_mll_grad_closed_form(name, X, y, ell, 1.0, 0.3, 0.0)
+    val, g = run_gpu(kind, X, y, ell, 1.0, 0.3, 0.0)
+    assert abs(val - ref) <= TOL * abs(ref)
+    for k in ("lengthscale", "variance", "obs_stddev", "mean_const"):
+        scale = np.max(np.abs(np.asarray(gref[k])))
+        assert np.max(np.abs(np.asarray(g[k]).reshape(np.shape(gref[k])) - np.asarray(gref[k]))) <= TOL * scale, k
+
+
+def test_mll_upstream_cotangent_and_repeat():
+    """Composes with user lambdas (negation / scaling, examples/regression.py:200) and is repeatable."""
+    from gpjax_b200 import ops
+
+    X, y = make_data(500, 3, 7)
+    ell = dev(np.array([0.9, 1.0, 1.1])).requires_grad_(True)
+    var, sn = dev(1.0).requires_grad_(True), dev(0.3).requires_grad_(True)
+    v1 = ops.conjugate_mll_fused(0, dev(X), dev(y), ell, var, sn, None, 1e-6)
+    (-2.0 * v1).backward()
+    g1 = ell.grad.clone()
+    ell.grad = None
+    v2 = ops.conjugate_mll_fused(0, dev(X), dev(y), ell, var, sn, None, 1e-6)
+    v2.backward()
+    assert torch.allclose(g1, -2.0 * ell.grad, rtol=1e-12, atol=0)
+    assert v1.item() == v2.item()
+
+
+def test_mll_not_pd_returns_nan():
+    from gpjax_b200 import ops
+
+    X = np.zeros((300, 2))  # all rows identical, zero noise, zero jitter -> singular
+    y = np.zeros((300, 1))
+    v = ops.conjugate_mll_fused(0, dev(X), dev(y), dev(np.array([1.0, 1.0])), dev(1.0), dev(0.0), None, 0.0)
+    assert np.isnan(v.item())
