@@ -41,7 +41,7 @@ struct GemmParams {
     int krange;
     int64_t kr_off;
     int64_t strideA, strideB, strideC;
-    int64_t tiles_n;
+    int64_t tiles_m, tiles_n;
     int a_vec16, b_vec16, c_vec16;
 };
 
@@ -108,6 +108,41 @@ __device__ __forceinline__ bool mask_keep(int mask, int64_t r, int64_t c, int64_
     }
 }
 
+
+__host__ __device__ inline int64_t floor_div(int64_t a, int64_t b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return -floor_div(-a, b); }
+
+// Column-tile range [lo, hi) of tile-row `tm` that can contain live (unmasked) elements.  May be a
+// slight over-estimate at the ragged last column tile; the kernel re-checks liveness exactly.
+template <int BM, int BN>
+__host__ __device__ inline void live_range(const GemmParams& p, int64_t tm, int64_t& lo, int64_t& hi) {
+    lo = 0;
+    hi = p.tiles_n;
+    if (p.mask == MASK_NONE) return;
+    const int64_t rend = (tm + 1) * BM < p.M ? (tm + 1) * BM : p.M;
+    const int64_t rmin = p.mask_row0 + tm * BM, rmax = p.mask_row0 + rend - 1;
+    int64_t t;
+    switch (p.mask) {
+        case MASK_LOWER:  // live iff rmax >= mask_col0 + tn*BN
+            t = floor_div(rmax - p.mask_col0, BN) + 1;
+            hi = t < 0 ? 0 : (t < hi ? t : hi);
+            break;
+        case MASK_UPPER:  // live iff rmin <= mask_col0 + (tn+1)*BN - 1
+            t = ceil_div(rmin - p.mask_col0 + 1, BN) - 1;
+            lo = t < 0 ? 0 : (t < hi ? t : hi);
+            break;
+        case MASK_BLOCK_STRICT_UPPER:  // live iff (rmin/nb + 1)*nb <= mask_col0 + (tn+1)*BN - 1
+            t = ceil_div((rmin / p.mask_nb + 1) * p.mask_nb - p.mask_col0 + 1, BN) - 1;
+            lo = t < 0 ? 0 : (t < hi ? t : hi);
+            break;
+        case MASK_BLOCK_STRICT_LOWER:  // live iff mask_col0 + tn*BN < (rmax/nb)*nb
+            t = ceil_div((rmax / p.mask_nb) * p.mask_nb - p.mask_col0, BN);
+            hi = t < 0 ? 0 : (t < hi ? t : hi);
+            break;
+        default: break;
+    }
+}
+
 template <int BM, int BN, int WM, int WN, int ALAY, int BLAY>
 __global__ void __launch_bounds__(NTHREADS, 2) gemm_f64_kernel(const GemmParams p) {
     constexpr int WARPS_N = BN / WN;
@@ -123,26 +158,57 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_f64_kernel(const GemmParams 
     const int wm0 = (warp / WARPS_N) * WM;
     const int wn0 = (warp % WARPS_N) * WN;
 
-    const int64_t tile_m = blockIdx.x / p.tiles_n;
-    const int64_t tile_n = blockIdx.x % p.tiles_n;
+    // Tile enumeration without dead CTAs: tile-row y is folded with tile-row T-1-y (their live
+    // column counts add up to ~const for triangular masks), blockIdx.x walks both live ranges.
+    int64_t tile_m = blockIdx.y, tile_n;
+    {
+        int64_t lo, hi, x = blockIdx.x;
+        live_range<BM, BN>(p, tile_m, lo, hi);
+        if (x < hi - lo) {
+            tile_n = lo + x;
+        } else {
+            x -= hi - lo;
+            const int64_t t2 = p.tiles_m - 1 - tile_m;
+            if (t2 == tile_m) return;
+            tile_m = t2;
+            live_range<BM, BN>(p, tile_m, lo, hi);
+            if (x >= hi - lo) return;
+            tile_n = lo + x;
+        }
+    }
     const int64_t m0 = tile_m * BM, n0 = tile_n * BN;
     const int64_t mend = min(m0 + (int64_t)BM, p.M), nend = min(n0 + (int64_t)BN, p.N);
 
-    // ---- tile-level mask: skip tiles with no live element -------------------------------
+    // ---- tile-level mask: skip dead tiles, detect fully-live ("interior") tiles ---------------
+    bool interior = (m0 + BM <= p.M) && (n0 + BN <= p.N) && (p.c_vec16 != 0);
     if (p.mask != MASK_NONE) {
         int64_t rmin = p.mask_row0 + m0, rmax = p.mask_row0 + mend - 1;
         int64_t cmin = p.mask_col0 + n0, cmax = p.mask_col0 + nend - 1;
-        bool live = true;
-        if (p.mask == MASK_LOWER) live = rmax >= cmin;
-        else if (p.mask == MASK_UPPER) live = rmin <= cmax;
-        else if (p.mask == MASK_BLOCK_STRICT_UPPER) live = (rmin / p.mask_nb) < (cmax / p.mask_nb);
-        else if (p.mask == MASK_BLOCK_STRICT_LOWER) live = (rmax / p.mask_nb) > (cmin / p.mask_nb);
+        bool live = true, full = true;
+        if (p.mask == MASK_LOWER) { live = rmax >= cmin; full = rmin >= cmax; }
+        else if (p.mask == MASK_UPPER) { live = rmin <= cmax; full = rmax <= cmin; }
+        else if (p.mask == MASK_BLOCK_STRICT_UPPER) {
+            live = (rmin / p.mask_nb) < (cmax / p.mask_nb);
+            full = (rmax / p.mask_nb) < (cmin / p.mask_nb);
+        } else if (p.mask == MASK_BLOCK_STRICT_LOWER) {
+            live = (rmax / p.mask_nb) > (cmin / p.mask_nb);
+            full = (rmin / p.mask_nb) > (cmax / p.mask_nb);
+        }
         if (!live) return;
+        interior = interior && full;
     }
 
-    const double* A = p.A + (int64_t)blockIdx.y * p.strideA;
-    const double* B = p.B + (int64_t)blockIdx.y * p.strideB;
-    double* C = p.C + (int64_t)blockIdx.y * p.strideC;
+    const double* A = p.A + (int64_t)blockIdx.z * p.strideA;
+    const double* B = p.B + (int64_t)blockIdx.z * p.strideB;
+    double* C = p.C + (int64_t)blockIdx.z * p.strideC;
+    if (p.beta != 0.0) {
+        // pull the C tile towards L2 while the main loop runs: 128 rows x 512 B = 4 lines per row
+        for (int id = tid; id < BM * (BN / 16); id += NTHREADS) {
+            int r = id / (BN / 16), q = id % (BN / 16);
+            if (m0 + r < p.M && n0 + q * 16 < p.N)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(C + (m0 + r) * p.ldc + n0 + q * 16));
+        }
+    }
 
     // ---- K range (triangular operands: structural zeros must be physically zero) ---------
     int64_t kbeg = 0, kend = p.K;
@@ -211,8 +277,43 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_f64_kernel(const GemmParams 
 
     // ---- epilogue ------------------------------------------------------------------------
     const double alpha = p.alpha, beta = p.beta;
-    const bool cvec = p.c_vec16 != 0;
+    if (interior) {
+        // Fast path (tile fully inside the matrix and the mask, 16-byte aligned rows): all C loads
+        // of a half-tile are issued back to back (one memory round trip per half instead of one per
+        // 8x8 fragment), then blended and stored as 128-bit words.
+        double* cbase = C + (m0 + wm0 + fr) * p.ldc + (n0 + wn0 + fc * 2);
+        if (beta != 0.0) {
+#pragma unroll
+            for (int h = 0; h < TM; h += 2) {
+                double2 old[2][TN];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j)
+                        old[i][j] = *reinterpret_cast<const double2*>(cbase + (int64_t)(h + i) * 8 * p.ldc + j * 8);
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) {
+                        double2 v;
+                        v.x = fma(beta, old[i][j].x, alpha * acc[h + i][j][0]);
+                        v.y = fma(beta, old[i][j].y, alpha * acc[h + i][j][1]);
+                        *reinterpret_cast<double2*>(cbase + (int64_t)(h + i) * 8 * p.ldc + j * 8) = v;
+                    }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j)
+                    *reinterpret_cast<double2*>(cbase + (int64_t)i * 8 * p.ldc + j * 8) =
+                        make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
+        }
+        return;
+    }
+    // Generic path: bounds, element masks, unaligned rows.
     const bool use_mask = p.mask != MASK_NONE;
+    const bool cvec = p.c_vec16 != 0;
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
         int64_t row = m0 + wm0 + i * 8 + fr;
@@ -232,17 +333,17 @@ __global__ void __launch_bounds__(NTHREADS, 2) gemm_f64_kernel(const GemmParams 
                 double2* ptr = reinterpret_cast<double2*>(crow + col);
                 if (beta != 0.0) {
                     double2 old = *ptr;
-                    v0 += beta * old.x;
-                    v1 += beta * old.y;
+                    v0 = fma(beta, old.x, v0);
+                    v1 = fma(beta, old.y, v1);
                 }
                 *ptr = make_double2(v0, v1);
             } else {
                 if (ok0) {
-                    if (beta != 0.0) v0 += beta * crow[col];
+                    if (beta != 0.0) v0 = fma(beta, crow[col], v0);
                     crow[col] = v0;
                 }
                 if (ok1) {
-                    if (beta != 0.0) v1 += beta * crow[col + 1];
+                    if (beta != 0.0) v1 = fma(beta, crow[col + 1], v1);
                     crow[col + 1] = v1;
                 }
             }
@@ -263,11 +364,23 @@ int launch_gemm(cudaStream_t st, const GemmParams& p, int batch) {
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         configured = true;
     }
-    int64_t tiles_m = (p.M + BM - 1) / BM;
-    int64_t ntiles = tiles_m * p.tiles_n;
-    if (ntiles <= 0 || batch <= 0) return GPB_OK;
-    if (ntiles > 2147483647LL || batch > 65535) return GPB_ERR_UNSUPPORTED;
-    dim3 grid((unsigned)ntiles, (unsigned)batch, 1);
+    const int64_t T = p.tiles_m;
+    if (T <= 0 || p.tiles_n <= 0 || batch <= 0) return GPB_OK;
+    const int64_t gy = (T + 1) / 2;
+    int64_t gx = 0;
+    for (int64_t y = 0; y < gy; ++y) {
+        int64_t lo, hi;
+        live_range<BM, BN>(p, y, lo, hi);
+        int64_t c = hi - lo;
+        if (T - 1 - y != y) {
+            live_range<BM, BN>(p, T - 1 - y, lo, hi);
+            c += hi - lo;
+        }
+        if (c > gx) gx = c;
+    }
+    if (gx == 0) return GPB_OK;
+    if (gx > 2147483647LL || gy > 65535 || batch > 65535) return GPB_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)batch);
     kern<<<grid, NTHREADS, smem, st>>>(p);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
@@ -288,6 +401,7 @@ int gemm(stream_t s, const GemmDesc& d) {
     p.mask_nb = d.mask_nb > 0 ? d.mask_nb : 1;
     p.krange = d.krange; p.kr_off = d.kr_off;
     p.strideA = d.strideA; p.strideB = d.strideB; p.strideC = d.strideC;
+    p.tiles_m = (d.M + BM - 1) / BM;
     p.tiles_n = (d.N + BN - 1) / BN;
     auto al16 = [](const void* ptr, int64_t ld, int64_t stride) {
         return ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0) && (ld % 2 == 0) && (stride % 2 == 0);

@@ -76,3 +76,24 @@ def normal(k, shape):
     lo = np.nextafter(np.float64(-1.0), np.float64(0.0))
     u = uniform(k, shape, lo, 1.0)
     return np.sqrt(2.0) * erfinv(u)
+
+
+# ---- the pre-"partitionable" stream (jax < 0.5 default), which the reference's stored goldens use ----
+def _threefry_original(k, counts):
+    counts = np.asarray(counts, np.uint64)
+    n = len(counts)
+    if n % 2:
+        counts = np.concatenate([counts, np.zeros(1, np.uint64)])
+    h = len(counts) // 2
+    a, b = threefry2x32(k[0], k[1], counts[:h], counts[h:])
+    return np.concatenate([a, b])[:n]
+
+
+def split_original(k, num: int = 2):
+    out = _threefry_original(k, np.arange(2 * num)).reshape(num, 2)
+    return [(int(r[0]), int(r[1])) for r in out]
+
+
+def random_bits64_original(k, n: int):
+    out = _threefry_original(k, np.arange(2 * n))
+    return (out[:n] << np.uint64(32)) | out[n:]

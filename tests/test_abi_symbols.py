@@ -1,0 +1,82 @@
+"""The C-ABI library loads and exports exactly what include/gpjax_b200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+from gpjax_b200 import _abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "gpjax_b200.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gpb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_matches_python_prototypes():
+    assert header_functions() == sorted(_abi.PROTOTYPES)
+
+
+def test_header_argument_counts_match_prototypes():
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for name, (_, args) in _abi.PROTOTYPES.items():
+        m = re.search(r"\b" + name + r"\s*\((.*?)\)\s*;", src, flags=re.S)
+        assert m, name
+        params = m.group(1).strip()
+        n = 0 if params in ("void", "") else len(params.split(","))
+        assert n == len(args), f"{name}: header has {n} parameters, _abi.py declares {len(args)}"
+
+
+@pytest.fixture(scope="module")
+def cuda_lib_path():
+    from gpjax_b200.build import build
+
+    return build()
+
+
+def test_cuda_library_exports_every_declared_symbol(cuda_lib_path):
+    out = subprocess.run(["nm", "-D", "--defined-only", cuda_lib_path], capture_output=True, text=True, check=True).stdout
+    exported = set(re.findall(r" T (gpb_[a-z0-9_]+)", out))
+    assert exported == set(header_functions())
+
+
+def test_cuda_library_loads_and_answers_queries(cuda_lib_path):
+    lib = _abi.declare(ctypes.CDLL(cuda_lib_path))
+    assert b"sm_100a" in lib.gpb_version()
+    assert lib.gpb_block_size() == 256
+    assert lib.gpb_max_input_dim() >= 16
+    assert lib.gpb_mll_workspace_bytes(50000, 8) > 0
+    assert lib.gpb_factor_workspace_bytes(1000, 1, 0) < lib.gpb_factor_workspace_bytes(1000, 1, 1)
+
+
+def test_cuda_library_is_sm100a_with_dmma(cuda_lib_path):
+    """The shipped kernels are sm_100a SASS and the GEMM really issues FP64 tensor-core MMAs."""
+    out = subprocess.run(["cuobjdump", "-lelf", cuda_lib_path], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    obj = os.path.join(os.path.dirname(cuda_lib_path), "obj", "gemm_f64.o")
+    sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+    assert sass.count("DMMA.8x8x4") >= 64 and "LDGSTS" in sass
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "gpjax_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".h", ".cuh")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "hostsim" not in txt or f in ("primitives.h", "algorithms.h"), f
+
+
+def test_missing_extension_fails_loudly(monkeypatch, tmp_path):
+    from gpjax_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_LIB", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_lib.ExtensionMissingError):
+        _lib.lib()

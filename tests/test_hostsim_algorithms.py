@@ -1,0 +1,144 @@
+"""CPU check of the product's blocked-algorithm orchestration + C ABI (gpjax_b200/csrc/algorithms.cpp,
+sgpr.cpp, abi.cpp) linked against a plain C++ host model of the device primitives
+(tests/hostsim/primitives_host.cpp).  The CUDA kernels themselves are checked by the -m gpu tests."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+import oracle as o
+from gpjax_b200 import _abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KINDS = [(0, "rbf"), (1, "matern32"), (2, "matern52")]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    hs = os.path.join(HERE, "hostsim")
+    subprocess.run(["make", "-s", "-C", hs], check=True)
+    return _abi.declare(C.CDLL(os.path.join(hs, "libgpjax_b200_hostsim.so")))
+
+
+def p(a):
+    return None if a is None else a.ctypes.data
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+def data(n, d, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-2, 2, (n, d))
+    y = np.sin(X[:, 0]) + 0.1 * rng.standard_normal(n)
+    return X, y
+
+
+@pytest.mark.parametrize("kind,name", KINDS)
+@pytest.mark.parametrize("N,D,iso", [(1, 1, True), (100, 3, False), (256, 2, False), (300, 3, False), (513, 1, True),
+                                     (700, 8, False)])
+def test_mll_forward_backward(lib, kind, name, N, D, iso):
+    X, y = data(N, D, N + D)
+    ell = np.array([0.9]) if iso else np.linspace(0.8, 1.6, D)
+    var, sn, c = np.array([1.3]), np.array([0.4]), np.array([0.2])
+    nbytes = lib.gpb_mll_workspace_bytes(N, D)
+    ws = np.zeros(nbytes // 8 + 8)
+    Sig = np.full((N, N), np.nan)
+    val, alpha, info = np.zeros(1), np.zeros(N), np.zeros(1, np.int32)
+    rc = lib.gpb_mll_forward(None, kind, N, D, p(X), D, p(y), p(ell), int(iso), p(var), p(sn), p(c), 1e-6, p(Sig), N,
+                             p(ws), nbytes, p(val), p(alpha), p(info))
+    assert rc == 0 and info[0] == 0
+    ellv = ell[0] if iso else ell
+    ref = o.conjugate_mll(name, X, y, ellv, var[0], sn[0], c[0])
+    assert abs(val[0] - ref) <= 1e-10 * abs(ref)
+    g_ell, g_var, g_sn, g_c = np.zeros(1 if iso else D), np.zeros(1), np.zeros(1), np.zeros(1)
+    gout = np.array([-2.0])
+    rc = lib.gpb_mll_backward(None, kind, N, D, p(X), D, p(ell), int(iso), p(var), p(sn), p(Sig), N, p(ws), nbytes,
+                              p(alpha), p(gout), p(g_ell), p(g_var), p(g_sn), p(g_c))
+    assert rc == 0
+    gr = o.conjugate_mll_grad_closed_form(name, X, y, ellv, var[0], sn[0], c[0])
+    tol = 1e-8
+    scale = max(np.max(np.abs(np.asarray(gr["lengthscale"]))), 1e-6)
+    assert np.max(np.abs(g_ell / -2.0 - gr["lengthscale"])) <= tol * scale
+    assert abs(g_var[0] / -2.0 - gr["variance"]) <= tol * max(abs(gr["variance"]), 1e-6 * abs(ref))
+    assert abs(g_sn[0] / -2.0 - gr["obs_stddev"]) <= tol * max(abs(gr["obs_stddev"]), 1e-6 * abs(ref))
+    assert abs(g_c[0] / -2.0 - gr["mean_const"]) <= tol * max(abs(gr["mean_const"]), 1e-6 * abs(ref))
+    # L survived the backward pass in the lower triangle
+    Lref = np.linalg.cholesky(o.gram(name, X, ellv, var[0]) + (1e-6 + sn[0] ** 2) * np.eye(N))
+    assert np.max(np.abs(np.tril(Sig) - Lref)) <= 1e-11 * np.abs(Lref).max()
+
+
+def test_mll_not_pd_sets_info_and_nan(lib):
+    N, D = 300, 2
+    X = np.zeros((N, D))
+    y = np.zeros(N)
+    ell, var, sn = np.ones(D), np.ones(1), np.zeros(1)
+    nbytes = lib.gpb_mll_workspace_bytes(N, D)
+    ws, Sig = np.zeros(nbytes // 8 + 8), np.zeros((N, N))
+    val, alpha, info = np.zeros(1), np.zeros(N), np.zeros(1, np.int32)
+    rc = lib.gpb_mll_forward(None, 0, N, D, p(X), D, p(y), p(ell), 0, p(var), p(sn), None, 0.0, p(Sig), N, p(ws),
+                             nbytes, p(val), p(alpha), p(info))
+    assert rc == 0 and info[0] == 2 and np.isnan(val[0])
+
+
+@pytest.mark.parametrize("n", [1, 5, 128, 129, 256, 257, 600])
+def test_factor_family(lib, n):
+    rng = np.random.default_rng(n)
+    X = rng.uniform(-2, 2, (n, 4))
+    S = o.gram("matern52", X, np.linspace(0.8, 1.4, 4), 1.0) + 0.09 * np.eye(n)
+    A = S.copy()
+    nbytes = lib.gpb_factor_workspace_bytes(n, 1, 1)
+    ws = np.zeros(nbytes // 8 + 8)
+    info = np.zeros(1, np.int32)
+    wsa = (p(ws), nbytes, n, 1, 1)
+    assert lib.gpb_potrf_lower(None, n, p(A), n, 1, *wsa, p(info)) == 0
+    Lref = np.linalg.cholesky(S)
+    assert np.max(np.abs(A - Lref)) <= 1e-12 * np.abs(Lref).max()
+    out = np.zeros(1)
+    assert lib.gpb_sum_log_diag(None, n, p(A), n, p(out)) == 0
+    assert abs(out[0] - np.log(np.diag(Lref)).sum()) <= 1e-12 * max(1, n)
+    b = rng.standard_normal(n)
+    for trans, Lm in ((0, Lref), (1, Lref.T)):
+        x = b.copy()
+        assert lib.gpb_trsv_lower(None, n, p(A), n, trans, p(x), *wsa) == 0
+        assert rel(x, sla.solve_triangular(Lm, b, lower=not trans)) <= 1e-9
+        T = min(n, 19)
+        Bm = rng.standard_normal((n, T))
+        Xm = Bm.copy()
+        assert lib.gpb_trsm_lower_left(None, n, T, p(A), n, trans, p(Xm), T, *wsa) == 0
+        assert np.max(np.abs(Lm @ Xm - Bm)) <= 1e-10 * n
+    # diag_inverses on a user-supplied factor reproduces the same workspace content
+    ws2 = np.zeros_like(ws)
+    assert lib.gpb_diag_inverses(None, n, p(A), n, p(ws2), nbytes, n, 1, 1) == 0
+    x1, x2 = b.copy(), b.copy()
+    lib.gpb_trsv_lower(None, n, p(A), n, 0, p(x1), *wsa)
+    lib.gpb_trsv_lower(None, n, p(A), n, 0, p(x2), p(ws2), nbytes, n, 1, 1)
+    assert rel(x2, x1) <= 1e-12
+    Sinv = np.zeros((n, n))
+    assert lib.gpb_potri_lower(None, n, p(A), n, p(Sinv), n, *wsa) == 0
+    assert np.max(np.abs(Sinv @ S - np.eye(n))) <= 1e-9
+
+
+def test_workspace_too_small_is_reported(lib):
+    n = 300
+    A = np.eye(n)
+    ws = np.zeros(16)
+    info = np.zeros(1, np.int32)
+    assert lib.gpb_potrf_lower(None, n, p(A), n, 1, p(ws), ws.nbytes, n, 1, 0, p(info)) == -4
+
+
+@pytest.mark.parametrize("kind,name", KINDS)
+def test_gram_and_gram_bwd_abi(lib, kind, name):
+    rng = np.random.default_rng(2)
+    N, M, D = 70, 150, 3
+    X, Z = rng.uniform(-2, 2, (N, D)), rng.uniform(-2, 2, (M, D))
+    ell, var = np.array([0.7, 1.0, 1.3]), np.array([1.2])
+    K = np.zeros((N, M))
+    assert lib.gpb_gram(None, kind, N, M, D, p(X), D, p(Z), D, p(ell), 0, p(var), 0.0, None, 0, p(K), M) == 0
+    assert rel(K, o.cross_covariance(name, X, Z, ell, var[0])) <= 1e-13
+    assert lib.gpb_gram(None, kind, N, M, 65, p(X), D, p(Z), D, p(ell), 0, p(var), 0.0, None, 0, p(K), M) == -2
