@@ -1,0 +1,454 @@
+#!/usr/bin/env python
+"""Benchmark of the GPJax hot path on B200 (driver contract: one JSON line on rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload auto|exact|sgpr]
+
+Headline (`value`): exact-GP ``conjugate_mll`` value+gradient evaluations per second at N=50,000, D=8,
+float64 (BASELINE.json metric; the configuration the metric is quoted on fits one GPU).  The exact
+path does not shard ("replicas only"), so ``--gpus N`` runs N independent replicas (weak
+scaling) -- and ALSO runs the path that does shard, SGPR ``collapsed_elbo`` at N=10M / M=2048 row-sharded
+over the ranks with an NCCL all-reduce, reported under the ``sgpr`` key (points/s, strong scaling).
+``--workload sgpr`` makes the SGPR number the main ``value`` instead.
+
+Timing: W warm-up steps, then exactly K steps between barrier + synchronize, CUDA events on the
+launching stream, MAX over ranks.  L2: every step streams a 20 GB (exact) / multi-GB (SGPR) working set,
+far beyond the 126 MB L2, so no explicit flush is needed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "exact-GP MLL+grad evals/s @N=50k fp64; SGPR ELBO points/s at 1/2/4/8 GPU"
+NOMINAL_FP64_TFLOPS = 128 * 148 * 1.965e9 / 1e12  # 128 flop/clk/SM x 148 SMs x 1.965 GHz = 37.2
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic data: X ~ U(-2,2)^{N x D}, y = sin(x0) + 0.1 eps, NumPy PCG64
+# ----------------------------------------------------------------------------------------------
+def synth(n, d, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-2.0, 2.0, (n, d))
+    y = np.sin(X[:, :1]) + 0.1 * rng.standard_normal((n, 1))
+    return X, y
+
+
+HYPER = dict(variance=1.0, obs_stddev=0.3, mean_const=0.0, jitter=1e-6)
+
+
+def ell_ard(d):
+    return np.linspace(0.8, 1.6, d)
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi in the background during the timed region)
+# ----------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])), smax.append(float(f[2])), power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port in the reference's operation order (jax absent)
+# ----------------------------------------------------------------------------------------------
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_exact_sample(n_target, d, budget_s=12.0):
+    """One MLL+grad evaluation of the reference formulation on a bounded sample, N^3-extrapolated."""
+    import oracle
+
+    def one(ns):
+        X, y = synth(ns, d, 50)
+        t0 = time.perf_counter()
+        oracle.reference_cpu_mll_value_and_grad("rbf", X, y, ell_ard(d), HYPER["variance"], HYPER["obs_stddev"],
+                                                HYPER["mean_const"], HYPER["jitter"])
+        return time.perf_counter() - t0
+
+    t_small = one(1500)
+    ns = int(min(8000, max(2000, 1500 * (budget_s / max(t_small, 1e-3)) ** (1 / 3))))
+    ns = (ns // 500) * 500
+    t = one(ns)
+    return {"n_sample": ns, "seconds": t, "evals_per_s_at_target": 1.0 / (t * (n_target / ns) ** 3)}
+
+
+def cpu_sgpr_sample(m, d, budget_rows=40000):
+    import oracle
+
+    X, y = synth(budget_rows, d, 4)
+    Z = synth(m, d, 5)[0]
+    t0 = time.perf_counter()
+    oracle.reference_cpu_elbo_value_and_grad("rbf", X, y, Z, ell_ard(d), HYPER["variance"], HYPER["obs_stddev"],
+                                             HYPER["mean_const"], HYPER["jitter"], block=8192)
+    t = time.perf_counter() - t0
+    return {"rows": budget_rows, "seconds": t, "points_per_s": budget_rows / t}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU formulation (oracle port; jax[cpu] cannot be installed
+    here: no jax/jaxlib wheels in /opt/wheelhouse, no network) on the box's host cores."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    n, d = env_int("GPB_BENCH_N", 50000), 8
+    cores = cpu_threads()
+    vals, ts = [], []
+    samp = None
+    for i in range(args.warmup + args.steps):
+        samp = cpu_exact_sample(n, d, budget_s=float(os.environ.get("GPB_REF_BUDGET_S", "10")))
+        if i >= args.warmup:
+            vals.append(samp["evals_per_s_at_target"])
+            ts.append(samp["seconds"])
+    v = float(np.mean(vals))
+    sample = (f"one MLL+grad (LU slogdet + LU solve + full inverse, reference operation order) at "
+              f"N={samp['n_sample']}, D={d} of the same synthetic data, {np.mean(ts):.2f} s per eval, "
+              f"N^3-extrapolated to N={n}")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "evals/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"exact_gp_conjugate_mll_value_and_grad_N{n}_D{d}_RBF_ARD", "N": n, "D": d},
+            "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+class Dist:
+    def __init__(self, n_gpus):
+        import torch
+
+        self.torch = torch
+        self.world = env_int("WORLD_SIZE", 1)
+        self.rank = env_int("RANK", 0)
+        self.local = env_int("LOCAL_RANK", 0)
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py (impl ours) needs a CUDA device: gpjax_b200 has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            import torch.distributed as dist
+
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+        else:
+            self.dist = None
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x: float) -> float:
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+
+def timed(D: Dist, step, warmup, steps):
+    torch = D.torch
+    for _ in range(warmup):
+        step()
+    D.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3
+    D.barrier()
+    return D.max_over_ranks(t)
+
+
+def measure_cublas_dgemm(D: Dist):
+    torch = D.torch
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=D.dev)
+    b = torch.randn(n, n, dtype=torch.float64, device=D.dev)
+    for _ in range(2):
+        a @ b
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        a @ b
+    e1.record()
+    torch.cuda.synchronize()
+    return 3 * 2 * n**3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+
+
+def bench_exact(D: Dist, args):
+    torch = D.torch
+    import gpjax_b200 as gpx
+    from gpjax_b200 import ops
+    from gpjax_b200._lib import lib
+    from gpjax_b200.parameters import NonNegativeReal, PositiveReal, Real
+
+    n, d = env_int("GPB_BENCH_N", 50000), 8
+    Xn, yn = synth(n, d, 50 + D.rank)
+    Xh, yh = torch.from_numpy(Xn).pin_memory(), torch.from_numpy(yn).pin_memory()
+    X, y = Xh.to(D.dev), yh.to(D.dev)
+    mk = lambda v: torch.as_tensor(np.asarray(v, np.float64), device=D.dev).requires_grad_(True)
+    ell, var, sn, c = mk(ell_ard(d)), mk(HYPER["variance"]), mk(HYPER["obs_stddev"]), mk(HYPER["mean_const"])
+    params = (ell, var, sn, c)
+
+    def step():
+        for p in params:
+            p.grad = None
+        v = ops.conjugate_mll_fused(0, X, y, ell, var, sn, c, HYPER["jitter"])
+        v.backward()
+
+    L = lib()
+    clocks = Clocks(D.local)
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    L.gpb_profile_reset(1)
+    clocks.start()
+    t = timed(D, step, 0, args.steps)
+    clk = clocks.stop()
+    import ctypes as C
+
+    gemm_ms, gemm_n, all_n = C.c_double(), C.c_int64(), C.c_int64()
+    L.gpb_profile_read(C.byref(gemm_ms), C.byref(gemm_n), C.byref(all_n))
+    L.gpb_profile_reset(0)
+    value = D.world * args.steps / t
+    flops_per_eval = float(n) ** 3  # N^3/3 potrf + 2N^3/3 potri
+    achieved = flops_per_eval * args.steps / (gemm_ms.value * 1e-3) / 1e12
+    roof = {"bound": "tensor", "kernel": "gemm_f64_kernel (FP64 DMMA.8x8x4)", "achieved": achieved,
+            "peak": NOMINAL_FP64_TFLOPS, "unit": "TFLOP/s", "frac": achieved / NOMINAL_FP64_TFLOPS,
+            "peak_source": "nominal FP64 DMMA peak 128 flop/clk/SM x 148 SM x 1.965 GHz (MEASURED_PEAKS.json has no "
+                           "FP64 figure); cuBLAS DGEMM measured live alongside",
+            "peak_cublas_dgemm": measure_cublas_dgemm(D), "algorithmic_flop_per_eval": flops_per_eval,
+            "gemm_launches_per_step": gemm_n.value / args.steps, "gemm_time_share_of_step": gemm_ms.value * 1e-3 / t,
+            "whole_step_tflops": flops_per_eval * args.steps / t / 1e12, "traffic": None}
+
+    # ---- e2e: the public API with HOST buffers (pinned), H2D + D2H inside the timed region -------------------
+    prior = gpx.gps.Prior(mean_function=gpx.mean_functions.Constant(Real(HYPER["mean_const"])),
+                          kernel=gpx.kernels.RBF(lengthscale=PositiveReal(ell_ard(d)),
+                                                 variance=NonNegativeReal(HYPER["variance"])), jitter=HYPER["jitter"])
+    post = prior * gpx.likelihoods.Gaussian(num_datapoints=n, obs_stddev=NonNegativeReal(HYPER["obs_stddev"]))
+    leaves = [p for _, p in post.named_parameters()]
+    host_out = {}
+
+    def e2e_step():
+        data = gpx.Dataset(X=Xh.to(D.dev, non_blocking=True), y=yh.to(D.dev, non_blocking=True))
+        vals = [p.value.detach().requires_grad_(True) for p in leaves]
+        for p, v in zip(leaves, vals):
+            p.value = v
+        loss = -gpx.objectives.conjugate_mll(post, data)
+        grads = torch.autograd.grad(loss, vals)
+        host_out["loss"] = loss.item()
+        host_out["grads"] = [g.cpu() for g in grads]
+
+    e2e_steps = max(1, min(args.steps, 3))
+    t_e2e = timed(D, e2e_step, 1, e2e_steps)
+    e2e = {"value": D.world * e2e_steps / t_e2e, "unit": "evals/s", "h2d_bytes_per_step": int(n * d * 8 + n * 8),
+           "d2h_bytes_per_step": int(8 * (1 + d + 3)), "steps": e2e_steps,
+           "api": "gpx.objectives.conjugate_mll(posterior, Dataset) + autograd, pinned host X/y copied every step"}
+    ops.release_buffers()
+    torch.cuda.empty_cache()
+    return dict(n=n, d=d, t=t, value=value, roofline=roof, clocks=clk, e2e=e2e, gpu_launches=int(all_n.value),
+                workload=f"exact_gp_conjugate_mll_value_and_grad_N{n}_D{d}_RBF_ARD")
+
+
+def bench_sgpr(D: Dist, args, steps=None, warmup=None):
+    torch = D.torch
+    import gpjax_b200 as gpx
+    from gpjax_b200 import sgpr_ops
+    from gpjax_b200._lib import lib
+    from gpjax_b200.parameters import NonNegativeReal, PositiveReal, Real
+
+    n_total, m, d = env_int("GPB_BENCH_SGPR_N", 10_000_000), env_int("GPB_BENCH_SGPR_M", 2048), 8
+    block = env_int("GPB_BENCH_SGPR_BLOCK", 65536)
+    steps = steps or max(1, min(args.steps, 2))
+    warmup = warmup if warmup is not None else 1
+    lo, hi = D.rank * n_total // D.world, (D.rank + 1) * n_total // D.world
+    Xn, yn = synth(hi - lo, d, 4 + 1000 * D.rank)
+    Xh, yh = torch.from_numpy(Xn).pin_memory(), torch.from_numpy(yn).pin_memory()
+    X, y = Xh.to(D.dev), yh.to(D.dev)
+    Zn = synth(m, d, 5)[0]
+    mk = lambda v: torch.as_tensor(np.asarray(v, np.float64), device=D.dev).requires_grad_(True)
+    Z, ell, var, sn, c = mk(Zn), mk(ell_ard(d)), mk(HYPER["variance"]), mk(HYPER["obs_stddev"]), mk(HYPER["mean_const"])
+    params = (Z, ell, var, sn, c)
+
+    def step():
+        for p in params:
+            p.grad = None
+        v = sgpr_ops.collapsed_elbo_fused(0, X, y, Z, ell, var, sn, c, HYPER["jitter"], block)
+        v.backward()
+
+    L = lib()
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    L.gpb_profile_reset(1)
+    t = timed(D, step, 0, steps)
+    import ctypes as C
+
+    gemm_ms, gemm_n, all_n = C.c_double(), C.c_int64(), C.c_int64()
+    L.gpb_profile_read(C.byref(gemm_ms), C.byref(gemm_n), C.byref(all_n))
+    L.gpb_profile_reset(0)
+    value = n_total * steps / t
+    flops = 4.0 * (hi - lo) * m * m  # SURVEY 8d reference formulation: fwd 2NM^2 + bwd 2NM^2 (per rank share)
+    achieved = flops * steps / (gemm_ms.value * 1e-3) / 1e12
+    roof = {"bound": "tensor", "kernel": "gemm_f64_kernel (FP64 DMMA.8x8x4)", "achieved": achieved,
+            "peak": NOMINAL_FP64_TFLOPS, "unit": "TFLOP/s", "frac": achieved / NOMINAL_FP64_TFLOPS,
+            "algorithmic_flop_per_point": 4.0 * m * m, "gemm_time_share_of_step": gemm_ms.value * 1e-3 / t,
+            "whole_step_tflops_per_gpu": flops * steps / t / 1e12, "traffic": None}
+
+    # e2e through the public API with host-resident shards
+    prior = gpx.gps.Prior(mean_function=gpx.mean_functions.Constant(Real(HYPER["mean_const"])),
+                          kernel=gpx.kernels.RBF(lengthscale=PositiveReal(ell_ard(d)),
+                                                 variance=NonNegativeReal(HYPER["variance"])))
+    post = prior * gpx.likelihoods.Gaussian(num_datapoints=n_total, obs_stddev=NonNegativeReal(HYPER["obs_stddev"]))
+    q = gpx.variational_families.CollapsedVariationalGaussian(posterior=post, inducing_inputs=Real(Zn),
+                                                              jitter=HYPER["jitter"])
+    leaves = [p for _, p in q.named_parameters()]
+    host_out = {}
+
+    def e2e_step():
+        data = gpx.Dataset(X=Xh.to(D.dev, non_blocking=True), y=yh.to(D.dev, non_blocking=True))
+        vals = [p.value.detach().requires_grad_(True) for p in leaves]
+        for p, v in zip(leaves, vals):
+            p.value = v
+        loss = -gpx.objectives.collapsed_elbo(q, data, block_rows=block)
+        grads = torch.autograd.grad(loss, vals)
+        host_out["loss"] = loss.item()
+        host_out["grads"] = [g.cpu() for g in grads]
+
+    t_e2e = timed(D, e2e_step, 1, 1)
+    e2e = {"value": n_total / t_e2e, "unit": "points/s", "h2d_bytes_per_step": int((hi - lo) * (d + 1) * 8),
+           "d2h_bytes_per_step": int(8 * (1 + m * d + d + 3)), "steps": 1,
+           "api": "gpx.objectives.collapsed_elbo(q, Dataset) + autograd, pinned host shard copied every step"}
+    sgpr_ops.release_buffers()
+    torch.cuda.empty_cache()
+    return dict(metric="SGPR collapsed_elbo value+grad points/s", value=value, unit="points/s", n_gpus=D.world,
+                steps=steps, warmup=warmup, ms_per_step=1e3 * t / steps, scaling="strong",
+                config={"workload": f"sgpr_collapsed_elbo_value_and_grad_N{n_total}_M{m}_D{d}_RBF_ARD",
+                        "N": n_total, "M": m, "D": d, "block_rows": block, "rows_per_rank": hi - lo,
+                        "collective": "all-reduce (M+2)^2 fp64 fwd + (M*D+D+1) fp64 bwd, NCCL"},
+                roofline=roof, e2e=e2e, gpu_launches=int(all_n.value))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "exact", "sgpr"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    D = Dist(args.gpus)
+    line = {}
+    if args.workload in ("auto", "exact"):
+        ex = bench_exact(D, args)
+        line = {"metric": METRIC, "value": ex["value"], "unit": "evals/s", "n_gpus": D.world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * ex["t"] / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": ex["workload"], "N": ex["n"], "D": ex["d"], "kernel": "RBF ARD",
+                           "parallelism": "replicas only (exact GP does not shard)" if D.world > 1 else "single GPU",
+                           "l2": "20 GB working set per step >> 126 MB L2 (no flush needed)"},
+                "roofline": ex["roofline"], "clocks": ex["clocks"], "e2e": ex["e2e"], "gpu_launches": ex["gpu_launches"]}
+    if args.workload in ("auto", "sgpr"):
+        sg = bench_sgpr(D, args)
+        if args.workload == "sgpr":
+            line = {**sg, "higher_is_better": True, "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+        else:
+            line["sgpr"] = sg
+    if D.rank == 0 and not args.no_cpu_baseline and D.world == 1:
+        if args.workload in ("auto", "exact"):
+            s = cpu_exact_sample(line["config"]["N"], 8)
+            line["cpu_baseline"] = {"value": s["evals_per_s_at_target"], "unit": "evals/s", "cores": cpu_threads(),
+                                    "kind": "port",
+                                    "sample": f"one MLL+grad in the reference's LU formulation at N={s['n_sample']} "
+                                              f"({s['seconds']:.2f} s), N^3-extrapolated to N={line['config']['N']}"}
+        if args.workload in ("auto", "sgpr"):
+            s = cpu_sgpr_sample(env_int("GPB_BENCH_SGPR_M", 2048), 8)
+            cb = {"value": s["points_per_s"], "unit": "points/s", "cores": cpu_threads(), "kind": "port",
+                  "sample": f"collapsed_elbo value+grad on {s['rows']} rows, M=2048 ({s['seconds']:.2f} s), linear in N"}
+            if args.workload == "sgpr":
+                line["cpu_baseline"] = cb
+            else:
+                line["sgpr"]["cpu_baseline"] = cb
+    if D.rank == 0:
+        print(json.dumps(line), flush=True)
+    if D.dist is not None:
+        D.dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

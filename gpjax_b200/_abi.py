@@ -18,6 +18,8 @@ PROTOTYPES = {
     "gpb_version": (C.c_char_p, []),
     "gpb_max_input_dim": (i32, []),
     "gpb_block_size": (i64, []),
+    "gpb_profile_reset": (None, [i32]),
+    "gpb_profile_read": (i32, [vp, vp, vp]),
     "gpb_gram": (i32, [vp, i32, i64, i64, i32, vp, i64, vp, i64, vp, i32, vp, f64, vp, i32, vp, i64]),
     "gpb_gram_bwd_workspace_bytes": (i64, [i64, i64, i32]),
     "gpb_gram_bwd": (
@@ -40,6 +42,21 @@ PROTOTYPES = {
     "gpb_mll_backward": (
         i32,
         [vp, i32, i64, i32, vp, i64, vp, i32, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp],
+    ),
+    "gpb_sgpr_workspace_bytes": (i64, [i64, i32, i64]),
+    "gpb_sgpr_stats_count": (i64, [i64]),
+    "gpb_sgpr_stats": (
+        i32,
+        [vp, i32, i64, i64, i32, vp, i64, vp, vp, i64, vp, i32, vp, vp, vp, f64, i64, vp, i64, vp],
+    ),
+    "gpb_sgpr_finish": (i32, [vp, i32, i64, i32, vp, i64, vp, i32, vp, vp, i64, vp, i64, vp, i32, vp, vp]),
+    "gpb_sgpr_grad_local": (
+        i32,
+        [vp, i32, i64, i64, i32, vp, i64, vp, vp, i64, vp, i32, vp, vp, vp, i64, vp, i64, vp, vp, vp],
+    ),
+    "gpb_sgpr_grad_finish": (
+        i32,
+        [vp, i32, i64, i32, vp, i64, vp, i32, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp],
     ),
 }
 

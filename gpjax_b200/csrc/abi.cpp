@@ -1,6 +1,7 @@
 // extern "C" boundary (see include/gpjax_b200.h for the contract and the reference citations).
 #include "../../include/gpjax_b200.h"
 #include "algorithms.h"
+#include "sgpr.h"
 
 using namespace gpb;
 
@@ -15,6 +16,10 @@ extern "C" {
 const char* gpb_version(void) { return "gpjax_b200 0.1.0 (sm_100a, fp64 DMMA)"; }
 int gpb_max_input_dim(void) { return max_input_dim(); }
 int64_t gpb_block_size(void) { return NB; }
+void gpb_profile_reset(int enable) { profile_reset(enable); }
+int gpb_profile_read(double* gemm_ms, int64_t* gemm_launches, int64_t* all_launches) {
+    return profile_read(gemm_ms, gemm_launches, all_launches);
+}
 
 int gpb_gram(void* stream, int kind, int64_t N, int64_t M, int D, const double* X, int64_t ldx, const double* Z,
              int64_t ldz, const double* lengthscale, int lengthscale_is_scalar, const double* variance,
@@ -155,6 +160,69 @@ int gpb_mll_backward(void* stream, int kind, int64_t N, int D, const double* X, 
     a.ell = lengthscale; a.ell_is_scalar = lengthscale_is_scalar; a.variance = variance;
     a.obs_stddev = obs_stddev; a.Sigma = Sigma; a.lds = lds;
     return mll_backward(stream, a, w, alpha, gout, g_lengthscale, g_variance, g_obs_stddev, g_mean_const);
+}
+
+int64_t gpb_sgpr_workspace_bytes(int64_t M, int D, int64_t block_rows) { return sgpr_ws_bytes(M, D, block_rows); }
+int64_t gpb_sgpr_stats_count(int64_t M) { return (M + 2) * (M + 2); }
+
+static SgprArgs sgpr_args(int kind, int64_t Nloc, int64_t M, int D, const double* X, int64_t ldx, const double* y,
+                          const double* Z, int64_t ldz, const double* ell, int iso, const double* var,
+                          const double* sn, const double* mean, double jitter, int64_t block_rows) {
+    SgprArgs a;
+    a.kind = kind; a.Nloc = Nloc; a.M = M; a.D = D; a.X = X; a.ldx = ldx; a.y = y; a.Z = Z; a.ldz = ldz;
+    a.ell = ell; a.ell_is_scalar = iso; a.variance = var; a.obs_stddev = sn; a.mean_const = mean;
+    a.jitter = jitter; a.block_rows = block_rows;
+    return a;
+}
+
+int gpb_sgpr_stats(void* stream, int kind, int64_t Nloc, int64_t M, int D, const double* X, int64_t ldx,
+                   const double* y, const double* Z, int64_t ldz, const double* lengthscale,
+                   int lengthscale_is_scalar, const double* variance, const double* obs_stddev,
+                   const double* mean_const, double jitter, int64_t block_rows, void* ws, int64_t ws_bytes,
+                   double* Paug) {
+    SgprWs w;
+    int rc = sgpr_ws_carve(ws, ws_bytes, M, D, block_rows, &w);
+    if (rc) return rc;
+    return sgpr_stats(stream, sgpr_args(kind, Nloc, M, D, X, ldx, y, Z, ldz, lengthscale, lengthscale_is_scalar,
+                                        variance, obs_stddev, mean_const, jitter, block_rows), w, Paug);
+}
+
+int gpb_sgpr_finish(void* stream, int kind, int64_t M, int D, const double* Z, int64_t ldz,
+                    const double* lengthscale, int lengthscale_is_scalar, const double* variance,
+                    const double* obs_stddev, int64_t block_rows, void* ws, int64_t ws_bytes, const double* Paug,
+                    int need_grad, double* elbo_out, int* info_out) {
+    SgprWs w;
+    int rc = sgpr_ws_carve(ws, ws_bytes, M, D, block_rows, &w);
+    if (rc) return rc;
+    return sgpr_finish(stream, sgpr_args(kind, 0, M, D, nullptr, 0, nullptr, Z, ldz, lengthscale, lengthscale_is_scalar,
+                                         variance, obs_stddev, nullptr, 0.0, block_rows), w, Paug, need_grad, elbo_out,
+                       info_out);
+}
+
+int gpb_sgpr_grad_local(void* stream, int kind, int64_t Nloc, int64_t M, int D, const double* X, int64_t ldx,
+                        const double* y, const double* Z, int64_t ldz, const double* lengthscale,
+                        int lengthscale_is_scalar, const double* variance, const double* obs_stddev,
+                        const double* mean_const, int64_t block_rows, void* ws, int64_t ws_bytes, double* g_Z,
+                        double* g_lengthscale, double* g_variance) {
+    SgprWs w;
+    int rc = sgpr_ws_carve(ws, ws_bytes, M, D, block_rows, &w);
+    if (rc) return rc;
+    return sgpr_grad_local(stream, sgpr_args(kind, Nloc, M, D, X, ldx, y, Z, ldz, lengthscale, lengthscale_is_scalar,
+                                             variance, obs_stddev, mean_const, 0.0, block_rows), w, g_Z,
+                           g_lengthscale, g_variance);
+}
+
+int gpb_sgpr_grad_finish(void* stream, int kind, int64_t M, int D, const double* Z, int64_t ldz,
+                         const double* lengthscale, int lengthscale_is_scalar, const double* variance,
+                         const double* obs_stddev, int64_t block_rows, void* ws, int64_t ws_bytes, const double* gout,
+                         double* g_Z, double* g_lengthscale, double* g_variance, double* g_obs_stddev,
+                         double* g_mean_const) {
+    SgprWs w;
+    int rc = sgpr_ws_carve(ws, ws_bytes, M, D, block_rows, &w);
+    if (rc) return rc;
+    return sgpr_grad_finish(stream, sgpr_args(kind, 0, M, D, nullptr, 0, nullptr, Z, ldz, lengthscale,
+                                              lengthscale_is_scalar, variance, obs_stddev, nullptr, 0.0, block_rows),
+                            w, gout, g_Z, g_lengthscale, g_variance, g_obs_stddev, g_mean_const);
 }
 
 }  // extern "C"

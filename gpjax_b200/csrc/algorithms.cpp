@@ -76,49 +76,55 @@ int factor_ws_carve(void* buf, int64_t bytes, int64_t N, int D, int with_potri, 
 }
 
 // -------------------------------------------------------------------------------------------
-// diagonal block: factor (optional) + explicit inverse, n <= NB, via two leaves and four small GEMMs
+// diagonal block: factor (optional) + explicit inverse, n <= NB, by recursive halving down to the
+// single-CTA leaves (n <= LEAFN); the off-diagonal parts are small DMMA GEMMs:
+//   L21 = A21 inv(L11)^T,  A22 -= L21 L21^T,  inv(L)21 = -inv(L22) L21 inv(L11)
+// D / DT are the inverse and its transpose, row stride NB.  `small` provides 2*h*h doubles of
+// scratch per recursion level (h = 256, 128), laid out back to back.
 // -------------------------------------------------------------------------------------------
 static int diag_block(stream_t s, int n, double* Ablk, int64_t lda, double* D, double* DT, double* small,
                       int* info, int64_t row0, int factor) {
-    const int n1 = n < LEAFN ? n : (int)LEAFN;
-    const int n2 = n - n1;
-    GPB_TRY(potrf_leaf(s, n1, Ablk, lda, D, NB, DT, NB, info, row0, factor));
-    if (n2 <= 0) return GPB_OK;
-    double* t21 = small;                  // [n2 x n1], ld LEAFN : L21
-    double* tt = small + LEAFN * LEAFN;   // [n2 x n1], ld LEAFN : L21 * Dinv1
+    if (n <= LEAFN) return potrf_leaf(s, n, Ablk, lda, D, NB, DT, NB, info, row0, factor);
+    int h = (int)LEAFN;
+    while (2 * h < n) h *= 2;  // largest power-of-two multiple of LEAFN strictly below n
+    const int n1 = h, n2 = n - h;
+    double* t21 = small;                     // [n2 x n1], ld h : L21
+    double* tt = small + (int64_t)h * h;     // [n2 x n1], ld h : L21 * inv(L11)
+    double* next_small = small + 2 * (int64_t)h * h;
     double* A21 = Ablk + (int64_t)n1 * lda;
     double* A22 = A21 + n1;
+    double* D22 = D + (int64_t)n1 * NB + n1;
+    double* DT22 = DT + (int64_t)n1 * NB + n1;
+    GPB_TRY(diag_block(s, n1, Ablk, lda, D, DT, next_small, info, row0, factor));
     GemmDesc g;
     if (factor) {
         // L21 = A21 * inv(L11)^T
         g = GemmDesc();
         g.M = n2; g.N = n1; g.K = n1;
-        g.A = A21; g.lda = lda; g.B = D; g.ldb = NB; g.C = t21; g.ldc = LEAFN;
+        g.A = A21; g.lda = lda; g.B = D; g.ldb = NB; g.C = t21; g.ldc = h;
         g.krange = KR_B_LOWER;
         GPB_TRY(gemm(s, g));
-        GPB_TRY(copy2d(s, n2, n1, t21, LEAFN, A21, lda));
+        GPB_TRY(copy2d(s, n2, n1, t21, h, A21, lda));
         // A22 -= L21 L21^T (lower)
         g = GemmDesc();
         g.M = n2; g.N = n2; g.K = n1;
-        g.A = t21; g.lda = LEAFN; g.B = t21; g.ldb = LEAFN; g.C = A22; g.ldc = lda;
+        g.A = t21; g.lda = h; g.B = t21; g.ldb = h; g.C = A22; g.ldc = lda;
         g.alpha = -1.0; g.beta = 1.0; g.mask = MASK_LOWER;
         GPB_TRY(gemm(s, g));
     } else {
-        GPB_TRY(copy2d(s, n2, n1, A21, lda, t21, LEAFN));
+        GPB_TRY(copy2d(s, n2, n1, A21, lda, t21, h));
     }
-    double* D22 = D + (int64_t)n1 * NB + n1;
-    double* DT22 = DT + (int64_t)n1 * NB + n1;
-    GPB_TRY(potrf_leaf(s, n2, A22, lda, D22, NB, DT22, NB, info, row0 + n1, factor));
-    // tt = L21 * Dinv1          (B operand = DinvT1, upper triangular)
+    GPB_TRY(diag_block(s, n2, A22, lda, D22, DT22, next_small, info, row0 + n1, factor));
+    // tt = L21 * inv(L11)          (B operand = inv(L11)^T, upper triangular)
     g = GemmDesc();
     g.M = n2; g.N = n1; g.K = n1;
-    g.A = t21; g.lda = LEAFN; g.B = DT; g.ldb = NB; g.C = tt; g.ldc = LEAFN;
+    g.A = t21; g.lda = h; g.B = DT; g.ldb = NB; g.C = tt; g.ldc = h;
     g.krange = KR_B_UPPER;
     GPB_TRY(gemm(s, g));
-    // Dinv21 = -Dinv2 * tt      (B operand tt is N-contiguous)
+    // inv(L)21 = -inv(L22) * tt    (B operand tt is N-contiguous)
     g = GemmDesc();
     g.M = n2; g.N = n1; g.K = n2;
-    g.A = D22; g.lda = NB; g.B = tt; g.ldb = LEAFN; g.b_layout = LAYOUT_MN;
+    g.A = D22; g.lda = NB; g.B = tt; g.ldb = h; g.b_layout = LAYOUT_MN;
     g.C = D + (int64_t)n1 * NB; g.ldc = NB; g.alpha = -1.0;
     g.krange = KR_A_LOWER;
     GPB_TRY(gemm(s, g));

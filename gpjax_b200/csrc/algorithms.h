@@ -7,7 +7,10 @@
 
 namespace gpb {
 
-constexpr int64_t NB = 256;    // block size of every blocked algorithm
+#ifndef GPB_NB
+#define GPB_NB 512
+#endif
+constexpr int64_t NB = GPB_NB;  // block size of every blocked algorithm (power-of-two multiple of 128)
 constexpr int64_t LEAFN = 128; // leaf size handled by potrf_leaf
 
 inline int64_t nblocks(int64_t n) { return (n + NB - 1) / NB; }

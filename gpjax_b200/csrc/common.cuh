@@ -10,6 +10,7 @@ namespace gpb {
     do {                                                     \
         cudaError_t e__ = cudaGetLastError();                \
         if (e__ != cudaSuccess) return GPB_ERR_LAUNCH;       \
+        profile_count_launch();                              \
     } while (0)
 
 static inline cudaStream_t to_stream(stream_t s) { return reinterpret_cast<cudaStream_t>(s); }

@@ -381,7 +381,10 @@ int launch_gemm(cudaStream_t st, const GemmParams& p, int batch) {
     if (gx == 0) return GPB_OK;
     if (gx > 2147483647LL || gy > 65535 || batch > 65535) return GPB_ERR_UNSUPPORTED;
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)batch);
+    const bool prof = profile_enabled();
+    if (prof) profile_gemm_begin(st);
     kern<<<grid, NTHREADS, smem, st>>>(p);
+    if (prof) profile_gemm_end(st);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
 }

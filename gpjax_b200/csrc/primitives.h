@@ -180,6 +180,45 @@ int64_t gram_bwd_partials_count(int64_t N, int64_t M, int D);
 // g_theta += scale * <dK, dK/dtheta>, g_X / g_Z likewise; dK read once, K recomputed on the fly.
 int gram_bwd(stream_t s, const GramBwdDesc& d);
 
+
+// ---- small helpers used by the SGPR (collapsed_elbo) path -----------------------------------
+// A = I (n x n)
+int set_identity(stream_t s, int64_t n, double* A, int64_t lda);
+// out[0] = sum_i x[i]
+int vec_sum(stream_t s, int64_t n, const double* x, double* out);
+// x[i] *= (*f) (f device scalar; null -> no-op)
+int scale_inplace(stream_t s, int64_t n, double* x, const double* f);
+// T[r*ld + M] = y[r] - (*c) ; T[r*ld + M + 1] = 1      (c may be null)
+int sgpr_aug_columns(stream_t s, int64_t rows, double* T, int64_t ld, int64_t M, const double* y,
+                     const double* c);
+// Unpack the (all-reduced) augmented statistics Paug [(M+2) x (M+2), lower stored]:
+//   s = obs_stddev^2, Bmat = I + Phi~/s (full symmetric, ld M), psi = Paug[M,:M]/sqrt(s),
+//   a1 = Paug[M+1,:M]/sqrt(s), sc = {dd, sd, n, tr(Phi~)/s, s}
+int sgpr_prepare(stream_t s, int64_t M, const double* Paug, int64_t ldp, const double* obs_stddev,
+                 double* Bmat, double* psi, double* a1, double* sc);
+// out = 1/2 [ -n log(2 pi s) - 2 hl - (dd - wtw)/s - (n var / s - trPhi) ];  NaN if info[0] or info[1]
+int sgpr_value(stream_t s, const double* sc, const double* half_logdetB, const double* wtw,
+               const double* variance, const int* info, double* out);
+// dPhi = 1/2 (I - Binv - v v^T / s), Phi = Bmat - I:
+//   G1 = (2/s) dPhi, G2 = dPhi - Phi/2, u = v / (s sqrt s), rowsum[r] = sum_c dPhi[r,c] Phi[r,c]
+int sgpr_adjoints(stream_t s, int64_t M, const double* Binv, const double* Bmat, const double* v,
+                  const double* sc, double* G1, double* G2, double* u, double* rowsum);
+// replicated scalar part of the gradient (dots = {psi.v, v.a1, <dPhi,Phi>}):
+//   g_var += -n/(2s);  g_obs = 2 sn g_s;  g_mean = -(v.a1)/s + sd/s   with
+//   g_s = -n/(2s) + (dd - psi.v)/(2 s^2) + n var/(2 s^2) - (2 <dPhi,Phi> + psi.v / s)/(2 s)
+int sgpr_scalar_grads(stream_t s, const double* sc, const double* dots, const double* variance,
+                      const double* obs_stddev, double* g_var, double* g_obs, double* g_mean);
+
+// ---- optional measurement hooks (bench.py roofline): off by default, zero cost when off ----------
+// enable != 0: every gemm() launch is bracketed by CUDA events on its own stream and every kernel
+// launch of the library is counted.  profile_read synchronises the recorded events.
+void profile_reset(int enable);
+int profile_read(double* gemm_ms, int64_t* gemm_launches, int64_t* all_launches);
+void profile_count_launch();
+bool profile_enabled();
+void profile_gemm_begin(stream_t s);
+void profile_gemm_end(stream_t s);
+
 // maximum input dimension D the compiled kernels support
 int max_input_dim();
 

@@ -1,0 +1,66 @@
+// Optional measurement hooks used by bench.py to time the dominant kernel (the DMMA GEMM) live with
+// CUDA events on the launching stream.  Disabled by default; the product path never enables it.
+#include <atomic>
+#include <mutex>
+#include <vector>
+#include "common.cuh"
+
+namespace gpb {
+
+namespace {
+struct Prof {
+    std::atomic<int> enabled{0};
+    std::atomic<long long> launches{0};
+    std::mutex mu;
+    std::vector<cudaEvent_t> begin, end;
+    size_t used = 0;
+} g_prof;
+}  // namespace
+
+void profile_reset(int enable) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    g_prof.used = 0;
+    g_prof.launches = 0;
+    g_prof.enabled = enable;
+}
+
+bool profile_enabled() { return g_prof.enabled.load(std::memory_order_relaxed) != 0; }
+
+void profile_count_launch() {
+    if (g_prof.enabled.load(std::memory_order_relaxed)) g_prof.launches.fetch_add(1, std::memory_order_relaxed);
+}
+
+void profile_gemm_begin(stream_t s) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    if (g_prof.used == g_prof.begin.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        g_prof.begin.push_back(a);
+        g_prof.end.push_back(b);
+    }
+    cudaEventRecord(g_prof.begin[g_prof.used], to_stream(s));
+}
+
+void profile_gemm_end(stream_t s) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    cudaEventRecord(g_prof.end[g_prof.used], to_stream(s));
+    g_prof.used++;
+}
+
+int profile_read(double* gemm_ms, int64_t* gemm_launches, int64_t* all_launches) {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    double total = 0.0;
+    for (size_t i = 0; i < g_prof.used; ++i) {
+        if (cudaEventSynchronize(g_prof.end[i]) != cudaSuccess) return GPB_ERR_LAUNCH;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, g_prof.begin[i], g_prof.end[i]) != cudaSuccess) return GPB_ERR_LAUNCH;
+        total += ms;
+    }
+    if (gemm_ms) *gemm_ms = total;
+    if (gemm_launches) *gemm_launches = (int64_t)g_prof.used;
+    if (all_launches) *all_launches = (int64_t)g_prof.launches.load();
+    return GPB_OK;
+}
+
+}  // namespace gpb

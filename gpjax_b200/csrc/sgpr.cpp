@@ -1,0 +1,240 @@
+// collapsed_elbo orchestration.  Reference: gpjax/objectives.py:342-416; gradient: SURVEY Appendix B.
+//
+// The reference materialises Kzx (M x N) and A = Lz^-1 Kzx / sigma (M x N) -- 2 x 164 GB at
+// N = 1e7, M = 2048.  Here the data enter only through the row-additive (M+2)^2 statistics
+//   Paug = sum_b [At_b | d_b | 1]^T [At_b | d_b | 1],   At_b = k(X_b, Z) Lz^-T   (block_rows x M)
+// streamed block by block: Gram tile kernel -> DMMA GEMM against the explicit (triangular-skipping)
+// inverse factor -> DMMA SYRK.  One all-reduce of Paug over the ranks, then a replicated M x M
+// finish.  The backward is a second streamed pass: dK_b = [K_b | d_b | 1] Caug^T (DMMA GEMM)
+// contracted on the fly with dk/dtheta (gram_bwd), never materialising anything N x M in HBM
+// beyond one block.
+#include "sgpr.h"
+
+namespace gpb {
+
+#define GPB_TRY(expr)                    \
+    do {                                 \
+        int rc__ = (expr);               \
+        if (rc__ != GPB_OK) return rc__; \
+    } while (0)
+
+namespace {
+struct Lay {
+    int64_t fz, fb, mm[10], vec[7], sc, dots, T1, T2, gpart, info, total;
+    int64_t fz_bytes, fb_bytes;
+};
+Lay layout(int64_t M, int D, int64_t Bs) {
+    Lay L;
+    int64_t o = 0;
+    auto take = [&](int64_t n) {
+        int64_t r = o;
+        o += align_up(n, 32);
+        return r;
+    };
+    L.fz_bytes = factor_ws_bytes(M, D, 0);
+    L.fb_bytes = factor_ws_bytes(M, D, 1);
+    L.fz = take(L.fz_bytes / 8);
+    L.fb = take(L.fb_bytes / 8);
+    for (int i = 0; i < 10; ++i) L.mm[i] = take(M * (M + 2));
+    for (int i = 0; i < 7; ++i) L.vec[i] = take(M + 2);
+    L.sc = take(16);
+    L.dots = take(16);
+    L.T1 = take(Bs * (M + 2));
+    L.T2 = take(Bs * (M + 2));
+    int64_t p1 = gram_bwd_partials_count(Bs, M, D), p2 = gram_bwd_partials_count(M, M, D);
+    L.gpart = take(p1 > p2 ? p1 : p2);
+    L.info = take(8);
+    L.total = o;
+    return L;
+}
+}  // namespace
+
+int64_t sgpr_ws_bytes(int64_t M, int D, int64_t block_rows) {
+    if (M <= 0 || D <= 0 || block_rows <= 0) return 0;
+    return layout(M, D, block_rows).total * (int64_t)sizeof(double);
+}
+
+int sgpr_ws_carve(void* buf, int64_t bytes, int64_t M, int D, int64_t block_rows, SgprWs* ws) {
+    if (!buf || !ws || M <= 0 || D <= 0 || block_rows <= 0) return GPB_ERR_INVALID;
+    Lay L = layout(M, D, block_rows);
+    if (bytes < L.total * (int64_t)sizeof(double)) return GPB_ERR_WORKSPACE;
+    double* b = static_cast<double*>(buf);
+    GPB_TRY(factor_ws_carve(b + L.fz, L.fz_bytes, M, D, 0, &ws->fz));
+    GPB_TRY(factor_ws_carve(b + L.fb, L.fb_bytes, M, D, 1, &ws->fb));
+    double** mm[10] = {&ws->Lz, &ws->Linv, &ws->Bmat, &ws->LB, &ws->Binv, &ws->G1, &ws->G2, &ws->Tmp, &ws->Caug, &ws->dKzz};
+    for (int i = 0; i < 10; ++i) *mm[i] = b + L.mm[i];
+    double** vv[7] = {&ws->psi, &ws->a1, &ws->w, &ws->v, &ws->u, &ws->cvec, &ws->rowsum};
+    for (int i = 0; i < 7; ++i) *vv[i] = b + L.vec[i];
+    ws->sc = b + L.sc;
+    ws->dots = b + L.dots;
+    ws->T1 = b + L.T1;
+    ws->T2 = b + L.T2;
+    ws->gpart = b + L.gpart;
+    ws->info2 = reinterpret_cast<int*>(b + L.info);
+    return GPB_OK;
+}
+
+static int check_args(const SgprArgs& a) {
+    if (a.Nloc < 0 || a.M <= 0 || a.D <= 0 || a.block_rows <= 0) return GPB_ERR_INVALID;
+    if (!a.Z || !a.ell || !a.variance || !a.obs_stddev) return GPB_ERR_INVALID;
+    if (a.Nloc > 0 && (!a.X || !a.y)) return GPB_ERR_INVALID;
+    return GPB_OK;
+}
+
+static GramDesc gram_desc(const SgprArgs& a, const double* X, int64_t ldx, int64_t rows, double* K, int64_t ldk) {
+    GramDesc g;
+    g.kind = a.kind; g.N = rows; g.M = a.M; g.D = a.D;
+    g.X = X; g.ldx = ldx; g.Z = a.Z; g.ldz = a.ldz;
+    g.ell = a.ell; g.ell_is_scalar = a.ell_is_scalar; g.variance = a.variance;
+    g.K = K; g.ldk = ldk;
+    return g;
+}
+
+int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug) {
+    GPB_TRY(check_args(a));
+    if (!Paug) return GPB_ERR_INVALID;
+    const int64_t M = a.M, ld = M + 2;
+    // Kzz + jitter I = Lz Lz^T   (objectives.py:352-359)
+    GramDesc gz = gram_desc(a, a.Z, a.ldz, M, ws.Lz, M);
+    gz.lower_only = 1; gz.diag_add = a.jitter;
+    GPB_TRY(gram(s, gz));
+    GPB_TRY(fill2d(s, 1, 2, reinterpret_cast<double*>(ws.info2), 2, 0.0));  // clears both info words (bit pattern 0)
+    GPB_TRY(potrf_lower(s, M, ws.Lz, M, ws.fz, ws.info2));
+    GPB_TRY(zero_triangle(s, M, ws.Lz, M, 2));
+    // explicit inverse factor (lower, physically zero above the diagonal)
+    GPB_TRY(set_identity(s, M, ws.Linv, M));
+    GPB_TRY(trsm_lower_left(s, M, M, ws.Lz, M, ws.fz, ws.Linv, M, 0));
+    GPB_TRY(fill2d(s, ld, ld, Paug, ld, 0.0));
+    for (int64_t r0 = 0; r0 < a.Nloc; r0 += a.block_rows) {
+        const int64_t rows = (a.Nloc - r0) < a.block_rows ? (a.Nloc - r0) : a.block_rows;
+        // K_b^T = k(X_b, Z)   (objectives.py:355, one row block)
+        GPB_TRY(gram(s, gram_desc(a, a.X + r0 * a.ldx, a.ldx, rows, ws.T1, ld)));
+        // At_b = K_b^T Lz^-T  (objectives.py:387 without the 1/sigma, folded into the finish)
+        GemmDesc g;
+        g.M = rows; g.N = M; g.K = M;
+        g.A = ws.T1; g.lda = ld; g.B = ws.Linv; g.ldb = M; g.C = ws.T2; g.ldc = ld;
+        g.krange = KR_B_LOWER;
+        GPB_TRY(gemm(s, g));
+        GPB_TRY(sgpr_aug_columns(s, rows, ws.T2, ld, M, a.y + r0, a.mean_const));
+        // Paug += [At_b | d_b | 1]^T [At_b | d_b | 1]   (objectives.py:390,404,407 in one SYRK)
+        GemmDesc u;
+        u.M = ld; u.N = ld; u.K = rows;
+        u.A = ws.T2; u.lda = ld; u.a_layout = LAYOUT_MN;
+        u.B = ws.T2; u.ldb = ld; u.b_layout = LAYOUT_MN;
+        u.C = Paug; u.ldc = ld; u.beta = 1.0; u.mask = MASK_LOWER;
+        GPB_TRY(gemm(s, u));
+    }
+    return GPB_OK;
+}
+
+int sgpr_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const double* Paug, int need_grad, double* elbo_out,
+                int* info_out) {
+    GPB_TRY(check_args(a));
+    if (!Paug || !elbo_out) return GPB_ERR_INVALID;
+    const int64_t M = a.M, ld = M + 2;
+    double* hl = ws.dots + 4;
+    double* wtw = ws.dots + 5;
+    GPB_TRY(sgpr_prepare(s, M, Paug, ld, a.obs_stddev, ws.Bmat, ws.psi, ws.a1, ws.sc));
+    // L L^T = I + A A^T   (objectives.py:393-396)
+    GPB_TRY(copy2d(s, M, M, ws.Bmat, M, ws.LB, M));
+    GPB_TRY(potrf_lower(s, M, ws.LB, M, ws.fb, ws.info2 + 1));
+    GPB_TRY(sum_log_diag(s, M, ws.LB, M, hl));              // :399
+    GPB_TRY(copy2d(s, 1, M, ws.psi, M, ws.w, M));
+    GPB_TRY(trsv_lower(s, M, ws.LB, M, ws.fb, ws.w, 0));    // :404
+    GPB_TRY(dot(s, M, ws.w, ws.w, wtw));
+    GPB_TRY(sgpr_value(s, ws.sc, hl, wtw, a.variance, ws.info2, elbo_out));  // :407-416
+    if (info_out) GPB_TRY(copy2d(s, 1, 1, reinterpret_cast<const double*>(ws.info2), 1, reinterpret_cast<double*>(info_out), 1));
+    if (!need_grad) return GPB_OK;
+    // v = B^-1 psi, B^-1, adjoints
+    GPB_TRY(copy2d(s, 1, M, ws.w, M, ws.v, M));
+    GPB_TRY(trsv_lower(s, M, ws.LB, M, ws.fb, ws.v, 1));
+    GPB_TRY(trtri_into_upper(s, M, ws.LB, M, ws.fb));
+    GPB_TRY(lauum_upper(s, M, ws.LB, M, ws.fb));
+    {   // assemble the full symmetric inverse
+        const int64_t nblk = nblocks(M);
+        for (int64_t k = 0; k < nblk; ++k) {
+            const int64_t j0 = k * NB;
+            const int64_t nbk = (M - j0) < NB ? (M - j0) : NB;
+            GPB_TRY(copy2d(s, nbk, nbk, ws.fb.Sdiag + k * NB * NB, NB, ws.Binv + j0 * M + j0, M));
+            const int64_t right = M - j0 - nbk;
+            if (right > 0) GPB_TRY(copy2d(s, nbk, right, ws.LB + j0 * M + j0 + nbk, M, ws.Binv + j0 * M + j0 + nbk, M));
+        }
+        GPB_TRY(symmetrize(s, M, ws.Binv, M, 0));
+    }
+    GPB_TRY(sgpr_adjoints(s, M, ws.Binv, ws.Bmat, ws.v, ws.sc, ws.G1, ws.G2, ws.u, ws.rowsum));
+    GPB_TRY(dot(s, M, ws.psi, ws.v, ws.dots + 0));
+    GPB_TRY(dot(s, M, ws.v, ws.a1, ws.dots + 1));
+    GPB_TRY(vec_sum(s, M, ws.rowsum, ws.dots + 2));
+    // C = Linv^T G1 Linv  -> Caug[:, 0:M];  cvec = Linv^T u -> Caug[:, M];  Caug[:, M+1] = 0
+    GemmDesc t;
+    t.M = M; t.N = M; t.K = M;
+    t.A = ws.G1; t.lda = M; t.B = ws.Linv; t.ldb = M; t.b_layout = LAYOUT_MN; t.C = ws.Tmp; t.ldc = M;
+    GPB_TRY(gemm(s, t));
+    GemmDesc c;
+    c.M = M; c.N = M; c.K = M;
+    c.A = ws.Linv; c.lda = M; c.a_layout = LAYOUT_MN; c.B = ws.Tmp; c.ldb = M; c.b_layout = LAYOUT_MN;
+    c.C = ws.Caug; c.ldc = ld;
+    GPB_TRY(gemm(s, c));
+    GPB_TRY(gemv(s, M, M, ws.Linv, M, 1, ws.u, ws.cvec, 1.0, 0.0));
+    GPB_TRY(copy2d(s, M, 1, ws.cvec, 1, ws.Caug + M, ld));
+    GPB_TRY(fill2d(s, M, 1, ws.Caug + M + 1, ld, 0.0));
+    // dKzz = Linv^T G2 Linv
+    t.A = ws.G2;
+    GPB_TRY(gemm(s, t));
+    c.C = ws.dKzz; c.ldc = M;
+    GPB_TRY(gemm(s, c));
+    return GPB_OK;
+}
+
+int sgpr_grad_local(stream_t s, const SgprArgs& a, const SgprWs& ws, double* g_Z, double* g_ell, double* g_var) {
+    GPB_TRY(check_args(a));
+    if (!g_Z || !g_ell || !g_var) return GPB_ERR_INVALID;
+    const int64_t M = a.M, ld = M + 2;
+    GPB_TRY(fill2d(s, M, a.D, g_Z, a.D, 0.0));
+    GPB_TRY(fill2d(s, 1, a.ell_is_scalar ? 1 : a.D, g_ell, a.D, 0.0));
+    GPB_TRY(fill2d(s, 1, 1, g_var, 1, 0.0));
+    for (int64_t r0 = 0; r0 < a.Nloc; r0 += a.block_rows) {
+        const int64_t rows = (a.Nloc - r0) < a.block_rows ? (a.Nloc - r0) : a.block_rows;
+        GPB_TRY(gram(s, gram_desc(a, a.X + r0 * a.ldx, a.ldx, rows, ws.T1, ld)));
+        GPB_TRY(sgpr_aug_columns(s, rows, ws.T1, ld, M, a.y + r0, a.mean_const));
+        // dK_b^T = [K_b^T | d_b | 1] Caug^T   (= K_b^T C + d_b cvec^T)
+        GemmDesc g;
+        g.M = rows; g.N = M; g.K = ld;
+        g.A = ws.T1; g.lda = ld; g.B = ws.Caug; g.ldb = ld; g.C = ws.T2; g.ldc = ld;
+        GPB_TRY(gemm(s, g));
+        GramBwdDesc b;
+        b.kind = a.kind; b.N = rows; b.M = M; b.D = a.D;
+        b.X = a.X + r0 * a.ldx; b.ldx = a.ldx; b.Z = a.Z; b.ldz = a.ldz;
+        b.ell = a.ell; b.ell_is_scalar = a.ell_is_scalar; b.variance = a.variance;
+        b.dK = ws.T2; b.lddk = ld; b.partials = ws.gpart;
+        b.g_ell = g_ell; b.g_var = g_var; b.g_Z = g_Z; b.ldgz = a.D;
+        GPB_TRY(gram_bwd(s, b));
+    }
+    return GPB_OK;
+}
+
+int sgpr_grad_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const double* gout, double* g_Z, double* g_ell,
+                     double* g_var, double* g_obs, double* g_mean) {
+    GPB_TRY(check_args(a));
+    if (!g_Z || !g_ell || !g_var) return GPB_ERR_INVALID;
+    const int64_t M = a.M;
+    // Kzz term: both arguments of k(z, z') are Z
+    GramBwdDesc b;
+    b.kind = a.kind; b.N = M; b.M = M; b.D = a.D;
+    b.X = a.Z; b.ldx = a.ldz; b.Z = a.Z; b.ldz = a.ldz;
+    b.ell = a.ell; b.ell_is_scalar = a.ell_is_scalar; b.variance = a.variance;
+    b.dK = ws.dKzz; b.lddk = M; b.partials = ws.gpart;
+    b.g_ell = g_ell; b.g_var = g_var; b.g_X = g_Z; b.ldgx = a.D; b.g_Z = g_Z; b.ldgz = a.D;
+    GPB_TRY(gram_bwd(s, b));
+    GPB_TRY(sgpr_scalar_grads(s, ws.sc, ws.dots, a.variance, a.obs_stddev, g_var, g_obs, g_mean));
+    if (gout) {
+        GPB_TRY(scale_inplace(s, M * a.D, g_Z, gout));
+        GPB_TRY(scale_inplace(s, a.ell_is_scalar ? 1 : a.D, g_ell, gout));
+        GPB_TRY(scale_inplace(s, 1, g_var, gout));
+        if (g_obs) GPB_TRY(scale_inplace(s, 1, g_obs, gout));
+        if (g_mean) GPB_TRY(scale_inplace(s, 1, g_mean, gout));
+    }
+    return GPB_OK;
+}
+
+}  // namespace gpb

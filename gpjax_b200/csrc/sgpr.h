@@ -1,0 +1,55 @@
+// collapsed_elbo (SGPR) through row-additive statistics -- gpjax/objectives.py:321-416.
+// Host orchestration only (device pointers are opaque), same rules as algorithms.h.
+#pragma once
+#include "algorithms.h"
+
+namespace gpb {
+
+struct SgprArgs {
+    int kind = 0;
+    int64_t Nloc = 0;  // rows of this rank's shard
+    int64_t M = 0;     // inducing points
+    int D = 0;
+    const double* X = nullptr;  // [Nloc, D]
+    int64_t ldx = 0;
+    const double* y = nullptr;  // [Nloc]
+    const double* Z = nullptr;  // [M, D]
+    int64_t ldz = 0;
+    const double* ell = nullptr;
+    int ell_is_scalar = 0;
+    const double* variance = nullptr;
+    const double* obs_stddev = nullptr;
+    const double* mean_const = nullptr;  // nullable
+    double jitter = 1e-6;
+    int64_t block_rows = 32768;  // rows per streamed block
+};
+
+struct SgprWs {
+    FactorWs fz, fb;
+    double *Lz, *Linv, *Bmat, *LB, *Binv, *G1, *G2, *Tmp, *Caug, *dKzz;
+    double *psi, *a1, *w, *v, *u, *cvec, *rowsum, *sc, *dots;
+    double *T1, *T2;
+    double* gpart;
+    int* info2;  // [2]: info of chol(Kzz), chol(B)
+};
+
+int64_t sgpr_ws_bytes(int64_t M, int D, int64_t block_rows);
+int sgpr_ws_carve(void* buf, int64_t bytes, int64_t M, int D, int64_t block_rows, SgprWs* ws);
+inline int64_t sgpr_stats_ld(int64_t M) { return M + 2; }
+
+// Pass 1 (per rank): Paug[(M+2)x(M+2)] (row stride M+2, lower triangle) = local sums of
+//   [A~ ; d^T ; 1^T] [A~ ; d^T ; 1^T]^T  with  A~ = Lz^-1 Kzx  (UNSCALED by the noise).
+// It is exactly the quantity that is all-reduced over ranks (M^2 + 2M + 3 useful doubles).
+int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug);
+// Replicated M x M finish on the (all-reduced) statistics: ELBO value; with need_grad also the
+// adjoint matrices for pass 2 (kept in ws).
+int sgpr_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const double* Paug, int need_grad, double* elbo_out,
+                int* info_out);
+// Pass 2 (per rank): local contributions  g_Z[M,D], g_ell[D|1], g_var[1]  (overwritten).
+int sgpr_grad_local(stream_t s, const SgprArgs& a, const SgprWs& ws, double* g_Z, double* g_ell, double* g_var);
+// Replicated part added to the (all-reduced) local gradients: Kzz term + scalar terms; then
+// everything is scaled by *gout (null -> 1).  g_obs / g_mean are overwritten.
+int sgpr_grad_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const double* gout, double* g_Z, double* g_ell,
+                     double* g_var, double* g_obs, double* g_mean);
+
+}  // namespace gpb

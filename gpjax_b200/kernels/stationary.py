@@ -1,0 +1,85 @@
+"""Stationary kernels -- gpjax/kernels/stationary/{base,rbf,matern32,matern52}.py."""
+from __future__ import annotations
+
+import numbers
+import typing as tp
+
+import numpy as np
+import torch
+
+from ..parameters import NonNegativeReal, Parameter, PositiveReal
+from .base import AbstractKernel
+from .computations import AbstractKernelComputation
+
+
+def _shape_of(lengthscale) -> tuple:
+    if isinstance(lengthscale, Parameter):
+        return tuple(lengthscale.value.shape)
+    if isinstance(lengthscale, torch.Tensor):
+        return tuple(lengthscale.shape)
+    return np.shape(np.asarray(lengthscale))
+
+
+def _check_lengthscale(lengthscale: tp.Any):
+    """stationary/base.py:150-168."""
+    if isinstance(lengthscale, Parameter):
+        return _check_lengthscale(lengthscale.value)
+    if not isinstance(lengthscale, (numbers.Real, np.ndarray, torch.Tensor, list, tuple)) or isinstance(lengthscale, bool):
+        raise TypeError(f"Expected `lengthscale` to be a array-like. Got {lengthscale}.")
+    if isinstance(lengthscale, (np.ndarray, torch.Tensor, list)):
+        ls_shape = _shape_of(lengthscale)
+        if len(ls_shape) > 1:
+            raise ValueError(
+                f"Expected `lengthscale` to be a scalar or 1D array. Got `lengthscale` with shape {ls_shape}."
+            )
+
+
+def _check_lengthscale_dims_compat(lengthscale, n_dims):
+    """stationary/base.py:120-147."""
+    ls_shape = _shape_of(lengthscale)
+    if ls_shape == ():
+        return n_dims
+    if n_dims is None:
+        return ls_shape[0]
+    if ls_shape != (n_dims,):
+        raise ValueError(
+            "Expected `lengthscale` to be compatible with the number "
+            f"of input dimensions. Got `lengthscale` with shape {ls_shape}, "
+            f"but the number of input dimensions is {n_dims}."
+        )
+    return n_dims
+
+
+class StationaryKernel(AbstractKernel):
+    """stationary/base.py:42-106."""
+
+    _b200_kind: tp.Optional[int] = None
+
+    def __init__(self, active_dims=None, lengthscale=1.0, variance=1.0, n_dims: tp.Optional[int] = None,
+                 compute_engine: AbstractKernelComputation = None):
+        super().__init__(active_dims, n_dims, compute_engine)
+        _check_lengthscale(lengthscale)
+        self.n_dims = _check_lengthscale_dims_compat(lengthscale, self.n_dims)
+        self.lengthscale = lengthscale if isinstance(lengthscale, Parameter) else PositiveReal(lengthscale)
+        self.variance = variance if isinstance(variance, Parameter) else NonNegativeReal(variance)
+
+
+class RBF(StationaryKernel):
+    """k = s2 exp(-|x-y|^2 / (2 l^2))  (stationary/rbf.py:40-44)."""
+
+    name = "RBF"
+    _b200_kind = 0
+
+
+class Matern32(StationaryKernel):
+    """k = s2 (1 + sqrt3 tau) exp(-sqrt3 tau)  (stationary/matern32.py:41-54)."""
+
+    name = "Matérn32"
+    _b200_kind = 1
+
+
+class Matern52(StationaryKernel):
+    """k = s2 (1 + sqrt5 tau + 5/3 tau^2) exp(-sqrt5 tau)  (stationary/matern52.py:42-53)."""
+
+    name = "Matérn52"
+    _b200_kind = 2

@@ -1,0 +1,102 @@
+"""Type-dispatched lower_cholesky / solve / logdet / diag -- gpjax/linalg/operations.py:22-237.
+
+Dense and Triangular branches run on the hand-written CUDA path (blocked DMMA Cholesky, triangular
+solves through explicit diagonal-block inverses, fused diagonal log-sum).  Differences from the
+reference that callers should know:
+  * Dense `solve` / `logdet` factor with Cholesky instead of LU (identical for the SPD matrices every
+    call site on the hot path passes; a non-SPD matrix yields NaN exactly like jnp.linalg.cholesky).
+  * These free functions are forward-only; gradients flow through the fused objectives
+    (gpjax_b200.objectives), which carry their own analytic backward.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+from .operators import Dense, Diagonal, Identity, LinearOperator, Triangular
+
+
+def _factor(A: torch.Tensor):
+    """Cholesky of a dense SPD tensor -> (L storage with zero upper, workspace)."""
+    n = A.shape[0]
+    L = A.detach().clone().contiguous()
+    ws = ops.FactorWorkspace(n, 1, potri=False, device=A.device)
+    ops.potrf_lower_(L, ws, zero_upper=True)
+    return L, ws
+
+
+def lower_cholesky(A: LinearOperator) -> LinearOperator:
+    if isinstance(A, Identity):
+        return A
+    if isinstance(A, Diagonal):
+        return Diagonal(torch.sqrt(A.diagonal))
+    if isinstance(A, Triangular):
+        if A.lower:
+            return A
+        raise ValueError("lower_cholesky of an upper-triangular operator is not defined")
+    if isinstance(A, Dense):
+        L, ws = _factor(A.array)
+        out = Triangular(L, lower=True)
+        out._ws = ws
+        return out
+    return lower_cholesky(Dense(A.to_dense()))
+
+
+def _tri_storage(A: Triangular):
+    """(lower-triangular storage, workspace, trans) for a Triangular operator."""
+    if A._base is not None and A._base.lower:  # transposed view of a lower factor: no copy
+        base, trans, store = A._base, True, A._base.array
+    elif A.lower:
+        base, trans, store = A, False, A.array
+    else:  # genuinely upper storage: U = L^T with L = U^T (one materialised transpose)
+        base, trans, store = A, True, A.array.T
+    if not store.is_contiguous():
+        store = store.contiguous()
+    ws = getattr(base, "_ws", None)
+    if ws is None or ws.n < store.shape[0]:
+        ws = ops.FactorWorkspace(store.shape[0], 1, potri=False, device=store.device)
+        ops.diag_inverses(store, ws)
+        base._ws = ws
+    return store, ws, trans
+
+
+def solve(A: LinearOperator, b: torch.Tensor) -> torch.Tensor:
+    """operations.py:73-120 incl. the 1-D promote/squeeze rule."""
+    was_1d = b.ndim == 1
+    if isinstance(A, Identity):
+        return b
+    if isinstance(A, Diagonal):
+        return b / (A.diagonal if was_1d else A.diagonal[:, None])
+    if isinstance(A, Triangular):
+        store, ws, trans = _tri_storage(A)
+        if was_1d:
+            return ops.trsv_lower_(store, b.detach().clone().contiguous(), ws, trans=trans)
+        x = b.detach().clone().contiguous()
+        if x.shape[1] > ws.n:
+            ws = ops.FactorWorkspace(max(store.shape[0], x.shape[1]), 1, device=store.device)
+            ops.diag_inverses(store, ws)
+        return ops.trsm_lower_left_(store, x, ws, trans=trans)
+    # Dense (SPD): Cholesky, then two triangular solves
+    L = lower_cholesky(A if isinstance(A, Dense) else Dense(A.to_dense()))
+    return solve(L.T, solve(L, b))
+
+
+def logdet(A: LinearOperator) -> torch.Tensor:
+    """operations.py:123-181.  Triangular: sum(log(diag)) -- NO factor 2 (operations.py:142-144)."""
+    if isinstance(A, Identity):
+        return torch.zeros((), dtype=torch.float64, device=A._device)
+    if isinstance(A, Diagonal):
+        return torch.sum(torch.log(A.diagonal))
+    if isinstance(A, Triangular):
+        arr = A.array if A.array.stride(1) == 1 else A.array.T  # the diagonal is transpose-invariant
+        return ops.sum_log_diag(arr)
+    L = lower_cholesky(A if isinstance(A, Dense) else Dense(A.to_dense()))
+    return 2.0 * ops.sum_log_diag(L.array)
+
+
+def diag(A: LinearOperator) -> torch.Tensor:
+    if isinstance(A, Diagonal):
+        return A.diagonal
+    if isinstance(A, Identity):
+        return torch.ones(A.shape[0], dtype=torch.float64, device=A._device)
+    return torch.diagonal(A.to_dense() if not isinstance(A, (Dense, Triangular)) else A.array).clone()

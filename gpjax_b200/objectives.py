@@ -1,0 +1,70 @@
+"""conjugate_mll and collapsed_elbo -- gpjax/objectives.py:36-107 and :321-416.
+
+Same call signature as the reference (`Objective = Callable[[Module, Dataset], scalar]`,
+objectives.py:33); the returned scalar is a device tensor attached to the autograd graph through a
+fused custom backward, so user lambdas such as ``lambda p, d: -conjugate_mll(p, d)``
+(examples/regression.py:200) compose unchanged.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops, sgpr_ops
+from .dataset import Dataset
+from .mean_functions import Constant, Zero
+from .parameters import Parameter
+
+
+def _mean_constant(mean_function):
+    """Zero -> None; Constant -> its scalar tensor (objectives read the mean only as a vector m(x))."""
+    if not isinstance(mean_function, Constant):
+        raise NotImplementedError(
+            "the fused objectives support Zero / Constant mean functions (SURVEY section 2, component 15)"
+        )
+    if isinstance(mean_function, Zero):
+        return None
+    c = mean_function.constant
+    return c.value if isinstance(c, Parameter) else c
+
+
+def _kernel_args(kernel):
+    kind = kernel.compute_engine._kind(kernel)
+    return kind, kernel.lengthscale.value, kernel.variance.value
+
+
+def conjugate_mll(posterior, data: Dataset) -> torch.Tensor:
+    """log p(y | X, theta) of a conjugate GP: Sigma = Kxx + prior.jitter I + obs_stddev^2 I
+    (objectives.py:96-103), value through the fused Gram -> Cholesky -> solve/logdet pipeline."""
+    x, y = data.X, data.y
+    kernel = posterior.prior.kernel
+    kind, ell, var = _kernel_args(kernel)
+    xs = kernel.slice_input(x)
+    xs = xs if xs.is_contiguous() else xs.contiguous()
+    mean = _mean_constant(posterior.prior.mean_function)
+    if mean is not None:
+        mean = mean.to(xs.device)
+    return ops.conjugate_mll_fused(kind, xs, y, ell, var, posterior.likelihood.obs_stddev.value, mean,
+                                   float(posterior.prior.jitter))
+
+
+def collapsed_elbo(variational_family, data: Dataset, *, block_rows: int = sgpr_ops.DEFAULT_BLOCK_ROWS,
+                   group=None) -> torch.Tensor:
+    """Collapsed (Titsias) evidence lower bound (objectives.py:342-416).
+
+    `data` holds THIS rank's rows; when torch.distributed is initialised the row-additive statistics
+    and the gradient are all-reduced over `group`, so every rank returns the full-data ELBO."""
+    x, y = data.X, data.y
+    post = variational_family.posterior
+    kernel = post.prior.kernel
+    kind, ell, var = _kernel_args(kernel)
+    xs = kernel.slice_input(x)
+    xs = xs if xs.is_contiguous() else xs.contiguous()
+    z = kernel.slice_input(variational_family.inducing_inputs.value)
+    mean = _mean_constant(post.prior.mean_function)
+    if mean is not None:
+        mean = mean.to(xs.device)
+    return sgpr_ops.collapsed_elbo_fused(kind, xs, y, z, ell, var, post.likelihood.obs_stddev.value, mean,
+                                         float(variational_family.jitter), block_rows, group)
+
+
+__all__ = ["conjugate_mll", "collapsed_elbo"]

@@ -1,0 +1,141 @@
+"""collapsed_elbo (SGPR) on the C ABI: two streamed passes over the local rows, one all-reduce each.
+
+Row sharding: every rank holds a contiguous shard of (X, y); Z and the hyper-parameters
+are replicated.  The only exchange steps are
+  * forward : all-reduce(sum) of the (M+2)^2 augmented statistics  (33.6 MB at M = 2048),
+  * backward: all-reduce(sum) of [g_Z (M x D), g_lengthscale, g_variance].
+``torch.distributed`` (NCCL over NVLink on the GPU box, gloo in the CPU tests of the host logic)
+is only the plumbing for those two calls; everything else is the hand-written CUDA path.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _abi
+from ._lib import lib
+from .ops import _check_mat, _ell_args, _p, _scalar, _stream, require_cuda
+
+DEFAULT_BLOCK_ROWS = 32768
+
+
+def _world(group) -> int:
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group)
+    return 1
+
+
+def _all_reduce(t: torch.Tensor, group) -> None:
+    import torch.distributed as dist
+
+    if _world(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
+class _SgprState:
+    def __init__(self, m, d, block_rows, device):
+        self.nbytes = lib().gpb_sgpr_workspace_bytes(m, d, block_rows)
+        self.ws = torch.empty(max(self.nbytes // 8, 1), dtype=torch.float64, device=device)
+        self.generation = 0
+
+
+_CACHE: dict = {}
+
+
+def _state(m, d, block_rows, device) -> _SgprState:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), m, d, block_rows)
+    st = _CACHE.get(key)
+    if st is None:
+        _CACHE.clear()
+        st = _SgprState(m, d, block_rows, device)
+        _CACHE[key] = st
+    return st
+
+
+def release_buffers() -> None:
+    _CACHE.clear()
+
+
+def _forward_raw(st, kind, X, y, Z, ell_v, iso, var, sn, mean, jitter, block_rows, group, need_grad):
+    n_loc, D = X.shape
+    M = Z.shape[0]
+    L = lib()
+    P = torch.empty(L.gpb_sgpr_stats_count(M), dtype=torch.float64, device=Z.device)
+    rc = L.gpb_sgpr_stats(_stream(), kind, n_loc, M, D, _p(X), X.stride(0) if n_loc else D, _p(y), _p(Z), Z.stride(0),
+                          _p(ell_v), iso, _p(var), _p(sn), _p(mean), float(jitter), block_rows, _p(st.ws), st.nbytes,
+                          _p(P))
+    _abi.check(rc, "gpb_sgpr_stats")
+    _all_reduce(P, group)
+    val = torch.empty(1, dtype=torch.float64, device=Z.device)
+    info = torch.zeros(2, dtype=torch.int32, device=Z.device)
+    rc = L.gpb_sgpr_finish(_stream(), kind, M, D, _p(Z), Z.stride(0), _p(ell_v), iso, _p(var), _p(sn), block_rows,
+                           _p(st.ws), st.nbytes, _p(P), int(need_grad), _p(val), _p(info))
+    _abi.check(rc, "gpb_sgpr_finish")
+    st.generation += 1
+    return val, info
+
+
+class CollapsedElboFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kind, X, y, Z, ell, variance, obs_stddev, mean_const, jitter, block_rows, group):
+        _check_mat(X, "X")
+        _check_mat(Z, "Z")
+        require_cuda(y)
+        n_loc, D = X.shape
+        M = Z.shape[0]
+        y = y.reshape(-1).contiguous()
+        if y.numel() != n_loc:
+            raise ValueError("collapsed_elbo supports a single output column (y of shape [N, 1])")
+        Z = Z.contiguous()
+        ell_v, iso = _ell_args(ell, D)
+        var = _scalar(variance, "variance")
+        sn = _scalar(obs_stddev, "obs_stddev")
+        mean = None if mean_const is None else _scalar(mean_const, "mean constant")
+        block_rows = int(min(block_rows, max(n_loc, 1)))
+        st = _state(M, D, block_rows, Z.device)
+        need_grad = any(ctx.needs_input_grad)
+        val, info = _forward_raw(st, kind, X, y, Z, ell_v, iso, var, sn, mean, jitter, block_rows, group, need_grad)
+        ctx.cfg = (kind, iso, jitter, block_rows, group, mean is not None)
+        ctx.gen = st.generation
+        ctx.shapes = (ell.shape, variance.shape, obs_stddev.shape, None if mean_const is None else mean_const.shape)
+        ctx.save_for_backward(X, y, Z, ell_v, var, sn, mean if mean is not None else var)
+        return val.reshape(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        X, y, Z, ell_v, var, sn, mean = ctx.saved_tensors
+        kind, iso, jitter, block_rows, group, has_mean = ctx.cfg
+        n_loc, D = X.shape
+        M = Z.shape[0]
+        st = _state(M, D, block_rows, Z.device)
+        if st.generation != ctx.gen:
+            _forward_raw(st, kind, X, y, Z, ell_v, iso, var, sn, mean if has_mean else None, jitter, block_rows, group,
+                         True)
+        L = lib()
+        nl = 1 if iso else D
+        flat = torch.empty(M * D + nl + 1, dtype=torch.float64, device=Z.device)
+        g_Z, g_ell, g_var = flat[: M * D], flat[M * D: M * D + nl], flat[M * D + nl:]
+        rc = L.gpb_sgpr_grad_local(_stream(), kind, n_loc, M, D, _p(X), X.stride(0) if n_loc else D, _p(y), _p(Z),
+                                   Z.stride(0), _p(ell_v), iso, _p(var), _p(sn), _p(mean if has_mean else None),
+                                   block_rows, _p(st.ws), st.nbytes, _p(g_Z), _p(g_ell), _p(g_var))
+        _abi.check(rc, "gpb_sgpr_grad_local")
+        _all_reduce(flat, group)
+        g_sn = torch.empty(1, dtype=torch.float64, device=Z.device)
+        g_mean = torch.empty(1, dtype=torch.float64, device=Z.device)
+        g = gout.reshape(1).contiguous()
+        rc = L.gpb_sgpr_grad_finish(_stream(), kind, M, D, _p(Z), Z.stride(0), _p(ell_v), iso, _p(var), _p(sn),
+                                    block_rows, _p(st.ws), st.nbytes, _p(g), _p(g_Z), _p(g_ell), _p(g_var), _p(g_sn),
+                                    _p(g_mean))
+        _abi.check(rc, "gpb_sgpr_grad_finish")
+        s_ell, s_var, s_sn, s_mean = ctx.shapes
+        return (None, None, None, g_Z.reshape(M, D), g_ell.reshape(s_ell), g_var.reshape(s_var), g_sn.reshape(s_sn),
+                g_mean.reshape(s_mean) if has_mean else None, None, None, None)
+
+
+def collapsed_elbo_fused(kind, X, y, Z, ell, variance, obs_stddev, mean_const=None, jitter=1e-6,
+                         block_rows: int = DEFAULT_BLOCK_ROWS, group=None):
+    """ELBO of the collapsed (Titsias) bound for the rows held by this rank, all-reduced over `group`."""
+    return CollapsedElboFunction.apply(kind, X, y, Z, ell, variance, obs_stddev, mean_const, jitter, block_rows, group)

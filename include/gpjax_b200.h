@@ -43,7 +43,13 @@ extern "C" {
 
 const char* gpb_version(void);
 int gpb_max_input_dim(void); /* largest D the compiled kernels accept */
-int64_t gpb_block_size(void); /* NB of the blocked algorithms (256) */
+int64_t gpb_block_size(void); /* NB of the blocked algorithms */
+
+/* Measurement hooks for bench.py (off by default; not part of the reference-facing surface):
+ * while enabled, every DMMA GEMM launch is bracketed by CUDA events on its stream and every kernel
+ * launch of the library is counted.  gpb_profile_read blocks until the recorded events completed. */
+void gpb_profile_reset(int enable);
+int gpb_profile_read(double* gemm_ms, int64_t* gemm_launches, int64_t* all_launches);
 
 /* ---- K1: fused Gram / cross-covariance -------------------------------------------------------
  * Replaces DenseKernelComputation._cross_covariance (gpjax/kernels/computations/dense.py:32-36),
@@ -115,6 +121,42 @@ int gpb_mll_backward(void* stream, int kind, int64_t N, int D, const double* X, 
                      const double* obs_stddev, double* Sigma, int64_t lds, void* ws, int64_t ws_bytes,
                      const double* alpha, const double* gout, double* g_lengthscale, double* g_variance,
                      double* g_obs_stddev, double* g_mean_const);
+
+
+/* ---- collapsed_elbo (SGPR) value + analytic gradient, row-sharded ------------------------------
+ * Reference: gpjax/objectives.py:321-416.  The N-sized data enter only through row-additive
+ * statistics, which is what makes the path shard over GPUs:
+ *   1. gpb_sgpr_stats      (per rank, local rows)  -> Paug[(M+2) x (M+2)], row stride M+2, lower
+ *        triangle: sums of [A~; d^T; 1^T][A~; d^T; 1^T]^T with A~ = Lz^-1 Kzx (objectives.py:352-390)
+ *   2. all-reduce(sum) of Paug over the ranks (ncclAllReduce / torch.distributed; (M+2)^2 doubles)
+ *   3. gpb_sgpr_finish     (replicated)            -> ELBO (objectives.py:393-416) (+ adjoints)
+ *   4. gpb_sgpr_grad_local (per rank, local rows)  -> g_Z[M,D], g_lengthscale, g_variance partials
+ *   5. all-reduce(sum) of those three
+ *   6. gpb_sgpr_grad_finish (replicated)           -> adds the Kzz / scalar terms, applies *gout,
+ *        writes g_obs_stddev and g_mean_const.
+ * The same workspace must be passed to all calls of one evaluation.  info_out: int[2] =
+ * {chol(Kzz) failure, chol(I + A A^T) failure} (0 = ok; value is NaN otherwise). */
+int64_t gpb_sgpr_workspace_bytes(int64_t M, int D, int64_t block_rows);
+int64_t gpb_sgpr_stats_count(int64_t M);
+int gpb_sgpr_stats(void* stream, int kind, int64_t Nloc, int64_t M, int D, const double* X, int64_t ldx,
+                   const double* y, const double* Z, int64_t ldz, const double* lengthscale,
+                   int lengthscale_is_scalar, const double* variance, const double* obs_stddev,
+                   const double* mean_const, double jitter, int64_t block_rows, void* ws, int64_t ws_bytes,
+                   double* Paug);
+int gpb_sgpr_finish(void* stream, int kind, int64_t M, int D, const double* Z, int64_t ldz,
+                    const double* lengthscale, int lengthscale_is_scalar, const double* variance,
+                    const double* obs_stddev, int64_t block_rows, void* ws, int64_t ws_bytes,
+                    const double* Paug, int need_grad, double* elbo_out, int* info_out);
+int gpb_sgpr_grad_local(void* stream, int kind, int64_t Nloc, int64_t M, int D, const double* X, int64_t ldx,
+                        const double* y, const double* Z, int64_t ldz, const double* lengthscale,
+                        int lengthscale_is_scalar, const double* variance, const double* obs_stddev,
+                        const double* mean_const, int64_t block_rows, void* ws, int64_t ws_bytes, double* g_Z,
+                        double* g_lengthscale, double* g_variance);
+int gpb_sgpr_grad_finish(void* stream, int kind, int64_t M, int D, const double* Z, int64_t ldz,
+                         const double* lengthscale, int lengthscale_is_scalar, const double* variance,
+                         const double* obs_stddev, int64_t block_rows, void* ws, int64_t ws_bytes,
+                         const double* gout, double* g_Z, double* g_lengthscale, double* g_variance,
+                         double* g_obs_stddev, double* g_mean_const);
 
 #ifdef __cplusplus
 }

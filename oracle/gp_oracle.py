@@ -43,6 +43,8 @@ __all__ = [
     "conjugate_predict",
     "gram_longdouble",
     "conjugate_mll_longdouble",
+    "reference_cpu_mll_value_and_grad",
+    "reference_cpu_elbo_value_and_grad",
 ]
 
 
@@ -561,3 +563,47 @@ def conjugate_mll_longdouble(kind, X, y, lengthscale, variance, obs_stddev, mean
         w[i] = (d[i] - L[i, :i] @ w[:i]) / L[i, i]
     val = ld(-0.5) * (n * np.log(2 * ld(np.pi)) + 2 * np.sum(np.log(np.diag(L))) + w @ w)
     return val
+
+
+# ----------------------------------------------------------------------------------------
+# Timed CPU stand-ins for the reference's jax[cpu] path (bench.py cpu_baseline / --impl reference)
+# ----------------------------------------------------------------------------------------
+def reference_cpu_mll_value_and_grad(kind, X, y, lengthscale, variance, obs_stddev, mean_const=0.0, jitter=1e-6):
+    """conjugate_mll value + gradient in the reference's operation order on LAPACK:
+    LU slogdet + LU solve for the value (distributions.py:132-134 -> operations.py:109-111,163-165)
+    and the full inverse that reverse-mode of slogdet/solve materialises for the gradient
+    (SURVEY section 3.1).  O(N^2) memory beyond Sigma and its inverse; D-loop kept out of N^2 D storage."""
+    kind = _kind_id(kind)
+    X = np.asarray(X, np.float64)
+    y = np.asarray(y, np.float64).reshape(-1)
+    n, D = X.shape
+    ell = np.asarray(lengthscale, np.float64)
+    ell_v = np.full(D, float(ell)) if ell.ndim == 0 else ell
+    xs = X / ell_v
+    r2 = _r2_matrix(xs, xs)
+    K = _profile(kind, r2, variance)
+    Sigma = add_jitter(K, jitter) + np.eye(n) * obs_stddev**2
+    d = y - mean_const
+    logdet = np.linalg.slogdet(Sigma)[1]            # LU #1
+    alpha = np.linalg.solve(Sigma, d)               # LU #2
+    value = float(-0.5 * (n * np.log(2.0 * np.pi) + logdet + d @ alpha))
+    Sinv = np.linalg.inv(Sigma)                     # LU #3 + N-RHS solve
+    W = 0.5 * (np.outer(alpha, alpha) - Sinv)
+    G = W * _dK_dr2(kind, r2, K, variance)
+    g_ell = np.empty(D)
+    for k in range(D):
+        diff = xs[:, k : k + 1] - xs[:, k][None, :]
+        g_ell[k] = -2.0 / ell_v[k] * np.sum(G * diff * diff)
+    grads = {
+        "lengthscale": float(g_ell.sum()) if ell.ndim == 0 else g_ell,
+        "variance": float(np.sum(W * K) / variance),
+        "obs_stddev": float(2.0 * obs_stddev * np.trace(W)),
+        "mean_const": float(alpha.sum()),
+    }
+    return value, grads
+
+
+def reference_cpu_elbo_value_and_grad(kind, X, y, Z, lengthscale, variance, obs_stddev, mean_const=0.0, jitter=1e-6,
+                                      block=8192):
+    """collapsed_elbo value + gradient, blocked over rows (A never materialised for all N), LAPACK/BLAS."""
+    return collapsed_elbo_grad_closed_form(kind, X, y, Z, lengthscale, variance, obs_stddev, mean_const, jitter, block)

@@ -140,3 +140,39 @@ for n in (20000, 50000):
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/first_look.json", "w"), indent=1)
 print(json.dumps(out))
+
+# --- SGPR collapsed_elbo value + grad --------------------------------------------------------------
+from gpjax_b200.sgpr_ops import collapsed_elbo_fused  # noqa: E402
+import gpjax_b200.sgpr_ops as sgpr_ops  # noqa: E402
+
+for n, block in ((1_000_000, 32768), (1_000_000, 65536)):
+    m, d = 2048, 8
+    rng = np.random.default_rng(4)
+    X = torch.as_tensor(rng.uniform(-2, 2, (n, d)), device=dev)
+    y = torch.sin(X[:, :1]) + 0.1 * torch.randn(n, 1, dtype=torch.float64, device=dev)
+    Z = torch.as_tensor(np.random.default_rng(5).uniform(-2, 2, (m, d)), device=dev).requires_grad_(True)
+    ell = torch.as_tensor(np.linspace(0.8, 1.6, d), device=dev).requires_grad_(True)
+    var = torch.tensor(1.0, dtype=torch.float64, device=dev, requires_grad=True)
+    sn = torch.tensor(0.3, dtype=torch.float64, device=dev, requires_grad=True)
+    c = torch.tensor(0.0, dtype=torch.float64, device=dev, requires_grad=True)
+
+    def fwd():
+        return collapsed_elbo_fused(0, X, y, Z, ell, var, sn, c, 1e-6, block)
+
+    fwd().backward()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    v = fwd()
+    ev[1].record()
+    v.backward()
+    ev[2].record()
+    torch.cuda.synchronize()
+    tf, tbk = ev[0].elapsed_time(ev[1]) * 1e-3, ev[1].elapsed_time(ev[2]) * 1e-3
+    print(f"SGPR N={n} M={m} block={block}: fwd {tf:.3f} s bwd {tbk:.3f} s -> {n/(tf+tbk)/1e6:.3f} Mpoints/s, "
+          f"{4*n*m*m/(tf+tbk)/1e12:.2f} TF/s (4NM^2); elbo {v.item():.8f}")
+    out[f"sgpr_{n}_{block}"] = dict(fwd_s=tf, bwd_s=tbk, mpoints_s=n / (tf + tbk) / 1e6)
+    sgpr_ops.release_buffers()
+    del X, y
+    torch.cuda.empty_cache()
+json.dump(out, open("gpurun_out/first_look.json", "w"), indent=1)

@@ -309,3 +309,96 @@ int gram_bwd(stream_t, const GramBwdDesc& d) {
 }
 
 }  // namespace gpb
+
+// ---- SGPR helpers ---------------------------------------------------------------------------
+namespace gpb {
+int set_identity(stream_t, int64_t n, double* A, int64_t lda) {
+    for (int64_t r = 0; r < n; ++r)
+        for (int64_t c = 0; c < n; ++c) A[r * lda + c] = (r == c) ? 1.0 : 0.0;
+    return GPB_OK;
+}
+int vec_sum(stream_t, int64_t n, const double* x, double* out) {
+    double s = 0.0;
+    for (int64_t i = 0; i < n; ++i) s += x[i];
+    out[0] = s;
+    return GPB_OK;
+}
+int scale_inplace(stream_t, int64_t n, double* x, const double* f) {
+    if (!f || !x) return GPB_OK;
+    for (int64_t i = 0; i < n; ++i) x[i] *= f[0];
+    return GPB_OK;
+}
+int sgpr_aug_columns(stream_t, int64_t rows, double* T, int64_t ld, int64_t M, const double* y, const double* c) {
+    for (int64_t r = 0; r < rows; ++r) {
+        T[r * ld + M] = y[r] - (c ? c[0] : 0.0);
+        T[r * ld + M + 1] = 1.0;
+    }
+    return GPB_OK;
+}
+int sgpr_prepare(stream_t, int64_t M, const double* P, int64_t ldp, const double* obs_stddev, double* Bmat,
+                 double* psi, double* a1, double* sc) {
+    double s = obs_stddev[0] * obs_stddev[0];
+    double tr = 0.0;
+    for (int64_t r = 0; r < M; ++r) {
+        for (int64_t c = 0; c < M; ++c) {
+            double v = (c <= r) ? P[r * ldp + c] : P[c * ldp + r];
+            Bmat[r * M + c] = v / s + (r == c ? 1.0 : 0.0);
+        }
+        tr += P[r * ldp + r];
+        psi[r] = P[M * ldp + r] / std::sqrt(s);
+        a1[r] = P[(M + 1) * ldp + r] / std::sqrt(s);
+    }
+    sc[0] = P[M * ldp + M];
+    sc[1] = P[(M + 1) * ldp + M];
+    sc[2] = P[(M + 1) * ldp + M + 1];
+    sc[3] = tr / s;
+    sc[4] = s;
+    return GPB_OK;
+}
+int sgpr_value(stream_t, const double* sc, const double* hl, const double* wtw, const double* variance,
+               const int* info, double* out) {
+    double dd = sc[0], n = sc[2], trphi = sc[3], s = sc[4];
+    double v = 0.5 * ((-n * std::log(2.0 * M_PI * s) - 2.0 * hl[0] - (dd - wtw[0]) / s) - (n * variance[0] / s - trphi));
+    if (info && (info[0] != 0 || info[1] != 0)) v = std::numeric_limits<double>::quiet_NaN();
+    out[0] = v;
+    return GPB_OK;
+}
+int sgpr_adjoints(stream_t, int64_t M, const double* Binv, const double* Bmat, const double* v, const double* sc,
+                  double* G1, double* G2, double* u, double* rowsum) {
+    double s = sc[4];
+    for (int64_t r = 0; r < M; ++r) {
+        double acc = 0.0;
+        for (int64_t c = 0; c < M; ++c) {
+            double eye = (r == c) ? 1.0 : 0.0;
+            double dphi = 0.5 * (eye - Binv[r * M + c] - v[r] * v[c] / s);
+            double phi = Bmat[r * M + c] - eye;
+            G1[r * M + c] = (2.0 / s) * dphi;
+            G2[r * M + c] = dphi - 0.5 * phi;
+            acc += dphi * phi;
+        }
+        rowsum[r] = acc;
+        u[r] = v[r] / (s * std::sqrt(s));
+    }
+    return GPB_OK;
+}
+int sgpr_scalar_grads(stream_t, const double* sc, const double* dots, const double* variance, const double* obs_stddev,
+                      double* g_var, double* g_obs, double* g_mean) {
+    double dd = sc[0], sd = sc[1], n = sc[2], s = sc[4];
+    double psiv = dots[0], va1 = dots[1], dpp = dots[2];
+    double g_s = -n / (2 * s) + (dd - psiv) / (2 * s * s) + n * variance[0] / (2 * s * s) - (2 * dpp + psiv / s) / (2 * s);
+    if (g_var) g_var[0] += -n / (2 * s);
+    if (g_obs) g_obs[0] = 2 * obs_stddev[0] * g_s;
+    if (g_mean) g_mean[0] = -va1 / s + sd / s;
+    return GPB_OK;
+}
+}  // namespace gpb
+
+// measurement hooks are inert in the host model
+namespace gpb {
+void profile_reset(int) {}
+int profile_read(double* a, int64_t* b, int64_t* c) { if (a) *a = 0; if (b) *b = 0; if (c) *c = 0; return GPB_OK; }
+void profile_count_launch() {}
+bool profile_enabled() { return false; }
+void profile_gemm_begin(stream_t) {}
+void profile_gemm_end(stream_t) {}
+}  // namespace gpb

@@ -1,0 +1,85 @@
+"""collapsed_elbo value + gradient on the GPU (C ABI, streamed two-pass) vs the oracle's reverse-mode
+autodiff of the literal reference formulation (gpjax/objectives.py:342-416).  Tolerance 1e-8 relative."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as o
+
+pytestmark = pytest.mark.gpu
+KINDS = [(0, "rbf"), (1, "matern32"), (2, "matern52")]
+TOL = 1e-8
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
+
+
+def make(n, m, d, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-2.0, 2.0, (n, d))
+    y = np.sin(X[:, :1]) + 0.1 * rng.standard_normal((n, 1))
+    Z = rng.uniform(-2.0, 2.0, (m, d))
+    return X, y, Z
+
+
+def run_gpu(kind, X, y, Z, ell, var, sn, c, block_rows, jitter=1e-6):
+    from gpjax_b200.sgpr_ops import collapsed_elbo_fused
+
+    p = {k: dev(v).requires_grad_(True) for k, v in dict(Z=Z, ell=ell, var=var, sn=sn).items()}
+    mean = None if c is None else dev(c).requires_grad_(True)
+    val = collapsed_elbo_fused(kind, dev(X), dev(y), p["Z"], p["ell"], p["var"], p["sn"], mean, jitter, block_rows)
+    val.backward()
+    g = dict(inducing_inputs=p["Z"].grad.cpu().numpy(), lengthscale=p["ell"].grad.cpu().numpy(),
+             variance=p["var"].grad.item(), obs_stddev=p["sn"].grad.item())
+    if mean is not None:
+        g["mean_const"] = mean.grad.item()
+    return val.item(), g
+
+
+def check(val, g, ref, gref):
+    assert abs(val - ref) <= TOL * abs(ref)
+    for k in g:
+        a, b = np.asarray(g[k]).reshape(np.shape(gref[k])), np.asarray(gref[k])
+        assert np.max(np.abs(a - b)) <= TOL * max(np.max(np.abs(b)), 1e-6 * abs(ref)), k
+
+
+@pytest.mark.parametrize("kind,name", KINDS)
+@pytest.mark.parametrize("n,m,d,iso,block", [(10, 3, 1, True, 4), (200, 16, 3, False, 64), (1000, 130, 8, False, 300),
+                                             (777, 300, 6, False, 1000), (2500, 50, 1, True, 512)])
+def test_elbo_vs_autodiff_oracle(kind, name, n, m, d, iso, block):
+    X, y, Z = make(n, m, d, n + m)
+    ell = np.array(0.9) if iso else np.linspace(0.8, 1.6, d)
+    ref, gref = o.collapsed_elbo_value_and_grad_autodiff(name, X, y, Z, ell, 1.2, 0.5, 0.1)
+    val, g = run_gpu(kind, X, y, Z, ell, 1.2, 0.5, 0.1, block)
+    check(val, g, ref, gref)
+
+
+def test_elbo_block_size_independent_and_zero_mean():
+    X, y, Z = make(3000, 64, 8, 1)
+    ell = np.linspace(0.8, 1.6, 8)
+    v1, g1 = run_gpu(0, X, y, Z, ell, 1.0, 0.3, None, 128)
+    v2, g2 = run_gpu(0, X, y, Z, ell, 1.0, 0.3, None, 4096)
+    assert abs(v1 - v2) <= 1e-11 * abs(v1)
+    assert np.max(np.abs(g1["inducing_inputs"] - g2["inducing_inputs"])) <= 1e-9 * np.max(np.abs(g1["inducing_inputs"]))
+    ref = o.collapsed_elbo_streamed("rbf", X, y, Z, ell, 1.0, 0.3, 0.0)
+    assert abs(v1 - ref) <= TOL * abs(ref)
+
+
+def test_elbo_matches_mll_when_z_is_x():
+    """tests/test_objectives.py:170-199 of the reference (rel 1e-6 there; jitter sits on Kzz vs Kxx)."""
+    from gpjax_b200 import ops
+
+    X, y, _ = make(20, 1, 2, 5)
+    v, _ = run_gpu(0, X, y, X.copy(), np.array(1.0), 1.0, 1.0, None, 64)
+    mll = ops.conjugate_mll_fused(0, dev(X), dev(y), dev(np.array(1.0)), dev(1.0), dev(1.0), None, 1e-6).item()
+    assert abs(v - mll) <= 1e-5 * abs(mll)
+
+
+def test_elbo_config4_shape_small_sample_vs_closed_form():
+    """Config-4 geometry (D=8, M=2048) on a 20k-row sample against the oracle's streamed closed form."""
+    X, y, Z = make(20000, 2048, 8, 4)
+    ell = np.linspace(0.8, 1.6, 8)
+    ref, gref = o.collapsed_elbo_grad_closed_form("rbf", X, y, Z, ell, 1.0, 0.3, 0.0, block=4096)
+    val, g = run_gpu(0, X, y, Z, ell, 1.0, 0.3, 0.0, 8192)
+    check(val, g, ref, gref)

@@ -1,0 +1,179 @@
+"""Host-side mirror of the reference interface (no GPU needed): constructor validation, containers,
+parameter routing in fit -- modelled on the reference's tests/test_kernels/test_stationary.py:133-183,
+tests/test_fit.py:193-257,512-690, tests/test_linalg.py:491-558, tests/test_variational_families.py:236-262."""
+import numpy as np
+import pytest
+import torch
+
+import gpjax_b200 as gpx
+from gpjax_b200.parameters import (DEFAULT_BIJECTION, NonNegativeReal, Parameter, PositiveReal, Real,
+                                   SoftplusTransform, transform)
+
+CPU = torch.device("cpu")
+KERNELS = [gpx.kernels.RBF, gpx.kernels.Matern32, gpx.kernels.Matern52]
+
+
+@pytest.mark.parametrize("K", KERNELS)
+def test_kernel_ctor_validation(K):
+    with pytest.raises(ValueError):
+        K(lengthscale=-1.0)
+    with pytest.raises(ValueError):
+        K(variance=-1.0)
+    with pytest.raises(ValueError):
+        K(lengthscale=np.ones((2, 2)))
+    with pytest.raises(TypeError):
+        K(lengthscale="one")
+    with pytest.raises(ValueError):
+        K(lengthscale=[1.0, 2.0], n_dims=3)
+    k = K(lengthscale=[0.1, 0.2])
+    assert k.n_dims == 2 and isinstance(k.lengthscale, PositiveReal) and isinstance(k.variance, NonNegativeReal)
+    assert K(active_dims=[0, 2]).n_dims == 2
+    assert K().name in ("RBF", "Matérn32", "Matérn52")
+    assert isinstance(K().compute_engine, gpx.kernels.DenseKernelComputation)
+
+
+def test_engine_is_swappable_and_has_no_fallback():
+    k = gpx.kernels.RBF()
+    eng = gpx.kernels.DenseKernelComputation()
+    k.compute_engine = eng
+    assert k.compute_engine is eng
+
+    class Periodic(gpx.kernels.StationaryKernel):
+        name = "Periodic"
+
+    with pytest.raises(NotImplementedError):
+        Periodic().gram(torch.zeros((3, 1), dtype=torch.float64))
+
+
+def test_compute_on_cpu_tensor_fails_loudly():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        gpx.kernels.RBF().gram(torch.zeros((3, 1), dtype=torch.float64))
+
+
+def test_dataset_checks():
+    X, y = torch.zeros((5, 2), dtype=torch.float64), torch.zeros((5, 1), dtype=torch.float64)
+    D = gpx.Dataset(X=X, y=y)
+    assert D.n == 5 and D.in_dim == 2 and D.is_supervised()
+    assert (D + D).n == 10
+    with pytest.raises(ValueError):
+        gpx.Dataset(X=X, y=torch.zeros((4, 1), dtype=torch.float64))
+    with pytest.raises(ValueError):
+        gpx.Dataset(X=torch.zeros(5, dtype=torch.float64), y=y)
+    with pytest.raises(ValueError):
+        gpx.Dataset(X=X, y=torch.zeros(5, dtype=torch.float64))
+    with pytest.warns(UserWarning):
+        gpx.Dataset(X=X.float(), y=y)
+
+
+def test_add_jitter_and_psd():
+    from gpjax_b200.linalg import PSD, Dense, add_jitter, psd
+
+    M = torch.eye(3, dtype=torch.float64)
+    assert torch.equal(add_jitter(M, 0.5), 1.5 * torch.eye(3, dtype=torch.float64))
+    with pytest.raises(ValueError):
+        add_jitter(torch.zeros((2, 3), dtype=torch.float64))
+    with pytest.raises(ValueError):
+        add_jitter(torch.zeros(3, dtype=torch.float64))
+    assert PSD in psd(Dense(M)).annotations
+
+
+def test_containers_and_posterior_construction():
+    prior = gpx.gps.Prior(mean_function=gpx.mean_functions.Zero(), kernel=gpx.kernels.RBF())
+    assert prior.jitter == 1e-6
+    lik = gpx.likelihoods.Gaussian(num_datapoints=10)
+    assert float(lik.obs_stddev.value) == 1.0 and isinstance(lik.obs_stddev, NonNegativeReal)
+    post = prior * lik
+    assert isinstance(post, gpx.gps.ConjugatePosterior) and isinstance(lik * prior, gpx.gps.ConjugatePosterior)
+    q = gpx.variational_families.CollapsedVariationalGaussian(posterior=post, inducing_inputs=np.zeros((7, 1)))
+    assert q.num_inducing == 7 and isinstance(q.inducing_inputs, Real) and q.jitter == 1e-6
+
+    class NotGaussian(gpx.likelihoods.AbstractLikelihood):
+        pass
+
+    bad = gpx.gps.AbstractPosterior(prior, NotGaussian(10))
+    with pytest.raises(TypeError):
+        gpx.variational_families.CollapsedVariationalGaussian(posterior=bad, inducing_inputs=np.zeros((7, 1)))
+    m = gpx.mean_functions.Constant(Real(1.5))
+    assert m(torch.zeros((4, 2), dtype=torch.float64)).shape == (4, 1)
+
+
+def test_softplus_bijection_roundtrip():
+    sp = SoftplusTransform()
+    y = torch.tensor([1e-3, 0.3, 1.0, 25.0], dtype=torch.float64)
+    assert torch.allclose(sp(sp.inv(y)), y, rtol=1e-14)
+    p = {"a": PositiveReal(torch.tensor([1.0], dtype=torch.float64, device=CPU))}
+    out = transform(p, DEFAULT_BIJECTION)
+    assert abs(float(out["a"].value) - 1.3132617) < 1e-6  # docstring example of gpjax/parameters.py:33-35
+
+
+def _toy_model():
+    k = gpx.kernels.RBF(lengthscale=PositiveReal(torch.tensor(2.0, dtype=torch.float64, device=CPU)),
+                        variance=NonNegativeReal(torch.tensor(3.0, dtype=torch.float64, device=CPU)))
+    prior = gpx.gps.Prior(mean_function=gpx.mean_functions.Constant(Real(torch.tensor(1.0, dtype=torch.float64, device=CPU))),
+                          kernel=k)
+    lik = gpx.likelihoods.Gaussian(10, NonNegativeReal(torch.tensor(0.5, dtype=torch.float64, device=CPU)))
+    return prior * lik
+
+
+def _toy_objective(p, d):  # quadratic bowl in constrained space; exercises the bijection chain rule
+    return ((p.prior.kernel.lengthscale.value - 1.0) ** 2 + (p.prior.kernel.variance.value - 1.0) ** 2
+            + (p.likelihood.obs_stddev.value - 1.0) ** 2 + (p.prior.mean_function.constant.value - 0.0) ** 2).sum()
+
+
+def test_fit_host_logic_and_trainable_filters():
+    D = gpx.Dataset(X=torch.zeros((10, 1), dtype=torch.float64), y=torch.zeros((10, 1), dtype=torch.float64))
+    post = _toy_model()
+    opt, hist = gpx.fit(model=post, objective=_toy_objective, train_data=D, optim=gpx.optim.adam(0.1), num_iters=15,
+                        verbose=False)
+    assert isinstance(opt, gpx.gps.ConjugatePosterior) and hist.shape == (15,) and hist[-1] < hist[0]
+    assert float(post.prior.kernel.lengthscale.value) == 2.0  # the input model is not mutated
+    # freeze everything but PositiveReal (lengthscale): tests/test_fit.py:649-690
+    opt, _ = gpx.fit(model=post, objective=_toy_objective, train_data=D, optim=gpx.optim.adam(0.1), num_iters=5,
+                     trainable=PositiveReal, verbose=False)
+    assert float(opt.prior.kernel.variance.value) == 3.0 and float(opt.likelihood.obs_stddev.value) == 0.5
+    assert float(opt.prior.kernel.lengthscale.value) != 2.0
+    # predicate filter: variance frozen (tests/test_fit.py:512-545)
+    opt, _ = gpx.fit(model=post, objective=_toy_objective, train_data=D, optim=gpx.optim.sgd(0.1), num_iters=5,
+                     trainable=lambda path, p: "variance" not in path, verbose=False)
+    assert float(opt.prior.kernel.variance.value) == 3.0 and float(opt.prior.mean_function.constant.value) != 1.0
+    # Zero mean is never trained (tests/test_fit.py:548-646)
+    post.prior.mean_function = gpx.mean_functions.Zero()
+    assert all("mean_function" not in n for n, _ in post.named_parameters())
+
+
+def test_fit_argument_checks():
+    D = gpx.Dataset(X=torch.zeros((4, 1), dtype=torch.float64), y=torch.zeros((4, 1), dtype=torch.float64))
+    post, opt = _toy_model(), gpx.optim.adam(0.1)
+    kw = dict(model=post, objective=_toy_objective, train_data=D, optim=opt, verbose=False)
+    with pytest.raises(TypeError):
+        gpx.fit(**{**kw, "model": object()})
+    with pytest.raises(TypeError):
+        gpx.fit(**{**kw, "train_data": (1, 2)})
+    with pytest.raises(TypeError):
+        gpx.fit(**{**kw, "optim": 3})
+    with pytest.raises(ValueError):
+        gpx.fit(**kw, num_iters=0)
+    with pytest.raises(TypeError):
+        gpx.fit(**kw, num_iters=1.5)
+    with pytest.raises(ValueError):
+        gpx.fit(**kw, batch_size=0)
+    with pytest.raises(ValueError):
+        gpx.fit(**kw, log_rate=0)
+    with pytest.raises(TypeError):
+        gpx.fit(**{**kw, "verbose": "yes"})
+
+
+def test_fit_scipy_host_logic():
+    D = gpx.Dataset(X=torch.zeros((4, 1), dtype=torch.float64), y=torch.zeros((4, 1), dtype=torch.float64))
+    opt, hist = gpx.fit_scipy(model=_toy_model(), objective=_toy_objective, train_data=D, verbose=False)
+    assert hist[-1] < 1e-8 and abs(float(opt.prior.kernel.lengthscale.value) - 1.0) < 1e-4
+
+
+def test_adam_matches_optax_semantics():
+    """One step of adam from zero state moves every coordinate by -lr * sign(g) (bias-corrected)."""
+    opt = gpx.optim.adam(0.01)
+    p = {"a": torch.tensor([1.0, -2.0], dtype=torch.float64)}
+    g = {"a": torch.tensor([0.5, -3.0], dtype=torch.float64)}
+    upd, st = opt.update(g, opt.init(p), p)
+    assert torch.allclose(upd["a"], torch.tensor([-0.01, 0.01], dtype=torch.float64), atol=1e-9)
+    assert st["count"] == 1

@@ -142,3 +142,72 @@ def test_gram_and_gram_bwd_abi(lib, kind, name):
     assert lib.gpb_gram(None, kind, N, M, D, p(X), D, p(Z), D, p(ell), 0, p(var), 0.0, None, 0, p(K), M) == 0
     assert rel(K, o.cross_covariance(name, X, Z, ell, var[0])) <= 1e-13
     assert lib.gpb_gram(None, kind, N, M, 65, p(X), D, p(Z), D, p(ell), 0, p(var), 0.0, None, 0, p(K), M) == -2
+
+
+def _sgpr_run(lib, kind, X, y, Z, ell, iso, var, sn, c, jitter, block_rows, shards=1, gout=1.0):
+    """Drive the 6-step SGPR protocol of include/gpjax_b200.h on `shards` simulated ranks."""
+    N, D = X.shape
+    M = Z.shape[0]
+    ellv = np.atleast_1d(np.asarray(ell, np.float64)).copy()
+    var_a, sn_a = np.array([var]), np.array([sn])
+    c_a = None if c is None else np.array([c])
+    nbytes = lib.gpb_sgpr_workspace_bytes(M, D, block_rows)
+    cnt = lib.gpb_sgpr_stats_count(M)
+    bounds = np.linspace(0, N, shards + 1).astype(int)
+    wss = [np.zeros(nbytes // 8 + 8) for _ in range(shards)]
+    Ps = []
+    for r in range(shards):
+        Xr, yr = np.ascontiguousarray(X[bounds[r]:bounds[r + 1]]), np.ascontiguousarray(y[bounds[r]:bounds[r + 1]])
+        P = np.full(cnt, np.nan)
+        rc = lib.gpb_sgpr_stats(None, kind, len(Xr), M, D, p(Xr), D, p(yr), p(Z), D, p(ellv), int(iso), p(var_a),
+                                p(sn_a), p(c_a), jitter, block_rows, p(wss[r]), nbytes, p(P))
+        assert rc == 0
+        Ps.append(P)
+    Pall = np.sum(Ps, axis=0)  # the all-reduce
+    vals = []
+    for r in range(shards):
+        val, info = np.zeros(1), np.zeros(2, np.int32)
+        rc = lib.gpb_sgpr_finish(None, kind, M, D, p(Z), D, p(ellv), int(iso), p(var_a), p(sn_a), block_rows,
+                                 p(wss[r]), nbytes, p(Pall), 1, p(val), p(info))
+        assert rc == 0 and not info.any()
+        vals.append(val[0])
+    assert len(set(vals)) == 1  # replicated finish is bit-identical on every rank
+    gZ, gl, gv = [], [], []
+    for r in range(shards):
+        Xr, yr = np.ascontiguousarray(X[bounds[r]:bounds[r + 1]]), np.ascontiguousarray(y[bounds[r]:bounds[r + 1]])
+        a, b, cc = np.zeros((M, D)), np.zeros(1 if iso else D), np.zeros(1)
+        rc = lib.gpb_sgpr_grad_local(None, kind, len(Xr), M, D, p(Xr), D, p(yr), p(Z), D, p(ellv), int(iso), p(var_a),
+                                     p(sn_a), p(c_a), block_rows, p(wss[r]), nbytes, p(a), p(b), p(cc))
+        assert rc == 0
+        gZ.append(a), gl.append(b), gv.append(cc)
+    g_Z, g_ell, g_var = np.sum(gZ, axis=0), np.sum(gl, axis=0), np.sum(gv, axis=0)
+    g_sn, g_c, go = np.zeros(1), np.zeros(1), np.array([gout])
+    rc = lib.gpb_sgpr_grad_finish(None, kind, M, D, p(Z), D, p(ellv), int(iso), p(var_a), p(sn_a), block_rows,
+                                  p(wss[0]), nbytes, p(go), p(g_Z), p(g_ell), p(g_var), p(g_sn), p(g_c))
+    assert rc == 0
+    return vals[0], dict(lengthscale=g_ell, variance=g_var[0], obs_stddev=g_sn[0], mean_const=g_c[0],
+                         inducing_inputs=g_Z)
+
+
+@pytest.mark.parametrize("kind,name", KINDS)
+@pytest.mark.parametrize("N,M,D,iso,block,shards", [(60, 12, 3, False, 16, 1), (300, 40, 2, True, 128, 3),
+                                                     (500, 130, 8, False, 200, 2), (257, 30, 1, True, 64, 1),
+                                                     (300, 260, 3, False, 100, 2)])
+def test_sgpr_value_and_gradient(lib, kind, name, N, M, D, iso, block, shards):
+    X, y = data(N, D, N + M)
+    rng = np.random.default_rng(M)
+    Z = np.ascontiguousarray(rng.uniform(-2, 2, (M, D)))
+    ell = 0.9 if iso else np.linspace(0.8, 1.6, D)
+    val, g = _sgpr_run(lib, kind, X, y, Z, ell, iso, 1.3, 0.4, 0.2, 1e-6, block, shards, gout=-1.0)
+    ref, gref = o.collapsed_elbo_value_and_grad_autodiff(name, X, y, Z, ell, 1.3, 0.4, 0.2)
+    assert abs(val - ref) <= 1e-9 * abs(ref)
+    for k in gref:
+        a, b = -np.asarray(g[k]).reshape(np.shape(gref[k])), np.asarray(gref[k])
+        assert np.max(np.abs(a - b)) <= 1e-7 * max(np.max(np.abs(b)), 1e-8 * abs(ref)), k
+
+
+def test_sgpr_zero_mean_and_identity_with_mll(lib):
+    """tests/test_objectives.py:170-199 of the reference: ELBO(z = X) ~= MLL (rel 1e-6)."""
+    X, y = data(20, 2, 3)
+    val, _ = _sgpr_run(lib, 0, X, y, X.copy(), 1.0, True, 1.0, 1.0, None, 1e-6, 8)
+    assert abs(val - o.conjugate_mll("rbf", X, y, 1.0, 1.0, 1.0, 0.0)) <= 1e-5 * abs(val)
