@@ -17,6 +17,7 @@ const char* gpb_version(void) { return "gpjax_b200 0.1.0 (sm_100a, fp64 DMMA)"; 
 int gpb_max_input_dim(void) { return max_input_dim(); }
 int64_t gpb_block_size(void) { return NB; }
 void gpb_profile_reset(int enable) { profile_reset(enable); }
+void gpb_debug_set_gemm_variant(int v) { debug_set_gemm_variant(v); }
 int gpb_profile_read(double* gemm_ms, int64_t* gemm_launches, int64_t* all_launches) {
     return profile_read(gemm_ms, gemm_launches, all_launches);
 }

@@ -22,26 +22,32 @@ __global__ void __launch_bounds__(256) gemv_n_kernel(int64_t m, int64_t n, const
     if (lane == 0) y[row] = (beta == 0.0 ? 0.0 : beta * y[row]) + alpha * s;
 }
 
-// y[n] = beta*y + alpha * A[m x n]^T x : one thread per column, rows split over blockIdx.y chunks of
-// `rows_per_chunk`; chunk partials are combined with a second pass when more than one chunk exists.
+// y[n] = beta*y + alpha * A[m x n]^T x : a CTA owns 64 columns; its 4 thread groups take every 4th row
+// (coalesced 512-byte row segments, 4-way unrolled for memory-level parallelism) and combine in smem.
 __global__ void __launch_bounds__(256) gemv_t_kernel(int64_t m, int64_t n, const double* __restrict__ A, int64_t lda,
                                                      const double* __restrict__ x, double* __restrict__ y,
                                                      double alpha, double beta) {
-    int64_t col = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    __shared__ double xs[256];
-    double s = 0.0;
-    for (int64_t r0 = 0; r0 < m; r0 += 256) {
-        __syncthreads();
-        if (r0 + threadIdx.x < m) xs[threadIdx.x] = x[r0 + threadIdx.x];
-        __syncthreads();
-        int64_t rmax = min((int64_t)256, m - r0);
-        if (col < n) {
-            const double* a = A + r0 * lda + col;
-#pragma unroll 4
-            for (int64_t r = 0; r < rmax; ++r) s = fma(a[r * lda], xs[r], s);
+    __shared__ double red[4][64];
+    const int cg = threadIdx.x & 63, rg = threadIdx.x >> 6;
+    const int64_t col = (int64_t)blockIdx.x * 64 + cg;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    if (col < n) {
+        const double* a = A + col;
+        int64_t r = rg;
+        for (; r + 12 < m; r += 16) {
+            s0 = fma(a[r * lda], x[r], s0);
+            s1 = fma(a[(r + 4) * lda], x[r + 4], s1);
+            s2 = fma(a[(r + 8) * lda], x[r + 8], s2);
+            s3 = fma(a[(r + 12) * lda], x[r + 12], s3);
         }
+        for (; r < m; r += 4) s0 = fma(a[r * lda], x[r], s0);
     }
-    if (col < n) y[col] = (beta == 0.0 ? 0.0 : beta * y[col]) + alpha * s;
+    red[rg][cg] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (rg == 0 && col < n) {
+        double s = (red[0][cg] + red[1][cg]) + (red[2][cg] + red[3][cg]);
+        y[col] = (beta == 0.0 ? 0.0 : beta * y[col]) + alpha * s;
+    }
 }
 
 __global__ void __launch_bounds__(1024) sum_log_diag_kernel(int64_t n, const double* __restrict__ A, int64_t lda,
@@ -142,7 +148,7 @@ int gemv(stream_t s, int64_t m, int64_t n, const double* A, int64_t lda, int tra
         gemv_n_kernel<<<(unsigned)((m + 7) / 8), 256, 0, st>>>(m, n, A, lda, x, y, alpha, beta);
     } else {
         if (n == 0) return GPB_OK;
-        gemv_t_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m, n, A, lda, x, y, alpha, beta);
+        gemv_t_kernel<<<(unsigned)((n + 63) / 64), 256, 0, st>>>(m, n, A, lda, x, y, alpha, beta);
     }
     GPB_LAUNCH_CHECK();
     return GPB_OK;

@@ -69,6 +69,8 @@ struct GemmDesc {
 
 // C = beta*C + alpha * A * B^T on the FP64 tensor pipe (DMMA).
 int gemm(stream_t s, const GemmDesc& d);
+// tuning hook (bench scripts only): 0 = 8 warps x (32x32), 1 = 4 warps x (64x32), 2 = 4 warps x (32x64) [default]
+void debug_set_gemm_variant(int v);
 
 struct GramDesc {
     int kind = KIND_RBF;
@@ -186,6 +188,8 @@ int gram_bwd(stream_t s, const GramBwdDesc& d);
 int set_identity(stream_t s, int64_t n, double* A, int64_t lda);
 // out[0] = sum_i x[i]
 int vec_sum(stream_t s, int64_t n, const double* x, double* out);
+// y[i] += alpha * x[i]
+int axpy(stream_t s, int64_t n, double alpha, const double* x, double* y);
 // x[i] *= (*f) (f device scalar; null -> no-op)
 int scale_inplace(stream_t s, int64_t n, double* x, const double* f);
 // T[r*ld + M] = y[r] - (*c) ; T[r*ld + M + 1] = 1      (c may be null)

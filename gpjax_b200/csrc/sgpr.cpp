@@ -19,8 +19,9 @@ namespace gpb {
     } while (0)
 
 namespace {
+constexpr int SPLITK = 4;  // K-slices of the statistics SYRK (its output is only (M+2)^2: ~300 tiles)
 struct Lay {
-    int64_t fz, fb, mm[10], vec[7], sc, dots, T1, T2, gpart, info, total;
+    int64_t fz, fb, mm[10], vec[7], sc, dots, T1, T2, gpart, info, ppart, total;
     int64_t fz_bytes, fb_bytes;
 };
 Lay layout(int64_t M, int D, int64_t Bs) {
@@ -40,7 +41,8 @@ Lay layout(int64_t M, int D, int64_t Bs) {
     L.sc = take(16);
     L.dots = take(16);
     L.T1 = take(Bs * (M + 2));
-    L.T2 = take(Bs * (M + 2));
+    L.T2 = take((Bs + 16 * SPLITK) * (M + 2));
+    L.ppart = take(SPLITK * (M + 2) * (M + 2));
     int64_t p1 = gram_bwd_partials_count(Bs, M, D), p2 = gram_bwd_partials_count(M, M, D);
     L.gpart = take(p1 > p2 ? p1 : p2);
     L.info = take(8);
@@ -70,6 +72,7 @@ int sgpr_ws_carve(void* buf, int64_t bytes, int64_t M, int D, int64_t block_rows
     ws->T1 = b + L.T1;
     ws->T2 = b + L.T2;
     ws->gpart = b + L.gpart;
+    ws->Ppart = b + L.ppart;
     ws->info2 = reinterpret_cast<int*>(b + L.info);
     return GPB_OK;
 }
@@ -105,6 +108,7 @@ int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug) {
     GPB_TRY(set_identity(s, M, ws.Linv, M));
     GPB_TRY(trsm_lower_left(s, M, M, ws.Lz, M, ws.fz, ws.Linv, M, 0));
     GPB_TRY(fill2d(s, ld, ld, Paug, ld, 0.0));
+    GPB_TRY(fill2d(s, SPLITK * ld, ld, ws.Ppart, ld, 0.0));
     for (int64_t r0 = 0; r0 < a.Nloc; r0 += a.block_rows) {
         const int64_t rows = (a.Nloc - r0) < a.block_rows ? (a.Nloc - r0) : a.block_rows;
         // K_b^T = k(X_b, Z)   (objectives.py:355, one row block)
@@ -116,14 +120,21 @@ int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug) {
         g.krange = KR_B_LOWER;
         GPB_TRY(gemm(s, g));
         GPB_TRY(sgpr_aug_columns(s, rows, ws.T2, ld, M, a.y + r0, a.mean_const));
-        // Paug += [At_b | d_b | 1]^T [At_b | d_b | 1]   (objectives.py:390,404,407 in one SYRK)
+        // Paug += [At_b | d_b | 1]^T [At_b | d_b | 1]   (objectives.py:390,404,407 in one SYRK).
+        // The output has only ~(M/128)*(M/64)/2 tiles, so K (= rows) is split into SPLITK slices that run as
+        // one batched launch into separate partial sums (summed after the block loop).
+        const int S = rows >= 256 ? SPLITK : 1;
+        const int64_t Ks = align_up((rows + S - 1) / S, 16);
+        if (S * Ks > rows) GPB_TRY(fill2d(s, S * Ks - rows, ld, ws.T2 + rows * ld, ld, 0.0));
         GemmDesc u;
-        u.M = ld; u.N = ld; u.K = rows;
+        u.M = ld; u.N = ld; u.K = Ks;
         u.A = ws.T2; u.lda = ld; u.a_layout = LAYOUT_MN;
         u.B = ws.T2; u.ldb = ld; u.b_layout = LAYOUT_MN;
-        u.C = Paug; u.ldc = ld; u.beta = 1.0; u.mask = MASK_LOWER;
+        u.C = ws.Ppart; u.ldc = ld; u.beta = 1.0; u.mask = MASK_LOWER;
+        u.batch = S; u.strideA = Ks * ld; u.strideB = Ks * ld; u.strideC = ld * ld;
         GPB_TRY(gemm(s, u));
     }
+    for (int i = 0; i < SPLITK; ++i) GPB_TRY(axpy(s, ld * ld, 1.0, ws.Ppart + (int64_t)i * ld * ld, Paug));
     return GPB_OK;
 }
 

@@ -28,7 +28,7 @@ struct SgprWs {
     FactorWs fz, fb;
     double *Lz, *Linv, *Bmat, *LB, *Binv, *G1, *G2, *Tmp, *Caug, *dKzz;
     double *psi, *a1, *w, *v, *u, *cvec, *rowsum, *sc, *dots;
-    double *T1, *T2;
+    double *T1, *T2, *Ppart;
     double* gpart;
     int* info2;  // [2]: info of chol(Kzz), chol(B)
 };

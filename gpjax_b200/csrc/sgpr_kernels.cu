@@ -25,6 +25,11 @@ __global__ void scale_inplace_kernel(int64_t n, double* __restrict__ x, const do
     if (i < n) x[i] *= f[0];
 }
 
+__global__ void axpy_kernel(int64_t n, double alpha, const double* __restrict__ x, double* __restrict__ y) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = fma(alpha, x[i], y[i]);
+}
+
 __global__ void aug_columns_kernel(int64_t rows, double* __restrict__ T, int64_t ld, int64_t M,
                                    const double* __restrict__ y, const double* __restrict__ c) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -137,6 +142,13 @@ int vec_sum(stream_t s, int64_t n, const double* x, double* out) {
 int scale_inplace(stream_t s, int64_t n, double* x, const double* f) {
     if (n <= 0 || !f || !x) return GPB_OK;
     scale_inplace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, to_stream(s)>>>(n, x, f);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+int axpy(stream_t s, int64_t n, double alpha, const double* x, double* y) {
+    if (n <= 0) return GPB_OK;
+    axpy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, to_stream(s)>>>(n, alpha, x, y);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
 }

@@ -49,6 +49,7 @@ int64_t gpb_block_size(void); /* NB of the blocked algorithms */
  * while enabled, every DMMA GEMM launch is bracketed by CUDA events on its stream and every kernel
  * launch of the library is counted.  gpb_profile_read blocks until the recorded events completed. */
 void gpb_profile_reset(int enable);
+void gpb_debug_set_gemm_variant(int v); /* kernel-tuning hook for scripts/gemm_bench.py; 0 = default */
 int gpb_profile_read(double* gemm_ms, int64_t* gemm_launches, int64_t* all_launches);
 
 /* ---- K1: fused Gram / cross-covariance -------------------------------------------------------

@@ -323,6 +323,10 @@ int vec_sum(stream_t, int64_t n, const double* x, double* out) {
     out[0] = s;
     return GPB_OK;
 }
+int axpy(stream_t, int64_t n, double alpha, const double* x, double* y) {
+    for (int64_t i = 0; i < n; ++i) y[i] += alpha * x[i];
+    return GPB_OK;
+}
 int scale_inplace(stream_t, int64_t n, double* x, const double* f) {
     if (!f || !x) return GPB_OK;
     for (int64_t i = 0; i < n; ++i) x[i] *= f[0];
@@ -396,6 +400,7 @@ int sgpr_scalar_grads(stream_t, const double* sc, const double* dots, const doub
 // measurement hooks are inert in the host model
 namespace gpb {
 void profile_reset(int) {}
+void debug_set_gemm_variant(int) {}
 int profile_read(double* a, int64_t* b, int64_t* c) { if (a) *a = 0; if (b) *b = 0; if (c) *c = 0; return GPB_OK; }
 void profile_count_launch() {}
 bool profile_enabled() { return false; }

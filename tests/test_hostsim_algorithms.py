@@ -192,7 +192,7 @@ def _sgpr_run(lib, kind, X, y, Z, ell, iso, var, sn, c, jitter, block_rows, shar
 @pytest.mark.parametrize("kind,name", KINDS)
 @pytest.mark.parametrize("N,M,D,iso,block,shards", [(60, 12, 3, False, 16, 1), (300, 40, 2, True, 128, 3),
                                                      (500, 130, 8, False, 200, 2), (257, 30, 1, True, 64, 1),
-                                                     (300, 260, 3, False, 100, 2)])
+                                                     (300, 260, 3, False, 100, 2), (700, 20, 2, False, 300, 1)])
 def test_sgpr_value_and_gradient(lib, kind, name, N, M, D, iso, block, shards):
     X, y = data(N, D, N + M)
     rng = np.random.default_rng(M)
