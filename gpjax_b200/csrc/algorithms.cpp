@@ -27,7 +27,7 @@ namespace gpb {
 // -------------------------------------------------------------------------------------------
 namespace {
 struct WsLayout {
-    int64_t off_dinv, off_dinvt, off_sdiag, off_panel, off_small, off_vec, off_scal, off_part, total;
+    int64_t off_dinv, off_dinvt, off_sdiag, off_panel, off_panel2, off_small, off_vec, off_scal, off_part, total;
     int64_t partials_count;
 };
 WsLayout ws_layout(int64_t N, int D, int with_potri) {
@@ -43,6 +43,7 @@ WsLayout ws_layout(int64_t N, int D, int with_potri) {
     L.off_dinvt = take(blk);
     L.off_sdiag = take(with_potri ? blk : 0);
     L.off_panel = take(align_up(N, NB) * NB);
+    L.off_panel2 = take(align_up(N, NB) * NB);
     L.off_small = take(4 * NB * NB);
     L.off_vec = take(4 * align_up(N, NB));
     L.off_scal = take(16);
@@ -67,6 +68,7 @@ int factor_ws_carve(void* buf, int64_t bytes, int64_t N, int D, int with_potri, 
     ws->DinvT = b + L.off_dinvt;
     ws->Sdiag = with_potri ? b + L.off_sdiag : nullptr;
     ws->panel = b + L.off_panel;
+    ws->panel2 = b + L.off_panel2;
     ws->small = b + L.off_small;
     ws->vec = b + L.off_vec;
     ws->scal = b + L.off_scal;
@@ -134,33 +136,60 @@ static int diag_block(stream_t s, int n, double* Ablk, int64_t lda, double* D, d
     return GPB_OK;
 }
 
+// Right-looking blocked Cholesky with one-step LOOKAHEAD: the trailing update of step k is split into
+// the next block column (U1) and the rest (U2); as soon as U1 is done the latency-bound chain of step
+// k+1 (diagonal-block factorisation + inverse, panel X = P inv(L)^T) runs on a high-priority side stream
+// while U2 -- >95 % of the step's flops -- keeps the SMs busy on the caller's stream.
+static int potrf_panel(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& ws, int* info, int64_t k,
+                       double* panel) {
+    const int64_t j0 = k * NB;
+    const int nbk = (int)((N - j0) < NB ? (N - j0) : NB);
+    double* Dk = ws.Dinv + k * NB * NB;
+    GPB_TRY(diag_block(s, nbk, A + j0 * lda + j0, lda, Dk, ws.DinvT + k * NB * NB, ws.small, info, j0, 1));
+    const int64_t rows = N - j0 - nbk;
+    if (rows <= 0) return GPB_OK;
+    double* P = A + (j0 + nbk) * lda + j0;
+    GemmDesc g;  // X = P * inv(L_kk)^T -> contiguous copy, then back in place
+    g.M = rows; g.N = nbk; g.K = nbk;
+    g.A = P; g.lda = lda; g.B = Dk; g.ldb = NB; g.C = panel; g.ldc = NB;
+    g.krange = KR_B_LOWER;
+    GPB_TRY(gemm(s, g));
+    return copy2d(s, rows, nbk, panel, NB, P, lda);
+}
+
 int potrf_lower(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& ws, int* info) {
     if (N < 0 || (N > 0 && !A)) return GPB_ERR_INVALID;
     const int64_t nblk = nblocks(N);
-    for (int64_t k = 0; k < nblk; ++k) {
-        const int64_t j0 = k * NB;
-        const int nbk = (int)((N - j0) < NB ? (N - j0) : NB);
-        double* Akk = A + j0 * lda + j0;
-        double* Dk = ws.Dinv + k * NB * NB;
-        double* DTk = ws.DinvT + k * NB * NB;
-        GPB_TRY(diag_block(s, nbk, Akk, lda, Dk, DTk, ws.small, info, j0, 1));
-        const int64_t rows = N - j0 - nbk;
-        if (rows <= 0) continue;
-        double* P = A + (j0 + nbk) * lda + j0;
-        // panel: X = P * inv(L_kk)^T -> contiguous copy, then back in place
-        GemmDesc g;
-        g.M = rows; g.N = nbk; g.K = nbk;
-        g.A = P; g.lda = lda; g.B = Dk; g.ldb = NB; g.C = ws.panel; g.ldc = NB;
-        g.krange = KR_B_LOWER;
-        GPB_TRY(gemm(s, g));
-        GPB_TRY(copy2d(s, rows, nbk, ws.panel, NB, P, lda));
-        // trailing update (lower triangle only): A22 -= X X^T
-        GemmDesc u;
-        u.M = rows; u.N = rows; u.K = nbk;
-        u.A = ws.panel; u.lda = NB; u.B = ws.panel; u.ldb = NB;
-        u.C = A + (j0 + nbk) * lda + (j0 + nbk); u.ldc = lda;
+    if (nblk == 0) return GPB_OK;
+    stream_t side = side_stream(s, 0);
+    double* pcur = ws.panel;
+    double* pnext = ws.panel2;
+    GPB_TRY(potrf_panel(s, N, A, lda, ws, info, 0, pcur));
+    for (int64_t k = 0; k + 1 < nblk; ++k) {
+        const int64_t j1 = (k + 1) * NB;        // first row/column of the trailing matrix
+        const int64_t rows = N - j1;             // pcur holds X_k: rows x NB
+        const int64_t nb1 = rows < NB ? rows : NB;
+        GemmDesc u;  // U1: next block column, A[j1:, j1:j1+nb1] -= X X[0:nb1]^T (lower part)
+        u.M = rows; u.N = nb1; u.K = NB;
+        u.A = pcur; u.lda = NB; u.B = pcur; u.ldb = NB;
+        u.C = A + j1 * lda + j1; u.ldc = lda;
         u.alpha = -1.0; u.beta = 1.0; u.mask = MASK_LOWER;
         GPB_TRY(gemm(s, u));
+        const int64_t rest = rows - nb1;
+        if (rest > 0) {
+            GPB_TRY(stream_fork(s, side));
+            GPB_TRY(potrf_panel(side, N, A, lda, ws, info, k + 1, pnext));
+            GemmDesc v;  // U2: A[j1+nb1:, j1+nb1:] -= X[nb1:] X[nb1:]^T (lower part)
+            v.M = rest; v.N = rest; v.K = NB;
+            v.A = pcur + nb1 * NB; v.lda = NB; v.B = pcur + nb1 * NB; v.ldb = NB;
+            v.C = A + (j1 + nb1) * lda + (j1 + nb1); v.ldc = lda;
+            v.alpha = -1.0; v.beta = 1.0; v.mask = MASK_LOWER;
+            GPB_TRY(gemm(s, v));
+            GPB_TRY(stream_fork(side, s));
+        } else {
+            GPB_TRY(potrf_panel(s, N, A, lda, ws, info, k + 1, pnext));
+        }
+        double* t = pcur; pcur = pnext; pnext = t;
     }
     return GPB_OK;
 }

@@ -22,6 +22,7 @@ struct FactorWs {
     double* DinvT = nullptr;  // their transposes
     double* Sdiag = nullptr;  // nblk blocks [NB x NB], diagonal blocks of Sigma^-1 (potri only)
     double* panel = nullptr;  // [N x NB] contiguous panel copy
+    double* panel2 = nullptr; // second panel buffer (lookahead double-buffering)
     double* small = nullptr;  // 4 x [NB x NB] scratch
     double* vec = nullptr;    // 4 x [N] vectors (d, w, tmp, spare)
     double* scal = nullptr;   // 16 scalars

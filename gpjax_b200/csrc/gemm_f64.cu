@@ -23,7 +23,6 @@ namespace gpb {
 namespace {
 
 constexpr int BK = 16;
-constexpr int STAGES = 3;
 constexpr int PAD = 4;
 
 struct GemmParams {
@@ -184,8 +183,8 @@ __host__ __device__ inline void live_range(const GemmParams& p, int64_t tm, int6
     }
 }
 
-template <int BM, int BN, int WM, int WN, int ALAY, int BLAY>
-__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 2) gemm_f64_kernel(const GemmParams p) {
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB, int ALAY, int BLAY>
+__global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) gemm_f64_kernel(const GemmParams p) {
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
     constexpr int WARPS_N = BN / WN;
     constexpr int TM = WM / 8, TN = WN / 8;
@@ -412,12 +411,12 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, 2) gemm_f64_kernel
     }
 }
 
-template <int BM, int BN, int WM, int WN, int ALAY, int BLAY>
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB, int ALAY, int BLAY>
 int launch_gemm(cudaStream_t st, const GemmParams& p, int batch) {
     using GA = TileGeom<BM, ALAY>;
     using GB = TileGeom<BN, BLAY>;
     constexpr size_t smem = sizeof(double) * STAGES * (GA::SIZE + GB::SIZE);
-    auto kern = gemm_f64_kernel<BM, BN, WM, WN, ALAY, BLAY>;
+    auto kern = gemm_f64_kernel<BM, BN, WM, WN, STAGES, MINB, ALAY, BLAY>;
     static bool configured = false;  // per-instantiation, idempotent
     if (!configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -458,16 +457,18 @@ int launch_gemm(cudaStream_t st, const GemmParams& p, int batch) {
 static int g_variant = 2;
 void debug_set_gemm_variant(int v) { g_variant = v; }
 
-template <int BM, int BN, int WM, int WN>
-static int dispatch_layouts(cudaStream_t st, const GemmParams& p, const GemmDesc& d) {
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB>
+static int dispatch_layouts(cudaStream_t st, GemmParams p, const GemmDesc& d) {
+    p.tiles_m = (d.M + BM - 1) / BM;
+    p.tiles_n = (d.N + BN - 1) / BN;
     if (d.a_layout == LAYOUT_K && d.b_layout == LAYOUT_K)
-        return launch_gemm<BM, BN, WM, WN, LAYOUT_K, LAYOUT_K>(st, p, d.batch);
+        return launch_gemm<BM, BN, WM, WN, STAGES, MINB, LAYOUT_K, LAYOUT_K>(st, p, d.batch);
     if (d.a_layout == LAYOUT_K && d.b_layout == LAYOUT_MN)
-        return launch_gemm<BM, BN, WM, WN, LAYOUT_K, LAYOUT_MN>(st, p, d.batch);
+        return launch_gemm<BM, BN, WM, WN, STAGES, MINB, LAYOUT_K, LAYOUT_MN>(st, p, d.batch);
     if (d.a_layout == LAYOUT_MN && d.b_layout == LAYOUT_K)
-        return launch_gemm<BM, BN, WM, WN, LAYOUT_MN, LAYOUT_K>(st, p, d.batch);
+        return launch_gemm<BM, BN, WM, WN, STAGES, MINB, LAYOUT_MN, LAYOUT_K>(st, p, d.batch);
     if (d.a_layout == LAYOUT_MN && d.b_layout == LAYOUT_MN)
-        return launch_gemm<BM, BN, WM, WN, LAYOUT_MN, LAYOUT_MN>(st, p, d.batch);
+        return launch_gemm<BM, BN, WM, WN, STAGES, MINB, LAYOUT_MN, LAYOUT_MN>(st, p, d.batch);
     return GPB_ERR_INVALID;
 }
 
@@ -475,7 +476,6 @@ int gemm(stream_t s, const GemmDesc& d) {
     if (d.M < 0 || d.N < 0 || d.K < 0) return GPB_ERR_INVALID;
     if (d.M == 0 || d.N == 0 || d.batch == 0) return GPB_OK;
     if (!d.C || (d.K > 0 && (!d.A || !d.B))) return GPB_ERR_INVALID;
-    constexpr int BM = 128, BN = 64, WM = 32, WN = 32;
     GemmParams p;
     p.M = d.M; p.N = d.N; p.K = d.K;
     p.A = d.A; p.lda = d.lda; p.B = d.B; p.ldb = d.ldb; p.C = d.C; p.ldc = d.ldc;
@@ -485,8 +485,7 @@ int gemm(stream_t s, const GemmDesc& d) {
     p.krange = d.krange; p.kr_off = d.kr_off;
     p.strideA = d.strideA; p.strideB = d.strideB; p.strideC = d.strideC;
     p.batch = d.batch;
-    p.tiles_m = (d.M + BM - 1) / BM;
-    p.tiles_n = (d.N + BN - 1) / BN;
+    p.tiles_m = p.tiles_n = 0;  // set per tile shape in dispatch_layouts
     auto al16 = [](const void* ptr, int64_t ld, int64_t stride) {
         return ((reinterpret_cast<uintptr_t>(ptr) & 15) == 0) && (ld % 2 == 0) && (stride % 2 == 0);
     };
@@ -495,9 +494,12 @@ int gemm(stream_t s, const GemmDesc& d) {
     p.c_vec16 = al16(d.C, d.ldc, d.strideC);
     cudaStream_t st = to_stream(s);
     // measured on B200 (scripts/gemm_bench.py): 4 warps x (32x64) 34.7 TF/s, 4 x (64x32) 34.7, 8 x (32x32) 33.2
-    if (g_variant == 1) return dispatch_layouts<BM, BN, 64, 32>(st, p, d);
-    if (g_variant == 0) return dispatch_layouts<BM, BN, WM, WN>(st, p, d);
-    return dispatch_layouts<BM, BN, 32, 64>(st, p, d);
+    if (g_variant == 1) return dispatch_layouts<128, 64, 64, 32, 3, 2>(st, p, d);
+    if (g_variant == 0) return dispatch_layouts<128, 64, 32, 32, 3, 2>(st, p, d);
+    if (g_variant == 3) return dispatch_layouts<128, 128, 32, 64, 3, 1>(st, p, d);  // 8 warps, 1 CTA/SM
+    if (g_variant == 4) return dispatch_layouts<128, 128, 32, 64, 4, 1>(st, p, d);  // same, 4-stage ring
+    if (g_variant == 5) return dispatch_layouts<128, 128, 64, 32, 4, 1>(st, p, d);
+    return dispatch_layouts<128, 64, 32, 64, 3, 2>(st, p, d);
 }
 
 }  // namespace gpb

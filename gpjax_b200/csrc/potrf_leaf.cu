@@ -68,18 +68,16 @@ __global__ void __launch_bounds__(LT, 1) potrf_leaf_kernel(int n, double* __rest
                                                            double* __restrict__ DinvT, int64_t lddt, int* info,
                                                            int64_t global_row0, int factor) {
     extern __shared__ __align__(16) double sm[];
-    double* S = sm;                   // [LEAF][LDSM]
-    double* Lp = sm + LEAF * LDSM;    // [LEAF][PW] compact copy of the current panel
-    double* part = Lp + LEAF * PW;    // [LEAF][PW] partial sums of the second thread of a row
+    double* S = sm;  // [LEAF][LDSM]; only the lower triangle is ever read
     const int tid = threadIdx.x;
-    const int i = tid & (LEAF - 1);  // row owned by this thread
-    const int q = tid >> 7;          // 0 / 1: which half of the column range it takes
+    const int i = tid >> 1;  // row owned by this thread: the two threads of a row are adjacent lanes,
+    const int q = tid & 1;   // so their partial sums combine with one shuffle instead of shared memory
 
     // lower triangle of the block, identity padding beyond n (keeps partial panels well defined)
     {
-        const int c = tid & (LEAF - 1);
+        const int c = tid & (LEAF - 1), r0 = tid >> 7;
 #pragma unroll 8
-        for (int r = q; r < LEAF; r += 2) {  // independent, coalesced loads: 8 in flight per thread
+        for (int r = r0; r < LEAF; r += 2) {  // independent, coalesced loads: 8 in flight per thread
             double v = 0.0;
             if (r < n && c <= r) v = A[(int64_t)r * lda + c];
             else if (r >= n && c == r) v = 1.0;
@@ -92,8 +90,10 @@ __global__ void __launch_bounds__(LT, 1) potrf_leaf_kernel(int n, double* __rest
     if (factor) {
         for (int p0 = 0; p0 < n; p0 += PW) {
             unsigned bad = 0;
-            if (q == 0 && i >= p0 && i < n) {
-                double D[PW][PW], L[PW][PW], inv[PW], l[PW];
+            double l[PW];
+            const bool active = (q == 0 && i >= p0 && i < n);
+            if (active) {
+                double D[PW][PW], L[PW][PW], inv[PW];
 #pragma unroll
                 for (int r = 0; r < PW; ++r)
 #pragma unroll
@@ -109,11 +109,11 @@ __global__ void __launch_bounds__(LT, 1) potrf_leaf_kernel(int n, double* __rest
                     if (i < p0 + c) t = 0.0;       // strict upper part of the diagonal block
                     l[c] = t;
                 }
+            }
+            __syncthreads();  // every thread has read the un-factored diagonal block before its rows change
+            if (active) {
 #pragma unroll
-                for (int c = 0; c < PW; ++c) {
-                    S[i * LDSM + p0 + c] = l[c];
-                    Lp[i * PW + c] = l[c];
-                }
+                for (int c = 0; c < PW; ++c) S[i * LDSM + p0 + c] = l[c];
             }
             const int anybad = __syncthreads_or((int)bad);  // also publishes the panel
             if (anybad) {
@@ -122,13 +122,13 @@ __global__ void __launch_bounds__(LT, 1) potrf_leaf_kernel(int n, double* __rest
             }
             // rank-PW update of the trailing lower triangle
             if (i >= p0 + PW && i < n) {
-                double l[PW];
 #pragma unroll
-                for (int k = 0; k < PW; ++k) l[k] = Lp[i * PW + k];
+                for (int k = 0; k < PW; ++k) l[k] = S[i * LDSM + p0 + k];
                 for (int c = p0 + PW + q; c <= i; c += 2) {
                     double t = S[i * LDSM + c];
+                    const double* lc = S + c * LDSM + p0;  // panel entries of row c
 #pragma unroll
-                    for (int k = 0; k < PW; ++k) t = fma(-l[k], Lp[c * PW + k], t);
+                    for (int k = 0; k < PW; ++k) t = fma(-l[k], lc[k], t);
                     S[i * LDSM + c] = t;
                 }
             }
@@ -150,52 +150,46 @@ __global__ void __launch_bounds__(LT, 1) potrf_leaf_kernel(int n, double* __rest
 
     // ---- write L back (lower triangle only) --------------------------------------------------
     if (factor) {
-        const int c = tid & (LEAF - 1);
+        const int c = tid & (LEAF - 1), r0 = tid >> 7;
 #pragma unroll 8
-        for (int r = q; r < LEAF; r += 2)
+        for (int r = r0; r < LEAF; r += 2)
             if (r < n && c <= r) A[(int64_t)r * lda + c] = S[r * LDSM + c];
     }
     if (!Dinv && !DinvT) return;
     __syncthreads();
 
     // ---- in-place inverse, panels from the right ------------------------------------------------
+    // X21 = -(X22 L21) inv(L11).  L21 is read straight from S: it is only overwritten after the
+    // barrier that follows the product loop.
     const int plast = ((n - 1) / PW) * PW;
     for (int p0 = plast; p0 >= 0; p0 -= PW) {
         double X[PW][PW];
-        if (q == 0 && i >= p0 && i < LEAF) {
+        if (q == 0 && i >= p0) {
             double L[PW][PW];
 #pragma unroll
             for (int r = 0; r < PW; ++r)
 #pragma unroll
                 for (int c = 0; c <= r; ++c) L[r][c] = S[(p0 + r) * LDSM + p0 + c];
             trinv8(L, X);
-            if (i >= p0 + PW && i < n) {
-#pragma unroll
-                for (int c = 0; c < PW; ++c) Lp[i * PW + c] = S[i * LDSM + p0 + c];  // L21 row (still the factor)
-            }
         }
-        __syncthreads();
         double acc[PW];
 #pragma unroll
         for (int c = 0; c < PW; ++c) acc[c] = 0.0;
         if (i >= p0 + PW && i < n) {
             for (int k = p0 + PW + q; k <= i; k += 2) {  // X22[i][k] (already inverted) times L21[k][:]
                 const double x = S[i * LDSM + k];
+                const double* lk = S + k * LDSM + p0;
 #pragma unroll
-                for (int c = 0; c < PW; ++c) acc[c] = fma(x, Lp[k * PW + c], acc[c]);
-            }
-            if (q == 1) {
-#pragma unroll
-                for (int c = 0; c < PW; ++c) part[i * PW + c] = acc[c];
+                for (int c = 0; c < PW; ++c) acc[c] = fma(x, lk[c], acc[c]);
             }
         }
-        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < PW; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], 1);  // q=0 + q=1 halves
+        __syncthreads();  // every read of the old panel is done
         if (q == 0 && i >= p0 && i < n) {
             if (i >= p0 + PW) {
 #pragma unroll
-                for (int c = 0; c < PW; ++c) acc[c] += part[i * PW + c];
-#pragma unroll
-                for (int c = 0; c < PW; ++c) {  // X21 row = -(X22 L21)[i,:] * inv(L11)
+                for (int c = 0; c < PW; ++c) {
                     double t = 0.0;
 #pragma unroll
                     for (int cc = c; cc < PW; ++cc) t = fma(acc[cc], X[cc][c], t);
@@ -215,10 +209,10 @@ __global__ void __launch_bounds__(LT, 1) potrf_leaf_kernel(int n, double* __rest
     }
 
     {
-        const int c = tid & (LEAF - 1);
+        const int c = tid & (LEAF - 1), r0 = tid >> 7;
         if (c < n) {
 #pragma unroll 8
-            for (int r = q; r < n; r += 2) {
+            for (int r = r0; r < n; r += 2) {
                 if (Dinv) Dinv[(int64_t)r * ldd + c] = (c <= r) ? S[r * LDSM + c] : 0.0;
                 if (DinvT) DinvT[(int64_t)r * lddt + c] = (r <= c) ? S[c * LDSM + r] : 0.0;  // = Dinv[c][r]
             }
@@ -233,7 +227,7 @@ int potrf_leaf(stream_t s, int n, double* A, int64_t lda, double* Dinv, int64_t 
     if (n < 0 || n > LEAF) return GPB_ERR_INVALID;
     if (n == 0) return GPB_OK;
     if (!A) return GPB_ERR_INVALID;
-    constexpr size_t smem = sizeof(double) * (LEAF * LDSM + 2 * LEAF * PW);
+    constexpr size_t smem = sizeof(double) * (LEAF * LDSM);  // 129 KB: fits next to one resident GEMM CTA
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=

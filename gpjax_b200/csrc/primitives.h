@@ -213,6 +213,14 @@ int sgpr_adjoints(stream_t s, int64_t M, const double* Binv, const double* Bmat,
 int sgpr_scalar_grads(stream_t s, const double* sc, const double* dots, const double* variance,
                       const double* obs_stddev, double* g_var, double* g_obs, double* g_mean);
 
+// ---- intra-call concurrency (lookahead) ---------------------------------------------------------------
+// side_stream: a lazily created, higher-priority helper stream of the current device (index 0..3).
+// stream_fork(from, to): everything enqueued on `to` afterwards waits for what is on `from` now
+// (event record + wait; no host synchronisation).  Work put on a side stream must be joined back
+// into the caller's stream (stream_fork(side, main)) before the entry point returns.
+stream_t side_stream(stream_t main, int idx);
+int stream_fork(stream_t from, stream_t to);
+
 // ---- optional measurement hooks (bench.py roofline): off by default, zero cost when off ----------
 // enable != 0: every gemm() launch is bracketed by CUDA events on its own stream and every kernel
 // launch of the library is counted.  profile_read synchronises the recorded events.

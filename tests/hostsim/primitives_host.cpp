@@ -399,6 +399,8 @@ int sgpr_scalar_grads(stream_t, const double* sc, const double* dots, const doub
 
 // measurement hooks are inert in the host model
 namespace gpb {
+stream_t side_stream(stream_t main, int) { return main; }
+int stream_fork(stream_t, stream_t) { return GPB_OK; }
 void profile_reset(int) {}
 void debug_set_gemm_variant(int) {}
 int profile_read(double* a, int64_t* b, int64_t* c) { if (a) *a = 0; if (b) *b = 0; if (c) *c = 0; return GPB_OK; }
