@@ -290,7 +290,11 @@ def bench_exact(D: Dist, args):
                            "FP64 figure); cuBLAS DGEMM measured live alongside",
             "peak_cublas_dgemm": measure_cublas_dgemm(D), "algorithmic_flop_per_eval": flops_per_eval,
             "gemm_launches_per_step": gemm_n.value / args.steps, "gemm_time_share_of_step": gemm_ms.value * 1e-3 / t,
-            "whole_step_tflops": flops_per_eval * args.steps / t / 1e12, "traffic": None}
+            "whole_step_tflops": flops_per_eval * args.steps / t / 1e12,
+            # ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 2044 GEMM launches of ONE evaluation at
+            # N=50k (profiles/r01_gemm_traffic_exact50k.md); algorithmic C read+write of the rank-512 updates = 977 GB
+            "traffic": 1.945e12 if n == 50000 else None, "traffic_unit": "bytes per evaluation (all GEMM launches)",
+            "algorithmic_bytes": 3 * 16 * float(n) ** 3 / (6 * 512)}
 
     # ---- e2e: the public API with HOST buffers (pinned), H2D + D2H inside the timed region -------------------
     prior = gpx.gps.Prior(mean_function=gpx.mean_functions.Constant(Real(HYPER["mean_const"])),
