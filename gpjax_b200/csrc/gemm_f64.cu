@@ -5,17 +5,26 @@
 // reaches the same arithmetic through jnp.linalg.cholesky / jsp.linalg.solve_triangular /
 // jnp.matmul (gpjax/linalg/operations.py:55,107; gpjax/objectives.py:387-404).
 //
-// Design (B200: 128 FP64 flop/clk/SM, tensor == vector peak, so the kernel is built to keep the
-// DMMA pipe issue-saturated while everything else hides behind it):
-//   * CTA tile 128x64, 8 warps (4x2), warp tile 32x32 -> 16 DMMA accumulator tiles (64 regs),
-//     <=128 regs/thread so TWO CTAs are resident per SM: one CTA's C read-modify-write epilogue
-//     overlaps the other's main loop (the rank-256 updates are otherwise ~20 % epilogue).
-//   * K is consumed in 16-wide chunks through a 3-stage cp.async (LDGSTS) shared-memory ring;
-//     out-of-range rows / K tails are zero-filled by the copy itself (src-size operand).
+// Design (B200: 128 FP64 flop/clk/SM, tensor == vector peak = 37.2 TF/s, so the kernel is built to keep
+// the DMMA pipe issue-saturated while everything else hides behind it; all choices below were measured
+// with scripts/gemm_bench.py + ncu, see profiles/r01_summary.md):
+//   * CTA tile 128x64, 4 warps (4x1), warp tile 32x64 -> 32 DMMA accumulator tiles per warp (12 fragment
+//     loads per 32 DMMAs), ~230 regs, TWO CTAs resident per SM with independent barriers: one CTA's C
+//     read-modify-write epilogue and chunk barriers overlap the other's main loop.  (8 warps x 32x32:
+//     -4 %; a 128x128 CTA with one CTA/SM: -8 %.)
+//   * K is consumed in 16-wide chunks through a 3-stage cp.async (LDGSTS) shared-memory ring; interior
+//     tiles use a precomputed-pointer fast path (3 instructions per 16-byte copy), edge tiles a fully
+//     predicated path whose zero-fill comes from the copy's src-size operand.
 //   * Shared-memory rows are padded by 4 doubles (32 B) so the 8x4 / 4x8 fragment reads of one
-//     half-warp hit all 32 banks exactly once for both operand layouts.
-//   * Output masks (triangular / block-triangular) and triangular K-range skipping are applied
-//     per tile so SYRK / TRMM-shaped work never touches the dead half.
+//     half-warp hit all 32 banks exactly once for both operand layouts; fragments for k-slice kk+1 are
+//     fetched while slice kk feeds the tensor pipe.
+//   * Epilogue: the C tile is prefetched to L2 at kernel start (beta != 0) and interior tiles load all
+//     C fragments of a half tile back to back (one memory round trip per half instead of one per
+//     fragment: rank-256 updates went from 75 % to 89 % DMMA-pipe utilisation).
+//   * Grid: tile rows are folded (y, T-1-y) so triangular / block-triangular masks launch no dead CTAs,
+//     and live columns are walked in chunks of 64 tiles (blockIdx.z) so the B rows of a chunk stay
+//     L2-resident while all tile rows sweep them (DRAM reads of a 44.5k^2 rank-512 update: 41 GB -> 10 GB).
+//   * Triangular K-range skipping for operands with physically-zero triangles (explicit inverses).
 #include "common.cuh"
 
 namespace gpb {
