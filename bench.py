@@ -407,13 +407,67 @@ def bench_sgpr(D: Dist, args, steps=None, warmup=None):
                 roofline=roof, e2e=e2e, gpu_launches=int(all_n.value))
 
 
+def bench_svgp(D: Dist, args):
+    """BASELINE config 5: SVGP minibatch ELBO value+grad, Matern32, N=50M (num_datapoints), D=16, M=4096,
+    batch 65,536 per GPU drawn with replacement from the rank's shard (gpjax/fit.py:364-381), data-parallel."""
+    torch = D.torch
+    from gpjax_b200 import sgpr_ops, svgp_ops
+    from gpjax_b200._lib import lib
+
+    n_total, m, d = env_int("GPB_BENCH_SVGP_N", 50_000_000), env_int("GPB_BENCH_SVGP_M", 4096), 16
+    batch = env_int("GPB_BENCH_SVGP_BATCH", 65536)
+    shard = min(n_total // D.world, env_int("GPB_BENCH_SVGP_SHARD_ROWS", 4_000_000))  # resident part of the shard
+    gen = torch.Generator(device=D.dev).manual_seed(5 + D.rank)
+    X = torch.rand((shard, d), dtype=torch.float64, device=D.dev, generator=gen) * 4.0 - 2.0
+    y = torch.sin(X[:, :1]) + 0.1 * torch.randn((shard, 1), dtype=torch.float64, device=D.dev, generator=gen)
+    mk = lambda v: torch.as_tensor(np.asarray(v, np.float64), device=D.dev).requires_grad_(True)
+    Z = mk(synth(m, d, 6)[0])
+    ell, var, sn, c = mk(ell_ard(d)), mk(HYPER["variance"]), mk(HYPER["obs_stddev"]), mk(HYPER["mean_const"])
+    mu, W = mk(np.zeros((m, 1))), mk(np.eye(m))
+    params = (Z, ell, var, sn, c, mu, W)
+
+    def step():
+        for p in params:
+            p.grad = None
+        idx = torch.randint(0, shard, (batch,), device=D.dev, generator=gen)
+        v = svgp_ops.svgp_elbo_fused(1, X[idx], y[idx], Z, ell, var, sn, c, mu, W, float(n_total), HYPER["jitter"], batch)
+        v.backward()
+
+    steps = max(2, args.steps)
+    L = lib()
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    torch.cuda.synchronize()
+    L.gpb_profile_reset(1)
+    t = timed(D, step, 0, steps)
+    import ctypes as C
+
+    gemm_ms, gemm_n, all_n = C.c_double(), C.c_int64(), C.c_int64()
+    L.gpb_profile_read(C.byref(gemm_ms), C.byref(gemm_n), C.byref(all_n))
+    L.gpb_profile_reset(0)
+    value = D.world * batch * steps / t
+    flops = 4.0 * batch * m * m + 20.0 * m**3  # streamed passes + replicated M x M finish (see DESIGN section 9)
+    sgpr_ops.release_buffers()
+    return dict(metric="SVGP elbo value+grad minibatch points/s", value=value, unit="points/s", n_gpus=D.world, steps=steps,
+                ms_per_step=1e3 * t / steps, scaling="weak", higher_is_better=True, vs_baseline=None, dtype="f64",
+                data="synthetic",
+                config={"workload": f"svgp_elbo_value_and_grad_N{n_total}_M{m}_D{d}_B{batch}_Matern32", "N": n_total,
+                        "M": m, "D": d, "batch_per_gpu": batch, "resident_shard_rows": shard},
+                roofline={"bound": "tensor", "kernel": "gemm_f64_kernel (FP64 DMMA.8x8x4)",
+                          "achieved": flops * steps / (gemm_ms.value * 1e-3) / 1e12, "peak": NOMINAL_FP64_TFLOPS,
+                          "unit": "TFLOP/s", "frac": flops * steps / (gemm_ms.value * 1e-3) / 1e12 / NOMINAL_FP64_TFLOPS,
+                          "algorithmic_flop_per_step": flops, "gemm_time_over_step_time": gemm_ms.value * 1e-3 / t,
+                          "traffic": None},
+                gpu_launches=int(all_n.value))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto", choices=["auto", "exact", "sgpr"])
+    ap.add_argument("--workload", default="auto", choices=["auto", "exact", "sgpr", "svgp"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -436,6 +490,8 @@ def main():
             line = {**sg, "higher_is_better": True, "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
         else:
             line["sgpr"] = sg
+    if args.workload == "svgp":
+        line = bench_svgp(D, args)
     if D.rank == 0 and not args.no_cpu_baseline and D.world == 1:
         if args.workload in ("auto", "exact"):
             s = cpu_exact_sample(line["config"]["N"], 8)

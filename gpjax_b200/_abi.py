@@ -59,6 +59,14 @@ PROTOTYPES = {
         i32,
         [vp, i32, i64, i32, vp, i64, vp, i32, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp],
     ),
+    "gpb_svgp_finish": (
+        i32,
+        [vp, i32, i64, i32, vp, i64, vp, i32, vp, vp, vp, vp, vp, i64, f64, f64, i64, vp, i64, vp, i32, vp, vp],
+    ),
+    "gpb_svgp_grad_finish": (
+        i32,
+        [vp, i32, i64, i32, vp, i64, vp, i32, vp, vp, f64, i64, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64],
+    ),
 }
 
 ERRORS = {

@@ -20,7 +20,7 @@ OUT_DIR = os.path.join(HERE, "lib")
 OBJ_DIR = os.path.join(OUT_DIR, "obj")
 LIB_PATH = os.path.join(OUT_DIR, "libgpjax_b200.so")
 
-CU_SOURCES = ["gemm_f64.cu", "gram.cu", "potrf_leaf.cu", "level2.cu", "sgpr_kernels.cu", "profile.cu"]
+CU_SOURCES = ["gemm_f64.cu", "gram.cu", "potrf_leaf.cu", "level2.cu", "sgpr_kernels.cu", "svgp_kernels.cu", "profile.cu"]
 CPP_SOURCES = ["algorithms.cpp", "sgpr.cpp", "abi.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]

@@ -226,4 +226,31 @@ int gpb_sgpr_grad_finish(void* stream, int kind, int64_t M, int D, const double*
                             w, gout, g_Z, g_lengthscale, g_variance, g_obs_stddev, g_mean_const);
 }
 
+int gpb_svgp_finish(void* stream, int kind, int64_t M, int D, const double* Z, int64_t ldz, const double* lengthscale,
+                    int lengthscale_is_scalar, const double* variance, const double* obs_stddev,
+                    const double* mean_const, const double* mu, const double* W, int64_t ldw, double num_datapoints,
+                    double jitter, int64_t block_rows, void* ws, int64_t ws_bytes, const double* Paug, int need_grad,
+                    double* elbo_out, int* info_out) {
+    SgprWs w;
+    int rc = sgpr_ws_carve(ws, ws_bytes, M, D, block_rows, &w);
+    if (rc) return rc;
+    return svgp_finish(stream, sgpr_args(kind, 0, M, D, nullptr, 0, nullptr, Z, ldz, lengthscale, lengthscale_is_scalar,
+                                         variance, obs_stddev, mean_const, jitter, block_rows), w, Paug, mu, W, ldw,
+                       num_datapoints, need_grad, elbo_out, info_out);
+}
+
+int gpb_svgp_grad_finish(void* stream, int kind, int64_t M, int D, const double* Z, int64_t ldz,
+                         const double* lengthscale, int lengthscale_is_scalar, const double* variance,
+                         const double* obs_stddev, double jitter, int64_t block_rows, void* ws, int64_t ws_bytes,
+                         const double* gout, const double* W, int64_t ldw, double* g_Z, double* g_lengthscale,
+                         double* g_variance, double* g_obs_stddev, double* g_mean_const, double* g_mu, double* g_W,
+                         int64_t ldgw) {
+    SgprWs w;
+    int rc = sgpr_ws_carve(ws, ws_bytes, M, D, block_rows, &w);
+    if (rc) return rc;
+    return svgp_grad_finish(stream, sgpr_args(kind, 0, M, D, nullptr, 0, nullptr, Z, ldz, lengthscale,
+                                              lengthscale_is_scalar, variance, obs_stddev, nullptr, jitter, block_rows),
+                            w, gout, W, ldw, g_Z, g_lengthscale, g_variance, g_obs_stddev, g_mean_const, g_mu, g_W, ldgw);
+}
+
 }  // extern "C"

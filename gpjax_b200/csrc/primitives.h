@@ -213,6 +213,34 @@ int sgpr_adjoints(stream_t s, int64_t M, const double* Binv, const double* Bmat,
 int sgpr_scalar_grads(stream_t s, const double* sc, const double* dots, const double* variance,
                       const double* obs_stddev, double* g_var, double* g_obs, double* g_mean);
 
+
+// ---- SVGP (uncollapsed ELBO) finish helpers; statistics are the same Paug as SGPR -----------------------
+// out[0] = sum_i log|A[i*(lda+1)]|
+int sum_log_abs_diag(stream_t s, int64_t n, const double* A, int64_t lda, double* out);
+// Unpack Paug WITHOUT noise scaling: Phi = A~A~^T (full symmetric, ld M), psi = A~ d, a1 = A~ 1,
+//   sc = {dd, sd, B, tr(Phi), s = obs_stddev^2, coef = (num_datapoints / B) / s}
+int svgp_unpack(stream_t s, int64_t M, const double* Paug, int64_t ldp, const double* obs_stddev,
+                double num_datapoints, double* Phi, double* psi, double* a1, double* sc);
+// dots = {u.psi, u.u, |V|_F^2, <Phi,Ttil>, half_logdet_Kzz, sum log|W_ii|}:
+//   ELL = -1/2 [B log(2 pi s) + (dd - 2 u.psi + <Phi,Ttil> + B (var + jitter) - tr Phi) / s]
+//   KL  = 1/2 [u.u - M - 2 sum log|W_ii| + 2 half_logdet_Kzz + |V|_F^2],  out = (N/B) ELL - KL  (NaN if info[0])
+int svgp_value(stream_t s, int64_t M, const double* sc, const double* dots, const double* variance, double jitter,
+               const int* info, double* out);
+// G1 = coef (I - Ttil);  E = -coef sym(u psi^T) + coef/2 (PT + PT^T) - coef/2 Phi + Ttil/2 - I/2   (PT = Phi Ttil)
+int svgp_adjoints(stream_t s, int64_t M, const double* Phi, const double* Ttil, const double* PT, const double* u,
+                  const double* psi, const double* sc, double* G1, double* E);
+// tvec = coef (psi - Phiu) - u ;  uvec = coef u
+int svgp_vectors(stream_t s, int64_t M, const double* psi, const double* Phiu, const double* u, const double* sc,
+                 double* tvec, double* uvec);
+// H = coef * PhiV + V   (M x M, contiguous)
+int svgp_h(stream_t s, int64_t M, const double* PhiV, const double* V, const double* sc, double* H);
+// gW[i*ldg + i] += 1 / W[i*ldw + i]
+int svgp_gw_diag(stream_t s, int64_t M, const double* W, int64_t ldw, double* gW, int64_t ldg);
+// scalar gradients: g_var += -(N/B) B/(2s); g_obs = 2 sn (N/B)(-B/(2s) + Q/(2 s^2)); g_mean = coef (sd - u.a1) - sum(dF/dmu)
+//   dots2 = {u.a1, sum(dF/dmu)};  Q = dd - 2 u.psi + <Phi,Ttil> + B (var + jitter) - tr Phi
+int svgp_scalar_grads(stream_t s, const double* sc, const double* dots, const double* dots2, const double* variance,
+                      const double* obs_stddev, double jitter, double* g_var, double* g_obs, double* g_mean);
+
 // ---- intra-call concurrency (lookahead) ---------------------------------------------------------------
 // side_stream: a lazily created, higher-priority helper stream of the current device (index 0..3).
 // stream_fork(from, to): everything enqueued on `to` afterwards waits for what is on `from` now

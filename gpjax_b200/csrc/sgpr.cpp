@@ -21,7 +21,7 @@ namespace gpb {
 namespace {
 constexpr int SPLITK = 4;  // K-slices of the statistics SYRK (its output is only (M+2)^2: ~300 tiles)
 struct Lay {
-    int64_t fz, fb, mm[10], vec[7], sc, dots, T1, T2, gpart, info, ppart, total;
+    int64_t fz, fb, mm[13], vec[9], sc, dots, T1, T2, gpart, info, ppart, total;
     int64_t fz_bytes, fb_bytes;
 };
 Lay layout(int64_t M, int D, int64_t Bs) {
@@ -36,8 +36,8 @@ Lay layout(int64_t M, int D, int64_t Bs) {
     L.fb_bytes = factor_ws_bytes(M, D, 1);
     L.fz = take(L.fz_bytes / 8);
     L.fb = take(L.fb_bytes / 8);
-    for (int i = 0; i < 10; ++i) L.mm[i] = take(M * (M + 2));
-    for (int i = 0; i < 7; ++i) L.vec[i] = take(M + 2);
+    for (int i = 0; i < 13; ++i) L.mm[i] = take(M * (M + 2));
+    for (int i = 0; i < 9; ++i) L.vec[i] = take(M + 2);
     L.sc = take(16);
     L.dots = take(16);
     L.T1 = take(Bs * (M + 2));
@@ -63,10 +63,11 @@ int sgpr_ws_carve(void* buf, int64_t bytes, int64_t M, int D, int64_t block_rows
     double* b = static_cast<double*>(buf);
     GPB_TRY(factor_ws_carve(b + L.fz, L.fz_bytes, M, D, 0, &ws->fz));
     GPB_TRY(factor_ws_carve(b + L.fb, L.fb_bytes, M, D, 1, &ws->fb));
-    double** mm[10] = {&ws->Lz, &ws->Linv, &ws->Bmat, &ws->LB, &ws->Binv, &ws->G1, &ws->G2, &ws->Tmp, &ws->Caug, &ws->dKzz};
-    for (int i = 0; i < 10; ++i) *mm[i] = b + L.mm[i];
-    double** vv[7] = {&ws->psi, &ws->a1, &ws->w, &ws->v, &ws->u, &ws->cvec, &ws->rowsum};
-    for (int i = 0; i < 7; ++i) *vv[i] = b + L.vec[i];
+    double** mm[13] = {&ws->Lz, &ws->Linv, &ws->Bmat, &ws->LB, &ws->Binv, &ws->G1, &ws->G2, &ws->Tmp, &ws->Caug, &ws->dKzz,
+                       &ws->Wc, &ws->H, &ws->X3};
+    for (int i = 0; i < 13; ++i) *mm[i] = b + L.mm[i];
+    double** vv[9] = {&ws->psi, &ws->a1, &ws->w, &ws->v, &ws->u, &ws->cvec, &ws->rowsum, &ws->phiu, &ws->tvec};
+    for (int i = 0; i < 9; ++i) *vv[i] = b + L.vec[i];
     ws->sc = b + L.sc;
     ws->dots = b + L.dots;
     ws->T1 = b + L.T1;
@@ -91,6 +92,31 @@ static GramDesc gram_desc(const SgprArgs& a, const double* X, int64_t ldx, int64
     g.ell = a.ell; g.ell_is_scalar = a.ell_is_scalar; g.variance = a.variance;
     g.K = K; g.ldk = ldk;
     return g;
+}
+
+
+// Caug = [Linv^T G1 Linv | Linv^T uvec | 0]  (M x (M+2), row stride M+2): pass 2 forms dK_b^T = [K_b^T|d|1] Caug^T.
+// dKzz = Linv^T G2 Linv.
+static int build_pass2_adjoints(stream_t s, int64_t M, const SgprWs& ws, const double* G1, const double* G2,
+                                const double* uvec) {
+    const int64_t ld = M + 2;
+    GemmDesc t;
+    t.M = M; t.N = M; t.K = M;
+    t.A = G1; t.lda = M; t.B = ws.Linv; t.ldb = M; t.b_layout = LAYOUT_MN; t.C = ws.Tmp; t.ldc = M;
+    GPB_TRY(gemm(s, t));
+    GemmDesc c;
+    c.M = M; c.N = M; c.K = M;
+    c.A = ws.Linv; c.lda = M; c.a_layout = LAYOUT_MN; c.B = ws.Tmp; c.ldb = M; c.b_layout = LAYOUT_MN;
+    c.C = ws.Caug; c.ldc = ld;
+    GPB_TRY(gemm(s, c));
+    GPB_TRY(gemv(s, M, M, ws.Linv, M, 1, uvec, ws.cvec, 1.0, 0.0));
+    GPB_TRY(copy2d(s, M, 1, ws.cvec, 1, ws.Caug + M, ld));
+    GPB_TRY(fill2d(s, M, 1, ws.Caug + M + 1, ld, 0.0));
+    t.A = G2;
+    GPB_TRY(gemm(s, t));
+    c.C = ws.dKzz; c.ldc = M;
+    GPB_TRY(gemm(s, c));
+    return GPB_OK;
 }
 
 int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug) {
@@ -176,24 +202,7 @@ int sgpr_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const double* P
     GPB_TRY(dot(s, M, ws.psi, ws.v, ws.dots + 0));
     GPB_TRY(dot(s, M, ws.v, ws.a1, ws.dots + 1));
     GPB_TRY(vec_sum(s, M, ws.rowsum, ws.dots + 2));
-    // C = Linv^T G1 Linv  -> Caug[:, 0:M];  cvec = Linv^T u -> Caug[:, M];  Caug[:, M+1] = 0
-    GemmDesc t;
-    t.M = M; t.N = M; t.K = M;
-    t.A = ws.G1; t.lda = M; t.B = ws.Linv; t.ldb = M; t.b_layout = LAYOUT_MN; t.C = ws.Tmp; t.ldc = M;
-    GPB_TRY(gemm(s, t));
-    GemmDesc c;
-    c.M = M; c.N = M; c.K = M;
-    c.A = ws.Linv; c.lda = M; c.a_layout = LAYOUT_MN; c.B = ws.Tmp; c.ldb = M; c.b_layout = LAYOUT_MN;
-    c.C = ws.Caug; c.ldc = ld;
-    GPB_TRY(gemm(s, c));
-    GPB_TRY(gemv(s, M, M, ws.Linv, M, 1, ws.u, ws.cvec, 1.0, 0.0));
-    GPB_TRY(copy2d(s, M, 1, ws.cvec, 1, ws.Caug + M, ld));
-    GPB_TRY(fill2d(s, M, 1, ws.Caug + M + 1, ld, 0.0));
-    // dKzz = Linv^T G2 Linv
-    t.A = ws.G2;
-    GPB_TRY(gemm(s, t));
-    c.C = ws.dKzz; c.ldc = M;
-    GPB_TRY(gemm(s, c));
+    GPB_TRY(build_pass2_adjoints(s, M, ws, ws.G1, ws.G2, ws.u));
     return GPB_OK;
 }
 
@@ -244,6 +253,107 @@ int sgpr_grad_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const doub
         GPB_TRY(scale_inplace(s, 1, g_var, gout));
         if (g_obs) GPB_TRY(scale_inplace(s, 1, g_obs, gout));
         if (g_mean) GPB_TRY(scale_inplace(s, 1, g_mean, gout));
+    }
+    return GPB_OK;
+}
+
+// -------------------------------------------------------------------------------------------
+// SVGP (uncollapsed) ELBO -- gpjax/objectives.py:241-315.  With A~ = Lz^-1 Kzb, u = Lz^-1 (mu - mu_z),
+// V = Lz^-1 W (S = W W^T) and Ttil = u u^T + V V^T the minibatch enters ONLY through the same
+// row-additive statistics as the collapsed bound (Phi = A~A~^T, psi = A~ d, dd, sd, B):
+//   sum_b (y_b - mean_b)^2 = dd - 2 u.psi + u^T Phi u,   sum_b var_b = B (var + jitter) - tr Phi + tr(V^T Phi V)
+//   ELBO = (N/B) * { -1/2 [B log(2 pi s) + (dd - 2 u.psi + <Phi,Ttil> + B(var+jitter) - tr Phi)/s] }
+//          - 1/2 [u.u - M - logdet S + logdet Kzz + |V|_F^2]
+// so pass 1 (gpb_sgpr_stats), both all-reduces and pass 2 (gpb_sgpr_grad_local) are shared with SGPR;
+// only this M x M finish differs.
+// -------------------------------------------------------------------------------------------
+int svgp_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const double* Paug, const double* mu, const double* W,
+                int64_t ldw, double num_datapoints, int need_grad, double* elbo_out, int* info_out) {
+    GPB_TRY(check_args(a));
+    if (!Paug || !mu || !W || !elbo_out || !(num_datapoints > 0)) return GPB_ERR_INVALID;
+    const int64_t M = a.M, ld = M + 2;
+    double* Phi = ws.Bmat;
+    double* V = ws.LB;
+    double* Tt = ws.Binv;
+    double* uvec = ws.w;
+    double* dots = ws.dots;
+    GPB_TRY(svgp_unpack(s, M, Paug, ld, a.obs_stddev, num_datapoints, Phi, ws.psi, ws.a1, ws.sc));
+    GPB_TRY(sub_scalar(s, M, mu, a.mean_const, ws.v));                      // mu - mu_z
+    GPB_TRY(gemv(s, M, M, ws.Linv, M, 0, ws.v, uvec, 1.0, 0.0));            // u = Lz^-1 (mu - mu_z)
+    GPB_TRY(copy2d(s, M, M, W, ldw, ws.Wc, M));
+    GPB_TRY(zero_triangle(s, M, ws.Wc, M, 2));                              // LowerTriangular parameter
+    GemmDesc g;                                                             // V = Lz^-1 W
+    g.M = M; g.N = M; g.K = M;
+    g.A = ws.Linv; g.lda = M; g.B = ws.Wc; g.ldb = M; g.b_layout = LAYOUT_MN; g.C = V; g.ldc = M;
+    g.krange = KR_A_LOWER;
+    GPB_TRY(gemm(s, g));
+    g = GemmDesc();                                                         // Ttil = V V^T + u u^T
+    g.M = M; g.N = M; g.K = M; g.A = V; g.lda = M; g.B = V; g.ldb = M; g.C = Tt; g.ldc = M;
+    GPB_TRY(gemm(s, g));
+    g = GemmDesc();
+    g.M = M; g.N = M; g.K = 1; g.A = uvec; g.lda = 1; g.B = uvec; g.ldb = 1; g.C = Tt; g.ldc = M; g.beta = 1.0;
+    GPB_TRY(gemm(s, g));
+    GPB_TRY(dot(s, M, uvec, ws.psi, dots + 0));
+    GPB_TRY(dot(s, M, uvec, uvec, dots + 1));
+    GPB_TRY(dot(s, M * M, V, V, dots + 2));
+    GPB_TRY(dot(s, M * M, Phi, Tt, dots + 3));
+    GPB_TRY(sum_log_diag(s, M, ws.Lz, M, dots + 4));
+    GPB_TRY(sum_log_abs_diag(s, M, ws.Wc, M, dots + 5));
+    GPB_TRY(svgp_value(s, M, ws.sc, dots, a.variance, a.jitter, ws.info2, elbo_out));
+    if (info_out) GPB_TRY(copy2d(s, 1, 1, reinterpret_cast<const double*>(ws.info2), 1, reinterpret_cast<double*>(info_out), 1));
+    if (!need_grad) return GPB_OK;
+    g = GemmDesc();                                                         // PT = Phi Ttil
+    g.M = M; g.N = M; g.K = M; g.A = Phi; g.lda = M; g.B = Tt; g.ldb = M; g.C = ws.Tmp; g.ldc = M;
+    GPB_TRY(gemm(s, g));
+    GPB_TRY(svgp_adjoints(s, M, Phi, Tt, ws.Tmp, uvec, ws.psi, ws.sc, ws.G1, ws.G2));
+    GPB_TRY(gemv(s, M, M, Phi, M, 0, uvec, ws.phiu, 1.0, 0.0));
+    GPB_TRY(svgp_vectors(s, M, ws.psi, ws.phiu, uvec, ws.sc, ws.tvec, ws.u));
+    GPB_TRY(dot(s, M, uvec, ws.a1, dots + 8));
+    g = GemmDesc();                                                         // H = coef Phi V + V
+    g.M = M; g.N = M; g.K = M; g.A = Phi; g.lda = M; g.B = V; g.ldb = M; g.b_layout = LAYOUT_MN; g.C = ws.X3; g.ldc = M;
+    GPB_TRY(gemm(s, g));
+    GPB_TRY(svgp_h(s, M, ws.X3, V, ws.sc, ws.H));
+    GPB_TRY(build_pass2_adjoints(s, M, ws, ws.G1, ws.G2, ws.u));            // clobbers ws.Tmp (PT no longer needed)
+    return GPB_OK;
+}
+
+int svgp_grad_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const double* gout, const double* W, int64_t ldw,
+                     double* g_Z, double* g_ell, double* g_var, double* g_obs, double* g_mean, double* g_mu, double* g_W,
+                     int64_t ldgw) {
+    GPB_TRY(check_args(a));
+    if (!g_Z || !g_ell || !g_var || !W) return GPB_ERR_INVALID;
+    const int64_t M = a.M;
+    GramBwdDesc b;  // Kzz term
+    b.kind = a.kind; b.N = M; b.M = M; b.D = a.D;
+    b.X = a.Z; b.ldx = a.ldz; b.Z = a.Z; b.ldz = a.ldz;
+    b.ell = a.ell; b.ell_is_scalar = a.ell_is_scalar; b.variance = a.variance;
+    b.dK = ws.dKzz; b.lddk = M; b.partials = ws.gpart;
+    b.g_ell = g_ell; b.g_var = g_var; b.g_X = g_Z; b.ldgx = a.D; b.g_Z = g_Z; b.ldgz = a.D;
+    GPB_TRY(gram_bwd(s, b));
+    double* gmu = g_mu ? g_mu : ws.phiu;
+    GPB_TRY(gemv(s, M, M, ws.Linv, M, 1, ws.tvec, gmu, 1.0, 0.0));  // dF/dmu = Lz^-T [coef (psi - Phi u) - u]
+    GPB_TRY(vec_sum(s, M, gmu, ws.dots + 9));                       // mu - mu_z: the mean constant sees -1^T dF/dmu
+    GPB_TRY(svgp_scalar_grads(s, ws.sc, ws.dots, ws.dots + 8, a.variance, a.obs_stddev, a.jitter, g_var, g_obs, g_mean));
+    if (g_W) {  // tril( -Lz^-T (coef Phi + I) V + W^-T )
+        GPB_TRY(fill2d(s, M, M, g_W, ldgw, 0.0));
+        GemmDesc g;
+        g.M = M; g.N = M; g.K = M;
+        g.A = ws.Linv; g.lda = M; g.a_layout = LAYOUT_MN; g.B = ws.H; g.ldb = M; g.b_layout = LAYOUT_MN;
+        g.C = g_W; g.ldc = ldgw; g.alpha = -1.0; g.mask = MASK_LOWER;
+        GPB_TRY(gemm(s, g));
+        GPB_TRY(svgp_gw_diag(s, M, W, ldw, g_W, ldgw));
+    }
+    if (gout) {
+        GPB_TRY(scale_inplace(s, M * a.D, g_Z, gout));
+        GPB_TRY(scale_inplace(s, a.ell_is_scalar ? 1 : a.D, g_ell, gout));
+        GPB_TRY(scale_inplace(s, 1, g_var, gout));
+        if (g_obs) GPB_TRY(scale_inplace(s, 1, g_obs, gout));
+        if (g_mean) GPB_TRY(scale_inplace(s, 1, g_mean, gout));
+        if (g_mu) GPB_TRY(scale_inplace(s, M, g_mu, gout));
+        if (g_W) {
+            if (ldgw != M) return GPB_ERR_INVALID;  // contiguous gradient buffer expected
+            GPB_TRY(scale_inplace(s, M * M, g_W, gout));
+        }
     }
     return GPB_OK;
 }

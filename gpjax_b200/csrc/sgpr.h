@@ -26,8 +26,8 @@ struct SgprArgs {
 
 struct SgprWs {
     FactorWs fz, fb;
-    double *Lz, *Linv, *Bmat, *LB, *Binv, *G1, *G2, *Tmp, *Caug, *dKzz;
-    double *psi, *a1, *w, *v, *u, *cvec, *rowsum, *sc, *dots;
+    double *Lz, *Linv, *Bmat, *LB, *Binv, *G1, *G2, *Tmp, *Caug, *dKzz, *Wc, *H, *X3;
+    double *psi, *a1, *w, *v, *u, *cvec, *rowsum, *phiu, *tvec, *sc, *dots;
     double *T1, *T2, *Ppart;
     double* gpart;
     int* info2;  // [2]: info of chol(Kzz), chol(B)
@@ -51,5 +51,14 @@ int sgpr_grad_local(stream_t s, const SgprArgs& a, const SgprWs& ws, double* g_Z
 // everything is scaled by *gout (null -> 1).  g_obs / g_mean are overwritten.
 int sgpr_grad_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const double* gout, double* g_Z, double* g_ell,
                      double* g_var, double* g_obs, double* g_mean);
+
+// SVGP (uncollapsed ELBO, gpjax/objectives.py:241-315): same pass 1 / pass 2 / all-reduces as SGPR (sgpr_stats,
+// sgpr_grad_local); only the replicated M x M finish differs.  mu: variational mean [M]; W: lower-triangular
+// variational root covariance [M x M]; num_datapoints: N of the full data set (the batch size B comes out of Paug).
+int svgp_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const double* Paug, const double* mu, const double* W,
+                int64_t ldw, double num_datapoints, int need_grad, double* elbo_out, int* info_out);
+int svgp_grad_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const double* gout, const double* W, int64_t ldw,
+                     double* g_Z, double* g_ell, double* g_var, double* g_obs, double* g_mean, double* g_mu, double* g_W,
+                     int64_t ldgw);
 
 }  // namespace gpb

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import torch
 
-from . import ops, sgpr_ops
+from . import ops, sgpr_ops, svgp_ops
 from .dataset import Dataset
 from .mean_functions import Constant, Zero
 from .parameters import Parameter
@@ -67,4 +67,28 @@ def collapsed_elbo(variational_family, data: Dataset, *, block_rows: int = sgpr_
                                          float(variational_family.jitter), block_rows, group)
 
 
-__all__ = ["conjugate_mll", "collapsed_elbo"]
+def elbo(variational_family, data: Dataset, *, block_rows: int = sgpr_ops.DEFAULT_BLOCK_ROWS, group=None) -> torch.Tensor:
+    """Evidence lower bound of a VariationalGaussian (objectives.py:241-273):
+    sum_b E_q[log p(y_b | f(x_b))] * num_datapoints / batch - KL[q(u) || p(u)], Gaussian likelihood (analytical
+    integrator, integrators.py:151-158).  `data` is THIS rank's minibatch; with torch.distributed initialised the
+    statistics and gradients are all-reduced over `group` (effective batch = sum of the rank batches)."""
+    from .likelihoods import Gaussian
+
+    q = variational_family
+    post = q.posterior
+    if not isinstance(post.likelihood, Gaussian):
+        raise NotImplementedError("the fused ELBO covers the Gaussian likelihood (analytical integrator) only")
+    kernel = post.prior.kernel
+    kind, ell, var = _kernel_args(kernel)
+    xs = kernel.slice_input(data.X)
+    xs = xs if xs.is_contiguous() else xs.contiguous()
+    z = kernel.slice_input(q.inducing_inputs.value)
+    mean = _mean_constant(post.prior.mean_function)
+    if mean is not None:
+        mean = mean.to(xs.device)
+    return svgp_ops.svgp_elbo_fused(kind, xs, data.y, z, ell, var, post.likelihood.obs_stddev.value, mean,
+                                    q.variational_mean.value, q.variational_root_covariance.value,
+                                    float(post.likelihood.num_datapoints), float(q.jitter), block_rows, group)
+
+
+__all__ = ["conjugate_mll", "collapsed_elbo", "elbo"]

@@ -80,6 +80,18 @@ class Real(Parameter):
         super().__init__(value, tag, device)
 
 
+class LowerTriangular(Parameter):
+    """Lower-triangular matrix parameter (gpjax/parameters.py:125-137): square and zero above the diagonal."""
+
+    def __init__(self, value, tag: str = "lower_triangular", device=None):
+        super().__init__(value, tag, device)
+        v = self.value
+        if v.dim() != 2 or v.shape[0] != v.shape[1]:
+            raise ValueError(f"value needs to be a square matrix, got {v}")
+        if not bool((torch.tril(v) == v).all()):
+            raise ValueError(f"value needs to be a lower triangular matrix, got {v}")
+
+
 # ---- bijections (numpyro SoftplusTransform / IdentityTransform as used by parameters.py:140-146) ----
 class Bijection:
     def __call__(self, u: torch.Tensor) -> torch.Tensor:  # unconstrained -> constrained
@@ -105,10 +117,31 @@ class IdentityTransform(Bijection):
         return y
 
 
+class FillTriangularTransform(Bijection):
+    """Vector of n(n+1)/2 entries <-> lower-triangular n x n matrix (gpjax/numpyro_extras.py:12-106);
+    row-major order of the lower triangle."""
+
+    def __call__(self, u):
+        k = u.shape[-1]
+        n = int((math.isqrt(8 * k + 1) - 1) // 2)
+        if n * (n + 1) // 2 != k:
+            raise ValueError(f"a vector of length {k} does not fill a lower triangle")
+        idx = torch.tril_indices(n, n, device=u.device)
+        out = torch.zeros((n, n), dtype=u.dtype, device=u.device)
+        out[idx[0], idx[1]] = u
+        return out
+
+    def inv(self, y):
+        n = y.shape[-1]
+        idx = torch.tril_indices(n, n, device=y.device)
+        return y[idx[0], idx[1]]
+
+
 DEFAULT_BIJECTION: tp.Dict[str, Bijection] = {
     "positive": SoftplusTransform(),
     "non_negative": SoftplusTransform(),
     "real": IdentityTransform(),
+    "lower_triangular": FillTriangularTransform(),
 }
 
 

@@ -159,6 +159,27 @@ int gpb_sgpr_grad_finish(void* stream, int kind, int64_t M, int D, const double*
                          const double* gout, double* g_Z, double* g_lengthscale, double* g_variance,
                          double* g_obs_stddev, double* g_mean_const);
 
+/* ---- SVGP: uncollapsed minibatch ELBO (gpjax/objectives.py:241-315; VariationalGaussian.prior_kl / predict,
+ * variational_families.py:169-285; KL, distributions.py:188-228; analytical Gaussian integrator,
+ * integrators.py:151-158) with the analytic gradient.  The minibatch enters only through the SAME statistics as
+ * the collapsed bound, so the protocol reuses the SGPR entry points:
+ *   gpb_sgpr_stats (jitter = q.jitter) -> all-reduce -> gpb_svgp_finish -> gpb_sgpr_grad_local -> all-reduce
+ *   -> gpb_svgp_grad_finish.
+ * mu: variational_mean [M]; W: variational_root_covariance [M x M] lower triangular (strict upper ignored);
+ * num_datapoints: likelihood.num_datapoints (the batch size is taken from the reduced statistics, so with G
+ * ranks the effective batch is the sum of the rank batches).  g_W receives the lower triangle (upper zero). */
+int gpb_svgp_finish(void* stream, int kind, int64_t M, int D, const double* Z, int64_t ldz,
+                    const double* lengthscale, int lengthscale_is_scalar, const double* variance,
+                    const double* obs_stddev, const double* mean_const, const double* mu, const double* W,
+                    int64_t ldw, double num_datapoints, double jitter, int64_t block_rows, void* ws,
+                    int64_t ws_bytes, const double* Paug, int need_grad, double* elbo_out, int* info_out);
+int gpb_svgp_grad_finish(void* stream, int kind, int64_t M, int D, const double* Z, int64_t ldz,
+                         const double* lengthscale, int lengthscale_is_scalar, const double* variance,
+                         const double* obs_stddev, double jitter, int64_t block_rows, void* ws, int64_t ws_bytes,
+                         const double* gout, const double* W, int64_t ldw, double* g_Z, double* g_lengthscale,
+                         double* g_variance, double* g_obs_stddev, double* g_mean_const, double* g_mu, double* g_W,
+                         int64_t ldgw);
+
 #ifdef __cplusplus
 }
 #endif

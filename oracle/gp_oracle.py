@@ -45,6 +45,9 @@ __all__ = [
     "conjugate_mll_longdouble",
     "reference_cpu_mll_value_and_grad",
     "reference_cpu_elbo_value_and_grad",
+    "svgp_elbo",
+    "svgp_elbo_value_and_grad_autodiff",
+    "svgp_predict",
 ]
 
 
@@ -607,3 +610,101 @@ def reference_cpu_elbo_value_and_grad(kind, X, y, Z, lengthscale, variance, obs_
                                       block=8192):
     """collapsed_elbo value + gradient, blocked over rows (A never materialised for all N), LAPACK/BLAS."""
     return collapsed_elbo_grad_closed_form(kind, X, y, Z, lengthscale, variance, obs_stddev, mean_const, jitter, block)
+
+
+# ----------------------------------------------------------------------------------------
+# section 8f rank 1: SVGP elbo -- gpjax/objectives.py:241-315, variational_families.py:169-285,
+# distributions.py:188-228, integrators.py:151-158
+# ----------------------------------------------------------------------------------------
+def svgp_elbo(kind, X, y, Z, lengthscale, variance, obs_stddev, mean_const, var_mean, var_sqrt, num_datapoints,
+              jitter=1e-6):
+    """Literal NumPy restatement: prior_kl (KL[N(mu,S)||N(mu_z,Kzz)]) + per-point predictive moments
+    (VariationalGaussian.predict evaluated one point at a time, incl. its add_jitter on the 1x1 covariance)
+    + the analytical Gaussian expected log-likelihood, scaled by num_datapoints / batch."""
+    kind = _kind_id(kind)
+    X = np.asarray(X, np.float64)
+    y = np.asarray(y, np.float64).reshape(-1)
+    Z = np.asarray(Z, np.float64)
+    mu = np.asarray(var_mean, np.float64).reshape(-1)
+    W = np.tril(np.asarray(var_sqrt, np.float64))
+    m, b = Z.shape[0], X.shape[0]
+    s = obs_stddev**2
+    Kzz = add_jitter(gram(kind, Z, lengthscale, variance), jitter)
+    # prior_kl: variational_families.py:169-213 -> distributions.py:188-228
+    S = W @ W.T
+    sqrt_p = np.linalg.cholesky(Kzz)
+    sqrt_q = np.linalg.cholesky(S)
+    diff = mean_const - mu
+    trace = np.sum(np.square(sla.solve_triangular(sqrt_p, sqrt_q, lower=True)))
+    mahal = np.sum(np.square(sla.solve_triangular(sqrt_p, diff, lower=True)))
+    kl = 0.5 * (mahal - m - np.linalg.slogdet(S)[1] + np.linalg.slogdet(Kzz)[1] + trace)
+    # predict: variational_families.py:234-285 (vectorised over the batch, diagonal only)
+    Lz = sqrt_p
+    Kzt = cross_covariance(kind, Z, X, lengthscale, variance)
+    Lz_inv_Kzt = sla.solve_triangular(Lz, Kzt, lower=True)
+    Kzz_inv_Kzt = sla.solve_triangular(Lz.T, Lz_inv_Kzt, lower=False)
+    Ktz_Kzz_inv_sqrt = Kzz_inv_Kzt.T @ W
+    mean = mean_const + Kzz_inv_Kzt.T @ (mu - mean_const)
+    var = variance - np.sum(Lz_inv_Kzt**2, axis=0) + np.sum(Ktz_Kzz_inv_sqrt**2, axis=1) + jitter
+    # integrators.py:151-158
+    ell = -0.5 * np.sum(np.log(2.0 * np.pi) + np.log(s) + ((y - mean) ** 2 + var) / s)
+    return float(ell * num_datapoints / b - kl)
+
+
+def svgp_elbo_value_and_grad_autodiff(kind, X, y, Z, lengthscale, variance, obs_stddev, mean_const, var_mean, var_sqrt,
+                                      num_datapoints, jitter=1e-6):
+    """torch-CPU reverse mode of the same restatement.  The gradient w.r.t. var_sqrt is reported on the
+    lower triangle (the parameter is LowerTriangular)."""
+    import torch
+
+    kind = _kind_id(kind)
+    t = lambda a: torch.tensor(np.asarray(a, np.float64), dtype=torch.float64, requires_grad=True)
+    Xt = torch.tensor(np.asarray(X, np.float64))
+    yt = torch.tensor(np.asarray(y, np.float64).reshape(-1))
+    ell, var, sn, c, Zt = t(lengthscale), t(variance), t(obs_stddev), t(mean_const), t(Z)
+    mu, Wp = t(np.asarray(var_mean).reshape(-1)), t(var_sqrt)
+    W = torch.tril(Wp)
+    m, b = Zt.shape[0], Xt.shape[0]
+    s = sn**2
+    eye = torch.eye(m, dtype=torch.float64)
+    Kzz = _t_cross(torch, kind, Zt, Zt, ell, var) + eye * jitter
+    S = W @ W.T
+    Lz = torch.linalg.cholesky(Kzz)
+    Lq = torch.linalg.cholesky(S)
+    diff = c - mu
+    trace = torch.sum(torch.linalg.solve_triangular(Lz, Lq, upper=False) ** 2)
+    mahal = torch.sum(torch.linalg.solve_triangular(Lz, diff[:, None], upper=False) ** 2)
+    kl = 0.5 * (mahal - m - torch.linalg.slogdet(S)[1] + torch.linalg.slogdet(Kzz)[1] + trace)
+    Kzt = _t_cross(torch, kind, Zt, Xt, ell, var)
+    A = torch.linalg.solve_triangular(Lz, Kzt, upper=False)
+    KiK = torch.linalg.solve_triangular(Lz.T, A, upper=True)
+    R = KiK.T @ W
+    mean = c + KiK.T @ (mu - c)
+    vpt = var - torch.sum(A**2, dim=0) + torch.sum(R**2, dim=1) + jitter
+    ellv = -0.5 * torch.sum(math.log(2.0 * math.pi) + torch.log(s) + ((yt - mean) ** 2 + vpt) / s)
+    val = ellv * num_datapoints / b - kl
+    val.backward()
+    g = {
+        "lengthscale": ell.grad.numpy().copy() if ell.grad.ndim else float(ell.grad),
+        "variance": float(var.grad), "obs_stddev": float(sn.grad), "mean_const": float(c.grad),
+        "inducing_inputs": Zt.grad.numpy().copy(), "variational_mean": mu.grad.numpy().copy(),
+        "variational_root_covariance": np.tril(Wp.grad.numpy()),
+    }
+    return float(val.detach()), g
+
+
+def svgp_predict(kind, T, Z, lengthscale, variance, mean_const, var_mean, var_sqrt, jitter=1e-6):
+    """VariationalGaussian.predict (variational_families.py:234-285): mean[T], cov[T,T]."""
+    kind = _kind_id(kind)
+    T, Z = np.asarray(T, np.float64), np.asarray(Z, np.float64)
+    mu = np.asarray(var_mean, np.float64).reshape(-1)
+    W = np.tril(np.asarray(var_sqrt, np.float64))
+    Lz = np.linalg.cholesky(add_jitter(gram(kind, Z, lengthscale, variance), jitter))
+    Ktt = gram(kind, T, lengthscale, variance)
+    Kzt = cross_covariance(kind, Z, T, lengthscale, variance)
+    A = sla.solve_triangular(Lz, Kzt, lower=True)
+    KiK = sla.solve_triangular(Lz.T, A, lower=False)
+    R = KiK.T @ W
+    mean = mean_const + KiK.T @ (mu - mean_const)
+    cov = Ktt - A.T @ A + R @ R.T
+    return mean, add_jitter(cov, jitter)

@@ -409,3 +409,75 @@ bool profile_enabled() { return false; }
 void profile_gemm_begin(stream_t) {}
 void profile_gemm_end(stream_t) {}
 }  // namespace gpb
+
+// ---- SVGP helpers -----------------------------------------------------------------------------
+namespace gpb {
+int sum_log_abs_diag(stream_t, int64_t n, const double* A, int64_t lda, double* out) {
+    double s = 0.0;
+    for (int64_t i = 0; i < n; ++i) s += std::log(std::fabs(A[i * (lda + 1)]));
+    out[0] = s;
+    return GPB_OK;
+}
+int svgp_unpack(stream_t, int64_t M, const double* P, int64_t ldp, const double* obs_stddev, double num_datapoints,
+                double* Phi, double* psi, double* a1, double* sc) {
+    double tr = 0.0;
+    for (int64_t r = 0; r < M; ++r) {
+        for (int64_t c = 0; c < M; ++c) Phi[r * M + c] = (c <= r) ? P[r * ldp + c] : P[c * ldp + r];
+        tr += P[r * ldp + r];
+        psi[r] = P[M * ldp + r];
+        a1[r] = P[(M + 1) * ldp + r];
+    }
+    double s = obs_stddev[0] * obs_stddev[0], B = P[(M + 1) * ldp + M + 1];
+    sc[0] = P[M * ldp + M]; sc[1] = P[(M + 1) * ldp + M]; sc[2] = B; sc[3] = tr; sc[4] = s;
+    sc[5] = (num_datapoints / B) / s;
+    return GPB_OK;
+}
+int svgp_value(stream_t, int64_t M, const double* sc, const double* dots, const double* variance, double jitter,
+               const int* info, double* out) {
+    double dd = sc[0], B = sc[2], trphi = sc[3], s = sc[4], coef = sc[5];
+    double Q = dd - 2 * dots[0] + dots[3] + B * (variance[0] + jitter) - trphi;
+    double ell = -0.5 * (B * std::log(2 * M_PI * s) + Q / s);
+    double kl = 0.5 * (dots[1] - (double)M - 2 * dots[5] + 2 * dots[4] + dots[2]);
+    double v = coef * s * ell - kl;
+    if (info && info[0] != 0) v = std::numeric_limits<double>::quiet_NaN();
+    out[0] = v;
+    return GPB_OK;
+}
+int svgp_adjoints(stream_t, int64_t M, const double* Phi, const double* Tt, const double* PT, const double* u,
+                  const double* psi, const double* sc, double* G1, double* E) {
+    double coef = sc[5];
+    for (int64_t r = 0; r < M; ++r)
+        for (int64_t c = 0; c < M; ++c) {
+            double eye = r == c ? 1.0 : 0.0, tt = Tt[r * M + c];
+            G1[r * M + c] = coef * (eye - tt);
+            E[r * M + c] = -0.5 * coef * (u[r] * psi[c] + u[c] * psi[r]) + 0.5 * coef * (PT[r * M + c] + PT[c * M + r]) -
+                           0.5 * coef * Phi[r * M + c] + 0.5 * tt - 0.5 * eye;
+        }
+    return GPB_OK;
+}
+int svgp_vectors(stream_t, int64_t M, const double* psi, const double* Phiu, const double* u, const double* sc,
+                 double* tvec, double* uvec) {
+    for (int64_t i = 0; i < M; ++i) {
+        tvec[i] = sc[5] * (psi[i] - Phiu[i]) - u[i];
+        uvec[i] = sc[5] * u[i];
+    }
+    return GPB_OK;
+}
+int svgp_h(stream_t, int64_t M, const double* PhiV, const double* V, const double* sc, double* H) {
+    for (int64_t i = 0; i < M * M; ++i) H[i] = sc[5] * PhiV[i] + V[i];
+    return GPB_OK;
+}
+int svgp_gw_diag(stream_t, int64_t M, const double* W, int64_t ldw, double* gW, int64_t ldg) {
+    for (int64_t i = 0; i < M; ++i) gW[i * ldg + i] += 1.0 / W[i * ldw + i];
+    return GPB_OK;
+}
+int svgp_scalar_grads(stream_t, const double* sc, const double* dots, const double* dots2, const double* variance,
+                      const double* obs_stddev, double jitter, double* g_var, double* g_obs, double* g_mean) {
+    double dd = sc[0], sd = sc[1], B = sc[2], trphi = sc[3], s = sc[4], coef = sc[5], kappa = coef * s;
+    double Q = dd - 2 * dots[0] + dots[3] + B * (variance[0] + jitter) - trphi;
+    if (g_var) g_var[0] += -kappa * B / (2 * s);
+    if (g_obs) g_obs[0] = 2 * obs_stddev[0] * kappa * (-B / (2 * s) + Q / (2 * s * s));
+    if (g_mean) g_mean[0] = coef * (sd - dots2[0]) - dots2[1];
+    return GPB_OK;
+}
+}  // namespace gpb

@@ -211,3 +211,56 @@ def test_sgpr_zero_mean_and_identity_with_mll(lib):
     X, y = data(20, 2, 3)
     val, _ = _sgpr_run(lib, 0, X, y, X.copy(), 1.0, True, 1.0, 1.0, None, 1e-6, 8)
     assert abs(val - o.conjugate_mll("rbf", X, y, 1.0, 1.0, 1.0, 0.0)) <= 1e-5 * abs(val)
+
+
+@pytest.mark.parametrize("kind,name", KINDS)
+@pytest.mark.parametrize("N,M,D,iso,block,shards", [(120, 9, 2, False, 50, 1), (400, 40, 3, True, 128, 2),
+                                                     (600, 140, 4, False, 300, 3)])
+def test_svgp_elbo_value_and_gradient(lib, kind, name, N, M, D, iso, block, shards):
+    """SVGP elbo through the shared SGPR statistics protocol + gpb_svgp_finish/grad_finish vs the oracle's autodiff."""
+    X, y = data(N, D, N + M)
+    rng = np.random.default_rng(M)
+    Z = np.ascontiguousarray(rng.uniform(-2, 2, (M, D)))
+    mu = rng.standard_normal(M) * 0.3
+    W = np.ascontiguousarray(np.tril(rng.standard_normal((M, M)) * 0.1) + 0.7 * np.eye(M))
+    W += np.triu(np.full((M, M), 123.0), 1)  # garbage above the diagonal must be ignored
+    ell = np.array([0.9]) if iso else np.linspace(0.8, 1.6, D)
+    var_a, sn_a, c_a = np.array([1.3]), np.array([0.4]), np.array([0.2])
+    ndata, jitter = 5000.0, 1e-6
+    nbytes = lib.gpb_sgpr_workspace_bytes(M, D, block)
+    cnt = lib.gpb_sgpr_stats_count(M)
+    bounds = np.linspace(0, N, shards + 1).astype(int)
+    wss, Ps = [np.zeros(nbytes // 8 + 8) for _ in range(shards)], []
+    for r in range(shards):
+        Xr, yr = np.ascontiguousarray(X[bounds[r]:bounds[r + 1]]), np.ascontiguousarray(y[bounds[r]:bounds[r + 1]])
+        P = np.zeros(cnt)
+        assert lib.gpb_sgpr_stats(None, kind, len(Xr), M, D, p(Xr), D, p(yr), p(Z), D, p(ell), int(iso), p(var_a), p(sn_a),
+                                  p(c_a), jitter, block, p(wss[r]), nbytes, p(P)) == 0
+        Ps.append(P)
+    Pall = np.sum(Ps, axis=0)
+    val, info = np.zeros(1), np.zeros(2, np.int32)
+    for r in range(shards):
+        assert lib.gpb_svgp_finish(None, kind, M, D, p(Z), D, p(ell), int(iso), p(var_a), p(sn_a), p(c_a), p(mu), p(W), M,
+                                   ndata, jitter, block, p(wss[r]), nbytes, p(Pall), 1, p(val), p(info)) == 0
+    ellv = ell[0] if iso else ell
+    ref, gref = o.svgp_elbo_value_and_grad_autodiff(name, X, y, Z, ellv, 1.3, 0.4, 0.2, mu, np.tril(W), ndata, jitter)
+    assert abs(val[0] - ref) <= 1e-9 * abs(ref)
+    flat = np.zeros(M * D + (1 if iso else D) + 1)
+    nl = 1 if iso else D
+    tot = np.zeros_like(flat)
+    for r in range(shards):
+        Xr, yr = np.ascontiguousarray(X[bounds[r]:bounds[r + 1]]), np.ascontiguousarray(y[bounds[r]:bounds[r + 1]])
+        f = np.zeros_like(flat)
+        assert lib.gpb_sgpr_grad_local(None, kind, len(Xr), M, D, p(Xr), D, p(yr), p(Z), D, p(ell), int(iso), p(var_a),
+                                       p(sn_a), p(c_a), block, p(wss[r]), nbytes, p(f[:M * D]), p(f[M * D:M * D + nl]),
+                                       p(f[M * D + nl:])) == 0
+        tot += f
+    gZ, gl, gv = tot[:M * D].copy(), tot[M * D:M * D + nl].copy(), tot[M * D + nl:].copy()
+    gs, gc, gmu, gW = np.zeros(1), np.zeros(1), np.zeros(M), np.full((M, M), np.nan)
+    assert lib.gpb_svgp_grad_finish(None, kind, M, D, p(Z), D, p(ell), int(iso), p(var_a), p(sn_a), jitter, block,
+                                    p(wss[0]), nbytes, None, p(W), M, p(gZ), p(gl), p(gv), p(gs), p(gc), p(gmu), p(gW), M) == 0
+    got = dict(lengthscale=gl, variance=gv[0], obs_stddev=gs[0], mean_const=gc[0], inducing_inputs=gZ.reshape(M, D),
+               variational_mean=gmu, variational_root_covariance=gW)
+    for k in gref:
+        a, b = np.asarray(got[k]).reshape(np.shape(gref[k])), np.asarray(gref[k])
+        assert np.max(np.abs(a - b)) <= 1e-7 * max(np.max(np.abs(b)), 1e-8 * abs(ref)), k
