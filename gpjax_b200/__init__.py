@@ -13,8 +13,8 @@ Only the path named in DESIGN.md is implemented; everything computes on CUDA (no
 from . import (dataset, distributions, fit as _fit_mod, gps, kernels, likelihoods, linalg, mean_functions, objectives,
                optim, parameters, variational_families)
 from .dataset import Dataset
-from .fit import fit, fit_scipy, get_batch
+from .fit import fit, fit_lbfgs, fit_scipy, get_batch
 
 __version__ = "0.1.0"
-__all__ = ["Dataset", "fit", "fit_scipy", "get_batch", "kernels", "linalg", "objectives", "gps", "likelihoods",
+__all__ = ["Dataset", "fit", "fit_scipy", "fit_lbfgs", "get_batch", "kernels", "linalg", "objectives", "gps", "likelihoods",
            "mean_functions", "variational_families", "parameters", "optim", "distributions", "dataset"]

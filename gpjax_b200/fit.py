@@ -138,6 +138,45 @@ def fit_scipy(*, model: Module, objective, train_data: Dataset, trainable=Parame
     return model, torch.as_tensor(history, dtype=torch.float64)
 
 
+def fit_lbfgs(*, model: Module, objective, train_data: Dataset, params_bijection: tp.Optional[dict] = DEFAULT_BIJECTION,
+              trainable=Parameter, max_iters: int = 100, safe: bool = True, max_linesearch_steps: int = 32,
+              gtol: float = 1e-5):
+    """fit.py:259-361.  The reference drives optax's L-BFGS (zoom line search) inside a lax.while_loop; the
+    optimiser is host-side glue here as well: SciPy's L-BFGS-B on the raveled unconstrained parameters with the
+    same stopping knobs.  Returns (optimised model, final loss)."""
+    import numpy as np
+    from scipy.optimize import minimize
+
+    if safe:
+        _check_model(model)
+        _check_train_data(train_data)
+        _check_num_iters(max_iters)
+    model = copy.deepcopy(model)
+    loss = _Loss(model, objective, _select(model, trainable), params_bijection)
+    u0 = loss.unconstrained()
+    keys = list(u0)
+    shapes = [u0[k].shape for k in keys]
+    sizes = [int(u0[k].numel()) for k in keys]
+    dev = train_data.X.device
+
+    def unravel(x):
+        out, o = {}, 0
+        for k, sh, sz in zip(keys, shapes, sizes):
+            out[k] = torch.as_tensor(x[o:o + sz], dtype=torch.float64, device=dev).reshape(sh)
+            o += sz
+        return out
+
+    def wrapper(x):
+        val, g = loss.value_and_grad(unravel(x), train_data)
+        return float(val), np.concatenate([g[k].reshape(-1).cpu().numpy() for k in keys])
+
+    x0 = np.concatenate([u0[k].reshape(-1).cpu().numpy() for k in keys])
+    result = minimize(fun=wrapper, x0=x0, jac=True, method="L-BFGS-B",
+                      options={"maxiter": max_iters, "maxls": max_linesearch_steps, "gtol": gtol})
+    loss.commit(unravel(result.x))
+    return model, torch.as_tensor(result.fun, dtype=torch.float64)
+
+
 def _check_model(model) -> None:
     if not isinstance(model, Module):
         raise TypeError(f"Expected model to be a subclass of nnx.Module. Got {model} of type {type(model)}.")
@@ -179,4 +218,4 @@ def _check_batch_size(batch_size) -> None:
         raise ValueError(f"Expected batch_size to be positive or -1. Got {batch_size}.")
 
 
-__all__ = ["fit", "fit_scipy", "get_batch"]
+__all__ = ["fit", "fit_scipy", "fit_lbfgs", "get_batch"]

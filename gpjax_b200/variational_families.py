@@ -34,6 +34,63 @@ class CollapsedVariationalGaussian(AbstractVariationalGaussian):
         if not isinstance(posterior.likelihood, Gaussian):
             raise TypeError("Likelihood must be Gaussian.")
 
+    def predict(self, test_inputs, train_data, *, block_rows: int = 32768, group=None):
+        """Predictive Gaussian of the collapsed bound (variational_families.py:786-870).  The training data
+        enter through the streamed, row-additive statistics of the ELBO path (all-reduced over `group`
+        when `train_data` is this rank's shard), never through an N x M matrix:
+            mean = mu_t + (Lz^-1 Kzt)^T B^-1 (Lz^-1 Kzx d) / s,      B = I + Lz^-1 Kzx Kxz Lz^-T / s
+            cov  = Ktt - At^T At + (L^-1 At)^T (L^-1 At) + jitter I, At = Lz^-1 Kzt, L L^T = B."""
+        from . import _abi, ops
+        from ._lib import lib
+        from .distributions import GaussianDistribution
+        from .linalg import Dense
+        from .objectives import _mean_constant
+        from .ops import _ell_args, _p, _scalar, _stream
+        from .sgpr_ops import _all_reduce, _state
+
+        post = self.posterior
+        kern = post.prior.kernel
+        kind = kern.compute_engine._kind(kern)
+        x = kern.slice_input(train_data.X).contiguous()
+        t = kern.slice_input(test_inputs).contiguous()
+        z = kern.slice_input(self.inducing_inputs.value).contiguous()
+        y = train_data.y.reshape(-1).contiguous()
+        n_loc, D = x.shape
+        M, T = z.shape[0], t.shape[0]
+        ell_v, iso = _ell_args(kern.lengthscale.value, D)
+        var = _scalar(kern.variance.value, "variance")
+        sn = _scalar(post.likelihood.obs_stddev.value, "obs_stddev")
+        mean = _mean_constant(post.prior.mean_function)
+        mean = None if mean is None else _scalar(mean.to(x.device), "mean constant")
+        block_rows = int(min(block_rows, max(n_loc, 1)))
+        st = _state(M, D, block_rows, z.device)
+        L_ = lib()
+        P = torch.empty(L_.gpb_sgpr_stats_count(M), dtype=torch.float64, device=z.device)
+        rc = L_.gpb_sgpr_stats(_stream(), kind, n_loc, M, D, _p(x), x.stride(0), _p(y), _p(z), z.stride(0), _p(ell_v), iso,
+                               _p(var), _p(sn), _p(mean), float(self.jitter), block_rows, _p(st.ws), st.nbytes, _p(P))
+        _abi.check(rc, "gpb_sgpr_stats")
+        st.generation += 1
+        _all_reduce(P, group)
+        P = P.reshape(M + 2, M + 2)
+        s = sn.reshape(()) ** 2
+        Phi = torch.tril(P[:M, :M])
+        Bmat = (Phi + torch.tril(Phi, -1).T) / s + torch.eye(M, dtype=torch.float64, device=z.device)  # M x M glue
+        psi = P[M, :M].contiguous()
+        wsB = ops.FactorWorkspace(max(M, T), 1, device=z.device)
+        ops.potrf_lower_(Bmat, wsB, zero_upper=False)                              # L L^T = I + A A^T
+        v = ops.trsv_lower_(Bmat, ops.trsv_lower_(Bmat, psi.clone(), wsB), wsB, trans=True)   # B^-1 (Lz^-1 Kzx d)
+        Lz = ops.gram_forward(kind, z, z, ell_v, var, diag_add=self.jitter, lower_only=True)
+        wsZ = ops.FactorWorkspace(max(M, T), 1, device=z.device)
+        ops.potrf_lower_(Lz, wsZ, zero_upper=False)
+        At = ops.trsm_lower_left_(Lz, ops.gram_forward(kind, z, t, ell_v, var), wsZ)          # Lz^-1 Kzt  [M, T]
+        mean_fn = post.prior.mean_function
+        mu = mean_fn(test_inputs).reshape(-1) + ops.gemm(At, (v / s).reshape(1, -1).contiguous(), a_layout=1).reshape(-1)
+        cov = ops.gram_forward(kind, t, t, ell_v, var, diag_add=self.jitter)
+        ops.gemm(At, At, cov, alpha=-1.0, beta=1.0, a_layout=1, b_layout=1)
+        LAt = ops.trsm_lower_left_(Bmat, At.clone(), wsB)                                      # L^-1 At
+        ops.gemm(LAt, LAt, cov, alpha=1.0, beta=1.0, a_layout=1, b_layout=1)
+        return GaussianDistribution(torch.atleast_1d(mu), Dense(cov))
+
 
 class VariationalGaussian(AbstractVariationalGaussian):
     """q(u) = N(mu, S), S = sqrt sqrt^T (gpjax/variational_families.py:134-285).  `prior_kl` and the

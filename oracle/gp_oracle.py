@@ -48,6 +48,7 @@ __all__ = [
     "svgp_elbo",
     "svgp_elbo_value_and_grad_autodiff",
     "svgp_predict",
+    "collapsed_predict",
 ]
 
 
@@ -707,4 +708,28 @@ def svgp_predict(kind, T, Z, lengthscale, variance, mean_const, var_mean, var_sq
     R = KiK.T @ W
     mean = mean_const + KiK.T @ (mu - mean_const)
     cov = Ktt - A.T @ A + R @ R.T
+    return mean, add_jitter(cov, jitter)
+
+
+def collapsed_predict(kind, X, y, T, Z, lengthscale, variance, obs_stddev, mean_const=0.0, jitter=1e-6):
+    """CollapsedVariationalGaussian.predict (variational_families.py:786-870): mean[T], cov[T,T]."""
+    kind = _kind_id(kind)
+    X, T, Z = np.asarray(X, np.float64), np.asarray(T, np.float64), np.asarray(Z, np.float64)
+    y = np.asarray(y, np.float64).reshape(-1)
+    m = Z.shape[0]
+    noise = obs_stddev**2
+    Kzx = cross_covariance(kind, Z, X, lengthscale, variance)
+    Lz = np.linalg.cholesky(add_jitter(gram(kind, Z, lengthscale, variance), jitter))
+    Lz_inv_Kzx = sla.solve_triangular(Lz, Kzx, lower=True)
+    A = Lz_inv_Kzx / obs_stddev
+    L = np.linalg.cholesky(np.eye(m) + A @ A.T)
+    diff = y - mean_const
+    Lz_inv_Kzx_diff = sla.cho_solve((L, True), Lz_inv_Kzx @ diff)
+    Kzz_inv_Kzx_diff = sla.solve_triangular(Lz.T, Lz_inv_Kzx_diff, lower=False)
+    Ktt = gram(kind, T, lengthscale, variance)
+    Kzt = cross_covariance(kind, Z, T, lengthscale, variance)
+    Lz_inv_Kzt = sla.solve_triangular(Lz, Kzt, lower=True)
+    L_inv_Lz_inv_Kzt = sla.solve_triangular(L, Lz_inv_Kzt, lower=True)
+    mean = mean_const + (Kzt.T / noise) @ Kzz_inv_Kzx_diff
+    cov = Ktt - Lz_inv_Kzt.T @ Lz_inv_Kzt + L_inv_Lz_inv_Kzt.T @ L_inv_Lz_inv_Kzt
     return mean, add_jitter(cov, jitter)

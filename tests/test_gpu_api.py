@@ -177,3 +177,26 @@ def test_fit_sgpr_trains_inducing_inputs():
     frozen, _ = gpx.fit(model=q, objective=neg, train_data=D, optim=gpx.optim.adam(0.02), num_iters=3,
                         trainable=PositiveReal, verbose=False)
     assert torch.equal(frozen.inducing_inputs.value, dev(z0))
+
+
+def test_collapsed_predict_and_fit_lbfgs():
+    """section 8f rank 2 (CollapsedVariationalGaussian.predict, variational_families.py:786-870) and fit_lbfgs
+    (fit.py:259-361; tests/test_fit.py:226-257 of the reference: loss decreases, model type preserved)."""
+    import gpjax_b200 as gpx
+
+    X, y = build_data(900, 2, 11)
+    T = np.random.default_rng(2).uniform(-2, 2, (41, 2))
+    Z = np.random.default_rng(3).uniform(-2, 2, (25, 2))
+    D = gpx.Dataset(X=dev(X), y=dev(y))
+    post = gpx.gps.Prior(mean_function=gpx.mean_functions.Constant(0.3), kernel=gpx.kernels.Matern52(lengthscale=[0.9, 1.3])) * \
+        gpx.likelihoods.Gaussian(num_datapoints=D.n, obs_stddev=0.4)
+    q = gpx.variational_families.CollapsedVariationalGaussian(posterior=post, inducing_inputs=dev(Z))
+    dist = q.predict(dev(T), D, block_rows=256)
+    mean, cov = o.collapsed_predict("matern52", X, y, T, Z, np.array([0.9, 1.3]), 1.0, 0.4, 0.3)
+    assert np.max(np.abs(dist.mean().cpu().numpy() - mean)) <= 1e-8 * np.abs(mean).max()
+    assert np.max(np.abs(dist.covariance().cpu().numpy() - cov)) <= 1e-8
+    neg = lambda p, d: -gpx.objectives.collapsed_elbo(p, d)
+    before = neg(q, D).item()
+    opt, final = gpx.fit_lbfgs(model=q, objective=neg, train_data=D, max_iters=15)
+    assert isinstance(opt, gpx.variational_families.CollapsedVariationalGaussian)
+    assert final.item() < before and abs(neg(opt, D).item() - final.item()) <= 1e-8 * abs(final.item())

@@ -177,3 +177,31 @@ def test_adam_matches_optax_semantics():
     upd, st = opt.update(g, opt.init(p), p)
     assert torch.allclose(upd["a"], torch.tensor([-0.01, 0.01], dtype=torch.float64), atol=1e-9)
     assert st["count"] == 1
+
+
+def test_fit_lbfgs_host_logic():
+    D = gpx.Dataset(X=torch.zeros((4, 1), dtype=torch.float64), y=torch.zeros((4, 1), dtype=torch.float64))
+    opt, final = gpx.fit_lbfgs(model=_toy_model(), objective=_toy_objective, train_data=D, max_iters=50)
+    assert final.item() < 1e-10 and abs(float(opt.prior.kernel.lengthscale.value) - 1.0) < 1e-5
+    with pytest.raises(ValueError):
+        gpx.fit_lbfgs(model=_toy_model(), objective=_toy_objective, train_data=D, max_iters=0)
+
+
+def test_lower_triangular_parameter_and_bijection():
+    from gpjax_b200.parameters import FillTriangularTransform, LowerTriangular
+
+    L = torch.tril(torch.arange(1.0, 10.0, dtype=torch.float64).reshape(3, 3))
+    p = LowerTriangular(L)
+    assert p.tag == "lower_triangular"
+    with pytest.raises(ValueError):
+        LowerTriangular(torch.ones((3, 3), dtype=torch.float64))
+    with pytest.raises(ValueError):
+        LowerTriangular(torch.ones((2, 3), dtype=torch.float64))
+    bij = FillTriangularTransform()
+    v = bij.inv(L)
+    assert v.shape == (6,) and torch.equal(bij(v), L)
+    q = gpx.variational_families.VariationalGaussian(
+        posterior=_toy_model(), inducing_inputs=torch.zeros((4, 1), dtype=torch.float64))
+    assert q.variational_mean.value.shape == (4, 1) and torch.equal(q.variational_root_covariance.value,
+                                                                    torch.eye(4, dtype=torch.float64))
+    assert sorted(n for n, _ in q.named_parameters())[:2] == ["inducing_inputs", "posterior.likelihood.obs_stddev"]
