@@ -24,6 +24,8 @@ def lib() -> ctypes.CDLL:
                 "CUDA library first with `python -m gpjax_b200.build` (needs nvcc)."
             )
         _LIB = _abi.declare(ctypes.CDLL(LIB_PATH))
+        if os.environ.get("GPB_GEMM_VARIANT"):  # kernel-tuning hook (scripts/gemm_bench.py, profiles/)
+            _LIB.gpb_debug_set_gemm_variant(int(os.environ["GPB_GEMM_VARIANT"]))
     return _LIB
 
 

@@ -53,19 +53,29 @@ struct GemmParams {
     int batch;
 };
 
-template <int ROWS, int LAY>
+// Shared-memory tile geometry.  Two conflict-free schemes for the 8x4 / 4x8 fragment reads:
+//   SWZ = false: rows padded by 4 doubles (32 B)          -> 30.7 KB per 128x64 stage
+//   SWZ = true : no padding, the 32-byte segments of a row are XOR-permuted with (row & 3) -> 24.6 KB per stage,
+//                which is what lets THREE CTAs share an SM (3 x 73.7 KB).
+template <int ROWS, int LAY, bool SWZ>
 struct TileGeom {
-    // LAYOUT_K : smem [ROWS][BK+PAD];  LAYOUT_MN: smem [BK][ROWS+PAD]
-    static constexpr int LD = (LAY == LAYOUT_K) ? (BK + PAD) : (ROWS + PAD);
-    static constexpr int SIZE = (LAY == LAYOUT_K) ? ROWS * (BK + PAD) : BK * (ROWS + PAD);
+    // LAYOUT_K : smem [ROWS][BK(+PAD)];  LAYOUT_MN: smem [BK][ROWS(+PAD)]
+    static constexpr int P = SWZ ? 0 : PAD;
+    static constexpr int LD = (LAY == LAYOUT_K) ? (BK + P) : (ROWS + P);
+    static constexpr int SIZE = (LAY == LAYOUT_K) ? ROWS * (BK + P) : BK * (ROWS + P);
+    // element (major, minor): LAYOUT_K -> (row, k), LAYOUT_MN -> (k, row)
+    __device__ __forceinline__ static int index(int major, int minor) {
+        if (SWZ) return major * LD + ((((minor >> 2) ^ (major & 3)) << 2) | (minor & 3));
+        return major * LD + minor;
+    }
 };
 
 // Copy one ROWS x BK operand tile into shared memory (zero-filling everything out of range).
-template <int ROWS, int LAY, int NT>
+template <int ROWS, int LAY, int NT, bool SWZ>
 __device__ __forceinline__ void load_tile(double* __restrict__ sm, const double* __restrict__ G,
                                           int64_t ld, int64_t row0, int64_t nrows, int64_t k0,
                                           int64_t kend, bool vec16, int tid) {
-    constexpr int LD = TileGeom<ROWS, LAY>::LD;
+    using G_ = TileGeom<ROWS, LAY, SWZ>;
     if (LAY == LAYOUT_K) {
         constexpr int CHUNKS = ROWS * (BK / 2);
 #pragma unroll
@@ -76,7 +86,7 @@ __device__ __forceinline__ void load_tile(double* __restrict__ sm, const double*
             int64_t left = kend - k;
             int nb = (gm < nrows) ? (left >= 2 ? 16 : (left == 1 ? 8 : 0)) : 0;
             const double* src = (nb > 0) ? (G + gm * ld + k) : G;
-            double* dst = sm + r * LD + ch * 2;
+            double* dst = sm + G_::index(r, ch * 2);
             if (vec16) {
                 cp_async16(dst, src, nb);
             } else {
@@ -95,7 +105,7 @@ __device__ __forceinline__ void load_tile(double* __restrict__ sm, const double*
             int64_t left = nrows - m;
             int nb = (k < kend) ? (left >= 2 ? 16 : (left == 1 ? 8 : 0)) : 0;
             const double* src = (nb > 0) ? (G + k * ld + m) : G;
-            double* dst = sm + kr * LD + ch * 2;
+            double* dst = sm + G_::index(kr, ch * 2);
             if (vec16) {
                 cp_async16(dst, src, nb);
             } else {
@@ -111,39 +121,34 @@ __device__ __forceinline__ void load_tile(double* __restrict__ sm, const double*
 // K chunk is inside [kbeg, kend) and rows are 16-byte aligned, so each thread issues its 16-byte
 // cp.async's from a precomputed base pointer with compile-time strides (3 instructions per copy
 // instead of ~20 for the fully predicated path).
-template <int ROWS, int LAY, int NT>
+template <int ROWS, int LAY, int NT, bool SWZ>
 struct FastPlan {
-    static constexpr int LD = TileGeom<ROWS, LAY>::LD;
+    using G_ = TileGeom<ROWS, LAY, SWZ>;
     static constexpr int NCOPY = ROWS * (BK / 2) / NT;
     static_assert(ROWS * (BK / 2) % NT == 0, "tile copies must divide evenly over the threads");
+    static constexpr int CPM = (LAY == LAYOUT_K) ? (BK / 2) : (ROWS / 2);  // 16-byte chunks per major index
+    static constexpr int MSTEP = NT / CPM;                                 // major-index step between copies
     const double* src;   // global address of this thread's first chunk at k = 0
     int64_t src_step;    // elements between consecutive chunks of this thread
     int64_t k_step;      // elements per unit of k
-    int dst;             // shared-memory element offset of the first chunk (within one stage)
-    int dst_step;
+    int major0, minor0;  // (row, k) resp. (k, row) of the first chunk inside the tile
     __device__ __forceinline__ void init(const double* G, int64_t ld, int64_t row0, int tid) {
+        major0 = tid / CPM;
+        minor0 = (tid % CPM) * 2;
         if (LAY == LAYOUT_K) {
-            const int r = tid / (BK / 2), ch = tid % (BK / 2);
-            src = G + (row0 + r) * ld + ch * 2;
-            src_step = (int64_t)(NT / (BK / 2)) * ld;
+            src = G + (row0 + major0) * ld + minor0;
             k_step = 1;
-            dst = r * LD + ch * 2;
-            dst_step = (NT / (BK / 2)) * LD;
         } else {
-            constexpr int CPR = ROWS / 2;
-            const int kr = tid / CPR, ch = tid % CPR;
-            src = G + (int64_t)kr * ld + row0 + ch * 2;
-            src_step = (int64_t)(NT / CPR) * ld;
+            src = G + (int64_t)major0 * ld + row0 + minor0;
             k_step = ld;
-            dst = kr * LD + ch * 2;
-            dst_step = (NT / CPR) * LD;
         }
+        src_step = (int64_t)MSTEP * ld;
     }
     __device__ __forceinline__ void issue(double* stage, int64_t k0) const {
         const double* s0 = src + k0 * k_step;
-        double* d0 = stage + dst;
 #pragma unroll
-        for (int i = 0; i < NCOPY; ++i) cp_async16(d0 + i * dst_step, s0 + i * src_step, 16);
+        for (int i = 0; i < NCOPY; ++i)
+            cp_async16(stage + G_::index(major0 + i * MSTEP, minor0), s0 + i * src_step, 16);
     }
 };
 
@@ -192,13 +197,13 @@ __host__ __device__ inline void live_range(const GemmParams& p, int64_t tm, int6
     }
 }
 
-template <int BM, int BN, int WM, int WN, int STAGES, int MINB, int ALAY, int BLAY>
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB, bool SWZ, int ALAY, int BLAY>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) gemm_f64_kernel(const GemmParams p) {
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
     constexpr int WARPS_N = BN / WN;
     constexpr int TM = WM / 8, TN = WN / 8;
-    using GA = TileGeom<BM, ALAY>;
-    using GB = TileGeom<BN, BLAY>;
+    using GA = TileGeom<BM, ALAY, SWZ>;
+    using GB = TileGeom<BN, BLAY, SWZ>;
     extern __shared__ __align__(16) double smem[];
     double* As = smem;
     double* Bs = smem + STAGES * GA::SIZE;
@@ -283,17 +288,17 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) gemm_f64_ker
     // CTA-uniform fast-path conditions (see FastPlan)
     const bool a_fast = av && (m0 + BM <= p.M);
     const bool b_fast = bv && (n0 + BN <= p.N);
-    FastPlan<BM, ALAY, NT> pa;
-    FastPlan<BN, BLAY, NT> pb;
+    FastPlan<BM, ALAY, NT, SWZ> pa;
+    FastPlan<BN, BLAY, NT, SWZ> pb;
     pa.init(A, p.lda, m0, tid);
     pb.init(B, p.ldb, n0, tid);
 
     auto load_stage = [&](int st, int64_t k0) {
         const bool kfull = (k0 + BK <= kend);
         if (a_fast && kfull) pa.issue(As + st * GA::SIZE, k0);
-        else load_tile<BM, ALAY, NT>(As + st * GA::SIZE, A, p.lda, m0, p.M, k0, kend, av, tid);
+        else load_tile<BM, ALAY, NT, SWZ>(As + st * GA::SIZE, A, p.lda, m0, p.M, k0, kend, av, tid);
         if (b_fast && kfull) pb.issue(Bs + st * GB::SIZE, k0);
-        else load_tile<BN, BLAY, NT>(Bs + st * GB::SIZE, B, p.ldb, n0, p.N, k0, kend, bv, tid);
+        else load_tile<BN, BLAY, NT, SWZ>(Bs + st * GB::SIZE, B, p.ldb, n0, p.N, k0, kend, bv, tid);
     };
 
     // ---- prologue ------------------------------------------------------------------------
@@ -304,13 +309,28 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) gemm_f64_ker
     }
 
     const int fr = lane >> 2, fc = lane & 3;
-    // per-thread fragment base offsets inside a stage
-    const int a_off = (ALAY == LAYOUT_K) ? ((wm0 + fr) * GA::LD + fc) : (fc * GA::LD + wm0 + fr);
-    const int b_off = (BLAY == LAYOUT_K) ? ((wn0 + fr) * GB::LD + fc) : (fc * GB::LD + wn0 + fr);
-    constexpr int A_I = (ALAY == LAYOUT_K) ? 8 * GA::LD : 8;      // step between the TM row fragments
-    constexpr int A_K = (ALAY == LAYOUT_K) ? 4 : 4 * GA::LD;      // step between k4 slices
-    constexpr int B_J = (BLAY == LAYOUT_K) ? 8 * GB::LD : 8;
-    constexpr int B_K = (BLAY == LAYOUT_K) ? 4 : 4 * GB::LD;
+    // Per-thread fragment offsets inside a stage: element (row, k) of A / (col, k) of B for
+    // row = w?0 + i*8 + fr, k = kk*4 + fc.  Split into an i/j-dependent and a kk-dependent part so the
+    // unrolled loop only adds compile-time constants (padded) or a precomputed XOR term (swizzled).
+    int a_i[TM], b_j[TN], a_k[BK / 4], b_k[BK / 4];
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const int row = wm0 + i * 8 + fr;
+        if (ALAY == LAYOUT_K) a_i[i] = row * GA::LD + fc;
+        else a_i[i] = SWZ ? ((((row >> 2) ^ fc) << 2) | (row & 3)) : row;
+    }
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+        const int col = wn0 + j * 8 + fr;
+        if (BLAY == LAYOUT_K) b_j[j] = col * GB::LD + fc;
+        else b_j[j] = SWZ ? ((((col >> 2) ^ fc) << 2) | (col & 3)) : col;
+    }
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+        // LAYOUT_K: k segment kk, permuted with (row & 3) = (fr & 3) when swizzled; LAYOUT_MN: k-row (kk*4 + fc)
+        a_k[kk] = (ALAY == LAYOUT_K) ? ((SWZ ? (kk ^ (fr & 3)) : kk) << 2) : (kk * 4 + fc) * GA::LD;
+        b_k[kk] = (BLAY == LAYOUT_K) ? ((SWZ ? (kk ^ (fr & 3)) : kk) << 2) : (kk * 4 + fc) * GB::LD;
+    }
 
     for (int it = 0; it < nk; ++it) {
         cp_async_wait<STAGES - 2>();
@@ -320,21 +340,21 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) gemm_f64_ker
             if (nx < nk) load_stage(nx % STAGES, kbeg + (int64_t)nx * BK);
             cp_async_commit();
         }
-        const double* as = As + (it % STAGES) * GA::SIZE + a_off;
-        const double* bs = Bs + (it % STAGES) * GB::SIZE + b_off;
+        const double* as = As + (it % STAGES) * GA::SIZE;
+        const double* bs = Bs + (it % STAGES) * GB::SIZE;
         double af[2][TM], bf[2][TN];
 #pragma unroll
-        for (int i = 0; i < TM; ++i) af[0][i] = as[i * A_I];
+        for (int i = 0; i < TM; ++i) af[0][i] = as[a_i[i] + a_k[0]];
 #pragma unroll
-        for (int j = 0; j < TN; ++j) bf[0][j] = bs[j * B_J];
+        for (int j = 0; j < TN; ++j) bf[0][j] = bs[b_j[j] + b_k[0]];
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
             const int cur = kk & 1, nxt = cur ^ 1;
             if (kk + 1 < BK / 4) {  // fetch the next k4 slice while this one feeds the tensor pipe
 #pragma unroll
-                for (int i = 0; i < TM; ++i) af[nxt][i] = as[(kk + 1) * A_K + i * A_I];
+                for (int i = 0; i < TM; ++i) af[nxt][i] = as[a_i[i] + a_k[kk + 1]];
 #pragma unroll
-                for (int j = 0; j < TN; ++j) bf[nxt][j] = bs[(kk + 1) * B_K + j * B_J];
+                for (int j = 0; j < TN; ++j) bf[nxt][j] = bs[b_j[j] + b_k[kk + 1]];
             }
 #pragma unroll
             for (int i = 0; i < TM; ++i)
@@ -420,12 +440,12 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) gemm_f64_ker
     }
 }
 
-template <int BM, int BN, int WM, int WN, int STAGES, int MINB, int ALAY, int BLAY>
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB, bool SWZ, int ALAY, int BLAY>
 int launch_gemm(cudaStream_t st, const GemmParams& p, int batch) {
-    using GA = TileGeom<BM, ALAY>;
-    using GB = TileGeom<BN, BLAY>;
+    using GA = TileGeom<BM, ALAY, SWZ>;
+    using GB = TileGeom<BN, BLAY, SWZ>;
     constexpr size_t smem = sizeof(double) * STAGES * (GA::SIZE + GB::SIZE);
-    auto kern = gemm_f64_kernel<BM, BN, WM, WN, STAGES, MINB, ALAY, BLAY>;
+    auto kern = gemm_f64_kernel<BM, BN, WM, WN, STAGES, MINB, SWZ, ALAY, BLAY>;
     static bool configured = false;  // per-instantiation, idempotent
     if (!configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -466,18 +486,18 @@ int launch_gemm(cudaStream_t st, const GemmParams& p, int batch) {
 static int g_variant = 2;
 void debug_set_gemm_variant(int v) { g_variant = v; }
 
-template <int BM, int BN, int WM, int WN, int STAGES, int MINB>
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB, bool SWZ>
 static int dispatch_layouts(cudaStream_t st, GemmParams p, const GemmDesc& d) {
     p.tiles_m = (d.M + BM - 1) / BM;
     p.tiles_n = (d.N + BN - 1) / BN;
     if (d.a_layout == LAYOUT_K && d.b_layout == LAYOUT_K)
-        return launch_gemm<BM, BN, WM, WN, STAGES, MINB, LAYOUT_K, LAYOUT_K>(st, p, d.batch);
+        return launch_gemm<BM, BN, WM, WN, STAGES, MINB, SWZ, LAYOUT_K, LAYOUT_K>(st, p, d.batch);
     if (d.a_layout == LAYOUT_K && d.b_layout == LAYOUT_MN)
-        return launch_gemm<BM, BN, WM, WN, STAGES, MINB, LAYOUT_K, LAYOUT_MN>(st, p, d.batch);
+        return launch_gemm<BM, BN, WM, WN, STAGES, MINB, SWZ, LAYOUT_K, LAYOUT_MN>(st, p, d.batch);
     if (d.a_layout == LAYOUT_MN && d.b_layout == LAYOUT_K)
-        return launch_gemm<BM, BN, WM, WN, STAGES, MINB, LAYOUT_MN, LAYOUT_K>(st, p, d.batch);
+        return launch_gemm<BM, BN, WM, WN, STAGES, MINB, SWZ, LAYOUT_MN, LAYOUT_K>(st, p, d.batch);
     if (d.a_layout == LAYOUT_MN && d.b_layout == LAYOUT_MN)
-        return launch_gemm<BM, BN, WM, WN, STAGES, MINB, LAYOUT_MN, LAYOUT_MN>(st, p, d.batch);
+        return launch_gemm<BM, BN, WM, WN, STAGES, MINB, SWZ, LAYOUT_MN, LAYOUT_MN>(st, p, d.batch);
     return GPB_ERR_INVALID;
 }
 
@@ -503,12 +523,15 @@ int gemm(stream_t s, const GemmDesc& d) {
     p.c_vec16 = al16(d.C, d.ldc, d.strideC);
     cudaStream_t st = to_stream(s);
     // measured on B200 (scripts/gemm_bench.py): 4 warps x (32x64) 34.7 TF/s, 4 x (64x32) 34.7, 8 x (32x32) 33.2
-    if (g_variant == 1) return dispatch_layouts<128, 64, 64, 32, 3, 2>(st, p, d);
-    if (g_variant == 0) return dispatch_layouts<128, 64, 32, 32, 3, 2>(st, p, d);
-    if (g_variant == 3) return dispatch_layouts<128, 128, 32, 64, 3, 1>(st, p, d);  // 8 warps, 1 CTA/SM
-    if (g_variant == 4) return dispatch_layouts<128, 128, 32, 64, 4, 1>(st, p, d);  // same, 4-stage ring
-    if (g_variant == 5) return dispatch_layouts<128, 128, 64, 32, 4, 1>(st, p, d);
-    return dispatch_layouts<128, 64, 32, 64, 3, 2>(st, p, d);
+    // Tile configurations measured on B200 (scripts/gemm_bench.py, 8192^3 / SYRK-lower 44.5k^2 K=512, TF/s):
+    //   4 warps x (32x64), padded smem, 3 stages, 2 CTAs/SM : 34.7 / 33.2   <- default
+    //   4 warps x (32x64), XOR-swizzled smem, 4 stages, 2/SM : 34.8 / 33.3   (variant 8, kept as a tuning hook)
+    //   8 warps x (32x32), padded, 3 stages, 2 CTAs/SM       : 33.2 / 31.9   (variant 0, first version)
+    //   rejected and removed: 4 x (64x32) (= default), swizzled 3 CTAs/SM at 168 regs (31.1, spills),
+    //   128x128 CTA with 1 CTA/SM and 3 or 4 stages (31.9).
+    if (g_variant == 0) return dispatch_layouts<128, 64, 32, 32, 3, 2, false>(st, p, d);
+    if (g_variant == 8) return dispatch_layouts<128, 64, 32, 64, 4, 2, true>(st, p, d);
+    return dispatch_layouts<128, 64, 32, 64, 3, 2, false>(st, p, d);
 }
 
 }  // namespace gpb

@@ -69,7 +69,7 @@ struct GemmDesc {
 
 // C = beta*C + alpha * A * B^T on the FP64 tensor pipe (DMMA).
 int gemm(stream_t s, const GemmDesc& d);
-// tuning hook (bench scripts only): 0 = 8 warps x (32x32), 1 = 4 warps x (64x32), 2 = 4 warps x (32x64) [default]
+// tuning hook (bench scripts only): 0 = 8 warps x (32x32); 8 = swizzled smem, 4 stages; anything else = default
 void debug_set_gemm_variant(int v);
 
 struct GramDesc {
