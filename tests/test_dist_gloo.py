@@ -68,7 +68,11 @@ def test_sgpr_row_sharded_world2_gloo(tmp_path):
     subprocess.run(["make", "-s", "-C", os.path.join(HERE, "hostsim")], check=True)
     script = tmp_path / "worker.py"
     script.write_text(WORKER.format(root=ROOT, here=HERE))
-    port = 29500 + (os.getpid() % 2000)
+    import socket
+
+    with socket.socket() as sk:  # ask the OS for a free rendezvous port
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), str(script)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env={**os.environ, "OMP_NUM_THREADS": "2"})
