@@ -50,6 +50,8 @@ __device__ __forceinline__ double kprofile(double r2, double var) {
         const double s3 = 1.7320508075688772;
         double tau = sqrt(fmax(r2, 1e-36));
         return var * (1.0 + s3 * tau) * exp(-s3 * tau);
+    } else if (KIND == KIND_MATERN12) {  // gpjax/kernels/stationary/matern12.py:44-48
+        return var * exp(-sqrt(fmax(r2, 1e-36)));
     } else {
         const double s5 = 2.23606797749979;
         double tau = sqrt(fmax(r2, 1e-36));
@@ -68,6 +70,10 @@ __device__ __forceinline__ void kprofile_grad(double r2, double var, double& k, 
         double e = exp(-s3 * tau);
         k = var * (1.0 + s3 * tau) * e;
         dk_dr2 = (r2 > 1e-36) ? (-1.5 * var * e) : 0.0;
+    } else if (KIND == KIND_MATERN12) {
+        double tau = sqrt(fmax(r2, 1e-36));
+        k = var * exp(-tau);
+        dk_dr2 = (r2 > 1e-36) ? (-0.5 * k / tau) : 0.0;  // d/dr2 exp(-sqrt(r2)); clamp kills it at r2 <= 1e-36
     } else {
         const double s5 = 2.23606797749979;
         double tau = sqrt(fmax(r2, 1e-36));

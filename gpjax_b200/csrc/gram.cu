@@ -453,6 +453,7 @@ int gram(stream_t s, const GramDesc& d) {
         case KIND_RBF: return launch_gram<KIND_RBF>(st, p, ntiles);
         case KIND_MATERN32: return launch_gram<KIND_MATERN32>(st, p, ntiles);
         case KIND_MATERN52: return launch_gram<KIND_MATERN52>(st, p, ntiles);
+        case KIND_MATERN12: return launch_gram<KIND_MATERN12>(st, p, ntiles);
         default: return GPB_ERR_INVALID;
     }
 }
@@ -511,6 +512,7 @@ int gram_bwd(stream_t s, const GramBwdDesc& d) {
         case KIND_RBF: rc = launch_gram_bwd<KIND_RBF>(st, p, ntiles); break;
         case KIND_MATERN32: rc = launch_gram_bwd<KIND_MATERN32>(st, p, ntiles); break;
         case KIND_MATERN52: rc = launch_gram_bwd<KIND_MATERN52>(st, p, ntiles); break;
+        case KIND_MATERN12: rc = launch_gram_bwd<KIND_MATERN12>(st, p, ntiles); break;
         default: return GPB_ERR_INVALID;
     }
     if (rc != GPB_OK) return rc;
@@ -566,6 +568,7 @@ int mll_bwd(stream_t s, const MllBwdDesc& d) {
         case KIND_RBF: rc = launch_mll_bwd<KIND_RBF>(st, p, ntiles); break;
         case KIND_MATERN32: rc = launch_mll_bwd<KIND_MATERN32>(st, p, ntiles); break;
         case KIND_MATERN52: rc = launch_mll_bwd<KIND_MATERN52>(st, p, ntiles); break;
+        case KIND_MATERN12: rc = launch_mll_bwd<KIND_MATERN12>(st, p, ntiles); break;
         default: return GPB_ERR_INVALID;
     }
     if (rc != GPB_OK) return rc;

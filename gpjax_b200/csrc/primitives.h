@@ -13,7 +13,7 @@ namespace gpb {
 
 typedef void* stream_t;
 
-enum KernelKind { KIND_RBF = 0, KIND_MATERN32 = 1, KIND_MATERN52 = 2 };
+enum KernelKind { KIND_RBF = 0, KIND_MATERN32 = 1, KIND_MATERN52 = 2, KIND_MATERN12 = 3 };
 
 // error codes (identical to include/gpjax_b200.h)
 #ifndef GPB_OK

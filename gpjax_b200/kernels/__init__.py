@@ -1,6 +1,6 @@
 from .base import AbstractKernel
 from .computations import AbstractKernelComputation, DenseKernelComputation
-from .stationary import RBF, Matern32, Matern52, StationaryKernel
+from .stationary import RBF, Matern12, Matern32, Matern52, StationaryKernel
 
-__all__ = ["AbstractKernel", "StationaryKernel", "RBF", "Matern32", "Matern52", "AbstractKernelComputation",
+__all__ = ["AbstractKernel", "StationaryKernel", "RBF", "Matern12", "Matern32", "Matern52", "AbstractKernelComputation",
            "DenseKernelComputation"]

@@ -83,3 +83,10 @@ class Matern52(StationaryKernel):
 
     name = "Matérn52"
     _b200_kind = 2
+
+
+class Matern12(StationaryKernel):
+    """k = s2 exp(-tau)  (stationary/matern12.py:44-48)."""
+
+    name = "Matérn12"
+    _b200_kind = 3

@@ -16,7 +16,7 @@ import torch
 from . import _abi
 from ._lib import lib, require_cuda
 
-KIND_IDS = {"RBF": 0, "Matern32": 1, "Matern52": 2, "Matérn32": 1, "Matérn52": 2}
+KIND_IDS = {"RBF": 0, "Matern32": 1, "Matern52": 2, "Matern12": 3, "Matérn32": 1, "Matérn52": 2, "Matérn12": 3}
 
 
 def _p(t: Optional[torch.Tensor]):

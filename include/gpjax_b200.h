@@ -18,7 +18,7 @@
  *     Factorisation workspaces are position-dependent: pass the same (ws, ws_n, ws_d, ws_potri)
  *     to every call that works on the same factor.
  *   - kind: 0 = RBF (gpjax/kernels/stationary/rbf.py:40-44), 1 = Matern32 (matern32.py:41-54),
- *           2 = Matern52 (matern52.py:42-53).
+ *           2 = Matern52 (matern52.py:42-53), 3 = Matern12 (matern12.py:44-48).
  *
  * Citations are file:line in the reference tree (gpjax 0.13.2).
  */
@@ -40,6 +40,7 @@ extern "C" {
 #define GPB_KIND_RBF 0
 #define GPB_KIND_MATERN32 1
 #define GPB_KIND_MATERN52 2
+#define GPB_KIND_MATERN12 3
 
 const char* gpb_version(void);
 int gpb_max_input_dim(void); /* largest D the compiled kernels accept */

@@ -17,7 +17,7 @@ import math
 import numpy as np
 import scipy.linalg as sla
 
-KINDS = {"rbf": 0, "matern32": 1, "matern52": 2}
+KINDS = {"rbf": 0, "matern32": 1, "matern52": 2, "matern12": 3}
 KIND_NAMES = {v: k for k, v in KINDS.items()}
 
 __all__ = [
@@ -79,6 +79,8 @@ def _profile(kind: int, r2: np.ndarray, variance) -> np.ndarray:
     if kind == 0:
         return variance * np.exp(-0.5 * r2)
     tau = np.sqrt(np.maximum(r2, 1e-36))
+    if kind == 3:  # matern12.py:44-48
+        return variance * np.exp(-tau)
     if kind == 1:
         return variance * (1.0 + np.sqrt(3.0) * tau) * np.exp(-np.sqrt(3.0) * tau)
     if kind == 2:
@@ -189,7 +191,9 @@ def _dK_dr2(kind: int, r2: np.ndarray, K: np.ndarray, variance) -> np.ndarray:
         return -0.5 * K
     tau = np.sqrt(np.maximum(r2, 1e-36))
     live = r2 > 1e-36
-    if kind == 1:
+    if kind == 3:
+        g = -0.5 * K / tau
+    elif kind == 1:
         g = -1.5 * variance * np.exp(-np.sqrt(3.0) * tau)
     else:
         g = -(5.0 / 6.0) * variance * (1.0 + np.sqrt(5.0) * tau) * np.exp(-np.sqrt(5.0) * tau)
@@ -241,6 +245,8 @@ def _t_profile(torch, kind, r2, variance):
     if kind == 0:
         return variance * torch.exp(-0.5 * r2)
     tau = torch.sqrt(torch.clamp_min(r2, 1e-36))
+    if kind == 3:
+        return variance * torch.exp(-tau)
     if kind == 1:
         s3 = math.sqrt(3.0)
         return variance * (1.0 + s3 * tau) * torch.exp(-s3 * tau)
@@ -541,6 +547,8 @@ def gram_longdouble(kind, x, z, lengthscale, variance) -> np.ndarray:
     if kind == 0:
         return var * np.exp(ld(-0.5) * r2)
     tau = np.sqrt(np.maximum(r2, ld(1e-36)))
+    if kind == 3:
+        return var * np.exp(-tau)
     if kind == 1:
         s3 = np.sqrt(ld(3.0))
         return var * (1 + s3 * tau) * np.exp(-s3 * tau)

@@ -65,6 +65,7 @@ int gemm(stream_t, const GemmDesc& d) {
 static double profile(int kind, double r2, double var) {
     if (kind == KIND_RBF) return var * std::exp(-0.5 * r2);
     double tau = std::sqrt(std::fmax(r2, 1e-36));
+    if (kind == KIND_MATERN12) return var * std::exp(-tau);
     if (kind == KIND_MATERN32) return var * (1.0 + std::sqrt(3.0) * tau) * std::exp(-std::sqrt(3.0) * tau);
     return var * (1.0 + std::sqrt(5.0) * tau + 5.0 / 3.0 * tau * tau) * std::exp(-std::sqrt(5.0) * tau);
 }
@@ -72,6 +73,7 @@ static double dprofile(int kind, double r2, double var, double k) {
     if (kind == KIND_RBF) return -0.5 * k;
     if (!(r2 > 1e-36)) return 0.0;
     double tau = std::sqrt(r2);
+    if (kind == KIND_MATERN12) return -0.5 * k / tau;
     if (kind == KIND_MATERN32) return -1.5 * var * std::exp(-std::sqrt(3.0) * tau);
     return -(5.0 / 6.0) * var * (1.0 + std::sqrt(5.0) * tau) * std::exp(-std::sqrt(5.0) * tau);
 }

@@ -59,7 +59,7 @@ err = dict(value=abs(val[0] - ref) / abs(ref),
 vals = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
 dist.all_gather(vals, torch.tensor([val[0]], dtype=torch.float64))
 err["identical_across_ranks"] = bool(all(float(v) == float(vals[0]) for v in vals))
-print("RESULT", rank, json.dumps(err), flush=True)
+open(os.path.join({out!r}, f"result_{{rank}}.json"), "w").write(json.dumps(err))
 dist.destroy_process_group()
 '''
 
@@ -67,7 +67,7 @@ dist.destroy_process_group()
 def test_sgpr_row_sharded_world2_gloo(tmp_path):
     subprocess.run(["make", "-s", "-C", os.path.join(HERE, "hostsim")], check=True)
     script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(root=ROOT, here=HERE))
+    script.write_text(WORKER.format(root=ROOT, here=HERE, out=str(tmp_path)))
     import socket
 
     with socket.socket() as sk:  # ask the OS for a free rendezvous port
@@ -79,8 +79,7 @@ def test_sgpr_row_sharded_world2_gloo(tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     import json
 
-    results = [json.loads(l.split(" ", 2)[2]) for l in r.stdout.splitlines() if l.startswith("RESULT")]
-    assert len(results) == 2
+    results = [json.loads((tmp_path / f"result_{rank}.json").read_text()) for rank in range(2)]
     for e in results:
         assert e["n"] == 420.0 and e["identical_across_ranks"]
         for k in ("value", "Z", "ell", "var", "sn", "c"):

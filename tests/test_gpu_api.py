@@ -10,7 +10,7 @@ import torch
 import oracle as o
 
 pytestmark = pytest.mark.gpu
-NAMES = {"RBF": "rbf", "Matern32": "matern32", "Matern52": "matern52"}
+NAMES = {"RBF": "rbf", "Matern32": "matern32", "Matern52": "matern52", "Matern12": "matern12"}
 
 
 def dev(a):

@@ -7,7 +7,7 @@ import torch
 import oracle as o
 
 pytestmark = pytest.mark.gpu
-KINDS = [(0, "rbf"), (1, "matern32"), (2, "matern52")]
+KINDS = [(0, "rbf"), (1, "matern32"), (2, "matern52"), (3, "matern12")]
 TOL = 1e-8
 
 

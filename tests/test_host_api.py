@@ -10,7 +10,7 @@ from gpjax_b200.parameters import (DEFAULT_BIJECTION, NonNegativeReal, Parameter
                                    SoftplusTransform, transform)
 
 CPU = torch.device("cpu")
-KERNELS = [gpx.kernels.RBF, gpx.kernels.Matern32, gpx.kernels.Matern52]
+KERNELS = [gpx.kernels.RBF, gpx.kernels.Matern12, gpx.kernels.Matern32, gpx.kernels.Matern52]
 
 
 @pytest.mark.parametrize("K", KERNELS)
@@ -28,7 +28,7 @@ def test_kernel_ctor_validation(K):
     k = K(lengthscale=[0.1, 0.2])
     assert k.n_dims == 2 and isinstance(k.lengthscale, PositiveReal) and isinstance(k.variance, NonNegativeReal)
     assert K(active_dims=[0, 2]).n_dims == 2
-    assert K().name in ("RBF", "Matérn32", "Matérn52")
+    assert K().name in ("RBF", "Matérn12", "Matérn32", "Matérn52")
     assert isinstance(K().compute_engine, gpx.kernels.DenseKernelComputation)
 
 

@@ -13,7 +13,7 @@ import oracle as o
 from gpjax_b200 import _abi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-KINDS = [(0, "rbf"), (1, "matern32"), (2, "matern52")]
+KINDS = [(0, "rbf"), (1, "matern32"), (2, "matern52"), (3, "matern12")]
 
 
 @pytest.fixture(scope="module")

@@ -102,7 +102,7 @@ def test_log_prob_vs_scipy_mvn(n):
     assert abs(o.gaussian_log_prob_lu(mu, S, y) - multivariate_normal(mu, S).logpdf(y)) < 1e-9 * max(1, n)
 
 
-@pytest.mark.parametrize("kind", ["rbf", "matern32", "matern52"])
+@pytest.mark.parametrize("kind", ["rbf", "matern12", "matern32", "matern52"])
 def test_closed_form_gradients_match_autodiff(kind):
     rng = np.random.default_rng(5)
     n, D, m = 70, 3, 11
