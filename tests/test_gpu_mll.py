@@ -104,3 +104,12 @@ def test_mll_not_pd_returns_nan():
     y = np.zeros((300, 1))
     v = ops.conjugate_mll_fused(0, dev(X), dev(y), dev(np.array([1.0, 1.0])), dev(1.0), dev(0.0), None, 0.0)
     assert np.isnan(v.item())
+
+
+def test_mll_large_input_dim():
+    X, y = make_data(400, 40, 3)
+    ell = np.linspace(3.0, 5.0, 40)
+    ref, gref = o.conjugate_mll_value_and_grad_autodiff("matern32", X, y, ell, 1.1, 0.25, 0.0)
+    val, g = run_gpu(1, X, y, ell, 1.1, 0.25, 0.0)
+    assert abs(val - ref) <= TOL * abs(ref)
+    assert np.max(np.abs(g["lengthscale"] - gref["lengthscale"])) <= TOL * np.max(np.abs(gref["lengthscale"]))

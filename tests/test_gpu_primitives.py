@@ -188,3 +188,34 @@ def test_potrf_not_positive_definite_nan_fills():
     assert int(info.item()) == 201
     assert torch.isnan(A[299, 299])
     assert not torch.isnan(A[100, 50])  # rows factored before the failure stay valid
+
+
+@pytest.mark.parametrize("D", [33, 64])
+def test_gram_and_backward_large_input_dim(D):
+    """Input dimensions beyond one 8-wide chunk, up to the compiled maximum (64)."""
+    from gpjax_b200 import ops
+    from oracle.gp_oracle import _t_cross
+
+    rng = np.random.default_rng(D)
+    N, M = 130, 200
+    X, Z = rng.uniform(-1, 1, (N, D)), rng.uniform(-1, 1, (M, D))
+    ell = np.linspace(2.0, 4.0, D)
+    K = ops.gram_forward(2, dev(X), dev(Z), dev(ell), dev(1.3)).cpu().numpy()
+    assert rel(K, o.cross_covariance("matern52", X, Z, ell, 1.3)) <= 1e-12
+    dK = rng.standard_normal((N, M))
+    Xt, Zt = torch.tensor(X, requires_grad=True), torch.tensor(Z, requires_grad=True)
+    et, vt = torch.tensor(ell, requires_grad=True), torch.tensor(1.3, dtype=torch.float64, requires_grad=True)
+    (_t_cross(torch, 2, Xt, Zt, et, vt) * torch.tensor(dK)).sum().backward()
+    g_ell, g_var, g_X, g_Z = ops.gram_backward(2, dev(X), dev(Z), dev(ell), dev(1.3), dev(dK), want_X=True, want_Z=True)
+    assert np.max(np.abs(g_ell.cpu().numpy() - et.grad.numpy())) <= 1e-10 * np.abs(et.grad.numpy()).max()
+    assert abs(g_var.item() - vt.grad.item()) <= 1e-10 * abs(vt.grad.item())
+    assert np.max(np.abs(g_X.cpu().numpy() - Xt.grad.numpy())) <= 1e-10 * np.abs(Xt.grad.numpy()).max()
+    assert np.max(np.abs(g_Z.cpu().numpy() - Zt.grad.numpy())) <= 1e-10 * np.abs(Zt.grad.numpy()).max()
+
+
+def test_input_dim_above_compiled_maximum_is_rejected():
+    from gpjax_b200 import ops
+
+    X = torch.zeros((4, 65), dtype=torch.float64, device="cuda")
+    with pytest.raises(RuntimeError, match="UNSUPPORTED"):
+        ops.gram_forward(0, X, X, torch.ones(65, dtype=torch.float64, device="cuda"), dev(1.0))
