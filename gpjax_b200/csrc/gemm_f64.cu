@@ -197,8 +197,9 @@ __host__ __device__ inline void live_range(const GemmParams& p, int64_t tm, int6
     }
 }
 
-template <int BM, int BN, int WM, int WN, int STAGES, int MINB, bool SWZ, int ALAY, int BLAY>
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB, bool SWZ, bool BULK, int ALAY, int BLAY>
 __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) gemm_f64_kernel(const GemmParams p) {
+    static_assert(!(BULK && SWZ), "bulk row copies need the contiguous (padded) row layout");
     constexpr int NT = (BM / WM) * (BN / WN) * 32;
     constexpr int WARPS_N = BN / WN;
     constexpr int TM = WM / 8, TN = WN / 8;
@@ -207,11 +208,20 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) gemm_f64_ker
     extern __shared__ __align__(16) double smem[];
     double* As = smem;
     double* Bs = smem + STAGES * GA::SIZE;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (GA::SIZE + GB::SIZE));  // [STAGES] (BULK only)
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
     const int wm0 = (warp / WARPS_N) * WM;
     const int wn0 = (warp % WARPS_N) * WN;
+    if (BULK) {
+        if (tid == 0) {
+#pragma unroll
+            for (int st = 0; st < STAGES; ++st) mbar_init(full + st, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
 
     // Tile enumeration without dead CTAs: tile-row y is folded with tile-row T-1-y (their live
     // column counts add up to ~const for triangular masks), blockIdx.x walks both live ranges.
@@ -293,7 +303,28 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) gemm_f64_ker
     pa.init(A, p.lda, m0, tid);
     pb.init(B, p.ldb, n0, tid);
 
+    // Bulk path (CTA-uniform): every chunk of this tile is a full, aligned BK-wide slab, so each operand row is
+    // ONE cp.async.bulk (TMA engine) of BK*8 (K layout) or ROWS*8 (MN layout) bytes tracked by the stage's
+    // mbarrier; 1-2 copy instructions per thread per chunk instead of 12 LDGSTS.
+    const bool use_bulk = BULK && a_fast && b_fast && ((kend - kbeg) % BK == 0);
+    auto bulk_stage = [&](int st, int64_t k0) {
+        if (tid == 0) mbar_arrive_expect_tx(full + st, (unsigned)((BM + BN) * BK * sizeof(double)));
+        double* as_ = As + st * GA::SIZE;
+        double* bs_ = Bs + st * GB::SIZE;
+        if (ALAY == LAYOUT_K) {
+            for (int r = tid; r < BM; r += NT) bulk_g2s(as_ + r * GA::LD, A + (m0 + r) * p.lda + k0, BK * 8, full + st);
+        } else {
+            for (int kr = tid; kr < BK; kr += NT) bulk_g2s(as_ + kr * GA::LD, A + (k0 + kr) * p.lda + m0, BM * 8, full + st);
+        }
+        if (BLAY == LAYOUT_K) {
+            for (int r = tid; r < BN; r += NT) bulk_g2s(bs_ + r * GB::LD, B + (n0 + r) * p.ldb + k0, BK * 8, full + st);
+        } else {
+            // spread over the upper lanes so the A and B row copies of an MN/MN tile come from different threads
+            for (int kr = NT - 1 - tid; kr < BK; kr += NT) bulk_g2s(bs_ + kr * GB::LD, B + (k0 + kr) * p.ldb + n0, BN * 8, full + st);
+        }
+    };
     auto load_stage = [&](int st, int64_t k0) {
+        if (use_bulk) { bulk_stage(st, k0); return; }
         const bool kfull = (k0 + BK <= kend);
         if (a_fast && kfull) pa.issue(As + st * GA::SIZE, k0);
         else load_tile<BM, ALAY, NT, SWZ>(As + st * GA::SIZE, A, p.lda, m0, p.M, k0, kend, av, tid);
@@ -333,7 +364,8 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) gemm_f64_ker
     }
 
     for (int it = 0; it < nk; ++it) {
-        cp_async_wait<STAGES - 2>();
+        if (use_bulk) mbar_wait(full + (it % STAGES), (unsigned)((it / STAGES) & 1));
+        else cp_async_wait<STAGES - 2>();
         __syncthreads();
         {
             const int nx = it + STAGES - 1;
@@ -440,12 +472,12 @@ __global__ void __launch_bounds__((BM / WM) * (BN / WN) * 32, MINB) gemm_f64_ker
     }
 }
 
-template <int BM, int BN, int WM, int WN, int STAGES, int MINB, bool SWZ, int ALAY, int BLAY>
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB, bool SWZ, bool BULK, int ALAY, int BLAY>
 int launch_gemm(cudaStream_t st, const GemmParams& p, int batch) {
     using GA = TileGeom<BM, ALAY, SWZ>;
     using GB = TileGeom<BN, BLAY, SWZ>;
-    constexpr size_t smem = sizeof(double) * STAGES * (GA::SIZE + GB::SIZE);
-    auto kern = gemm_f64_kernel<BM, BN, WM, WN, STAGES, MINB, SWZ, ALAY, BLAY>;
+    constexpr size_t smem = sizeof(double) * STAGES * (GA::SIZE + GB::SIZE) + (BULK ? STAGES * sizeof(uint64_t) : 0);
+    auto kern = gemm_f64_kernel<BM, BN, WM, WN, STAGES, MINB, SWZ, BULK, ALAY, BLAY>;
     static bool configured = false;  // per-instantiation, idempotent
     if (!configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -486,18 +518,18 @@ int launch_gemm(cudaStream_t st, const GemmParams& p, int batch) {
 static int g_variant = 2;
 void debug_set_gemm_variant(int v) { g_variant = v; }
 
-template <int BM, int BN, int WM, int WN, int STAGES, int MINB, bool SWZ>
+template <int BM, int BN, int WM, int WN, int STAGES, int MINB, bool SWZ, bool BULK>
 static int dispatch_layouts(cudaStream_t st, GemmParams p, const GemmDesc& d) {
     p.tiles_m = (d.M + BM - 1) / BM;
     p.tiles_n = (d.N + BN - 1) / BN;
     if (d.a_layout == LAYOUT_K && d.b_layout == LAYOUT_K)
-        return launch_gemm<BM, BN, WM, WN, STAGES, MINB, SWZ, LAYOUT_K, LAYOUT_K>(st, p, d.batch);
+        return launch_gemm<BM, BN, WM, WN, STAGES, MINB, SWZ, BULK, LAYOUT_K, LAYOUT_K>(st, p, d.batch);
     if (d.a_layout == LAYOUT_K && d.b_layout == LAYOUT_MN)
-        return launch_gemm<BM, BN, WM, WN, STAGES, MINB, SWZ, LAYOUT_K, LAYOUT_MN>(st, p, d.batch);
+        return launch_gemm<BM, BN, WM, WN, STAGES, MINB, SWZ, BULK, LAYOUT_K, LAYOUT_MN>(st, p, d.batch);
     if (d.a_layout == LAYOUT_MN && d.b_layout == LAYOUT_K)
-        return launch_gemm<BM, BN, WM, WN, STAGES, MINB, SWZ, LAYOUT_MN, LAYOUT_K>(st, p, d.batch);
+        return launch_gemm<BM, BN, WM, WN, STAGES, MINB, SWZ, BULK, LAYOUT_MN, LAYOUT_K>(st, p, d.batch);
     if (d.a_layout == LAYOUT_MN && d.b_layout == LAYOUT_MN)
-        return launch_gemm<BM, BN, WM, WN, STAGES, MINB, SWZ, LAYOUT_MN, LAYOUT_MN>(st, p, d.batch);
+        return launch_gemm<BM, BN, WM, WN, STAGES, MINB, SWZ, BULK, LAYOUT_MN, LAYOUT_MN>(st, p, d.batch);
     return GPB_ERR_INVALID;
 }
 
@@ -529,9 +561,15 @@ int gemm(stream_t s, const GemmDesc& d) {
     //   8 warps x (32x32), padded, 3 stages, 2 CTAs/SM       : 33.2 / 31.9   (variant 0, first version)
     //   rejected and removed: 4 x (64x32) (= default), swizzled 3 CTAs/SM at 168 regs (31.1, spills),
     //   128x128 CTA with 1 CTA/SM and 3 or 4 stages (31.9).
-    if (g_variant == 0) return dispatch_layouts<128, 64, 32, 32, 3, 2, false>(st, p, d);
-    if (g_variant == 8) return dispatch_layouts<128, 64, 32, 64, 4, 2, true>(st, p, d);
-    return dispatch_layouts<128, 64, 32, 64, 3, 2, false>(st, p, d);
+    //   variant 9 = operand staging through the TMA engine (cp.async.bulk row copies + mbarrier tx-count, SASS
+    //   UBLKCP / SYNCS): correct, but 192 x 128-byte copies per stage are too fine-grained for it -- 20.1 TF/s for
+    //   K-contiguous operands, 29.6 for the 512/1024-byte rows of the MN/MN layout -- so LDGSTS stays the default.
+    //   (A 2-D tensor-map TMA cannot produce the padded rows, and its hardware swizzles are not conflict-free for
+    //   the 8x4 f64 fragment: rows r and r^1 land in the same 32-byte bank group.)
+    if (g_variant == 0) return dispatch_layouts<128, 64, 32, 32, 3, 2, false, false>(st, p, d);
+    if (g_variant == 8) return dispatch_layouts<128, 64, 32, 64, 4, 2, true, false>(st, p, d);
+    if (g_variant == 9) return dispatch_layouts<128, 64, 32, 64, 3, 2, false, true>(st, p, d);  // TMA bulk-copy staging
+    return dispatch_layouts<128, 64, 32, 64, 3, 2, false, false>(st, p, d);
 }
 
 }  // namespace gpb
