@@ -200,3 +200,33 @@ def test_collapsed_predict_and_fit_lbfgs():
     opt, final = gpx.fit_lbfgs(model=q, objective=neg, train_data=D, max_iters=15)
     assert isinstance(opt, gpx.variational_families.CollapsedVariationalGaussian)
     assert final.item() < before and abs(neg(opt, D).item() - final.item()) <= 1e-8 * abs(final.item())
+
+
+def test_reference_regression_golden_on_gpu():
+    """The CUDA path on the data of the reference's examples/regression.py (tests/golden/regression_example.npz):
+    the objective at the stored optimum equals the reference's stored golden 55.07405622 (tests/integration_tests.py:
+    99-107, tolerance there: 1.0), gpx.fit_scipy from the example's initial parameters gets there, and the predictive
+    moments match the fixture."""
+    import os
+
+    import gpjax_b200 as gpx
+    from gpjax_b200.parameters import Real
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "regression_example.npz"))
+    D = gpx.Dataset(X=dev(g["x"]), y=dev(g["y"]))
+    neg = lambda p, d: -gpx.objectives.conjugate_mll(p, d)
+
+    def posterior(ell, var, sn, c):
+        prior = gpx.gps.Prior(mean_function=gpx.mean_functions.Constant(Real(c)), kernel=gpx.kernels.RBF(lengthscale=ell, variance=var))
+        return prior * gpx.likelihoods.Gaussian(num_datapoints=D.n, obs_stddev=sn)
+
+    at_opt = neg(posterior(float(g["lengthscale"]), float(g["variance"]), float(g["obs_stddev"]), float(g["mean_const"])), D).item()
+    assert abs(at_opt - float(g["neg_mll_at_optimum"])) <= 1e-8 * abs(at_opt)
+    assert abs(at_opt - float(g["reference_golden_history_last"])) < 1e-4
+    init = posterior(1.0, 1.0, 1.0, 0.0)
+    assert abs(neg(init, D).item() - float(g["neg_mll_at_init"])) <= 1e-8 * float(g["neg_mll_at_init"])
+    opt, hist = gpx.fit_scipy(model=init, objective=neg, train_data=D, verbose=False)
+    assert abs(hist[-1].item() - float(g["reference_golden_history_last"])) < 1e-3
+    pred = opt.likelihood(opt.predict(dev(g["xtest"]), D))
+    assert abs(pred.mean().sum().item() - float(g["reference_golden_predictive_mean_sum"])) < 1.0
+    assert abs(pred.stddev().sum().item() - float(g["reference_golden_predictive_std_sum"])) < 1.0

@@ -137,3 +137,17 @@ def test_add_jitter_errors():  # tests/test_linalg.py:491-558
         o.add_jitter(np.zeros((2, 3)), 1e-6)
     with pytest.raises(ValueError):
         o.add_jitter(np.zeros(3), 1e-6)
+
+
+def test_committed_golden_fixture_is_consistent():
+    """tests/golden/regression_example.npz (made by tests/golden/make_regression_fixture.py): the stored data
+    reproduce the stored optimum on the oracle, and that optimum sits on the reference's stored golden."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "regression_example.npz"))
+    v = -o.conjugate_mll("rbf", g["x"], g["y"], float(g["lengthscale"]), float(g["variance"]), float(g["obs_stddev"]),
+                         float(g["mean_const"]))
+    assert abs(v - float(g["neg_mll_at_optimum"])) <= 1e-10 * abs(v)
+    assert abs(v - float(g["reference_golden_history_last"])) < 1e-4          # reference tolerance: 1.0
+    assert abs(g["predictive_mean"].sum() - float(g["reference_golden_predictive_mean_sum"])) < 1.0
+    assert abs(g["predictive_std"].sum() - float(g["reference_golden_predictive_std_sum"])) < 1.0
