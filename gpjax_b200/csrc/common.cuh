@@ -70,12 +70,14 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "d"(a), "d"(b));
 }
 
-// ---- stationary kernel profiles (reference: gpjax/kernels/stationary/{rbf,matern32,matern52}.py) ----
+// ---- stationary kernel profiles (reference: gpjax/kernels/stationary/*.py) ---------------------------
 // value and d/d(r2) of g(r2) with variance folded in.  The 1e-36 clamp of
 // euclidean_distance (stationary/utils.py:67) makes the derivative vanish where r2 <= 1e-36.
+// `shp` is the kernel's shape parameter (RationalQuadratic alpha, PoweredExponential power); for
+// KIND_PERIODIC r2 is already sum_d (sin(pi (x_d - y_d) / p) / l_d)^2, so its profile is the RBF one.
 template <int KIND>
-__device__ __forceinline__ double kprofile(double r2, double var) {
-    if (KIND == KIND_RBF) {
+__device__ __forceinline__ double kprofile(double r2, double var, double shp) {
+    if (KIND == KIND_RBF || KIND == KIND_PERIODIC) {
         return var * exp(-0.5 * r2);
     } else if (KIND == KIND_MATERN32) {
         const double s3 = 1.7320508075688772;
@@ -83,6 +85,12 @@ __device__ __forceinline__ double kprofile(double r2, double var) {
         return var * (1.0 + s3 * tau) * exp(-s3 * tau);
     } else if (KIND == KIND_MATERN12) {  // gpjax/kernels/stationary/matern12.py:44-48
         return var * exp(-sqrt(fmax(r2, 1e-36)));
+    } else if (KIND == KIND_RATQUAD) {  // rational_quadratic.py:77-83
+        return var * pow(1.0 + 0.5 * r2 / shp, -shp);
+    } else if (KIND == KIND_POWEXP) {  // powered_exponential.py:85-89
+        return var * exp(-pow(sqrt(fmax(r2, 1e-36)), shp));
+    } else if (KIND == KIND_WHITE) {  // white.py:63-64: all(x == y); lengthscale is 1 so r2 == 0 <=> equal inputs
+        return r2 == 0.0 ? var : 0.0;
     } else {
         const double s5 = 2.23606797749979;
         double tau = sqrt(fmax(r2, 1e-36));
@@ -90,9 +98,13 @@ __device__ __forceinline__ double kprofile(double r2, double var) {
     }
 }
 
+// also returns d k / d shp (0 for kinds without a shape parameter; KIND_PERIODIC's period gradient is
+// assembled in the per-dimension contraction instead)
 template <int KIND>
-__device__ __forceinline__ void kprofile_grad(double r2, double var, double& k, double& dk_dr2) {
-    if (KIND == KIND_RBF) {
+__device__ __forceinline__ void kprofile_grad(double r2, double var, double shp, double& k, double& dk_dr2,
+                                              double& dk_dshp) {
+    dk_dshp = 0.0;
+    if (KIND == KIND_RBF || KIND == KIND_PERIODIC) {
         k = var * exp(-0.5 * r2);
         dk_dr2 = -0.5 * k;
     } else if (KIND == KIND_MATERN32) {
@@ -105,6 +117,20 @@ __device__ __forceinline__ void kprofile_grad(double r2, double var, double& k, 
         double tau = sqrt(fmax(r2, 1e-36));
         k = var * exp(-tau);
         dk_dr2 = (r2 > 1e-36) ? (-0.5 * k / tau) : 0.0;  // d/dr2 exp(-sqrt(r2)); clamp kills it at r2 <= 1e-36
+    } else if (KIND == KIND_RATQUAD) {
+        double u = 0.5 * r2 / shp, b = 1.0 + u;
+        k = var * pow(b, -shp);
+        dk_dr2 = -0.5 * k / b;
+        dk_dshp = k * (u / b - log1p(u));
+    } else if (KIND == KIND_POWEXP) {
+        double tau = sqrt(fmax(r2, 1e-36));
+        double tp = pow(tau, shp);
+        k = var * exp(-tp);
+        dk_dr2 = (r2 > 1e-36) ? (-0.5 * shp * tp / (tau * tau) * k) : 0.0;
+        dk_dshp = -k * tp * log(tau);
+    } else if (KIND == KIND_WHITE) {
+        k = r2 == 0.0 ? var : 0.0;
+        dk_dr2 = 0.0;
     } else {
         const double s5 = 2.23606797749979;
         double tau = sqrt(fmax(r2, 1e-36));

@@ -30,7 +30,8 @@ __host__ __device__ inline int pad_dim(int D, int DC) { return ((D + DC - 1) / D
 
 // Load a tile of inputs divided by the lengthscale into shared memory, zero padded.
 //  ROWMAJOR: dst[r*Dp + d]   else dst[d*rows + r]
-template <bool ROWMAJOR>
+//  RAW (periodic kernel): the inputs are stored as they are; the lengthscale enters after the sine.
+template <bool ROWMAJOR, bool RAW = false>
 __device__ __forceinline__ void load_scaled(double* dst, const double* __restrict__ P, int64_t ld,
                                             int64_t r0, int64_t nrows, int rows, int D, int Dp,
                                             const double* __restrict__ ell, int ell_is_scalar) {
@@ -39,15 +40,23 @@ __device__ __forceinline__ void load_scaled(double* dst, const double* __restric
         int r = id / Dp, d = id % Dp;
         double v = 0.0;
         int64_t gr = r0 + r;
-        if (gr < nrows && d < D) v = P[gr * ld + d] / ell[ell_is_scalar ? 0 : d];
+        if (gr < nrows && d < D) v = RAW ? P[gr * ld + d] : P[gr * ld + d] / ell[ell_is_scalar ? 0 : d];
         dst[ROWMAJOR ? (r * Dp + d) : (d * rows + r)] = v;
     }
 }
 
+// lengthscales into shared memory, padded with 1 (periodic kernel only)
+__device__ __forceinline__ void load_ell(double* ell_s, const double* __restrict__ ell, int ell_is_scalar, int D, int Dp) {
+    for (int d = threadIdx.x; d < Dp; d += blockDim.x) ell_s[d] = d < D ? ell[ell_is_scalar ? 0 : d] : 1.0;
+}
+
 // r2 for the thread's RPT x 2 outputs
-template <int DC>
+// PER (periodic.py:81-88): the per-dimension term is sin(pi (x_d - z_d) / p) / l_d instead of (x_d - z_d) / l_d;
+// pc = pi / p, ell_s = lengthscales in shared memory.
+template <int DC, bool PER = false>
 __device__ __forceinline__ void tile_r2(const double* __restrict__ Xs, const double* __restrict__ Zs, int Dp,
-                                        int tx, int ty, double (&r2)[RPT][2]) {
+                                        int tx, int ty, double (&r2)[RPT][2], const double* __restrict__ ell_s = nullptr,
+                                        double pc = 0.0) {
 #pragma unroll
     for (int i = 0; i < RPT; ++i) r2[i][0] = r2[i][1] = 0.0;
     for (int d0 = 0; d0 < Dp; d0 += DC) {
@@ -65,6 +74,11 @@ __device__ __forceinline__ void tile_r2(const double* __restrict__ Xs, const dou
             for (int d = 0; d < DC; ++d) {
                 double x = xr[d];
                 double a = x - z0[d], b = x - z1[d];
+                if (PER) {
+                    const double l = ell_s[d0 + d];
+                    a = sin(a * pc) / l;
+                    b = sin(b * pc) / l;
+                }
                 r2[i][0] = fma(a, a, r2[i][0]);
                 r2[i][1] = fma(b, b, r2[i][1]);
             }
@@ -94,16 +108,21 @@ __global__ void __launch_bounds__(GT, 2) gram_kernel(const GramParams p) {
     const int Dp = pad_dim(p.D, DC);
     double* Xs = sm;             // [TR][Dp]
     double* Zs = sm + TR * Dp;   // [Dp][TC]
+    double* ell_s = Zs + Dp * TC;  // [Dp]  (periodic only)
+    constexpr bool PER = (KIND == KIND_PERIODIC);
+    constexpr bool SHP = (KIND == KIND_RATQUAD || KIND == KIND_POWEXP || KIND == KIND_PERIODIC);
     const int64_t tr = blockIdx.x / p.tiles_c, tc = blockIdx.x % p.tiles_c;
     const int64_t r0 = tr * TR, c0 = tc * TC;
     if (p.lower_only && (p.row0 + min(r0 + TR, p.N) - 1 < p.col0 + c0)) return;
-    load_scaled<true>(Xs, p.X, p.ldx, r0, p.N, TR, p.D, Dp, p.ell, p.ell_is_scalar);
-    load_scaled<false>(Zs, p.Z, p.ldz, c0, p.M, TC, p.D, Dp, p.ell, p.ell_is_scalar);
+    load_scaled<true, PER>(Xs, p.X, p.ldx, r0, p.N, TR, p.D, Dp, p.ell, p.ell_is_scalar);
+    load_scaled<false, PER>(Zs, p.Z, p.ldz, c0, p.M, TC, p.D, Dp, p.ell, p.ell_is_scalar);
+    if (PER) load_ell(ell_s, p.ell, p.ell_is_scalar, p.D, Dp);
     __syncthreads();
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const double var = p.variance[0];
+    const double shp = SHP ? p.variance[1] : 0.0;
     double r2[RPT][2];
-    tile_r2<DC>(Xs, Zs, Dp, tx, ty, r2);
-    const double var = *p.variance;
+    tile_r2<DC, PER>(Xs, Zs, Dp, tx, ty, r2, ell_s, PER ? (3.141592653589793 / shp) : 0.0);
     double dadd = p.diag_add;
     if (p.diag_add_sq) { double t = *p.diag_add_sq; dadd += t * t; }
     const int64_t c = c0 + 2 * tx;
@@ -113,8 +132,8 @@ __global__ void __launch_bounds__(GT, 2) gram_kernel(const GramParams p) {
     for (int i = 0; i < RPT; ++i) {
         int64_t r = r0 + ty + 4 * i;
         if (r >= p.N) continue;
-        double k0 = kprofile<KIND>(r2[i][0], var);
-        double k1 = kprofile<KIND>(r2[i][1], var);
+        double k0 = kprofile<KIND>(r2[i][0], var, shp);
+        double k1 = kprofile<KIND>(r2[i][1], var, shp);
         if (p.row0 + r == p.col0 + c) k0 += dadd;
         if (p.row0 + r == p.col0 + c + 1) k1 += dadd;
         double* out = p.K + r * p.ldk + c;
@@ -131,7 +150,7 @@ template <int KIND>
 int launch_gram(cudaStream_t st, const GramParams& p, int64_t ntiles) {
     int DC = p.D <= 2 ? 2 : (p.D <= 4 ? 4 : 8);
     int Dp = pad_dim(p.D, DC);
-    size_t smem = sizeof(double) * (size_t)(TR + TC) * Dp;
+    size_t smem = sizeof(double) * ((size_t)(TR + TC) * Dp + Dp);
     dim3 grid((unsigned)ntiles);
 #define GPB_GRAM_LAUNCH(DCV)                                                                         \
     {                                                                                                \
@@ -156,12 +175,18 @@ int launch_gram(cudaStream_t st, const GramParams& p, int64_t ntiles) {
 // and accumulates   sum w*K  (for d/dvariance)  and, per input dimension,
 //   sum G * (xs_d - zs_d)^2   (for d/dl_d = -2/l_d * that)
 // plus, optionally, per-row / per-column   sum G * (xs_d - zs_d)   (for dX, dZ).
-template <int DC, bool WANT_X, bool WANT_Z>
+// PER: with u = pi (x_d - z_d) / p and a = sin(u) / l_d the lengthscale term keeps its form (sum G a^2), the
+// input gradients pick up cos(u) (and a factor pi / p applied by the caller), and the period gradient is
+// -(2 / p) sum G a cos(u) u / l_d, returned through `per_acc`.
+template <int DC, bool WANT_X, bool WANT_Z, bool PER = false>
 __device__ __forceinline__ void contract_dims(const double* __restrict__ Xs, const double* __restrict__ Zs,
                                               int Dp, int tx, int ty, const double (&G)[RPT][2],
                                               double* __restrict__ ell_acc /*[Dp] smem, atomically added*/,
                                               double* __restrict__ gx_s /*[TR][Dp] smem*/,
-                                              double* __restrict__ gz_s /*[Dp][TC] smem*/) {
+                                              double* __restrict__ gz_s /*[Dp][TC] smem*/,
+                                              const double* __restrict__ ell_s = nullptr, double pc = 0.0,
+                                              double* per_acc = nullptr) {
+    double pacc = 0.0;
     for (int d0 = 0; d0 < Dp; d0 += DC) {
         double z0[DC], z1[DC], acc[DC], gz0[DC], gz1[DC];
 #pragma unroll
@@ -180,15 +205,28 @@ __device__ __forceinline__ void contract_dims(const double* __restrict__ Xs, con
             for (int d = 0; d < DC; ++d) {
                 double x = xr[d];
                 double a = x - z0[d], b = x - z1[d];
+                double ax = a, bx = b;  // factors of the input gradients
+                if (PER) {
+                    const double l = ell_s[d0 + d];
+                    double ua = a * pc, ub = b * pc, sa, ca, sb, cb;
+                    sincos(ua, &sa, &ca);
+                    sincos(ub, &sb, &cb);
+                    a = sa / l;
+                    b = sb / l;
+                    ax = a * ca;
+                    bx = b * cb;
+                    pacc = fma(g0 * ax, ua / l, pacc);
+                    pacc = fma(g1 * bx, ub / l, pacc);
+                }
                 acc[d] = fma(g0 * a, a, acc[d]);
                 acc[d] = fma(g1 * b, b, acc[d]);
                 if (WANT_Z) {
-                    gz0[d] = fma(g0, a, gz0[d]);
-                    gz1[d] = fma(g1, b, gz1[d]);
+                    gz0[d] = fma(g0, ax, gz0[d]);
+                    gz1[d] = fma(g1, bx, gz1[d]);
                 }
                 if (WANT_X) {
                     // row gradient: reduce over the 64 column-threads of this row group
-                    double gx = fma(g0, a, g1 * b);
+                    double gx = fma(g0, ax, g1 * bx);
                     gx = warp_sum(gx);
                     if ((threadIdx.x & 31) == 0) atomicAdd(gx_s + (ty + 4 * i) * Dp + d0 + d, gx);
                 }
@@ -204,6 +242,7 @@ __device__ __forceinline__ void contract_dims(const double* __restrict__ Xs, con
             }
         }
     }
+    if (PER) *per_acc = pacc;
 }
 
 struct GramBwdParams {
@@ -215,7 +254,7 @@ struct GramBwdParams {
     const double* variance;
     const double* dK; int64_t lddk;
     double scale;
-    double* partials;  // [ntiles][Dp + 1]
+    double* partials;  // [ntiles][Dp + 2]  (.., sum w*K, shape-parameter term)
     double* g_X; int64_t ldgx;
     double* g_Z; int64_t ldgz;
     int64_t tiles_c;
@@ -229,12 +268,16 @@ __global__ void __launch_bounds__(GT, (WANT_X || WANT_Z) ? 1 : 2) gram_bwd_kerne
     double* Zs = Xs + TR * Dp;           // [Dp][TC]
     double* ell_acc = Zs + Dp * TC;      // [Dp]
     double* red = ell_acc + Dp;          // [32]
-    double* gx_s = red + 32;             // [TR][Dp]   (WANT_X)
+    double* ell_s = red + 32;            // [Dp]       (periodic only)
+    double* gx_s = ell_s + Dp;           // [TR][Dp]   (WANT_X)
     double* gz_s = gx_s + (WANT_X ? TR * Dp : 0);  // [Dp][TC]   (WANT_Z)
+    constexpr bool PER = (KIND == KIND_PERIODIC);
+    constexpr bool SHP = (KIND == KIND_RATQUAD || KIND == KIND_POWEXP || KIND == KIND_PERIODIC);
     const int64_t tr = blockIdx.x / p.tiles_c, tc = blockIdx.x % p.tiles_c;
     const int64_t r0 = tr * TR, c0 = tc * TC;
-    load_scaled<true>(Xs, p.X, p.ldx, r0, p.N, TR, p.D, Dp, p.ell, p.ell_is_scalar);
-    load_scaled<false>(Zs, p.Z, p.ldz, c0, p.M, TC, p.D, Dp, p.ell, p.ell_is_scalar);
+    load_scaled<true, PER>(Xs, p.X, p.ldx, r0, p.N, TR, p.D, Dp, p.ell, p.ell_is_scalar);
+    load_scaled<false, PER>(Zs, p.Z, p.ldz, c0, p.M, TC, p.D, Dp, p.ell, p.ell_is_scalar);
+    if (PER) load_ell(ell_s, p.ell, p.ell_is_scalar, p.D, Dp);
     for (int i = threadIdx.x; i < Dp; i += GT) ell_acc[i] = 0.0;
     if (WANT_X)
         for (int i = threadIdx.x; i < TR * Dp; i += GT) gx_s[i] = 0.0;
@@ -242,11 +285,13 @@ __global__ void __launch_bounds__(GT, (WANT_X || WANT_Z) ? 1 : 2) gram_bwd_kerne
         for (int i = threadIdx.x; i < Dp * TC; i += GT) gz_s[i] = 0.0;
     __syncthreads();
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const double var = p.variance[0];
+    const double shp = SHP ? p.variance[1] : 0.0;
+    const double pc = PER ? (3.141592653589793 / shp) : 0.0;
     double r2[RPT][2];
-    tile_r2<DC>(Xs, Zs, Dp, tx, ty, r2);
-    const double var = *p.variance;
+    tile_r2<DC, PER>(Xs, Zs, Dp, tx, ty, r2, ell_s, pc);
     const int64_t c = c0 + 2 * tx;
-    double wk = 0.0;
+    double wk = 0.0, wshp = 0.0;
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
         int64_t r = r0 + ty + 4 * i;
@@ -254,16 +299,18 @@ __global__ void __launch_bounds__(GT, (WANT_X || WANT_Z) ? 1 : 2) gram_bwd_kerne
         for (int j = 0; j < 2; ++j) {
             double w = 0.0;
             if (r < p.N && c + j < p.M) w = p.dK[r * p.lddk + c + j];
-            double k, dk;
-            kprofile_grad<KIND>(r2[i][j], var, k, dk);
+            double k, dk, ds;
+            kprofile_grad<KIND>(r2[i][j], var, shp, k, dk, ds);
             wk = fma(w, k, wk);
+            if (SHP && !PER) wshp = fma(w, ds, wshp);
             r2[i][j] = w * dk;  // becomes G
         }
     }
-    contract_dims<DC, WANT_X, WANT_Z>(Xs, Zs, Dp, tx, ty, r2, ell_acc, gx_s, gz_s);
+    contract_dims<DC, WANT_X, WANT_Z, PER>(Xs, Zs, Dp, tx, ty, r2, ell_acc, gx_s, gz_s, ell_s, pc, &wshp);
     double s = block_sum(wk, red);  // contains __syncthreads -> smem atomics above are complete
-    double* out = p.partials + (int64_t)blockIdx.x * (Dp + 1);
-    if (threadIdx.x == 0) out[Dp] = s;
+    double s2 = SHP ? block_sum(wshp, red) : 0.0;
+    double* out = p.partials + (int64_t)blockIdx.x * (Dp + 2);
+    if (threadIdx.x == 0) { out[Dp] = s; out[Dp + 1] = s2; }
     for (int i = threadIdx.x; i < Dp; i += GT) out[i] = ell_acc[i];
     {
         // dr2/dx_d = 2 (xs_d - zs_d) / l_d ; dr2/dz_d = -2 (xs_d - zs_d) / l_d
@@ -272,7 +319,7 @@ __global__ void __launch_bounds__(GT, (WANT_X || WANT_Z) ? 1 : 2) gram_bwd_kerne
                 int r = i / p.D, d = i % p.D;
                 if (r0 + r < p.N) {
                     double l = p.ell[p.ell_is_scalar ? 0 : d];
-                    atomicAdd(p.g_X + (r0 + r) * p.ldgx + d, p.scale * 2.0 * gx_s[r * Dp + d] / l);
+                    atomicAdd(p.g_X + (r0 + r) * p.ldgx + d, p.scale * (PER ? 2.0 * pc : 2.0) * gx_s[r * Dp + d] / l);
                 }
             }
         }
@@ -281,7 +328,7 @@ __global__ void __launch_bounds__(GT, (WANT_X || WANT_Z) ? 1 : 2) gram_bwd_kerne
                 int cc = i / p.D, d = i % p.D;
                 if (c0 + cc < p.M) {
                     double l = p.ell[p.ell_is_scalar ? 0 : d];
-                    atomicAdd(p.g_Z + (c0 + cc) * p.ldgz + d, -p.scale * 2.0 * gz_s[d * TC + cc] / l);
+                    atomicAdd(p.g_Z + (c0 + cc) * p.ldgz + d, -p.scale * (PER ? 2.0 * pc : 2.0) * gz_s[d * TC + cc] / l);
                 }
             }
         }
@@ -289,20 +336,23 @@ __global__ void __launch_bounds__(GT, (WANT_X || WANT_Z) ? 1 : 2) gram_bwd_kerne
 }
 
 // final deterministic reduction of per-tile partials: g_ell[d] += scale*(-2/l_d)*sum, g_var += scale*sum/var
+// (shape_mode 0: no shape parameter; 1: g_var[1] += scale * sum; 2 (periodic): g_var[1] += scale * (-2/p) * sum)
 __global__ void gram_bwd_reduce_kernel(const double* __restrict__ partials, int64_t ntiles, int Dp, int D,
                                        const double* __restrict__ ell, int ell_is_scalar,
                                        const double* __restrict__ variance, double scale,
-                                       double* g_ell, double* g_var) {
+                                       double* g_ell, double* g_var, int shape_mode) {
     __shared__ double red[32];
     __shared__ double iso;
     if (threadIdx.x == 0) iso = 0.0;
-    for (int d = 0; d <= D; ++d) {
-        int col = (d == D) ? Dp : d;
+    for (int d = 0; d <= D + (shape_mode ? 1 : 0); ++d) {
+        int col = (d >= D) ? Dp + (d - D) : d;
         double s = 0.0;
-        for (int64_t t = threadIdx.x; t < ntiles; t += blockDim.x) s += partials[t * (Dp + 1) + col];
+        for (int64_t t = threadIdx.x; t < ntiles; t += blockDim.x) s += partials[t * (Dp + 2) + col];
         s = block_sum(s, red);
         if (threadIdx.x == 0) {
-            if (d == D) {
+            if (d == D + 1) {
+                if (g_var) g_var[1] += scale * (shape_mode == 2 ? -2.0 / variance[1] : 1.0) * s;
+            } else if (d == D) {
                 if (g_var) g_var[0] += scale * s / variance[0];
             } else if (g_ell) {
                 double l = ell[ell_is_scalar ? 0 : d];
@@ -327,7 +377,7 @@ struct MllBwdParams {
     const double* Sdiag;
     const double* ell; int ell_is_scalar;
     const double* variance;
-    double* partials;  // [ntiles][Dp + 2]  (.., sum W*K, tr W)
+    double* partials;  // [ntiles][Dp + 3]  (.., sum W*K, tr W, shape-parameter term)
     int64_t tiles_c;
 };
 
@@ -339,22 +389,28 @@ __global__ void __launch_bounds__(GT, 2) mll_bwd_kernel(const MllBwdParams p) {
     double* Zs = Xs + TR * Dp;
     double* ell_acc = Zs + Dp * TC;
     double* red = ell_acc + Dp;
+    double* ell_s = red + 32;  // [Dp] (periodic only)
+    constexpr bool PER = (KIND == KIND_PERIODIC);
+    constexpr bool SHP = (KIND == KIND_RATQUAD || KIND == KIND_POWEXP || KIND == KIND_PERIODIC);
     const int64_t tr = blockIdx.x / p.tiles_c, tc = blockIdx.x % p.tiles_c;
     const int64_t r0 = tr * TR, c0 = tc * TC;
-    double* out = p.partials + (int64_t)blockIdx.x * (Dp + 2);
+    double* out = p.partials + (int64_t)blockIdx.x * (Dp + 3);
     const int64_t br = r0 / p.nb, bc = c0 / p.nb;  // tiles never straddle nb-blocks (nb % 128 == 0)
     if (br > bc) {
-        for (int i = threadIdx.x; i < Dp + 2; i += GT) out[i] = 0.0;
+        for (int i = threadIdx.x; i < Dp + 3; i += GT) out[i] = 0.0;
         return;
     }
-    load_scaled<true>(Xs, p.X, p.ldx, r0, p.N, TR, p.D, Dp, p.ell, p.ell_is_scalar);
-    load_scaled<false>(Zs, p.X, p.ldx, c0, p.N, TC, p.D, Dp, p.ell, p.ell_is_scalar);
+    load_scaled<true, PER>(Xs, p.X, p.ldx, r0, p.N, TR, p.D, Dp, p.ell, p.ell_is_scalar);
+    load_scaled<false, PER>(Zs, p.X, p.ldx, c0, p.N, TC, p.D, Dp, p.ell, p.ell_is_scalar);
+    if (PER) load_ell(ell_s, p.ell, p.ell_is_scalar, p.D, Dp);
     for (int i = threadIdx.x; i < Dp; i += GT) ell_acc[i] = 0.0;
     __syncthreads();
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const double var = p.variance[0];
+    const double shp = SHP ? p.variance[1] : 0.0;
+    const double pc = PER ? (3.141592653589793 / shp) : 0.0;
     double r2[RPT][2];
-    tile_r2<DC>(Xs, Zs, Dp, tx, ty, r2);
-    const double var = *p.variance;
+    tile_r2<DC, PER>(Xs, Zs, Dp, tx, ty, r2, ell_s, pc);
     const int64_t c = c0 + 2 * tx;
     const bool diag_blk = (br == bc);
     const double wgt = diag_blk ? 1.0 : 2.0;  // strictly-upper blocks stand for their mirror image too
@@ -362,7 +418,7 @@ __global__ void __launch_bounds__(GT, 2) mll_bwd_kernel(const MllBwdParams p) {
     const int64_t sld = diag_blk ? p.nb : p.lds;
     const int64_t roff = diag_blk ? br * p.nb : 0;
     double ac0 = (c < p.N) ? p.alpha[c] : 0.0, ac1 = (c + 1 < p.N) ? p.alpha[c + 1] : 0.0;
-    double wk = 0.0, trw = 0.0;
+    double wk = 0.0, trw = 0.0, wshp = 0.0;
 #pragma unroll
     for (int i = 0; i < RPT; ++i) {
         int64_t r = r0 + ty + 4 * i;
@@ -376,16 +432,18 @@ __global__ void __launch_bounds__(GT, 2) mll_bwd_kernel(const MllBwdParams p) {
                 if (r == c + j) trw += w;
                 w *= wgt;
             }
-            double k, dk;
-            kprofile_grad<KIND>(r2[i][j], var, k, dk);
+            double k, dk, ds;
+            kprofile_grad<KIND>(r2[i][j], var, shp, k, dk, ds);
             wk = fma(w, k, wk);
+            if (SHP && !PER) wshp = fma(w, ds, wshp);
             r2[i][j] = w * dk;
         }
     }
-    contract_dims<DC, false, false>(Xs, Zs, Dp, tx, ty, r2, ell_acc, nullptr, nullptr);
+    contract_dims<DC, false, false, PER>(Xs, Zs, Dp, tx, ty, r2, ell_acc, nullptr, nullptr, ell_s, pc, &wshp);
     double s1 = block_sum(wk, red);
     double s2 = block_sum(trw, red);
-    if (threadIdx.x == 0) { out[Dp] = s1; out[Dp + 1] = s2; }
+    double s3 = SHP ? block_sum(wshp, red) : 0.0;
+    if (threadIdx.x == 0) { out[Dp] = s1; out[Dp + 1] = s2; out[Dp + 2] = s3; }
     for (int i = threadIdx.x; i < Dp; i += GT) out[i] = ell_acc[i];
 }
 
@@ -393,15 +451,15 @@ __global__ void mll_bwd_reduce_kernel(const double* __restrict__ partials, int64
                                       const double* __restrict__ ell, int ell_is_scalar,
                                       const double* __restrict__ variance, const double* __restrict__ obs_stddev,
                                       const double* __restrict__ gout, const double* __restrict__ alpha, int64_t N,
-                                      double* g_ell, double* g_var, double* g_obs, double* g_mean) {
+                                      double* g_ell, double* g_var, double* g_obs, double* g_mean, int shape_mode) {
     __shared__ double red[32];
     __shared__ double iso;
     if (threadIdx.x == 0) iso = 0.0;
     const double g = gout ? gout[0] : 1.0;
-    for (int d = 0; d < D + 2; ++d) {
+    for (int d = 0; d < D + 2 + (shape_mode ? 1 : 0); ++d) {
         int col = (d < D) ? d : (Dp + (d - D));
         double s = 0.0;
-        for (int64_t t = threadIdx.x; t < ntiles; t += blockDim.x) s += partials[t * (Dp + 2) + col];
+        for (int64_t t = threadIdx.x; t < ntiles; t += blockDim.x) s += partials[t * (Dp + 3) + col];
         s = block_sum(s, red);
         if (threadIdx.x == 0) {
             if (d < D) {
@@ -412,8 +470,10 @@ __global__ void mll_bwd_reduce_kernel(const double* __restrict__ partials, int64
                 }
             } else if (d == D) {
                 if (g_var) g_var[0] = g * s / variance[0];
-            } else {
+            } else if (d == D + 1) {
                 if (g_obs) g_obs[0] = g * 2.0 * obs_stddev[0] * s;
+            } else {
+                if (g_var) g_var[1] = g * (shape_mode == 2 ? -2.0 / variance[1] : 1.0) * s;
             }
         }
     }
@@ -454,19 +514,23 @@ int gram(stream_t s, const GramDesc& d) {
         case KIND_MATERN32: return launch_gram<KIND_MATERN32>(st, p, ntiles);
         case KIND_MATERN52: return launch_gram<KIND_MATERN52>(st, p, ntiles);
         case KIND_MATERN12: return launch_gram<KIND_MATERN12>(st, p, ntiles);
+        case KIND_RATQUAD: return launch_gram<KIND_RATQUAD>(st, p, ntiles);
+        case KIND_POWEXP: return launch_gram<KIND_POWEXP>(st, p, ntiles);
+        case KIND_PERIODIC: return launch_gram<KIND_PERIODIC>(st, p, ntiles);
+        case KIND_WHITE: return launch_gram<KIND_WHITE>(st, p, ntiles);
         default: return GPB_ERR_INVALID;
     }
 }
 
 int64_t gram_bwd_partials_count(int64_t N, int64_t M, int D) {
     int Dp = pad_dim(D, pick_dc(D));
-    return ((N + TR - 1) / TR) * ((M + TC - 1) / TC) * (Dp + 1);
+    return ((N + TR - 1) / TR) * ((M + TC - 1) / TC) * (Dp + 2);
 }
 
 template <int KIND, int DCV, bool WX, bool WZ>
 static int launch_gram_bwd_one(cudaStream_t st, const GramBwdParams& p, int64_t ntiles) {
     int Dp = pad_dim(p.D, DCV);
-    size_t smem = sizeof(double) * ((size_t)(TR + TC) * Dp + (WX ? TR * Dp : 0) + (WZ ? TC * Dp : 0) + Dp + 32);
+    size_t smem = sizeof(double) * ((size_t)(TR + TC) * Dp + (WX ? TR * Dp : 0) + (WZ ? TC * Dp : 0) + 2 * Dp + 32);
     auto kern = gram_bwd_kernel<KIND, DCV, WX, WZ>;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -513,12 +577,17 @@ int gram_bwd(stream_t s, const GramBwdDesc& d) {
         case KIND_MATERN32: rc = launch_gram_bwd<KIND_MATERN32>(st, p, ntiles); break;
         case KIND_MATERN52: rc = launch_gram_bwd<KIND_MATERN52>(st, p, ntiles); break;
         case KIND_MATERN12: rc = launch_gram_bwd<KIND_MATERN12>(st, p, ntiles); break;
+        case KIND_RATQUAD: rc = launch_gram_bwd<KIND_RATQUAD>(st, p, ntiles); break;
+        case KIND_POWEXP: rc = launch_gram_bwd<KIND_POWEXP>(st, p, ntiles); break;
+        case KIND_PERIODIC: rc = launch_gram_bwd<KIND_PERIODIC>(st, p, ntiles); break;
+        case KIND_WHITE: rc = launch_gram_bwd<KIND_WHITE>(st, p, ntiles); break;
         default: return GPB_ERR_INVALID;
     }
     if (rc != GPB_OK) return rc;
     int Dp = pad_dim(d.D, pick_dc(d.D));
     gram_bwd_reduce_kernel<<<1, 1024, 0, st>>>(d.partials, ntiles, Dp, d.D, d.ell, d.ell_is_scalar, d.variance,
-                                               d.scale, d.g_ell, d.g_var);
+                                               d.scale, d.g_ell, d.g_var,
+                                               kind_has_shape(d.kind) ? (d.kind == KIND_PERIODIC ? 2 : 1) : 0);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
 }
@@ -526,14 +595,14 @@ int gram_bwd(stream_t s, const GramBwdDesc& d) {
 int64_t mll_bwd_partials_count(int64_t N, int D, int64_t nb) {
     (void)nb;
     int Dp = pad_dim(D, pick_dc(D));
-    return ((N + TR - 1) / TR) * ((N + TC - 1) / TC) * (Dp + 2);
+    return ((N + TR - 1) / TR) * ((N + TC - 1) / TC) * (Dp + 3);
 }
 
 template <int KIND>
 static int launch_mll_bwd(cudaStream_t st, const MllBwdParams& p, int64_t ntiles) {
     int DC = pick_dc(p.D);
     int Dp = pad_dim(p.D, DC);
-    size_t smem = sizeof(double) * ((size_t)(TR + TC) * Dp + Dp + 32);
+    size_t smem = sizeof(double) * ((size_t)(TR + TC) * Dp + 2 * Dp + 32);
     dim3 grid((unsigned)ntiles);
 #define GPB_MLL_LAUNCH(DCV)                                                                          \
     {                                                                                                \
@@ -569,13 +638,18 @@ int mll_bwd(stream_t s, const MllBwdDesc& d) {
         case KIND_MATERN32: rc = launch_mll_bwd<KIND_MATERN32>(st, p, ntiles); break;
         case KIND_MATERN52: rc = launch_mll_bwd<KIND_MATERN52>(st, p, ntiles); break;
         case KIND_MATERN12: rc = launch_mll_bwd<KIND_MATERN12>(st, p, ntiles); break;
+        case KIND_RATQUAD: rc = launch_mll_bwd<KIND_RATQUAD>(st, p, ntiles); break;
+        case KIND_POWEXP: rc = launch_mll_bwd<KIND_POWEXP>(st, p, ntiles); break;
+        case KIND_PERIODIC: rc = launch_mll_bwd<KIND_PERIODIC>(st, p, ntiles); break;
+        case KIND_WHITE: rc = launch_mll_bwd<KIND_WHITE>(st, p, ntiles); break;
         default: return GPB_ERR_INVALID;
     }
     if (rc != GPB_OK) return rc;
     int Dp = pad_dim(d.D, pick_dc(d.D));
     mll_bwd_reduce_kernel<<<1, 1024, 0, st>>>(d.partials, ntiles, Dp, d.D, d.ell, d.ell_is_scalar, d.variance,
                                               d.obs_stddev, d.gout, d.alpha, d.N, d.g_ell, d.g_var,
-                                              d.g_obs_stddev, d.g_mean);
+                                              d.g_obs_stddev, d.g_mean,
+                                              kind_has_shape(d.kind) ? (d.kind == KIND_PERIODIC ? 2 : 1) : 0);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
 }

@@ -13,7 +13,17 @@ namespace gpb {
 
 typedef void* stream_t;
 
-enum KernelKind { KIND_RBF = 0, KIND_MATERN32 = 1, KIND_MATERN52 = 2, KIND_MATERN12 = 3 };
+enum KernelKind {
+    KIND_RBF = 0, KIND_MATERN32 = 1, KIND_MATERN52 = 2, KIND_MATERN12 = 3,
+    KIND_RATQUAD = 4,   // shape parameter: alpha
+    KIND_POWEXP = 5,    // shape parameter: power
+    KIND_PERIODIC = 6,  // shape parameter: period
+    KIND_WHITE = 7
+};
+// Kinds 4..6 carry one extra scalar.  Convention on every entry point: `variance` then points to TWO
+// consecutive device doubles {variance, shape} and the variance gradient output likewise to {g_variance, g_shape}.
+inline bool kind_has_shape(int kind) { return kind == KIND_RATQUAD || kind == KIND_POWEXP || kind == KIND_PERIODIC; }
+inline bool kind_valid(int kind) { return kind >= KIND_RBF && kind <= KIND_WHITE; }
 
 // error codes (identical to include/gpjax_b200.h)
 #ifndef GPB_OK

@@ -82,6 +82,11 @@ static int check_args(const SgprArgs& a) {
     if (a.Nloc < 0 || a.M <= 0 || a.D <= 0 || a.block_rows <= 0) return GPB_ERR_INVALID;
     if (!a.Z || !a.ell || !a.variance || !a.obs_stddev) return GPB_ERR_INVALID;
     if (a.Nloc > 0 && (!a.X || !a.y)) return GPB_ERR_INVALID;
+    if (!kind_valid(a.kind)) return GPB_ERR_INVALID;
+    // The sparse objectives use k(x, x) = variance for the trace term (objectives.py:356).  Under the reference's
+    // 1e-36 distance clamp PoweredExponential gives variance * exp(-(1e-18)^power) instead, which differs from
+    // variance for small powers -- not carried through the statistics here.
+    if (a.kind == KIND_POWEXP) return GPB_ERR_UNSUPPORTED;
     return GPB_OK;
 }
 
@@ -212,7 +217,7 @@ int sgpr_grad_local(stream_t s, const SgprArgs& a, const SgprWs& ws, double* g_Z
     const int64_t M = a.M, ld = M + 2;
     GPB_TRY(fill2d(s, M, a.D, g_Z, a.D, 0.0));
     GPB_TRY(fill2d(s, 1, a.ell_is_scalar ? 1 : a.D, g_ell, a.D, 0.0));
-    GPB_TRY(fill2d(s, 1, 1, g_var, 1, 0.0));
+    GPB_TRY(fill2d(s, 1, kind_has_shape(a.kind) ? 2 : 1, g_var, 2, 0.0));
     for (int64_t r0 = 0; r0 < a.Nloc; r0 += a.block_rows) {
         const int64_t rows = (a.Nloc - r0) < a.block_rows ? (a.Nloc - r0) : a.block_rows;
         GPB_TRY(gram(s, gram_desc(a, a.X + r0 * a.ldx, a.ldx, rows, ws.T1, ld)));
@@ -250,7 +255,7 @@ int sgpr_grad_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const doub
     if (gout) {
         GPB_TRY(scale_inplace(s, M * a.D, g_Z, gout));
         GPB_TRY(scale_inplace(s, a.ell_is_scalar ? 1 : a.D, g_ell, gout));
-        GPB_TRY(scale_inplace(s, 1, g_var, gout));
+        GPB_TRY(scale_inplace(s, kind_has_shape(a.kind) ? 2 : 1, g_var, gout));
         if (g_obs) GPB_TRY(scale_inplace(s, 1, g_obs, gout));
         if (g_mean) GPB_TRY(scale_inplace(s, 1, g_mean, gout));
     }
@@ -346,7 +351,7 @@ int svgp_grad_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const doub
     if (gout) {
         GPB_TRY(scale_inplace(s, M * a.D, g_Z, gout));
         GPB_TRY(scale_inplace(s, a.ell_is_scalar ? 1 : a.D, g_ell, gout));
-        GPB_TRY(scale_inplace(s, 1, g_var, gout));
+        GPB_TRY(scale_inplace(s, kind_has_shape(a.kind) ? 2 : 1, g_var, gout));
         if (g_obs) GPB_TRY(scale_inplace(s, 1, g_obs, gout));
         if (g_mean) GPB_TRY(scale_inplace(s, 1, g_mean, gout));
         if (g_mu) GPB_TRY(scale_inplace(s, M, g_mu, gout));

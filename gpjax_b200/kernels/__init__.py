@@ -1,6 +1,8 @@
-from .base import AbstractKernel
-from .computations import AbstractKernelComputation, DenseKernelComputation
-from .stationary import RBF, Matern12, Matern32, Matern52, StationaryKernel
+from .base import AbstractKernel, CombinationKernel, Constant, ProductKernel, SumKernel
+from .computations import AbstractKernelComputation, ConstantDiagonalKernelComputation, DenseKernelComputation
+from .stationary import (RBF, Matern12, Matern32, Matern52, Periodic, PoweredExponential, RationalQuadratic,
+                         StationaryKernel, White)
 
-__all__ = ["AbstractKernel", "StationaryKernel", "RBF", "Matern12", "Matern32", "Matern52", "AbstractKernelComputation",
-           "DenseKernelComputation"]
+__all__ = ["AbstractKernel", "StationaryKernel", "RBF", "Matern12", "Matern32", "Matern52", "RationalQuadratic",
+           "PoweredExponential", "Periodic", "White", "Constant", "CombinationKernel", "SumKernel", "ProductKernel",
+           "AbstractKernelComputation", "DenseKernelComputation", "ConstantDiagonalKernelComputation"]

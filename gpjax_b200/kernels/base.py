@@ -59,3 +59,58 @@ class AbstractKernel(Module):
 
     def slice_input(self, x: torch.Tensor) -> torch.Tensor:
         return x[..., self.active_dims] if self.active_dims is not None else x
+
+
+    # ---- kernel algebra (kernels/base.py:150-205) ------------------------------------------------------------
+    def __add__(self, other):
+        return SumKernel(kernels=[self, other if isinstance(other, AbstractKernel) else Constant(constant=other)])
+
+    def __radd__(self, other):
+        return self.__add__(other)
+
+    def __mul__(self, other):
+        return ProductKernel(kernels=[self, other if isinstance(other, AbstractKernel) else Constant(constant=other)])
+
+
+class Constant(AbstractKernel):
+    """k(x, y) = constant  (kernels/base.py:223-243)."""
+
+    name = "Constant"
+    _is_constant_kernel = True
+
+    def __init__(self, active_dims=None, constant=0.0, compute_engine: AbstractKernelComputation = None):
+        from ..parameters import Parameter, Real
+
+        self.constant = constant if isinstance(constant, Parameter) else Real(constant)
+        super().__init__(active_dims=active_dims, compute_engine=compute_engine)
+
+
+class CombinationKernel(AbstractKernel):
+    """Sum or product of kernels, nested instances of the same combination flattened (kernels/base.py:246-310)."""
+
+    name = "Combination"
+
+    def __init__(self, kernels, operator: str, compute_engine: AbstractKernelComputation = None):
+        if operator not in ("sum", "prod"):
+            raise ValueError("operator must be 'sum' or 'prod'")
+        flat = []
+        for kernel in kernels:
+            if not isinstance(kernel, AbstractKernel):
+                raise TypeError("can only combine Kernel instances")
+            if isinstance(kernel, CombinationKernel) and kernel.operator_name == operator:
+                flat.extend(kernel.kernels)
+            else:
+                flat.append(kernel)
+        self.kernels = flat
+        self.operator_name = operator
+        super().__init__(compute_engine=compute_engine)
+
+
+def SumKernel(kernels, compute_engine: AbstractKernelComputation = None) -> CombinationKernel:
+    """kernels/base.py:338."""
+    return CombinationKernel(kernels, "sum", compute_engine)
+
+
+def ProductKernel(kernels, compute_engine: AbstractKernelComputation = None) -> CombinationKernel:
+    """kernels/base.py:339."""
+    return CombinationKernel(kernels, "prod", compute_engine)

@@ -28,8 +28,35 @@ def _mean_constant(mean_function):
 
 
 def _kernel_args(kernel):
-    kind = kernel.compute_engine._kind(kernel)
-    return kind, kernel.lengthscale.value, kernel.variance.value
+    """(kind, lengthscale, [variance(, shape)]) of a kernel with a fused epilogue."""
+    if getattr(kernel, "_b200_kind", None) is None:
+        raise NotImplementedError(
+            f"{type(kernel).__name__}: the fused sparse objectives take a single stationary kernel with a fused "
+            "sm_100a epilogue (sum / product kernels are supported by conjugate_mll and conjugate_loocv only)"
+        )
+    return kernel._b200_kind, kernel.lengthscale.value, kernel.kernel_scalars()
+
+
+def _is_fused(kernel) -> bool:
+    return getattr(kernel, "_b200_kind", None) is not None
+
+
+def _dense_sigma(posterior, data: Dataset):
+    """(Sigma, y - m(x)) with Sigma = Kxx + (jitter + obs_stddev^2) I assembled from differentiable Gram launches
+    (objectives.py:96-103) -- the composable route for sum / product kernels."""
+    x, y = data.X, data.y
+    if y.shape[-1] != 1 and y.dim() > 1:
+        raise ValueError("single-output objectives: y must have shape [N, 1]")
+    prior = posterior.prior
+    K = prior.kernel.gram(x).to_dense()
+    Sigma = K.clone() if K.requires_grad or not K.is_contiguous() else K
+    sn = posterior.likelihood.obs_stddev.value.reshape(()).to(Sigma.device)
+    torch.diagonal(Sigma).add_(sn * sn + float(prior.jitter))
+    mean = _mean_constant(prior.mean_function)
+    d = y.reshape(-1).to(Sigma.device)
+    if mean is not None:
+        d = d - mean.reshape(()).to(Sigma.device)
+    return Sigma, d
 
 
 def conjugate_mll(posterior, data: Dataset) -> torch.Tensor:
@@ -37,6 +64,9 @@ def conjugate_mll(posterior, data: Dataset) -> torch.Tensor:
     (objectives.py:96-103), value through the fused Gram -> Cholesky -> solve/logdet pipeline."""
     x, y = data.X, data.y
     kernel = posterior.prior.kernel
+    if not _is_fused(kernel):  # combination kernels: dense Sigma from the parts' Gram launches
+        Sigma, d = _dense_sigma(posterior, data)
+        return ops.GaussianLogProbFunction.apply(Sigma, d)
     kind, ell, var = _kernel_args(kernel)
     xs = kernel.slice_input(x)
     xs = xs if xs.is_contiguous() else xs.contiguous()
@@ -45,6 +75,14 @@ def conjugate_mll(posterior, data: Dataset) -> torch.Tensor:
         mean = mean.to(xs.device)
     return ops.conjugate_mll_fused(kind, xs, y, ell, var, posterior.likelihood.obs_stddev.value, mean,
                                    float(posterior.prior.jitter))
+
+
+def conjugate_loocv(posterior, data: Dataset) -> torch.Tensor:
+    """Leave-one-out log predictive probability of a conjugate GP (objectives.py:110-178): with P = Sigma^-1 and
+    alpha = P (y - m), sum_i log N(y_i; y_i - alpha_i / P_ii, 1 / P_ii).  Sigma^-1 comes from the blocked
+    POTRF + TRTRI + LAUUM (the reference calls jnp.linalg.inv, objectives.py:171)."""
+    Sigma, d = _dense_sigma(posterior, data)
+    return ops.LoocvFunction.apply(Sigma, d)
 
 
 def collapsed_elbo(variational_family, data: Dataset, *, block_rows: int = sgpr_ops.DEFAULT_BLOCK_ROWS,
@@ -91,4 +129,4 @@ def elbo(variational_family, data: Dataset, *, block_rows: int = sgpr_ops.DEFAUL
                                     float(post.likelihood.num_datapoints), float(q.jitter), block_rows, group)
 
 
-__all__ = ["conjugate_mll", "collapsed_elbo", "elbo"]
+__all__ = ["conjugate_mll", "conjugate_loocv", "collapsed_elbo", "elbo"]

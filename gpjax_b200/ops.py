@@ -16,7 +16,9 @@ import torch
 from . import _abi
 from ._lib import lib, require_cuda
 
-KIND_IDS = {"RBF": 0, "Matern32": 1, "Matern52": 2, "Matern12": 3, "Matérn32": 1, "Matérn52": 2, "Matérn12": 3}
+KIND_IDS = {"RBF": 0, "Matern32": 1, "Matern52": 2, "Matern12": 3, "Matérn32": 1, "Matérn52": 2, "Matérn12": 3,
+            "RationalQuadratic": 4, "PoweredExponential": 5, "Periodic": 6, "White": 7}
+SHAPE_KINDS = (4, 5, 6)  # kinds whose `variance` argument is the pair [variance, shape] (include/gpjax_b200.h)
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -49,6 +51,16 @@ def _scalar(t: torch.Tensor, name: str) -> torch.Tensor:
     return t.reshape(1)
 
 
+def _kscalars(kind: int, t: torch.Tensor) -> torch.Tensor:
+    """The kernel scalars as the C ABI wants them: [variance], or [variance, shape] for kinds 4..6."""
+    require_cuda(t)
+    want = 2 if kind in SHAPE_KINDS else 1
+    if t.numel() != want:
+        raise ValueError(f"kernel kind {kind} takes {want} scalar(s) (variance{', shape' if want == 2 else ''}); "
+                         f"got {t.numel()}")
+    return t.reshape(want).contiguous()
+
+
 # ------------------------------------------------------------------------------------------
 # K1: Gram / cross-covariance
 # ------------------------------------------------------------------------------------------
@@ -60,7 +72,7 @@ def gram_forward(kind: int, X, Z, ell, variance, diag_add=0.0, diag_add_sq=None,
     if Z.shape[1] != D:
         raise ValueError("X and Z must have the same number of columns")
     ell_v, iso = _ell_args(ell, D)
-    var = _scalar(variance, "variance")
+    var = _kscalars(kind, variance)
     if out is None:
         out = torch.empty((N, M), dtype=torch.float64, device=X.device)
     _check_mat(out, "out")
@@ -78,7 +90,7 @@ def gram_backward(kind: int, X, Z, ell, variance, dK, want_X=False, want_Z=False
     N, D = X.shape
     M = Z.shape[0]
     ell_v, iso = _ell_args(ell, D)
-    var = _scalar(variance, "variance")
+    var = _kscalars(kind, variance)
     dev = X.device
     accum = accum or {}
     g_ell = accum.get("ell")
@@ -86,7 +98,7 @@ def gram_backward(kind: int, X, Z, ell, variance, dK, want_X=False, want_Z=False
         g_ell = torch.zeros(1 if iso else D, dtype=torch.float64, device=dev)
     g_var = accum.get("var")
     if g_var is None:
-        g_var = torch.zeros(1, dtype=torch.float64, device=dev)
+        g_var = torch.zeros(var.numel(), dtype=torch.float64, device=dev)
     g_X = accum.get("X")
     if g_X is None and want_X:
         g_X = torch.zeros((N, D), dtype=torch.float64, device=dev)
@@ -267,7 +279,7 @@ class ConjugateMllFunction(torch.autograd.Function):
         if y.numel() != N:
             raise ValueError("conjugate_mll supports a single output column (y of shape [N, 1])")
         ell_v, iso = _ell_args(ell, D)
-        var = _scalar(variance, "variance")
+        var = _kscalars(kind, variance)
         sn = _scalar(obs_stddev, "obs_stddev")
         mean = None if mean_const is None else _scalar(mean_const, "mean constant")
         st = _mll_state(N, D, X.device)
@@ -289,7 +301,7 @@ class ConjugateMllFunction(torch.autograd.Function):
                                            mean if ctx.has_mean else None, ctx.jitter)
         dev = X.device
         g_ell = torch.empty(1 if ctx.iso else D, dtype=torch.float64, device=dev)
-        g_var = torch.empty(1, dtype=torch.float64, device=dev)
+        g_var = torch.empty(var.numel(), dtype=torch.float64, device=dev)
         g_sn = torch.empty(1, dtype=torch.float64, device=dev)
         g_mean = torch.empty(1, dtype=torch.float64, device=dev) if ctx.has_mean else None
         g = gout.reshape(1).contiguous()
@@ -307,3 +319,94 @@ def conjugate_mll_fused(kind, X, y, ell, variance, obs_stddev, mean_const=None, 
 
 
 LOG_2PI = math.log(2.0 * math.pi)
+
+
+# ------------------------------------------------------------------------------------------
+# Dense-covariance objectives: the composable route for kernels without a fused objective
+# (sum / product kernels).  Sigma arrives as a tensor built by differentiable Gram launches; the
+# factorisation, solves and the N^3 part of the backward run on the same CUDA path as the fused one.
+# ------------------------------------------------------------------------------------------
+def _factor_for_backward(Sigma: torch.Tensor):
+    n = Sigma.shape[0]
+    L = Sigma.detach().clone().contiguous()
+    ws = FactorWorkspace(n, 1, potri=True, device=Sigma.device)
+    info = potrf_lower_(L, ws, zero_upper=False)
+    return L, ws, info
+
+
+class GaussianLogProbFunction(torch.autograd.Function):
+    """log N(y; mu, Sigma) as a function of (Sigma, diff = y - mu)  -- gpjax/distributions.py:115-134.
+    Backward: dSigma = 1/2 (alpha alpha^T - Sigma^-1), ddiff = -alpha, with Sigma^-1 from TRTRI + LAUUM."""
+
+    @staticmethod
+    def forward(ctx, Sigma, diff):
+        _check_mat(Sigma, "Sigma")
+        n = Sigma.shape[0]
+        d = diff.detach().reshape(-1).contiguous()
+        if d.numel() != n or Sigma.shape[1] != n:
+            raise ValueError("Sigma must be [n, n] and diff [n]")
+        L, ws, info = _factor_for_backward(Sigma)
+        w = trsv_lower_(L, d.clone(), ws, trans=False)
+        quad = gemm(w.reshape(1, -1), w.reshape(1, -1)).reshape(())
+        alpha = trsv_lower_(L, w, ws, trans=True)  # w is overwritten: alpha = Sigma^-1 diff
+        val = -0.5 * (n * LOG_2PI + 2.0 * sum_log_diag(L) + quad)
+        ctx.state = (L, ws)
+        ctx.diff_shape = diff.shape
+        ctx.save_for_backward(alpha)
+        return val
+
+    @staticmethod
+    def backward(ctx, gout):
+        (alpha,) = ctx.saved_tensors
+        L, ws = ctx.state
+        g_sigma = g_diff = None
+        if ctx.needs_input_grad[0]:
+            P = potri_lower(L, ws)
+            a = alpha.reshape(-1, 1)
+            gemm(a, a, C=P, alpha=0.5, beta=-0.5)  # P <- 1/2 (alpha alpha^T - Sigma^-1)
+            g_sigma = P.mul_(gout)
+        if ctx.needs_input_grad[1]:
+            g_diff = (-gout * alpha).reshape(ctx.diff_shape)
+        return g_sigma, g_diff
+
+
+class LoocvFunction(torch.autograd.Function):
+    """Leave-one-out log predictive probability (gpjax/objectives.py:161-178) as a function of (Sigma, diff):
+    with P = Sigma^-1, alpha = P diff:  sum_i [ -1/2 log 2pi + 1/2 log P_ii - 1/2 alpha_i^2 / P_ii ].
+    Backward: dSigma = -P R P + sym((P s) alpha^T), R = diag(1/(2 P_ii) + alpha_i^2/(2 P_ii^2)), s = alpha / diag(P);
+    ddiff = -P s.  The N^3 term P R P = (P R^1/2)(P R^1/2)^T is one DMMA product."""
+
+    @staticmethod
+    def forward(ctx, Sigma, diff):
+        _check_mat(Sigma, "Sigma")
+        n = Sigma.shape[0]
+        d = diff.detach().reshape(-1).contiguous()
+        if d.numel() != n or Sigma.shape[1] != n:
+            raise ValueError("Sigma must be [n, n] and diff [n]")
+        L, ws, info = _factor_for_backward(Sigma)
+        alpha = trsv_lower_(L, trsv_lower_(L, d.clone(), ws, trans=False), ws, trans=True)
+        P = potri_lower(L, ws)
+        pd = torch.diagonal(P)
+        val = torch.sum(-0.5 * LOG_2PI + 0.5 * torch.log(pd) - 0.5 * alpha * alpha / pd)
+        ctx.diff_shape = diff.shape
+        ctx.save_for_backward(P, alpha)
+        return val
+
+    @staticmethod
+    def backward(ctx, gout):
+        P, alpha = ctx.saved_tensors
+        pd = torch.diagonal(P)
+        s = (alpha / pd).contiguous()
+        Ps = gemm(P, s.reshape(1, -1)).reshape(-1)  # P s (P symmetric)
+        g_sigma = g_diff = None
+        if ctx.needs_input_grad[0]:
+            r = 0.5 / pd + 0.5 * alpha * alpha / (pd * pd)
+            A = P * torch.sqrt(r)[None, :]
+            G = gemm(A, A, alpha=-1.0)  # -P R P
+            u, a = Ps.reshape(-1, 1), alpha.reshape(-1, 1)
+            gemm(u, a, C=G, alpha=0.5, beta=1.0)
+            gemm(a, u, C=G, alpha=0.5, beta=1.0)
+            g_sigma = G.mul_(gout)
+        if ctx.needs_input_grad[1]:
+            g_diff = (-gout * Ps).reshape(ctx.diff_shape)
+        return g_sigma, g_diff

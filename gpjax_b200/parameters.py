@@ -80,6 +80,15 @@ class Real(Parameter):
         super().__init__(value, tag, device)
 
 
+class SigmoidBounded(Parameter):
+    """Parameter bounded between 0 and 1 (gpjax/parameters.py:106-122)."""
+
+    def __init__(self, value, tag: str = "sigmoid", device=None):
+        super().__init__(value, tag, device)
+        if not bool(((self.value >= 0) & (self.value <= 1)).all()):
+            raise ValueError(f"value needs to be bounded between 0.0 and 1.0, got {self.value}")
+
+
 class LowerTriangular(Parameter):
     """Lower-triangular matrix parameter (gpjax/parameters.py:125-137): square and zero above the diagonal."""
 
@@ -117,6 +126,14 @@ class IdentityTransform(Bijection):
         return y
 
 
+class SigmoidTransform(Bijection):
+    def __call__(self, u):
+        return torch.sigmoid(u)
+
+    def inv(self, y):
+        return torch.log(y) - torch.log1p(-y)
+
+
 class FillTriangularTransform(Bijection):
     """Vector of n(n+1)/2 entries <-> lower-triangular n x n matrix (gpjax/numpyro_extras.py:12-106);
     row-major order of the lower triangle."""
@@ -141,6 +158,7 @@ DEFAULT_BIJECTION: tp.Dict[str, Bijection] = {
     "positive": SoftplusTransform(),
     "non_negative": SoftplusTransform(),
     "real": IdentityTransform(),
+    "sigmoid": SigmoidTransform(),
     "lower_triangular": FillTriangularTransform(),
 }
 

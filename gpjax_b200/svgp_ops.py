@@ -8,7 +8,7 @@ import torch
 
 from . import _abi
 from ._lib import lib
-from .ops import _check_mat, _ell_args, _p, _scalar, _stream, require_cuda
+from .ops import _check_mat, _ell_args, _kscalars, _p, _scalar, _stream, require_cuda
 from .sgpr_ops import DEFAULT_BLOCK_ROWS, _all_reduce, _state
 
 
@@ -50,7 +50,7 @@ class SvgpElboFunction(torch.autograd.Function):
             raise ValueError("variational parameters do not match the number of inducing points")
         W = var_sqrt.contiguous()
         ell_v, iso = _ell_args(ell, D)
-        var = _scalar(variance, "variance")
+        var = _kscalars(kind, variance)
         sn = _scalar(obs_stddev, "obs_stddev")
         mean = None if mean_const is None else _scalar(mean_const, "mean constant")
         block_rows = int(min(block_rows, max(n_loc, 1)))
@@ -77,7 +77,7 @@ class SvgpElboFunction(torch.autograd.Function):
                          block_rows, group, True)
         L = lib()
         nl = 1 if iso else D
-        flat = torch.empty(M * D + nl + 1, dtype=torch.float64, device=Z.device)
+        flat = torch.empty(M * D + nl + var.numel(), dtype=torch.float64, device=Z.device)
         g_Z, g_ell, g_var = flat[: M * D], flat[M * D: M * D + nl], flat[M * D + nl:]
         rc = L.gpb_sgpr_grad_local(_stream(), kind, n_loc, M, D, _p(X), X.stride(0) if n_loc else D, _p(y), _p(Z),
                                    Z.stride(0), _p(ell_v), iso, _p(var), _p(sn), _p(mean if has_mean else None),

@@ -34,6 +34,7 @@ class CollapsedVariationalGaussian(AbstractVariationalGaussian):
         if not isinstance(posterior.likelihood, Gaussian):
             raise TypeError("Likelihood must be Gaussian.")
 
+    @torch.no_grad()  # forward-only: the predictive moments are not part of the training graph
     def predict(self, test_inputs, train_data, *, block_rows: int = 32768, group=None):
         """Predictive Gaussian of the collapsed bound (variational_families.py:786-870).  The training data
         enter through the streamed, row-additive statistics of the ELBO path (all-reduced over `group`
@@ -58,7 +59,7 @@ class CollapsedVariationalGaussian(AbstractVariationalGaussian):
         n_loc, D = x.shape
         M, T = z.shape[0], t.shape[0]
         ell_v, iso = _ell_args(kern.lengthscale.value, D)
-        var = _scalar(kern.variance.value, "variance")
+        var = ops._kscalars(kind, kern.kernel_scalars())
         sn = _scalar(post.likelihood.obs_stddev.value, "obs_stddev")
         mean = _mean_constant(post.prior.mean_function)
         mean = None if mean is None else _scalar(mean.to(x.device), "mean constant")
@@ -111,6 +112,7 @@ class VariationalGaussian(AbstractVariationalGaussian):
                                             if isinstance(variational_root_covariance, LowerTriangular)
                                             else LowerTriangular(variational_root_covariance))
 
+    @torch.no_grad()  # forward-only: the predictive moments are not part of the training graph
     def predict(self, test_inputs):
         """N(mu_t + Ktz Kzz^-1 (mu - mu_z), Ktt - Ktz Kzz^-1 Kzt + Ktz Kzz^-1 S Kzz^-1 Kzt + jitter I)
         (variational_families.py:234-285) on the CUDA path: fused Gram tiles, blocked DMMA Cholesky,
@@ -123,7 +125,7 @@ class VariationalGaussian(AbstractVariationalGaussian):
         kind = kern.compute_engine._kind(kern)
         z = kern.slice_input(self.inducing_inputs.value).contiguous()
         t = kern.slice_input(test_inputs).contiguous()
-        ell, var = kern.lengthscale.value, kern.variance.value
+        ell, var = kern.lengthscale.value, kern.kernel_scalars()
         mean_fn = self.posterior.prior.mean_function
         m, T = z.shape[0], t.shape[0]
         Lz = ops.gram_forward(kind, z, z, ell, var, diag_add=self.jitter, lower_only=True)

@@ -41,6 +41,12 @@ extern "C" {
 #define GPB_KIND_MATERN32 1
 #define GPB_KIND_MATERN52 2
 #define GPB_KIND_MATERN12 3
+/* Kinds with one extra "shape" scalar.  For these every `variance` argument points to TWO consecutive device
+ * doubles {variance, shape} and every `g_variance` output to {g_variance, g_shape}. */
+#define GPB_KIND_RATIONAL_QUADRATIC 4 /* shape = alpha   (gpjax/kernels/stationary/rational_quadratic.py:77-83) */
+#define GPB_KIND_POWERED_EXPONENTIAL 5 /* shape = power  (powered_exponential.py:85-89); not for the sparse objectives */
+#define GPB_KIND_PERIODIC 6            /* shape = period  (periodic.py:81-88) */
+#define GPB_KIND_WHITE 7               /* variance * all(x == y)  (white.py:63-64); lengthscale must be 1 */
 
 const char* gpb_version(void);
 int gpb_max_input_dim(void); /* largest D the compiled kernels accept */

@@ -17,7 +17,17 @@ import math
 import numpy as np
 import scipy.linalg as sla
 
-KINDS = {"rbf": 0, "matern32": 1, "matern52": 2, "matern12": 3}
+KINDS = {"rbf": 0, "matern32": 1, "matern52": 2, "matern12": 3,
+         "rational_quadratic": 4, "powered_exponential": 5, "periodic": 6, "white": 7}
+# Kinds 4..6 have one extra scalar (alpha / power / period).  Throughout this module their `variance` argument is
+# the pair (variance, shape) -- the same packing the C ABI uses -- and gradients come back as a pair as well.
+SHAPE_KINDS = (4, 5, 6)
+
+
+def _split_scal(kind: int, variance):
+    if kind in SHAPE_KINDS:
+        return variance[0], variance[1]
+    return variance, None
 KIND_NAMES = {v: k for k, v in KINDS.items()}
 
 __all__ = [
@@ -49,6 +59,9 @@ __all__ = [
     "svgp_elbo_value_and_grad_autodiff",
     "svgp_predict",
     "collapsed_predict",
+    "conjugate_loocv",
+    "conjugate_loocv_value_and_grad_autodiff",
+    "SHAPE_KINDS",
 ]
 
 
@@ -76,9 +89,16 @@ def _profile(kind: int, r2: np.ndarray, variance) -> np.ndarray:
 
     rbf.py:43, matern32.py:46-53 (tau via utils.py:67), matern52.py:45-52.
     """
-    if kind == 0:
+    variance, shape = _split_scal(kind, variance)
+    if kind == 0 or kind == 6:  # periodic.py:88: r2 is then sum_d (sin(pi (x_d - y_d) / p) / l_d)^2
         return variance * np.exp(-0.5 * r2)
+    if kind == 4:  # rational_quadratic.py:80-82
+        return variance * (1.0 + 0.5 * r2 / shape) ** (-shape)
+    if kind == 7:  # white.py:63: all(x == y) * variance  (lengthscale is 1, so r2 == 0 <=> equal)
+        return variance * (np.asarray(r2) == 0.0)
     tau = np.sqrt(np.maximum(r2, 1e-36))
+    if kind == 5:  # powered_exponential.py:88
+        return variance * np.exp(-(tau**shape))
     if kind == 3:  # matern12.py:44-48
         return variance * np.exp(-tau)
     if kind == 1:
@@ -95,6 +115,10 @@ def _profile(kind: int, r2: np.ndarray, variance) -> np.ndarray:
 def kernel_pair(kind, x, y, lengthscale, variance) -> np.floating:
     """Scalar ``kernel(x, y)``: scale both inputs by 1/l first (rbf.py:41-42), then a1."""
     kind = _kind_id(kind)
+    if kind == 6:  # periodic.py:81-88
+        period = variance[1]
+        sine_squared = (np.sin(np.pi * (np.asarray(x, np.float64) - np.asarray(y, np.float64)) / period) / lengthscale) ** 2
+        return variance[0] * np.exp(-0.5 * np.sum(sine_squared, axis=0))
     xs = np.asarray(x, np.float64) / lengthscale
     ys = np.asarray(y, np.float64) / lengthscale
     return _profile(kind, squared_distance(xs, ys), variance)
@@ -115,6 +139,13 @@ def cross_covariance(kind, x, z, lengthscale, variance) -> np.ndarray:
     kind = _kind_id(kind)
     x = np.atleast_2d(np.asarray(x, np.float64))
     z = np.atleast_2d(np.asarray(z, np.float64))
+    if kind == 6:
+        ell = np.broadcast_to(np.asarray(lengthscale, np.float64), (x.shape[1],))
+        r2 = np.zeros((x.shape[0], z.shape[0]), np.float64)
+        for k in range(x.shape[1]):
+            sk = np.sin(np.pi * (x[:, k : k + 1] - z[:, k][None, :]) / variance[1]) / ell[k]
+            r2 += sk * sk
+        return _profile(kind, r2, variance)
     xs = x / lengthscale
     zs = z / lengthscale
     return _profile(kind, _r2_matrix(xs, zs), variance)
@@ -241,10 +272,23 @@ def conjugate_mll_grad_closed_form(
 # ----------------------------------------------------------------------------------------
 # torch-CPU literal restatement, differentiated by autograd (jax.value_and_grad analogue)
 # ----------------------------------------------------------------------------------------
+def _grad_of(t):
+    """numpy gradient of a leaf (zeros when the value does not depend on it, e.g. White's lengthscale)."""
+    g = t.grad if t.grad is not None else t.detach() * 0.0
+    return g.numpy().copy() if g.ndim else float(g)
+
+
 def _t_profile(torch, kind, r2, variance):
-    if kind == 0:
+    variance, shape = _split_scal(kind, variance)
+    if kind == 0 or kind == 6:
         return variance * torch.exp(-0.5 * r2)
+    if kind == 4:
+        return variance * (1.0 + 0.5 * r2 / shape) ** (-shape)
+    if kind == 7:
+        return variance * (r2 == 0.0).to(torch.float64)
     tau = torch.sqrt(torch.clamp_min(r2, 1e-36))
+    if kind == 5:
+        return variance * torch.exp(-(tau**shape))
     if kind == 3:
         return variance * torch.exp(-tau)
     if kind == 1:
@@ -255,6 +299,9 @@ def _t_profile(torch, kind, r2, variance):
 
 
 def _t_cross(torch, kind, x, z, ell, variance):
+    if kind == 6:
+        sine = torch.sin(math.pi * (x[:, None, :] - z[None, :, :]) / variance[1]) / ell
+        return _t_profile(torch, kind, (sine * sine).sum(-1), variance)
     xs = x / ell
     zs = z / ell
     diff = xs[:, None, :] - zs[None, :, :]
@@ -288,8 +335,8 @@ def conjugate_mll_value_and_grad_autodiff(
     val = -0.5 * (n * math.log(2.0 * math.pi) + logdet + quad)
     val.backward()
     g = {
-        "lengthscale": ell.grad.numpy().copy() if ell.grad.ndim else float(ell.grad),
-        "variance": float(var.grad),
+        "lengthscale": _grad_of(ell),
+        "variance": _grad_of(var),
         "obs_stddev": float(sn.grad),
         "mean_const": float(c.grad),
     }
@@ -372,7 +419,7 @@ def _sgpr_finish(Phi, psi, dd, n, variance, noise):
     w = sla.solve_triangular(L, psi, lower=True)
     quad = (dd - w @ w) / noise
     two_log_prob = -n * np.log(2.0 * np.pi * noise) - 2.0 * np.sum(np.log(np.diag(L))) - quad
-    two_trace = n * variance / noise - np.trace(Phi)
+    two_trace = n * (variance[0] if np.ndim(variance) else variance) / noise - np.trace(Phi)
     return float((two_log_prob - two_trace) / 2.0)
 
 
@@ -411,8 +458,8 @@ def collapsed_elbo_value_and_grad_autodiff(
     val = (two_log_prob - two_trace) / 2.0
     val.backward()
     g = {
-        "lengthscale": ell.grad.numpy().copy() if ell.grad.ndim else float(ell.grad),
-        "variance": float(var.grad),
+        "lengthscale": _grad_of(ell),
+        "variance": _grad_of(var),
         "obs_stddev": float(sn.grad),
         "mean_const": float(c.grad),
         "inducing_inputs": Zt.grad.numpy().copy(),
@@ -694,8 +741,8 @@ def svgp_elbo_value_and_grad_autodiff(kind, X, y, Z, lengthscale, variance, obs_
     val = ellv * num_datapoints / b - kl
     val.backward()
     g = {
-        "lengthscale": ell.grad.numpy().copy() if ell.grad.ndim else float(ell.grad),
-        "variance": float(var.grad), "obs_stddev": float(sn.grad), "mean_const": float(c.grad),
+        "lengthscale": _grad_of(ell),
+        "variance": _grad_of(var), "obs_stddev": float(sn.grad), "mean_const": float(c.grad),
         "inducing_inputs": Zt.grad.numpy().copy(), "variational_mean": mu.grad.numpy().copy(),
         "variational_root_covariance": np.tril(Wp.grad.numpy()),
     }
@@ -741,3 +788,46 @@ def collapsed_predict(kind, X, y, T, Z, lengthscale, variance, obs_stddev, mean_
     mean = mean_const + (Kzt.T / noise) @ Kzz_inv_Kzx_diff
     cov = Ktt - Lz_inv_Kzt.T @ Lz_inv_Kzt + L_inv_Lz_inv_Kzt.T @ L_inv_Lz_inv_Kzt
     return mean, add_jitter(cov, jitter)
+
+
+# ----------------------------------------------------------------------------------------
+# f-4: conjugate_loocv -- gpjax/objectives.py:161-178
+# ----------------------------------------------------------------------------------------
+def conjugate_loocv(kind, X, y, lengthscale, variance, obs_stddev, mean_const=0.0, jitter=1e-6, sigma=None):
+    """Literal order of objectives.py:161-178 (LU solve + explicit inverse).  `sigma` overrides the covariance
+    (used for combination kernels assembled by the caller)."""
+    X = np.asarray(X, np.float64)
+    y = np.asarray(y, np.float64).reshape(-1, 1)
+    n = X.shape[0]
+    mx = np.ones((n, 1)) * mean_const
+    if sigma is None:
+        sigma = gram(kind, X, lengthscale, variance) + np.eye(n) * (obs_stddev**2 + jitter)  # :166-168
+    sigma_inv_y = np.linalg.solve(sigma, y - mx)  # :171
+    sigma_inv_diag = np.diag(np.linalg.inv(sigma))[:, None]  # :172-173
+    loocv_means = mx + (y - mx) - sigma_inv_y / sigma_inv_diag  # :175
+    loocv_stds = np.sqrt(1.0 / sigma_inv_diag)  # :176
+    z = (y - loocv_means) / loocv_stds
+    return float(np.sum(-0.5 * z * z - np.log(loocv_stds) - 0.5 * np.log(2.0 * np.pi)))  # :177-178
+
+
+def conjugate_loocv_value_and_grad_autodiff(kind, X, y, lengthscale, variance, obs_stddev, mean_const=0.0, jitter=1e-6):
+    """Reverse-mode gradient of the literal restatement of objectives.py:161-178."""
+    import torch
+
+    kind = _kind_id(kind)
+    t = lambda a: torch.tensor(np.asarray(a, np.float64), dtype=torch.float64, requires_grad=True)
+    Xt = torch.tensor(np.asarray(X, np.float64))
+    yt = torch.tensor(np.asarray(y, np.float64).reshape(-1, 1))
+    ell, var, sn, c = t(lengthscale), t(variance), t(obs_stddev), t(mean_const)
+    n = Xt.shape[0]
+    mx = torch.ones((n, 1), dtype=torch.float64) * c
+    sigma = _t_cross(torch, kind, Xt, Xt, ell, var) + torch.eye(n, dtype=torch.float64) * (sn**2 + jitter)
+    sigma_inv_y = torch.linalg.solve(sigma, yt - mx)
+    sigma_inv_diag = torch.diagonal(torch.linalg.inv(sigma))[:, None]
+    means = mx + (yt - mx) - sigma_inv_y / sigma_inv_diag
+    stds = torch.sqrt(1.0 / sigma_inv_diag)
+    z = (yt - means) / stds
+    val = torch.sum(-0.5 * z * z - torch.log(stds) - 0.5 * math.log(2.0 * math.pi))
+    val.backward()
+    g = {"lengthscale": _grad_of(ell), "variance": _grad_of(var), "obs_stddev": float(sn.grad), "mean_const": float(c.grad)}
+    return float(val.detach()), g

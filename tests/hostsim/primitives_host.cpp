@@ -62,29 +62,80 @@ int gemm(stream_t, const GemmDesc& d) {
     return GPB_OK;
 }
 
-static double profile(int kind, double r2, double var) {
-    if (kind == KIND_RBF) return var * std::exp(-0.5 * r2);
-    double tau = std::sqrt(std::fmax(r2, 1e-36));
-    if (kind == KIND_MATERN12) return var * std::exp(-tau);
-    if (kind == KIND_MATERN32) return var * (1.0 + std::sqrt(3.0) * tau) * std::exp(-std::sqrt(3.0) * tau);
-    return var * (1.0 + std::sqrt(5.0) * tau + 5.0 / 3.0 * tau * tau) * std::exp(-std::sqrt(5.0) * tau);
-}
-static double dprofile(int kind, double r2, double var, double k) {
-    if (kind == KIND_RBF) return -0.5 * k;
-    if (!(r2 > 1e-36)) return 0.0;
-    double tau = std::sqrt(r2);
-    if (kind == KIND_MATERN12) return -0.5 * k / tau;
-    if (kind == KIND_MATERN32) return -1.5 * var * std::exp(-std::sqrt(3.0) * tau);
-    return -(5.0 / 6.0) * var * (1.0 + std::sqrt(5.0) * tau) * std::exp(-std::sqrt(5.0) * tau);
-}
-static double r2_of(const double* x, const double* z, int D, const double* ell, int iso) {
-    double r2 = 0.0;
+// One kernel evaluation with all first derivatives, written pair-by-pair (an independent scalar model of the
+// tiled device code).  `scal` = {variance, shape}: shape = alpha (RationalQuadratic), power (PoweredExponential),
+// period (Periodic).
+struct PairOut {
+    double k = 0.0;        // value
+    double dshape = 0.0;   // d k / d shape
+    double dx[64];         // d k / d x_d   (= - d k / d z_d)
+    double dl[64];         // d k / d l_d
+};
+static void pair_eval(int kind, const double* x, const double* z, int D, const double* ell, int iso,
+                      const double* scal, PairOut& o) {
+    const double var = scal[0];
+    const double shp = kind_has_shape(kind) ? scal[1] : 0.0;
+    o.dshape = 0.0;
+    if (kind == KIND_PERIODIC) {
+        const double pi = 3.141592653589793;
+        double r2 = 0.0, s[64], c[64], u[64];
+        for (int d = 0; d < D; ++d) {
+            u[d] = pi * (x[d] - z[d]) / shp;
+            s[d] = std::sin(u[d]) / ell[iso ? 0 : d];
+            c[d] = std::cos(u[d]);
+            r2 += s[d] * s[d];
+        }
+        o.k = var * std::exp(-0.5 * r2);
+        for (int d = 0; d < D; ++d) {
+            double l = ell[iso ? 0 : d];
+            o.dx[d] = -o.k * s[d] * c[d] / l * pi / shp;
+            o.dl[d] = o.k * s[d] * s[d] / l;
+            o.dshape += o.k * s[d] * c[d] / l * u[d] / shp;
+        }
+        return;
+    }
+    double r2 = 0.0, a[64];
     for (int d = 0; d < D; ++d) {
         double l = ell[iso ? 0 : d];
-        double a = x[d] / l - z[d] / l;
-        r2 += a * a;
+        a[d] = x[d] / l - z[d] / l;
+        r2 += a[d] * a[d];
     }
-    return r2;
+    double k, dk = 0.0;  // dk = d k / d r2
+    const double tau = std::sqrt(std::fmax(r2, 1e-36));
+    const bool live = r2 > 1e-36;
+    switch (kind) {
+        case KIND_RBF: k = var * std::exp(-0.5 * r2); dk = -0.5 * k; break;
+        case KIND_MATERN12: k = var * std::exp(-tau); dk = live ? -0.5 * k / tau : 0.0; break;
+        case KIND_MATERN32:
+            k = var * (1.0 + std::sqrt(3.0) * tau) * std::exp(-std::sqrt(3.0) * tau);
+            dk = live ? -1.5 * var * std::exp(-std::sqrt(3.0) * tau) : 0.0;
+            break;
+        case KIND_MATERN52:
+            k = var * (1.0 + std::sqrt(5.0) * tau + 5.0 / 3.0 * tau * tau) * std::exp(-std::sqrt(5.0) * tau);
+            dk = live ? -(5.0 / 6.0) * var * (1.0 + std::sqrt(5.0) * tau) * std::exp(-std::sqrt(5.0) * tau) : 0.0;
+            break;
+        case KIND_RATQUAD: {
+            double base = 1.0 + 0.5 * r2 / shp;
+            k = var * std::pow(base, -shp);
+            dk = -0.5 * var * std::pow(base, -shp - 1.0);
+            o.dshape = k * (-std::log(base) + (0.5 * r2 / shp) / base);
+            break;
+        }
+        case KIND_POWEXP: {
+            double tp = std::pow(tau, shp);
+            k = var * std::exp(-tp);
+            dk = live ? -k * shp * std::pow(tau, shp - 1.0) / (2.0 * tau) : 0.0;
+            o.dshape = -k * tp * std::log(tau);
+            break;
+        }
+        default: k = (r2 == 0.0) ? var : 0.0; dk = 0.0; break;  // KIND_WHITE
+    }
+    o.k = k;
+    for (int d = 0; d < D; ++d) {
+        double l = ell[iso ? 0 : d];
+        o.dx[d] = dk * 2.0 * a[d] / l;
+        o.dl[d] = dk * (-2.0) * a[d] * a[d] / l;
+    }
 }
 
 int max_input_dim() { return 64; }
@@ -92,7 +143,7 @@ int max_input_dim() { return 64; }
 int gram(stream_t, const GramDesc& d) {
     if (d.N < 0 || d.M < 0 || d.D <= 0) return GPB_ERR_INVALID;
     if (d.D > 64) return GPB_ERR_UNSUPPORTED;
-    double var = d.variance[0];
+    if (!kind_valid(d.kind)) return GPB_ERR_INVALID;
     double dadd = d.diag_add + (d.diag_add_sq ? d.diag_add_sq[0] * d.diag_add_sq[0] : 0.0);
     const int64_t TR = 64, TC = 128;
     for (int64_t i = 0; i < d.N; ++i)
@@ -101,7 +152,9 @@ int gram(stream_t, const GramDesc& d) {
                 int64_t r0 = (i / TR) * TR, c0 = (j / TC) * TC;
                 if (d.row0 + std::min(r0 + TR, d.N) - 1 < d.col0 + c0) continue;
             }
-            double k = profile(d.kind, r2_of(d.X + i * d.ldx, d.Z + j * d.ldz, d.D, d.ell, d.ell_is_scalar), var);
+            PairOut po;
+            pair_eval(d.kind, d.X + i * d.ldx, d.Z + j * d.ldz, d.D, d.ell, d.ell_is_scalar, d.variance, po);
+            double k = po.k;
             if (d.row0 + i == d.col0 + j) k += dadd;
             d.K[i * d.ldk + j] = k;
         }
@@ -229,15 +282,16 @@ int mll_value(stream_t, int64_t n, const double* half_logdet, const double* quad
 int64_t mll_bwd_partials_count(int64_t N, int D, int64_t) {
     int DC = D <= 2 ? 2 : (D <= 4 ? 4 : 8);
     int Dp = (D + DC - 1) / DC * DC;
-    return ((N + 63) / 64) * ((N + 127) / 128) * (Dp + 2);
+    return ((N + 63) / 64) * ((N + 127) / 128) * (Dp + 3);
 }
 
 int mll_bwd(stream_t, const MllBwdDesc& d) {
     if (d.nb <= 0 || d.nb % 128 != 0) return GPB_ERR_INVALID;
+    if (!kind_valid(d.kind)) return GPB_ERR_INVALID;
     const int64_t N = d.N;
     const double var = d.variance[0];
     std::vector<double> acc(d.D, 0.0);
-    double wk = 0.0, trw = 0.0;
+    double wk = 0.0, trw = 0.0, wshape = 0.0;
     for (int64_t r = 0; r < N; ++r)
         for (int64_t c = 0; c < N; ++c) {
             int64_t br = r / d.nb, bc = c / d.nb;
@@ -248,25 +302,25 @@ int mll_bwd(stream_t, const MllBwdDesc& d) {
             double w = 0.5 * (d.alpha[r] * d.alpha[c] - sv);
             if (r == c) trw += w;
             w *= wgt;
-            double r2 = r2_of(d.X + r * d.ldx, d.X + c * d.ldx, d.D, d.ell, d.ell_is_scalar);
-            double k = profile(d.kind, r2, var), dk = dprofile(d.kind, r2, var, k);
-            wk += w * k;
-            for (int dd = 0; dd < d.D; ++dd) {
-                double l = d.ell[d.ell_is_scalar ? 0 : dd];
-                double a = d.X[r * d.ldx + dd] / l - d.X[c * d.ldx + dd] / l;
-                acc[dd] += w * dk * a * a;
-            }
+            PairOut po;
+            pair_eval(d.kind, d.X + r * d.ldx, d.X + c * d.ldx, d.D, d.ell, d.ell_is_scalar, d.variance, po);
+            wk += w * po.k;
+            wshape += w * po.dshape;
+            for (int dd = 0; dd < d.D; ++dd) acc[dd] += w * po.dl[dd];
         }
     double g = d.gout ? d.gout[0] : 1.0;
     if (d.g_ell) {
         if (d.ell_is_scalar) {
             double s = 0.0;
-            for (int dd = 0; dd < d.D; ++dd) s += g * (-2.0 / d.ell[0]) * acc[dd];
+            for (int dd = 0; dd < d.D; ++dd) s += g * acc[dd];
             d.g_ell[0] = s;
         } else
-            for (int dd = 0; dd < d.D; ++dd) d.g_ell[dd] = g * (-2.0 / d.ell[dd]) * acc[dd];
+            for (int dd = 0; dd < d.D; ++dd) d.g_ell[dd] = g * acc[dd];
     }
-    if (d.g_var) d.g_var[0] = g * wk / var;
+    if (d.g_var) {
+        d.g_var[0] = g * wk / var;
+        if (kind_has_shape(d.kind)) d.g_var[1] = g * wshape;
+    }
     if (d.g_obs_stddev) d.g_obs_stddev[0] = g * 2.0 * d.obs_stddev[0] * trw;
     if (d.g_mean) {
         double s = 0.0;
@@ -279,34 +333,37 @@ int mll_bwd(stream_t, const MllBwdDesc& d) {
 int64_t gram_bwd_partials_count(int64_t N, int64_t M, int D) {
     int DC = D <= 2 ? 2 : (D <= 4 ? 4 : 8);
     int Dp = (D + DC - 1) / DC * DC;
-    return ((N + 63) / 64) * ((M + 127) / 128) * (Dp + 1);
+    return ((N + 63) / 64) * ((M + 127) / 128) * (Dp + 2);
 }
 
 int gram_bwd(stream_t, const GramBwdDesc& d) {
+    if (!kind_valid(d.kind)) return GPB_ERR_INVALID;
     const double var = d.variance[0];
     std::vector<double> acc(d.D, 0.0);
-    double wk = 0.0;
+    double wk = 0.0, wshape = 0.0;
     for (int64_t r = 0; r < d.N; ++r)
         for (int64_t c = 0; c < d.M; ++c) {
             double w = d.dK[r * d.lddk + c];
-            double r2 = r2_of(d.X + r * d.ldx, d.Z + c * d.ldz, d.D, d.ell, d.ell_is_scalar);
-            double k = profile(d.kind, r2, var), dk = dprofile(d.kind, r2, var, k);
-            wk += w * k;
+            PairOut po;
+            pair_eval(d.kind, d.X + r * d.ldx, d.Z + c * d.ldz, d.D, d.ell, d.ell_is_scalar, d.variance, po);
+            wk += w * po.k;
+            wshape += w * po.dshape;
             for (int dd = 0; dd < d.D; ++dd) {
-                double l = d.ell[d.ell_is_scalar ? 0 : dd];
-                double a = d.X[r * d.ldx + dd] / l - d.Z[c * d.ldz + dd] / l;
-                acc[dd] += w * dk * a * a;
-                if (d.g_X) d.g_X[r * d.ldgx + dd] += d.scale * 2.0 * w * dk * a / l;
-                if (d.g_Z) d.g_Z[c * d.ldgz + dd] -= d.scale * 2.0 * w * dk * a / l;
+                acc[dd] += w * po.dl[dd];
+                if (d.g_X) d.g_X[r * d.ldgx + dd] += d.scale * w * po.dx[dd];
+                if (d.g_Z) d.g_Z[c * d.ldgz + dd] -= d.scale * w * po.dx[dd];
             }
         }
     if (d.g_ell) {
         if (d.ell_is_scalar) {
-            for (int dd = 0; dd < d.D; ++dd) d.g_ell[0] += d.scale * (-2.0 / d.ell[0]) * acc[dd];
+            for (int dd = 0; dd < d.D; ++dd) d.g_ell[0] += d.scale * acc[dd];
         } else
-            for (int dd = 0; dd < d.D; ++dd) d.g_ell[dd] += d.scale * (-2.0 / d.ell[dd]) * acc[dd];
+            for (int dd = 0; dd < d.D; ++dd) d.g_ell[dd] += d.scale * acc[dd];
     }
-    if (d.g_var) d.g_var[0] += d.scale * wk / var;
+    if (d.g_var) {
+        d.g_var[0] += d.scale * wk / var;
+        if (kind_has_shape(d.kind)) d.g_var[1] += d.scale * wshape;
+    }
     return GPB_OK;
 }
 

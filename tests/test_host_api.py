@@ -205,3 +205,47 @@ def test_lower_triangular_parameter_and_bijection():
     assert q.variational_mean.value.shape == (4, 1) and torch.equal(q.variational_root_covariance.value,
                                                                     torch.eye(4, dtype=torch.float64))
     assert sorted(n for n, _ in q.named_parameters())[:2] == ["inducing_inputs", "posterior.likelihood.obs_stddev"]
+
+
+# ---- kernels beyond RBF / Matern and kernel algebra -------------------------------------------
+def test_shape_parameter_kernels_and_packing():
+    from gpjax_b200.parameters import SigmoidBounded
+
+    rq = gpx.kernels.RationalQuadratic(lengthscale=[0.5, 0.7], variance=2.0, alpha=0.3)
+    assert rq.alpha == 0.3 and rq.n_dims == 2  # stored as given (rational_quadratic.py:72): not trainable by default
+    assert torch.equal(rq.kernel_scalars(), torch.tensor([2.0, 0.3], dtype=torch.float64))
+    assert set(dict(rq.named_parameters())) == {"lengthscale", "variance"}
+    pe = gpx.kernels.PoweredExponential(power=SigmoidBounded(0.4))
+    assert "power" in dict(pe.named_parameters()) and pe.power.tag == "sigmoid"
+    assert torch.equal(pe.kernel_scalars(), torch.tensor([1.0, 0.4], dtype=torch.float64))
+    with pytest.raises(ValueError):
+        SigmoidBounded(1.5)
+    per = gpx.kernels.Periodic(period=PositiveReal(2.0))
+    assert per.kernel_scalars().tolist() == [1.0, 2.0]
+    w = gpx.kernels.White(variance=0.1)
+    assert isinstance(w.compute_engine, gpx.kernels.ConstantDiagonalKernelComputation)
+    assert w.kernel_scalars().numel() == 1 and w.lengthscale.value.item() == 1.0
+    assert gpx.kernels.RBF().kernel_scalars().numel() == 1
+    u = torch.tensor([-3.0, 0.0, 2.0], dtype=torch.float64)
+    sg = DEFAULT_BIJECTION["sigmoid"]
+    assert torch.allclose(sg.inv(sg(u)), u, atol=1e-12)
+
+
+def test_kernel_algebra_builds_flattened_combinations():
+    k1, k2, k3 = gpx.kernels.RBF(), gpx.kernels.Matern32(), gpx.kernels.White()
+    s = k1 + k2 + k3
+    assert isinstance(s, gpx.kernels.CombinationKernel) and s.operator_name == "sum" and s.kernels == [k1, k2, k3]
+    p = k1 * k2 * k3
+    assert p.operator_name == "prod" and p.kernels == [k1, k2, k3]
+    m = k1 * k2 + k3
+    assert m.operator_name == "sum" and len(m.kernels) == 2 and m.kernels[0].operator_name == "prod"
+    c = k1 + 2.0  # scalars become Constant kernels (kernels/base.py:150-165)
+    assert isinstance(c.kernels[1], gpx.kernels.Constant) and c.kernels[1].constant.value.item() == 2.0
+    assert (3.0 + k1).operator_name == "sum"
+    names = set(dict(m.named_parameters()))
+    assert {"kernels[0].kernels[0].lengthscale", "kernels[0].kernels[1].variance", "kernels[1].variance"} <= names
+    with pytest.raises(TypeError):
+        gpx.kernels.ProductKernel(kernels=[k1, "rbf"])
+    with pytest.raises(NotImplementedError):  # a combination has no single fused epilogue: the sparse objectives refuse
+        from gpjax_b200.objectives import _kernel_args
+        _kernel_args(s)
