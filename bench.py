@@ -305,10 +305,12 @@ def bench_exact(D: Dist, args):
             # overlap the trailing update on the main stream
             "gemm_time_over_step_time": gemm_ms.value * 1e-3 / t,
             "whole_step_tflops": flops_per_eval * args.steps / t / 1e12,
-            # ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 2044 GEMM launches of ONE evaluation at
-            # N=50k (profiles/r01_gemm_traffic_exact50k.md); algorithmic C read+write of the rank-512 updates = 977 GB
-            "traffic": 1.945e12 if n == 50000 else None, "traffic_unit": "bytes per evaluation (all GEMM launches)",
-            "algorithmic_bytes": 3 * 16 * float(n) ** 3 / (6 * 512)}
+            # ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 1846 GEMM launches of ONE evaluation at
+            # N=50k with the 1024 block (profiles/r01_gemm_traffic_exact50k_nb1024.md: 1147 GB read + 499 GB written);
+            # algorithmic = read + write of every C tile touched by the rank-NB updates of the three N^3/3 phases
+            "traffic": 1.646e12 if (n == 50000 and L.gpb_block_size() == 1024) else None,
+            "traffic_unit": "bytes per evaluation (all GEMM launches)",
+            "algorithmic_bytes": 3 * 16 * float(n) ** 3 / (6 * L.gpb_block_size())}
 
     # ---- e2e: the public API with HOST buffers (pinned), H2D + D2H inside the timed region -------------------
     prior = gpx.gps.Prior(mean_function=gpx.mean_functions.Constant(Real(HYPER["mean_const"])),

@@ -144,7 +144,7 @@ def _spd(n, seed, kind="rbf", D=4):
     return o.gram(kind, X, np.linspace(0.8, 1.4, D), 1.0) + 0.09 * np.eye(n)
 
 
-@pytest.mark.parametrize("n", [1, 2, 5, 100, 128, 129, 256, 300, 513, 1500])
+@pytest.mark.parametrize("n", [1, 2, 5, 100, 128, 129, 256, 300, 513, 1024, 1025, 1500, 2300, 3200])  # block = 1024
 def test_potrf_trsv_trsm_logdet_potri(n):
     from gpjax_b200 import ops
 

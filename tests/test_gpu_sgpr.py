@@ -57,7 +57,7 @@ def check(val, g, ref, gref, cond=1.0):
 @pytest.mark.parametrize("kind,name", KINDS)
 @pytest.mark.parametrize("n,m,d,iso,block", [(10, 3, 1, True, 4), (200, 16, 3, False, 64), (1000, 130, 8, False, 300),
                                              (777, 300, 6, False, 1000), (2500, 12, 1, True, 512),
-                                             (2500, 50, 1, True, 512)])
+                                             (2500, 50, 1, True, 512), (3000, 1100, 6, False, 1024)])
 def test_elbo_vs_autodiff_oracle(kind, name, n, m, d, iso, block):
     X, y, Z = make(n, m, d, n + m)
     ell = np.array(0.9) if iso else np.linspace(0.8, 1.6, d)
