@@ -379,11 +379,20 @@ def bench_sgpr(D: Dist, args, steps=None, warmup=None):
     L.gpb_profile_read(C.byref(gemm_ms), C.byref(gemm_n), C.byref(all_n))
     L.gpb_profile_reset(0)
     value = n_total * steps / t
-    flops = 4.0 * (hi - lo) * m * m  # SURVEY 8d reference formulation: fwd 2NM^2 + bwd 2NM^2 (per rank share)
+    # Flop actually executed per point (per rank share).  The public default (statistics="auto") takes the raw-product route
+    # while Kzz is well conditioned: forward N M^2 (SYRK on [K_b|d|1]; the whitening is applied once to the M x M sums --
+    # SURVEY 8d's "accumulate Kzx Kxz first" variant, counted at its own, smaller figure) + backward 2 N M^2
+    # (dK_b = [K_b|d|1] Caug^T).  The reference formulation (TRSM + SYRK forward, statistics="whitened") is 4 M^2.
+    cond_est = sgpr_ops.kzz_condition_estimate(0, Z.detach(), ell.detach(), var.detach(), HYPER["jitter"])
+    raw_route = cond_est <= sgpr_ops.RAW_STATISTICS_COND_LIMIT
+    fpp = (3.0 if raw_route else 4.0) * m * m
+    flops = fpp * (hi - lo)
     achieved = flops * steps / (gemm_ms.value * 1e-3) / 1e12
     roof = {"bound": "tensor", "kernel": "gemm_f64_kernel (FP64 DMMA.8x8x4)", "achieved": achieved,
             "peak": NOMINAL_FP64_TFLOPS, "unit": "TFLOP/s", "frac": achieved / NOMINAL_FP64_TFLOPS,
-            "algorithmic_flop_per_point": 4.0 * m * m, "gemm_time_over_step_time": gemm_ms.value * 1e-3 / t,
+            "algorithmic_flop_per_point": fpp, "reference_formulation_flop_per_point": 4.0 * m * m,
+            "statistics_route": "raw" if raw_route else "whitened", "kzz_condition_estimate": cond_est,
+            "gemm_time_over_step_time": gemm_ms.value * 1e-3 / t,
             "whole_step_tflops_per_gpu": flops * steps / t / 1e12, "traffic": None}
 
     # e2e through the public API with host-resident shards
@@ -459,7 +468,11 @@ def bench_svgp(D: Dist, args):
     L.gpb_profile_read(C.byref(gemm_ms), C.byref(gemm_n), C.byref(all_n))
     L.gpb_profile_reset(0)
     value = D.world * batch * steps / t
-    flops = 4.0 * batch * m * m + 20.0 * m**3  # streamed passes + replicated M x M finish
+    # streamed passes (3 B M^2 on the raw-statistics route "auto" takes for a well-conditioned Kzz, else 4 B M^2)
+    # + replicated M x M finish
+    cond_est = sgpr_ops.kzz_condition_estimate(1, Z.detach(), ell.detach(), var.detach(), HYPER["jitter"])
+    raw_route = cond_est <= sgpr_ops.RAW_STATISTICS_COND_LIMIT
+    flops = (3.0 if raw_route else 4.0) * batch * m * m + 22.0 * m**3
     sgpr_ops.release_buffers()
     return dict(metric="SVGP elbo value+grad minibatch points/s", value=value, unit="points/s", n_gpus=D.world, steps=steps,
                 ms_per_step=1e3 * t / steps, scaling="weak", higher_is_better=True, vs_baseline=None, dtype="f64",
@@ -470,6 +483,7 @@ def bench_svgp(D: Dist, args):
                           "achieved": flops * steps / (gemm_ms.value * 1e-3) / 1e12, "peak": NOMINAL_FP64_TFLOPS,
                           "unit": "TFLOP/s", "frac": flops * steps / (gemm_ms.value * 1e-3) / 1e12 / NOMINAL_FP64_TFLOPS,
                           "algorithmic_flop_per_step": flops, "gemm_time_over_step_time": gemm_ms.value * 1e-3 / t,
+                          "statistics_route": "raw" if raw_route else "whitened", "kzz_condition_estimate": cond_est,
                           "traffic": None},
                 gpu_launches=int(all_n.value))
 

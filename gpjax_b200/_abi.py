@@ -50,6 +50,10 @@ PROTOTYPES = {
         i32,
         [vp, i32, i64, i64, i32, vp, i64, vp, vp, i64, vp, i32, vp, vp, vp, f64, i64, vp, i64, vp],
     ),
+    "gpb_sgpr_stats_raw": (
+        i32,
+        [vp, i32, i64, i64, i32, vp, i64, vp, vp, i64, vp, i32, vp, vp, vp, f64, i64, vp, i64, vp],
+    ),
     "gpb_sgpr_finish": (i32, [vp, i32, i64, i32, vp, i64, vp, i32, vp, vp, i64, vp, i64, vp, i32, vp, vp]),
     "gpb_sgpr_grad_local": (
         i32,

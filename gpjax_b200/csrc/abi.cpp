@@ -188,6 +188,20 @@ int gpb_sgpr_stats(void* stream, int kind, int64_t Nloc, int64_t M, int D, const
                                         variance, obs_stddev, mean_const, jitter, block_rows), w, Paug);
 }
 
+int gpb_sgpr_stats_raw(void* stream, int kind, int64_t Nloc, int64_t M, int D, const double* X, int64_t ldx,
+                       const double* y, const double* Z, int64_t ldz, const double* lengthscale,
+                       int lengthscale_is_scalar, const double* variance, const double* obs_stddev,
+                       const double* mean_const, double jitter, int64_t block_rows, void* ws, int64_t ws_bytes,
+                       double* Paug) {
+    SgprWs w;
+    int rc = sgpr_ws_carve(ws, ws_bytes, M, D, block_rows, &w);
+    if (rc) return rc;
+    SgprArgs a = sgpr_args(kind, Nloc, M, D, X, ldx, y, Z, ldz, lengthscale, lengthscale_is_scalar, variance, obs_stddev,
+                           mean_const, jitter, block_rows);
+    a.raw_stats = 1;
+    return sgpr_stats(stream, a, w, Paug);
+}
+
 int gpb_sgpr_finish(void* stream, int kind, int64_t M, int D, const double* Z, int64_t ldz,
                     const double* lengthscale, int lengthscale_is_scalar, const double* variance,
                     const double* obs_stddev, int64_t block_rows, void* ws, int64_t ws_bytes, const double* Paug,

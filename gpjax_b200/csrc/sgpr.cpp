@@ -140,18 +140,28 @@ int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug) {
     GPB_TRY(trsm_lower_left(s, M, M, ws.Lz, M, ws.fz, ws.Linv, M, 0));
     GPB_TRY(fill2d(s, ld, ld, Paug, ld, 0.0));
     GPB_TRY(fill2d(s, SPLITK * ld, ld, ws.Ppart, ld, 0.0));
+    // Two ways to the same row-additive statistics Paug = sum_b [A~_b ; d_b^T ; 1^T][..]^T, A~_b = Lz^-1 K_b:
+    //  * whiten first (reference order, objectives.py:387-390; default): At_b = K_b^T Lz^-T per block, then the SYRK.
+    //    Forward 2 N M^2 flop; backward-stable (error ~ eps * sqrt(cond(Kzz))).
+    //  * raw statistics (a.raw_stats; SURVEY 8d's "accumulate Kzx Kxz first" variant): SYRK on [K_b^T | d_b | 1]
+    //    directly, Paug = T Praw T^T with T = blockdiag(Lz^-1, 1, 1) once at the end (two M^3 products).
+    //    Forward N M^2 flop, but the rounding of Praw is amplified by cond(Kzz) (normal-equations-like:
+    //    relative error of Phi ~ eps * sqrt(N) * cond(Kzz)); callers enable it for well-conditioned Kzz only.
+    const bool raw = a.raw_stats != 0;
     for (int64_t r0 = 0; r0 < a.Nloc; r0 += a.block_rows) {
         const int64_t rows = (a.Nloc - r0) < a.block_rows ? (a.Nloc - r0) : a.block_rows;
         // K_b^T = k(X_b, Z)   (objectives.py:355, one row block)
-        GPB_TRY(gram(s, gram_desc(a, a.X + r0 * a.ldx, a.ldx, rows, ws.T1, ld)));
-        // At_b = K_b^T Lz^-T  (objectives.py:387 without the 1/sigma, folded into the finish)
-        GemmDesc g;
-        g.M = rows; g.N = M; g.K = M;
-        g.A = ws.T1; g.lda = ld; g.B = ws.Linv; g.ldb = M; g.C = ws.T2; g.ldc = ld;
-        g.krange = KR_B_LOWER;
-        GPB_TRY(gemm(s, g));
+        GPB_TRY(gram(s, gram_desc(a, a.X + r0 * a.ldx, a.ldx, rows, raw ? ws.T2 : ws.T1, ld)));
+        if (!raw) {
+            // At_b = K_b^T Lz^-T  (objectives.py:387 without the 1/sigma, folded into the finish)
+            GemmDesc g;
+            g.M = rows; g.N = M; g.K = M;
+            g.A = ws.T1; g.lda = ld; g.B = ws.Linv; g.ldb = M; g.C = ws.T2; g.ldc = ld;
+            g.krange = KR_B_LOWER;
+            GPB_TRY(gemm(s, g));
+        }
         GPB_TRY(sgpr_aug_columns(s, rows, ws.T2, ld, M, a.y + r0, a.mean_const));
-        // Paug += [At_b | d_b | 1]^T [At_b | d_b | 1]   (objectives.py:390,404,407 in one SYRK).
+        // Ppart += [T2 | d_b | 1]^T [T2 | d_b | 1]   (objectives.py:390,404,407 in one SYRK).
         // The output has only ~(M/128)*(M/64)/2 tiles, so K (= rows) is split into SPLITK slices that run as
         // one batched launch into separate partial sums (summed after the block loop).
         const int S = rows >= 256 ? SPLITK : 1;
@@ -165,7 +175,28 @@ int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug) {
         u.batch = S; u.strideA = Ks * ld; u.strideB = Ks * ld; u.strideC = ld * ld;
         GPB_TRY(gemm(s, u));
     }
-    for (int i = 0; i < SPLITK; ++i) GPB_TRY(axpy(s, ld * ld, 1.0, ws.Ppart + (int64_t)i * ld * ld, Paug));
+    if (!raw) {
+        for (int i = 0; i < SPLITK; ++i) GPB_TRY(axpy(s, ld * ld, 1.0, ws.Ppart + (int64_t)i * ld * ld, Paug));
+        return GPB_OK;
+    }
+    double* Praw = ws.Ppart;                       // slab 0 collects the sum
+    double* W1 = ws.Ppart + (int64_t)ld * ld;      // slab 1 is scratch afterwards
+    for (int i = 1; i < SPLITK; ++i) GPB_TRY(axpy(s, ld * ld, 1.0, ws.Ppart + (int64_t)i * ld * ld, Praw));
+    GPB_TRY(symmetrize(s, ld, Praw, ld, 1));
+    // W1 = Praw[:, :M] Lz^-T   ((M+2) x M; its last two rows are already the whitened psi / a1 rows)
+    GemmDesc g;
+    g.M = ld; g.N = M; g.K = M;
+    g.A = Praw; g.lda = ld; g.B = ws.Linv; g.ldb = M; g.C = W1; g.ldc = ld;
+    g.krange = KR_B_LOWER;
+    GPB_TRY(gemm(s, g));
+    // Phi = Lz^-1 W1[:M] = (W1[:M]^T Lz^-T)^T, symmetric: the lower triangle of the product is what is kept
+    GemmDesc h;
+    h.M = M; h.N = M; h.K = M;
+    h.A = W1; h.lda = ld; h.a_layout = LAYOUT_MN; h.B = ws.Linv; h.ldb = M; h.C = Paug; h.ldc = ld;
+    h.krange = KR_B_LOWER; h.mask = MASK_LOWER;
+    GPB_TRY(gemm(s, h));
+    GPB_TRY(copy2d(s, 2, M, W1 + M * ld, ld, Paug + M * ld, ld));
+    GPB_TRY(copy2d(s, 2, 2, Praw + M * ld + M, ld, Paug + M * ld + M, ld));
     return GPB_OK;
 }
 

@@ -22,6 +22,7 @@ struct SgprArgs {
     const double* mean_const = nullptr;  // nullable
     double jitter = 1e-6;
     int64_t block_rows = 32768;  // rows per streamed block
+    int raw_stats = 0;           // pass 1 accumulates raw [K_b^T|d|1] products and whitens once at the end (see sgpr.cpp)
 };
 
 struct SgprWs {

@@ -86,11 +86,13 @@ def conjugate_loocv(posterior, data: Dataset) -> torch.Tensor:
 
 
 def collapsed_elbo(variational_family, data: Dataset, *, block_rows: int = sgpr_ops.DEFAULT_BLOCK_ROWS,
-                   group=None) -> torch.Tensor:
+                   group=None, statistics: str = "auto") -> torch.Tensor:
     """Collapsed (Titsias) evidence lower bound (objectives.py:342-416).
 
     `data` holds THIS rank's rows; when torch.distributed is initialised the row-additive statistics
-    and the gradient are all-reduced over `group`, so every rank returns the full-data ELBO."""
+    and the gradient are all-reduced over `group`, so every rank returns the full-data ELBO.
+    `statistics` selects how pass 1 forms them ("auto" | "whitened" | "raw", see sgpr_ops.collapsed_elbo_fused):
+    the reference's whiten-first order always, or the cheaper raw-product route while Kzz is well conditioned."""
     x, y = data.X, data.y
     post = variational_family.posterior
     kernel = post.prior.kernel
@@ -102,10 +104,11 @@ def collapsed_elbo(variational_family, data: Dataset, *, block_rows: int = sgpr_
     if mean is not None:
         mean = mean.to(xs.device)
     return sgpr_ops.collapsed_elbo_fused(kind, xs, y, z, ell, var, post.likelihood.obs_stddev.value, mean,
-                                         float(variational_family.jitter), block_rows, group)
+                                         float(variational_family.jitter), block_rows, group, statistics)
 
 
-def elbo(variational_family, data: Dataset, *, block_rows: int = sgpr_ops.DEFAULT_BLOCK_ROWS, group=None) -> torch.Tensor:
+def elbo(variational_family, data: Dataset, *, block_rows: int = sgpr_ops.DEFAULT_BLOCK_ROWS, group=None,
+         statistics: str = "auto") -> torch.Tensor:
     """Evidence lower bound of a VariationalGaussian (objectives.py:241-273):
     sum_b E_q[log p(y_b | f(x_b))] * num_datapoints / batch - KL[q(u) || p(u)], Gaussian likelihood (analytical
     integrator, integrators.py:151-158).  `data` is THIS rank's minibatch; with torch.distributed initialised the
@@ -126,7 +129,7 @@ def elbo(variational_family, data: Dataset, *, block_rows: int = sgpr_ops.DEFAUL
         mean = mean.to(xs.device)
     return svgp_ops.svgp_elbo_fused(kind, xs, data.y, z, ell, var, post.likelihood.obs_stddev.value, mean,
                                     q.variational_mean.value, q.variational_root_covariance.value,
-                                    float(post.likelihood.num_datapoints), float(q.jitter), block_rows, group)
+                                    float(post.likelihood.num_datapoints), float(q.jitter), block_rows, group, statistics)
 
 
 __all__ = ["conjugate_mll", "conjugate_loocv", "collapsed_elbo", "elbo"]

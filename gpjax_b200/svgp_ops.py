@@ -9,17 +9,19 @@ import torch
 from . import _abi
 from ._lib import lib
 from .ops import _check_mat, _ell_args, _kscalars, _p, _scalar, _stream, require_cuda
-from .sgpr_ops import DEFAULT_BLOCK_ROWS, _all_reduce, _state
+from .sgpr_ops import DEFAULT_BLOCK_ROWS, _all_reduce, _state, _stats, _use_raw_statistics
 
 
-def _forward_raw(st, kind, X, y, Z, ell_v, iso, var, sn, mean, mu, W, ndata, jitter, block_rows, group, need_grad):
+def _forward_raw(st, kind, X, y, Z, ell_v, iso, var, sn, mean, mu, W, ndata, jitter, block_rows, group, need_grad,
+                 raw=False):
     n_loc, D = X.shape
     M = Z.shape[0]
     L = lib()
     P = torch.empty(L.gpb_sgpr_stats_count(M), dtype=torch.float64, device=Z.device)
-    rc = L.gpb_sgpr_stats(_stream(), kind, n_loc, M, D, _p(X), X.stride(0) if n_loc else D, _p(y), _p(Z), Z.stride(0),
-                          _p(ell_v), iso, _p(var), _p(sn), _p(mean), float(jitter), block_rows, _p(st.ws), st.nbytes, _p(P))
-    _abi.check(rc, "gpb_sgpr_stats")
+    fn, name = _stats(L, raw)
+    rc = fn(_stream(), kind, n_loc, M, D, _p(X), X.stride(0) if n_loc else D, _p(y), _p(Z), Z.stride(0),
+            _p(ell_v), iso, _p(var), _p(sn), _p(mean), float(jitter), block_rows, _p(st.ws), st.nbytes, _p(P))
+    _abi.check(rc, name)
     _all_reduce(P, group)
     val = torch.empty(1, dtype=torch.float64, device=Z.device)
     info = torch.zeros(2, dtype=torch.int32, device=Z.device)
@@ -34,7 +36,7 @@ def _forward_raw(st, kind, X, y, Z, ell_v, iso, var, sn, mean, mu, W, ndata, jit
 class SvgpElboFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, kind, X, y, Z, ell, variance, obs_stddev, mean_const, var_mean, var_sqrt, num_datapoints, jitter,
-                block_rows, group):
+                block_rows, group, statistics="auto"):
         _check_mat(X, "X")
         _check_mat(Z, "Z")
         _check_mat(var_sqrt, "variational_root_covariance")
@@ -56,9 +58,10 @@ class SvgpElboFunction(torch.autograd.Function):
         block_rows = int(min(block_rows, max(n_loc, 1)))
         st = _state(M, D, block_rows, Z.device)
         need_grad = any(ctx.needs_input_grad)
+        raw = _use_raw_statistics(statistics, kind, Z, ell_v, var, jitter)
         val = _forward_raw(st, kind, X, y, Z, ell_v, iso, var, sn, mean, mu, W, num_datapoints, jitter, block_rows, group,
-                           need_grad)
-        ctx.cfg = (kind, iso, jitter, block_rows, group, mean is not None, float(num_datapoints))
+                           need_grad, raw)
+        ctx.cfg = (kind, iso, jitter, block_rows, group, mean is not None, float(num_datapoints), raw)
         ctx.gen = st.generation
         ctx.shapes = (ell.shape, variance.shape, obs_stddev.shape, None if mean_const is None else mean_const.shape,
                       var_mean.shape)
@@ -68,13 +71,13 @@ class SvgpElboFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         X, y, Z, ell_v, var, sn, mean, mu, W = ctx.saved_tensors
-        kind, iso, jitter, block_rows, group, has_mean, ndata = ctx.cfg
+        kind, iso, jitter, block_rows, group, has_mean, ndata, raw = ctx.cfg
         n_loc, D = X.shape
         M = Z.shape[0]
         st = _state(M, D, block_rows, Z.device)
         if st.generation != ctx.gen:
             _forward_raw(st, kind, X, y, Z, ell_v, iso, var, sn, mean if has_mean else None, mu, W, ndata, jitter,
-                         block_rows, group, True)
+                         block_rows, group, True, raw)
         L = lib()
         nl = 1 if iso else D
         flat = torch.empty(M * D + nl + var.numel(), dtype=torch.float64, device=Z.device)
@@ -96,10 +99,11 @@ class SvgpElboFunction(torch.autograd.Function):
         _abi.check(rc, "gpb_svgp_grad_finish")
         s_ell, s_var, s_sn, s_mean, s_mu = ctx.shapes
         return (None, None, None, g_Z.reshape(M, D), g_ell.reshape(s_ell), g_var.reshape(s_var), g_sn.reshape(s_sn),
-                g_mean.reshape(s_mean) if has_mean else None, g_mu.reshape(s_mu), g_W, None, None, None, None)
+                g_mean.reshape(s_mean) if has_mean else None, g_mu.reshape(s_mu), g_W, None, None, None, None, None)
 
 
 def svgp_elbo_fused(kind, X, y, Z, ell, variance, obs_stddev, mean_const, var_mean, var_sqrt, num_datapoints,
-                    jitter=1e-6, block_rows: int = DEFAULT_BLOCK_ROWS, group=None):
+                    jitter=1e-6, block_rows: int = DEFAULT_BLOCK_ROWS, group=None, statistics: str = "auto"):
+    """`statistics`: see sgpr_ops.collapsed_elbo_fused."""
     return SvgpElboFunction.apply(kind, X, y, Z, ell, variance, obs_stddev, mean_const, var_mean, var_sqrt,
-                                  num_datapoints, jitter, block_rows, group)
+                                  num_datapoints, jitter, block_rows, group, statistics)

@@ -151,6 +151,15 @@ int gpb_sgpr_stats(void* stream, int kind, int64_t Nloc, int64_t M, int D, const
                    int lengthscale_is_scalar, const double* variance, const double* obs_stddev,
                    const double* mean_const, double jitter, int64_t block_rows, void* ws, int64_t ws_bytes,
                    double* Paug);
+/* Same result and contract as gpb_sgpr_stats, cheaper route: accumulates the RAW products [K_b^T|d|1]^T[K_b^T|d|1]
+ * and applies Lz^-1 once to the M x M sums (forward N M^2 instead of 2 N M^2 flop).  Rounding of the raw sums is
+ * amplified by cond(Kzz + jitter I) (relative error of the statistics ~ eps * sqrt(N) * cond), so use it for
+ * well-conditioned Kzz only; gpb_sgpr_stats keeps the reference's whiten-first order (objectives.py:387-390). */
+int gpb_sgpr_stats_raw(void* stream, int kind, int64_t Nloc, int64_t M, int D, const double* X, int64_t ldx,
+                       const double* y, const double* Z, int64_t ldz, const double* lengthscale,
+                       int lengthscale_is_scalar, const double* variance, const double* obs_stddev,
+                       const double* mean_const, double jitter, int64_t block_rows, void* ws, int64_t ws_bytes,
+                       double* Paug);
 int gpb_sgpr_finish(void* stream, int kind, int64_t M, int D, const double* Z, int64_t ldz,
                     const double* lengthscale, int lengthscale_is_scalar, const double* variance,
                     const double* obs_stddev, int64_t block_rows, void* ws, int64_t ws_bytes,

@@ -23,12 +23,15 @@ def make(n, m, d, seed):
     return X, y, Z
 
 
-def run_gpu(kind, X, y, Z, ell, var, sn, c, block_rows, jitter=1e-6):
+def run_gpu(kind, X, y, Z, ell, var, sn, c, block_rows, jitter=1e-6, statistics="whitened"):
+    """`statistics="whitened"` pins the reference's evaluation order (the public default "auto" switches to the raw-product
+    route for well-conditioned Kzz; that route and the switch have their own tests below)."""
     from gpjax_b200.sgpr_ops import collapsed_elbo_fused
 
     p = {k: dev(v).requires_grad_(True) for k, v in dict(Z=Z, ell=ell, var=var, sn=sn).items()}
     mean = None if c is None else dev(c).requires_grad_(True)
-    val = collapsed_elbo_fused(kind, dev(X), dev(y), p["Z"], p["ell"], p["var"], p["sn"], mean, jitter, block_rows)
+    val = collapsed_elbo_fused(kind, dev(X), dev(y), p["Z"], p["ell"], p["var"], p["sn"], mean, jitter, block_rows,
+                               None, statistics)
     val.backward()
     g = dict(inducing_inputs=p["Z"].grad.cpu().numpy(), lengthscale=p["ell"].grad.cpu().numpy(),
              variance=p["var"].grad.item(), obs_stddev=p["sn"].grad.item())
@@ -94,3 +97,53 @@ def test_elbo_config4_shape_small_sample_vs_closed_form():
     ref, gref = o.collapsed_elbo_grad_closed_form("rbf", X, y, Z, ell, 1.0, 0.3, 0.0, block=4096)
     val, g = run_gpu(0, X, y, Z, ell, 1.0, 0.3, 0.0, 8192)
     check(val, g, ref, gref)
+
+
+# ---- the raw-statistics route (csrc/sgpr.cpp, gpb_sgpr_stats_raw) and its automatic selection ---------------------
+@pytest.mark.parametrize("kind,name", KINDS)
+@pytest.mark.parametrize("n,m,d,block", [(1000, 130, 8, 300), (3000, 1100, 6, 1024), (777, 300, 6, 1000)])
+def test_raw_statistics_route_meets_the_tolerance_when_kzz_is_well_conditioned(kind, name, n, m, d, block):
+    X, y, Z = make(n, m, d, n + m)
+    ell = np.linspace(0.8, 1.6, d)
+    cond = cond_kzz(name, Z, ell, 1.2)
+    assert cond < 1e4
+    ref, gref = o.collapsed_elbo_value_and_grad_autodiff(name, X, y, Z, ell, 1.2, 0.5, 0.1)
+    val, g = run_gpu(kind, X, y, Z, ell, 1.2, 0.5, 0.1, block, statistics="raw")
+    check(val, g, ref, gref)
+    va, ga = run_gpu(kind, X, y, Z, ell, 1.2, 0.5, 0.1, block, statistics="auto")
+    check(va, ga, ref, gref)
+
+
+def test_condition_estimate_and_automatic_route_selection():
+    from gpjax_b200 import sgpr_ops
+
+    picks = {}
+    for tag, (n, m, d) in {"well": (2000, 200, 8), "ill": (2500, 50, 1)}.items():
+        X, y, Z = make(n, m, d, 9)
+        ell = np.linspace(0.8, 1.6, d)
+        true = cond_kzz("rbf", Z, ell, 1.2)
+        est = sgpr_ops.kzz_condition_estimate(0, dev(Z), dev(ell), dev(1.2), 1e-6)
+        assert true / 3.0 <= est <= true * 1.0001, (tag, true, est)  # power / inverse iteration approach from below
+        sgpr_ops.release_buffers()  # drops the cached route decision of the previous problem
+        picks[tag] = sgpr_ops._use_raw_statistics("auto", 0, dev(Z), dev(ell), dev(1.2), 1e-6)
+        # whichever route "auto" takes, the result meets the (condition-scaled) tolerance of the default tests
+        ref, gref = o.collapsed_elbo_value_and_grad_autodiff("rbf", X, y, Z, ell, 1.2, 0.5, 0.1)
+        val, g = run_gpu(0, X, y, Z, ell, 1.2, 0.5, 0.1, 512, statistics="auto")
+        check(val, g, ref, gref, true)
+    assert picks == {"well": True, "ill": False}
+    with pytest.raises(ValueError):
+        sgpr_ops._use_raw_statistics("fast", 0, dev(Z), dev(ell), dev(1.2), 1e-6)
+
+
+def test_raw_route_error_grows_with_condition_number_as_documented():
+    """1-D inducing points (cond ~ 1e7): the raw route loses ~cond * eps * sqrt(N) in the VALUE, the whiten-first route
+    does not -- which is why "auto" refuses the raw route there."""
+    X, y, Z = make(2500, 50, 1, 2550)
+    ell = np.array(0.9)
+    cond = cond_kzz("rbf", Z, ell, 1.2)
+    ref = o.collapsed_elbo("rbf", X, y, Z, ell, 1.2, 0.5, 0.1)
+    vw, _ = run_gpu(0, X, y, Z, ell, 1.2, 0.5, 0.1, 512, statistics="whitened")
+    vr, _ = run_gpu(0, X, y, Z, ell, 1.2, 0.5, 0.1, 512, statistics="raw")
+    assert cond > 1e6
+    assert abs(vw - ref) <= 1e-10 * abs(ref)
+    assert abs(vr - ref) <= 100 * np.finfo(float).eps * np.sqrt(2500) * cond * abs(ref)

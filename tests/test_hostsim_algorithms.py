@@ -144,8 +144,9 @@ def test_gram_and_gram_bwd_abi(lib, kind, name):
     assert lib.gpb_gram(None, kind, N, M, 65, p(X), D, p(Z), D, p(ell), 0, p(var), 0.0, None, 0, p(K), M) == -2
 
 
-def _sgpr_run(lib, kind, X, y, Z, ell, iso, var, sn, c, jitter, block_rows, shards=1, gout=1.0):
+def _sgpr_run(lib, kind, X, y, Z, ell, iso, var, sn, c, jitter, block_rows, shards=1, gout=1.0, raw=False, stats_out=None):
     """Drive the 6-step SGPR protocol of include/gpjax_b200.h on `shards` simulated ranks."""
+    stats_fn = lib.gpb_sgpr_stats_raw if raw else lib.gpb_sgpr_stats
     N, D = X.shape
     M = Z.shape[0]
     ellv = np.atleast_1d(np.asarray(ell, np.float64)).copy()
@@ -159,11 +160,13 @@ def _sgpr_run(lib, kind, X, y, Z, ell, iso, var, sn, c, jitter, block_rows, shar
     for r in range(shards):
         Xr, yr = np.ascontiguousarray(X[bounds[r]:bounds[r + 1]]), np.ascontiguousarray(y[bounds[r]:bounds[r + 1]])
         P = np.full(cnt, np.nan)
-        rc = lib.gpb_sgpr_stats(None, kind, len(Xr), M, D, p(Xr), D, p(yr), p(Z), D, p(ellv), int(iso), p(var_a),
-                                p(sn_a), p(c_a), jitter, block_rows, p(wss[r]), nbytes, p(P))
+        rc = stats_fn(None, kind, len(Xr), M, D, p(Xr), D, p(yr), p(Z), D, p(ellv), int(iso), p(var_a),
+                      p(sn_a), p(c_a), jitter, block_rows, p(wss[r]), nbytes, p(P))
         assert rc == 0
         Ps.append(P)
     Pall = np.sum(Ps, axis=0)  # the all-reduce
+    if stats_out is not None:
+        stats_out.append(Pall.reshape(M + 2, M + 2).copy())
     vals = []
     for r in range(shards):
         val, info = np.zeros(1), np.zeros(2, np.int32)
@@ -204,6 +207,29 @@ def test_sgpr_value_and_gradient(lib, kind, name, N, M, D, iso, block, shards):
     for k in gref:
         a, b = -np.asarray(g[k]).reshape(np.shape(gref[k])), np.asarray(gref[k])
         assert np.max(np.abs(a - b)) <= 1e-7 * max(np.max(np.abs(b)), 1e-8 * abs(ref)), k
+
+
+@pytest.mark.parametrize("N,M,D,block,shards", [(500, 130, 8, 200, 2), (300, 40, 2, 128, 3), (257, 30, 1, 64, 1)])
+def test_sgpr_raw_statistics_route(lib, N, M, D, block, shards):
+    """gpb_sgpr_stats_raw (raw Kzx Kxz products, one whitening of the M x M sums) returns the SAME statistics as the
+    whiten-first gpb_sgpr_stats up to rounding amplified by cond(Kzz): the lower triangle agrees within
+    eps * sqrt(N) * cond, and value / gradients meet the tolerance of the default route while Kzz is well conditioned."""
+    X, y = data(N, D, N + M)
+    Z = np.ascontiguousarray(np.random.default_rng(M).uniform(-2, 2, (M, D)))
+    ell = np.linspace(0.8, 1.6, D)
+    cond = np.linalg.cond(o.gram("matern52", Z, ell, 1.3) + 1e-6 * np.eye(M))
+    Sw, Sr = [], []
+    vw, gw = _sgpr_run(lib, 2, X, y, Z, ell, False, 1.3, 0.4, 0.2, 1e-6, block, shards, stats_out=Sw)
+    vr, gr = _sgpr_run(lib, 2, X, y, Z, ell, False, 1.3, 0.4, 0.2, 1e-6, block, shards, raw=True, stats_out=Sr)
+    tl = np.tril_indices(M + 2)
+    scale = np.max(np.abs(Sw[0][tl]))
+    assert np.max(np.abs(Sw[0][tl] - Sr[0][tl])) <= 50 * np.finfo(float).eps * np.sqrt(N) * cond * scale
+    ref, gref = o.collapsed_elbo_value_and_grad_autodiff("matern52", X, y, Z, ell, 1.3, 0.4, 0.2)
+    amp = max(1.0, cond / 1e3)  # the raw route is meant for cond <= ~1e3 (sgpr_ops.RAW_STATISTICS_COND_LIMIT)
+    assert abs(vr - ref) <= 1e-9 * amp * abs(ref)
+    for k in gref:
+        a, b = np.asarray(gr[k]).reshape(np.shape(gref[k])), np.asarray(gref[k])
+        assert np.max(np.abs(a - b)) <= 1e-7 * amp * max(np.max(np.abs(b)), 1e-8 * abs(ref)), (k, cond)
 
 
 def test_sgpr_zero_mean_and_identity_with_mll(lib):
