@@ -24,7 +24,7 @@ CU_SOURCES = ["gemm_f64.cu", "gram.cu", "potrf_leaf.cu", "level2.cu", "sgpr_kern
 CPP_SOURCES = ["algorithms.cpp", "sgpr.cpp", "abi.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
-if os.environ.get("GPB_NB"):  # experiment hook: block size of the blocked algorithms (default 512, see algorithms.h)
+if os.environ.get("GPB_NB"):  # experiment hook: block size of the blocked algorithms (default 1024, see algorithms.h)
     COMMON += [f"-DGPB_NB={int(os.environ['GPB_NB'])}"]
 
 

@@ -25,12 +25,15 @@ class GaussianDistribution:
         return torch.sqrt(self.variance())
 
     def log_prob(self, y: torch.Tensor) -> torch.Tensor:
-        """-1/2 [ n log 2pi + logdet(Sigma) + d^T solve(Sigma, d) ]  (forward-only; see linalg.operations)."""
+        """-1/2 [ n log 2pi + logdet(Sigma) + d^T solve(Sigma, d) ].  Differentiable w.r.t. a dense Sigma, the location
+        and y through ops.GaussianLogProbFunction (dSigma = 1/2 (alpha alpha^T - Sigma^-1) from TRTRI + LAUUM)."""
         from . import ops
 
         mu, sigma = self.loc, self.scale
         n = mu.shape[-1]
         diff = (y - mu).contiguous()
+        if isinstance(sigma, Dense) and torch.is_grad_enabled() and (sigma.array.requires_grad or diff.requires_grad):
+            return ops.GaussianLogProbFunction.apply(sigma.array.contiguous(), diff.reshape(-1))
         if isinstance(sigma, Dense):  # one Cholesky serves both the log-determinant and the solve
             from .linalg import lower_cholesky
 

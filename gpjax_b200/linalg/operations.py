@@ -5,8 +5,10 @@ solves through explicit diagonal-block inverses, fused diagonal log-sum).  Diffe
 reference that callers should know:
   * Dense `solve` / `logdet` factor with Cholesky instead of LU (identical for the SPD matrices every
     call site on the hot path passes; a non-SPD matrix yields NaN exactly like jnp.linalg.cholesky).
-  * These free functions are forward-only; gradients flow through the fused objectives
-    (gpjax_b200.objectives), which carry their own analytic backward.
+  * The fused objectives (gpjax_b200.objectives) carry their own analytic backward and never go through these
+    functions.  For user-composed expressions the Dense / Triangular branches are differentiable as well: when an
+    operand requires grad they run through ops.CholeskyFunction / ops.TriangularSolveFunction (the reverse mode
+    jax.grad derives through jnp.linalg.cholesky / solve_triangular), otherwise through the in-place fast path.
 """
 from __future__ import annotations
 
@@ -35,6 +37,8 @@ def lower_cholesky(A: LinearOperator) -> LinearOperator:
             return A
         raise ValueError("lower_cholesky of an upper-triangular operator is not defined")
     if isinstance(A, Dense):
+        if A.array.requires_grad and torch.is_grad_enabled():
+            return Triangular(ops.CholeskyFunction.apply(A.array.contiguous()), lower=True)
         L, ws = _factor(A.array)
         out = Triangular(L, lower=True)
         out._ws = ws
@@ -69,6 +73,11 @@ def solve(A: LinearOperator, b: torch.Tensor) -> torch.Tensor:
         return b / (A.diagonal if was_1d else A.diagonal[:, None])
     if isinstance(A, Triangular):
         store, ws, trans = _tri_storage(A)
+        if torch.is_grad_enabled() and (store.requires_grad or b.requires_grad):
+            if not was_1d and b.shape[1] > ws.n:
+                ws = ops.FactorWorkspace(max(store.shape[0], b.shape[1]), 1, device=store.device)
+                ops.diag_inverses(store.detach(), ws)
+            return ops.TriangularSolveFunction.apply(store, b, trans, ws)
         if was_1d:
             return ops.trsv_lower_(store, b.detach().clone().contiguous(), ws, trans=trans)
         x = b.detach().clone().contiguous()
@@ -88,10 +97,12 @@ def logdet(A: LinearOperator) -> torch.Tensor:
     if isinstance(A, Diagonal):
         return torch.sum(torch.log(A.diagonal))
     if isinstance(A, Triangular):
+        if A.array.requires_grad and torch.is_grad_enabled():
+            return torch.sum(torch.log(torch.diagonal(A.array)))  # N-element glue, differentiable
         arr = A.array if A.array.stride(1) == 1 else A.array.T  # the diagonal is transpose-invariant
         return ops.sum_log_diag(arr)
     L = lower_cholesky(A if isinstance(A, Dense) else Dense(A.to_dense()))
-    return 2.0 * ops.sum_log_diag(L.array)
+    return 2.0 * logdet(L)
 
 
 def diag(A: LinearOperator) -> torch.Tensor:

@@ -410,3 +410,67 @@ class LoocvFunction(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             g_diff = (-gout * Ps).reshape(ctx.diff_shape)
         return g_sigma, g_diff
+
+
+# ------------------------------------------------------------------------------------------
+# Reverse mode for the free linalg functions (gpjax/linalg/operations.py) -- what jax.grad derives through
+# jnp.linalg.cholesky / jsp.linalg.solve_triangular.  All N^3 work stays on the DMMA GEMM + blocked solves.
+# ------------------------------------------------------------------------------------------
+class CholeskyFunction(torch.autograd.Function):
+    """L = chol(A) (lower, strict upper zero).  Backward (symmetrised, as JAX's cholesky JVP/VJP):
+    Abar = sym( L^-T Phi(L^T Lbar) L^-1 ),  Phi = lower triangle with the diagonal halved."""
+
+    @staticmethod
+    def forward(ctx, A):
+        _check_mat(A, "A")
+        n = A.shape[0]
+        L = A.detach().clone().contiguous()
+        ws = FactorWorkspace(n, 1, potri=False, device=A.device)
+        potrf_lower_(L, ws, zero_upper=True)
+        ctx.ws = ws
+        ctx.save_for_backward(L)
+        return L
+
+    @staticmethod
+    def backward(ctx, Lbar):
+        (L,) = ctx.saved_tensors
+        ws = ctx.ws
+        P = gemm(L, torch.tril(Lbar).contiguous(), a_layout=1, b_layout=1)  # L^T Lbar
+        P = torch.tril(P)
+        torch.diagonal(P).mul_(0.5)
+        Y = trsm_lower_left_(L, P.contiguous(), ws, trans=True)             # L^-T Phi
+        St = trsm_lower_left_(L, Y.T.contiguous(), ws, trans=True)          # (Y L^-1)^T
+        return 0.5 * (St + St.T)
+
+
+class TriangularSolveFunction(torch.autograd.Function):
+    """X = op(L)^-1 B for a lower-triangular L (op = transpose when `trans`).  Backward:
+    Bbar = op(L)^-T Xbar;  Lbar = -tril(Bbar X^T)  (or -tril(X Bbar^T) when `trans`)."""
+
+    @staticmethod
+    def forward(ctx, L, B, trans, ws):
+        _check_mat(L, "L")
+        vec = B.dim() == 1
+        X = B.detach().reshape(L.shape[0], -1).clone().contiguous()
+        if vec:
+            X = trsv_lower_(L.detach(), X.reshape(-1), ws, trans=trans).reshape(-1, 1)
+        else:
+            X = trsm_lower_left_(L.detach(), X, ws, trans=trans)
+        ctx.trans, ctx.ws, ctx.vec = bool(trans), ws, vec
+        ctx.save_for_backward(L.detach(), X)
+        return X.reshape(-1) if vec else X
+
+    @staticmethod
+    def backward(ctx, Xbar):
+        L, X = ctx.saved_tensors
+        G = Xbar.detach().reshape(L.shape[0], -1).clone().contiguous()
+        if ctx.vec:
+            G = trsv_lower_(L, G.reshape(-1), ctx.ws, trans=not ctx.trans).reshape(-1, 1)
+        else:
+            G = trsm_lower_left_(L, G, ctx.ws, trans=not ctx.trans)
+        g_L = None
+        if ctx.needs_input_grad[0]:
+            outer = gemm(X, G) if ctx.trans else gemm(G, X)   # X Bbar^T  or  Bbar X^T
+            g_L = -torch.tril(outer)
+        g_B = (G.reshape(-1) if ctx.vec else G) if ctx.needs_input_grad[1] else None
+        return g_L, g_B, None, None

@@ -230,3 +230,46 @@ def test_reference_regression_golden_on_gpu():
     pred = opt.likelihood(opt.predict(dev(g["xtest"]), D))
     assert abs(pred.mean().sum().item() - float(g["reference_golden_predictive_mean_sum"])) < 1.0
     assert abs(pred.stddev().sum().item() - float(g["reference_golden_predictive_std_sum"])) < 1.0
+
+
+@pytest.mark.parametrize("n", [5, 300, 1300])
+def test_linalg_free_functions_are_differentiable(n):
+    """What jax.grad derives through lower_cholesky / solve / logdet (linalg/operations.py:22-181) and
+    GaussianDistribution.log_prob (distributions.py:115-134): compared with torch-CPU autograd of the same expressions."""
+    from gpjax_b200.distributions import GaussianDistribution
+    from gpjax_b200.linalg import Dense, logdet, lower_cholesky, psd, solve
+
+    rng = np.random.default_rng(n)
+    Xn = rng.uniform(-2, 2, (n, 3))
+    S0 = o.gram("rbf", Xn, np.array([0.8, 1.0, 1.3]), 1.0) + 0.3 * np.eye(n)
+    b0, B0, y0, m0 = rng.standard_normal(n), rng.standard_normal((n, 4)), rng.standard_normal(n), rng.standard_normal(n)
+
+    def expr(S, b, B, y, m, mine):
+        if mine:
+            L = lower_cholesky(psd(Dense(S)))
+            w = solve(L, b)                       # 1-D right-hand side, squeeze rule
+            V = solve(L.T, solve(L, B))           # Sigma^-1 B through the transposed view
+            ld = logdet(L)
+            lp = GaussianDistribution(m, psd(Dense(S))).log_prob(y)
+            L = L.array
+        else:
+            L = torch.linalg.cholesky(S)
+            w = torch.linalg.solve_triangular(L, b[:, None], upper=False)[:, 0]
+            V = torch.cholesky_solve(B, L)
+            ld = torch.log(torch.diagonal(L)).sum()
+            d = y - m
+            lp = -0.5 * (n * np.log(2 * np.pi) + torch.linalg.slogdet(S)[1] + d @ torch.linalg.solve(S, d))
+        return (w * w).sum() + 0.3 * (V * V).sum() + 2.0 * ld + 0.7 * lp + (L * L).sum() * 0.01
+
+    outs = []
+    for mine in (True, False):
+        mk = (lambda a: dev(a).requires_grad_(True)) if mine else (lambda a: torch.tensor(a, requires_grad=True))
+        leaves = [mk(a) for a in (S0, b0, B0, y0, m0)]
+        val = expr(*leaves, mine)
+        val.backward()
+        outs.append((val.item(), [t.grad.detach().cpu().numpy() for t in leaves]))
+    (v1, g1), (v2, g2) = outs
+    assert abs(v1 - v2) <= 1e-10 * abs(v2)
+    g1[0], g2[0] = 0.5 * (g1[0] + g1[0].T), 0.5 * (g2[0] + g2[0].T)  # only the symmetric part of dSigma is defined
+    for a, b in zip(g1, g2):
+        assert np.max(np.abs(a - b)) <= 1e-9 * max(np.max(np.abs(b)), 1.0)
