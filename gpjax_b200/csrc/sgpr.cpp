@@ -19,7 +19,10 @@ namespace gpb {
     } while (0)
 
 namespace {
-constexpr int SPLITK = 4;  // K-slices of the statistics SYRK (its output is only (M+2)^2: ~300 tiles)
+// K-slices of the statistics SYRK.  Its output is only (M+2)^2: 305 live 128x64 tiles at M = 2048 against 296 resident
+// CTAs, i.e. 1.03 waves per slice -- 4 slices run as 5 waves (82 % occupancy of the last-wave-quantised schedule),
+// 16 slices as 17 waves (97 %).  The partial sums accumulate across row blocks and are added up once per evaluation.
+constexpr int SPLITK = 16;
 struct Lay {
     int64_t fz, fb, mm[13], vec[9], sc, dots, T1, T2, gpart, info, ppart, total;
     int64_t fz_bytes, fb_bytes;
