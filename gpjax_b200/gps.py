@@ -62,7 +62,9 @@ class ConjugatePosterior(AbstractPosterior):
         sn = self.likelihood.obs_stddev.value.reshape(1)
         mx = self.prior.mean_function(train_data.X)
         mean_t = self.prior.mean_function(test_inputs)
-        fused = getattr(kern, "_b200_kind", None) is not None
+        from .objectives import _is_fused
+
+        fused = _is_fused(kern)
         if fused:
             kind, ell, var = kern._b200_kind, kern.lengthscale.value, kern.kernel_scalars()
             Sigma = ops.gram_forward(kind, x, x, ell, var, diag_add=self.jitter, diag_add_sq=sn, lower_only=True)

@@ -38,7 +38,12 @@ def _kernel_args(kernel):
 
 
 def _is_fused(kernel) -> bool:
-    return getattr(kernel, "_b200_kind", None) is not None
+    """True when `kernel.gram` is exactly one launch of the fused dense epilogue.  A kernel whose engine is not the plain
+    DenseKernelComputation (White's constant-diagonal engine, a user-supplied engine) goes through `kernel.gram` instead,
+    so that the engine's semantics are kept (computations/constant_diagonal.py:39-43 ignores coincident rows)."""
+    from .kernels.computations import DenseKernelComputation
+
+    return getattr(kernel, "_b200_kind", None) is not None and type(kernel.compute_engine) is DenseKernelComputation
 
 
 def _dense_sigma(posterior, data: Dataset):

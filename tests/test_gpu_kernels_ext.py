@@ -337,3 +337,19 @@ def test_fit_with_periodic_plus_white_kernel():
     assert hist[-1].item() < start - 5.0
     period = dict(opt.named_parameters())["prior.kernel.kernels[0].period"].value.item()
     assert abs(period - 1.5) < 0.1
+
+
+def test_white_kernel_objective_keeps_the_constant_diagonal_engine_semantics():
+    """White.gram goes through ConstantDiagonalKernelComputation (white.py:47, constant_diagonal.py:39-43): variance on the
+    diagonal even when rows coincide -- conjugate_mll must see that matrix, not the pairwise all-equal evaluation."""
+    import gpjax_b200 as gpx
+
+    X, y = data(60, 2, 5, dup=True)  # rows 1 and 30 coincide
+    post = gpx.gps.Prior(mean_function=gpx.mean_functions.Zero(), kernel=gpx.kernels.White(variance=0.7)) * \
+        gpx.likelihoods.Gaussian(num_datapoints=60, obs_stddev=0.4)
+    val = gpx.objectives.conjugate_mll(post, gpx.Dataset(X=dev(X), y=dev(y))).item()
+    s2 = 0.7 + 1e-6 + 0.16
+    ref = -0.5 * (60 * np.log(2 * np.pi * s2) + float((y**2).sum()) / s2)
+    assert abs(val - ref) <= 1e-10 * abs(ref)
+    Kc = gpx.kernels.White(variance=0.7).cross_covariance(dev(X), dev(X)).cpu().numpy()
+    assert Kc[1, 30] == 0.7 and Kc[30, 1] == 0.7  # the dense pairwise evaluation does see the coincidence
