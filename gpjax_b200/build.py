@@ -20,7 +20,7 @@ OUT_DIR = os.path.join(HERE, "lib")
 OBJ_DIR = os.path.join(OUT_DIR, "obj")
 LIB_PATH = os.path.join(OUT_DIR, "libgpjax_b200.so")
 
-CU_SOURCES = ["gemm_f64.cu", "gram.cu", "potrf_leaf.cu", "level2.cu", "sgpr_kernels.cu", "svgp_kernels.cu", "profile.cu"]
+CU_SOURCES = ["gemm_f64.cu", "gram.cu", "potrf_leaf.cu", "level2.cu", "sgpr_kernels.cu", "svgp_kernels.cu", "ozaki_i8.cu", "profile.cu"]
 CPP_SOURCES = ["algorithms.cpp", "sgpr.cpp", "abi.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
@@ -44,19 +44,40 @@ def _deps_mtime() -> float:
     return m
 
 
+def _local_deps(path: str, seen=None) -> set:
+    """`path` plus every quoted #include reachable from it (so one header edit rebuilds only its users)."""
+    import re
+
+    seen = set() if seen is None else seen
+    path = os.path.normpath(path)
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    for inc in re.findall(r'^\s*#\s*include\s+"([^"]+)"', open(path).read(), flags=re.M):
+        _local_deps(os.path.join(os.path.dirname(path), inc), seen)
+    return seen
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
     srcs = [s for s in CU_SOURCES + CPP_SOURCES if os.path.exists(os.path.join(CSRC, s))]
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _deps_mtime():
         return LIB_PATH
     nvcc = _nvcc()
+    flags_tag = " ".join(COMMON)
 
     def compile_one(src: str) -> str:
         obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
+        tag = obj + ".flags"
+        newest = max(os.path.getmtime(d) for d in _local_deps(os.path.join(CSRC, src)))
+        if (not force and os.path.exists(obj) and os.path.getmtime(obj) >= newest and os.path.exists(tag)
+                and open(tag).read() == flags_tag):
+            return obj
         cmd = [nvcc, *ARCH, *COMMON, "-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        open(tag, "w").write(flags_tag)
         if verbose and (r.stdout or r.stderr):
             print(r.stdout, r.stderr)
         return obj

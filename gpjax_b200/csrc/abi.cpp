@@ -132,6 +132,29 @@ int gpb_gemm(void* stream, int64_t M, int64_t N, int64_t K, double alpha, const 
     return gemm(stream, g);
 }
 
+int gpb_ozaki_available(void) { return ozaki_available() ? 1 : 0; }
+void gpb_set_ozaki_slices(int nslices) { set_ozaki_slices(nslices); }
+int gpb_get_ozaki_slices(void) { return get_ozaki_slices(); }
+int gpb_ozaki_slice(void* stream, int64_t rows, int64_t K, const double* X, int64_t ldx, int nslices, void* Q,
+                    int64_t ldq, double* scale) {
+    return ozaki_slice(stream, rows, K, X, ldx, nslices, static_cast<int8_t*>(Q), ldq, scale);
+}
+int gpb_ozaki_gemm(void* stream, int64_t M, int64_t N, int64_t K, int nslices, const void* Qa, int64_t ldqa,
+                   const double* scale_a, const void* Qb, int64_t ldqb, const double* scale_b, double alpha,
+                   double* C, int64_t ldc, int mask_lower) {
+    OzakiGemmDesc d;
+    d.M = M; d.N = N; d.K = K; d.nslices = nslices;
+    d.Qa = static_cast<const int8_t*>(Qa); d.ldqa = ldqa; d.sa = scale_a;
+    d.Qb = static_cast<const int8_t*>(Qb); d.ldqb = ldqb; d.sb = scale_b;
+    d.alpha = alpha; d.C = C; d.ldc = ldc; d.mask_lower = mask_lower;
+    return ozaki_gemm(stream, d);
+}
+int gpb_igemm_i8(void* stream, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
+                 int64_t ldb, void* C, int64_t ldc) {
+    return igemm_i8(stream, M, N, K, static_cast<const int8_t*>(A), lda, static_cast<const int8_t*>(B), ldb,
+                    static_cast<int32_t*>(C), ldc);
+}
+
 int64_t gpb_mll_workspace_bytes(int64_t N, int D) { return factor_ws_bytes(N, D, 1); }
 
 int gpb_mll_forward(void* stream, int kind, int64_t N, int D, const double* X, int64_t ldx, const double* y,

@@ -14,6 +14,8 @@
 // row-major lower/upper split gives for free.
 #include "algorithms.h"
 
+#include <cstdlib>
+
 namespace gpb {
 
 #define GPB_TRY(expr)                 \
@@ -23,11 +25,35 @@ namespace gpb {
     } while (0)
 
 // -------------------------------------------------------------------------------------------
+// Ozaki switch
+// -------------------------------------------------------------------------------------------
+namespace {
+int g_oz_slices = -1;  // -1: not initialised yet
+int clamp_slices(int v) { return (v >= 5 && v <= OZ_MAX_SLICES) ? v : 0; }
+}  // namespace
+void set_ozaki_slices(int nslices) { g_oz_slices = clamp_slices(nslices); }
+int get_ozaki_slices() {
+    if (g_oz_slices < 0) {
+        const char* e = std::getenv("GPB_OZAKI");
+        g_oz_slices = e ? clamp_slices(std::atoi(e)) : 0;
+    }
+    return g_oz_slices;
+}
+// digit planes to use for a rank-NB update with `rows` output rows, 0 = stay on the DMMA pipe
+static int oz_planes(const FactorWs& ws, int64_t rows) {
+    const int s = get_ozaki_slices();
+    if (s == 0 || !ws.oz_q || rows < OZ_MIN_ROWS || NB % 128 != 0 || !ozaki_available()) return 0;
+    return s;
+}
+
+// -------------------------------------------------------------------------------------------
 // workspace
 // -------------------------------------------------------------------------------------------
 namespace {
 struct WsLayout {
     int64_t off_dinv, off_dinvt, off_sdiag, off_panel, off_panel2, off_small, off_vec, off_scal, off_part, total;
+    int64_t off_ozq, off_ozq2, off_ozs, off_ozs2;
+    bool with_oz;
     int64_t partials_count;
 };
 WsLayout ws_layout(int64_t N, int D, int with_potri) {
@@ -49,6 +75,13 @@ WsLayout ws_layout(int64_t N, int D, int with_potri) {
     L.off_scal = take(16);
     L.partials_count = with_potri ? mll_bwd_partials_count(N, D > 0 ? D : 1, NB) : 0;
     L.off_part = take(L.partials_count);
+    // Ozaki digit buffers: OZ_MAX_SLICES * NB bytes per row == NB doubles per row (OZ_MAX_SLICES == 8)
+    L.with_oz = N >= OZ_MIN_ROWS + NB;
+    const int64_t qd = L.with_oz ? align_up(N, NB) * (OZ_MAX_SLICES * NB / 8) : 0;
+    L.off_ozq = take(qd);
+    L.off_ozq2 = take(qd);
+    L.off_ozs = take(L.with_oz ? align_up(N, NB) : 0);
+    L.off_ozs2 = take(L.with_oz ? align_up(N, NB) : 0);
     L.total = o;
     return L;
 }
@@ -74,6 +107,10 @@ int factor_ws_carve(void* buf, int64_t bytes, int64_t N, int D, int with_potri, 
     ws->scal = b + L.off_scal;
     ws->partials = with_potri ? b + L.off_part : nullptr;
     ws->partials_count = L.partials_count;
+    ws->oz_q = L.with_oz ? reinterpret_cast<int8_t*>(b + L.off_ozq) : nullptr;
+    ws->oz_q2 = L.with_oz ? reinterpret_cast<int8_t*>(b + L.off_ozq2) : nullptr;
+    ws->oz_scale = L.with_oz ? b + L.off_ozs : nullptr;
+    ws->oz_scale2 = L.with_oz ? b + L.off_ozs2 : nullptr;
     return GPB_OK;
 }
 
@@ -141,7 +178,7 @@ static int diag_block(stream_t s, int n, double* Ablk, int64_t lda, double* D, d
 // k+1 (diagonal-block factorisation + inverse, panel X = P inv(L)^T) runs on a high-priority side stream
 // while U2 -- >95 % of the step's flops -- keeps the SMs busy on the caller's stream.
 static int potrf_panel(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& ws, int* info, int64_t k,
-                       double* panel) {
+                       double* panel, int8_t* oz_q, double* oz_scale) {
     const int64_t j0 = k * NB;
     const int nbk = (int)((N - j0) < NB ? (N - j0) : NB);
     double* Dk = ws.Dinv + k * NB * NB;
@@ -154,7 +191,11 @@ static int potrf_panel(stream_t s, int64_t N, double* A, int64_t lda, const Fact
     g.A = P; g.lda = lda; g.B = Dk; g.ldb = NB; g.C = panel; g.ldc = NB;
     g.krange = KR_B_LOWER;
     GPB_TRY(gemm(s, g));
-    return copy2d(s, rows, nbk, panel, NB, P, lda);
+    GPB_TRY(copy2d(s, rows, nbk, panel, NB, P, lda));
+    // Ozaki path: digit planes of the panel, extracted on the stream that produced it (the side stream under lookahead)
+    const int planes = (nbk == NB) ? oz_planes(ws, rows) : 0;
+    if (planes) GPB_TRY(ozaki_slice(s, rows, NB, panel, NB, planes, oz_q, OZ_MAX_SLICES * NB, oz_scale));
+    return GPB_OK;
 }
 
 int potrf_lower(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& ws, int* info) {
@@ -164,32 +205,59 @@ int potrf_lower(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& w
     stream_t side = side_stream(s, 0);
     double* pcur = ws.panel;
     double* pnext = ws.panel2;
-    GPB_TRY(potrf_panel(s, N, A, lda, ws, info, 0, pcur));
+    int8_t* qcur = ws.oz_q;
+    int8_t* qnext = ws.oz_q2;
+    double* scur = ws.oz_scale;
+    double* snext = ws.oz_scale2;
+    const int64_t ldq = OZ_MAX_SLICES * NB;
+    GPB_TRY(potrf_panel(s, N, A, lda, ws, info, 0, pcur, qcur, scur));
     for (int64_t k = 0; k + 1 < nblk; ++k) {
         const int64_t j1 = (k + 1) * NB;        // first row/column of the trailing matrix
         const int64_t rows = N - j1;             // pcur holds X_k: rows x NB
         const int64_t nb1 = rows < NB ? rows : NB;
-        GemmDesc u;  // U1: next block column, A[j1:, j1:j1+nb1] -= X X[0:nb1]^T (lower part)
-        u.M = rows; u.N = nb1; u.K = NB;
-        u.A = pcur; u.lda = NB; u.B = pcur; u.ldb = NB;
-        u.C = A + j1 * lda + j1; u.ldc = lda;
-        u.alpha = -1.0; u.beta = 1.0; u.mask = MASK_LOWER;
-        GPB_TRY(gemm(s, u));
+        const int planes = oz_planes(ws, rows);  // same predicate potrf_panel used when it sliced X_k
+        // U1: next block column, A[j1:, j1:j1+nb1] -= X X[0:nb1]^T (lower part)
+        if (planes) {
+            OzakiGemmDesc u;
+            u.M = rows; u.N = nb1; u.K = NB; u.nslices = planes;
+            u.Qa = qcur; u.ldqa = ldq; u.sa = scur; u.Qb = qcur; u.ldqb = ldq; u.sb = scur;
+            u.C = A + j1 * lda + j1; u.ldc = lda; u.alpha = -1.0; u.mask_lower = 1;
+            GPB_TRY(ozaki_gemm(s, u));
+        } else {
+            GemmDesc u;
+            u.M = rows; u.N = nb1; u.K = NB;
+            u.A = pcur; u.lda = NB; u.B = pcur; u.ldb = NB;
+            u.C = A + j1 * lda + j1; u.ldc = lda;
+            u.alpha = -1.0; u.beta = 1.0; u.mask = MASK_LOWER;
+            GPB_TRY(gemm(s, u));
+        }
         const int64_t rest = rows - nb1;
         if (rest > 0) {
             GPB_TRY(stream_fork(s, side));
-            GPB_TRY(potrf_panel(side, N, A, lda, ws, info, k + 1, pnext));
-            GemmDesc v;  // U2: A[j1+nb1:, j1+nb1:] -= X[nb1:] X[nb1:]^T (lower part)
-            v.M = rest; v.N = rest; v.K = NB;
-            v.A = pcur + nb1 * NB; v.lda = NB; v.B = pcur + nb1 * NB; v.ldb = NB;
-            v.C = A + (j1 + nb1) * lda + (j1 + nb1); v.ldc = lda;
-            v.alpha = -1.0; v.beta = 1.0; v.mask = MASK_LOWER;
-            GPB_TRY(gemm(s, v));
+            GPB_TRY(potrf_panel(side, N, A, lda, ws, info, k + 1, pnext, qnext, snext));
+            // U2: A[j1+nb1:, j1+nb1:] -= X[nb1:] X[nb1:]^T (lower part)
+            if (planes) {
+                OzakiGemmDesc v;
+                v.M = rest; v.N = rest; v.K = NB; v.nslices = planes;
+                v.Qa = qcur + nb1 * ldq; v.ldqa = ldq; v.sa = scur + nb1;
+                v.Qb = v.Qa; v.ldqb = ldq; v.sb = v.sa;
+                v.C = A + (j1 + nb1) * lda + (j1 + nb1); v.ldc = lda; v.alpha = -1.0; v.mask_lower = 1;
+                GPB_TRY(ozaki_gemm(s, v));
+            } else {
+                GemmDesc v;
+                v.M = rest; v.N = rest; v.K = NB;
+                v.A = pcur + nb1 * NB; v.lda = NB; v.B = pcur + nb1 * NB; v.ldb = NB;
+                v.C = A + (j1 + nb1) * lda + (j1 + nb1); v.ldc = lda;
+                v.alpha = -1.0; v.beta = 1.0; v.mask = MASK_LOWER;
+                GPB_TRY(gemm(s, v));
+            }
             GPB_TRY(stream_fork(side, s));
         } else {
-            GPB_TRY(potrf_panel(s, N, A, lda, ws, info, k + 1, pnext));
+            GPB_TRY(potrf_panel(s, N, A, lda, ws, info, k + 1, pnext, qnext, snext));
         }
         double* t = pcur; pcur = pnext; pnext = t;
+        int8_t* tq = qcur; qcur = qnext; qnext = tq;
+        double* ts = scur; scur = snext; snext = ts;
     }
     return GPB_OK;
 }

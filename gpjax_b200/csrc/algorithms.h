@@ -18,6 +18,16 @@ constexpr int64_t LEAFN = 128; // leaf size handled by potrf_leaf
 inline int64_t nblocks(int64_t n) { return (n + NB - 1) / NB; }
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
+// ---- runtime switch: digit planes of the Ozaki (int8 tensor pipe) trailing updates; 0 = FP64 DMMA everywhere (default).
+// Read from the environment variable GPB_OZAKI at first use, overridable through set_ozaki_slices.
+void set_ozaki_slices(int nslices);
+int get_ozaki_slices();
+constexpr int OZ_MAX_SLICES = 8;
+#ifndef GPB_OZ_MIN_ROWS
+#define GPB_OZ_MIN_ROWS 2048
+#endif
+constexpr int64_t OZ_MIN_ROWS = GPB_OZ_MIN_ROWS;  // smaller updates stay on the DMMA pipe (launch + slicing overhead dominates)
+
 // ---- workspace for the exact-GP factorisation family --------------------------------------
 struct FactorWs {
     double* Dinv = nullptr;   // nblk blocks [NB x NB], inverse of the diagonal blocks of L
@@ -30,6 +40,12 @@ struct FactorWs {
     double* scal = nullptr;   // 16 scalars
     double* partials = nullptr;
     int64_t partials_count = 0;
+    // Ozaki path (null when N < OZ_MIN_ROWS + NB): two digit buffers [N x OZ_MAX_SLICES*NB] int8 and two row-scale vectors
+    // (double-buffered like panel / panel2 so the lookahead may slice panel k+1 while update k still reads panel k)
+    int8_t* oz_q = nullptr;
+    int8_t* oz_q2 = nullptr;
+    double* oz_scale = nullptr;
+    double* oz_scale2 = nullptr;
 };
 // bytes needed for an N x N problem with D input dims (with_potri: include Sdiag + backward partials)
 int64_t factor_ws_bytes(int64_t N, int D, int with_potri);

@@ -1,0 +1,470 @@
+// FP64 rank-k updates on the INT8 tensor pipe (Ozaki scheme) -- tcgen05.mma kind::i8, TMA-fed, TMEM accumulators.
+//
+// Why: every O(N^3) flop of the exact-GP path (reference call site: jnp.linalg.cholesky, gpjax/linalg/operations.py:54-55,
+// and the reverse-mode solve it implies) is a rank-NB update C += alpha * A B^T.  The FP64 tensor instruction of sm_100a
+// (DMMA.8x8x4) peaks at 37 TFLOP/s; the int8 tcgen05 pipe of the same chip is ~100x wider.  Splitting every fp64 operand
+// row into `s` signed 7-bit digits after an exact power-of-two row scaling,
+//      x_ik = 2^e_i * sum_p q^(p)_ik * 2^(-7 (p+1)),      |q| <= 64,
+// makes every digit-pair product an EXACT integer GEMM (int8 x int8 -> int32), and the fp64 result is recovered as
+//      (A B^T)_ij ~= 2^(ea_i + eb_j) * sum_{t < s} 2^(-7 (t+2)) * sum_{p+q = t} (Q_a^(p) Q_b^(q)^T)_ij .
+// All pairs of equal order t share one scale, so they are accumulated inside ONE int32 TMEM accumulator (|sum| <=
+// (t+1) k 64^2 < 2^31 for k <= 2^15), i.e. s accumulator passes per output tile instead of s (s+1) / 2 separate GEMMs.
+// The truncation error is bounded by the dropped orders: <= (s+1) 2^(-7 s) |a_i|_inf |b_j|_inf k  (s = 7: 2^-46 per entry
+// relative to the row maxima -- measured against the DMMA product in tests/test_gpu_ozaki.py and DESIGN section 12).
+//
+// Kernel (persistent, one CTA per SM, 12 warps, warp-specialised):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d of 128 x 128-byte digit tiles (SWIZZLE_128B) into a 6-stage ring
+//   warp 1      MMA issuer  : one thread issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=128, K=32 per instruction),
+//                             tcgen05.commit releases ring slots / publishes accumulators through mbarriers
+//   warp 2      TMEM allocator (512 columns = 4 accumulator stages of 128 x 128 int32)
+//   warps 4-11  epilogue    : tcgen05.ld the int32 accumulator of order t, convert exactly to fp64, scale by 2^(-7 (t+2)) and
+//                             add into per-thread fp64 registers (64 per thread) while the MMA warp already works on
+//                             order t+1; after the last order: C -= / += 2^(ea_i + eb_j) * acc, masked, ONE read-modify-write
+//                             of the fp64 tile in HBM.
+// The digit tiles are addressed directly in the [rows, s*k] digit matrix by TMA coordinates, so A and B may be the same
+// buffer (SYRK) and no order-reversed copy exists.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace gpb {
+namespace {
+
+constexpr int OZ_BM = 128, OZ_BN = 128, OZ_BK = 128;  // BK in bytes == int8 elements == one 128-byte swizzle row
+constexpr int OZ_STAGES = 6;
+constexpr int OZ_STAGE_BYTES = (OZ_BM + OZ_BN) * OZ_BK;  // 32 KB
+constexpr int OZ_ACC_STAGES = 4;                         // x 128 TMEM columns
+constexpr int OZ_THREADS = 384;
+constexpr int OZ_EPI_WARP0 = 4, OZ_EPI_WARPS = 8;
+constexpr int OZ_CHUNK_TILES = 32;  // output tile columns walked together so their B digits stay L2-resident
+constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int OZ_BETA = 7;
+
+struct OzParams {
+    int m, n;             // output extents
+    int kblocks;          // k / 128 per digit plane
+    int nslices;          // digit planes used (1 in raw mode)
+    int mask_lower;       // write only (row0 + i) >= (col0 + j)
+    long long row0, col0;
+    double* C;            // fp64 in/out (MODE 1)
+    long long ldc;
+    int* Ci;              // int32 out (MODE 0)
+    long long ldci;
+    const double* sa;     // 2^ea_i
+    const double* sb;     // 2^eb_j
+    double alpha;
+    int ntm, ntn;
+};
+
+// ---- tile enumeration shared by the three roles: column chunks -> tile rows -> tile columns, dead tiles of the lower
+// mask never enumerated ----------------------------------------------------------------------------------------------
+struct TileWalk {
+    int chunk = 0, tm = 0, c0 = 0, c1 = 0;
+    long long base = 0;  // linear index of the first tile of (chunk, tm)
+    __device__ int live_end(const OzParams& p, int tm_) const {  // one past the last live tile column of tile row tm_
+        if (!p.mask_lower) return p.ntn;
+        long long last_row = p.row0 + (long long)tm_ * OZ_BM + OZ_BM - 1;
+        long long d = last_row - p.col0;
+        if (d < 0) return 0;
+        long long e = d / OZ_BN + 1;
+        return e < p.ntn ? (int)e : p.ntn;
+    }
+    __device__ int count(const OzParams& p) const {
+        int e = live_end(p, tm);
+        int hi = e < c1 ? e : c1;
+        return hi > c0 ? hi - c0 : 0;
+    }
+    __device__ void set_chunk(const OzParams& p, int ch) {
+        chunk = ch;
+        c0 = ch * OZ_CHUNK_TILES;
+        c1 = c0 + OZ_CHUNK_TILES < p.ntn ? c0 + OZ_CHUNK_TILES : p.ntn;
+        tm = 0;
+    }
+    __device__ void init(const OzParams& p) { set_chunk(p, 0); base = 0; }
+    // advance to the tile with linear index idx (monotonically increasing calls); false when past the end
+    __device__ bool seek(const OzParams& p, long long idx, int& tm_out, int& tn_out) {
+        const int nchunks = (p.ntn + OZ_CHUNK_TILES - 1) / OZ_CHUNK_TILES;
+        while (true) {
+            if (chunk >= nchunks) return false;
+            int cnt = count(p);
+            if (idx < base + cnt) {
+                tm_out = tm;
+                tn_out = c0 + (int)(idx - base);
+                return true;
+            }
+            base += cnt;
+            if (++tm >= p.ntm) set_chunk(p, chunk + 1);
+        }
+    }
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps (-> launch error) instead of hanging the device
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, unsigned parity) {
+    if (mbar_try(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try(bar, parity)) {
+        if (clock64() - t0 > 8000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(unsigned tmem_d, uint64_t adesc, uint64_t bdesc, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(unsigned taddr, unsigned (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
+// K-major operand tile in shared memory: rows of 128 bytes, 8-row groups 1024 bytes apart, 128-byte swizzle
+// (what TMA SWIZZLE_128B writes for a {128 B, rows} box into a 1024-byte aligned buffer).
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(unsigned saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address, 16-byte units           bits [0,14)
+    d |= (uint64_t)1 << 16;                    // leading byte offset (unused: swizzled)  bits [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset: 8 rows x 128 B      bits [32,46)
+    d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)             bits [46,48)
+    d |= (uint64_t)2 << 61;                    // SWIZZLE_128B                            bits [61,64)
+    return d;
+}
+// instruction descriptor: D = s32, A = B = signed int8, both K-major, N = 128, M = 128
+constexpr unsigned OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(OZ_BN >> 3) << 17) | ((unsigned)(OZ_BM >> 4) << 24);
+
+__device__ __forceinline__ double exact_i2d(int v) {  // exact int32 -> fp64 on the FP64 add pipe (no I2F)
+    return __hiloint2double(0x43300000, (int)((unsigned)v ^ 0x80000000u)) - 4503601774854144.0;  // 2^52 + 2^31
+}
+
+// MODE 0: Ci = A B^T (raw int32, test / building block); MODE 1: C += alpha * 2^(ea+eb) * sum_t 2^(-7(t+2)) P_t
+template <int MODE>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const OzParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const unsigned raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OZ_STAGES * OZ_STAGE_BYTES);
+    uint64_t* full = bars;                         // [STAGES]   TMA -> MMA
+    uint64_t* empty = bars + OZ_STAGES;            // [STAGES]   MMA -> TMA
+    uint64_t* tfull = bars + 2 * OZ_STAGES;        // [ACC]      MMA -> epilogue
+    uint64_t* tempty = tfull + OZ_ACC_STAGES;      // [ACC]      epilogue -> MMA
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty + OZ_ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < OZ_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < OZ_ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], OZ_EPI_WARPS); }
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem_base = *tmem_slot;
+
+    const int groups = MODE == 0 ? 1 : p.nslices;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ===== TMA producer =====
+            TileWalk w; w.init(p);
+            int stage = 0; unsigned phase = 0;
+            int tm, tn;
+            for (long long idx = blockIdx.x; w.seek(p, idx, tm, tn); idx += gridDim.x) {
+                const int m0 = tm * OZ_BM, n0 = tn * OZ_BN;
+                for (int t = 0; t < groups; ++t) {
+                    for (int pa = 0; pa <= t; ++pa) {
+                        const int xa0 = pa * p.kblocks * OZ_BK, xb0 = (t - pa) * p.kblocks * OZ_BK;
+                        for (int kb = 0; kb < p.kblocks; ++kb) {
+                            mbar_wait_bounded(&empty[stage], phase ^ 1u);
+                            uint8_t* sA = smem + stage * OZ_STAGE_BYTES;
+                            mbar_arrive_expect_tx(&full[stage], OZ_STAGE_BYTES);
+                            tma_load_2d(sA, &tmA, &full[stage], xa0 + kb * OZ_BK, m0);
+                            tma_load_2d(sA + OZ_BM * OZ_BK, &tmB, &full[stage], xb0 + kb * OZ_BK, n0);
+                            if (++stage == OZ_STAGES) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ===== MMA issuer =====
+            TileWalk w; w.init(p);
+            int stage = 0; unsigned phase = 0;
+            int acc = 0; unsigned aphase = 0;
+            int tm, tn;
+            for (long long idx = blockIdx.x; w.seek(p, idx, tm, tn); idx += gridDim.x) {
+                for (int t = 0; t < groups; ++t) {
+                    mbar_wait_bounded(&tempty[acc], aphase ^ 1u);
+                    tc_fence_after();
+                    const unsigned d_tmem = tmem_base + (unsigned)(acc * OZ_BN);
+                    const int nkb = (t + 1) * p.kblocks;
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait_bounded(&full[stage], phase);
+                        tc_fence_after();
+                        const unsigned sA = smem_u32(smem + stage * OZ_STAGE_BYTES);
+                        const uint64_t da = umma_desc_k_sw128(sA), db = umma_desc_k_sw128(sA + OZ_BM * OZ_BK);
+#pragma unroll
+                        for (int kk = 0; kk < OZ_BK / 32; ++kk)  // +32 bytes along K inside the swizzle row = +2 in the address field
+                            tc_mma_i8(d_tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), OZ_IDESC, (kb | kk) != 0);
+                        tc_commit(&empty[stage]);  // frees the ring slot once these MMAs have read it
+                        if (++stage == OZ_STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                    tc_commit(&tfull[acc]);  // accumulator of order t complete
+                    if (++acc == OZ_ACC_STAGES) { acc = 0; aphase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp >= OZ_EPI_WARP0) {
+        // ===== epilogue: warp (4 + 4 h + q) owns TMEM lanes [32 q, 32 q + 32) and tile columns [64 h, 64 h + 64) =====
+        const int q = warp & 3, h = (warp - OZ_EPI_WARP0) >> 2;
+        TileWalk w; w.init(p);
+        int acc = 0; unsigned aphase = 0;
+        int tm, tn;
+        for (long long idx = blockIdx.x; w.seek(p, idx, tm, tn); idx += gridDim.x) {
+            const int row = tm * OZ_BM + q * 32 + lane;
+            const int col0 = tn * OZ_BN + h * 64;
+            double accd[MODE == 1 ? 64 : 1];
+            if (MODE == 1) {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) accd[j] = 0.0;
+            }
+            for (int t = 0; t < groups; ++t) {
+                mbar_wait_bounded(&tfull[acc], aphase);
+                tc_fence_after();
+                const double sc = __hiloint2double((1023 - OZ_BETA * (t + 2)) << 20, 0);  // 2^(-7 (t+2))
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    unsigned r[32];
+                    tc_ld32(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(acc * OZ_BN + h * 64 + c * 32), r);
+                    if (MODE == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) accd[c * 32 + j] = fma(exact_i2d((int)r[j]), sc, accd[c * 32 + j]);
+                    } else {
+                        if (row < p.m) {
+                            int* dst = p.Ci + (long long)row * p.ldci + col0 + c * 32;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + c * 32 + j < p.n) dst[j] = (int)r[j];
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
+                if (++acc == OZ_ACC_STAGES) { acc = 0; aphase ^= 1u; }
+            }
+            if (MODE == 1 && row < p.m) {
+                const double sr = p.alpha * __ldg(p.sa + row);
+                double* crow = p.C + (long long)row * p.ldc;
+                const long long grow = p.row0 + row;
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                    const int col = col0 + j;
+                    if (col < p.n && (!p.mask_lower || grow >= p.col0 + col)) crow[col] += accd[j] * (sr * __ldg(p.sb + col));
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---- digit extraction ----------------------------------------------------------------------------------------------
+// one CTA per row: exponent from the row maximum, then `s` rounds of  R <- 128 R;  q = rint(R);  R <- R - q  (all exact)
+__global__ void __launch_bounds__(128) ozaki_slice_kernel(long long rows, int k, const double* __restrict__ X, long long ldx,
+                                                          int nslices, signed char* __restrict__ Q, long long ldq,
+                                                          double* __restrict__ scale) {
+    __shared__ double red[4];
+    const long long r = blockIdx.x;
+    if (r >= rows) return;
+    const double* x = X + r * ldx;
+    double mx = 0.0;
+    bool bad = false;
+    for (int c = threadIdx.x; c < k; c += 128) {
+        double v = fabs(x[c]);
+        bad |= !(v <= 1.7976931348623157e308);  // NaN or Inf
+        mx = fmax(mx, v);
+    }
+    mx = bad ? __longlong_as_double(0x7ff8000000000000LL) : mx;
+    // NaN-propagating max across the CTA
+    for (int o = 16; o > 0; o >>= 1) {
+        double other = __shfl_xor_sync(0xffffffffu, mx, o);
+        mx = (mx != mx || other != other) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(mx, other);
+    }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int i = 1; i < 4; ++i) mx = (mx != mx || red[i] != red[i]) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(mx, red[i]);
+    int e = 0;
+    double sc;
+    if (mx != mx) {
+        sc = mx;  // NaN row scale: the product becomes NaN (JAX semantics for a failed factorisation)
+    } else if (mx == 0.0) {
+        sc = 1.0;
+    } else {
+        e = ilogb(mx) + 2;  // |x| 2^-e < 1/2
+        sc = scalbn(1.0, e);
+    }
+    if (threadIdx.x == 0) scale[r] = sc;
+    signed char* qrow = Q + r * ldq;
+    for (int c = threadIdx.x; c < k; c += 128) {
+        double R = (mx != mx) ? 0.0 : scalbn(x[c], -e);
+        for (int p = 0; p < nslices; ++p) {
+            R *= 128.0;
+            double d = rint(R);
+            qrow[(long long)p * k + c] = (signed char)(int)d;
+            R -= d;
+        }
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
+        if (f && q != cudaDriverEntryPointSuccess) f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+// digit matrix [rows, width] int8, row stride ld bytes -> 2-D map with a {128 B, 128 rows} box
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t width, int64_t ld) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return GPB_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 15)) return GPB_ERR_INVALID;
+    cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld};
+    cuuint32_t box[2] = {(cuuint32_t)OZ_BK, (cuuint32_t)OZ_BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? GPB_OK : GPB_ERR_INVALID;
+}
+int sm_count() {
+    static int n = [] {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+        return v;
+    }();
+    return n;
+}
+template <int MODE>
+int launch(stream_t s, const CUtensorMap& ta, const CUtensorMap& tb, OzParams& p) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(ozaki_i8_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES) != cudaSuccess)
+            return GPB_ERR_LAUNCH;
+        attr_set = true;
+    }
+    p.ntm = (p.m + OZ_BM - 1) / OZ_BM;
+    p.ntn = (p.n + OZ_BN - 1) / OZ_BN;
+    long long tiles = (long long)p.ntm * p.ntn;  // upper bound on the live tiles; CTAs beyond the live count exit at once
+    int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    if (grid <= 0) return GPB_OK;
+    ozaki_i8_kernel<MODE><<<grid, OZ_THREADS, OZ_SMEM_BYTES, to_stream(s)>>>(ta, tb, p);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+}  // namespace
+
+int ozaki_slice(stream_t s, int64_t rows, int64_t k, const double* X, int64_t ldx, int nslices, int8_t* Q, int64_t ldq,
+                double* scale) {
+    if (rows < 0 || k <= 0 || nslices < 1 || nslices > 8 || !X || !Q || !scale || ldq < (int64_t)nslices * k) return GPB_ERR_INVALID;
+    if (rows == 0) return GPB_OK;
+    ozaki_slice_kernel<<<(unsigned)rows, 128, 0, to_stream(s)>>>(rows, (int)k, X, ldx, nslices, reinterpret_cast<signed char*>(Q),
+                                                                 ldq, scale);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+int igemm_i8(stream_t s, int64_t m, int64_t n, int64_t k, const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb, int32_t* C,
+             int64_t ldc) {
+    if (m < 0 || n < 0 || k <= 0 || !A || !B || !C) return GPB_ERR_INVALID;
+    if (k % OZ_BK) return GPB_ERR_UNSUPPORTED;
+    if (m == 0 || n == 0) return GPB_OK;
+    CUtensorMap ta, tb;
+    int rc = make_map(&ta, A, m, k, lda);
+    if (rc) return rc;
+    rc = make_map(&tb, B, n, k, ldb);
+    if (rc) return rc;
+    OzParams p = {};
+    p.m = (int)m; p.n = (int)n; p.kblocks = (int)(k / OZ_BK); p.nslices = 1;
+    p.Ci = C; p.ldci = ldc;
+    return launch<0>(s, ta, tb, p);
+}
+
+int ozaki_gemm(stream_t s, const OzakiGemmDesc& d) {
+    if (d.M < 0 || d.N < 0 || d.K <= 0 || d.nslices < 1 || d.nslices > 8 || !d.Qa || !d.Qb || !d.sa || !d.sb || !d.C)
+        return GPB_ERR_INVALID;
+    if (d.K % OZ_BK || d.K > 32768) return GPB_ERR_UNSUPPORTED;
+    if (d.M == 0 || d.N == 0) return GPB_OK;
+    CUtensorMap ta, tb;
+    int rc = make_map(&ta, d.Qa, d.M, (int64_t)d.nslices * d.K, d.ldqa);
+    if (rc) return rc;
+    rc = make_map(&tb, d.Qb, d.N, (int64_t)d.nslices * d.K, d.ldqb);
+    if (rc) return rc;
+    OzParams p = {};
+    p.m = (int)d.M; p.n = (int)d.N; p.kblocks = (int)(d.K / OZ_BK); p.nslices = d.nslices;
+    p.mask_lower = d.mask_lower; p.row0 = d.mask_row0; p.col0 = d.mask_col0;
+    p.C = d.C; p.ldc = d.ldc; p.sa = d.sa; p.sb = d.sb; p.alpha = d.alpha;
+    return launch<1>(s, ta, tb, p);
+}
+
+bool ozaki_available() { return encode_tiled() != nullptr; }
+
+}  // namespace gpb

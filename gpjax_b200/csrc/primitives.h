@@ -251,6 +251,34 @@ int svgp_gw_diag(stream_t s, int64_t M, const double* W, int64_t ldw, double* gW
 int svgp_scalar_grads(stream_t s, const double* sc, const double* dots, const double* dots2, const double* variance,
                       const double* obs_stddev, double jitter, double* g_var, double* g_obs, double* g_mean);
 
+// ---- FP64 rank-k updates on the INT8 tensor pipe (Ozaki scheme; ozaki_i8.cu) ---------------------------------------
+// x_ik = scale_i * sum_p Q[i, p*k + c] * 2^(-7 (p+1)),  scale_i = 2^e_i,  |Q| <= 64: `nslices` signed 7-bit digit planes
+// per entry, plane p stored at columns [p*k, (p+1)*k) of the int8 matrix Q (row stride ldq >= nslices*k bytes, multiple
+// of 16; Q 16-byte aligned).  Exact (no rounding) while nslices*7 covers the mantissa; a NaN/Inf row gets scale = NaN.
+int ozaki_slice(stream_t s, int64_t rows, int64_t k, const double* X, int64_t ldx, int nslices, int8_t* Q, int64_t ldq,
+                double* scale);
+struct OzakiGemmDesc {
+    int64_t M = 0, N = 0, K = 0;  // K = digits per plane (multiple of 128)
+    int nslices = 7;
+    const int8_t* Qa = nullptr;   // [M, nslices*K]
+    int64_t ldqa = 0;
+    const double* sa = nullptr;   // [M] row scales
+    const int8_t* Qb = nullptr;   // [N, nslices*K]
+    int64_t ldqb = 0;
+    const double* sb = nullptr;   // [N]
+    double* C = nullptr;          // C += alpha * A B^T (all digit pairs of order p+q < nslices)
+    int64_t ldc = 0;
+    double alpha = 1.0;
+    int mask_lower = 0;           // only entries with mask_row0 + i >= mask_col0 + j are touched
+    int64_t mask_row0 = 0, mask_col0 = 0;
+};
+int ozaki_gemm(stream_t s, const OzakiGemmDesc& d);
+// C[m,n] (int32) = A[m,k] B[n,k]^T for int8 operands (k multiple of 128, lda/ldb multiples of 16): the raw tcgen05 product
+int igemm_i8(stream_t s, int64_t m, int64_t n, int64_t k, const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb,
+             int32_t* C, int64_t ldc);
+// false when the driver cannot encode TMA tensor maps (then the blocked algorithms stay on the DMMA path)
+bool ozaki_available();
+
 // ---- intra-call concurrency (lookahead) ---------------------------------------------------------------
 // side_stream: a lazily created, higher-priority helper stream of the current device (index 0..3).
 // stream_fork(from, to): everything enqueued on `to` afterwards waits for what is on `from` now

@@ -224,6 +224,54 @@ def gemm(A, B, C=None, alpha=1.0, beta=0.0, a_layout=0, b_layout=0, mask=0):
 # ------------------------------------------------------------------------------------------
 # conjugate_mll: fused forward + analytic backward
 # ------------------------------------------------------------------------------------------
+# ---- FP64 products on the INT8 tensor pipe (Ozaki scheme; csrc/ozaki_i8.cu) ------------------------------------------
+def ozaki_available() -> bool:
+    return bool(lib().gpb_ozaki_available())
+
+
+def set_ozaki_slices(nslices: int) -> None:
+    """0: every blocked algorithm stays on the FP64 DMMA pipe (default); 5..8: rank-NB trailing updates of
+    ``lower_cholesky`` run as exact int8 digit-plane products (``tcgen05.mma kind::i8``) with that many planes."""
+    lib().gpb_set_ozaki_slices(int(nslices))
+
+
+def get_ozaki_slices() -> int:
+    return int(lib().gpb_get_ozaki_slices())
+
+
+def ozaki_slice(X: torch.Tensor, nslices: int):
+    """(Q int8 [rows, nslices*K], scale [rows]) digit planes of a row-major fp64 panel."""
+    _check_mat(X, "X")
+    rows, k = X.shape
+    Q = torch.empty((rows, nslices * k), dtype=torch.int8, device=X.device)
+    scale = torch.empty(rows, dtype=torch.float64, device=X.device)
+    rc = lib().gpb_ozaki_slice(_stream(), rows, k, _p(X), X.stride(0), int(nslices), _p(Q), Q.stride(0), _p(scale))
+    _abi.check(rc, "gpb_ozaki_slice")
+    return Q, scale
+
+
+def ozaki_gemm_(C: torch.Tensor, Qa, sa, Qb, sb, K: int, nslices: int, alpha: float = 1.0, mask_lower: bool = False):
+    """C += alpha * A B^T from digit planes (in place)."""
+    _check_mat(C, "C")
+    rc = lib().gpb_ozaki_gemm(_stream(), C.shape[0], C.shape[1], int(K), int(nslices), _p(Qa), Qa.stride(0), _p(sa),
+                              _p(Qb), Qb.stride(0), _p(sb), float(alpha), _p(C), C.stride(0), int(mask_lower))
+    _abi.check(rc, "gpb_ozaki_gemm")
+    return C
+
+
+def igemm_i8(A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    """int32 [m, n] = A[m, k] B[n, k]^T for int8 CUDA operands (the raw tcgen05 kind::i8 product)."""
+    if A.dtype != torch.int8 or B.dtype != torch.int8 or not A.is_cuda or not B.is_cuda:
+        raise TypeError("igemm_i8 takes int8 CUDA tensors")
+    if A.stride(1) != 1 or B.stride(1) != 1 or A.shape[1] != B.shape[1]:
+        raise ValueError("operands must be K-contiguous with equal K")
+    Cc = torch.empty((A.shape[0], B.shape[0]), dtype=torch.int32, device=A.device)
+    rc = lib().gpb_igemm_i8(_stream(), A.shape[0], B.shape[0], A.shape[1], _p(A), A.stride(0), _p(B), B.stride(0), _p(Cc),
+                            Cc.stride(0))
+    _abi.check(rc, "gpb_igemm_i8")
+    return Cc
+
+
 class _MllState:
     """Per-(device, N, D) buffers reused across iterations: the N x N Sigma/L/Sigma^-1 buffer and
     the factorisation workspace.  `generation` guards against backward being called on a stale

@@ -110,6 +110,30 @@ int gpb_gemm(void* stream, int64_t M, int64_t N, int64_t K, double alpha, const 
              int a_layout, const double* B, int64_t ldb, int b_layout, double beta, double* C, int64_t ldc,
              int mask);
 
+/* ---- FP64 rank-k updates on the INT8 tensor pipe (Ozaki scheme; tcgen05.mma kind::i8) --------------------------
+ * Building blocks of gpb_potrf_lower / gpb_potri_lower, i.e. still jnp.linalg.cholesky (gpjax/linalg/operations.py:54-55)
+ * and the inverse its reverse mode needs -- there is no separate reference function.  An fp64 operand row is split
+ * exactly into `nslices` signed 7-bit digit planes after a power-of-two row scaling (gpb_ozaki_slice); every
+ * digit-pair product is an exact int8 x int8 -> int32 GEMM on the tcgen05 pipe and gpb_ozaki_gemm recombines the
+ * orders p+q < nslices in fp64:  C += alpha * A B^T  up to a truncation error of (nslices+1) 2^(-7 nslices) K relative
+ * to the row maxima (nslices = 7: below fp64 rounding of a K = 1024 product).
+ *   Q        : int8 [rows, nslices*K], plane p at columns [p*K, (p+1)*K); 16-byte aligned, ldq multiple of 16
+ *   scale    : fp64 [rows], 2^e_i (NaN for a row holding NaN/Inf -> NaN output, JAX semantics)
+ *   K        : multiple of 128
+ * gpb_igemm_i8 exposes the raw integer product (C int32 = A B^T) for bit-exact testing.
+ * gpb_set_ozaki_slices(s): s in {0, 5..8}; 0 (default) keeps every blocked algorithm on the FP64 DMMA pipe, otherwise
+ * the rank-NB trailing updates of the factorisation family run through gpb_ozaki_gemm with s digit planes. */
+int gpb_ozaki_available(void);
+void gpb_set_ozaki_slices(int nslices);
+int gpb_get_ozaki_slices(void);
+int gpb_ozaki_slice(void* stream, int64_t rows, int64_t K, const double* X, int64_t ldx, int nslices, void* Q,
+                    int64_t ldq, double* scale);
+int gpb_ozaki_gemm(void* stream, int64_t M, int64_t N, int64_t K, int nslices, const void* Qa, int64_t ldqa,
+                   const double* scale_a, const void* Qb, int64_t ldqb, const double* scale_b, double alpha,
+                   double* C, int64_t ldc, int mask_lower);
+int gpb_igemm_i8(void* stream, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,
+                 int64_t ldb, void* C, int64_t ldc);
+
 /* ---- conjugate_mll value + analytic gradient -----------------------------------------------------
  * Forward = gpjax/objectives.py:93-107 + GaussianDistribution.log_prob (gpjax/distributions.py:124-134):
  *   Sigma = K(X,X) + (jitter + obs_stddev^2) I,  value = -1/2 (N log 2pi + logdet Sigma + d^T Sigma^-1 d),

@@ -456,6 +456,71 @@ int sgpr_scalar_grads(stream_t, const double* sc, const double* dots, const doub
 }
 }  // namespace gpb
 
+// ---- Ozaki (int8 digit plane) primitives: exact integer model of ozaki_i8.cu ------------------------------------
+namespace gpb {
+int ozaki_slice(stream_t, int64_t rows, int64_t k, const double* X, int64_t ldx, int nslices, int8_t* Q, int64_t ldq,
+                double* scale) {
+    if (rows < 0 || k <= 0 || nslices < 1 || nslices > 8 || !X || !Q || !scale || ldq < (int64_t)nslices * k) return GPB_ERR_INVALID;
+    for (int64_t r = 0; r < rows; ++r) {
+        double mx = 0.0;
+        bool bad = false;
+        for (int64_t c = 0; c < k; ++c) {
+            double v = std::fabs(X[r * ldx + c]);
+            if (!(v <= std::numeric_limits<double>::max())) bad = true;
+            if (v > mx) mx = v;
+        }
+        int e = 0;
+        if (bad) scale[r] = std::numeric_limits<double>::quiet_NaN();
+        else if (mx == 0.0) scale[r] = 1.0;
+        else { e = std::ilogb(mx) + 2; scale[r] = std::scalbn(1.0, e); }
+        for (int64_t c = 0; c < k; ++c) {
+            double R = bad ? 0.0 : std::scalbn(X[r * ldx + c], -e);
+            for (int p = 0; p < nslices; ++p) {
+                R *= 128.0;
+                double d = std::nearbyint(R);
+                Q[r * ldq + (int64_t)p * k + c] = (int8_t)(int)d;
+                R -= d;
+            }
+        }
+    }
+    return GPB_OK;
+}
+int ozaki_gemm(stream_t, const OzakiGemmDesc& d) {
+    if (d.M < 0 || d.N < 0 || d.K <= 0 || d.nslices < 1 || d.nslices > 8 || !d.Qa || !d.Qb || !d.sa || !d.sb || !d.C)
+        return GPB_ERR_INVALID;
+    if (d.K % 128) return GPB_ERR_UNSUPPORTED;
+    for (int64_t i = 0; i < d.M; ++i)
+        for (int64_t j = 0; j < d.N; ++j) {
+            if (d.mask_lower && d.mask_row0 + i < d.mask_col0 + j) continue;
+            double acc = 0.0;
+            for (int t = 0; t < d.nslices; ++t) {
+                int64_t P = 0;
+                for (int p = 0; p <= t; ++p) {
+                    const int8_t* a = d.Qa + i * d.ldqa + (int64_t)p * d.K;
+                    const int8_t* b = d.Qb + j * d.ldqb + (int64_t)(t - p) * d.K;
+                    int32_t part = 0;
+                    for (int64_t c = 0; c < d.K; ++c) part += (int32_t)a[c] * (int32_t)b[c];
+                    P += part;
+                }
+                acc = std::fma((double)P, std::scalbn(1.0, -7 * (t + 2)), acc);
+            }
+            d.C[i * d.ldc + j] += acc * (d.alpha * d.sa[i] * d.sb[j]);
+        }
+    return GPB_OK;
+}
+int igemm_i8(stream_t, int64_t m, int64_t n, int64_t k, const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb, int32_t* C,
+             int64_t ldc) {
+    for (int64_t i = 0; i < m; ++i)
+        for (int64_t j = 0; j < n; ++j) {
+            int32_t acc = 0;
+            for (int64_t c = 0; c < k; ++c) acc += (int32_t)A[i * lda + c] * (int32_t)B[j * ldb + c];
+            C[i * ldc + j] = acc;
+        }
+    return GPB_OK;
+}
+bool ozaki_available() { return true; }
+}  // namespace gpb
+
 // measurement hooks are inert in the host model
 namespace gpb {
 stream_t side_stream(stream_t main, int) { return main; }

@@ -1,0 +1,151 @@
+"""Parity of the INT8-tensor-pipe (Ozaki scheme) path: the raw tcgen05 kind::i8 product is bit-exact against integer
+matmul, the digit planes reconstruct the operand, the recombined fp64 product meets its truncation bound, and the
+blocked Cholesky / conjugate_mll built on it agree with the FP64 DMMA path and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _restore_switch():
+    from gpjax_b200 import ops
+
+    before = ops.get_ozaki_slices()
+    yield
+    ops.set_ozaki_slices(before)
+
+
+def test_driver_can_encode_tensor_maps():
+    from gpjax_b200 import ops
+
+    assert ops.ozaki_available()
+
+
+@pytest.mark.parametrize("m,n,k,pad", [(128, 128, 128, 0), (1, 1, 128, 0), (300, 200, 256, 128), (1000, 520, 1024, 0),
+                                       (4096, 4100, 2048, 1024), (129, 4500, 384, 0)])
+def test_raw_int8_product_is_bit_exact(m, n, k, pad):
+    from gpjax_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(m + 3 * n + 7 * k)
+    Afull = torch.randint(-128, 128, (m, k + pad), dtype=torch.int8, device="cuda", generator=g)
+    Bfull = torch.randint(-128, 128, (n, k + pad), dtype=torch.int8, device="cuda", generator=g)
+    A, B = Afull[:, pad:], Bfull[:, :k]  # strided views: lda != k, non-zero column offset
+    C = ops.igemm_i8(A, B)
+    torch.cuda.synchronize()
+    ref = (A.double() @ B.double().T).to(torch.int64)  # exact: |sum| < 2^31 << 2^53
+    assert torch.equal(C.to(torch.int64), ref)
+
+
+@pytest.mark.parametrize("s", [5, 7, 8])
+def test_digit_planes_reconstruct_the_operand(s):
+    from gpjax_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(s)
+    X = torch.randn(300, 256, dtype=torch.float64, device="cuda", generator=g)
+    X *= torch.exp(3 * torch.randn(300, 1, dtype=torch.float64, device="cuda", generator=g))
+    X[5] = 0.0
+    X[7, 3] = 1.0  # exact power of two as the row maximum
+    X[7, 4:] *= 1e-3
+    Q, sc = ops.ozaki_slice(X, s)
+    torch.cuda.synchronize()
+    assert int(Q.abs().max()) <= 64
+    planes = Q.view(300, s, 256).double()
+    w = torch.tensor([2.0 ** (-7 * (p + 1)) for p in range(s)], dtype=torch.float64, device="cuda")
+    rec = (planes * w[None, :, None]).sum(1) * sc[:, None]
+    err = (rec - X).abs() / sc[:, None]
+    assert float(err.max()) <= 2.0 ** (-7 * s - 1)
+    assert float(sc[5]) == 1.0 and int(Q[5].abs().max()) == 0
+    assert torch.all(X.abs().amax(1)[sc > 0] < 0.5 * sc[sc > 0] + 1e-300)
+
+
+def test_nan_row_poisons_its_scale_only():
+    from gpjax_b200 import ops
+
+    X = torch.ones(4, 128, dtype=torch.float64, device="cuda")
+    X[2, 17] = float("nan")
+    Q, sc = ops.ozaki_slice(X, 7)
+    assert torch.isnan(sc[2]) and torch.isfinite(sc[[0, 1, 3]]).all()
+
+
+@pytest.mark.parametrize("s,tol", [(5, 2e-8), (6, 2e-10), (7, 2e-12), (8, 2e-14)])
+@pytest.mark.parametrize("m,n,k,lower", [(700, 300, 1024, False), (2500, 2500, 1024, True), (130, 260, 128, False)])
+def test_recombined_product_meets_truncation_bound(s, tol, m, n, k, lower):
+    from gpjax_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(m + n + k + s)
+    A = torch.randn(m, k, dtype=torch.float64, device="cuda", generator=g)
+    A *= torch.exp(torch.randn(m, 1, dtype=torch.float64, device="cuda", generator=g))
+    B = A[:n] if lower else torch.randn(n, k, dtype=torch.float64, device="cuda", generator=g)
+    C0 = torch.randn(m, n, dtype=torch.float64, device="cuda", generator=g)
+    Qa, sa = ops.ozaki_slice(A, s)
+    Qb, sb = (Qa[:n], sa[:n]) if lower else ops.ozaki_slice(B, s)
+    C = C0.clone()
+    ops.ozaki_gemm_(C, Qa, sa, Qb, sb, k, s, alpha=-1.0, mask_lower=lower)
+    torch.cuda.synchronize()
+    ref = C0 - A @ B.T
+    if lower:
+        keep = torch.ones(m, n, dtype=torch.bool, device="cuda").tril()
+        assert torch.equal(C[~keep], C0[~keep])  # masked entries untouched
+        C, ref = C[keep], ref[keep]
+        bound = (A.abs().amax(1)[:, None] * B.abs().amax(1)[None, :])[keep]
+    else:
+        bound = A.abs().amax(1)[:, None] * B.abs().amax(1)[None, :]
+    # dropped orders: (s+1) 2^(-7 s) k (row max)(row max) 4 at worst; measured far below -- the test pins the order of magnitude
+    assert float(((C - ref).abs() / (k * bound)).max()) <= tol / 16
+    assert float(((C - ref).abs() / (A.norm(dim=1).max() * B.norm(dim=1).max())).max()) <= tol
+
+
+@pytest.mark.parametrize("n", [4096, 5000])
+def test_cholesky_on_the_int8_pipe_matches_the_dmma_factor(n):
+    from gpjax_b200 import ops
+
+    rng = np.random.default_rng(n)
+    X = rng.uniform(-2, 2, (n, 8))
+    ell = np.linspace(0.8, 1.6, 8)
+    Xd = torch.as_tensor(X, device="cuda")
+    S = ops.gram_forward(0, Xd, Xd, torch.as_tensor(ell, device="cuda"), torch.tensor(1.0, dtype=torch.float64, device="cuda"),
+                         diag_add=1e-6 + 0.09)
+    ws = ops.FactorWorkspace(n, 8, potri=False, device="cuda")
+    ops.set_ozaki_slices(0)
+    L0 = S.clone()
+    assert int(ops.potrf_lower_(L0, ws)) == 0
+    ops.set_ozaki_slices(7)
+    assert ops.get_ozaki_slices() == 7
+    L7 = S.clone()
+    assert int(ops.potrf_lower_(L7, ws)) == 0
+    torch.cuda.synchronize()
+    assert not torch.equal(L0, L7), "the switch did not change the arithmetic: int8 path not taken"
+    assert float((L0 - L7).abs().max() / L0.abs().max()) <= 1e-12
+    rec = L7 @ L7.T
+    assert float((rec - S).abs().max()) <= 1e-12 * float(S.abs().max()) * 8
+    ops.set_ozaki_slices(5)
+    L5 = S.clone()
+    ops.potrf_lower_(L5, ws)
+    e5 = float((L0 - L5).abs().max() / L0.abs().max())
+    assert 1e-13 < e5 < 1e-7  # five planes are visibly coarser: the plane count really reaches the kernel
+
+
+def test_conjugate_mll_value_and_gradient_on_the_int8_pipe_vs_oracle():
+    from gpjax_b200 import ops
+
+    n, d = 4096, 8
+    rng = np.random.default_rng(41)
+    X = rng.uniform(-2, 2, (n, d))
+    y = np.sin(X[:, :1]) + 0.1 * rng.standard_normal((n, 1))
+    ell = np.linspace(0.8, 1.6, d)
+    dev = lambda a: torch.as_tensor(np.asarray(a, np.float64), device="cuda")
+    vref = o.conjugate_mll("rbf", X, y, ell, 1.0, 0.3, 0.0)
+    gref = o.conjugate_mll_grad_closed_form("rbf", X, y, ell, 1.0, 0.3, 0.0)
+    ops.set_ozaki_slices(7)
+    p = [dev(ell).requires_grad_(True), dev(1.0).requires_grad_(True), dev(0.3).requires_grad_(True),
+         dev(0.0).requires_grad_(True)]
+    val = ops.conjugate_mll_fused(0, dev(X), dev(y), p[0], p[1], p[2], p[3], 1e-6)
+    val.backward()
+    assert abs(val.item() - vref) <= 1e-8 * abs(vref)
+    assert np.max(np.abs(p[0].grad.cpu().numpy() - gref["lengthscale"])) <= 1e-8 * np.max(np.abs(gref["lengthscale"]))
+    assert abs(p[1].grad.item() - gref["variance"]) <= 1e-8 * abs(gref["variance"])
+    assert abs(p[2].grad.item() - gref["obs_stddev"]) <= 1e-8 * abs(gref["obs_stddev"])

@@ -290,3 +290,60 @@ def test_svgp_elbo_value_and_gradient(lib, kind, name, N, M, D, iso, block, shar
     for k in gref:
         a, b = np.asarray(got[k]).reshape(np.shape(gref[k])), np.asarray(gref[k])
         assert np.max(np.abs(a - b)) <= 1e-7 * max(np.max(np.abs(b)), 1e-8 * abs(ref)), k
+
+
+# ---- Ozaki (int8 digit plane) trailing updates: orchestration, workspace carving, double buffering ---------------------
+@pytest.mark.parametrize("N,planes", [(700, 7), (1024, 8), (900, 5)])
+def test_potrf_with_int8_digit_plane_updates(lib, N, planes):
+    """Host model block = 256, Ozaki threshold = 256 rows (hostsim/Makefile): N=700 runs two Ozaki steps and one DMMA-model
+    step, so digit buffers alternate exactly like the panels under lookahead."""
+    X, _ = data(N, 3, N)
+    S = o.gram("rbf", X, np.array([0.9, 1.1, 1.3]), 1.0) + (1e-6 + 0.09) * np.eye(N)
+    nbytes = lib.gpb_factor_workspace_bytes(N, 3, 0)
+    info = np.zeros(1, np.int32)
+    out = {}
+    try:
+        for s in (0, planes):
+            lib.gpb_set_ozaki_slices(s)
+            assert lib.gpb_get_ozaki_slices() == s
+            ws = np.zeros(nbytes // 8 + 8)
+            A = S.copy()
+            rc = lib.gpb_potrf_lower(None, N, p(A), N, 1, p(ws), nbytes, N, 3, 0, p(info))
+            assert rc == 0 and info[0] == 0
+            out[s] = np.tril(A)
+    finally:
+        lib.gpb_set_ozaki_slices(0)
+    Lref = np.linalg.cholesky(S)
+    assert np.max(np.abs(out[0] - Lref)) <= 1e-12 * np.abs(Lref).max()
+    assert not np.array_equal(out[0], out[planes])  # the int8 model really ran
+    tol = {5: 1e-8, 7: 1e-12, 8: 1e-12}[planes]
+    assert np.max(np.abs(out[planes] - Lref)) <= tol * np.abs(Lref).max()
+
+
+def test_ozaki_switch_rejects_unsupported_plane_counts(lib):
+    try:
+        for bad in (1, 4, 9, -3):
+            lib.gpb_set_ozaki_slices(bad)
+            assert lib.gpb_get_ozaki_slices() == 0
+    finally:
+        lib.gpb_set_ozaki_slices(0)
+
+
+def test_ozaki_slice_and_gemm_host_model_bounds(lib):
+    rng = np.random.default_rng(3)
+    m, n, k, s = 40, 30, 128, 7
+    A = rng.standard_normal((m, k)) * np.exp(rng.standard_normal((m, 1)))
+    B = rng.standard_normal((n, k))
+    Qa, Qb = np.zeros((m, s * k), np.int8), np.zeros((n, s * k), np.int8)
+    sa, sb = np.zeros(m), np.zeros(n)
+    assert lib.gpb_ozaki_slice(None, m, k, p(A), k, s, p(Qa), s * k, p(sa)) == 0
+    assert lib.gpb_ozaki_slice(None, n, k, p(B), k, s, p(Qb), s * k, p(sb)) == 0
+    assert np.abs(Qa).max() <= 64 and np.all(np.log2(sa) == np.round(np.log2(sa)))
+    C = np.ones((m, n))
+    assert lib.gpb_ozaki_gemm(None, m, n, k, s, p(Qa), s * k, p(sa), p(Qb), s * k, p(sb), -1.0, p(C), n, 0) == 0
+    ref = 1.0 - A @ B.T
+    bound = k * np.abs(A).max(1)[:, None] * np.abs(B).max(1)[None, :]
+    assert np.max(np.abs(C - ref) / bound) <= 2.0 ** (-7 * s + 4)
+    Ci = np.zeros((m, n), np.int32)
+    assert lib.gpb_igemm_i8(None, m, n, k, p(Qa), s * k, p(Qb), s * k, p(Ci), n) == 0
+    assert np.array_equal(Ci, Qa[:, :k].astype(np.int64) @ Qb[:, :k].astype(np.int64).T)
