@@ -137,7 +137,7 @@ void gpb_set_ozaki_slices(int nslices) { set_ozaki_slices(nslices); }
 int gpb_get_ozaki_slices(void) { return get_ozaki_slices(); }
 int gpb_ozaki_slice(void* stream, int64_t rows, int64_t K, const double* X, int64_t ldx, int nslices, void* Q,
                     int64_t ldq, double* scale) {
-    return ozaki_slice(stream, rows, K, X, ldx, nslices, static_cast<int8_t*>(Q), ldq, scale);
+    return ozaki_slice(stream, rows, K, K, X, ldx, nslices, static_cast<int8_t*>(Q), ldq, scale);
 }
 int gpb_ozaki_gemm(void* stream, int64_t M, int64_t N, int64_t K, int nslices, const void* Qa, int64_t ldqa,
                    const double* scale_a, const void* Qb, int64_t ldqb, const double* scale_b, double alpha,
@@ -146,7 +146,7 @@ int gpb_ozaki_gemm(void* stream, int64_t M, int64_t N, int64_t K, int nslices, c
     d.M = M; d.N = N; d.K = K; d.nslices = nslices;
     d.Qa = static_cast<const int8_t*>(Qa); d.ldqa = ldqa; d.sa = scale_a;
     d.Qb = static_cast<const int8_t*>(Qb); d.ldqb = ldqb; d.sb = scale_b;
-    d.alpha = alpha; d.C = C; d.ldc = ldc; d.mask_lower = mask_lower;
+    d.alpha = alpha; d.C = C; d.ldc = ldc; d.mask = mask_lower ? MASK_LOWER : MASK_NONE;
     return ozaki_gemm(stream, d);
 }
 int gpb_igemm_i8(void* stream, int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, const void* B,

@@ -194,7 +194,7 @@ static int potrf_panel(stream_t s, int64_t N, double* A, int64_t lda, const Fact
     GPB_TRY(copy2d(s, rows, nbk, panel, NB, P, lda));
     // Ozaki path: digit planes of the panel, extracted on the stream that produced it (the side stream under lookahead)
     const int planes = (nbk == NB) ? oz_planes(ws, rows) : 0;
-    if (planes) GPB_TRY(ozaki_slice(s, rows, NB, panel, NB, planes, oz_q, OZ_MAX_SLICES * NB, oz_scale));
+    if (planes) GPB_TRY(ozaki_slice(s, rows, NB, NB, panel, NB, planes, oz_q, OZ_MAX_SLICES * NB, oz_scale));
     return GPB_OK;
 }
 
@@ -221,7 +221,7 @@ int potrf_lower(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& w
             OzakiGemmDesc u;
             u.M = rows; u.N = nb1; u.K = NB; u.nslices = planes;
             u.Qa = qcur; u.ldqa = ldq; u.sa = scur; u.Qb = qcur; u.ldqb = ldq; u.sb = scur;
-            u.C = A + j1 * lda + j1; u.ldc = lda; u.alpha = -1.0; u.mask_lower = 1;
+            u.C = A + j1 * lda + j1; u.ldc = lda; u.alpha = -1.0; u.mask = MASK_LOWER;
             GPB_TRY(ozaki_gemm(s, u));
         } else {
             GemmDesc u;
@@ -241,7 +241,7 @@ int potrf_lower(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& w
                 v.M = rest; v.N = rest; v.K = NB; v.nslices = planes;
                 v.Qa = qcur + nb1 * ldq; v.ldqa = ldq; v.sa = scur + nb1;
                 v.Qb = v.Qa; v.ldqb = ldq; v.sb = v.sa;
-                v.C = A + (j1 + nb1) * lda + (j1 + nb1); v.ldc = lda; v.alpha = -1.0; v.mask_lower = 1;
+                v.C = A + (j1 + nb1) * lda + (j1 + nb1); v.ldc = lda; v.alpha = -1.0; v.mask = MASK_LOWER;
                 GPB_TRY(ozaki_gemm(s, v));
             } else {
                 GemmDesc v;
@@ -371,11 +371,25 @@ int trtri_into_upper(stream_t s, int64_t N, double* A, int64_t lda, const Factor
         GPB_TRY(copy2d(s, nbk, nbk, DTk, NB, Wp + j0 * NB, NB));  // W_kk = inv(L_kk)^T
         const double* Lp = A + (j0 + nbk) * lda + j0;            // L[k+1:, k]
         if (j0 > 0) {
-            GemmDesc u;  // Acc[0:j0, k+1:] += W[0:j0,k] * L[k+1:,k]^T
-            u.M = j0; u.N = right; u.K = nbk;
-            u.A = Wp; u.lda = NB; u.B = Lp; u.ldb = lda;
-            u.C = A + (j0 + nbk); u.ldc = lda; u.beta = 1.0;
-            GPB_TRY(gemm(s, u));
+            // Acc[0:j0, k+1:] += W[0:j0,k] * L[k+1:,k]^T   (nbk == NB here: block k is not the last one)
+            const int planes = oz_planes(ws, j0);
+            if (planes) {  // digit planes indexed by GLOBAL row: W rows [0, j0), L rows [j0 + nbk, N)
+                const int64_t ldq = OZ_MAX_SLICES * NB;
+                GPB_TRY(ozaki_slice(s, j0, NB, NB, Wp, NB, planes, ws.oz_q, ldq, ws.oz_scale));
+                GPB_TRY(ozaki_slice(s, right, NB, NB, Lp, lda, planes, ws.oz_q + (j0 + nbk) * ldq, ldq, ws.oz_scale + j0 + nbk));
+                OzakiGemmDesc u;
+                u.M = j0; u.N = right; u.K = NB; u.nslices = planes;
+                u.Qa = ws.oz_q; u.ldqa = ldq; u.sa = ws.oz_scale;
+                u.Qb = ws.oz_q + (j0 + nbk) * ldq; u.ldqb = ldq; u.sb = ws.oz_scale + j0 + nbk;
+                u.C = A + (j0 + nbk); u.ldc = lda; u.alpha = 1.0;
+                GPB_TRY(ozaki_gemm(s, u));
+            } else {
+                GemmDesc u;
+                u.M = j0; u.N = right; u.K = nbk;
+                u.A = Wp; u.lda = NB; u.B = Lp; u.ldb = lda;
+                u.C = A + (j0 + nbk); u.ldc = lda; u.beta = 1.0;
+                GPB_TRY(gemm(s, u));
+            }
         }
         GemmDesc v;  // Acc[k, k+1:] = W_kk * L[k+1:,k]^T   (first write of that block row)
         v.M = nbk; v.N = right; v.K = nbk;
@@ -396,11 +410,23 @@ int lauum_upper(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& w
         double* P = A + j0;  // W[0:j0, k], row stride lda
         if (j0 > 0) {
             // S[0:j0, 0:j0] (strictly-upper blocks) += P P^T
-            GemmDesc g;
-            g.M = j0; g.N = j0; g.K = nbk;
-            g.A = P; g.lda = lda; g.B = P; g.ldb = lda; g.C = A; g.ldc = lda;
-            g.beta = 1.0; g.mask = MASK_BLOCK_STRICT_UPPER; g.mask_nb = NB;
-            GPB_TRY(gemm(s, g));
+            const int planes = oz_planes(ws, j0);
+            if (planes) {  // a ragged last block (nbk < NB) is zero-padded to the next multiple of 128 digits
+                const int64_t ldq = OZ_MAX_SLICES * NB;
+                const int64_t kp = align_up(nbk, 128);
+                GPB_TRY(ozaki_slice(s, j0, nbk, kp, P, lda, planes, ws.oz_q, ldq, ws.oz_scale));
+                OzakiGemmDesc g;
+                g.M = j0; g.N = j0; g.K = kp; g.nslices = planes;
+                g.Qa = ws.oz_q; g.ldqa = ldq; g.sa = ws.oz_scale; g.Qb = ws.oz_q; g.ldqb = ldq; g.sb = ws.oz_scale;
+                g.C = A; g.ldc = lda; g.alpha = 1.0; g.mask = MASK_BLOCK_STRICT_UPPER; g.mask_nb = NB;
+                GPB_TRY(ozaki_gemm(s, g));
+            } else {
+                GemmDesc g;
+                g.M = j0; g.N = j0; g.K = nbk;
+                g.A = P; g.lda = lda; g.B = P; g.ldb = lda; g.C = A; g.ldc = lda;
+                g.beta = 1.0; g.mask = MASK_BLOCK_STRICT_UPPER; g.mask_nb = NB;
+                GPB_TRY(gemm(s, g));
+            }
             // diagonal blocks: Sdiag[j] += P_j P_j^T, j < k   (batched)
             GemmDesc b;
             b.M = NB; b.N = NB; b.K = nbk;

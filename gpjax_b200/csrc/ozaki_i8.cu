@@ -44,8 +44,8 @@ struct OzParams {
     int m, n;             // output extents
     int kblocks;          // k / 128 per digit plane
     int nslices;          // digit planes used (1 in raw mode)
-    int mask_lower;       // write only (row0 + i) >= (col0 + j)
-    long long row0, col0;
+    int mask;             // 0 none; 1 lower: (row0+i) >= (col0+j); 2 block-strict-upper: (row0+i)/mask_nb < (col0+j)/mask_nb
+    long long row0, col0, mask_nb;
     double* C;            // fp64 in/out (MODE 1)
     long long ldc;
     int* Ci;              // int32 out (MODE 0)
@@ -62,17 +62,30 @@ struct TileWalk {
     int chunk = 0, tm = 0, c0 = 0, c1 = 0;
     long long base = 0;  // linear index of the first tile of (chunk, tm)
     __device__ int live_end(const OzParams& p, int tm_) const {  // one past the last live tile column of tile row tm_
-        if (!p.mask_lower) return p.ntn;
+        if (p.mask != 1) return p.ntn;
         long long last_row = p.row0 + (long long)tm_ * OZ_BM + OZ_BM - 1;
         long long d = last_row - p.col0;
         if (d < 0) return 0;
         long long e = d / OZ_BN + 1;
         return e < p.ntn ? (int)e : p.ntn;
     }
+    __device__ int live_begin(const OzParams& p, int tm_) const {  // first live tile column of tile row tm_
+        if (p.mask != 2) return 0;
+        long long rb = (p.row0 + (long long)tm_ * OZ_BM) / p.mask_nb;     // block of the tile's FIRST row (smallest)
+        long long need = (rb + 1) * p.mask_nb - (OZ_BN - 1) - p.col0;     // col0 + tn*BN + BN-1 >= (rb+1)*nb
+        if (need <= 0) return 0;
+        long long b = (need + OZ_BN - 1) / OZ_BN;
+        return b < p.ntn ? (int)b : p.ntn;
+    }
+    __device__ int lo(const OzParams& p) const {
+        int b = live_begin(p, tm);
+        return b > c0 ? b : c0;
+    }
     __device__ int count(const OzParams& p) const {
         int e = live_end(p, tm);
         int hi = e < c1 ? e : c1;
-        return hi > c0 ? hi - c0 : 0;
+        int l = lo(p);
+        return hi > l ? hi - l : 0;
     }
     __device__ void set_chunk(const OzParams& p, int ch) {
         chunk = ch;
@@ -89,7 +102,7 @@ struct TileWalk {
             int cnt = count(p);
             if (idx < base + cnt) {
                 tm_out = tm;
-                tn_out = c0 + (int)(idx - base);
+                tn_out = lo(p) + (int)(idx - base);
                 return true;
             }
             base += cnt;
@@ -302,7 +315,10 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 64; ++j) {
                     const int col = col0 + j;
-                    if (col < p.n && (!p.mask_lower || grow >= p.col0 + col)) crow[col] += accd[j] * (sr * __ldg(p.sb + col));
+                    bool live = col < p.n;
+                    if (p.mask == 1) live = live && (grow >= p.col0 + col);
+                    else if (p.mask == 2) live = live && (grow / p.mask_nb < (p.col0 + col) / p.mask_nb);
+                    if (live) crow[col] += accd[j] * (sr * __ldg(p.sb + col));
                 }
             }
         }
@@ -318,9 +334,9 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
 // ---- digit extraction ----------------------------------------------------------------------------------------------
 // one CTA per row: exponent from the row maximum, then `s` rounds of  R <- 128 R;  q = rint(R);  R <- R - q  (all exact)
-__global__ void __launch_bounds__(128) ozaki_slice_kernel(long long rows, int k, const double* __restrict__ X, long long ldx,
-                                                          int nslices, signed char* __restrict__ Q, long long ldq,
-                                                          double* __restrict__ scale) {
+__global__ void __launch_bounds__(128) ozaki_slice_kernel(long long rows, int k, int kplane, const double* __restrict__ X,
+                                                          long long ldx, int nslices, signed char* __restrict__ Q,
+                                                          long long ldq, double* __restrict__ scale) {
     __shared__ double red[4];
     const long long r = blockIdx.x;
     if (r >= rows) return;
@@ -354,12 +370,12 @@ __global__ void __launch_bounds__(128) ozaki_slice_kernel(long long rows, int k,
     }
     if (threadIdx.x == 0) scale[r] = sc;
     signed char* qrow = Q + r * ldq;
-    for (int c = threadIdx.x; c < k; c += 128) {
-        double R = (mx != mx) ? 0.0 : scalbn(x[c], -e);
+    for (int c = threadIdx.x; c < kplane; c += 128) {
+        double R = (mx != mx || c >= k) ? 0.0 : scalbn(x[c], -e);  // columns [k, kplane) are zero padding
         for (int p = 0; p < nslices; ++p) {
             R *= 128.0;
             double d = rint(R);
-            qrow[(long long)p * k + c] = (signed char)(int)d;
+            qrow[(long long)p * kplane + c] = (signed char)(int)d;
             R -= d;
         }
     }
@@ -422,12 +438,13 @@ int launch(stream_t s, const CUtensorMap& ta, const CUtensorMap& tb, OzParams& p
 
 }  // namespace
 
-int ozaki_slice(stream_t s, int64_t rows, int64_t k, const double* X, int64_t ldx, int nslices, int8_t* Q, int64_t ldq,
-                double* scale) {
-    if (rows < 0 || k <= 0 || nslices < 1 || nslices > 8 || !X || !Q || !scale || ldq < (int64_t)nslices * k) return GPB_ERR_INVALID;
+int ozaki_slice(stream_t s, int64_t rows, int64_t k, int64_t kplane, const double* X, int64_t ldx, int nslices, int8_t* Q,
+                int64_t ldq, double* scale) {
+    if (rows < 0 || k <= 0 || kplane < k || nslices < 1 || nslices > 8 || !X || !Q || !scale || ldq < (int64_t)nslices * kplane)
+        return GPB_ERR_INVALID;
     if (rows == 0) return GPB_OK;
-    ozaki_slice_kernel<<<(unsigned)rows, 128, 0, to_stream(s)>>>(rows, (int)k, X, ldx, nslices, reinterpret_cast<signed char*>(Q),
-                                                                 ldq, scale);
+    ozaki_slice_kernel<<<(unsigned)rows, 128, 0, to_stream(s)>>>(rows, (int)k, (int)kplane, X, ldx, nslices,
+                                                                 reinterpret_cast<signed char*>(Q), ldq, scale);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
 }
@@ -452,6 +469,7 @@ int ozaki_gemm(stream_t s, const OzakiGemmDesc& d) {
     if (d.M < 0 || d.N < 0 || d.K <= 0 || d.nslices < 1 || d.nslices > 8 || !d.Qa || !d.Qb || !d.sa || !d.sb || !d.C)
         return GPB_ERR_INVALID;
     if (d.K % OZ_BK || d.K > 32768) return GPB_ERR_UNSUPPORTED;
+    if (d.mask != MASK_NONE && d.mask != MASK_LOWER && d.mask != MASK_BLOCK_STRICT_UPPER) return GPB_ERR_UNSUPPORTED;
     if (d.M == 0 || d.N == 0) return GPB_OK;
     CUtensorMap ta, tb;
     int rc = make_map(&ta, d.Qa, d.M, (int64_t)d.nslices * d.K, d.ldqa);
@@ -460,7 +478,7 @@ int ozaki_gemm(stream_t s, const OzakiGemmDesc& d) {
     if (rc) return rc;
     OzParams p = {};
     p.m = (int)d.M; p.n = (int)d.N; p.kblocks = (int)(d.K / OZ_BK); p.nslices = d.nslices;
-    p.mask_lower = d.mask_lower; p.row0 = d.mask_row0; p.col0 = d.mask_col0;
+    p.mask = d.mask == MASK_LOWER ? 1 : (d.mask == MASK_BLOCK_STRICT_UPPER ? 2 : 0); p.row0 = d.mask_row0; p.col0 = d.mask_col0; p.mask_nb = d.mask_nb > 0 ? d.mask_nb : 1;
     p.C = d.C; p.ldc = d.ldc; p.sa = d.sa; p.sb = d.sb; p.alpha = d.alpha;
     return launch<1>(s, ta, tb, p);
 }

@@ -255,8 +255,10 @@ int svgp_scalar_grads(stream_t s, const double* sc, const double* dots, const do
 // x_ik = scale_i * sum_p Q[i, p*k + c] * 2^(-7 (p+1)),  scale_i = 2^e_i,  |Q| <= 64: `nslices` signed 7-bit digit planes
 // per entry, plane p stored at columns [p*k, (p+1)*k) of the int8 matrix Q (row stride ldq >= nslices*k bytes, multiple
 // of 16; Q 16-byte aligned).  Exact (no rounding) while nslices*7 covers the mantissa; a NaN/Inf row gets scale = NaN.
-int ozaki_slice(stream_t s, int64_t rows, int64_t k, const double* X, int64_t ldx, int nslices, int8_t* Q, int64_t ldq,
-                double* scale);
+// Plane stride `kplane` >= k (columns [k, kplane) of every plane are written as zero digits, so a ragged K can be padded
+// to the multiple of 128 the product kernel needs).
+int ozaki_slice(stream_t s, int64_t rows, int64_t k, int64_t kplane, const double* X, int64_t ldx, int nslices, int8_t* Q,
+                int64_t ldq, double* scale);
 struct OzakiGemmDesc {
     int64_t M = 0, N = 0, K = 0;  // K = digits per plane (multiple of 128)
     int nslices = 7;
@@ -269,8 +271,8 @@ struct OzakiGemmDesc {
     double* C = nullptr;          // C += alpha * A B^T (all digit pairs of order p+q < nslices)
     int64_t ldc = 0;
     double alpha = 1.0;
-    int mask_lower = 0;           // only entries with mask_row0 + i >= mask_col0 + j are touched
-    int64_t mask_row0 = 0, mask_col0 = 0;
+    int mask = MASK_NONE;         // MASK_NONE, MASK_LOWER or MASK_BLOCK_STRICT_UPPER (same meaning as GemmDesc::mask)
+    int64_t mask_row0 = 0, mask_col0 = 0, mask_nb = 1;
 };
 int ozaki_gemm(stream_t s, const OzakiGemmDesc& d);
 // C[m,n] (int32) = A[m,k] B[n,k]^T for int8 operands (k multiple of 128, lda/ldb multiples of 16): the raw tcgen05 product

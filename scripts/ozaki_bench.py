@@ -74,6 +74,37 @@ def main():
             row["max_rel_diff_vs_dmma"] = float((torch.tril(A) - L0).abs().max() / L0.abs().max())
         out["potrf"].append(row)
     ops.set_ozaki_slices(0)
+    del A, ws, L0
+    torch.cuda.empty_cache()
+    # whole conjugate_mll value + gradient step (potrf + trtri + lauum + streamed backward)
+    y = torch.as_tensor(np.sin(rng.uniform(-2, 2, (n, 1))), device="cuda")
+    base = None
+    out["mll_step"] = []
+    for s in (0, 7, 6):
+        ops.set_ozaki_slices(s)
+        p = [ell.clone().requires_grad_(True), one.clone().requires_grad_(True),
+             torch.tensor(0.3, dtype=torch.float64, device="cuda", requires_grad=True),
+             torch.tensor(0.0, dtype=torch.float64, device="cuda", requires_grad=True)]
+
+        def step():
+            for q in p:
+                q.grad = None
+            v = ops.conjugate_mll_fused(0, Xd, y, p[0], p[1], p[2], p[3], 1e-6)
+            v.backward()
+            return v
+
+        t = ev(step, reps=2)
+        v = step()
+        torch.cuda.synchronize()
+        g = torch.cat([q.grad.reshape(-1) for q in p])
+        row = {"N": n, "slices": s, "step_s": t, "TF_s_fp64_equiv": n**3 / t / 1e12, "value": v.item()}
+        if s == 0:
+            base = (v.item(), g.clone())
+        else:
+            row["value_rel_diff_vs_dmma"] = abs(v.item() - base[0]) / abs(base[0])
+            row["grad_rel_diff_vs_dmma"] = float((g - base[1]).abs().max() / base[1].abs().max())
+        out["mll_step"].append(row)
+    ops.set_ozaki_slices(0)
     json.dump(out, sys.stdout, indent=1)
     print()
 

@@ -458,9 +458,10 @@ int sgpr_scalar_grads(stream_t, const double* sc, const double* dots, const doub
 
 // ---- Ozaki (int8 digit plane) primitives: exact integer model of ozaki_i8.cu ------------------------------------
 namespace gpb {
-int ozaki_slice(stream_t, int64_t rows, int64_t k, const double* X, int64_t ldx, int nslices, int8_t* Q, int64_t ldq,
-                double* scale) {
-    if (rows < 0 || k <= 0 || nslices < 1 || nslices > 8 || !X || !Q || !scale || ldq < (int64_t)nslices * k) return GPB_ERR_INVALID;
+int ozaki_slice(stream_t, int64_t rows, int64_t k, int64_t kplane, const double* X, int64_t ldx, int nslices, int8_t* Q,
+                int64_t ldq, double* scale) {
+    if (rows < 0 || k <= 0 || kplane < k || nslices < 1 || nslices > 8 || !X || !Q || !scale || ldq < (int64_t)nslices * kplane)
+        return GPB_ERR_INVALID;
     for (int64_t r = 0; r < rows; ++r) {
         double mx = 0.0;
         bool bad = false;
@@ -473,12 +474,12 @@ int ozaki_slice(stream_t, int64_t rows, int64_t k, const double* X, int64_t ldx,
         if (bad) scale[r] = std::numeric_limits<double>::quiet_NaN();
         else if (mx == 0.0) scale[r] = 1.0;
         else { e = std::ilogb(mx) + 2; scale[r] = std::scalbn(1.0, e); }
-        for (int64_t c = 0; c < k; ++c) {
-            double R = bad ? 0.0 : std::scalbn(X[r * ldx + c], -e);
+        for (int64_t c = 0; c < kplane; ++c) {
+            double R = (bad || c >= k) ? 0.0 : std::scalbn(X[r * ldx + c], -e);
             for (int p = 0; p < nslices; ++p) {
                 R *= 128.0;
                 double d = std::nearbyint(R);
-                Q[r * ldq + (int64_t)p * k + c] = (int8_t)(int)d;
+                Q[r * ldq + (int64_t)p * kplane + c] = (int8_t)(int)d;
                 R -= d;
             }
         }
@@ -491,7 +492,8 @@ int ozaki_gemm(stream_t, const OzakiGemmDesc& d) {
     if (d.K % 128) return GPB_ERR_UNSUPPORTED;
     for (int64_t i = 0; i < d.M; ++i)
         for (int64_t j = 0; j < d.N; ++j) {
-            if (d.mask_lower && d.mask_row0 + i < d.mask_col0 + j) continue;
+            if (d.mask == MASK_LOWER && d.mask_row0 + i < d.mask_col0 + j) continue;
+            if (d.mask == MASK_BLOCK_STRICT_UPPER && !((d.mask_row0 + i) / d.mask_nb < (d.mask_col0 + j) / d.mask_nb)) continue;
             double acc = 0.0;
             for (int t = 0; t < d.nslices; ++t) {
                 int64_t P = 0;

