@@ -39,7 +39,8 @@ def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             d = json.load(f)
-        return {"hbm_gbs": d.get("hbm_gbs"), "bf16_tflops": d.get("bf16_tflops")}
+        return {"hbm_gbs": d.get("hbm_gbs"), "bf16_tflops": d.get("bf16_tflops"),
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained")}
     except Exception:
         return None
 
@@ -289,28 +290,60 @@ def bench_exact(D: Dist, args):
     import ctypes as C
 
     gemm_ms, gemm_n, all_n = C.c_double(), C.c_int64(), C.c_int64()
+    oz_ms, oz_n, oz_ops = C.c_double(), C.c_int64(), C.c_double()
     L.gpb_profile_read(C.byref(gemm_ms), C.byref(gemm_n), C.byref(all_n))
+    L.gpb_profile_read_ozaki(C.byref(oz_ms), C.byref(oz_n), C.byref(oz_ops))
     L.gpb_profile_reset(0)
     value = D.world * args.steps / t
     flops_per_eval = float(n) ** 3  # N^3/3 potrf + 2N^3/3 potri
-    achieved = flops_per_eval * args.steps / (gemm_ms.value * 1e-3) / 1e12
-    roof = {"bound": "tensor", "kernel": "gemm_f64_kernel (FP64 DMMA.8x8x4)", "achieved": achieved,
-            "peak": NOMINAL_FP64_TFLOPS, "unit": "TFLOP/s", "frac": achieved / NOMINAL_FP64_TFLOPS,
-            "peak_source": "nominal FP64 DMMA peak 128 flop/clk/SM x 148 SM x 1.965 GHz (MEASURED_PEAKS.json has no "
-                           "FP64 figure); cuBLAS DGEMM measured live alongside",
-            "peak_cublas_dgemm": measure_cublas_dgemm(D), "measured_peaks_json": measured_peaks(),
-            "algorithmic_flop_per_eval": flops_per_eval,
-            "gemm_launches_per_step": gemm_n.value / args.steps,
-            # sum of GEMM launch durations / step time; can reach ~1.0 because the lookahead GEMMs on the side stream
-            # overlap the trailing update on the main stream
-            "gemm_time_over_step_time": gemm_ms.value * 1e-3 / t,
-            "whole_step_tflops": flops_per_eval * args.steps / t / 1e12,
-            # ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 1846 GEMM launches of ONE evaluation at
-            # N=50k with the 1024 block (profiles/r01_gemm_traffic_exact50k_nb1024.md: 1147 GB read + 499 GB written);
-            # algorithmic = read + write of every C tile touched by the rank-NB updates of the three N^3/3 phases
-            "traffic": 1.646e12 if (n == 50000 and L.gpb_block_size() == 1024) else None,
-            "traffic_unit": "bytes per evaluation (all GEMM launches)",
-            "algorithmic_bytes": 3 * 16 * float(n) ** 3 / (6 * L.gpb_block_size())}
+    planes = int(L.gpb_get_ozaki_slices())
+    dmma = {"kernel": "gemm_f64_kernel (FP64 DMMA.8x8x4)", "launches_per_step": gemm_n.value / args.steps,
+            "time_over_step_time": gemm_ms.value * 1e-3 / t}
+    if planes and oz_n.value > 0:
+        # Dominant kernel: ozaki_i8_kernel (tcgen05.mma kind::i8).  `achieved` = algorithmic int8 operations of its launches
+        # (live output entries x K x s(s+1)/2 digit pairs x 2, counted by the launcher) / summed launch durations (CUDA events
+        # on the launching stream).  MEASURED_PEAKS.json has no int8 figure: the int8 tcgen05 rate is nominally 2x bf16
+        # (4.5 vs 2.25 Pop/s), so the peak used is 2 x the measured SUSTAINED bf16 rate (kernel timed inside a long step).
+        mp = measured_peaks() or {}
+        bf16 = float(mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops") or 1414.5)
+        peak = 2.0 * bf16
+        achieved = oz_ops.value / (oz_ms.value * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "ozaki_i8_kernel (tcgen05.mma.cta_group::1.kind::i8, int8 x int8 -> int32 in TMEM)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (no int8 entry; int8 tcgen05 is nominally 2x bf16); "
+                               "unit is int8 Top/s (2 x MAC)",
+                "digit_planes": planes, "int8_ops_per_eval": oz_ops.value / args.steps,
+                "launches_per_step": oz_n.value / args.steps, "time_over_step_time": oz_ms.value * 1e-3 / t,
+                "mma_pacing_ceiling_measured": 2070.0,  # same kernel with TMA loads disabled (GPB_OZ_NOLOAD=1), profiles/r01_ozaki.md
+                "algorithmic_flop_per_eval": flops_per_eval,
+                "whole_step_tflops": flops_per_eval * args.steps / t / 1e12,
+                "whole_step_vs_fp64_dmma_peak": flops_per_eval * args.steps / t / 1e12 / NOMINAL_FP64_TFLOPS,
+                "fp64_dmma_peak": NOMINAL_FP64_TFLOPS, "measured_peaks_json": mp, "remaining_dmma_gemms": dmma,
+                "traffic": None}
+        # the same step with every update on the FP64 DMMA pipe (GPB_OZAKI=0), timed live for comparison
+        ops.set_ozaki_slices(0)
+        t_dmma = timed(D, step, 1, 1)
+        ops.set_ozaki_slices(planes)
+        roof["fp64_dmma_path_ms_per_step"] = 1e3 * t_dmma
+    else:
+        achieved = flops_per_eval * args.steps / (gemm_ms.value * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": dmma["kernel"], "achieved": achieved,
+                "peak": NOMINAL_FP64_TFLOPS, "unit": "TFLOP/s", "frac": achieved / NOMINAL_FP64_TFLOPS,
+                "peak_source": "nominal FP64 DMMA peak 128 flop/clk/SM x 148 SM x 1.965 GHz (MEASURED_PEAKS.json has no "
+                               "FP64 figure); cuBLAS DGEMM measured live alongside",
+                "peak_cublas_dgemm": measure_cublas_dgemm(D), "measured_peaks_json": measured_peaks(),
+                "algorithmic_flop_per_eval": flops_per_eval,
+                "gemm_launches_per_step": gemm_n.value / args.steps,
+                # sum of GEMM launch durations / step time; can reach ~1.0 because the lookahead GEMMs on the side stream
+                # overlap the trailing update on the main stream
+                "gemm_time_over_step_time": gemm_ms.value * 1e-3 / t,
+                "whole_step_tflops": flops_per_eval * args.steps / t / 1e12,
+                # ncu dram__bytes_read.sum + dram__bytes_write.sum summed over the 1846 GEMM launches of ONE evaluation at
+                # N=50k with the 1024 block (profiles/r01_gemm_traffic_exact50k_nb1024.md: 1147 GB read + 499 GB written);
+                # algorithmic = read + write of every C tile touched by the rank-NB updates of the three N^3/3 phases
+                "traffic": 1.646e12 if (n == 50000 and L.gpb_block_size() == 1024) else None,
+                "traffic_unit": "bytes per evaluation (all GEMM launches)",
+                "algorithmic_bytes": 3 * 16 * float(n) ** 3 / (6 * L.gpb_block_size())}
 
     # ---- e2e: the public API with HOST buffers (pinned), H2D + D2H inside the timed region -------------------
     prior = gpx.gps.Prior(mean_function=gpx.mean_functions.Constant(Real(HYPER["mean_const"])),
@@ -509,7 +542,9 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": ex["workload"], "N": ex["n"], "D": ex["d"], "kernel": "RBF ARD",
                            "parallelism": "replicas only (exact GP does not shard)" if D.world > 1 else "single GPU",
-                           "l2": "20 GB working set per step >> 126 MB L2 (no flush needed)"},
+                           "l2": "20 GB working set per step >> 126 MB L2 (no flush needed)",
+                           "trailing_updates": ("int8 digit planes (Ozaki), default" if ex["roofline"].get("digit_planes")
+                                                else "FP64 DMMA (GPB_OZAKI=0)")},
                 "roofline": ex["roofline"], "clocks": ex["clocks"], "e2e": ex["e2e"], "gpu_launches": ex["gpu_launches"]}
     if args.workload in ("auto", "sgpr"):
         sg = bench_sgpr(D, args)

@@ -21,6 +21,7 @@ PROTOTYPES = {
     "gpb_profile_reset": (None, [i32]),
     "gpb_debug_set_gemm_variant": (None, [i32]),
     "gpb_profile_read": (i32, [vp, vp, vp]),
+    "gpb_profile_read_ozaki": (i32, [vp, vp, vp]),
     "gpb_gram": (i32, [vp, i32, i64, i64, i32, vp, i64, vp, i64, vp, i32, vp, f64, vp, i32, vp, i64]),
     "gpb_gram_bwd_workspace_bytes": (i64, [i64, i64, i32]),
     "gpb_gram_bwd": (

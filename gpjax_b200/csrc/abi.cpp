@@ -132,6 +132,7 @@ int gpb_gemm(void* stream, int64_t M, int64_t N, int64_t K, double alpha, const 
     return gemm(stream, g);
 }
 
+int gpb_profile_read_ozaki(double* ms, int64_t* launches, double* int8_ops) { return profile_read_ozaki(ms, launches, int8_ops); }
 int gpb_ozaki_available(void) { return ozaki_available() ? 1 : 0; }
 void gpb_set_ozaki_slices(int nslices) { set_ozaki_slices(nslices); }
 int gpb_get_ozaki_slices(void) { return get_ozaki_slices(); }

@@ -35,7 +35,7 @@ void set_ozaki_slices(int nslices) { g_oz_slices = clamp_slices(nslices); }
 int get_ozaki_slices() {
     if (g_oz_slices < 0) {
         const char* e = std::getenv("GPB_OZAKI");
-        g_oz_slices = e ? clamp_slices(std::atoi(e)) : 0;
+        g_oz_slices = e ? clamp_slices(std::atoi(e)) : clamp_slices(GPB_OZ_DEFAULT);
     }
     return g_oz_slices;
 }

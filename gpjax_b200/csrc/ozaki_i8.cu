@@ -25,6 +25,8 @@
 // buffer (SYRK) and no order-reversed copy exists.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace gpb {
@@ -54,6 +56,8 @@ struct OzParams {
     const double* sb;     // 2^eb_j
     double alpha;
     int ntm, ntn;
+    int noload;           // measurement hook (GPB_OZ_NOLOAD=1): the producer signals `full` without issuing TMA -> pure MMA pacing
+    int bn;               // output tile width of the launched kernel variant (128: v1, 64: v2)
 };
 
 // ---- tile enumeration shared by the three roles: column chunks -> tile rows -> tile columns, dead tiles of the lower
@@ -66,15 +70,15 @@ struct TileWalk {
         long long last_row = p.row0 + (long long)tm_ * OZ_BM + OZ_BM - 1;
         long long d = last_row - p.col0;
         if (d < 0) return 0;
-        long long e = d / OZ_BN + 1;
+        long long e = d / p.bn + 1;
         return e < p.ntn ? (int)e : p.ntn;
     }
     __device__ int live_begin(const OzParams& p, int tm_) const {  // first live tile column of tile row tm_
         if (p.mask != 2) return 0;
         long long rb = (p.row0 + (long long)tm_ * OZ_BM) / p.mask_nb;     // block of the tile's FIRST row (smallest)
-        long long need = (rb + 1) * p.mask_nb - (OZ_BN - 1) - p.col0;     // col0 + tn*BN + BN-1 >= (rb+1)*nb
+        long long need = (rb + 1) * p.mask_nb - (p.bn - 1) - p.col0;     // col0 + tn*BN + BN-1 >= (rb+1)*nb
         if (need <= 0) return 0;
-        long long b = (need + OZ_BN - 1) / OZ_BN;
+        long long b = (need + p.bn - 1) / p.bn;
         return b < p.ntn ? (int)b : p.ntn;
     }
     __device__ int lo(const OzParams& p) const {
@@ -138,6 +142,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
             smem_u32(smem_dst)),
         "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y)
         : "memory");
+}
+// one lane of a CONVERGED warp; keeping the role loops warp-uniform lets the compiler hold descriptors / addresses in uniform
+// registers (an `if (lane == 0)` role makes every UTCIMMA / UTMALDG operand pass through an ELECT + R2UR waterfall loop)
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile("{\n .reg .pred P;\n elect.sync _|P, 0xffffffff;\n selp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred)::"memory");
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
@@ -220,7 +231,7 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int groups = MODE == 0 ? 1 : p.nslices;
 
     if (warp == 0) {
-        if (lane == 0) {  // ===== TMA producer =====
+        {  // ===== TMA producer (whole warp walks the schedule, one elected lane issues) =====
             TileWalk w; w.init(p);
             int stage = 0; unsigned phase = 0;
             int tm, tn;
@@ -232,9 +243,16 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         for (int kb = 0; kb < p.kblocks; ++kb) {
                             mbar_wait_bounded(&empty[stage], phase ^ 1u);
                             uint8_t* sA = smem + stage * OZ_STAGE_BYTES;
-                            mbar_arrive_expect_tx(&full[stage], OZ_STAGE_BYTES);
-                            tma_load_2d(sA, &tmA, &full[stage], xa0 + kb * OZ_BK, m0);
-                            tma_load_2d(sA + OZ_BM * OZ_BK, &tmB, &full[stage], xb0 + kb * OZ_BK, n0);
+                            if (elect_one()) {
+                                if (p.noload) {
+                                    mbar_arrive(&full[stage]);
+                                } else {
+                                    mbar_arrive_expect_tx(&full[stage], OZ_STAGE_BYTES);
+                                    tma_load_2d(sA, &tmA, &full[stage], xa0 + kb * OZ_BK, m0);
+                                    tma_load_2d(sA + OZ_BM * OZ_BK, &tmB, &full[stage], xb0 + kb * OZ_BK, n0);
+                                }
+                            }
+                            __syncwarp();
                             if (++stage == OZ_STAGES) { stage = 0; phase ^= 1u; }
                         }
                     }
@@ -242,7 +260,7 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {  // ===== MMA issuer =====
+        {  // ===== MMA issuer (whole warp walks the schedule, one elected lane issues) =====
             TileWalk w; w.init(p);
             int stage = 0; unsigned phase = 0;
             int acc = 0; unsigned aphase = 0;
@@ -258,13 +276,16 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         tc_fence_after();
                         const unsigned sA = smem_u32(smem + stage * OZ_STAGE_BYTES);
                         const uint64_t da = umma_desc_k_sw128(sA), db = umma_desc_k_sw128(sA + OZ_BM * OZ_BK);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int kk = 0; kk < OZ_BK / 32; ++kk)  // +32 bytes along K inside the swizzle row = +2 in the address field
-                            tc_mma_i8(d_tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), OZ_IDESC, (kb | kk) != 0);
-                        tc_commit(&empty[stage]);  // frees the ring slot once these MMAs have read it
+                            for (int kk = 0; kk < OZ_BK / 32; ++kk)  // +32 bytes along K inside the swizzle row = +2 in the address field
+                                tc_mma_i8(d_tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), OZ_IDESC, (kb | kk) != 0);
+                            tc_commit(&empty[stage]);  // frees the ring slot once these MMAs have read it
+                            if (kb == nkb - 1) tc_commit(&tfull[acc]);  // accumulator of order t complete
+                        }
+                        __syncwarp();
                         if (++stage == OZ_STAGES) { stage = 0; phase ^= 1u; }
                     }
-                    tc_commit(&tfull[acc]);  // accumulator of order t complete
                     if (++acc == OZ_ACC_STAGES) { acc = 0; aphase ^= 1u; }
                 }
             }
@@ -314,6 +335,205 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 const long long grow = p.row0 + row;
 #pragma unroll
                 for (int j = 0; j < 64; ++j) {
+                    const int col = col0 + j;
+                    bool live = col < p.n;
+                    if (p.mask == 1) live = live && (grow >= p.col0 + col);
+                    else if (p.mask == 2) live = live && (grow / p.mask_nb < (p.col0 + col) / p.mask_nb);
+                    if (live) crow[col] += accd[j] * (sr * __ldg(p.sb + col));
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---- variant 2: plane-resident schedule ------------------------------------------------------------------------------
+// v1 above re-reads every digit tile once per order: 28 (A,B) tile pairs x 32 KB per K-block of a 128 x 128 output tile,
+// which saturates the L2 -> SM path (measured 12.9 TB/s == the chip's LTS cap) at ~1.7 Pop/s.  Here ALL `s` order
+// accumulators of a 128 x 64 output tile are live in TMEM at once (s x 64 columns <= 512), the loop over the K-blocks is
+// outermost, and per K-block each digit plane of A (16 KB) and of B (8 KB) is loaded exactly once and reused by every
+// pair (p, q), p + q < s: 168 KB instead of 896 KB per K-block for 7 planes (per output element: 2.7x less L2 traffic).
+//   smem: A ring of 6 x 16 KB (plane tiles stream through it in consumption order) + B planes double-buffered by K-block
+//         parity, 2 x 8 x 8 KB; every buffer has its own full/empty mbarrier pair, tcgen05.commit frees a buffer as soon
+//         as the last MMA reading it has retired (A_p after its q sweep, B_q after the sweep of p = s-1-q).
+//   TMEM: accumulator of order t at columns [64 t, 64 t + 64); the epilogue folds the orders into 32 fp64 registers per
+//         thread, releases TMEM, then does the single read-modify-write of C while the next tile's MMAs already run.
+constexpr int O2_BN = 64;
+constexpr int O2_ASTAGES = 6;
+constexpr int O2_BBUFS = 16;
+constexpr int O2_A_BYTES = OZ_BM * OZ_BK;  // 16 KB
+constexpr int O2_B_BYTES = O2_BN * OZ_BK;  //  8 KB
+constexpr int O2_DATA_BYTES = O2_ASTAGES * O2_A_BYTES + O2_BBUFS * O2_B_BYTES;  // 224 KB
+constexpr int O2_SMEM_BYTES = O2_DATA_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+constexpr unsigned O2_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(O2_BN >> 3) << 17) | ((unsigned)(OZ_BM >> 4) << 24);
+static_assert(O2_SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
+
+template <int MODE>
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+ozaki_i8_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const OzParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const unsigned raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+    uint8_t* sBbase = smem + O2_ASTAGES * O2_A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + O2_DATA_BYTES);
+    uint64_t* afull = bars;                              // [6]
+    uint64_t* aempty = bars + O2_ASTAGES;                // [6]
+    uint64_t* bfull = bars + 2 * O2_ASTAGES;             // [16]
+    uint64_t* bempty = bfull + O2_BBUFS;                 // [16]
+    uint64_t* tfull = bempty + O2_BBUFS;                 // [1]
+    uint64_t* tempty = tfull + 1;                        // [1]
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < O2_ASTAGES; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
+        for (int i = 0; i < O2_BBUFS; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
+        mbar_init(tfull, 1);
+        mbar_init(tempty, OZ_EPI_WARPS);
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem_base = *tmem_slot;
+
+    const int S = MODE == 0 ? 1 : p.nslices;
+    const int KB = p.kblocks;
+
+    if (warp == 0) {
+        {  // ===== TMA producer: per K-block A_0, B_0..B_{S-1}, A_1, ..., A_{S-1} (consumption order) =====
+            TileWalk w; w.init(p);
+            int astage = 0; unsigned aphase = 0; unsigned kbc = 0;
+            int tm, tn;
+            for (long long idx = blockIdx.x; w.seek(p, idx, tm, tn); idx += gridDim.x) {
+                const int m0 = tm * OZ_BM, n0 = tn * O2_BN;
+                for (int kb = 0; kb < KB; ++kb, ++kbc) {
+                    const int par = (int)(kbc & 1u);
+                    const unsigned bph = (kbc >> 1) & 1u;
+                    for (int pl = 0; pl < S; ++pl) {
+                        mbar_wait_bounded(&aempty[astage], aphase ^ 1u);
+                        if (elect_one()) {
+                            if (p.noload) {
+                                mbar_arrive(&afull[astage]);
+                            } else {
+                                mbar_arrive_expect_tx(&afull[astage], O2_A_BYTES);
+                                tma_load_2d(smem + astage * O2_A_BYTES, &tmA, &afull[astage], (pl * KB + kb) * OZ_BK, m0);
+                            }
+                        }
+                        __syncwarp();
+                        if (++astage == O2_ASTAGES) { astage = 0; aphase ^= 1u; }
+                        if (pl == 0) {
+                            for (int q = 0; q < S; ++q) {
+                                const int buf = par * 8 + q;
+                                mbar_wait_bounded(&bempty[buf], bph ^ 1u);
+                                if (elect_one()) {
+                                    if (p.noload) {
+                                        mbar_arrive(&bfull[buf]);
+                                    } else {
+                                        mbar_arrive_expect_tx(&bfull[buf], O2_B_BYTES);
+                                        tma_load_2d(sBbase + buf * O2_B_BYTES, &tmB, &bfull[buf], (q * KB + kb) * OZ_BK, n0);
+                                    }
+                                }
+                                __syncwarp();
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        {  // ===== MMA issuer =====
+            TileWalk w; w.init(p);
+            int astage = 0; unsigned aphase = 0; unsigned kbc = 0; unsigned tph = 0;
+            int tm, tn;
+            for (long long idx = blockIdx.x; w.seek(p, idx, tm, tn); idx += gridDim.x) {
+                mbar_wait_bounded(tempty, tph ^ 1u);
+                tc_fence_after();
+                for (int kb = 0; kb < KB; ++kb, ++kbc) {
+                    const int par = (int)(kbc & 1u);
+                    const unsigned bph = (kbc >> 1) & 1u;
+                    for (int pl = 0; pl < S; ++pl) {
+                        mbar_wait_bounded(&afull[astage], aphase);
+                        const uint64_t da = umma_desc_k_sw128(smem_u32(smem + astage * O2_A_BYTES));
+                        for (int q = 0; q < S - pl; ++q) {
+                            const int buf = par * 8 + q;
+                            if (pl == 0) mbar_wait_bounded(&bfull[buf], bph);
+                            tc_fence_after();
+                            const uint64_t db = umma_desc_k_sw128(smem_u32(sBbase + buf * O2_B_BYTES));
+                            const unsigned d_tmem = tmem_base + (unsigned)((pl + q) * O2_BN);
+                            if (elect_one()) {
+#pragma unroll
+                                for (int kk = 0; kk < OZ_BK / 32; ++kk)
+                                    tc_mma_i8(d_tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), O2_IDESC,
+                                              !(kb == 0 && pl == 0 && kk == 0));
+                            }
+                            __syncwarp();
+                        }
+                        if (elect_one()) {
+                            tc_commit(&aempty[astage]);                  // A_pl fully consumed
+                            tc_commit(&bempty[par * 8 + (S - 1 - pl)]);  // B_{S-1-pl} had its last reader in this sweep
+                            if (kb == KB - 1 && pl == S - 1) tc_commit(tfull);
+                        }
+                        __syncwarp();
+                        if (++astage == O2_ASTAGES) { astage = 0; aphase ^= 1u; }
+                    }
+                }
+                tph ^= 1u;
+            }
+        }
+    } else if (warp >= OZ_EPI_WARP0) {
+        // ===== epilogue: warp (4 + 4 h + q4) owns TMEM lanes [32 q4, 32 q4 + 32) and tile columns [32 h, 32 h + 32) =====
+        const int q4 = warp & 3, h = (warp - OZ_EPI_WARP0) >> 2;
+        TileWalk w; w.init(p);
+        unsigned eph = 0;
+        int tm, tn;
+        for (long long idx = blockIdx.x; w.seek(p, idx, tm, tn); idx += gridDim.x) {
+            const int row = tm * OZ_BM + q4 * 32 + lane;
+            const int col0 = tn * O2_BN + h * 32;
+            double accd[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) accd[j] = 0.0;
+            mbar_wait_bounded(tfull, eph);
+            tc_fence_after();
+            for (int t = 0; t < S; ++t) {
+                unsigned r[32];
+                tc_ld32(tmem_base + ((unsigned)(q4 * 32) << 16) + (unsigned)(t * O2_BN + h * 32), r);
+                if (MODE == 1) {
+                    const double sc = __hiloint2double((1023 - OZ_BETA * (t + 2)) << 20, 0);  // 2^(-7 (t+2))
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) accd[j] = fma(exact_i2d((int)r[j]), sc, accd[j]);
+                } else if (row < p.m) {
+                    int* dst = p.Ci + (long long)row * p.ldci + col0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (col0 + j < p.n) dst[j] = (int)r[j];
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty);
+            eph ^= 1u;
+            if (MODE == 1 && row < p.m) {
+                const double sr = p.alpha * __ldg(p.sa + row);
+                double* crow = p.C + (long long)row * p.ldc;
+                const long long grow = p.row0 + row;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
                     const int col = col0 + j;
                     bool live = col < p.n;
                     if (p.mask == 1) live = live && (grow >= p.col0 + col);
@@ -396,13 +616,13 @@ EncodeTiledFn encode_tiled() {
     return fn;
 }
 // digit matrix [rows, width] int8, row stride ld bytes -> 2-D map with a {128 B, 128 rows} box
-int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t width, int64_t ld) {
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t width, int64_t ld, int box_rows) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return GPB_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld & 15)) return GPB_ERR_INVALID;
     cuuint64_t dims[2] = {(cuuint64_t)width, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld};
-    cuuint32_t box[2] = {(cuuint32_t)OZ_BK, (cuuint32_t)OZ_BM};
+    cuuint32_t box[2] = {(cuuint32_t)OZ_BK, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -418,20 +638,61 @@ int sm_count() {
     }();
     return n;
 }
-template <int MODE>
-int launch(stream_t s, const CUtensorMap& ta, const CUtensorMap& tb, OzParams& p) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(ozaki_i8_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES) != cudaSuccess)
-            return GPB_ERR_LAUNCH;
-        attr_set = true;
+int g_variant = -1;  // 1: order-by-order schedule (v1, default: measured faster), 2: plane-resident schedule (GPB_OZ_KERNEL=2)
+int variant() {
+    if (g_variant < 0) {
+        const char* e = std::getenv("GPB_OZ_KERNEL");
+        g_variant = (e && std::atoi(e) == 2) ? 2 : 1;
     }
+    return g_variant;
+}
+template <int MODE>
+int launch(stream_t s, const void* A, int64_t rowsA, int64_t lda, const void* B, int64_t rowsB, int64_t ldb, int64_t width,
+           OzParams& p) {
+    const int v = variant();
+    static bool attr_set[3] = {false, false, false};
+    if (!attr_set[v]) {
+        cudaError_t e = v == 1 ? cudaFuncSetAttribute(ozaki_i8_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES)
+                               : cudaFuncSetAttribute(ozaki_i8_kernel_v2<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, O2_SMEM_BYTES);
+        if (e != cudaSuccess) return GPB_ERR_LAUNCH;
+        attr_set[v] = true;
+    }
+    p.bn = v == 1 ? OZ_BN : O2_BN;
+    {
+        static int noload = [] { const char* e = std::getenv("GPB_OZ_NOLOAD"); return (e && std::atoi(e) == 1) ? 1 : 0; }();
+        p.noload = noload;
+    }
+    CUtensorMap ta, tb;
+    int rc = make_map(&ta, A, rowsA, width, lda, OZ_BM);
+    if (rc) return rc;
+    rc = make_map(&tb, B, rowsB, width, ldb, p.bn);
+    if (rc) return rc;
     p.ntm = (p.m + OZ_BM - 1) / OZ_BM;
-    p.ntn = (p.n + OZ_BN - 1) / OZ_BN;
+    p.ntn = (p.n + p.bn - 1) / p.bn;
     long long tiles = (long long)p.ntm * p.ntn;  // upper bound on the live tiles; CTAs beyond the live count exit at once
     int grid = (int)(tiles < sm_count() ? tiles : sm_count());
     if (grid <= 0) return GPB_OK;
-    ozaki_i8_kernel<MODE><<<grid, OZ_THREADS, OZ_SMEM_BYTES, to_stream(s)>>>(ta, tb, p);
+    const bool prof = profile_enabled();
+    if (prof) {  // algorithmic int8 operations: live output entries x K x digit pairs x 2
+        double live = 0.0;
+        for (long long i = 0; i < p.m; ++i) {
+            long long c = p.n;
+            if (p.mask == 1) {
+                c = p.row0 + i - p.col0 + 1;
+                c = c < 0 ? 0 : (c > p.n ? p.n : c);
+            } else if (p.mask == 2) {
+                long long first = ((p.row0 + i) / p.mask_nb + 1) * p.mask_nb - p.col0;
+                first = first < 0 ? 0 : (first > p.n ? p.n : first);
+                c = p.n - first;
+            }
+            live += (double)c;
+        }
+        const int S = MODE == 0 ? 1 : p.nslices;
+        profile_ozaki_begin(s, 2.0 * live * (double)p.kblocks * OZ_BK * (S * (S + 1) / 2));
+    }
+    if (v == 1) ozaki_i8_kernel<MODE><<<grid, OZ_THREADS, OZ_SMEM_BYTES, to_stream(s)>>>(ta, tb, p);
+    else ozaki_i8_kernel_v2<MODE><<<grid, OZ_THREADS, O2_SMEM_BYTES, to_stream(s)>>>(ta, tb, p);
+    if (prof) profile_gemm_end(s);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
 }
@@ -454,15 +715,10 @@ int igemm_i8(stream_t s, int64_t m, int64_t n, int64_t k, const int8_t* A, int64
     if (m < 0 || n < 0 || k <= 0 || !A || !B || !C) return GPB_ERR_INVALID;
     if (k % OZ_BK) return GPB_ERR_UNSUPPORTED;
     if (m == 0 || n == 0) return GPB_OK;
-    CUtensorMap ta, tb;
-    int rc = make_map(&ta, A, m, k, lda);
-    if (rc) return rc;
-    rc = make_map(&tb, B, n, k, ldb);
-    if (rc) return rc;
     OzParams p = {};
     p.m = (int)m; p.n = (int)n; p.kblocks = (int)(k / OZ_BK); p.nslices = 1;
     p.Ci = C; p.ldci = ldc;
-    return launch<0>(s, ta, tb, p);
+    return launch<0>(s, A, m, lda, B, n, ldb, k, p);
 }
 
 int ozaki_gemm(stream_t s, const OzakiGemmDesc& d) {
@@ -471,16 +727,11 @@ int ozaki_gemm(stream_t s, const OzakiGemmDesc& d) {
     if (d.K % OZ_BK || d.K > 32768) return GPB_ERR_UNSUPPORTED;
     if (d.mask != MASK_NONE && d.mask != MASK_LOWER && d.mask != MASK_BLOCK_STRICT_UPPER) return GPB_ERR_UNSUPPORTED;
     if (d.M == 0 || d.N == 0) return GPB_OK;
-    CUtensorMap ta, tb;
-    int rc = make_map(&ta, d.Qa, d.M, (int64_t)d.nslices * d.K, d.ldqa);
-    if (rc) return rc;
-    rc = make_map(&tb, d.Qb, d.N, (int64_t)d.nslices * d.K, d.ldqb);
-    if (rc) return rc;
     OzParams p = {};
     p.m = (int)d.M; p.n = (int)d.N; p.kblocks = (int)(d.K / OZ_BK); p.nslices = d.nslices;
     p.mask = d.mask == MASK_LOWER ? 1 : (d.mask == MASK_BLOCK_STRICT_UPPER ? 2 : 0); p.row0 = d.mask_row0; p.col0 = d.mask_col0; p.mask_nb = d.mask_nb > 0 ? d.mask_nb : 1;
     p.C = d.C; p.ldc = d.ldc; p.sa = d.sa; p.sb = d.sb; p.alpha = d.alpha;
-    return launch<1>(s, ta, tb, p);
+    return launch<1>(s, d.Qa, d.M, d.ldqa, d.Qb, d.N, d.ldqb, (int64_t)d.nslices * d.K, p);
 }
 
 bool ozaki_available() { return encode_tiled() != nullptr; }

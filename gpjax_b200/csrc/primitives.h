@@ -298,6 +298,9 @@ void profile_count_launch();
 bool profile_enabled();
 void profile_gemm_begin(stream_t s);
 void profile_gemm_end(stream_t s);
+// same bracket for the Ozaki int8 kernel (profile_gemm_end closes it); int8_ops = algorithmic int8 operations of the launch
+void profile_ozaki_begin(stream_t s, double int8_ops);
+int profile_read_ozaki(double* ms, int64_t* launches, double* int8_ops);
 
 // maximum input dimension D the compiled kernels support
 int max_input_dim();

@@ -230,8 +230,9 @@ def ozaki_available() -> bool:
 
 
 def set_ozaki_slices(nslices: int) -> None:
-    """0: every blocked algorithm stays on the FP64 DMMA pipe (default); 5..8: rank-NB trailing updates of
-    ``lower_cholesky`` run as exact int8 digit-plane products (``tcgen05.mma kind::i8``) with that many planes."""
+    """0: every blocked algorithm stays on the FP64 DMMA pipe; 5..8: the large rank-NB trailing updates of
+    ``lower_cholesky`` / the inverse run as exact int8 digit-plane products (``tcgen05.mma kind::i8``) with that many
+    planes.  Library default: 7 (``GPB_OZAKI`` in the environment overrides it at load time)."""
     lib().gpb_set_ozaki_slices(int(nslices))
 
 

@@ -58,6 +58,8 @@ int64_t gpb_block_size(void); /* NB of the blocked algorithms */
 void gpb_profile_reset(int enable);
 void gpb_debug_set_gemm_variant(int v); /* kernel-tuning hook for scripts/gemm_bench.py; 0 = default */
 int gpb_profile_read(double* gemm_ms, int64_t* gemm_launches, int64_t* all_launches);
+/* same for the launches of the int8 (Ozaki) kernel: summed duration, count, algorithmic int8 operations (2 x MACs) */
+int gpb_profile_read_ozaki(double* ms, int64_t* launches, double* int8_ops);
 
 /* ---- K1: fused Gram / cross-covariance -------------------------------------------------------
  * Replaces DenseKernelComputation._cross_covariance (gpjax/kernels/computations/dense.py:32-36),
@@ -121,8 +123,9 @@ int gpb_gemm(void* stream, int64_t M, int64_t N, int64_t K, double alpha, const 
  *   scale    : fp64 [rows], 2^e_i (NaN for a row holding NaN/Inf -> NaN output, JAX semantics)
  *   K        : multiple of 128
  * gpb_igemm_i8 exposes the raw integer product (C int32 = A B^T) for bit-exact testing.
- * gpb_set_ozaki_slices(s): s in {0, 5..8}; 0 (default) keeps every blocked algorithm on the FP64 DMMA pipe, otherwise
- * the rank-NB trailing updates of the factorisation family run through gpb_ozaki_gemm with s digit planes. */
+ * gpb_set_ozaki_slices(s): s in {0, 5..8}; 0 keeps every blocked algorithm on the FP64 DMMA pipe, otherwise the rank-NB
+ * trailing updates (>= 2048 output rows) of potrf / trtri / lauum run through gpb_ozaki_gemm with s digit planes.
+ * Default: 7 (environment variable GPB_OZAKI overrides; 8 = fp64 rounding level, 0 = DMMA only). */
 int gpb_ozaki_available(void);
 void gpb_set_ozaki_slices(int nslices);
 int gpb_get_ozaki_slices(void);

@@ -48,6 +48,10 @@ def main():
                               "int8_Pop_s": flop * s * (s + 1) / 2 / t_g / 1e15})
         del Q, sc
     del X, C
+    import os
+    if os.environ.get("OZ_BENCH_QUICK"):
+        json.dump(out, sys.stdout, indent=1)
+        return
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
     rng = np.random.default_rng(0)
     Xd = torch.as_tensor(rng.uniform(-2, 2, (n, 8)), device="cuda")
@@ -56,7 +60,7 @@ def main():
     ws = ops.FactorWorkspace(n, 8, potri=False, device="cuda")
     A = torch.empty(n, n, dtype=torch.float64, device="cuda")
     L0 = None
-    for s in (0, 7, 6):
+    for s in (0, 7, 8):
         ops.set_ozaki_slices(s)
 
         def run():
@@ -80,7 +84,7 @@ def main():
     y = torch.as_tensor(np.sin(rng.uniform(-2, 2, (n, 1))), device="cuda")
     base = None
     out["mll_step"] = []
-    for s in (0, 7, 6):
+    for s in (0, 7, 8):
         ops.set_ozaki_slices(s)
         p = [ell.clone().requires_grad_(True), one.clone().requires_grad_(True),
              torch.tensor(0.3, dtype=torch.float64, device="cuda", requires_grad=True),

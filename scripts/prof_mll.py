@@ -34,3 +34,12 @@ elif mode == "gemm":
     for _ in range(2):
         ops.gemm(A, A, C)
     torch.cuda.synchronize()
+elif mode == "ozaki":
+    # one lower-masked rank-1024 update of the potrf shape through the int8 digit-plane kernel (for ncu --set full)
+    m, k, s = 16384, 1024, 7
+    X = torch.randn(m, k, dtype=torch.float64, device=dev) * 0.05
+    Cb = torch.zeros(m, m, dtype=torch.float64, device=dev)
+    Q, sc = ops.ozaki_slice(X, s)
+    for _ in range(2):
+        ops.ozaki_gemm_(Cb, Q, sc, Q, sc, k, s, alpha=-1.0, mask_lower=True)
+    torch.cuda.synchronize()

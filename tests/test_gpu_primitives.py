@@ -162,10 +162,13 @@ def test_potrf_trsv_trsm_logdet_potri(n):
     b = rng.standard_normal(n)
     import scipy.linalg as sla
 
+    # n < 3072: every update is FP64 DMMA -> elementwise agreement; above, the int8 digit-plane updates (7 planes by
+    # default) leave L within 1e-12 normwise (asserted above), which bounds the solve normwise, not per tiny component
+    close = (lambda a, r: rel(a, r) <= 1e-9) if n < 3072 else (lambda a, r: np.max(np.abs(a - r)) <= 1e-10 * np.max(np.abs(r)))
     x = ops.trsv_lower_(A, dev(b), ws).cpu().numpy()
-    assert rel(x, sla.solve_triangular(Lref, b, lower=True)) <= 1e-9
+    assert close(x, sla.solve_triangular(Lref, b, lower=True))
     xt = ops.trsv_lower_(A, dev(b), ws, trans=True).cpu().numpy()
-    assert rel(xt, sla.solve_triangular(Lref.T, b, lower=False)) <= 1e-9
+    assert close(xt, sla.solve_triangular(Lref.T, b, lower=False))
     T = min(n, 37)
     Bm = rng.standard_normal((n, T))
     Xm = ops.trsm_lower_left_(A, dev(Bm), ws).cpu().numpy()
