@@ -319,7 +319,12 @@ def bench_exact(D: Dist, args):
                 "whole_step_tflops": flops_per_eval * args.steps / t / 1e12,
                 "whole_step_vs_fp64_dmma_peak": flops_per_eval * args.steps / t / 1e12 / NOMINAL_FP64_TFLOPS,
                 "fp64_dmma_peak": NOMINAL_FP64_TFLOPS, "measured_peaks_json": mp, "remaining_dmma_gemms": dmma,
-                "traffic": None}
+                # one `ncu --set full` capture of a single launch (lower-masked 16384^2 update, K=1024, 7 planes;
+                # profiles/r01_ozaki.md): dram__bytes_read.sum 1.387 GB + dram__bytes_write.sum 1.036 GB, against the
+                # algorithmic bytes of THAT launch: read + write of the live fp64 C entries (16384 * 16385 / 2 * 16 B) +
+                # the digit planes once (16384 * 7168 B)
+                "traffic": 2.423e9, "traffic_unit": "bytes per launch (the captured 16384^2 launch)",
+                "algorithmic_bytes": 16384 * 16385 / 2 * 16 + 16384 * 7168.0}
         # the same step with every update on the FP64 DMMA pipe (GPB_OZAKI=0), timed live for comparison
         ops.set_ozaki_slices(0)
         t_dmma = timed(D, step, 1, 1)

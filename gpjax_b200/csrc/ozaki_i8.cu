@@ -13,7 +13,7 @@
 // relative to the row maxima -- measured against the DMMA product in tests/test_gpu_ozaki.py and DESIGN section 12).
 //
 // Kernel (persistent, one CTA per SM, 12 warps, warp-specialised):
-//   warp 0      TMA producer: cp.async.bulk.tensor.2d of 128 x 128-byte digit tiles (SWIZZLE_128B) into a 6-stage ring
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d of 128 x 128-byte digit tiles (SWIZZLE_128B) into a 3-stage ring of 2 K-blocks
 //   warp 1      MMA issuer  : one thread issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=128, K=32 per instruction),
 //                             tcgen05.commit releases ring slots / publishes accumulators through mbarriers
 //   warp 2      TMEM allocator (512 columns = 4 accumulator stages of 128 x 128 int32)
@@ -33,8 +33,10 @@ namespace gpb {
 namespace {
 
 constexpr int OZ_BM = 128, OZ_BN = 128, OZ_BK = 128;  // BK in bytes == int8 elements == one 128-byte swizzle row
-constexpr int OZ_STAGES = 6;
-constexpr int OZ_STAGE_BYTES = (OZ_BM + OZ_BN) * OZ_BK;  // 32 KB
+constexpr int OZ_KBS_MAX = 2;                            // 128-byte K-blocks per ring stage (2 when the plane has an even count)
+constexpr int OZ_STAGES = 3;
+constexpr int OZ_KB_BYTES = (OZ_BM + OZ_BN) * OZ_BK;     // 32 KB: one (A, B) K-block pair
+constexpr int OZ_STAGE_BYTES = OZ_KBS_MAX * OZ_KB_BYTES;  // 64 KB
 constexpr int OZ_ACC_STAGES = 4;                         // x 128 TMEM columns
 constexpr int OZ_THREADS = 384;
 constexpr int OZ_EPI_WARP0 = 4, OZ_EPI_WARPS = 8;
@@ -56,6 +58,7 @@ struct OzParams {
     const double* sb;     // 2^eb_j
     double alpha;
     int ntm, ntn;
+    int kbs;              // K-blocks per ring stage (v1): 1 or 2
     int noload;           // measurement hook (GPB_OZ_NOLOAD=1): the producer signals `full` without issuing TMA -> pure MMA pacing
     int bn;               // output tile width of the launched kernel variant (128: v1, 64: v2)
 };
@@ -240,16 +243,18 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int t = 0; t < groups; ++t) {
                     for (int pa = 0; pa <= t; ++pa) {
                         const int xa0 = pa * p.kblocks * OZ_BK, xb0 = (t - pa) * p.kblocks * OZ_BK;
-                        for (int kb = 0; kb < p.kblocks; ++kb) {
+                        for (int kb = 0; kb < p.kblocks; kb += p.kbs) {
                             mbar_wait_bounded(&empty[stage], phase ^ 1u);
                             uint8_t* sA = smem + stage * OZ_STAGE_BYTES;
                             if (elect_one()) {
                                 if (p.noload) {
                                     mbar_arrive(&full[stage]);
                                 } else {
-                                    mbar_arrive_expect_tx(&full[stage], OZ_STAGE_BYTES);
-                                    tma_load_2d(sA, &tmA, &full[stage], xa0 + kb * OZ_BK, m0);
-                                    tma_load_2d(sA + OZ_BM * OZ_BK, &tmB, &full[stage], xb0 + kb * OZ_BK, n0);
+                                    mbar_arrive_expect_tx(&full[stage], p.kbs * OZ_KB_BYTES);
+                                    for (int j = 0; j < p.kbs; ++j) {
+                                        tma_load_2d(sA + j * OZ_KB_BYTES, &tmA, &full[stage], xa0 + (kb + j) * OZ_BK, m0);
+                                        tma_load_2d(sA + j * OZ_KB_BYTES + OZ_BM * OZ_BK, &tmB, &full[stage], xb0 + (kb + j) * OZ_BK, n0);
+                                    }
                                 }
                             }
                             __syncwarp();
@@ -271,17 +276,20 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     tc_fence_after();
                     const unsigned d_tmem = tmem_base + (unsigned)(acc * OZ_BN);
                     const int nkb = (t + 1) * p.kblocks;
-                    for (int kb = 0; kb < nkb; ++kb) {
+                    for (int kb = 0; kb < nkb; kb += p.kbs) {
                         mbar_wait_bounded(&full[stage], phase);
                         tc_fence_after();
                         const unsigned sA = smem_u32(smem + stage * OZ_STAGE_BYTES);
-                        const uint64_t da = umma_desc_k_sw128(sA), db = umma_desc_k_sw128(sA + OZ_BM * OZ_BK);
                         if (elect_one()) {
+                            for (int j = 0; j < p.kbs; ++j) {
+                                const uint64_t da = umma_desc_k_sw128(sA + j * OZ_KB_BYTES);
+                                const uint64_t db = umma_desc_k_sw128(sA + j * OZ_KB_BYTES + OZ_BM * OZ_BK);
 #pragma unroll
-                            for (int kk = 0; kk < OZ_BK / 32; ++kk)  // +32 bytes along K inside the swizzle row = +2 in the address field
-                                tc_mma_i8(d_tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), OZ_IDESC, (kb | kk) != 0);
+                                for (int kk = 0; kk < OZ_BK / 32; ++kk)  // +32 bytes along K inside the swizzle row = +2 in the address field
+                                    tc_mma_i8(d_tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), OZ_IDESC, (kb | j | kk) != 0);
+                            }
                             tc_commit(&empty[stage]);  // frees the ring slot once these MMAs have read it
-                            if (kb == nkb - 1) tc_commit(&tfull[acc]);  // accumulator of order t complete
+                            if (kb + p.kbs >= nkb) tc_commit(&tfull[acc]);  // accumulator of order t complete
                         }
                         __syncwarp();
                         if (++stage == OZ_STAGES) { stage = 0; phase ^= 1u; }
@@ -658,6 +666,7 @@ int launch(stream_t s, const void* A, int64_t rowsA, int64_t lda, const void* B,
         attr_set[v] = true;
     }
     p.bn = v == 1 ? OZ_BN : O2_BN;
+    p.kbs = (p.kblocks % OZ_KBS_MAX == 0 && !std::getenv("GPB_OZ_KBS1")) ? OZ_KBS_MAX : 1;
     {
         static int noload = [] { const char* e = std::getenv("GPB_OZ_NOLOAD"); return (e && std::atoi(e) == 1) ? 1 : 0; }();
         p.noload = noload;
