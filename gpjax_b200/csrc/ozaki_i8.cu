@@ -35,6 +35,7 @@ namespace {
 constexpr int OZ_BM = 128, OZ_BN = 128, OZ_BK = 128;  // BK in bytes == int8 elements == one 128-byte swizzle row
 constexpr int OZ_KBS_MAX = 2;                            // 128-byte K-blocks per ring stage (2 when the plane has an even count)
 constexpr int OZ_STAGES = 3;
+constexpr int OZ_MAX_RING = 6;                           // ring slots: 3 x 64 KB (2 K-blocks each) or 6 x 32 KB (paired-order schedule)
 constexpr int OZ_KB_BYTES = (OZ_BM + OZ_BN) * OZ_BK;     // 32 KB: one (A, B) K-block pair
 constexpr int OZ_STAGE_BYTES = OZ_KBS_MAX * OZ_KB_BYTES;  // 64 KB
 constexpr int OZ_ACC_STAGES = 4;                         // x 128 TMEM columns
@@ -59,6 +60,8 @@ struct OzParams {
     double alpha;
     int ntm, ntn;
     int kbs;              // K-blocks per ring stage (v1): 1 or 2
+    int nstages, stage_bytes;  // ring geometry (v1)
+    int pair;             // v1: accumulate orders (t, t+1) together so every loaded A tile feeds two MMAs (see kernel)
     int noload;           // measurement hook (GPB_OZ_NOLOAD=1): the producer signals `full` without issuing TMA -> pure MMA pacing
     int bn;               // output tile width of the launched kernel variant (128: v1, 64: v2)
 };
@@ -205,9 +208,9 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const unsigned raw = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OZ_STAGES * OZ_STAGE_BYTES);
-    uint64_t* full = bars;                         // [STAGES]   TMA -> MMA
-    uint64_t* empty = bars + OZ_STAGES;            // [STAGES]   MMA -> TMA
-    uint64_t* tfull = bars + 2 * OZ_STAGES;        // [ACC]      MMA -> epilogue
+    uint64_t* full = bars;                         // [<= 6]     TMA -> MMA
+    uint64_t* empty = bars + OZ_MAX_RING;          // [<= 6]     MMA -> TMA
+    uint64_t* tfull = bars + 2 * OZ_MAX_RING;      // [ACC]      MMA -> epilogue
     uint64_t* tempty = tfull + OZ_ACC_STAGES;      // [ACC]      epilogue -> MMA
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty + OZ_ACC_STAGES);
 
@@ -217,7 +220,7 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < OZ_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < OZ_MAX_RING; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < OZ_ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], OZ_EPI_WARPS); }
         mbar_fence_init();
     }
@@ -240,12 +243,34 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             int tm, tn;
             for (long long idx = blockIdx.x; w.seek(p, idx, tm, tn); idx += gridDim.x) {
                 const int m0 = tm * OZ_BM, n0 = tn * OZ_BN;
-                for (int t = 0; t < groups; ++t) {
+                for (int t = 0; t < groups;) {
+                    if (p.pair && ((groups - t) & 1) == 0) {  // odd plane count: the cheapest order (t = 0) is the unpaired one
+                        // orders (t, t+1) together: stage i of a K-block holds (A_i, B_{t+1-i}), i = 0..t+1
+                        for (int kb = 0; kb < p.kblocks; ++kb) {
+                            for (int i = 0; i <= t + 1; ++i) {
+                                mbar_wait_bounded(&empty[stage], phase ^ 1u);
+                                uint8_t* sA = smem + stage * p.stage_bytes;
+                                if (elect_one()) {
+                                    if (p.noload) {
+                                        mbar_arrive(&full[stage]);
+                                    } else {
+                                        mbar_arrive_expect_tx(&full[stage], OZ_KB_BYTES);
+                                        tma_load_2d(sA, &tmA, &full[stage], (i * p.kblocks + kb) * OZ_BK, m0);
+                                        tma_load_2d(sA + OZ_BM * OZ_BK, &tmB, &full[stage], ((t + 1 - i) * p.kblocks + kb) * OZ_BK, n0);
+                                    }
+                                }
+                                __syncwarp();
+                                if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+                            }
+                        }
+                        t += 2;
+                        continue;
+                    }
                     for (int pa = 0; pa <= t; ++pa) {
                         const int xa0 = pa * p.kblocks * OZ_BK, xb0 = (t - pa) * p.kblocks * OZ_BK;
                         for (int kb = 0; kb < p.kblocks; kb += p.kbs) {
                             mbar_wait_bounded(&empty[stage], phase ^ 1u);
-                            uint8_t* sA = smem + stage * OZ_STAGE_BYTES;
+                            uint8_t* sA = smem + stage * p.stage_bytes;
                             if (elect_one()) {
                                 if (p.noload) {
                                     mbar_arrive(&full[stage]);
@@ -258,9 +283,10 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 }
                             }
                             __syncwarp();
-                            if (++stage == OZ_STAGES) { stage = 0; phase ^= 1u; }
+                            if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
                         }
                     }
+                    ++t;
                 }
             }
         }
@@ -271,7 +297,52 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             int acc = 0; unsigned aphase = 0;
             int tm, tn;
             for (long long idx = blockIdx.x; w.seek(p, idx, tm, tn); idx += gridDim.x) {
-                for (int t = 0; t < groups; ++t) {
+                for (int t = 0; t < groups;) {
+                    if (p.pair && ((groups - t) & 1) == 0) {  // odd plane count: the cheapest order (t = 0) is the unpaired one
+                        // orders (t, t+1) in two accumulators: when stage i = (A_i, B_{t+1-i}) lands,
+                        //   acc_hi += A_i B_{t+1-i}^T   and   acc_lo += A_{i-1} B_{t+1-i}^T  (A_{i-1} still sits in the previous stage),
+                        // so t+2 stage loads feed 2t+3 digit-pair products instead of 2t+3 loads.
+                        const int a_lo = acc; const unsigned ph_lo = aphase;
+                        if (++acc == OZ_ACC_STAGES) { acc = 0; aphase ^= 1u; }
+                        const int a_hi = acc; const unsigned ph_hi = aphase;
+                        if (++acc == OZ_ACC_STAGES) { acc = 0; aphase ^= 1u; }
+                        mbar_wait_bounded(&tempty[a_lo], ph_lo ^ 1u);
+                        mbar_wait_bounded(&tempty[a_hi], ph_hi ^ 1u);
+                        tc_fence_after();
+                        const unsigned d_lo = tmem_base + (unsigned)(a_lo * OZ_BN), d_hi = tmem_base + (unsigned)(a_hi * OZ_BN);
+                        int prev = 0;
+                        for (int kb = 0; kb < p.kblocks; ++kb) {
+                            for (int i = 0; i <= t + 1; ++i) {
+                                mbar_wait_bounded(&full[stage], phase);
+                                tc_fence_after();
+                                const unsigned sA = smem_u32(smem + stage * p.stage_bytes);
+                                const unsigned sP = smem_u32(smem + prev * p.stage_bytes);
+                                if (elect_one()) {
+                                    const uint64_t da = umma_desc_k_sw128(sA), db = umma_desc_k_sw128(sA + OZ_BM * OZ_BK);
+#pragma unroll
+                                    for (int kk = 0; kk < OZ_BK / 32; ++kk)
+                                        tc_mma_i8(d_hi, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), OZ_IDESC, (kb | i | kk) != 0);
+                                    if (i >= 1) {
+                                        const uint64_t dp = umma_desc_k_sw128(sP);
+#pragma unroll
+                                        for (int kk = 0; kk < OZ_BK / 32; ++kk)
+                                            tc_mma_i8(d_lo, dp + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), OZ_IDESC,
+                                                      !(kb == 0 && i == 1 && kk == 0));
+                                        tc_commit(&empty[prev]);  // A_{i-1} and its B are done
+                                    }
+                                    if (i == t + 1) {
+                                        tc_commit(&empty[stage]);  // last stage of this K-block: nothing pairs with A_{t+1} later
+                                        if (kb == p.kblocks - 1) { tc_commit(&tfull[a_lo]); tc_commit(&tfull[a_hi]); }
+                                    }
+                                }
+                                __syncwarp();
+                                prev = stage;
+                                if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+                            }
+                        }
+                        t += 2;
+                        continue;
+                    }
                     mbar_wait_bounded(&tempty[acc], aphase ^ 1u);
                     tc_fence_after();
                     const unsigned d_tmem = tmem_base + (unsigned)(acc * OZ_BN);
@@ -279,7 +350,7 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     for (int kb = 0; kb < nkb; kb += p.kbs) {
                         mbar_wait_bounded(&full[stage], phase);
                         tc_fence_after();
-                        const unsigned sA = smem_u32(smem + stage * OZ_STAGE_BYTES);
+                        const unsigned sA = smem_u32(smem + stage * p.stage_bytes);
                         if (elect_one()) {
                             for (int j = 0; j < p.kbs; ++j) {
                                 const uint64_t da = umma_desc_k_sw128(sA + j * OZ_KB_BYTES);
@@ -292,9 +363,10 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                             if (kb + p.kbs >= nkb) tc_commit(&tfull[acc]);  // accumulator of order t complete
                         }
                         __syncwarp();
-                        if (++stage == OZ_STAGES) { stage = 0; phase ^= 1u; }
+                        if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
                     }
                     if (++acc == OZ_ACC_STAGES) { acc = 0; aphase ^= 1u; }
+                    ++t;
                 }
             }
         }
@@ -667,6 +739,15 @@ int launch(stream_t s, const void* A, int64_t rowsA, int64_t lda, const void* B,
     }
     p.bn = v == 1 ? OZ_BN : O2_BN;
     p.kbs = (p.kblocks % OZ_KBS_MAX == 0 && !std::getenv("GPB_OZ_KBS1")) ? OZ_KBS_MAX : 1;
+    {
+        static int pair = [] { const char* e = std::getenv("GPB_OZ_PAIR"); return (e && std::atoi(e) == 0) ? 0 : 1; }();
+        p.pair = pair;
+    }
+    if (p.pair && p.nslices > 1) {  // paired orders: 6 slots of one (A, B) K-block pair
+        p.kbs = 1; p.nstages = OZ_MAX_RING; p.stage_bytes = OZ_KB_BYTES;
+    } else {
+        p.pair = 0; p.nstages = OZ_STAGES; p.stage_bytes = OZ_STAGE_BYTES;
+    }
     {
         static int noload = [] { const char* e = std::getenv("GPB_OZ_NOLOAD"); return (e && std::atoi(e) == 1) ? 1 : 0; }();
         p.noload = noload;
