@@ -149,3 +149,31 @@ def test_conjugate_mll_value_and_gradient_on_the_int8_pipe_vs_oracle():
     assert np.max(np.abs(p[0].grad.cpu().numpy() - gref["lengthscale"])) <= 1e-8 * np.max(np.abs(gref["lengthscale"]))
     assert abs(p[1].grad.item() - gref["variance"]) <= 1e-8 * abs(gref["variance"])
     assert abs(p[2].grad.item() - gref["obs_stddev"]) <= 1e-8 * abs(gref["obs_stddev"])
+
+
+@pytest.mark.parametrize("env", [{"GPB_OZ_KERNEL": "2"}, {"GPB_OZ_PAIR": "0"}, {"GPB_OZ_PAIR": "0", "GPB_OZ_KBS1": "1"}])
+def test_alternative_kernel_schedules_agree(env):
+    """The measured-but-not-default schedules (plane-resident variant 2, unpaired orders, one K-block per stage) are
+    selected by environment variables read at first launch, so each runs in its own process."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import torch; from gpjax_b200 import ops\n"
+        "g = torch.Generator(device='cuda').manual_seed(5)\n"
+        "A = torch.randn(1500, 1024, dtype=torch.float64, device='cuda', generator=g)\n"
+        "C0 = torch.randn(1500, 1500, dtype=torch.float64, device='cuda', generator=g)\n"
+        "for s, tol in ((7, 2e-12), (8, 2e-14)):\n"
+        "    Q, sc = ops.ozaki_slice(A, s); C = C0.clone()\n"
+        "    ops.ozaki_gemm_(C, Q, sc, Q, sc, 1024, s, alpha=-1.0, mask_lower=True)\n"
+        "    ref = torch.where(torch.ones_like(C0, dtype=torch.bool).tril(), C0 - A @ A.T, C0)\n"
+        "    err = float(((C - ref).abs() / (A.norm(dim=1).max() ** 2)).max())\n"
+        "    assert err <= tol, (s, err)\n"
+        "I = torch.randint(-128, 128, (300, 512), dtype=torch.int8, device='cuda', generator=g)\n"
+        "assert torch.equal(ops.igemm_i8(I, I[:200]).long(), (I.double() @ I[:200].double().T).long())\n"
+        "print('ok')\n"
+    )
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
