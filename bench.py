@@ -414,24 +414,38 @@ def bench_sgpr(D: Dist, args, steps=None, warmup=None):
     import ctypes as C
 
     gemm_ms, gemm_n, all_n = C.c_double(), C.c_int64(), C.c_int64()
+    oz_ms, oz_n, oz_ops = C.c_double(), C.c_int64(), C.c_double()
     L.gpb_profile_read(C.byref(gemm_ms), C.byref(gemm_n), C.byref(all_n))
+    L.gpb_profile_read_ozaki(C.byref(oz_ms), C.byref(oz_n), C.byref(oz_ops))
     L.gpb_profile_reset(0)
     value = n_total * steps / t
-    # Flop actually executed per point (per rank share).  The public default (statistics="auto") takes the raw-product route
-    # while Kzz is well conditioned: forward N M^2 (SYRK on [K_b|d|1]; the whitening is applied once to the M x M sums --
-    # SURVEY 8d's "accumulate Kzx Kxz first" variant, counted at its own, smaller figure) + backward 2 N M^2
-    # (dK_b = [K_b|d|1] Caug^T).  The reference formulation (TRSM + SYRK forward, statistics="whitened") is 4 M^2.
+    # Flop per point (per rank share).  The public default (statistics="auto") takes the raw-product route while Kzz is well
+    # conditioned: forward N M^2 (SYRK on [K_b|d|1]; the whitening is applied once to the M x M sums -- SURVEY 8d's
+    # "accumulate Kzx Kxz first" variant, counted at its own, smaller figure) + backward 2 N M^2 (dK_b = [K_b|d|1] Caug^T).
+    # The reference formulation (TRSM + SYRK forward, statistics="whitened") is 4 M^2.
     cond_est = sgpr_ops.kzz_condition_estimate(0, Z.detach(), ell.detach(), var.detach(), HYPER["jitter"])
     raw_route = cond_est <= sgpr_ops.RAW_STATISTICS_COND_LIMIT
     fpp = (3.0 if raw_route else 4.0) * m * m
     flops = fpp * (hi - lo)
-    achieved = flops * steps / (gemm_ms.value * 1e-3) / 1e12
-    roof = {"bound": "tensor", "kernel": "gemm_f64_kernel (FP64 DMMA.8x8x4)", "achieved": achieved,
+    int8_pass2 = oz_n.value > 0
+    # with the int8 route the backward product (2 M^2 per point) leaves the DMMA pipe: the DMMA GEMMs carry the forward only
+    dmma_flops = (fpp - 2.0 * m * m if int8_pass2 else fpp) * (hi - lo)
+    achieved = dmma_flops * steps / (gemm_ms.value * 1e-3) / 1e12
+    roof = {"bound": "tensor", "kernel": "gemm_f64_kernel (FP64 DMMA.8x8x4): pass-1 statistics SYRK", "achieved": achieved,
             "peak": NOMINAL_FP64_TFLOPS, "unit": "TFLOP/s", "frac": achieved / NOMINAL_FP64_TFLOPS,
             "algorithmic_flop_per_point": fpp, "reference_formulation_flop_per_point": 4.0 * m * m,
             "statistics_route": "raw" if raw_route else "whitened", "kzz_condition_estimate": cond_est,
             "gemm_time_over_step_time": gemm_ms.value * 1e-3 / t,
             "whole_step_tflops_per_gpu": flops * steps / t / 1e12, "traffic": None}
+    if int8_pass2:
+        mp = measured_peaks() or {}
+        peak8 = 2.0 * float(mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops") or 1414.5)
+        a8 = oz_ops.value / (oz_ms.value * 1e-3) / 1e12
+        roof["pass2_int8"] = {"kernel": "ozaki_i8_kernel (tcgen05.mma kind::i8), 8 digit planes: dK_b = [K_b|d|1] Caug^T",
+                              "achieved": a8, "peak": peak8, "unit": "TFLOP/s (int8 Top/s)", "frac": a8 / peak8,
+                              "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json",
+                              "fp64_equivalent_tflops": 2.0 * m * m * (hi - lo) * steps / (oz_ms.value * 1e-3) / 1e12,
+                              "time_over_step_time": oz_ms.value * 1e-3 / t, "launches_per_step": oz_n.value / steps}
 
     # e2e through the public API with host-resident shards
     prior = gpx.gps.Prior(mean_function=gpx.mean_functions.Constant(Real(HYPER["mean_const"])),

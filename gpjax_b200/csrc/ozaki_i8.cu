@@ -60,6 +60,7 @@ struct OzParams {
     double alpha;
     int ntm, ntn;
     int kbs;              // K-blocks per ring stage (v1): 1 or 2
+    int beta0;            // C = alpha A B^T instead of C += (C is never read)
     int nstages, stage_bytes;  // ring geometry (v1)
     int pair;             // v1: accumulate orders (t, t+1) together so every loaded A tile feeds two MMAs (see kernel)
     int noload;           // measurement hook (GPB_OZ_NOLOAD=1): the producer signals `full` without issuing TMA -> pure MMA pacing
@@ -419,7 +420,10 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     bool live = col < p.n;
                     if (p.mask == 1) live = live && (grow >= p.col0 + col);
                     else if (p.mask == 2) live = live && (grow / p.mask_nb < (p.col0 + col) / p.mask_nb);
-                    if (live) crow[col] += accd[j] * (sr * __ldg(p.sb + col));
+                    if (live) {
+                        const double v = accd[j] * (sr * __ldg(p.sb + col));
+                        crow[col] = p.beta0 ? v : crow[col] + v;
+                    }
                 }
             }
         }
@@ -618,7 +622,10 @@ ozaki_i8_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     bool live = col < p.n;
                     if (p.mask == 1) live = live && (grow >= p.col0 + col);
                     else if (p.mask == 2) live = live && (grow / p.mask_nb < (p.col0 + col) / p.mask_nb);
-                    if (live) crow[col] += accd[j] * (sr * __ldg(p.sb + col));
+                    if (live) {
+                        const double v = accd[j] * (sr * __ldg(p.sb + col));
+                        crow[col] = p.beta0 ? v : crow[col] + v;
+                    }
                 }
             }
         }
@@ -820,7 +827,7 @@ int ozaki_gemm(stream_t s, const OzakiGemmDesc& d) {
     OzParams p = {};
     p.m = (int)d.M; p.n = (int)d.N; p.kblocks = (int)(d.K / OZ_BK); p.nslices = d.nslices;
     p.mask = d.mask == MASK_LOWER ? 1 : (d.mask == MASK_BLOCK_STRICT_UPPER ? 2 : 0); p.row0 = d.mask_row0; p.col0 = d.mask_col0; p.mask_nb = d.mask_nb > 0 ? d.mask_nb : 1;
-    p.C = d.C; p.ldc = d.ldc; p.sa = d.sa; p.sb = d.sb; p.alpha = d.alpha;
+    p.C = d.C; p.ldc = d.ldc; p.sa = d.sa; p.sb = d.sb; p.alpha = d.alpha; p.beta0 = d.beta0;
     return launch<1>(s, d.Qa, d.M, d.ldqa, d.Qb, d.N, d.ldqb, (int64_t)d.nslices * d.K, p);
 }
 

@@ -268,7 +268,8 @@ struct OzakiGemmDesc {
     const int8_t* Qb = nullptr;   // [N, nslices*K]
     int64_t ldqb = 0;
     const double* sb = nullptr;   // [N]
-    double* C = nullptr;          // C += alpha * A B^T (all digit pairs of order p+q < nslices)
+    double* C = nullptr;          // C += alpha * A B^T (all digit pairs of order p+q < nslices); beta0: C = alpha * A B^T
+    int beta0 = 0;
     int64_t ldc = 0;
     double alpha = 1.0;
     int mask = MASK_NONE;         // MASK_NONE, MASK_LOWER or MASK_BLOCK_STRICT_UPPER (same meaning as GemmDesc::mask)

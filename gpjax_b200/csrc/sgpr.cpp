@@ -26,6 +26,8 @@ constexpr int SPLITK = 16;
 struct Lay {
     int64_t fz, fb, mm[13], vec[9], sc, dots, T1, T2, gpart, info, ppart, total;
     int64_t fz_bytes, fb_bytes;
+    int64_t oz_qt, oz_qc, oz_st, oz_sc, oz_kplane;
+    bool with_oz;
 };
 Lay layout(int64_t M, int D, int64_t Bs) {
     Lay L;
@@ -49,6 +51,13 @@ Lay layout(int64_t M, int D, int64_t Bs) {
     int64_t p1 = gram_bwd_partials_count(Bs, M, D), p2 = gram_bwd_partials_count(M, M, D);
     L.gpart = take(p1 > p2 ? p1 : p2);
     L.info = take(8);
+    // pass-2 digit planes: OZ_MAX_SLICES planes of kplane int8 digits per row == kplane doubles per row
+    L.with_oz = Bs >= OZ_MIN_ROWS && M >= 256;
+    L.oz_kplane = align_up(M + 2, 128);
+    L.oz_qt = take(L.with_oz ? Bs * L.oz_kplane : 0);
+    L.oz_qc = take(L.with_oz ? M * L.oz_kplane : 0);
+    L.oz_st = take(L.with_oz ? Bs : 0);
+    L.oz_sc = take(L.with_oz ? M : 0);
     L.total = o;
     return L;
 }
@@ -78,6 +87,11 @@ int sgpr_ws_carve(void* buf, int64_t bytes, int64_t M, int D, int64_t block_rows
     ws->gpart = b + L.gpart;
     ws->Ppart = b + L.ppart;
     ws->info2 = reinterpret_cast<int*>(b + L.info);
+    ws->oz_qt = L.with_oz ? reinterpret_cast<int8_t*>(b + L.oz_qt) : nullptr;
+    ws->oz_qc = L.with_oz ? reinterpret_cast<int8_t*>(b + L.oz_qc) : nullptr;
+    ws->oz_st = L.with_oz ? b + L.oz_st : nullptr;
+    ws->oz_sc = L.with_oz ? b + L.oz_sc : nullptr;
+    ws->oz_kplane = L.oz_kplane;
     return GPB_OK;
 }
 
@@ -252,15 +266,30 @@ int sgpr_grad_local(stream_t s, const SgprArgs& a, const SgprWs& ws, double* g_Z
     GPB_TRY(fill2d(s, M, a.D, g_Z, a.D, 0.0));
     GPB_TRY(fill2d(s, 1, a.ell_is_scalar ? 1 : a.D, g_ell, a.D, 0.0));
     GPB_TRY(fill2d(s, 1, kind_has_shape(a.kind) ? 2 : 1, g_var, 2, 0.0));
+    // int8 digit-plane route for the pass-2 product: Caug is sliced once, every block of T1 once
+    // Always 8 planes here (fp64-rounding-level products): Caug carries Kzz^-1-like rows, so the product cancels by a factor
+    // ~cond(Kzz) and a 7-plane truncation (2^-46 of the row maxima) would be amplified by it; 8 planes cost 13 % more time.
+    const int planes = (ws.oz_qt && ozaki_available() && get_ozaki_slices() != 0) ? OZ_MAX_SLICES : 0;
+    const int64_t kp = ws.oz_kplane, ldq = OZ_MAX_SLICES * kp;
+    if (planes) GPB_TRY(ozaki_slice(s, M, ld, kp, ws.Caug, ld, planes, ws.oz_qc, ldq, ws.oz_sc));
     for (int64_t r0 = 0; r0 < a.Nloc; r0 += a.block_rows) {
         const int64_t rows = (a.Nloc - r0) < a.block_rows ? (a.Nloc - r0) : a.block_rows;
         GPB_TRY(gram(s, gram_desc(a, a.X + r0 * a.ldx, a.ldx, rows, ws.T1, ld)));
         GPB_TRY(sgpr_aug_columns(s, rows, ws.T1, ld, M, a.y + r0, a.mean_const));
         // dK_b^T = [K_b^T | d_b | 1] Caug^T   (= K_b^T C + d_b cvec^T)
-        GemmDesc g;
-        g.M = rows; g.N = M; g.K = ld;
-        g.A = ws.T1; g.lda = ld; g.B = ws.Caug; g.ldb = ld; g.C = ws.T2; g.ldc = ld;
-        GPB_TRY(gemm(s, g));
+        if (planes && rows >= OZ_MIN_ROWS) {
+            GPB_TRY(ozaki_slice(s, rows, ld, kp, ws.T1, ld, planes, ws.oz_qt, ldq, ws.oz_st));
+            OzakiGemmDesc g;
+            g.M = rows; g.N = M; g.K = kp; g.nslices = planes;
+            g.Qa = ws.oz_qt; g.ldqa = ldq; g.sa = ws.oz_st; g.Qb = ws.oz_qc; g.ldqb = ldq; g.sb = ws.oz_sc;
+            g.C = ws.T2; g.ldc = ld; g.alpha = 1.0; g.beta0 = 1;
+            GPB_TRY(ozaki_gemm(s, g));
+        } else {
+            GemmDesc g;
+            g.M = rows; g.N = M; g.K = ld;
+            g.A = ws.T1; g.lda = ld; g.B = ws.Caug; g.ldb = ld; g.C = ws.T2; g.ldc = ld;
+            GPB_TRY(gemm(s, g));
+        }
         GramBwdDesc b;
         b.kind = a.kind; b.N = rows; b.M = M; b.D = a.D;
         b.X = a.X + r0 * a.ldx; b.ldx = a.ldx; b.Z = a.Z; b.ldz = a.ldz;

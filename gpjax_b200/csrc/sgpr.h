@@ -32,6 +32,10 @@ struct SgprWs {
     double *T1, *T2, *Ppart;
     double* gpart;
     int* info2;  // [2]: info of chol(Kzz), chol(B)
+    // int8 digit planes for the pass-2 product (null when the block is too small for the int8 path): T1 rows and Caug rows
+    int8_t *oz_qt = nullptr, *oz_qc = nullptr;
+    double *oz_st = nullptr, *oz_sc = nullptr;
+    int64_t oz_kplane = 0;  // digits per plane = M + 2 rounded up to 128
 };
 
 int64_t sgpr_ws_bytes(int64_t M, int D, int64_t block_rows);

@@ -506,7 +506,8 @@ int ozaki_gemm(stream_t, const OzakiGemmDesc& d) {
                 }
                 acc = std::fma((double)P, std::scalbn(1.0, -7 * (t + 2)), acc);
             }
-            d.C[i * d.ldc + j] += acc * (d.alpha * d.sa[i] * d.sb[j]);
+            const double v = acc * (d.alpha * d.sa[i] * d.sb[j]);
+            d.C[i * d.ldc + j] = d.beta0 ? v : d.C[i * d.ldc + j] + v;
         }
     return GPB_OK;
 }
