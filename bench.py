@@ -427,25 +427,33 @@ def bench_sgpr(D: Dist, args, steps=None, warmup=None):
     raw_route = cond_est <= sgpr_ops.RAW_STATISTICS_COND_LIMIT
     fpp = (3.0 if raw_route else 4.0) * m * m
     flops = fpp * (hi - lo)
-    int8_pass2 = oz_n.value > 0
-    # with the int8 route the backward product (2 M^2 per point) leaves the DMMA pipe: the DMMA GEMMs carry the forward only
-    dmma_flops = (fpp - 2.0 * m * m if int8_pass2 else fpp) * (hi - lo)
-    achieved = dmma_flops * steps / (gemm_ms.value * 1e-3) / 1e12
-    roof = {"bound": "tensor", "kernel": "gemm_f64_kernel (FP64 DMMA.8x8x4): pass-1 statistics SYRK", "achieved": achieved,
-            "peak": NOMINAL_FP64_TFLOPS, "unit": "TFLOP/s", "frac": achieved / NOMINAL_FP64_TFLOPS,
-            "algorithmic_flop_per_point": fpp, "reference_formulation_flop_per_point": 4.0 * m * m,
-            "statistics_route": "raw" if raw_route else "whitened", "kzz_condition_estimate": cond_est,
-            "gemm_time_over_step_time": gemm_ms.value * 1e-3 / t,
-            "whole_step_tflops_per_gpu": flops * steps / t / 1e12, "traffic": None}
-    if int8_pass2:
+    int8_route = oz_n.value > 0
+    # with the int8 route both streamed products (statistics SYRK, pass-2 dK_b) leave the DMMA pipe; what remains on it are the
+    # replicated M x M finishes and blocks below the row threshold
+    if int8_route:
         mp = measured_peaks() or {}
         peak8 = 2.0 * float(mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops") or 1414.5)
         a8 = oz_ops.value / (oz_ms.value * 1e-3) / 1e12
-        roof["pass2_int8"] = {"kernel": "ozaki_i8_kernel (tcgen05.mma kind::i8), 8 digit planes: dK_b = [K_b|d|1] Caug^T",
-                              "achieved": a8, "peak": peak8, "unit": "TFLOP/s (int8 Top/s)", "frac": a8 / peak8,
-                              "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json",
-                              "fp64_equivalent_tflops": 2.0 * m * m * (hi - lo) * steps / (oz_ms.value * 1e-3) / 1e12,
-                              "time_over_step_time": oz_ms.value * 1e-3 / t, "launches_per_step": oz_n.value / steps}
+        roof = {"bound": "tensor",
+                "kernel": "ozaki_i8_kernel (tcgen05.mma kind::i8, 8 digit planes): K_b^T K_b statistics + dK_b = [K_b|d|1] Caug^T",
+                "achieved": a8, "peak": peak8, "unit": "TFLOP/s", "frac": a8 / peak8,
+                "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (no int8 entry); unit is int8 Top/s (2 x MAC)",
+                "int8_ops_per_point": oz_ops.value / steps / (hi - lo), "time_over_step_time": oz_ms.value * 1e-3 / t,
+                "launches_per_step": oz_n.value / steps,
+                "algorithmic_flop_per_point": fpp, "reference_formulation_flop_per_point": 4.0 * m * m,
+                "statistics_route": "raw" if raw_route else "whitened", "kzz_condition_estimate": cond_est,
+                "whole_step_tflops_per_gpu": flops * steps / t / 1e12,
+                "whole_step_vs_fp64_dmma_peak": flops * steps / t / 1e12 / NOMINAL_FP64_TFLOPS,
+                "remaining_dmma_gemms": {"time_over_step_time": gemm_ms.value * 1e-3 / t, "launches_per_step": gemm_n.value / steps},
+                "traffic": None}
+    else:
+        achieved = flops * steps / (gemm_ms.value * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_f64_kernel (FP64 DMMA.8x8x4)", "achieved": achieved,
+                "peak": NOMINAL_FP64_TFLOPS, "unit": "TFLOP/s", "frac": achieved / NOMINAL_FP64_TFLOPS,
+                "algorithmic_flop_per_point": fpp, "reference_formulation_flop_per_point": 4.0 * m * m,
+                "statistics_route": "raw" if raw_route else "whitened", "kzz_condition_estimate": cond_est,
+                "gemm_time_over_step_time": gemm_ms.value * 1e-3 / t,
+                "whole_step_tflops_per_gpu": flops * steps / t / 1e12, "traffic": None}
 
     # e2e through the public API with host-resident shards
     prior = gpx.gps.Prior(mean_function=gpx.mean_functions.Constant(Real(HYPER["mean_const"])),
@@ -517,7 +525,9 @@ def bench_svgp(D: Dist, args):
     import ctypes as C
 
     gemm_ms, gemm_n, all_n = C.c_double(), C.c_int64(), C.c_int64()
+    oz_ms, oz_n, oz_ops = C.c_double(), C.c_int64(), C.c_double()
     L.gpb_profile_read(C.byref(gemm_ms), C.byref(gemm_n), C.byref(all_n))
+    L.gpb_profile_read_ozaki(C.byref(oz_ms), C.byref(oz_n), C.byref(oz_ops))
     L.gpb_profile_reset(0)
     value = D.world * batch * steps / t
     # streamed passes (3 B M^2 on the raw-statistics route "auto" takes for a well-conditioned Kzz, else 4 B M^2)
@@ -525,18 +535,31 @@ def bench_svgp(D: Dist, args):
     cond_est = sgpr_ops.kzz_condition_estimate(1, Z.detach(), ell.detach(), var.detach(), HYPER["jitter"])
     raw_route = cond_est <= sgpr_ops.RAW_STATISTICS_COND_LIMIT
     flops = (3.0 if raw_route else 4.0) * batch * m * m + 22.0 * m**3
+    if oz_n.value > 0:  # streamed products on the int8 pipe (8 digit planes); the M x M finish stays on DMMA
+        mp = measured_peaks() or {}
+        peak8 = 2.0 * float(mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops") or 1414.5)
+        a8 = oz_ops.value / (oz_ms.value * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "ozaki_i8_kernel (tcgen05.mma kind::i8, 8 digit planes)", "achieved": a8, "peak": peak8,
+                "unit": "TFLOP/s", "frac": a8 / peak8,
+                "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (no int8 entry); unit is int8 Top/s",
+                "time_over_step_time": oz_ms.value * 1e-3 / t, "algorithmic_flop_per_step": flops,
+                "whole_step_tflops_per_gpu": flops * steps / t / 1e12,
+                "remaining_dmma_gemms": {"time_over_step_time": gemm_ms.value * 1e-3 / t},
+                "statistics_route": "raw" if raw_route else "whitened", "kzz_condition_estimate": cond_est, "traffic": None}
+    else:
+        roof = {"bound": "tensor", "kernel": "gemm_f64_kernel (FP64 DMMA.8x8x4)",
+                "achieved": flops * steps / (gemm_ms.value * 1e-3) / 1e12, "peak": NOMINAL_FP64_TFLOPS,
+                "unit": "TFLOP/s", "frac": flops * steps / (gemm_ms.value * 1e-3) / 1e12 / NOMINAL_FP64_TFLOPS,
+                "algorithmic_flop_per_step": flops, "gemm_time_over_step_time": gemm_ms.value * 1e-3 / t,
+                "statistics_route": "raw" if raw_route else "whitened", "kzz_condition_estimate": cond_est,
+                "traffic": None}
     sgpr_ops.release_buffers()
     return dict(metric="SVGP elbo value+grad minibatch points/s", value=value, unit="points/s", n_gpus=D.world, steps=steps,
                 ms_per_step=1e3 * t / steps, scaling="weak", higher_is_better=True, vs_baseline=None, dtype="f64",
                 data="synthetic",
                 config={"workload": f"svgp_elbo_value_and_grad_N{n_total}_M{m}_D{d}_B{batch}_Matern32", "N": n_total,
                         "M": m, "D": d, "batch_per_gpu": batch, "resident_shard_rows": shard},
-                roofline={"bound": "tensor", "kernel": "gemm_f64_kernel (FP64 DMMA.8x8x4)",
-                          "achieved": flops * steps / (gemm_ms.value * 1e-3) / 1e12, "peak": NOMINAL_FP64_TFLOPS,
-                          "unit": "TFLOP/s", "frac": flops * steps / (gemm_ms.value * 1e-3) / 1e12 / NOMINAL_FP64_TFLOPS,
-                          "algorithmic_flop_per_step": flops, "gemm_time_over_step_time": gemm_ms.value * 1e-3 / t,
-                          "statistics_route": "raw" if raw_route else "whitened", "kzz_condition_estimate": cond_est,
-                          "traffic": None},
+                roofline=roof,
                 gpu_launches=int(all_n.value))
 
 

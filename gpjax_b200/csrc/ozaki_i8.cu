@@ -61,6 +61,7 @@ struct OzParams {
     int ntm, ntn;
     int kbs;              // K-blocks per ring stage (v1): 1 or 2
     int beta0;            // C = alpha A B^T instead of C += (C is never read)
+    int pstride;          // digits between consecutive planes of one row (>= kblocks * 128)
     int nstages, stage_bytes;  // ring geometry (v1)
     int pair;             // v1: accumulate orders (t, t+1) together so every loaded A tile feeds two MMAs (see kernel)
     int noload;           // measurement hook (GPB_OZ_NOLOAD=1): the producer signals `full` without issuing TMA -> pure MMA pacing
@@ -256,8 +257,8 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                         mbar_arrive(&full[stage]);
                                     } else {
                                         mbar_arrive_expect_tx(&full[stage], OZ_KB_BYTES);
-                                        tma_load_2d(sA, &tmA, &full[stage], (i * p.kblocks + kb) * OZ_BK, m0);
-                                        tma_load_2d(sA + OZ_BM * OZ_BK, &tmB, &full[stage], ((t + 1 - i) * p.kblocks + kb) * OZ_BK, n0);
+                                        tma_load_2d(sA, &tmA, &full[stage], i * p.pstride + kb * OZ_BK, m0);
+                                        tma_load_2d(sA + OZ_BM * OZ_BK, &tmB, &full[stage], (t + 1 - i) * p.pstride + kb * OZ_BK, n0);
                                     }
                                 }
                                 __syncwarp();
@@ -268,7 +269,7 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                         continue;
                     }
                     for (int pa = 0; pa <= t; ++pa) {
-                        const int xa0 = pa * p.kblocks * OZ_BK, xb0 = (t - pa) * p.kblocks * OZ_BK;
+                        const int xa0 = pa * p.pstride, xb0 = (t - pa) * p.pstride;
                         for (int kb = 0; kb < p.kblocks; kb += p.kbs) {
                             mbar_wait_bounded(&empty[stage], phase ^ 1u);
                             uint8_t* sA = smem + stage * p.stage_bytes;
@@ -516,7 +517,7 @@ ozaki_i8_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                                 mbar_arrive(&afull[astage]);
                             } else {
                                 mbar_arrive_expect_tx(&afull[astage], O2_A_BYTES);
-                                tma_load_2d(smem + astage * O2_A_BYTES, &tmA, &afull[astage], (pl * KB + kb) * OZ_BK, m0);
+                                tma_load_2d(smem + astage * O2_A_BYTES, &tmA, &afull[astage], pl * p.pstride + kb * OZ_BK, m0);
                             }
                         }
                         __syncwarp();
@@ -530,7 +531,7 @@ ozaki_i8_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                                         mbar_arrive(&bfull[buf]);
                                     } else {
                                         mbar_arrive_expect_tx(&bfull[buf], O2_B_BYTES);
-                                        tma_load_2d(sBbase + buf * O2_B_BYTES, &tmB, &bfull[buf], (q * KB + kb) * OZ_BK, n0);
+                                        tma_load_2d(sBbase + buf * O2_B_BYTES, &tmB, &bfull[buf], q * p.pstride + kb * OZ_BK, n0);
                                     }
                                 }
                                 __syncwarp();
@@ -688,6 +689,104 @@ __global__ void __launch_bounds__(128) ozaki_slice_kernel(long long rows, int k,
     }
 }
 
+// ---- digit extraction along COLUMNS (contraction over the rows of X): Qt[c, p*kplane + r] = digit p of X[r, c] ------------
+// used by the SGPR statistics SYRK  K_b^T K_b  (operand "rows" are the columns of the rows x M block, K = block rows)
+__global__ void __launch_bounds__(256) col_absmax_kernel(long long rows, int cols, const double* __restrict__ X, long long ldx,
+                                                         unsigned long long* __restrict__ colmax_bits) {
+    // |x| as an unsigned 64-bit pattern is order preserving for non-negative doubles, Inf < NaN patterns: the max propagates NaN
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const long long r_begin = (long long)blockIdx.y * 1024;
+    const long long r_end = r_begin + 1024 < rows ? r_begin + 1024 : rows;
+    unsigned long long m = 0ull;
+    if (c < cols)
+        for (long long r = r_begin + (threadIdx.x >> 5); r < r_end; r += 8) {
+            unsigned long long b = (unsigned long long)__double_as_longlong(fabs(X[r * ldx + c]));
+            m = b > m ? b : m;
+        }
+    __shared__ unsigned long long red[8][32];
+    red[threadIdx.x >> 5][threadIdx.x & 31] = m;
+    __syncthreads();
+    if (threadIdx.x < 32 && c < cols) {
+        for (int i = 1; i < 8; ++i) m = red[i][threadIdx.x] > m ? red[i][threadIdx.x] : m;
+        atomicMax(colmax_bits + c, m);
+    }
+}
+// tile of 128 rows x 32 columns per CTA: coalesced reads along the columns, digits staged in shared memory, 128-byte
+// contiguous writes along r for every (plane, column); rows >= `rows` (up to kplane) are written as zero digits
+__global__ void __launch_bounds__(256) ozaki_slice_t_kernel(long long rows, int cols, long long kplane, const double* __restrict__ X,
+                                                            long long ldx, int nslices, signed char* __restrict__ Qt, long long ldq,
+                                                            const unsigned long long* __restrict__ colmax_bits,
+                                                            double* __restrict__ scale) {
+    __shared__ signed char dig[8][32][128 + 16];
+    const int c0 = blockIdx.x * 32;
+    const long long r0 = (long long)blockIdx.y * 128;
+    const int lc = threadIdx.x & 31;
+    const int c = c0 + lc;
+    double mx = 0.0;
+    int e = 0;
+    bool nanrow = false;
+    if (c < cols) {
+        mx = __longlong_as_double((long long)colmax_bits[c]);
+        nanrow = !(mx <= 1.7976931348623157e308);
+        if (!nanrow && mx != 0.0) e = ilogb(mx) + 2;
+        if (blockIdx.y == 0 && threadIdx.x < 32)
+            scale[c] = nanrow ? __longlong_as_double(0x7ff8000000000000LL) : (mx == 0.0 ? 1.0 : scalbn(1.0, e));
+    }
+    for (int lr = threadIdx.x >> 5; lr < 128; lr += 8) {
+        const long long r = r0 + lr;
+        double R = (c < cols && r < rows && !nanrow) ? scalbn(X[r * ldx + c], -e) : 0.0;
+        for (int p = 0; p < nslices; ++p) {
+            R *= 128.0;
+            double d = rint(R);
+            dig[p][lc][lr] = (signed char)(int)d;
+            R -= d;
+        }
+    }
+    __syncthreads();
+    // write-out: (plane, column) rows of 128 bytes, 4 bytes per thread
+    const int total = nslices * 32 * 32;  // 4-byte words
+    for (int w = threadIdx.x; w < total; w += 256) {
+        const int p = w / (32 * 32), rem = w % (32 * 32), cc = rem / 32, word = rem % 32;
+        if (c0 + cc < cols)
+            *reinterpret_cast<int*>(Qt + (long long)(c0 + cc) * ldq + (long long)p * kplane + r0 + word * 4) =
+                *reinterpret_cast<const int*>(&dig[p][cc][word * 4]);
+    }
+}
+
+// ---- out_w[c] += sum_r w[r] X[r,c],  out_1[c] += sum_r X[r,c]  (the two augmented rows of the SGPR statistics) -------------
+// two stages so the summation order is fixed: per-1024-row partials, then an ordered reduction
+__global__ void __launch_bounds__(256) col_wsum_partial_kernel(long long rows, int cols, const double* __restrict__ X, long long ldx,
+                                                               const double* __restrict__ w, double* __restrict__ part) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const long long r_begin = (long long)blockIdx.y * 1024;
+    const long long r_end = r_begin + 1024 < rows ? r_begin + 1024 : rows;
+    double sw = 0.0, s1 = 0.0;
+    if (c < cols)
+        for (long long r = r_begin + (threadIdx.x >> 5); r < r_end; r += 8) {
+            const double x = X[r * ldx + c];
+            sw = fma(w[r], x, sw);
+            s1 += x;
+        }
+    __shared__ double red[2][8][32];
+    red[0][threadIdx.x >> 5][threadIdx.x & 31] = sw;
+    red[1][threadIdx.x >> 5][threadIdx.x & 31] = s1;
+    __syncthreads();
+    if (threadIdx.x < 32 && c < cols) {
+        for (int i = 1; i < 8; ++i) { sw += red[0][i][threadIdx.x]; s1 += red[1][i][threadIdx.x]; }
+        part[((long long)blockIdx.y * 2 + 0) * cols + c] = sw;
+        part[((long long)blockIdx.y * 2 + 1) * cols + c] = s1;
+    }
+}
+__global__ void col_wsum_reduce_kernel(int chunks, int cols, const double* __restrict__ part, double* __restrict__ out_w,
+                                       double* __restrict__ out_1) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    double sw = 0.0, s1 = 0.0;
+    for (int k = 0; k < chunks; ++k) { sw += part[((long long)k * 2 + 0) * cols + c]; s1 += part[((long long)k * 2 + 1) * cols + c]; }
+    out_w[c] += sw;
+    out_1[c] += s1;
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -807,6 +906,34 @@ int ozaki_slice(stream_t s, int64_t rows, int64_t k, int64_t kplane, const doubl
     return GPB_OK;
 }
 
+int ozaki_slice_t(stream_t s, int64_t rows, int64_t cols, int64_t kplane, const double* X, int64_t ldx, int nslices, int8_t* Qt,
+                  int64_t ldq, double* scale, double* colmax_scratch) {
+    if (rows <= 0 || cols <= 0 || kplane < rows || kplane % 128 || nslices < 1 || nslices > 8 || !X || !Qt || !scale ||
+        !colmax_scratch || ldq < (int64_t)nslices * kplane || (ldq & 3) || (reinterpret_cast<uintptr_t>(Qt) & 3))
+        return GPB_ERR_INVALID;
+    if (cudaMemsetAsync(colmax_scratch, 0, (size_t)cols * sizeof(double), to_stream(s)) != cudaSuccess) return GPB_ERR_LAUNCH;
+    dim3 g1((unsigned)((cols + 31) / 32), (unsigned)((rows + 1023) / 1024));
+    col_absmax_kernel<<<g1, 256, 0, to_stream(s)>>>(rows, (int)cols, X, ldx, reinterpret_cast<unsigned long long*>(colmax_scratch));
+    GPB_LAUNCH_CHECK();
+    dim3 g2((unsigned)((cols + 31) / 32), (unsigned)(kplane / 128));
+    ozaki_slice_t_kernel<<<g2, 256, 0, to_stream(s)>>>(rows, (int)cols, kplane, X, ldx, nslices, reinterpret_cast<signed char*>(Qt),
+                                                        ldq, reinterpret_cast<const unsigned long long*>(colmax_scratch), scale);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+int col_weighted_sums(stream_t s, int64_t rows, int64_t cols, const double* X, int64_t ldx, const double* w, double* scratch,
+                      double* out_w, double* out_1) {
+    if (rows <= 0 || cols <= 0 || !X || !w || !scratch || !out_w || !out_1) return GPB_ERR_INVALID;
+    const int chunks = (int)((rows + 1023) / 1024);
+    dim3 g((unsigned)((cols + 31) / 32), (unsigned)chunks);
+    col_wsum_partial_kernel<<<g, 256, 0, to_stream(s)>>>(rows, (int)cols, X, ldx, w, scratch);
+    GPB_LAUNCH_CHECK();
+    col_wsum_reduce_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, to_stream(s)>>>(chunks, (int)cols, scratch, out_w, out_1);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
 int igemm_i8(stream_t s, int64_t m, int64_t n, int64_t k, const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb, int32_t* C,
              int64_t ldc) {
     if (m < 0 || n < 0 || k <= 0 || !A || !B || !C) return GPB_ERR_INVALID;
@@ -814,21 +941,25 @@ int igemm_i8(stream_t s, int64_t m, int64_t n, int64_t k, const int8_t* A, int64
     if (m == 0 || n == 0) return GPB_OK;
     OzParams p = {};
     p.m = (int)m; p.n = (int)n; p.kblocks = (int)(k / OZ_BK); p.nslices = 1;
-    p.Ci = C; p.ldci = ldc;
+    p.Ci = C; p.ldci = ldc; p.pstride = (int)k;
     return launch<0>(s, A, m, lda, B, n, ldb, k, p);
 }
 
 int ozaki_gemm(stream_t s, const OzakiGemmDesc& d) {
     if (d.M < 0 || d.N < 0 || d.K <= 0 || d.nslices < 1 || d.nslices > 8 || !d.Qa || !d.Qb || !d.sa || !d.sb || !d.C)
         return GPB_ERR_INVALID;
-    if (d.K % OZ_BK || d.K > 32768) return GPB_ERR_UNSUPPORTED;
+    // int32 accumulator headroom of the deepest order: nslices * K * 64^2 must stay below 2^31
+    if (d.K % OZ_BK || (int64_t)d.nslices * d.K * 4096 >= (1ll << 31)) return GPB_ERR_UNSUPPORTED;
     if (d.mask != MASK_NONE && d.mask != MASK_LOWER && d.mask != MASK_BLOCK_STRICT_UPPER) return GPB_ERR_UNSUPPORTED;
     if (d.M == 0 || d.N == 0) return GPB_OK;
     OzParams p = {};
     p.m = (int)d.M; p.n = (int)d.N; p.kblocks = (int)(d.K / OZ_BK); p.nslices = d.nslices;
     p.mask = d.mask == MASK_LOWER ? 1 : (d.mask == MASK_BLOCK_STRICT_UPPER ? 2 : 0); p.row0 = d.mask_row0; p.col0 = d.mask_col0; p.mask_nb = d.mask_nb > 0 ? d.mask_nb : 1;
     p.C = d.C; p.ldc = d.ldc; p.sa = d.sa; p.sb = d.sb; p.alpha = d.alpha; p.beta0 = d.beta0;
-    return launch<1>(s, d.Qa, d.M, d.ldqa, d.Qb, d.N, d.ldqb, (int64_t)d.nslices * d.K, p);
+    const int64_t ps = d.plane_stride > 0 ? d.plane_stride : d.K;
+    if (ps < d.K || ps % 16) return GPB_ERR_INVALID;
+    p.pstride = (int)ps;
+    return launch<1>(s, d.Qa, d.M, d.ldqa, d.Qb, d.N, d.ldqb, (int64_t)(d.nslices - 1) * ps + d.K, p);
 }
 
 bool ozaki_available() { return encode_tiled() != nullptr; }

@@ -259,6 +259,14 @@ int svgp_scalar_grads(stream_t s, const double* sc, const double* dots, const do
 // to the multiple of 128 the product kernel needs).
 int ozaki_slice(stream_t s, int64_t rows, int64_t k, int64_t kplane, const double* X, int64_t ldx, int nslices, int8_t* Q,
                 int64_t ldq, double* scale);
+// Same digits for the COLUMNS of a rows x cols block (contraction over the rows): Qt[c, p*kplane + r], scale[c] from the column
+// maxima; rows [rows, kplane) are zero digits (kplane multiple of 128); colmax_scratch: cols doubles.
+int ozaki_slice_t(stream_t s, int64_t rows, int64_t cols, int64_t kplane, const double* X, int64_t ldx, int nslices, int8_t* Qt,
+                  int64_t ldq, double* scale, double* colmax_scratch);
+// out_w[c] += sum_r w[r] X[r,c], out_1[c] += sum_r X[r,c] for a rows x cols block (deterministic two-stage reduction);
+// scratch: 2 * ceil(rows / 1024) * cols doubles
+int col_weighted_sums(stream_t s, int64_t rows, int64_t cols, const double* X, int64_t ldx, const double* w, double* scratch,
+                      double* out_w, double* out_1);
 struct OzakiGemmDesc {
     int64_t M = 0, N = 0, K = 0;  // K = digits per plane (multiple of 128)
     int nslices = 7;
@@ -270,6 +278,7 @@ struct OzakiGemmDesc {
     const double* sb = nullptr;   // [N]
     double* C = nullptr;          // C += alpha * A B^T (all digit pairs of order p+q < nslices); beta0: C = alpha * A B^T
     int beta0 = 0;
+    int64_t plane_stride = 0;     // digits between consecutive planes of one row (0 -> K): lets one launch cover a K sub-range
     int64_t ldc = 0;
     double alpha = 1.0;
     int mask = MASK_NONE;         // MASK_NONE, MASK_LOWER or MASK_BLOCK_STRICT_UPPER (same meaning as GemmDesc::mask)

@@ -26,7 +26,7 @@ constexpr int SPLITK = 16;
 struct Lay {
     int64_t fz, fb, mm[13], vec[9], sc, dots, T1, T2, gpart, info, ppart, total;
     int64_t fz_bytes, fb_bytes;
-    int64_t oz_qt, oz_qc, oz_st, oz_sc, oz_kplane;
+    int64_t oz_qt, oz_qc, oz_st, oz_sc, oz_kplane, oz_s1, oz_colmax, oz_ones, oz_kplane1;
     bool with_oz;
 };
 Lay layout(int64_t M, int D, int64_t Bs) {
@@ -54,10 +54,17 @@ Lay layout(int64_t M, int D, int64_t Bs) {
     // pass-2 digit planes: OZ_MAX_SLICES planes of kplane int8 digits per row == kplane doubles per row
     L.with_oz = Bs >= OZ_MIN_ROWS && M >= 256;
     L.oz_kplane = align_up(M + 2, 128);
-    L.oz_qt = take(L.with_oz ? Bs * L.oz_kplane : 0);
+    L.oz_kplane1 = align_up(Bs, 128);
+    {
+        const int64_t need2 = Bs * L.oz_kplane, need1 = M * L.oz_kplane1;  // pass-2 row digits / pass-1 column digits share it
+        L.oz_qt = take(L.with_oz ? (need2 > need1 ? need2 : need1) : 0);
+    }
     L.oz_qc = take(L.with_oz ? M * L.oz_kplane : 0);
     L.oz_st = take(L.with_oz ? Bs : 0);
     L.oz_sc = take(L.with_oz ? M : 0);
+    L.oz_s1 = take(L.with_oz ? M : 0);
+    L.oz_colmax = take(L.with_oz ? M : 0);
+    L.oz_ones = take(L.with_oz ? Bs : 0);
     L.total = o;
     return L;
 }
@@ -92,6 +99,10 @@ int sgpr_ws_carve(void* buf, int64_t bytes, int64_t M, int D, int64_t block_rows
     ws->oz_st = L.with_oz ? b + L.oz_st : nullptr;
     ws->oz_sc = L.with_oz ? b + L.oz_sc : nullptr;
     ws->oz_kplane = L.oz_kplane;
+    ws->oz_s1 = L.with_oz ? b + L.oz_s1 : nullptr;
+    ws->oz_colmax = L.with_oz ? b + L.oz_colmax : nullptr;
+    ws->oz_ones = L.with_oz ? b + L.oz_ones : nullptr;
+    ws->oz_kplane1 = L.oz_kplane1;
     return GPB_OK;
 }
 
@@ -165,6 +176,7 @@ int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug) {
     //    Forward N M^2 flop, but the rounding of Praw is amplified by cond(Kzz) (normal-equations-like:
     //    relative error of Phi ~ eps * sqrt(N) * cond(Kzz)); callers enable it for well-conditioned Kzz only.
     const bool raw = a.raw_stats != 0;
+    const int planes1 = (ws.oz_qt && ozaki_available() && get_ozaki_slices() != 0) ? OZ_MAX_SLICES : 0;
     for (int64_t r0 = 0; r0 < a.Nloc; r0 += a.block_rows) {
         const int64_t rows = (a.Nloc - r0) < a.block_rows ? (a.Nloc - r0) : a.block_rows;
         // K_b^T = k(X_b, Z)   (objectives.py:355, one row block)
@@ -181,6 +193,28 @@ int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug) {
         // Ppart += [T2 | d_b | 1]^T [T2 | d_b | 1]   (objectives.py:390,404,407 in one SYRK).
         // The output has only ~(M/128)*(M/64)/2 tiles, so K (= rows) is split into SPLITK slices that run as
         // one batched launch into separate partial sums (summed after the block loop).
+        if (planes1 && rows >= OZ_MIN_ROWS) {
+            // int8 route: K_b^T K_b (M x M, lower) from COLUMN digit planes of the block (8 planes: the raw statistics are later
+            // whitened, which amplifies their rounding by cond(Kzz)); the two augmented rows [d ; 1]^T [K_b | d | 1] are GEMVs.
+            const int64_t kp1 = align_up(rows, 128), ldq1 = OZ_MAX_SLICES * ws.oz_kplane1;
+            GPB_TRY(ozaki_slice_t(s, rows, M, kp1, ws.T2, ld, planes1, ws.oz_qt, ldq1, ws.oz_s1, ws.oz_colmax));
+            // int32 headroom: (t+1) K 64^2 < 2^31  ->  split K so that planes * Ksub * 4096 stays below it
+            const int64_t kmax = ((int64_t)((1ll << 31) - 1) / ((int64_t)planes1 * 4096)) / 256 * 256;
+            const int64_t nsplit = (kp1 + kmax - 1) / kmax;
+            const int64_t ksub = align_up((kp1 + nsplit - 1) / nsplit, 128);
+            for (int64_t k0 = 0; k0 < kp1; k0 += ksub) {
+                OzakiGemmDesc g;
+                g.M = M; g.N = M; g.K = (kp1 - k0) < ksub ? (kp1 - k0) : ksub; g.nslices = planes1;
+                g.Qa = ws.oz_qt + k0; g.ldqa = ldq1; g.sa = ws.oz_s1; g.Qb = g.Qa; g.ldqb = ldq1; g.sb = ws.oz_s1;
+                g.plane_stride = kp1;
+                g.C = ws.Ppart; g.ldc = ld; g.alpha = 1.0; g.mask = MASK_LOWER;
+                GPB_TRY(ozaki_gemm(s, g));
+            }
+            // rows M, M+1 of the statistics: [d ; 1]^T [K_b | d | 1]   (T1 is free here in both routes: scratch)
+            GPB_TRY(sub_scalar(s, rows, a.y + r0, a.mean_const, ws.oz_st));
+            GPB_TRY(col_weighted_sums(s, rows, ld, ws.T2, ld, ws.oz_st, ws.T1, ws.Ppart + M * ld, ws.Ppart + (M + 1) * ld));
+            continue;
+        }
         const int S = rows >= 256 ? SPLITK : 1;
         const int64_t Ks = align_up((rows + S - 1) / S, 16);
         if (S * Ks > rows) GPB_TRY(fill2d(s, S * Ks - rows, ld, ws.T2 + rows * ld, ld, 0.0));

@@ -36,6 +36,9 @@ struct SgprWs {
     int8_t *oz_qt = nullptr, *oz_qc = nullptr;
     double *oz_st = nullptr, *oz_sc = nullptr;
     int64_t oz_kplane = 0;  // digits per plane = M + 2 rounded up to 128
+    // pass 1 (statistics SYRK, contraction over the block rows): column digit planes share oz_qt; plane = block rows rounded to 128
+    double *oz_s1 = nullptr, *oz_colmax = nullptr, *oz_ones = nullptr;
+    int64_t oz_kplane1 = 0;
 };
 
 int64_t sgpr_ws_bytes(int64_t M, int D, int64_t block_rows);

@@ -486,6 +486,47 @@ int ozaki_slice(stream_t, int64_t rows, int64_t k, int64_t kplane, const double*
     }
     return GPB_OK;
 }
+int ozaki_slice_t(stream_t, int64_t rows, int64_t cols, int64_t kplane, const double* X, int64_t ldx, int nslices, int8_t* Qt,
+                  int64_t ldq, double* scale, double* colmax_scratch) {
+    if (rows <= 0 || cols <= 0 || kplane < rows || kplane % 128 || nslices < 1 || nslices > 8 || !X || !Qt || !scale || !colmax_scratch ||
+        ldq < (int64_t)nslices * kplane)
+        return GPB_ERR_INVALID;
+    for (int64_t c = 0; c < cols; ++c) {
+        double mx = 0.0;
+        bool bad = false;
+        for (int64_t r = 0; r < rows; ++r) {
+            double v = std::fabs(X[r * ldx + c]);
+            if (!(v <= std::numeric_limits<double>::max())) bad = true;
+            if (v > mx) mx = v;
+        }
+        colmax_scratch[c] = mx;
+        int e = 0;
+        if (bad) scale[c] = std::numeric_limits<double>::quiet_NaN();
+        else if (mx == 0.0) scale[c] = 1.0;
+        else { e = std::ilogb(mx) + 2; scale[c] = std::scalbn(1.0, e); }
+        for (int64_t r = 0; r < kplane; ++r) {
+            double R = (bad || r >= rows) ? 0.0 : std::scalbn(X[r * ldx + c], -e);
+            for (int p = 0; p < nslices; ++p) {
+                R *= 128.0;
+                double d = std::nearbyint(R);
+                Qt[c * ldq + (int64_t)p * kplane + r] = (int8_t)(int)d;
+                R -= d;
+            }
+        }
+    }
+    return GPB_OK;
+}
+int col_weighted_sums(stream_t, int64_t rows, int64_t cols, const double* X, int64_t ldx, const double* w, double* scratch,
+                      double* out_w, double* out_1) {
+    if (rows <= 0 || cols <= 0 || !X || !w || !scratch || !out_w || !out_1) return GPB_ERR_INVALID;
+    for (int64_t c = 0; c < cols; ++c) {
+        double sw = 0.0, s1 = 0.0;
+        for (int64_t r = 0; r < rows; ++r) { sw += w[r] * X[r * ldx + c]; s1 += X[r * ldx + c]; }
+        out_w[c] += sw;
+        out_1[c] += s1;
+    }
+    return GPB_OK;
+}
 int ozaki_gemm(stream_t, const OzakiGemmDesc& d) {
     if (d.M < 0 || d.N < 0 || d.K <= 0 || d.nslices < 1 || d.nslices > 8 || !d.Qa || !d.Qb || !d.sa || !d.sb || !d.C)
         return GPB_ERR_INVALID;
@@ -497,9 +538,10 @@ int ozaki_gemm(stream_t, const OzakiGemmDesc& d) {
             double acc = 0.0;
             for (int t = 0; t < d.nslices; ++t) {
                 int64_t P = 0;
+                const int64_t ps = d.plane_stride > 0 ? d.plane_stride : d.K;
                 for (int p = 0; p <= t; ++p) {
-                    const int8_t* a = d.Qa + i * d.ldqa + (int64_t)p * d.K;
-                    const int8_t* b = d.Qb + j * d.ldqb + (int64_t)(t - p) * d.K;
+                    const int8_t* a = d.Qa + i * d.ldqa + (int64_t)p * ps;
+                    const int8_t* b = d.Qb + j * d.ldqb + (int64_t)(t - p) * ps;
                     int32_t part = 0;
                     for (int64_t c = 0; c < d.K; ++c) part += (int32_t)a[c] * (int32_t)b[c];
                     P += part;

@@ -383,25 +383,32 @@ def test_mll_value_and_gradient_with_int8_digit_plane_updates(lib, N):
     assert not np.array_equal(res[0][1], ge)  # the digit-plane model really ran in the backward pass
 
 
-def test_sgpr_pass2_through_int8_digit_planes(lib):
-    """collapsed_elbo gradient with the pass-2 product dK_b = [K_b|d|1] Caug^T on the Ozaki model (M + 2 = 262 digits per plane
-    zero-padded to 384; one block below the row threshold stays on the GEMM model)."""
+@pytest.mark.parametrize("raw", [False, True])
+def test_sgpr_statistics_and_pass2_through_int8_digit_planes(lib, raw):
+    """collapsed_elbo with the statistics SYRK (column digit planes, contraction over the block rows, K split for the int32
+    headroom) and the pass-2 product dK_b = [K_b|d|1] Caug^T (M + 2 = 262 digits per plane zero-padded to 384) on the Ozaki
+    model; the ragged last block (100 rows, below the threshold) stays on the GEMM model."""
     N, M, D, block = 700, 260, 3, 300
     X, y = data(N, D, N + M)
     Z = np.ascontiguousarray(np.random.default_rng(M).uniform(-2, 2, (M, D)))
     ell = np.linspace(0.8, 1.6, D)
     try:
         lib.gpb_set_ozaki_slices(0)
-        v0, g0 = _sgpr_run(lib, 0, X, y, Z, ell, False, 1.3, 0.4, 0.2, 1e-6, block, 1)
+        v0, g0 = _sgpr_run(lib, 0, X, y, Z, ell, False, 1.3, 0.4, 0.2, 1e-6, block, 1, raw=raw)
         lib.gpb_set_ozaki_slices(7)
-        v7, g7 = _sgpr_run(lib, 0, X, y, Z, ell, False, 1.3, 0.4, 0.2, 1e-6, block, 1)
+        v7, g7 = _sgpr_run(lib, 0, X, y, Z, ell, False, 1.3, 0.4, 0.2, 1e-6, block, 1, raw=raw)
     finally:
         lib.gpb_set_ozaki_slices(0)
-    assert v0 == v7  # the forward pass does not use the digit planes
-    assert not np.array_equal(g0["inducing_inputs"], g7["inducing_inputs"])  # the int8 model really ran
+    assert v0 != v7  # the int8 model really ran in the forward pass
+    cond = np.linalg.cond(o.gram("rbf", Z, ell, 1.3) + 1e-6 * np.eye(M))
+    amp = max(1.0, cond / 1e3) if raw else 1.0
+    amp2 = max(1.0, cond / 1e6)  # two fp64-accurate evaluation orders of the statistics drift like cond * eps
+    assert abs(v0 - v7) <= 1e-11 * amp * abs(v0)
+    assert not np.array_equal(g0["inducing_inputs"], g7["inducing_inputs"])
     ref, gref = o.collapsed_elbo_value_and_grad_autodiff("rbf", X, y, Z, ell, 1.3, 0.4, 0.2)
+    assert abs(v7 - ref) <= 1e-9 * amp * abs(ref)
     for k in gref:
         a, b = np.asarray(g7[k]).reshape(np.shape(gref[k])), np.asarray(gref[k])
-        assert np.max(np.abs(a - b)) <= 1e-7 * max(np.max(np.abs(b)), 1e-8 * abs(ref)), k
+        assert np.max(np.abs(a - b)) <= 1e-7 * amp * max(np.max(np.abs(b)), 1e-8 * abs(ref)), k
         a0 = np.asarray(g0[k]).reshape(np.shape(gref[k]))
-        assert np.max(np.abs(a - a0)) <= 1e-10 * max(np.max(np.abs(b)), 1e-8 * abs(ref)), k
+        assert np.max(np.abs(a - a0)) <= 1e-10 * max(amp, amp2) * max(np.max(np.abs(b)), 1e-8 * abs(ref)), (k, cond)
