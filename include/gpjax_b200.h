@@ -121,10 +121,12 @@ int gpb_gemm(void* stream, int64_t M, int64_t N, int64_t K, double alpha, const 
  * to the row maxima (nslices = 7: below fp64 rounding of a K = 1024 product).
  *   Q        : int8 [rows, nslices*K], plane p at columns [p*K, (p+1)*K); 16-byte aligned, ldq multiple of 16
  *   scale    : fp64 [rows], 2^e_i (NaN for a row holding NaN/Inf -> NaN output, JAX semantics)
- *   K        : multiple of 128
+ *   K        : multiple of 128, and nslices * K * 4096 < 2^31 (int32 headroom of the deepest order; GPB_ERR_UNSUPPORTED beyond --
+ *              callers split K, as the SGPR statistics do for K = 65,536)
  * gpb_igemm_i8 exposes the raw integer product (C int32 = A B^T) for bit-exact testing.
  * gpb_set_ozaki_slices(s): s in {0, 5..8}; 0 keeps every blocked algorithm on the FP64 DMMA pipe, otherwise the rank-NB
- * trailing updates (>= 2048 output rows) of potrf / trtri / lauum run through gpb_ozaki_gemm with s digit planes.
+ * trailing updates (>= 2048 output rows) of potrf / trtri / lauum run through gpb_ozaki_gemm with s digit planes, and the two
+ * streamed products of gpb_sgpr_stats(_raw) / gpb_sgpr_grad_local (blocks of >= 2048 rows, M >= 256) with 8 planes.
  * Default: 7 (environment variable GPB_OZAKI overrides; 8 = fp64 rounding level, 0 = DMMA only). */
 int gpb_ozaki_available(void);
 void gpb_set_ozaki_slices(int nslices);
