@@ -10,6 +10,10 @@ scaling) -- and ALSO runs the path that does shard, SGPR ``collapsed_elbo`` at N
 over the ranks with an NCCL all-reduce, reported under the ``sgpr`` key (points/s, strong scaling).
 ``--workload sgpr`` makes the SGPR number the main ``value`` instead.
 
+Both paths run their O(N^3) / O(N M^2) products as exact int8 digit-plane (Ozaki) products on tcgen05 by default (DESIGN
+section 12); the roofline object then describes that kernel, and `fp64_dmma_path_ms_per_step` / `remaining_dmma_gemms` the
+FP64 DMMA path (GPB_OZAKI=0 in the environment benches it alone).
+
 Timing: W warm-up steps, then exactly K steps between barrier + synchronize, CUDA events on the
 launching stream, MAX over ranks.  L2: every step streams a 20 GB (exact) / multi-GB (SGPR) working set,
 far beyond the 126 MB L2, so no explicit flush is needed.

@@ -12,17 +12,24 @@
 // The truncation error is bounded by the dropped orders: <= (s+1) 2^(-7 s) |a_i|_inf |b_j|_inf k  (s = 7: 2^-46 per entry
 // relative to the row maxima -- measured against the DMMA product in tests/test_gpu_ozaki.py and DESIGN section 12).
 //
-// Kernel (persistent, one CTA per SM, 12 warps, warp-specialised):
-//   warp 0      TMA producer: cp.async.bulk.tensor.2d of 128 x 128-byte digit tiles (SWIZZLE_128B) into a 3-stage ring of 2 K-blocks
-//   warp 1      MMA issuer  : one thread issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=128, K=32 per instruction),
+// Kernel (persistent, one CTA per SM, 12 warps, warp-specialised; role loops are warp-uniform, elect.sync picks the issuing lane):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d of 128 x 128-byte digit tiles (SWIZZLE_128B) into a ring of (A, B) slots
+//   warp 1      MMA issuer  : tcgen05.mma.cta_group::1.kind::i8 (M=128, N=128, K=32 per instruction),
 //                             tcgen05.commit releases ring slots / publishes accumulators through mbarriers
 //   warp 2      TMEM allocator (512 columns = 4 accumulator stages of 128 x 128 int32)
 //   warps 4-11  epilogue    : tcgen05.ld the int32 accumulator of order t, convert exactly to fp64, scale by 2^(-7 (t+2)) and
 //                             add into per-thread fp64 registers (64 per thread) while the MMA warp already works on
-//                             order t+1; after the last order: C -= / += 2^(ea_i + eb_j) * acc, masked, ONE read-modify-write
-//                             of the fp64 tile in HBM.
+//                             the next orders; after the last order: C (+)= alpha 2^(ea_i + eb_j) * acc, masked, ONE
+//                             read-modify-write of the fp64 tile in HBM.
+// Schedule (default): orders are processed in PAIRS (t, t+1) with two live accumulators -- ring slot i of a K-block holds
+// (A_i, B_{t+1-i}); when it lands, acc_{t+1} += A_i B_{t+1-i}^T and acc_t += A_{i-1} B_{t+1-i}^T (A_{i-1} is still in the
+// previous slot), so t+2 slot loads feed 2t+3 digit-pair products (16 instead of 28 loads per K-block at 7 planes).  That
+// matters because the unpaired schedule saturates the L2 -> SM path (12.9 TB/s measured).  GPB_OZ_PAIR=0 selects the
+// unpaired schedule (3 slots of 2 K-blocks), GPB_OZ_KERNEL=2 the plane-resident variant further below, GPB_OZ_NOLOAD=1
+// disables the TMA copies (MMA pacing measurement) -- all three are measurement hooks, see profiles/r01_ozaki.md.
 // The digit tiles are addressed directly in the [rows, s*k] digit matrix by TMA coordinates, so A and B may be the same
-// buffer (SYRK) and no order-reversed copy exists.
+// buffer (SYRK) and no order-reversed copy exists.  Companion kernels: ozaki_slice_kernel (row digits), ozaki_slice_t_kernel +
+// col_absmax_kernel (column digits for products that contract over the rows), col_wsum_* (augmented SGPR rows).
 #include <cuda.h>
 
 #include <cstdlib>
