@@ -63,6 +63,18 @@ def test_cuda_library_is_sm100a_with_dmma(cuda_lib_path):
     assert sass.count("DMMA.8x8x4") >= 64 and "LDGSTS" in sass
 
 
+def test_int8_kernel_is_tcgen05_with_tma_and_tmem(cuda_lib_path):
+    """The Ozaki kernel really issues 5th-generation tensor-core int8 MMAs fed by TMA with TMEM accumulators, and the role
+    loops are warp-uniform: the four UTCIMMA of a K-block are issued back to back (no R2UR waterfall in between)."""
+    obj = os.path.join(os.path.dirname(cuda_lib_path), "obj", "ozaki_i8.o")
+    sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCIMMA", "UTMALDG.2D", "UTCBAR", "LDTM", "UTCATOMSWS"):
+        assert mnemonic in sass, mnemonic
+    lines = [ln for ln in sass.splitlines() if re.search(r"/\*[0-9a-f]{4,}\*/\s+\S", ln)]
+    idx = [i for i, ln in enumerate(lines) if "UTCIMMA" in ln]
+    assert any(idx[j + 3] - idx[j] == 3 for j in range(len(idx) - 3)), "no run of 4 consecutive UTCIMMA instructions"
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "gpjax_b200")
     for dirpath, _, files in os.walk(pkg):
