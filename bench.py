@@ -244,6 +244,20 @@ def timed(D: Dist, step, warmup, steps):
     return D.max_over_ranks(t)
 
 
+def ncu_capture(rel_path):
+    """`traffic` of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, parsed from the committed
+    summary of an `ncu --set full` capture of this bench command (scripts/parse_ncu.py writes it), next to the algorithmic bytes
+    of that launch's shape.  Absent file -> traffic null."""
+    try:
+        with open(os.path.join(ROOT, rel_path)) as f:
+            d = json.load(f)
+        return {"traffic": d["dram_bytes_read"] + d["dram_bytes_write"], "traffic_unit": "bytes per launch (the captured launch)",
+                "algorithmic_bytes": d["algorithmic_bytes"], "traffic_source": rel_path, "traffic_launch": d.get("launch"),
+                "tensor_pipe_active_pct_ncu": d.get("tensor_pipe_active_pct")}
+    except Exception:
+        return {"traffic": None}
+
+
 def measure_cublas_dgemm(D: Dist):
     torch = D.torch
     n = 8192
@@ -259,6 +273,43 @@ def measure_cublas_dgemm(D: Dist):
     e1.record()
     torch.cuda.synchronize()
     return 3 * 2 * n**3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+
+
+def measure_int8_ceiling(D: Dist, n=8192, sustain_s=2.0):
+    """Int8 tensor ceiling of THIS box, measured in THIS process (MEASURED_PEAKS.json has no int8 entry): cuBLASLt IGEMM through
+    torch._int_mm at n^3, burst = best of 10 single launches, sustained = back-to-back launches for >= sustain_s seconds
+    (the figure a kernel timed inside a long step is compared with), SM clock sampled during the sustained loop."""
+    torch = D.torch
+    g = torch.Generator(device=D.dev).manual_seed(1)
+    a = torch.randint(-128, 128, (n, n), dtype=torch.int8, device=D.dev, generator=g)
+    b = torch.randint(-128, 128, (n, n), dtype=torch.int8, device=D.dev, generator=g).t()  # column-major B, as cuBLASLt wants
+    for _ in range(3):
+        torch._int_mm(a, b)
+    torch.cuda.synchronize()
+    ops_per = 2.0 * float(n) ** 3
+    best = 0.0
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch._int_mm(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, ops_per / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    per = ops_per / (best * 1e12)
+    reps = max(10, int(sustain_s / per))
+    clocks = Clocks(D.local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        torch._int_mm(a, b)
+    e1.record()
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    sustained = reps * ops_per / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    return {"how": f"torch._int_mm (cuBLASLt IGEMM) {n}^3: best of 10 launches (burst), {reps} back-to-back launches (sustained)",
+            "burst_tops": best, "sustained_tops": sustained, "sustained_seconds": e0.elapsed_time(e1) * 1e-3,
+            "sm_mhz_sustained": clk.get("sm_mhz"), "power_w_max": clk.get("power_w_max"), "reasons": clk.get("reasons")}
 
 
 def bench_exact(D: Dist, args):
@@ -300,39 +351,42 @@ def bench_exact(D: Dist, args):
     L.gpb_profile_reset(0)
     value = D.world * args.steps / t
     flops_per_eval = float(n) ** 3  # N^3/3 potrf + 2N^3/3 potri
-    planes = int(L.gpb_get_ozaki_slices())
+    mode = int(L.gpb_get_ozaki_slices())  # -1: auto (device-side conditioning guard), 0: DMMA only, 5..8: forced
+    planes = (int(L.gpb_ozaki_auto_planes(n, HYPER["variance"], HYPER["obs_stddev"], HYPER["jitter"])) if mode == -1 else mode)
     dmma = {"kernel": "gemm_f64_kernel (FP64 DMMA.8x8x4)", "launches_per_step": gemm_n.value / args.steps,
             "time_over_step_time": gemm_ms.value * 1e-3 / t}
     if planes and oz_n.value > 0:
-        # Dominant kernel: ozaki_i8_kernel (tcgen05.mma kind::i8).  `achieved` = algorithmic int8 operations of its launches
-        # (live output entries x K x s(s+1)/2 digit pairs x 2, counted by the launcher) / summed launch durations (CUDA events
-        # on the launching stream).  MEASURED_PEAKS.json has no int8 figure: the int8 tcgen05 rate is nominally 2x bf16
-        # (4.5 vs 2.25 Pop/s), so the peak used is 2 x the measured SUSTAINED bf16 rate (kernel timed inside a long step).
+        # Dominant kernel: ozaki_i8_kernel_cg2 (tcgen05.mma.cta_group::2.kind::i8).  `achieved` = algorithmic int8 operations of
+        # its launches (live output entries x K x s(s+1)/2 digit pairs x 2) / summed launch durations (CUDA events on the
+        # launching stream).  The launcher counts with the 8 planes present in the digit buffers; the device-side guard used
+        # `planes` of them, hence the s(s+1)/72 factor.
+        oz_ops_used = oz_ops.value * (planes * (planes + 1) / 2) / 36.0
+        achieved = oz_ops_used / (oz_ms.value * 1e-3) / 1e12
+        # MEASURED_PEAKS.json has no int8 entry: the ceiling is measured live in this process (cuBLASLt IGEMM, torch._int_mm):
+        # `peak` = the SUSTAINED figure (the kernel is timed inside a seconds-long step under the 1 kW cap), burst alongside.
+        i8 = measure_int8_ceiling(D)
         mp = measured_peaks() or {}
         bf16 = float(mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops") or 1414.5)
-        peak = 2.0 * bf16
-        achieved = oz_ops.value / (oz_ms.value * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "ozaki_i8_kernel (tcgen05.mma.cta_group::1.kind::i8, int8 x int8 -> int32 in TMEM)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (no int8 entry; int8 tcgen05 is nominally 2x bf16); "
-                               "unit is int8 Top/s (2 x MAC)",
-                "digit_planes": planes, "int8_ops_per_eval": oz_ops.value / args.steps,
+        ncu = ncu_capture("profiles/r02_ozaki_cg2_ncu.json")
+        roof = {"bound": "tensor",
+                "kernel": "ozaki_i8_kernel_cg2 (tcgen05.mma.cta_group::2.kind::i8, M256 x N128 per CTA pair, int8 x int8 -> int32 in TMEM)",
+                "achieved": achieved, "peak": i8["sustained_tops"], "unit": "TFLOP/s", "frac": achieved / i8["sustained_tops"],
+                "peak_source": "measured live in this process: torch._int_mm (cuBLASLt IGEMM) 8192^3 back to back for >= 2 s "
+                               "(sustained, power-capped); unit is int8 Top/s (2 x MAC)",
+                "int8_ceiling_measured": i8, "frac_of_int8_burst": achieved / i8["burst_tops"],
+                "frac_of_2x_bf16_sustained": achieved / (2.0 * bf16),
+                "digit_planes": planes, "digit_plane_mode": "auto (device-side conditioning guard)" if mode == -1 else "forced",
+                "int8_ops_per_eval": oz_ops_used / args.steps,
                 "launches_per_step": oz_n.value / args.steps, "time_over_step_time": oz_ms.value * 1e-3 / t,
-                "mma_pacing_ceiling_measured": 2070.0,  # same kernel with TMA loads disabled (GPB_OZ_NOLOAD=1), profiles/r01_ozaki.md
                 "algorithmic_flop_per_eval": flops_per_eval,
-                "whole_step_tflops": flops_per_eval * args.steps / t / 1e12,
-                "whole_step_vs_fp64_dmma_peak": flops_per_eval * args.steps / t / 1e12 / NOMINAL_FP64_TFLOPS,
-                "fp64_dmma_peak": NOMINAL_FP64_TFLOPS, "measured_peaks_json": mp, "remaining_dmma_gemms": dmma,
-                # one `ncu --set full` capture of a single launch (lower-masked 16384^2 update, K=1024, 7 planes;
-                # profiles/r01_ozaki.md): dram__bytes_read.sum 1.387 GB + dram__bytes_write.sum 1.036 GB, against the
-                # algorithmic bytes of THAT launch: read + write of the live fp64 C entries (16384 * 16385 / 2 * 16 B) +
-                # the digit planes once (16384 * 7168 B)
-                "traffic": 2.423e9, "traffic_unit": "bytes per launch (the captured 16384^2 launch)",
-                "algorithmic_bytes": 16384 * 16385 / 2 * 16 + 16384 * 7168.0}
+                "whole_step_fp64_equivalent_tflops": flops_per_eval * args.steps / t / 1e12,
+                "whole_step_fp64_equivalent_over_dmma_peak_NOT_a_roofline_fraction": flops_per_eval * args.steps / t / 1e12 / NOMINAL_FP64_TFLOPS,
+                "fp64_dmma_peak": NOMINAL_FP64_TFLOPS, "measured_peaks_json": mp, "remaining_dmma_gemms": dmma}
+        roof.update(ncu)
         # the same step with every update on the FP64 DMMA pipe (GPB_OZAKI=0), timed live for comparison
         ops.set_ozaki_slices(0)
         t_dmma = timed(D, step, 1, 1)
-        ops.set_ozaki_slices(planes)
+        ops.set_ozaki_slices(mode)
         roof["fp64_dmma_path_ms_per_step"] = 1e3 * t_dmma
     else:
         achieved = flops_per_eval * args.steps / (gemm_ms.value * 1e-3) / 1e12

@@ -39,6 +39,7 @@ PROTOTYPES = {
     "gpb_ozaki_available": (i32, []),
     "gpb_set_ozaki_slices": (None, [i32]),
     "gpb_get_ozaki_slices": (i32, []),
+    "gpb_ozaki_auto_planes": (i32, [i64, f64, f64, f64]),
     "gpb_ozaki_slice": (i32, [vp, i64, i64, vp, i64, i32, vp, i64, vp]),
     "gpb_ozaki_gemm": (i32, [vp, i64, i64, i64, i32, vp, i64, vp, vp, i64, vp, f64, vp, i64, i32]),
     "gpb_igemm_i8": (i32, [vp, i64, i64, i64, vp, i64, vp, i64, vp, i64]),

@@ -63,6 +63,7 @@ int gpb_potrf_lower(void* stream, int64_t N, double* A, int64_t lda, int zero_up
     FactorWs w;
     int rc = carve(ws, ws_bytes, ws_n, ws_d, ws_potri, &w);
     if (rc) return rc;
+    if ((rc = factor_set_planes(stream, w, N, nullptr, nullptr, 0.0))) return rc;  // bare matrix: 8 planes unless forced
     rc = potrf_lower(stream, N, A, lda, w, info);
     if (rc) return rc;
     if (zero_upper) return zero_triangle(stream, N, A, lda, 2);
@@ -107,6 +108,7 @@ int gpb_potri_lower(void* stream, int64_t N, double* A, int64_t lda, double* out
     FactorWs w;
     int rc = carve(ws, ws_bytes, ws_n, ws_d, ws_potri, &w);
     if (rc) return rc;
+    if ((rc = factor_set_planes(stream, w, N, nullptr, nullptr, 0.0))) return rc;
     if ((rc = trtri_into_upper(stream, N, A, lda, w))) return rc;
     if ((rc = lauum_upper(stream, N, A, lda, w))) return rc;
     const int64_t nblk = nblocks(N);
@@ -136,6 +138,9 @@ int gpb_profile_read_ozaki(double* ms, int64_t* launches, double* int8_ops) { re
 int gpb_ozaki_available(void) { return ozaki_available() ? 1 : 0; }
 void gpb_set_ozaki_slices(int nslices) { set_ozaki_slices(nslices); }
 int gpb_get_ozaki_slices(void) { return get_ozaki_slices(); }
+int gpb_ozaki_auto_planes(int64_t N, double variance, double obs_stddev, double jitter) {
+    return ozaki_auto_planes_host(N, variance, obs_stddev, jitter);
+}
 int gpb_ozaki_slice(void* stream, int64_t rows, int64_t K, const double* X, int64_t ldx, int nslices, void* Q,
                     int64_t ldq, double* scale) {
     return ozaki_slice(stream, rows, K, K, X, ldx, nslices, static_cast<int8_t*>(Q), ldq, scale);

@@ -1,12 +1,13 @@
 // Blocked right-looking algorithms (host orchestration only -- see algorithms.h).
 //
-// Storage convention for the exact-GP path (one N x N row-major buffer A, block size NB = 256):
+// Storage convention for the exact-GP path (one N x N row-major buffer A, block size NB = GPB_NB = 1024):
 //   * lower triangle incl. the diagonal blocks : Sigma, then its Cholesky factor L (in place)
 //   * blocks strictly above the block diagonal : W = L^-T (trtri), then Sigma^-1 = W W^T (lauum)
 //   * ws.Dinv / ws.DinvT                       : inverses of the diagonal blocks of L (and transposes)
 //   * ws.Sdiag                                 : diagonal blocks of Sigma^-1
 // so a single N x N buffer carries forward AND backward (N = 100k -> 80 GB of the 180 GB HBM) and
-// L survives the backward pass.  Every O(N^3) step is a DMMA GEMM with K = NB:
+// L survives the backward pass.  Every O(N^3) step is a rank-NB update C += A B^T (int8 digit planes on tcgen05 for updates
+// with >= 2048 rows -- csrc/ozaki_i8.cu -- FP64 DMMA GEMM otherwise):
 //   potrf : panel  X = P * inv(L_kk)^T,  trailing  A22 -= X X^T          (N^3/3)
 //   trtri : W[:,k] = -Acc * inv(L_kk)^T, Acc[:, k+1:] += W[:,k] L[k+1:,k]^T   (N^3/3)
 //   lauum : S[:k,:k] += W[:,k] W[:,k]^T, S[:,k] = W[:,k] inv(L_kk)       (N^3/3)
@@ -14,7 +15,9 @@
 // row-major lower/upper split gives for free.
 #include "algorithms.h"
 
+#include <atomic>
 #include <cstdlib>
+#include <cstring>
 
 namespace gpb {
 
@@ -28,22 +31,28 @@ namespace gpb {
 // Ozaki switch
 // -------------------------------------------------------------------------------------------
 namespace {
-int g_oz_slices = -1;  // -1: not initialised yet
-int clamp_slices(int v) { return (v >= 5 && v <= OZ_MAX_SLICES) ? v : 0; }
+constexpr int OZ_UNSET = -100;
+std::atomic<int> g_oz_slices{OZ_UNSET};
+int clamp_slices(int v) { return (v == OZ_AUTO || (v >= 5 && v <= OZ_MAX_SLICES)) ? v : 0; }
 }  // namespace
-void set_ozaki_slices(int nslices) { g_oz_slices = clamp_slices(nslices); }
+void set_ozaki_slices(int nslices) { g_oz_slices.store(clamp_slices(nslices), std::memory_order_relaxed); }
 int get_ozaki_slices() {
-    if (g_oz_slices < 0) {
+    int v = g_oz_slices.load(std::memory_order_relaxed);
+    if (v == OZ_UNSET) {
         const char* e = std::getenv("GPB_OZAKI");
-        g_oz_slices = e ? clamp_slices(std::atoi(e)) : clamp_slices(GPB_OZ_DEFAULT);
+        v = (!e || !std::strcmp(e, "auto")) ? clamp_slices(GPB_OZ_DEFAULT) : clamp_slices(std::atoi(e));
+        g_oz_slices.store(v, std::memory_order_relaxed);
     }
-    return g_oz_slices;
+    return v;
 }
-// digit planes to use for a rank-NB update with `rows` output rows, 0 = stay on the DMMA pipe
-static int oz_planes(const FactorWs& ws, int64_t rows) {
-    const int s = get_ozaki_slices();
-    if (s == 0 || !ws.oz_q || rows < OZ_MIN_ROWS || NB % 128 != 0 || !ozaki_available()) return 0;
-    return s;
+// does a rank-NB update with `rows` output rows run on the int8 pipe?  (plane count: ws.oz_planes, decided on the device)
+static bool oz_on(const FactorWs& ws, int64_t rows) {
+    return get_ozaki_slices() != 0 && ws.oz_q && ws.oz_planes && rows >= OZ_MIN_ROWS && NB % 128 == 0 && ozaki_available();
+}
+int factor_set_planes(stream_t s, const FactorWs& ws, int64_t N, const double* variance, const double* obs_stddev, double jitter) {
+    const int req = get_ozaki_slices();
+    if (req == 0 || !ws.oz_planes || !ozaki_available()) return GPB_OK;
+    return ozaki_choose_planes(s, req, N, variance, obs_stddev, jitter, ws.oz_planes);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -52,7 +61,7 @@ static int oz_planes(const FactorWs& ws, int64_t rows) {
 namespace {
 struct WsLayout {
     int64_t off_dinv, off_dinvt, off_sdiag, off_panel, off_panel2, off_small, off_vec, off_scal, off_part, total;
-    int64_t off_ozq, off_ozq2, off_ozs, off_ozs2;
+    int64_t off_ozq, off_ozq2, off_ozs, off_ozs2, off_ozp;
     bool with_oz;
     int64_t partials_count;
 };
@@ -82,6 +91,7 @@ WsLayout ws_layout(int64_t N, int D, int with_potri) {
     L.off_ozq2 = take(qd);
     L.off_ozs = take(L.with_oz ? align_up(N, NB) : 0);
     L.off_ozs2 = take(L.with_oz ? align_up(N, NB) : 0);
+    L.off_ozp = take(L.with_oz ? 32 : 0);
     L.total = o;
     return L;
 }
@@ -111,6 +121,7 @@ int factor_ws_carve(void* buf, int64_t bytes, int64_t N, int D, int with_potri, 
     ws->oz_q2 = L.with_oz ? reinterpret_cast<int8_t*>(b + L.off_ozq2) : nullptr;
     ws->oz_scale = L.with_oz ? b + L.off_ozs : nullptr;
     ws->oz_scale2 = L.with_oz ? b + L.off_ozs2 : nullptr;
+    ws->oz_planes = L.with_oz ? reinterpret_cast<int*>(b + L.off_ozp) : nullptr;
     return GPB_OK;
 }
 
@@ -193,8 +204,8 @@ static int potrf_panel(stream_t s, int64_t N, double* A, int64_t lda, const Fact
     GPB_TRY(gemm(s, g));
     GPB_TRY(copy2d(s, rows, nbk, panel, NB, P, lda));
     // Ozaki path: digit planes of the panel, extracted on the stream that produced it (the side stream under lookahead)
-    const int planes = (nbk == NB) ? oz_planes(ws, rows) : 0;
-    if (planes) GPB_TRY(ozaki_slice(s, rows, NB, NB, panel, NB, planes, oz_q, OZ_MAX_SLICES * NB, oz_scale));
+    if (nbk == NB && oz_on(ws, rows))  // all OZ_MAX_SLICES planes are extracted; the product uses ws.oz_planes[0] of them
+        GPB_TRY(ozaki_slice(s, rows, NB, NB, panel, NB, OZ_MAX_SLICES, oz_q, OZ_MAX_SLICES * NB, oz_scale));
     return GPB_OK;
 }
 
@@ -215,11 +226,11 @@ int potrf_lower(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& w
         const int64_t j1 = (k + 1) * NB;        // first row/column of the trailing matrix
         const int64_t rows = N - j1;             // pcur holds X_k: rows x NB
         const int64_t nb1 = rows < NB ? rows : NB;
-        const int planes = oz_planes(ws, rows);  // same predicate potrf_panel used when it sliced X_k
+        const bool planes = oz_on(ws, rows);  // same predicate potrf_panel used when it sliced X_k
         // U1: next block column, A[j1:, j1:j1+nb1] -= X X[0:nb1]^T (lower part)
         if (planes) {
             OzakiGemmDesc u;
-            u.M = rows; u.N = nb1; u.K = NB; u.nslices = planes;
+            u.M = rows; u.N = nb1; u.K = NB; u.nslices = OZ_MAX_SLICES; u.nslices_dev = ws.oz_planes;
             u.Qa = qcur; u.ldqa = ldq; u.sa = scur; u.Qb = qcur; u.ldqb = ldq; u.sb = scur;
             u.C = A + j1 * lda + j1; u.ldc = lda; u.alpha = -1.0; u.mask = MASK_LOWER;
             GPB_TRY(ozaki_gemm(s, u));
@@ -238,7 +249,7 @@ int potrf_lower(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& w
             // U2: A[j1+nb1:, j1+nb1:] -= X[nb1:] X[nb1:]^T (lower part)
             if (planes) {
                 OzakiGemmDesc v;
-                v.M = rest; v.N = rest; v.K = NB; v.nslices = planes;
+                v.M = rest; v.N = rest; v.K = NB; v.nslices = OZ_MAX_SLICES; v.nslices_dev = ws.oz_planes;
                 v.Qa = qcur + nb1 * ldq; v.ldqa = ldq; v.sa = scur + nb1;
                 v.Qb = v.Qa; v.ldqb = ldq; v.sb = v.sa;
                 v.C = A + (j1 + nb1) * lda + (j1 + nb1); v.ldc = lda; v.alpha = -1.0; v.mask = MASK_LOWER;
@@ -372,13 +383,13 @@ int trtri_into_upper(stream_t s, int64_t N, double* A, int64_t lda, const Factor
         const double* Lp = A + (j0 + nbk) * lda + j0;            // L[k+1:, k]
         if (j0 > 0) {
             // Acc[0:j0, k+1:] += W[0:j0,k] * L[k+1:,k]^T   (nbk == NB here: block k is not the last one)
-            const int planes = oz_planes(ws, j0);
-            if (planes) {  // digit planes indexed by GLOBAL row: W rows [0, j0), L rows [j0 + nbk, N)
+            if (oz_on(ws, j0)) {  // digit planes indexed by GLOBAL row: W rows [0, j0), L rows [j0 + nbk, N)
+                const int planes = OZ_MAX_SLICES;
                 const int64_t ldq = OZ_MAX_SLICES * NB;
                 GPB_TRY(ozaki_slice(s, j0, NB, NB, Wp, NB, planes, ws.oz_q, ldq, ws.oz_scale));
                 GPB_TRY(ozaki_slice(s, right, NB, NB, Lp, lda, planes, ws.oz_q + (j0 + nbk) * ldq, ldq, ws.oz_scale + j0 + nbk));
                 OzakiGemmDesc u;
-                u.M = j0; u.N = right; u.K = NB; u.nslices = planes;
+                u.M = j0; u.N = right; u.K = NB; u.nslices = planes; u.nslices_dev = ws.oz_planes;
                 u.Qa = ws.oz_q; u.ldqa = ldq; u.sa = ws.oz_scale;
                 u.Qb = ws.oz_q + (j0 + nbk) * ldq; u.ldqb = ldq; u.sb = ws.oz_scale + j0 + nbk;
                 u.C = A + (j0 + nbk); u.ldc = lda; u.alpha = 1.0;
@@ -410,13 +421,13 @@ int lauum_upper(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& w
         double* P = A + j0;  // W[0:j0, k], row stride lda
         if (j0 > 0) {
             // S[0:j0, 0:j0] (strictly-upper blocks) += P P^T
-            const int planes = oz_planes(ws, j0);
-            if (planes) {  // a ragged last block (nbk < NB) is zero-padded to the next multiple of 128 digits
+            if (oz_on(ws, j0)) {  // a ragged last block (nbk < NB) is zero-padded to the next multiple of 128 digits
+                const int planes = OZ_MAX_SLICES;
                 const int64_t ldq = OZ_MAX_SLICES * NB;
                 const int64_t kp = align_up(nbk, 128);
                 GPB_TRY(ozaki_slice(s, j0, nbk, kp, P, lda, planes, ws.oz_q, ldq, ws.oz_scale));
                 OzakiGemmDesc g;
-                g.M = j0; g.N = j0; g.K = kp; g.nslices = planes;
+                g.M = j0; g.N = j0; g.K = kp; g.nslices = planes; g.nslices_dev = ws.oz_planes;
                 g.Qa = ws.oz_q; g.ldqa = ldq; g.sa = ws.oz_scale; g.Qb = ws.oz_q; g.ldqb = ldq; g.sb = ws.oz_scale;
                 g.C = A; g.ldc = lda; g.alpha = 1.0; g.mask = MASK_BLOCK_STRICT_UPPER; g.mask_nb = NB;
                 GPB_TRY(ozaki_gemm(s, g));
@@ -463,6 +474,7 @@ int mll_forward(stream_t s, const MllArgs& a, const FactorWs& ws, double* value_
     double* half_logdet = ws.scal;
     double* quad = ws.scal + 1;
     GPB_TRY(sub_scalar(s, N, a.y, a.mean_const, dvec));
+    GPB_TRY(factor_set_planes(s, ws, N, a.variance, a.obs_stddev, a.jitter));  // conditioning guard of the int8 updates
     GramDesc g;
     g.kind = a.kind; g.N = N; g.M = N; g.D = a.D;
     g.X = a.X; g.ldx = a.ldx; g.Z = a.X; g.ldz = a.ldx;
@@ -484,6 +496,7 @@ int mll_forward(stream_t s, const MllArgs& a, const FactorWs& ws, double* value_
 int mll_backward(stream_t s, const MllArgs& a, const FactorWs& ws, const double* alpha, const double* gout,
                  double* g_ell, double* g_var, double* g_obs_stddev, double* g_mean) {
     if (a.N <= 0 || !a.Sigma || !alpha || !ws.Sdiag || !ws.partials) return GPB_ERR_INVALID;
+    // ws.oz_planes still holds the plane count mll_forward's guard chose for this Sigma ("ws exactly as mll_forward left it")
     GPB_TRY(trtri_into_upper(s, a.N, a.Sigma, a.lds, ws));
     GPB_TRY(lauum_upper(s, a.N, a.Sigma, a.lds, ws));
     MllBwdDesc d;

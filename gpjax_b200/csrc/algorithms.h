@@ -18,12 +18,20 @@ constexpr int64_t LEAFN = 128; // leaf size handled by potrf_leaf
 inline int64_t nblocks(int64_t n) { return (n + NB - 1) / NB; }
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
-// ---- runtime switch: digit planes of the Ozaki (int8 tensor pipe) trailing updates; 0 = FP64 DMMA everywhere.
-// Default 7 planes (error of a rank-1024 update <= 1.5e-11 |a_i|_inf |b_j|_inf worst case, ~1e-13 measured: N = 50k value and
-// gradient agree with the DMMA path to 3e-13, far inside the 1e-8 contract); 8 planes reproduce fp64 rounding level.
-// Read from the environment variable GPB_OZAKI at first use, overridable through set_ozaki_slices.
+// ---- process-wide switch: arithmetic of the rank-NB trailing updates (>= OZ_MIN_ROWS output rows) ------------------------
+//   OZ_AUTO (-1, default): int8 digit planes on tcgen05, plane count decided per call ON THE DEVICE by ozaki_choose_planes:
+//                          the fused objectives use 7 planes only when the hyper-parameters bound cond(Sigma) by 1e7, else 8;
+//                          a bare matrix (gpb_potrf_lower / gpb_potri_lower: nothing known about it) always gets 8;
+//   5..8                 : that many planes everywhere (measurement / opt-in);
+//   0                    : FP64 DMMA everywhere (also switches the SGPR / SVGP int8 products off).
+// Why 8 unless proven benign (profiles/r02_cond_sweep_n8192.jsonl, tests/test_gpu_conditioning.py, N = 8192, cond 1e3 .. 3e8):
+// 8 planes (56 bits below the row maximum) are indistinguishable from the FP64 DMMA path against the CPU oracle at every
+// conditioning, and the triangular solves agree element-wise to 2e-10; 7 planes sit 10-30x above the DMMA path's error
+// (~5e-17 cond relative in the gradient: 1e-9 at cond 1e7, 1.1e-8 at cond 3e8) and 3e-8 element-wise in the solves.
+// Read from the environment variable GPB_OZAKI ("auto", 0, 5..8) at first use, overridable through set_ozaki_slices; the
+// value is a std::atomic configuration word -- it is not meant to change while calls are in flight.
 #ifndef GPB_OZ_DEFAULT
-#define GPB_OZ_DEFAULT 7
+#define GPB_OZ_DEFAULT OZ_AUTO
 #endif
 void set_ozaki_slices(int nslices);
 int get_ozaki_slices();
@@ -51,7 +59,11 @@ struct FactorWs {
     int8_t* oz_q2 = nullptr;
     double* oz_scale = nullptr;
     double* oz_scale2 = nullptr;
+    int* oz_planes = nullptr;  // device word: planes the int8 updates of the current call use (ozaki_choose_planes)
 };
+// Writes ws.oz_planes for the next factorisation-family call on this workspace: `variance` / `obs_stddev` (device scalars) of
+// the covariance being factored when known (fused objectives), nullptr for a bare matrix.  No-op on the DMMA path.
+int factor_set_planes(stream_t s, const FactorWs& ws, int64_t N, const double* variance, const double* obs_stddev, double jitter);
 // bytes needed for an N x N problem with D input dims (with_potri: include Sdiag + backward partials)
 int64_t factor_ws_bytes(int64_t N, int D, int with_potri);
 // carve `ws` out of a caller buffer; returns GPB_ERR_WORKSPACE if too small

@@ -1,6 +1,7 @@
 // Shared device helpers for the sm_100a kernels (float64 everywhere).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstdint>
 #include "primitives.h"
 
@@ -14,6 +15,21 @@ namespace gpb {
     } while (0)
 
 static inline cudaStream_t to_stream(stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- per-device (never per-process) launch state ------------------------------------------------------
+// One process may drive several GPUs from several threads (XLA's per-device executors, include/gpjax_b200.h "re-entrant"):
+// cudaFuncSetAttribute applies to the CURRENT device only, so every "already configured" flag is kept per device.
+constexpr int GPB_MAX_DEVICES = 64;
+static inline int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= GPB_MAX_DEVICES) return 0;
+    return dev;
+}
+struct PerDeviceOnce {
+    std::atomic<unsigned char> done[GPB_MAX_DEVICES];
+    bool needed(int dev) const { return done[dev].load(std::memory_order_acquire) == 0; }
+    void mark(int dev) { done[dev].store(1, std::memory_order_release); }  // setting the attribute twice is harmless
+};
 
 // ---- cp.async (LDGSTS) with zero-fill -------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {

@@ -478,12 +478,13 @@ int launch_gemm(cudaStream_t st, const GemmParams& p, int batch) {
     using GB = TileGeom<BN, BLAY, SWZ>;
     constexpr size_t smem = sizeof(double) * STAGES * (GA::SIZE + GB::SIZE) + (BULK ? STAGES * sizeof(uint64_t) : 0);
     auto kern = gemm_f64_kernel<BM, BN, WM, WN, STAGES, MINB, SWZ, BULK, ALAY, BLAY>;
-    static bool configured = false;  // per-instantiation, idempotent
-    if (!configured) {
+    static PerDeviceOnce configured;  // per instantiation AND per device
+    const int dev = current_device();
+    if (configured.needed(dev)) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return GPB_ERR_LAUNCH;
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-        configured = true;
+        configured.mark(dev);
     }
     const int64_t T = p.tiles_m;
     if (T <= 0 || p.tiles_n <= 0 || batch <= 0) return GPB_OK;

@@ -72,8 +72,17 @@ struct OzParams {
     int nstages, stage_bytes;  // ring geometry (v1)
     int pair;             // v1: accumulate orders (t, t+1) together so every loaded A tile feeds two MMAs (see kernel)
     int noload;           // measurement hook (GPB_OZ_NOLOAD=1): the producer signals `full` without issuing TMA -> pure MMA pacing
-    int bn;               // output tile width of the launched kernel variant (128: v1, 64: v2)
+    int bn;               // output tile width of the launched kernel variant (128: v1 / v3, 64: v2)
+    int bm;               // output tile height the walk enumerates (128: v1 / v2; 256: v3, one tile per CTA pair)
+    const int* planes_dev;  // optional device word overriding nslices (1..nslices): the conditioning guard, read in-kernel
 };
+// planes actually used by this launch (uniform across the grid: every role of every CTA reads the same word)
+__device__ __forceinline__ int oz_groups(const OzParams& p, int mode) {
+    if (mode == 0) return 1;
+    if (!p.planes_dev) return p.nslices;
+    const int v = __ldg(p.planes_dev);
+    return v < 1 ? 1 : (v > p.nslices ? p.nslices : v);
+}
 
 // ---- tile enumeration shared by the three roles: column chunks -> tile rows -> tile columns, dead tiles of the lower
 // mask never enumerated ----------------------------------------------------------------------------------------------
@@ -82,7 +91,7 @@ struct TileWalk {
     long long base = 0;  // linear index of the first tile of (chunk, tm)
     __device__ int live_end(const OzParams& p, int tm_) const {  // one past the last live tile column of tile row tm_
         if (p.mask != 1) return p.ntn;
-        long long last_row = p.row0 + (long long)tm_ * OZ_BM + OZ_BM - 1;
+        long long last_row = p.row0 + (long long)tm_ * p.bm + p.bm - 1;
         long long d = last_row - p.col0;
         if (d < 0) return 0;
         long long e = d / p.bn + 1;
@@ -90,7 +99,7 @@ struct TileWalk {
     }
     __device__ int live_begin(const OzParams& p, int tm_) const {  // first live tile column of tile row tm_
         if (p.mask != 2) return 0;
-        long long rb = (p.row0 + (long long)tm_ * OZ_BM) / p.mask_nb;     // block of the tile's FIRST row (smallest)
+        long long rb = (p.row0 + (long long)tm_ * p.bm) / p.mask_nb;     // block of the tile's FIRST row (smallest)
         long long need = (rb + 1) * p.mask_nb - (p.bn - 1) - p.col0;     // col0 + tn*BN + BN-1 >= (rb+1)*nb
         if (need <= 0) return 0;
         long long b = (need + p.bn - 1) / p.bn;
@@ -243,7 +252,7 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc_fence_after();
     const unsigned tmem_base = *tmem_slot;
 
-    const int groups = MODE == 0 ? 1 : p.nslices;
+    const int groups = oz_groups(p, MODE);
 
     if (warp == 0) {
         {  // ===== TMA producer (whole warp walks the schedule, one elected lane issues) =====
@@ -504,7 +513,7 @@ ozaki_i8_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tc_fence_after();
     const unsigned tmem_base = *tmem_slot;
 
-    const int S = MODE == 0 ? 1 : p.nslices;
+    const int S = oz_groups(p, MODE);
     const int KB = p.kblocks;
 
     if (warp == 0) {
@@ -644,6 +653,282 @@ ozaki_i8_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---- variant 3 (default): CTA pairs, tcgen05.mma.cta_group::2, M = 256 x N = 128 per pair -----------------------------------
+// Measured on v1 (profiles/r01_ozaki.md section 3, profiles/r02_ozaki_cg2.md): with the TMA loads switched off an M128 x N128 x K32
+// kind::i8 instruction still paces at ~145 clk, an N = 64 one at ~110 clk, cuBLASLt's N = 256 ones at ~210 clk, i.e.
+// ~(4096 + 32 N) / 56 clk: the instruction is paced by the 32 (M + N) operand bytes it pulls out of shared memory (~56 B/clk),
+// not by the int8 pipe (64 clk for 128 x 128 x 32).  A CTA pair sharing one MMA halves the B bytes per SM: each CTA stages its
+// own 128 rows of A (16 KB per K-block) and HALF of the B tile (64 rows, 8 KB); one elected thread of the leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256, N = 128), each SM accumulates its 128 x 128 half in its own TMEM.  Per SM that is 6 KB
+// instead of 8 KB of operand reads per instruction and 24 KB instead of 32 KB of L2 -> SM traffic per ring slot.
+//   * cluster of 2 CTAs (__cluster_dims__), one cluster per TPC, persistent over 256 x 128 output tiles (same TileWalk);
+//   * TMA: cp.async.bulk.tensor.2d.cta_group::2, both CTAs complete_tx on the LEADER's `full` barrier (mapa to rank 0);
+//   * tcgen05.commit.cta_group::2 ... multicast::cluster frees the ring slot / publishes the accumulator in BOTH CTAs;
+//   * the epilogue warps of both CTAs arrive on the leader's `tempty` barrier (count 2 x 8 warps);
+//   * same paired-order schedule as v1 (ring slot i of a K-block = (A_i, B_{t+1-i}), two live accumulators), 8-slot ring.
+constexpr int C2_BM = 256;                        // rows per pair tile (128 per CTA)
+constexpr int C2_BNH = OZ_BN / 2;                 // B rows staged by each CTA
+constexpr int C2_A_BYTES = OZ_BM * OZ_BK;         // 16 KB
+constexpr int C2_B_BYTES = C2_BNH * OZ_BK;        //  8 KB
+constexpr int C2_SLOT_BYTES = C2_A_BYTES + C2_B_BYTES;  // 24 KB
+constexpr int C2_RING = 8;
+constexpr int C2_SMEM_BYTES = C2_RING * C2_SLOT_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+// instruction descriptor: D = s32, A = B = signed int8, both K-major, N = 128, M = 256 (cta_group::2)
+constexpr unsigned C2_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(OZ_BN >> 3) << 17) | ((unsigned)(C2_BM >> 4) << 24);
+static_assert(C2_SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
+
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta pointer of this CTA) as seen in CTA `rank` of the cluster
+__device__ __forceinline__ unsigned mapa_u32(const void* p, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(unsigned cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of a CTA pair: data lands in THIS CTA's shared memory, the transaction bytes are signalled on the mbarrier at the
+// shared::cluster address `bar_cluster` (the leader's `full` barrier)
+__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* map, unsigned bar_cluster, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(bar_cluster), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_cg2(uint64_t* bar) {  // arrives on the barrier at this offset in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+                     smem_u32(bar)),
+                 "h"((unsigned short)3)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8_cg2(unsigned tmem_d, uint64_t adesc, uint64_t bdesc, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1)
+ozaki_i8_kernel_cg2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const OzParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const unsigned raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);  // identical offset in both CTAs of the pair
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C2_RING * C2_SLOT_BYTES);
+    uint64_t* full = bars;                       // [8]   TMA (both CTAs) -> MMA; only the leader's copies are used
+    uint64_t* empty = bars + C2_RING;            // [8]   MMA -> TMA, multicast to both CTAs
+    uint64_t* tfull = bars + 2 * C2_RING;        // [ACC] MMA -> epilogue, multicast to both CTAs
+    uint64_t* tempty = tfull + OZ_ACC_STAGES;    // [ACC] epilogue (both CTAs) -> MMA; only the leader's copies are used
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty + OZ_ACC_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < C2_RING; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < OZ_ACC_STAGES; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * OZ_EPI_WARPS); }
+        mbar_fence_init();
+    }
+    if (warp == 2) {  // the same warp of BOTH CTAs executes the pair allocation; each gets the base address in its own smem
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();  // barrier inits + TMEM base visible to the peer before anything signals across the pair
+    tc_fence_after();
+    const unsigned tmem_base = *tmem_slot;
+
+    const int groups = oz_groups(p, MODE);
+
+    if (warp == 0) {
+        {  // ===== TMA producer (both CTAs): own 128 rows of A, own 64 rows of B; bytes are counted on the leader's barrier =====
+            TileWalk w; w.init(p);
+            int stage = 0; unsigned phase = 0;
+            int tm, tn;
+            for (long long idx = pair; w.seek(p, idx, tm, tn); idx += npairs) {
+                const int m0 = tm * C2_BM + (int)rank * OZ_BM, n0 = tn * OZ_BN + (int)rank * C2_BNH;
+                for (int t = 0; t < groups;) {
+                    const bool paired = p.pair && ((groups - t) & 1) == 0;  // odd plane count: order 0 runs unpaired
+                    // paired: slot i of a K-block holds (A_i, B_{t+1-i}), i = 0..t+1; unpaired: (A_pa, B_{t-pa}), pa = 0..t
+                    const int nsl = paired ? t + 2 : t + 1;
+                    const int bsum = paired ? t + 1 : t;
+                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                        for (int i = 0; i < nsl; ++i) {
+                            mbar_wait_bounded(&empty[stage], phase ^ 1u);
+                            uint8_t* sA = smem + stage * C2_SLOT_BYTES;
+                            if (elect_one()) {
+                                if (p.noload) {
+                                    if (rank == 0) mbar_arrive(&full[stage]);
+                                } else {
+                                    if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * C2_SLOT_BYTES);
+                                    const unsigned fb = mapa_u32(&full[stage], 0);
+                                    tma_load_2d_cg2(sA, &tmA, fb, i * p.pstride + kb * OZ_BK, m0);
+                                    tma_load_2d_cg2(sA + C2_A_BYTES, &tmB, fb, (bsum - i) * p.pstride + kb * OZ_BK, n0);
+                                }
+                            }
+                            __syncwarp();
+                            if (++stage == C2_RING) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                    t += paired ? 2 : 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {  // ===== MMA issuer: leader CTA only, one elected lane =====
+            TileWalk w; w.init(p);
+            int stage = 0; unsigned phase = 0;
+            int acc = 0; unsigned aphase = 0;
+            int tm, tn;
+            for (long long idx = pair; w.seek(p, idx, tm, tn); idx += npairs) {
+                for (int t = 0; t < groups;) {
+                    if (p.pair && ((groups - t) & 1) == 0) {
+                        const int a_lo = acc; const unsigned ph_lo = aphase;
+                        if (++acc == OZ_ACC_STAGES) { acc = 0; aphase ^= 1u; }
+                        const int a_hi = acc; const unsigned ph_hi = aphase;
+                        if (++acc == OZ_ACC_STAGES) { acc = 0; aphase ^= 1u; }
+                        mbar_wait_bounded(&tempty[a_lo], ph_lo ^ 1u);
+                        mbar_wait_bounded(&tempty[a_hi], ph_hi ^ 1u);
+                        tc_fence_after();
+                        const unsigned d_lo = tmem_base + (unsigned)(a_lo * OZ_BN), d_hi = tmem_base + (unsigned)(a_hi * OZ_BN);
+                        int prev = 0;
+                        for (int kb = 0; kb < p.kblocks; ++kb) {
+                            for (int i = 0; i <= t + 1; ++i) {
+                                mbar_wait_bounded(&full[stage], phase);
+                                tc_fence_after();
+                                const unsigned sA = smem_u32(smem + stage * C2_SLOT_BYTES);
+                                const unsigned sP = smem_u32(smem + prev * C2_SLOT_BYTES);
+                                if (elect_one()) {
+                                    const uint64_t da = umma_desc_k_sw128(sA), db = umma_desc_k_sw128(sA + C2_A_BYTES);
+#pragma unroll
+                                    for (int kk = 0; kk < OZ_BK / 32; ++kk)
+                                        tc_mma_i8_cg2(d_hi, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), C2_IDESC, (kb | i | kk) != 0);
+                                    if (i >= 1) {
+                                        const uint64_t dp = umma_desc_k_sw128(sP);
+#pragma unroll
+                                        for (int kk = 0; kk < OZ_BK / 32; ++kk)
+                                            tc_mma_i8_cg2(d_lo, dp + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), C2_IDESC,
+                                                          !(kb == 0 && i == 1 && kk == 0));
+                                        tc_commit_cg2(&empty[prev]);
+                                    }
+                                    if (i == t + 1) {
+                                        tc_commit_cg2(&empty[stage]);
+                                        if (kb == p.kblocks - 1) { tc_commit_cg2(&tfull[a_lo]); tc_commit_cg2(&tfull[a_hi]); }
+                                    }
+                                }
+                                __syncwarp();
+                                prev = stage;
+                                if (++stage == C2_RING) { stage = 0; phase ^= 1u; }
+                            }
+                        }
+                        t += 2;
+                        continue;
+                    }
+                    mbar_wait_bounded(&tempty[acc], aphase ^ 1u);
+                    tc_fence_after();
+                    const unsigned d_tmem = tmem_base + (unsigned)(acc * OZ_BN);
+                    const int nkb = (t + 1) * p.kblocks;
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        mbar_wait_bounded(&full[stage], phase);
+                        tc_fence_after();
+                        const unsigned sA = smem_u32(smem + stage * C2_SLOT_BYTES);
+                        if (elect_one()) {
+                            const uint64_t da = umma_desc_k_sw128(sA), db = umma_desc_k_sw128(sA + C2_A_BYTES);
+#pragma unroll
+                            for (int kk = 0; kk < OZ_BK / 32; ++kk)
+                                tc_mma_i8_cg2(d_tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), C2_IDESC, (kb | kk) != 0);
+                            tc_commit_cg2(&empty[stage]);
+                            if (kb + 1 >= nkb) tc_commit_cg2(&tfull[acc]);
+                        }
+                        __syncwarp();
+                        if (++stage == C2_RING) { stage = 0; phase ^= 1u; }
+                    }
+                    if (++acc == OZ_ACC_STAGES) { acc = 0; aphase ^= 1u; }
+                    ++t;
+                }
+            }
+        }
+    } else if (warp >= OZ_EPI_WARP0) {
+        // ===== epilogue (both CTAs): warp (4 + 4 h + q) owns TMEM lanes [32 q, 32 q + 32) and tile columns [64 h, 64 h + 64) =====
+        const int q = warp & 3, h = (warp - OZ_EPI_WARP0) >> 2;
+        TileWalk w; w.init(p);
+        int acc = 0; unsigned aphase = 0;
+        int tm, tn;
+        for (long long idx = pair; w.seek(p, idx, tm, tn); idx += npairs) {
+            const int row = tm * C2_BM + (int)rank * OZ_BM + q * 32 + lane;
+            const int col0 = tn * OZ_BN + h * 64;
+            double accd[MODE == 1 ? 64 : 1];
+            if (MODE == 1) {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) accd[j] = 0.0;
+            }
+            for (int t = 0; t < groups; ++t) {
+                mbar_wait_bounded(&tfull[acc], aphase);
+                tc_fence_after();
+                const double sc = __hiloint2double((1023 - OZ_BETA * (t + 2)) << 20, 0);  // 2^(-7 (t+2))
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    unsigned r[32];
+                    tc_ld32(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(acc * OZ_BN + h * 64 + c * 32), r);
+                    if (MODE == 1) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) accd[c * 32 + j] = fma(exact_i2d((int)r[j]), sc, accd[c * 32 + j]);
+                    } else {
+                        if (row < p.m) {
+                            int* dst = p.Ci + (long long)row * p.ldci + col0 + c * 32;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + c * 32 + j < p.n) dst[j] = (int)r[j];
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty[acc], 0));  // the leader's barrier counts both CTAs
+                if (++acc == OZ_ACC_STAGES) { acc = 0; aphase ^= 1u; }
+            }
+            if (MODE == 1 && row < p.m) {
+                const double sr = p.alpha * __ldg(p.sa + row);
+                double* crow = p.C + (long long)row * p.ldc;
+                const long long grow = p.row0 + row;
+#pragma unroll
+                for (int j = 0; j < 64; ++j) {
+                    const int col = col0 + j;
+                    bool live = col < p.n;
+                    if (p.mask == 1) live = live && (grow >= p.col0 + col);
+                    else if (p.mask == 2) live = live && (grow / p.mask_nb < (p.col0 + col) / p.mask_nb);
+                    if (live) {
+                        const double v = accd[j] * (sr * __ldg(p.sb + col));
+                        crow[col] = p.beta0 ? v : crow[col] + v;
+                    }
+                }
+            }
+        }
+    }
+
+    // neither CTA may exit (or free its TMEM) while the peer can still read its shared memory / signal its barriers
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
@@ -822,41 +1107,48 @@ int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t width, in
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? GPB_OK : GPB_ERR_INVALID;
 }
-int sm_count() {
-    static int n = [] {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
-        return v;
-    }();
-    return n;
-}
-int g_variant = -1;  // 1: order-by-order schedule (v1, default: measured faster), 2: plane-resident schedule (GPB_OZ_KERNEL=2)
-int variant() {
-    if (g_variant < 0) {
-        const char* e = std::getenv("GPB_OZ_KERNEL");
-        g_variant = (e && std::atoi(e) == 2) ? 2 : 1;
+int sm_count() {  // per device: one process may drive several GPUs (XLA's per-device threads)
+    static int n[GPB_MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (n[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        n[dev] = v;
     }
-    return g_variant;
+    return n[dev];
+}
+// kernel variant: 3 = CTA pairs / cta_group::2 (default), 1 = one CTA per tile (round-1 kernel), 2 = plane-resident 128 x 64 tiles.
+// GPB_OZ_KERNEL selects 1 / 2 for measurements (profiles/r02_ozaki_cg2.md); read once, the value never changes afterwards.
+int variant() {
+    static const int v = [] {
+        const char* e = std::getenv("GPB_OZ_KERNEL");
+        const int x = e ? std::atoi(e) : 3;
+        return (x >= 1 && x <= 3) ? x : 3;
+    }();
+    return v;
 }
 template <int MODE>
 int launch(stream_t s, const void* A, int64_t rowsA, int64_t lda, const void* B, int64_t rowsB, int64_t ldb, int64_t width,
            OzParams& p) {
     const int v = variant();
-    static bool attr_set[3] = {false, false, false};
-    if (!attr_set[v]) {
-        cudaError_t e = v == 1 ? cudaFuncSetAttribute(ozaki_i8_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES)
-                               : cudaFuncSetAttribute(ozaki_i8_kernel_v2<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, O2_SMEM_BYTES);
+    // cudaFuncSetAttribute is per device: remember it per (device, variant), never per process
+    static bool attr_set[GPB_MAX_DEVICES][4] = {};
+    const int dev = current_device();
+    if (!attr_set[dev][v]) {
+        cudaError_t e = v == 1   ? cudaFuncSetAttribute(ozaki_i8_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES)
+                        : v == 2 ? cudaFuncSetAttribute(ozaki_i8_kernel_v2<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, O2_SMEM_BYTES)
+                                 : cudaFuncSetAttribute(ozaki_i8_kernel_cg2<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES);
         if (e != cudaSuccess) return GPB_ERR_LAUNCH;
-        attr_set[v] = true;
+        attr_set[dev][v] = true;
     }
-    p.bn = v == 1 ? OZ_BN : O2_BN;
+    p.bn = v == 2 ? O2_BN : OZ_BN;
+    p.bm = v == 3 ? C2_BM : OZ_BM;
     p.kbs = (p.kblocks % OZ_KBS_MAX == 0 && !std::getenv("GPB_OZ_KBS1")) ? OZ_KBS_MAX : 1;
     {
         static int pair = [] { const char* e = std::getenv("GPB_OZ_PAIR"); return (e && std::atoi(e) == 0) ? 0 : 1; }();
         p.pair = pair;
     }
-    if (p.pair && p.nslices > 1) {  // paired orders: 6 slots of one (A, B) K-block pair
+    if (p.pair && p.nslices > 1) {  // paired orders: ring slots of one (A, B) K-block pair
         p.kbs = 1; p.nstages = OZ_MAX_RING; p.stage_bytes = OZ_KB_BYTES;
     } else {
         p.pair = 0; p.nstages = OZ_STAGES; p.stage_bytes = OZ_STAGE_BYTES;
@@ -868,12 +1160,14 @@ int launch(stream_t s, const void* A, int64_t rowsA, int64_t lda, const void* B,
     CUtensorMap ta, tb;
     int rc = make_map(&ta, A, rowsA, width, lda, OZ_BM);
     if (rc) return rc;
-    rc = make_map(&tb, B, rowsB, width, ldb, p.bn);
+    rc = make_map(&tb, B, rowsB, width, ldb, v == 3 ? C2_BNH : p.bn);
     if (rc) return rc;
-    p.ntm = (p.m + OZ_BM - 1) / OZ_BM;
+    p.ntm = (p.m + p.bm - 1) / p.bm;
     p.ntn = (p.n + p.bn - 1) / p.bn;
     long long tiles = (long long)p.ntm * p.ntn;  // upper bound on the live tiles; CTAs beyond the live count exit at once
-    int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    const int ctas_per_tile = v == 3 ? 2 : 1;
+    const int units = sm_count() / ctas_per_tile;  // v3: one CTA pair per TPC
+    int grid = (int)(tiles < units ? tiles : units) * ctas_per_tile;
     if (grid <= 0) return GPB_OK;
     const bool prof = profile_enabled();
     if (prof) {  // algorithmic int8 operations: live output entries x K x digit pairs x 2
@@ -894,7 +1188,8 @@ int launch(stream_t s, const void* A, int64_t rowsA, int64_t lda, const void* B,
         profile_ozaki_begin(s, 2.0 * live * (double)p.kblocks * OZ_BK * (S * (S + 1) / 2));
     }
     if (v == 1) ozaki_i8_kernel<MODE><<<grid, OZ_THREADS, OZ_SMEM_BYTES, to_stream(s)>>>(ta, tb, p);
-    else ozaki_i8_kernel_v2<MODE><<<grid, OZ_THREADS, O2_SMEM_BYTES, to_stream(s)>>>(ta, tb, p);
+    else if (v == 2) ozaki_i8_kernel_v2<MODE><<<grid, OZ_THREADS, O2_SMEM_BYTES, to_stream(s)>>>(ta, tb, p);
+    else ozaki_i8_kernel_cg2<MODE><<<grid, OZ_THREADS, C2_SMEM_BYTES, to_stream(s)>>>(ta, tb, p);
     if (prof) profile_gemm_end(s);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
@@ -962,7 +1257,7 @@ int ozaki_gemm(stream_t s, const OzakiGemmDesc& d) {
     OzParams p = {};
     p.m = (int)d.M; p.n = (int)d.N; p.kblocks = (int)(d.K / OZ_BK); p.nslices = d.nslices;
     p.mask = d.mask == MASK_LOWER ? 1 : (d.mask == MASK_BLOCK_STRICT_UPPER ? 2 : 0); p.row0 = d.mask_row0; p.col0 = d.mask_col0; p.mask_nb = d.mask_nb > 0 ? d.mask_nb : 1;
-    p.C = d.C; p.ldc = d.ldc; p.sa = d.sa; p.sb = d.sb; p.alpha = d.alpha; p.beta0 = d.beta0;
+    p.C = d.C; p.ldc = d.ldc; p.sa = d.sa; p.sb = d.sb; p.alpha = d.alpha; p.beta0 = d.beta0; p.planes_dev = d.nslices_dev;
     const int64_t ps = d.plane_stride > 0 ? d.plane_stride : d.K;
     if (ps < d.K || ps % 16) return GPB_ERR_INVALID;
     p.pstride = (int)ps;
@@ -970,5 +1265,35 @@ int ozaki_gemm(stream_t s, const OzakiGemmDesc& d) {
 }
 
 bool ozaki_available() { return encode_tiled() != nullptr; }
+
+namespace {
+__global__ void ozaki_choose_planes_kernel(int requested, double n, const double* __restrict__ variance,
+                                           const double* __restrict__ obs_stddev, double jitter, int* __restrict__ out) {
+    int planes = requested;
+    if (requested == OZ_AUTO) {
+        planes = 8;
+        if (variance && obs_stddev) {
+            const double s = obs_stddev[0] * obs_stddev[0] + jitter;
+            const double bound = (n * fabs(variance[0]) + s) / s;  // NaN / s == 0 compare false -> 8 planes
+            if (bound <= OZ_AUTO_COND_LIMIT) planes = 7;
+        }
+    }
+    out[0] = planes;
+}
+}  // namespace
+
+int ozaki_choose_planes(stream_t s, int requested, int64_t N, const double* variance, const double* obs_stddev, double jitter,
+                        int* planes_out) {
+    if (!planes_out || N < 0 || !(requested == OZ_AUTO || (requested >= 1 && requested <= 8))) return GPB_ERR_INVALID;
+    ozaki_choose_planes_kernel<<<1, 1, 0, to_stream(s)>>>(requested, (double)N, variance, obs_stddev, jitter, planes_out);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+int ozaki_auto_planes_host(int64_t N, double variance, double obs_stddev, double jitter) {
+    const double s = obs_stddev * obs_stddev + jitter;
+    const double bound = ((double)N * (variance < 0 ? -variance : variance) + s) / s;
+    return bound <= OZ_AUTO_COND_LIMIT ? 7 : 8;
+}
 
 }  // namespace gpb

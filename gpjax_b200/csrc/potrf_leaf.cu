@@ -228,12 +228,13 @@ int potrf_leaf(stream_t s, int n, double* A, int64_t lda, double* Dinv, int64_t 
     if (n == 0) return GPB_OK;
     if (!A) return GPB_ERR_INVALID;
     constexpr size_t smem = sizeof(double) * (LEAF * LDSM);  // 129 KB: fits next to one resident GEMM CTA
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;
+    const int dev = current_device();
+    if (configured.needed(dev)) {
         if (cudaFuncSetAttribute(potrf_leaf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
             cudaSuccess)
             return GPB_ERR_LAUNCH;
-        configured = true;
+        configured.mark(dev);
     }
     potrf_leaf_kernel<<<1, LT, smem, to_stream(s)>>>(n, A, lda, Dinv, ldd, DinvT, lddt, info, global_row0, factor);
     GPB_LAUNCH_CHECK();

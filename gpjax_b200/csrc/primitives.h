@@ -269,7 +269,9 @@ int col_weighted_sums(stream_t s, int64_t rows, int64_t cols, const double* X, i
                       double* out_w, double* out_1);
 struct OzakiGemmDesc {
     int64_t M = 0, N = 0, K = 0;  // K = digits per plane (multiple of 128)
-    int nslices = 7;
+    int nslices = 7;              // digit planes present in Qa / Qb (and used, unless nslices_dev overrides it)
+    const int* nslices_dev = nullptr;  // optional DEVICE word: planes to use, 1..nslices (the guard of ozaki_choose_planes);
+                                       // read by the kernel, so the host never synchronises on the decision
     const int8_t* Qa = nullptr;   // [M, nslices*K]
     int64_t ldqa = 0;
     const double* sa = nullptr;   // [M] row scales
@@ -285,6 +287,20 @@ struct OzakiGemmDesc {
     int64_t mask_row0 = 0, mask_col0 = 0, mask_nb = 1;
 };
 int ozaki_gemm(stream_t s, const OzakiGemmDesc& d);
+// Digit planes of the int8 trailing updates of an N x N covariance factorisation, decided ON THE DEVICE (no host read):
+//   requested in 5..8        -> planes_out[0] = requested;
+//   requested == OZ_AUTO (-1)-> 7 if the hyper-parameters PROVE cond(Sigma) <= OZ_AUTO_COND_LIMIT, else 8, with the bound
+//                               cond(K + s I) <= (N * variance + s) / s,  s = obs_stddev^2 + jitter   (|k(x,y)| <= variance =>
+//                               lambda_max(K) <= N variance by Gershgorin; lambda_min(Sigma) >= s);
+//                               variance == nullptr (a bare matrix, nothing known about it) -> 8.
+// Calibration (profiles/r02_cond_sweep_n8192.jsonl): 8 planes = the FP64 DMMA path's own error level at every cond; 7 planes
+// ~ 5e-17 * cond relative error in the MLL gradient, i.e. <= 1e-9 while cond <= 1e7.
+constexpr int OZ_AUTO = -1;
+constexpr double OZ_AUTO_COND_LIMIT = 1e7;
+int ozaki_choose_planes(stream_t s, int requested, int64_t N, const double* variance, const double* obs_stddev, double jitter,
+                        int* planes_out);
+// the same rule on the host, for reporting (bench.py) and tests; never used to steer a launch
+int ozaki_auto_planes_host(int64_t N, double variance, double obs_stddev, double jitter);
 // C[m,n] (int32) = A[m,k] B[n,k]^T for int8 operands (k multiple of 128, lda/ldb multiples of 16): the raw tcgen05 product
 int igemm_i8(stream_t s, int64_t m, int64_t n, int64_t k, const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb,
              int32_t* C, int64_t ldc);

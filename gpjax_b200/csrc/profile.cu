@@ -88,44 +88,41 @@ int profile_read_ozaki(double* ms, int64_t* launches, double* int8_ops) {
 
 
 // ---- helper streams for lookahead ---------------------------------------------------------------------
+// Kept PER DEVICE (one process may drive several GPUs from several threads); created lazily, never destroyed.  Two host
+// threads driving the same device share its helper streams: the fork / join events keep every call's own ordering intact.
 namespace {
 struct Side {
     std::mutex mu;
-    int device = -1;
     cudaStream_t streams[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t events[64];
     int nev = 0, next = 0;
-} g_side;
+};
+Side g_side[GPB_MAX_DEVICES];
 }  // namespace
 
 stream_t side_stream(stream_t main, int idx) {
     if (idx < 0 || idx >= 4) return main;
-    std::lock_guard<std::mutex> lk(g_side.mu);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (g_side.device != dev) {  // one process drives one GPU; re-create if the device changed
-        for (auto& s : g_side.streams) s = nullptr;
-        g_side.nev = 0;
-        g_side.device = dev;
-    }
-    if (!g_side.streams[idx]) {
+    Side& sd = g_side[current_device()];
+    std::lock_guard<std::mutex> lk(sd.mu);
+    if (!sd.streams[idx]) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = numerically lowest = highest priority
-        if (cudaStreamCreateWithPriority(&g_side.streams[idx], cudaStreamNonBlocking, hi) != cudaSuccess) return main;
+        if (cudaStreamCreateWithPriority(&sd.streams[idx], cudaStreamNonBlocking, hi) != cudaSuccess) return main;
     }
-    return reinterpret_cast<stream_t>(g_side.streams[idx]);
+    return reinterpret_cast<stream_t>(sd.streams[idx]);
 }
 
 int stream_fork(stream_t from, stream_t to) {
     if (from == to) return GPB_OK;
-    std::lock_guard<std::mutex> lk(g_side.mu);
-    if (g_side.nev < 64) {
-        if (cudaEventCreateWithFlags(&g_side.events[g_side.nev], cudaEventDisableTiming) != cudaSuccess)
+    Side& sd = g_side[current_device()];
+    std::lock_guard<std::mutex> lk(sd.mu);
+    if (sd.nev < 64) {
+        if (cudaEventCreateWithFlags(&sd.events[sd.nev], cudaEventDisableTiming) != cudaSuccess)
             return GPB_ERR_LAUNCH;
-        g_side.nev++;
+        sd.nev++;
     }
-    cudaEvent_t ev = g_side.events[g_side.next % g_side.nev];
-    g_side.next++;
+    cudaEvent_t ev = sd.events[sd.next % sd.nev];
+    sd.next++;
     // re-recording an event does not disturb waits that were enqueued on its previous record
     if (cudaEventRecord(ev, to_stream(from)) != cudaSuccess) return GPB_ERR_LAUNCH;
     if (cudaStreamWaitEvent(to_stream(to), ev, 0) != cudaSuccess) return GPB_ERR_LAUNCH;

@@ -8,6 +8,7 @@ classes are the analogue of the ``jax.custom_vjp`` registrations the north-star 
 """
 from __future__ import annotations
 
+import itertools
 import math
 from typing import Optional
 
@@ -27,6 +28,24 @@ def _p(t: Optional[torch.Tensor]):
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+# Forward "generation" tokens: drawn from ONE process-wide counter, so a state object that is evicted and re-created
+# (another problem size took the buffer) can never hand out a number an older forward still holds.
+_GENERATION = itertools.count(1)
+
+
+def next_generation() -> int:
+    return next(_GENERATION)
+
+
+def _no_data_grad(ctx, positions, what: str) -> None:
+    """The fused objectives return no cotangent for the data (X, y): refuse instead of silently returning zero."""
+    if any(ctx.needs_input_grad[i] for i in positions):
+        raise NotImplementedError(
+            f"{what}: gradients with respect to the data (X / y) are not produced by the fused objective; build the "
+            "covariance with kernel.gram(...) / GaussianDistribution.log_prob (ops.GramFunction + GaussianLogProbFunction), "
+            "which differentiate through the inputs")
 
 
 def _check_mat(t: torch.Tensor, name: str) -> None:
@@ -229,11 +248,21 @@ def ozaki_available() -> bool:
     return bool(lib().gpb_ozaki_available())
 
 
+OZAKI_AUTO = -1
+
+
 def set_ozaki_slices(nslices: int) -> None:
-    """0: every blocked algorithm stays on the FP64 DMMA pipe; 5..8: the large rank-NB trailing updates of
-    ``lower_cholesky`` / the inverse run as exact int8 digit-plane products (``tcgen05.mma kind::i8``) with that many
-    planes.  Library default: 7 (``GPB_OZAKI`` in the environment overrides it at load time)."""
+    """Arithmetic of the large rank-NB trailing updates of ``lower_cholesky`` / the inverse (process-wide switch):
+    ``OZAKI_AUTO`` (-1, library default): exact int8 digit-plane products (``tcgen05.mma kind::i8``) whose plane count is chosen
+    on the device per call -- 8 planes (fp64-rounding-level) unless the hyper-parameters of a fused objective bound
+    cond(Sigma) by 1e7, then 7; 5..8: that many planes everywhere; 0: FP64 DMMA everywhere.
+    ``GPB_OZAKI`` in the environment sets the initial value."""
     lib().gpb_set_ozaki_slices(int(nslices))
+
+
+def ozaki_auto_planes(n: int, variance: float, obs_stddev: float, jitter: float) -> int:
+    """The plane count the device-side guard picks for a fused objective with these hyper-parameters (reporting only)."""
+    return int(lib().gpb_ozaki_auto_planes(int(n), float(variance), float(obs_stddev), float(jitter)))
 
 
 def get_ozaki_slices() -> int:
@@ -311,7 +340,7 @@ def _mll_forward_raw(st, kind, X, y, ell_v, iso, var, sn, mean, jitter):
                                _p(mean), float(jitter), _p(st.sigma), st.sigma.stride(0), _p(st.ws), st.nbytes,
                                _p(val), _p(alpha), _p(info))
     _abi.check(rc, "gpb_mll_forward")
-    st.generation += 1
+    st.generation = next_generation()
     return val, alpha, info
 
 
@@ -342,6 +371,7 @@ class ConjugateMllFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
+        _no_data_grad(ctx, (1, 2), "conjugate_mll")
         X, y, ell_v, var, sn, mean, alpha = ctx.saved_tensors
         N, D = X.shape
         st = _mll_state(N, D, X.device)

@@ -15,7 +15,7 @@ import torch
 
 from . import _abi
 from ._lib import lib
-from .ops import _check_mat, _ell_args, _kscalars, _p, _scalar, _stream, require_cuda
+from .ops import _check_mat, _ell_args, _kscalars, _no_data_grad, _p, _scalar, _stream, next_generation, require_cuda
 
 DEFAULT_BLOCK_ROWS = 32768
 
@@ -129,7 +129,7 @@ def _forward_raw(st, kind, X, y, Z, ell_v, iso, var, sn, mean, jitter, block_row
     rc = L.gpb_sgpr_finish(_stream(), kind, M, D, _p(Z), Z.stride(0), _p(ell_v), iso, _p(var), _p(sn), block_rows,
                            _p(st.ws), st.nbytes, _p(P), int(need_grad), _p(val), _p(info))
     _abi.check(rc, "gpb_sgpr_finish")
-    st.generation += 1
+    st.generation = next_generation()
     return val, info
 
 
@@ -162,6 +162,7 @@ class CollapsedElboFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
+        _no_data_grad(ctx, (1, 2), "collapsed_elbo")
         X, y, Z, ell_v, var, sn, mean = ctx.saved_tensors
         kind, iso, jitter, block_rows, group, has_mean, raw = ctx.cfg
         n_loc, D = X.shape

@@ -8,7 +8,7 @@ import torch
 
 from . import _abi
 from ._lib import lib
-from .ops import _check_mat, _ell_args, _kscalars, _p, _scalar, _stream, require_cuda
+from .ops import _check_mat, _ell_args, _kscalars, _no_data_grad, _p, _scalar, _stream, next_generation, require_cuda
 from .sgpr_ops import DEFAULT_BLOCK_ROWS, _all_reduce, _state, _stats, _use_raw_statistics
 
 
@@ -29,7 +29,7 @@ def _forward_raw(st, kind, X, y, Z, ell_v, iso, var, sn, mean, mu, W, ndata, jit
                            _p(W), W.stride(0), float(ndata), float(jitter), block_rows, _p(st.ws), st.nbytes, _p(P),
                            int(need_grad), _p(val), _p(info))
     _abi.check(rc, "gpb_svgp_finish")
-    st.generation += 1
+    st.generation = next_generation()
     return val
 
 
@@ -70,6 +70,7 @@ class SvgpElboFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
+        _no_data_grad(ctx, (1, 2), "elbo")
         X, y, Z, ell_v, var, sn, mean, mu, W = ctx.saved_tensors
         kind, iso, jitter, block_rows, group, has_mean, ndata, raw = ctx.cfg
         n_loc, D = X.shape

@@ -70,7 +70,7 @@ class CollapsedVariationalGaussian(AbstractVariationalGaussian):
         rc = L_.gpb_sgpr_stats(_stream(), kind, n_loc, M, D, _p(x), x.stride(0), _p(y), _p(z), z.stride(0), _p(ell_v), iso,
                                _p(var), _p(sn), _p(mean), float(self.jitter), block_rows, _p(st.ws), st.nbytes, _p(P))
         _abi.check(rc, "gpb_sgpr_stats")
-        st.generation += 1
+        st.generation = ops.next_generation()  # the workspace was overwritten: a pending backward must replay its forward
         _all_reduce(P, group)
         P = P.reshape(M + 2, M + 2)
         s = sn.reshape(()) ** 2

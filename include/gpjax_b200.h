@@ -124,13 +124,23 @@ int gpb_gemm(void* stream, int64_t M, int64_t N, int64_t K, double alpha, const 
  *   K        : multiple of 128, and nslices * K * 4096 < 2^31 (int32 headroom of the deepest order; GPB_ERR_UNSUPPORTED beyond --
  *              callers split K, as the SGPR statistics do for K = 65,536)
  * gpb_igemm_i8 exposes the raw integer product (C int32 = A B^T) for bit-exact testing.
- * gpb_set_ozaki_slices(s): s in {0, 5..8}; 0 keeps every blocked algorithm on the FP64 DMMA pipe, otherwise the rank-NB
- * trailing updates (>= 2048 output rows) of potrf / trtri / lauum run through gpb_ozaki_gemm with s digit planes, and the two
- * streamed products of gpb_sgpr_stats(_raw) / gpb_sgpr_grad_local (blocks of >= 2048 rows, M >= 256) with 8 planes.
- * Default: 7 (environment variable GPB_OZAKI overrides; 8 = fp64 rounding level, 0 = DMMA only). */
+ * gpb_set_ozaki_slices(s): s in {-1 (auto, default), 0, 5..8}; 0 keeps every blocked algorithm on the FP64 DMMA pipe, otherwise
+ * the rank-NB trailing updates (>= 2048 output rows) of potrf / trtri / lauum run through gpb_ozaki_gemm, and the two streamed
+ * products of gpb_sgpr_stats(_raw) / gpb_sgpr_grad_local (blocks of >= 2048 rows, M >= 256) with 8 planes.
+ * Plane count of the exact-GP updates in auto mode -- the conditioning guard -- is decided per call ON THE DEVICE (a one-thread
+ * kernel writes it into the workspace, the product kernels read it: no host synchronisation):
+ *   gpb_potrf_lower / gpb_potri_lower (a bare matrix, nothing known about it): 8 planes = fp64-rounding-level products;
+ *   gpb_mll_forward / gpb_mll_backward: 7 planes iff the hyper-parameters PROVE cond(Sigma) <= 1e7 through
+ *     cond(K + s I) <= (N variance + s) / s, s = obs_stddev^2 + jitter  (|k| <= variance), else 8.
+ * Measured against the CPU oracle (profiles/r02_cond_sweep_n8192.jsonl): 8 planes equal the FP64 path's own error at every
+ * conditioning; 7 planes carry ~5e-17 cond relative error in the gradient (<= 1e-9 under the guard; contract 1e-8).
+ * gpb_ozaki_auto_planes is the same rule evaluated on host values, for reporting and tests only.
+ * Environment variable GPB_OZAKI ("auto", 0, 5..8) sets the initial value of the switch; the switch is an atomic
+ * process-wide configuration word, not meant to change while calls are in flight. */
 int gpb_ozaki_available(void);
 void gpb_set_ozaki_slices(int nslices);
 int gpb_get_ozaki_slices(void);
+int gpb_ozaki_auto_planes(int64_t N, double variance, double obs_stddev, double jitter);
 int gpb_ozaki_slice(void* stream, int64_t rows, int64_t K, const double* X, int64_t ldx, int nslices, void* Q,
                     int64_t ldq, double* scale);
 int gpb_ozaki_gemm(void* stream, int64_t M, int64_t N, int64_t K, int nslices, const void* Qa, int64_t ldqa,

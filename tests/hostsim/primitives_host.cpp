@@ -5,6 +5,7 @@
 // tests/hostsim/libgpjax_b200_hostsim.so so the CPU test-suite can check the blocked-algorithm
 // orchestration (block indexing, masks, workspace carving, K-range hints) against the oracle
 // without a GPU.  It is never shipped, never loaded by gpjax_b200, and is not a fallback.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -536,7 +537,8 @@ int ozaki_gemm(stream_t, const OzakiGemmDesc& d) {
             if (d.mask == MASK_LOWER && d.mask_row0 + i < d.mask_col0 + j) continue;
             if (d.mask == MASK_BLOCK_STRICT_UPPER && !((d.mask_row0 + i) / d.mask_nb < (d.mask_col0 + j) / d.mask_nb)) continue;
             double acc = 0.0;
-            for (int t = 0; t < d.nslices; ++t) {
+            const int planes = d.nslices_dev ? std::min(std::max(d.nslices_dev[0], 1), d.nslices) : d.nslices;
+            for (int t = 0; t < planes; ++t) {
                 int64_t P = 0;
                 const int64_t ps = d.plane_stride > 0 ? d.plane_stride : d.K;
                 for (int p = 0; p <= t; ++p) {
@@ -564,6 +566,17 @@ int igemm_i8(stream_t, int64_t m, int64_t n, int64_t k, const int8_t* A, int64_t
     return GPB_OK;
 }
 bool ozaki_available() { return true; }
+int ozaki_auto_planes_host(int64_t N, double variance, double obs_stddev, double jitter) {
+    const double s = obs_stddev * obs_stddev + jitter;
+    return ((double)N * std::fabs(variance) + s) / s <= OZ_AUTO_COND_LIMIT ? 7 : 8;
+}
+int ozaki_choose_planes(stream_t, int requested, int64_t N, const double* variance, const double* obs_stddev, double jitter,
+                        int* planes_out) {
+    if (!planes_out || N < 0 || !(requested == OZ_AUTO || (requested >= 1 && requested <= 8))) return GPB_ERR_INVALID;
+    if (requested != OZ_AUTO) planes_out[0] = requested;
+    else planes_out[0] = (variance && obs_stddev) ? ozaki_auto_planes_host(N, variance[0], obs_stddev[0], jitter) : 8;
+    return GPB_OK;
+}
 }  // namespace gpb
 
 // measurement hooks are inert in the host model

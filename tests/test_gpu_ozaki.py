@@ -151,10 +151,12 @@ def test_conjugate_mll_value_and_gradient_on_the_int8_pipe_vs_oracle():
     assert abs(p[2].grad.item() - gref["obs_stddev"]) <= 1e-8 * abs(gref["obs_stddev"])
 
 
-@pytest.mark.parametrize("env", [{"GPB_OZ_KERNEL": "2"}, {"GPB_OZ_PAIR": "0"}, {"GPB_OZ_PAIR": "0", "GPB_OZ_KBS1": "1"}])
+@pytest.mark.parametrize("env", [{"GPB_OZ_KERNEL": "1"}, {"GPB_OZ_KERNEL": "2"}, {"GPB_OZ_PAIR": "0"},
+                                 {"GPB_OZ_KERNEL": "1", "GPB_OZ_PAIR": "0"}, {"GPB_OZ_KERNEL": "1", "GPB_OZ_PAIR": "0", "GPB_OZ_KBS1": "1"}])
 def test_alternative_kernel_schedules_agree(env):
-    """The measured-but-not-default schedules (plane-resident variant 2, unpaired orders, one K-block per stage) are
-    selected by environment variables read at first launch, so each runs in its own process."""
+    """The measured-but-not-default kernels (variant 1: one CTA per 128 x 128 tile, the round-1 default; variant 2:
+    plane-resident; unpaired orders; one K-block per stage) are selected by environment variables read at first launch, so each
+    runs in its own process.  The default is variant 3 (CTA pairs, cta_group::2), which every other test exercises."""
     import os
     import subprocess
     import sys

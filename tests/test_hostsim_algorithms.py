@@ -322,7 +322,7 @@ def test_potrf_with_int8_digit_plane_updates(lib, N, planes):
 
 def test_ozaki_switch_rejects_unsupported_plane_counts(lib):
     try:
-        for bad in (1, 4, 9, -3):
+        for bad in (1, 4, 9, -3):  # -1 is OZ_AUTO and valid
             lib.gpb_set_ozaki_slices(bad)
             assert lib.gpb_get_ozaki_slices() == 0
     finally:
@@ -380,6 +380,43 @@ def test_mll_value_and_gradient_with_int8_digit_plane_updates(lib, N):
     assert abs(gs - gr["obs_stddev"]) <= 1e-8 * max(abs(gr["obs_stddev"]), 1e-6 * abs(ref))
     assert abs(gc - gr["mean_const"]) <= 1e-8 * max(abs(gr["mean_const"]), 1e-6 * abs(ref))
     assert not np.array_equal(res[0][1], ge)  # the digit-plane model really ran in the backward pass
+
+
+def test_auto_mode_guard_picks_planes_from_the_hyperparameters(lib):
+    """OZ_AUTO (-1): the plane count of the int8 updates is written into the workspace by ozaki_choose_planes -- 8 for a bare
+    matrix (gpb_potrf_lower), 7 only while (N variance + s) / s <= 1e7, s = obs_stddev^2 + jitter, for the fused objective --
+    and the product kernels read it from there.  The host model's workspace is host memory, so the word can be inspected."""
+    N, D = 700, 3
+    X, y = data(N, D, N)
+    ell, c = np.linspace(0.8, 1.6, D), np.array([0.0])
+    assert lib.gpb_ozaki_auto_planes(50000, 1.0, 0.3, 1e-6) == 7       # the benchmark's hyper-parameters: bound 5.6e5
+    assert lib.gpb_ozaki_auto_planes(100000, 1.0, 0.3, 1e-6) == 7      # config 3: 1.1e6
+    assert lib.gpb_ozaki_auto_planes(8192, 1.0, 0.03, 1e-6) == 7       # 9.1e6
+    assert lib.gpb_ozaki_auto_planes(8192, 1.0, 0.003, 1e-6) == 8      # 8.2e8
+    assert lib.gpb_ozaki_auto_planes(50000, 1.0, 0.0, 0.0) == 8        # s = 0 -> inf -> 8
+    nbytes = lib.gpb_mll_workspace_bytes(N, D)
+    words = {}
+    try:
+        for tag, (var, sn, mode) in {"benign": (1.3, 0.4, -1), "ill": (1.3, 1e-3, -1), "forced5": (1.3, 0.4, 5)}.items():
+            lib.gpb_set_ozaki_slices(mode)
+            assert lib.gpb_get_ozaki_slices() == mode
+            ws = np.zeros(nbytes // 8 + 8)
+            Sig = np.full((N, N), np.nan)
+            val, alpha, info = np.zeros(1), np.zeros(N), np.zeros(1, np.int32)
+            assert lib.gpb_mll_forward(None, 0, N, D, p(X), D, p(y), p(ell), 0, p(np.array([var])), p(np.array([sn])), p(c), 1e-6,
+                                       p(Sig), N, p(ws), nbytes, p(val), p(alpha), p(info)) == 0
+            # the guard's word is the first int32 of the LAST 256-byte slot of the workspace (algorithms.cpp: off_ozp)
+            words[tag] = int(ws[: nbytes // 8].view(np.int32)[-64])
+            assert np.isfinite(val[0])
+        lib.gpb_set_ozaki_slices(-1)
+        S = o.gram("rbf", X, ell, 1.0) + 0.09 * np.eye(N)
+        nb2 = lib.gpb_factor_workspace_bytes(N, D, 0)
+        ws = np.zeros(nb2 // 8 + 8)
+        assert lib.gpb_potrf_lower(None, N, p(S), N, 1, p(ws), nb2, N, D, 0, p(np.zeros(1, np.int32))) == 0
+        words["bare"] = int(ws[: nb2 // 8].view(np.int32)[-64])
+    finally:
+        lib.gpb_set_ozaki_slices(0)
+    assert words == {"benign": 7, "ill": 8, "forced5": 5, "bare": 8}
 
 
 @pytest.mark.parametrize("raw", [False, True])
