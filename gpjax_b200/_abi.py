@@ -79,6 +79,11 @@ PROTOTYPES = {
         i32,
         [vp, i32, i64, i32, vp, i64, vp, i32, vp, vp, f64, i64, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64],
     ),
+    "gpb_nccl_version": (i32, []),
+    "gpb_nccl_unique_id": (i32, [vp]),
+    "gpb_nccl_comm_init_rank": (i32, [vp, i32, vp, i32]),
+    "gpb_nccl_comm_destroy": (i32, [vp]),
+    "gpb_allreduce_f64": (i32, [vp, vp, vp, i64]),
 }
 
 ERRORS = {

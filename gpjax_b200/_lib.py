@@ -42,3 +42,7 @@ def require_cuda(*tensors) -> None:
             )
         if t.dtype != torch.float64:
             raise TypeError(f"gpjax_b200 is float64-only (GPJax runs with x64); got {t.dtype}")
+        cur = torch.cuda.current_device()
+        if t.device.index != cur:  # launches go to the CURRENT device's stream: refuse instead of using the wrong one
+            raise RuntimeError(f"tensor lives on cuda:{t.device.index} but the current device is cuda:{cur}; wrap the call "
+                               "in `with torch.cuda.device(tensor.device):`")

@@ -21,7 +21,7 @@ OBJ_DIR = os.path.join(OUT_DIR, "obj")
 LIB_PATH = os.path.join(OUT_DIR, "libgpjax_b200.so")
 
 CU_SOURCES = ["gemm_f64.cu", "gram.cu", "potrf_leaf.cu", "level2.cu", "sgpr_kernels.cu", "svgp_kernels.cu", "ozaki_i8.cu", "profile.cu"]
-CPP_SOURCES = ["algorithms.cpp", "sgpr.cpp", "abi.cpp"]
+CPP_SOURCES = ["algorithms.cpp", "sgpr.cpp", "abi.cpp", "collective.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC"]
 if os.environ.get("GPB_NB"):  # experiment hook: block size of the blocked algorithms (default 1024, see algorithms.h)
@@ -84,7 +84,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [nvcc, *ARCH, "-shared", "-o", LIB_PATH, *objs, "-cudart", "static"]
+    cmd = [nvcc, *ARCH, "-shared", "-o", LIB_PATH, *objs, "-cudart", "static", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

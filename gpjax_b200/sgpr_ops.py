@@ -28,10 +28,53 @@ def _world(group) -> int:
     return 1
 
 
+# ---- exchange step: NCCL through the C ABI (gpb_allreduce_f64) when a native communicator exists, else torch.distributed ----
+_NATIVE_COMMS: dict = {}  # id(group) or None -> ncclComm_t (int)
+
+
+def init_native_collective(group=None) -> bool:
+    """Create an NCCL communicator for `group` through the C ABI (``gpb_nccl_unique_id`` / ``gpb_nccl_comm_init_rank``) so the two
+    all-reduces of the sharded path are issued by ``gpb_allreduce_f64`` on the launching stream -- the same call a non-torch
+    binding makes.  ``torch.distributed`` only ships the 128-byte unique id (rendezvous).  Returns False (and changes
+    nothing) when the process has no NCCL or a single rank."""
+    import ctypes
+
+    import torch.distributed as dist
+
+    L = lib()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2 or L.gpb_nccl_version() == 0:
+        return False
+    key = None if group is None else id(group)
+    if key in _NATIVE_COMMS:
+        return True
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    idbuf = (ctypes.c_char * 128)()
+    if rank == 0:
+        _abi.check(L.gpb_nccl_unique_id(idbuf), "gpb_nccl_unique_id")
+    box = [bytes(idbuf.raw) if rank == 0 else None]
+    src = 0 if group is None else dist.get_global_rank(group, 0)
+    dist.broadcast_object_list(box, src=src, group=group)
+    comm = ctypes.c_void_p()
+    _abi.check(L.gpb_nccl_comm_init_rank(ctypes.byref(comm), world, box[0], rank), "gpb_nccl_comm_init_rank")
+    _NATIVE_COMMS[key] = comm.value
+    return True
+
+
+def destroy_native_collectives() -> None:
+    for comm in _NATIVE_COMMS.values():
+        lib().gpb_nccl_comm_destroy(comm)
+    _NATIVE_COMMS.clear()
+
+
 def _all_reduce(t: torch.Tensor, group) -> None:
     import torch.distributed as dist
 
-    if _world(group) > 1:
+    if _world(group) <= 1:
+        return
+    comm = _NATIVE_COMMS.get(None if group is None else id(group))
+    if comm is not None and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous():
+        _abi.check(lib().gpb_allreduce_f64(comm, _stream(), t.data_ptr(), t.numel()), "gpb_allreduce_f64")
+    else:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
 
@@ -62,13 +105,34 @@ def release_buffers() -> None:
 
 # ---- which route to the statistics (csrc/sgpr.cpp: whiten-first vs raw products + one whitening at the end) ----------
 RAW_STATISTICS_COND_LIMIT = 1e3  # "auto": raw route only while cond(Kzz + jitter I) is estimated below this
-RAW_STATISTICS_RECHECK = 10      # "auto": the estimate (a few ms at M = 4096) is refreshed every this many evaluations
-_ROUTE_CACHE: dict = {}          # (device, kind, M, D) -> [evaluations until the next estimate, decision, fingerprint]
+RAW_STATISTICS_RECHECK = 10      # "auto": a new estimate is launched every this many evaluations
+_ROUTE_CACHE: dict = {}          # (device, kind, M, D, jitter) -> _RouteSlot
 
 
-def kzz_condition_estimate(kind, Z, ell, var, jitter, iters: int = 8) -> float:
-    """Estimate of cond_2(Kzz + jitter I): lambda_max by power iteration on the matrix, lambda_min by inverse iteration
-    through its Cholesky factor (a few GEMV / TRSV launches on the M x M matrix, one host read at the end)."""
+class _RouteSlot:
+    """Decision state of statistics="auto" for one problem shape.  The estimate is computed on the DEVICE and travels to a pinned
+    host word with a non-blocking copy; a forward only ever *polls* the copy's event, so the training loop never synchronises
+    with the host.  Until the first estimate has landed the reference's order ("whitened") is used."""
+
+    def __init__(self):
+        self.decision = False   # raw route allowed?
+        self.countdown = 0      # evaluations until the next estimate is launched
+        self.pending = None     # (event, pinned host tensor) of an estimate in flight
+        self.estimates = 0      # completed estimates (tests / reporting)
+        self.last = None        # last completed estimate (host float)
+
+    def harvest(self) -> None:
+        if self.pending is not None and self.pending[0].query():
+            est = float(self.pending[1][0])
+            self.last = est if est == est else float("inf")  # NaN (Kzz not positive definite) -> never the raw route
+            self.decision = self.last <= RAW_STATISTICS_COND_LIMIT
+            self.estimates += 1
+            self.pending = None
+
+
+def kzz_condition_estimate_device(kind, Z, ell, var, jitter, iters: int = 8) -> torch.Tensor:
+    """Estimate of cond_2(Kzz + jitter I) as a DEVICE scalar: lambda_max by power iteration on the matrix, lambda_min by
+    inverse iteration through its Cholesky factor (a few GEMV / TRSV launches on the M x M matrix; no host read)."""
     from . import ops
 
     M = Z.shape[0]
@@ -84,8 +148,13 @@ def kzz_condition_estimate(kind, Z, ell, var, jitter, iters: int = 8) -> float:
         v = ops.gemm(K, (v / v.norm()).reshape(1, -1).contiguous()).reshape(-1)                    # K v
         u = u / u.norm()
         u = ops.trsv_lower_(Lf, ops.trsv_lower_(Lf, u.contiguous(), ws, trans=False), ws, trans=True)  # K^-1 u
-    est = (v.norm() * u.norm()).item()
-    return est if est == est else float("inf")  # NaN (Kzz not positive definite) -> never take the raw route
+    return (v.norm() * u.norm()).reshape(1)
+
+
+def kzz_condition_estimate(kind, Z, ell, var, jitter, iters: int = 8) -> float:
+    """Host value of :func:`kzz_condition_estimate_device` (one host read: tests and bench reporting only)."""
+    est = kzz_condition_estimate_device(kind, Z, ell, var, jitter, iters).item()
+    return est if est == est else float("inf")
 
 
 def _use_raw_statistics(mode: str, kind, Z, ell_v, var, jitter) -> bool:
@@ -95,19 +164,29 @@ def _use_raw_statistics(mode: str, kind, Z, ell_v, var, jitter) -> bool:
         return True
     if mode != "auto":
         raise ValueError("statistics must be 'auto', 'whitened' or 'raw'")
-    # hyper-parameters move slowly between optimiser steps, and the limit leaves two orders of magnitude of margin
-    # to the stated tolerance, so the decision is reused for a few evaluations of the same problem shape
     key = (Z.device.index, kind, Z.shape[0], Z.shape[1], float(jitter))
-    zd = Z.detach()
-    fp = torch.stack([zd.sum(), zd.square().sum(), ell_v.detach().sum(), var.detach().sum()]).tolist()
     slot = _ROUTE_CACHE.get(key)
-    moved = slot is None or any(abs(a - b) > 0.02 * max(abs(a), abs(b), 1e-300) for a, b in zip(fp, slot[2]))
-    if moved or slot[0] <= 0:
-        slot = [RAW_STATISTICS_RECHECK,
-                kzz_condition_estimate(kind, Z, ell_v, var, jitter) <= RAW_STATISTICS_COND_LIMIT, fp]
-        _ROUTE_CACHE[key] = slot
-    slot[0] -= 1
-    return slot[1]
+    if slot is None:
+        slot = _ROUTE_CACHE[key] = _RouteSlot()
+    slot.harvest()
+    if slot.pending is None and slot.countdown <= 0:
+        # hyper-parameters move slowly between optimiser steps and the limit leaves two orders of magnitude of margin to the
+        # stated tolerance, so a decision that lags the parameters by a few evaluations is safe
+        with torch.no_grad():
+            est = kzz_condition_estimate_device(kind, Z.detach(), ell_v.detach(), var.detach(), jitter)
+            host = torch.empty(1, dtype=torch.float64, pin_memory=True)
+            host.copy_(est, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        slot.pending = (ev, host)
+        slot.countdown = RAW_STATISTICS_RECHECK
+    slot.countdown -= 1
+    return slot.decision
+
+
+def route_state(kind, Z, jitter):
+    """The `_RouteSlot` of a problem shape (tests / bench reporting), or None."""
+    return _ROUTE_CACHE.get((Z.device.index, kind, Z.shape[0], Z.shape[1], float(jitter)))
 
 
 def _stats(L, raw: bool):

@@ -9,7 +9,11 @@
  *     hyper-parameters (lengthscale[D] or [1], variance, obs_stddev, mean constant) so a training
  *     loop never synchronises with the host.
  *   - `stream` is a cudaStream_t.  Calls only enqueue work: no allocation, no synchronisation,
- *     no host read-back, no exceptions.  Re-entrant; no mutable global state.
+ *     no host read-back, no exceptions.  Re-entrant: one process may drive several devices from several
+ *     threads (XLA's per-device executors) -- everything a call mutates lives in the buffers it is handed;
+ *     library-internal launch state (kernel attributes, the look-ahead helper streams and their events) is kept
+ *     PER DEVICE behind a mutex, and the only process-wide words are the atomic configuration switches
+ *     (gpb_set_ozaki_slices, gpb_profile_reset), which are not meant to change while calls are in flight.
  *   - return value: 0 = OK, <0 = GPB_ERR_* (argument / capability / launch error).  Numerical
  *     failure (non-positive-definite pivot) is NOT an error code: outputs are NaN-filled and the
  *     device word `*info` receives the 1-based index of the first failing pivot, mirroring the
@@ -234,6 +238,20 @@ int gpb_svgp_grad_finish(void* stream, int kind, int64_t M, int D, const double*
                          const double* gout, const double* W, int64_t ldw, double* g_Z, double* g_lengthscale,
                          double* g_variance, double* g_obs_stddev, double* g_mean_const, double* g_mu, double* g_W,
                          int64_t ldgw);
+
+/* ---- exchange step of the row-sharded sparse path: all-reduce(sum) over NCCL --------------------------------------
+ * Steps 2 and 5 of the protocol above.  In the reference the sum over data rows is the contraction
+ * inside collapsed_elbo (gpjax/objectives.py:380-398); sharded over devices it becomes one all-reduce of Paug
+ * ((M+2)^2 doubles) and one of [g_Z | g_lengthscale | g_variance].  `comm` is an ncclComm_t of the NCCL loaded in the
+ * process (resolved at run time: the host framework's copy when one is mapped, else libnccl.so.2; GPB_ERR_UNSUPPORTED when
+ * there is none).  gpb_allreduce_f64 is in place and only enqueues on `stream`.  The three communicator helpers let a host
+ * without its own NCCL handle (the ctypes shim, a C++ trainer) build one: rank 0 calls gpb_nccl_unique_id, ships the 128
+ * bytes to the other ranks by any means, and every rank calls gpb_nccl_comm_init_rank with ITS device current. */
+int gpb_nccl_version(void); /* e.g. 22809; 0 = no NCCL in the process */
+int gpb_nccl_unique_id(void* id_out_128_bytes);
+int gpb_nccl_comm_init_rank(void** comm_out, int nranks, const void* id_128_bytes, int rank);
+int gpb_nccl_comm_destroy(void* comm);
+int gpb_allreduce_f64(void* comm, void* stream, double* buf, int64_t count);
 
 #ifdef __cplusplus
 }

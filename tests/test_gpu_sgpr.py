@@ -125,7 +125,14 @@ def test_condition_estimate_and_automatic_route_selection():
         est = sgpr_ops.kzz_condition_estimate(0, dev(Z), dev(ell), dev(1.2), 1e-6)
         assert true / 3.0 <= est <= true * 1.0001, (tag, true, est)  # power / inverse iteration approach from below
         sgpr_ops.release_buffers()  # drops the cached route decision of the previous problem
+        # "auto" never blocks on the host: the first evaluation launches the estimate and takes the reference's order; once the
+        # non-blocking copy of the estimate has landed (here: after a synchronize) the decision follows it
+        first = sgpr_ops._use_raw_statistics("auto", 0, dev(Z), dev(ell), dev(1.2), 1e-6)
+        assert first is False and sgpr_ops.route_state(0, dev(Z), 1e-6).pending is not None
+        torch.cuda.synchronize()
         picks[tag] = sgpr_ops._use_raw_statistics("auto", 0, dev(Z), dev(ell), dev(1.2), 1e-6)
+        slot = sgpr_ops.route_state(0, dev(Z), 1e-6)
+        assert slot.estimates == 1 and true / 3.0 <= slot.last <= true * 1.0001
         # whichever route "auto" takes, the result meets the (condition-scaled) tolerance of the default tests
         ref, gref = o.collapsed_elbo_value_and_grad_autodiff("rbf", X, y, Z, ell, 1.2, 0.5, 0.1)
         val, g = run_gpu(0, X, y, Z, ell, 1.2, 0.5, 0.1, 512, statistics="auto")
