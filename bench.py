@@ -63,6 +63,23 @@ def synth(n, d, seed):
     return X, y
 
 
+SYNTH_CHUNK = 65536
+
+
+def synth_rows(lo, hi, d, seed):
+    """Rows [lo, hi) of ONE global synthetic data set, independent of how the rows are sharded: chunk c (65,536 rows) is
+    drawn from its own PCG64 stream seeded (seed, c), so every world size sees the same N rows and the ELBO printed at
+    1 / 2 / 4 / 8 GPUs can be cross-checked."""
+    Xs, ys = [], []
+    for c in range(lo // SYNTH_CHUNK, (hi - 1) // SYNTH_CHUNK + 1):
+        rng = np.random.default_rng([seed, c])
+        X = rng.uniform(-2.0, 2.0, (SYNTH_CHUNK, d))
+        y = np.sin(X[:, :1]) + 0.1 * rng.standard_normal((SYNTH_CHUNK, 1))
+        a, b = max(lo, c * SYNTH_CHUNK) - c * SYNTH_CHUNK, min(hi, (c + 1) * SYNTH_CHUNK) - c * SYNTH_CHUNK
+        Xs.append(X[a:b]), ys.append(y[a:b])
+    return np.concatenate(Xs), np.concatenate(ys)
+
+
 HYPER = dict(variance=1.0, obs_stddev=0.3, mean_const=0.0, jitter=1e-6)
 
 
@@ -446,22 +463,26 @@ def bench_sgpr(D: Dist, args, steps=None, warmup=None):
 
     n_total, m, d = env_int("GPB_BENCH_SGPR_N", 10_000_000), env_int("GPB_BENCH_SGPR_M", 2048), 8
     block = env_int("GPB_BENCH_SGPR_BLOCK", 65536)
-    steps = steps or max(1, min(args.steps, 2))
-    warmup = warmup if warmup is not None else 1
+    steps = steps or max(5, args.steps)
+    warmup = warmup if warmup is not None else max(3, min(args.warmup, 3))
     lo, hi = D.rank * n_total // D.world, (D.rank + 1) * n_total // D.world
-    Xn, yn = synth(hi - lo, d, 4 + 1000 * D.rank)
+    Xn, yn = synth_rows(lo, hi, d, 4)  # rank-independent: the same N rows at every world size
     Xh, yh = torch.from_numpy(Xn).pin_memory(), torch.from_numpy(yn).pin_memory()
     X, y = Xh.to(D.dev), yh.to(D.dev)
     Zn = synth(m, d, 5)[0]
     mk = lambda v: torch.as_tensor(np.asarray(v, np.float64), device=D.dev).requires_grad_(True)
     Z, ell, var, sn, c = mk(Zn), mk(ell_ard(d)), mk(HYPER["variance"]), mk(HYPER["obs_stddev"]), mk(HYPER["mean_const"])
     params = (Z, ell, var, sn, c)
+    # exchange step through the C ABI (gpb_allreduce_f64 on the launching stream); torch.distributed only ships the unique id
+    native = sgpr_ops.init_native_collective() if (D.world > 1 and os.environ.get("GPB_NATIVE_NCCL", "1") != "0") else False
+    last = {}
 
     def step():
         for p in params:
             p.grad = None
         v = sgpr_ops.collapsed_elbo_fused(0, X, y, Z, ell, var, sn, c, HYPER["jitter"], block)
         v.backward()
+        last["v"] = v.detach()
 
     L = lib()
     for _ in range(warmup):
@@ -482,9 +503,13 @@ def bench_sgpr(D: Dist, args, steps=None, warmup=None):
     # "accumulate Kzx Kxz first" variant, counted at its own, smaller figure) + backward 2 N M^2 (dK_b = [K_b|d|1] Caug^T).
     # The reference formulation (TRSM + SYRK forward, statistics="whitened") is 4 M^2.
     cond_est = sgpr_ops.kzz_condition_estimate(0, Z.detach(), ell.detach(), var.detach(), HYPER["jitter"])
-    raw_route = cond_est <= sgpr_ops.RAW_STATISTICS_COND_LIMIT
+    slot = sgpr_ops.route_state(0, Z, HYPER["jitter"])
+    raw_route = bool(slot.decision) if slot is not None else False  # the route the timed steps actually took
     fpp = (3.0 if raw_route else 4.0) * m * m
     flops = fpp * (hi - lo)
+    elbo = float(last["v"].item())
+    phases = sgpr_ops.profile_phases(0, X, y, Z, ell, var, sn, c, HYPER["jitter"], block, None, raw_route)
+    phases = {k: (D.max_over_ranks(v) if k != "elbo" else v) for k, v in phases.items()}
     int8_route = oz_n.value > 0
     # with the int8 route both streamed products (statistics SYRK, pass-2 dK_b) leave the DMMA pipe; what remains on it are the
     # replicated M x M finishes and blocks below the row threshold
@@ -533,9 +558,10 @@ def bench_sgpr(D: Dist, args, steps=None, warmup=None):
         host_out["loss"] = loss.item()
         host_out["grads"] = [g.cpu() for g in grads]
 
-    t_e2e = timed(D, e2e_step, 1, 1)
-    e2e = {"value": n_total / t_e2e, "unit": "points/s", "h2d_bytes_per_step": int((hi - lo) * (d + 1) * 8),
-           "d2h_bytes_per_step": int(8 * (1 + m * d + d + 3)), "steps": 1,
+    e2e_steps = 2
+    t_e2e = timed(D, e2e_step, 1, e2e_steps)
+    e2e = {"value": n_total * e2e_steps / t_e2e, "unit": "points/s", "h2d_bytes_per_step": int((hi - lo) * (d + 1) * 8),
+           "d2h_bytes_per_step": int(8 * (1 + m * d + d + 3)), "steps": e2e_steps,
            "api": "gpx.objectives.collapsed_elbo(q, Dataset) + autograd, pinned host shard copied every step"}
     sgpr_ops.release_buffers()
     torch.cuda.empty_cache()
@@ -543,7 +569,12 @@ def bench_sgpr(D: Dist, args, steps=None, warmup=None):
                 steps=steps, warmup=warmup, ms_per_step=1e3 * t / steps, scaling="strong",
                 config={"workload": f"sgpr_collapsed_elbo_value_and_grad_N{n_total}_M{m}_D{d}_RBF_ARD",
                         "N": n_total, "M": m, "D": d, "block_rows": block, "rows_per_rank": hi - lo,
-                        "collective": "all-reduce (M+2)^2 fp64 fwd + (M*D+D+1) fp64 bwd, NCCL"},
+                        "data": "one global synthetic set (65,536-row chunks seeded (4, chunk)); identical rows at every world size",
+                        "collective": ("all-reduce (M+2)^2 fp64 fwd + (M*D+D+1) fp64 bwd: "
+                                       + ("gpb_allreduce_f64 (NCCL through the C ABI, launching stream)" if native
+                                          else "torch.distributed NCCL" if D.world > 1 else "none (1 rank)"))},
+                elbo=elbo, elbo_note="same data at every world size: the values at 1/2/4/8 GPUs must agree to ~1e-11 relative",
+                phases_ms_max_over_ranks={k: v for k, v in phases.items() if k != "elbo"}, elbo_from_phase_run=phases["elbo"],
                 roofline=roof, e2e=e2e, gpu_launches=int(all_n.value))
 
 

@@ -271,6 +271,59 @@ class CollapsedElboFunction(torch.autograd.Function):
                 g_mean.reshape(s_mean) if has_mean else None, None, None, None, None)
 
 
+def profile_phases(kind, X, y, Z, ell, variance, obs_stddev, mean_const=None, jitter=1e-6,
+                   block_rows: int = DEFAULT_BLOCK_ROWS, group=None, raw: bool = True) -> dict:
+    """One value+gradient evaluation with CUDA events between the six protocol steps (measurement only: bench.py reports where
+    the time of a sharded evaluation goes).  Returns milliseconds per phase on this rank and the ELBO."""
+    L = lib()
+    n_loc, D = X.shape
+    M = Z.shape[0]
+    y = y.reshape(-1).contiguous()
+    Z = Z.detach().contiguous()
+    ell_v, iso = _ell_args(ell.detach(), D)
+    var = _kscalars(kind, variance.detach())
+    sn = _scalar(obs_stddev.detach(), "obs_stddev")
+    mean = None if mean_const is None else _scalar(mean_const.detach(), "mean constant")
+    block_rows = int(min(block_rows, max(n_loc, 1)))
+    st = _state(M, D, block_rows, Z.device)
+    st.generation = next_generation()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+    P = torch.empty(L.gpb_sgpr_stats_count(M), dtype=torch.float64, device=Z.device)
+    val = torch.empty(1, dtype=torch.float64, device=Z.device)
+    info = torch.zeros(2, dtype=torch.int32, device=Z.device)
+    nl = 1 if iso else D
+    flat = torch.empty(M * D + nl + var.numel(), dtype=torch.float64, device=Z.device)
+    g_Z, g_ell, g_var = flat[: M * D], flat[M * D: M * D + nl], flat[M * D + nl:]
+    g_sn = torch.empty(1, dtype=torch.float64, device=Z.device)
+    g_mean = torch.empty(1, dtype=torch.float64, device=Z.device)
+    fn, name = _stats(L, raw)
+    ev[0].record()
+    _abi.check(fn(_stream(), kind, n_loc, M, D, _p(X), X.stride(0) if n_loc else D, _p(y), _p(Z), Z.stride(0), _p(ell_v), iso,
+                  _p(var), _p(sn), _p(mean), float(jitter), block_rows, _p(st.ws), st.nbytes, _p(P)), name)
+    ev[1].record()
+    _all_reduce(P, group)
+    ev[2].record()
+    _abi.check(L.gpb_sgpr_finish(_stream(), kind, M, D, _p(Z), Z.stride(0), _p(ell_v), iso, _p(var), _p(sn), block_rows,
+                                 _p(st.ws), st.nbytes, _p(P), 1, _p(val), _p(info)), "gpb_sgpr_finish")
+    ev[3].record()
+    _abi.check(L.gpb_sgpr_grad_local(_stream(), kind, n_loc, M, D, _p(X), X.stride(0) if n_loc else D, _p(y), _p(Z),
+                                     Z.stride(0), _p(ell_v), iso, _p(var), _p(sn), _p(mean), block_rows, _p(st.ws), st.nbytes,
+                                     _p(g_Z), _p(g_ell), _p(g_var)), "gpb_sgpr_grad_local")
+    ev[4].record()
+    _all_reduce(flat, group)
+    ev[5].record()
+    _abi.check(L.gpb_sgpr_grad_finish(_stream(), kind, M, D, _p(Z), Z.stride(0), _p(ell_v), iso, _p(var), _p(sn), block_rows,
+                                      _p(st.ws), st.nbytes, None, _p(g_Z), _p(g_ell), _p(g_var), _p(g_sn), _p(g_mean)),
+               "gpb_sgpr_grad_finish")
+    ev[6].record()
+    torch.cuda.synchronize()
+    names = ["pass1_statistics", "allreduce_statistics", "finish_replicated", "pass2_gradient", "allreduce_gradient",
+             "grad_finish_replicated"]
+    out = {nm: ev[i].elapsed_time(ev[i + 1]) for i, nm in enumerate(names)}
+    out["elbo"] = float(val.item())
+    return out
+
+
 def collapsed_elbo_fused(kind, X, y, Z, ell, variance, obs_stddev, mean_const=None, jitter=1e-6,
                          block_rows: int = DEFAULT_BLOCK_ROWS, group=None, statistics: str = "auto"):
     """ELBO of the collapsed (Titsias) bound for the rows held by this rank, all-reduced over `group`.

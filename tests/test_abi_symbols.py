@@ -75,6 +75,40 @@ def test_int8_kernel_is_tcgen05_with_tma_and_tmem(cuda_lib_path):
     assert any(idx[j + 3] - idx[j] == 3 for j in range(len(idx) - 3)), "no run of 4 consecutive UTCIMMA instructions"
 
 
+SHIM = os.path.join(ROOT, "gpjax_b200", "csrc", "xla_ffi_shim.cc")
+XLA_STUB = os.path.join(ROOT, "tests", "xla_stub")
+# entry points a jax.ffi binding of the hot path needs a handler for (queries, measurement hooks, raw int8 building blocks and
+# the NCCL helpers -- XLA owns its collectives: jax.lax.psum -- are host-side / not part of the reference-facing surface)
+SHIM_MUST_BIND = ["gpb_gram", "gpb_gram_bwd", "gpb_potrf_lower", "gpb_trsv_lower", "gpb_trsm_lower_left", "gpb_sum_log_diag",
+                  "gpb_potri_lower", "gpb_mll_forward", "gpb_mll_backward", "gpb_sgpr_stats", "gpb_sgpr_stats_raw",
+                  "gpb_sgpr_finish", "gpb_sgpr_grad_local", "gpb_sgpr_grad_finish", "gpb_svgp_finish", "gpb_svgp_grad_finish"]
+
+
+def _compile_shim(path):
+    return subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", XLA_STUB, "-I", "/usr/local/cuda/include", path],
+                          capture_output=True, text=True)
+
+
+def test_xla_ffi_shim_compiles_against_the_stub_and_binds_the_whole_path(tmp_path):
+    """jaxlib is not installable here, so the jax.ffi handlers are type-checked against a stand-in of xla/ffi/api/ffi.h whose
+    binder performs the real header's check (handler parameters == Bind() chain).  A deliberately wrong chain must fail."""
+    src = open(SHIM).read()
+    for fn in SHIM_MUST_BIND:
+        assert re.search(r"\b" + fn + r"\b", src), f"no handler forwards to {fn}"
+    assert src.count("XLA_FFI_DEFINE_HANDLER_SYMBOL(") >= 14
+    ok = _compile_shim(SHIM)
+    assert ok.returncode == 0, ok.stderr[-3000:]
+    # the in-place backward declares its residuals as results (aliased), never mutates a read-only operand
+    assert "ffi::Result<F64> sigma_out, ffi::Result<F64> ws_out" in src and "const_cast" not in src
+    broken = tmp_path / "broken_shim.cc"
+    bad = src.replace('#include "../../include/gpjax_b200.h"', f'#include "{HEADER}"')
+    bad = bad.replace("ffi::Ffi::Bind().Ctx<Stream>().Arg<F64>().Ret<F64>());", "ffi::Ffi::Bind().Ctx<Stream>().Arg<F64>().Arg<F64>().Ret<F64>());")
+    assert bad != src
+    broken.write_text(bad)
+    r = _compile_shim(str(broken))
+    assert r.returncode != 0 and "does not match its Ffi::Bind() chain" in r.stderr
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "gpjax_b200")
     for dirpath, _, files in os.walk(pkg):
