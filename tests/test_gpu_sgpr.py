@@ -154,3 +154,39 @@ def test_raw_route_error_grows_with_condition_number_as_documented():
     assert cond > 1e6
     assert abs(vw - ref) <= 1e-10 * abs(ref)
     assert abs(vr - ref) <= 100 * np.finfo(float).eps * np.sqrt(2500) * cond * abs(ref)
+
+
+def test_bench_route_auto_statistics_int8_block_65536_vs_oracle_fixture():
+    """The route bench.py times: statistics="auto" (raw products once the non-blocking condition estimate has landed), block
+    65,536, M = 2048, D = 8 -- statistics SYRK on the int8 pipe with the K = 65,536 split + column digit planes, pass 2 on the
+    int8 pipe -- on N = 131,072 rows against the CPU oracle's streamed closed form (committed fixture
+    tests/golden/sgpr_bench_route.npz, generated by tests/golden/make_sgpr_fixture.py).  Both the first evaluation (reference
+    order, "whitened") and the second (raw route) must meet 1e-8."""
+    import os
+    import sys
+
+    from gpjax_b200 import sgpr_ops
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    from make_sgpr_fixture import HYPER, make_inputs
+
+    fx = np.load(os.path.join(here, "golden", "sgpr_bench_route.npz"))
+    X, y, Z, ell = make_inputs()
+    assert float(X.sum()) == float(fx["x_checksum"]) and float(y.sum()) == float(fx["y_checksum"]) and float(Z.sum()) == float(fx["z_checksum"])
+    gref = dict(inducing_inputs=fx["g_inducing_inputs"], lengthscale=fx["g_lengthscale"], variance=float(fx["g_variance"]),
+                obs_stddev=float(fx["g_obs_stddev"]), mean_const=float(fx["g_mean_const"]))
+    ref, cond = float(fx["value"]), float(fx["cond_kzz"])
+    assert cond < sgpr_ops.RAW_STATISTICS_COND_LIMIT
+    sgpr_ops.release_buffers()
+    args = (0, X, y, Z, ell, HYPER["variance"], HYPER["obs_stddev"], HYPER["mean_const"], 65536, HYPER["jitter"])
+    v1, g1 = run_gpu(*args, statistics="auto")
+    torch.cuda.synchronize()
+    slot = sgpr_ops.route_state(0, dev(Z), HYPER["jitter"])
+    assert slot is not None and slot.decision is False  # evaluation 1 ran before any estimate existed: reference order
+    v2, g2 = run_gpu(*args, statistics="auto")
+    assert slot.decision is True and slot.estimates == 1 and cond / 3.0 <= slot.last <= cond * 1.0001
+    check(v1, g1, ref, gref)
+    check(v2, g2, ref, gref)
+    assert v1 != v2  # two different evaluation orders really ran
+    sgpr_ops.release_buffers()
