@@ -368,16 +368,16 @@ def bench_exact(D: Dist, args):
     L.gpb_profile_reset(0)
     value = D.world * args.steps / t
     flops_per_eval = float(n) ** 3  # N^3/3 potrf + 2N^3/3 potri
-    mode = int(L.gpb_get_ozaki_slices())  # -1: auto (device-side conditioning guard), 0: DMMA only, 5..8: forced
+    mode = int(L.gpb_get_ozaki_slices())  # -1: auto (device-side conditioning guard), 0: DMMA only, 4..7: forced
     planes = (int(L.gpb_ozaki_auto_planes(n, HYPER["variance"], HYPER["obs_stddev"], HYPER["jitter"])) if mode == -1 else mode)
     dmma = {"kernel": "gemm_f64_kernel (FP64 DMMA.8x8x4)", "launches_per_step": gemm_n.value / args.steps,
             "time_over_step_time": gemm_ms.value * 1e-3 / t}
     if planes and oz_n.value > 0:
         # Dominant kernel: ozaki_i8_kernel_cg2 (tcgen05.mma.cta_group::2.kind::i8).  `achieved` = algorithmic int8 operations of
         # its launches (live output entries x K x s(s+1)/2 digit pairs x 2) / summed launch durations (CUDA events on the
-        # launching stream).  The launcher counts with the 8 planes present in the digit buffers; the device-side guard used
-        # `planes` of them, hence the s(s+1)/72 factor.
-        oz_ops_used = oz_ops.value * (planes * (planes + 1) / 2) / 36.0
+        # launching stream).  The launcher counts with the 7 planes present in the digit buffers; the device-side guard used
+        # `planes` of them, hence the s(s+1)/56 factor.
+        oz_ops_used = oz_ops.value * (planes * (planes + 1) / 2) / 28.0
         achieved = oz_ops_used / (oz_ms.value * 1e-3) / 1e12
         # MEASURED_PEAKS.json has no int8 entry: the ceiling is measured live in this process (cuBLASLt IGEMM, torch._int_mm):
         # `peak` = the SUSTAINED figure (the kernel is timed inside a seconds-long step under the 1 kW cap), burst alongside.
@@ -518,7 +518,7 @@ def bench_sgpr(D: Dist, args, steps=None, warmup=None):
         peak8 = 2.0 * float(mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops") or 1414.5)
         a8 = oz_ops.value / (oz_ms.value * 1e-3) / 1e12
         roof = {"bound": "tensor",
-                "kernel": "ozaki_i8_kernel (tcgen05.mma kind::i8, 8 digit planes): K_b^T K_b statistics + dK_b = [K_b|d|1] Caug^T",
+                "kernel": "ozaki_i8_kernel (tcgen05.mma kind::i8, 7 radix-256 digit planes): K_b^T K_b statistics + dK_b = [K_b|d|1] Caug^T",
                 "achieved": a8, "peak": peak8, "unit": "TFLOP/s", "frac": a8 / peak8,
                 "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (no int8 entry); unit is int8 Top/s (2 x MAC)",
                 "int8_ops_per_point": oz_ops.value / steps / (hi - lo), "time_over_step_time": oz_ms.value * 1e-3 / t,
@@ -624,11 +624,11 @@ def bench_svgp(D: Dist, args):
     cond_est = sgpr_ops.kzz_condition_estimate(1, Z.detach(), ell.detach(), var.detach(), HYPER["jitter"])
     raw_route = cond_est <= sgpr_ops.RAW_STATISTICS_COND_LIMIT
     flops = (3.0 if raw_route else 4.0) * batch * m * m + 22.0 * m**3
-    if oz_n.value > 0:  # streamed products on the int8 pipe (8 digit planes); the M x M finish stays on DMMA
+    if oz_n.value > 0:  # streamed products on the int8 pipe (7 radix-256 digit planes); the M x M finish stays on DMMA
         mp = measured_peaks() or {}
         peak8 = 2.0 * float(mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops") or 1414.5)
         a8 = oz_ops.value / (oz_ms.value * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "ozaki_i8_kernel (tcgen05.mma kind::i8, 8 digit planes)", "achieved": a8, "peak": peak8,
+        roof = {"bound": "tensor", "kernel": "ozaki_i8_kernel (tcgen05.mma kind::i8, 7 radix-256 digit planes)", "achieved": a8, "peak": peak8,
                 "unit": "TFLOP/s", "frac": a8 / peak8,
                 "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (no int8 entry); unit is int8 Top/s",
                 "time_over_step_time": oz_ms.value * 1e-3 / t, "algorithmic_flop_per_step": flops,

@@ -33,7 +33,7 @@ namespace gpb {
 namespace {
 constexpr int OZ_UNSET = -100;
 std::atomic<int> g_oz_slices{OZ_UNSET};
-int clamp_slices(int v) { return (v == OZ_AUTO || (v >= 5 && v <= OZ_MAX_SLICES)) ? v : 0; }
+int clamp_slices(int v) { return (v == OZ_AUTO || (v >= OZ_MIN_SLICES && v <= OZ_MAX_SLICES)) ? v : 0; }
 }  // namespace
 void set_ozaki_slices(int nslices) { g_oz_slices.store(clamp_slices(nslices), std::memory_order_relaxed); }
 int get_ozaki_slices() {
@@ -84,7 +84,7 @@ WsLayout ws_layout(int64_t N, int D, int with_potri) {
     L.off_scal = take(16);
     L.partials_count = with_potri ? mll_bwd_partials_count(N, D > 0 ? D : 1, NB) : 0;
     L.off_part = take(L.partials_count);
-    // Ozaki digit buffers: OZ_MAX_SLICES * NB bytes per row == NB doubles per row (OZ_MAX_SLICES == 8)
+    // Ozaki digit buffers: OZ_MAX_SLICES * NB bytes per row (NB is a multiple of 8)
     L.with_oz = N >= OZ_MIN_ROWS + NB;
     const int64_t qd = L.with_oz ? align_up(N, NB) * (OZ_MAX_SLICES * NB / 8) : 0;
     L.off_ozq = take(qd);
@@ -204,8 +204,8 @@ static int potrf_panel(stream_t s, int64_t N, double* A, int64_t lda, const Fact
     GPB_TRY(gemm(s, g));
     GPB_TRY(copy2d(s, rows, nbk, panel, NB, P, lda));
     // Ozaki path: digit planes of the panel, extracted on the stream that produced it (the side stream under lookahead)
-    if (nbk == NB && oz_on(ws, rows))  // all OZ_MAX_SLICES planes are extracted; the product uses ws.oz_planes[0] of them
-        GPB_TRY(ozaki_slice(s, rows, NB, NB, panel, NB, OZ_MAX_SLICES, oz_q, OZ_MAX_SLICES * NB, oz_scale));
+    if (nbk == NB && oz_on(ws, rows))  // ws.oz_planes[0] planes are extracted (rounded at the last one) and used by the product
+        GPB_TRY(ozaki_slice(s, rows, NB, NB, panel, NB, OZ_MAX_SLICES, oz_q, OZ_MAX_SLICES * NB, oz_scale, ws.oz_planes));
     return GPB_OK;
 }
 
@@ -386,8 +386,8 @@ int trtri_into_upper(stream_t s, int64_t N, double* A, int64_t lda, const Factor
             if (oz_on(ws, j0)) {  // digit planes indexed by GLOBAL row: W rows [0, j0), L rows [j0 + nbk, N)
                 const int planes = OZ_MAX_SLICES;
                 const int64_t ldq = OZ_MAX_SLICES * NB;
-                GPB_TRY(ozaki_slice(s, j0, NB, NB, Wp, NB, planes, ws.oz_q, ldq, ws.oz_scale));
-                GPB_TRY(ozaki_slice(s, right, NB, NB, Lp, lda, planes, ws.oz_q + (j0 + nbk) * ldq, ldq, ws.oz_scale + j0 + nbk));
+                GPB_TRY(ozaki_slice(s, j0, NB, NB, Wp, NB, planes, ws.oz_q, ldq, ws.oz_scale, ws.oz_planes));
+                GPB_TRY(ozaki_slice(s, right, NB, NB, Lp, lda, planes, ws.oz_q + (j0 + nbk) * ldq, ldq, ws.oz_scale + j0 + nbk, ws.oz_planes));
                 OzakiGemmDesc u;
                 u.M = j0; u.N = right; u.K = NB; u.nslices = planes; u.nslices_dev = ws.oz_planes;
                 u.Qa = ws.oz_q; u.ldqa = ldq; u.sa = ws.oz_scale;
@@ -420,16 +420,21 @@ int lauum_upper(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& w
         const double* DTk = ws.DinvT + k * NB * NB;
         double* P = A + j0;  // W[0:j0, k], row stride lda
         if (j0 > 0) {
-            // S[0:j0, 0:j0] (strictly-upper blocks) += P P^T
+            // S[0:j0, 0:j0] (strictly-upper blocks) += P P^T   and   Sdiag[j] += P_j P_j^T, j < k
+            bool diag_done = false;
             if (oz_on(ws, j0)) {  // a ragged last block (nbk < NB) is zero-padded to the next multiple of 128 digits
                 const int planes = OZ_MAX_SLICES;
                 const int64_t ldq = OZ_MAX_SLICES * NB;
                 const int64_t kp = align_up(nbk, 128);
-                GPB_TRY(ozaki_slice(s, j0, nbk, kp, P, lda, planes, ws.oz_q, ldq, ws.oz_scale));
+                GPB_TRY(ozaki_slice(s, j0, nbk, kp, P, lda, planes, ws.oz_q, ldq, ws.oz_scale, ws.oz_planes));
                 OzakiGemmDesc g;
                 g.M = j0; g.N = j0; g.K = kp; g.nslices = planes; g.nslices_dev = ws.oz_planes;
                 g.Qa = ws.oz_q; g.ldqa = ldq; g.sa = ws.oz_scale; g.Qb = ws.oz_q; g.ldqb = ldq; g.sb = ws.oz_scale;
                 g.C = A; g.ldc = lda; g.alpha = 1.0; g.mask = MASK_BLOCK_STRICT_UPPER; g.mask_nb = NB;
+                if (ozaki_supports_extensions()) {  // the same launch also accumulates the diagonal blocks (into ws.Sdiag)
+                    g.mask = MASK_BLOCK_UPPER_DIAG_TO_C2; g.C2 = ws.Sdiag;
+                    diag_done = true;
+                }
                 GPB_TRY(ozaki_gemm(s, g));
             } else {
                 GemmDesc g;
@@ -438,12 +443,13 @@ int lauum_upper(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& w
                 g.beta = 1.0; g.mask = MASK_BLOCK_STRICT_UPPER; g.mask_nb = NB;
                 GPB_TRY(gemm(s, g));
             }
-            // diagonal blocks: Sdiag[j] += P_j P_j^T, j < k   (batched)
-            GemmDesc b;
-            b.M = NB; b.N = NB; b.K = nbk;
-            b.A = P; b.lda = lda; b.B = P; b.ldb = lda; b.C = ws.Sdiag; b.ldc = NB;
-            b.beta = 1.0; b.batch = (int)k; b.strideA = NB * lda; b.strideB = NB * lda; b.strideC = NB * NB;
-            GPB_TRY(gemm(s, b));
+            if (!diag_done) {  // diagonal blocks on the DMMA pipe (batched)
+                GemmDesc b;
+                b.M = NB; b.N = NB; b.K = nbk;
+                b.A = P; b.lda = lda; b.B = P; b.ldb = lda; b.C = ws.Sdiag; b.ldc = NB;
+                b.beta = 1.0; b.batch = (int)k; b.strideA = NB * lda; b.strideB = NB * lda; b.strideC = NB * NB;
+                GPB_TRY(gemm(s, b));
+            }
             // S[0:j0, k] = W[0:j0,k] * inv(L_kk)          (B operand = DinvT_k, upper triangular)
             GemmDesc c;
             c.M = j0; c.N = nbk; c.K = nbk;

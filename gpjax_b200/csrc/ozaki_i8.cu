@@ -3,21 +3,23 @@
 // Why: every O(N^3) flop of the exact-GP path (reference call site: jnp.linalg.cholesky, gpjax/linalg/operations.py:54-55,
 // and the reverse-mode solve it implies) is a rank-NB update C += alpha * A B^T.  The FP64 tensor instruction of sm_100a
 // (DMMA.8x8x4) peaks at 37 TFLOP/s; the int8 tcgen05 pipe of the same chip is ~100x wider.  Splitting every fp64 operand
-// row into `s` signed 7-bit digits after an exact power-of-two row scaling,
-//      x_ik = 2^e_i * sum_p q^(p)_ik * 2^(-7 (p+1)),      |q| <= 64,
+// row into `s` balanced radix-256 digits (the FULL int8 range, 8 bits per plane) after an exact power-of-two row scaling,
+//      x_ik = 2^e_i * sum_p q^(p)_ik * 2^(-8 (p+1)),      -128 <= q <= 127,
 // makes every digit-pair product an EXACT integer GEMM (int8 x int8 -> int32), and the fp64 result is recovered as
-//      (A B^T)_ij ~= 2^(ea_i + eb_j) * sum_{t < s} 2^(-7 (t+2)) * sum_{p+q = t} (Q_a^(p) Q_b^(q)^T)_ij .
+//      (A B^T)_ij ~= 2^(ea_i + eb_j) * sum_{t < s} 2^(-8 (t+2)) * sum_{p+q = t} (Q_a^(p) Q_b^(q)^T)_ij .
 // All pairs of equal order t share one scale, so they are accumulated inside ONE int32 TMEM accumulator (|sum| <=
-// (t+1) k 64^2 < 2^31 for k <= 2^15), i.e. s accumulator passes per output tile instead of s (s+1) / 2 separate GEMMs.
-// The truncation error is bounded by the dropped orders: <= (s+1) 2^(-7 s) |a_i|_inf |b_j|_inf k  (s = 7: 2^-46 per entry
-// relative to the row maxima -- measured against the DMMA product in tests/test_gpu_ozaki.py and DESIGN section 12).
+// (t+1) k 128^2 < 2^31 for s k < 2^17), i.e. s accumulator passes per output tile instead of s (s+1) / 2 separate GEMMs.
+// The truncation error is bounded by the dropped orders: <= (s+1) 2^(-8 s - 2) 2^(ea_i + eb_j) k  (s = 6: 2^-47 per entry
+// relative to the row maxima, s = 7: 2^-55 -- measured against the DMMA product in tests/test_gpu_ozaki.py and DESIGN
+// section 12).  Round 1 used 7-bit digits (|q| <= 64): the same accuracy took one plane more, i.e. 28 instead of 22 (36
+// instead of 28) digit-pair products.  An EVEN plane count also keeps the equal-plane pair (s/2, s/2) of order s: oz_has_diag.
 //
 // Kernel (persistent, one CTA per SM, 12 warps, warp-specialised; role loops are warp-uniform, elect.sync picks the issuing lane):
 //   warp 0      TMA producer: cp.async.bulk.tensor.2d of 128 x 128-byte digit tiles (SWIZZLE_128B) into a ring of (A, B) slots
 //   warp 1      MMA issuer  : tcgen05.mma.cta_group::1.kind::i8 (M=128, N=128, K=32 per instruction),
 //                             tcgen05.commit releases ring slots / publishes accumulators through mbarriers
 //   warp 2      TMEM allocator (512 columns = 4 accumulator stages of 128 x 128 int32)
-//   warps 4-11  epilogue    : tcgen05.ld the int32 accumulator of order t, convert exactly to fp64, scale by 2^(-7 (t+2)) and
+//   warps 4-11  epilogue    : tcgen05.ld the int32 accumulator of order t, convert exactly to fp64, scale by 2^(-8 (t+2)) and
 //                             add into per-thread fp64 registers (64 per thread) while the MMA warp already works on
 //                             the next orders; after the last order: C (+)= alpha 2^(ea_i + eb_j) * acc, masked, ONE
 //                             read-modify-write of the fp64 tile in HBM.
@@ -50,14 +52,18 @@ constexpr int OZ_THREADS = 384;
 constexpr int OZ_EPI_WARP0 = 4, OZ_EPI_WARPS = 8;
 constexpr int OZ_CHUNK_TILES = 32;  // output tile columns walked together so their B digits stay L2-resident
 constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int OZ_BETA = 7;
+constexpr int OZ_BETA = OZ_DIGIT_BITS;  // 8: radix-256 digits
 
 struct OzParams {
     int m, n;             // output extents
     int kblocks;          // k / 128 per digit plane
     int nslices;          // digit planes used (1 in raw mode)
-    int mask;             // 0 none; 1 lower: (row0+i) >= (col0+j); 2 block-strict-upper: (row0+i)/mask_nb < (col0+j)/mask_nb
+    int mask;             // 0 none; 1 lower: (row0+i) >= (col0+j); 2 block-strict-upper: (row0+i)/mask_nb < (col0+j)/mask_nb;
+                          // 3 block-upper: blocks with row block <= column block are live, and the DIAGONAL blocks go to C2 (v3 only)
     long long row0, col0, mask_nb;
+    double* C2;           // mask 3: diagonal block b is the dense mask_nb x mask_nb matrix at C2 + b * mask_nb^2 (row stride mask_nb)
+    int krange;           // v3 only: structural zeros of a triangular operand are never multiplied (same meaning as GemmDesc::krange)
+    long long kr_off;
     double* C;            // fp64 in/out (MODE 1)
     long long ldc;
     int* Ci;              // int32 out (MODE 0)
@@ -75,6 +81,7 @@ struct OzParams {
     int bn;               // output tile width of the launched kernel variant (128: v1 / v3, 64: v2)
     int bm;               // output tile height the walk enumerates (128: v1 / v2; 256: v3, one tile per CTA pair)
     const int* planes_dev;  // optional device word overriding nslices (1..nslices): the conditioning guard, read in-kernel
+    int max_ctas;         // > 0: launch at most this many CTAs (SMs left free for a concurrent look-ahead chain)
 };
 // planes actually used by this launch (uniform across the grid: every role of every CTA reads the same word)
 __device__ __forceinline__ int oz_groups(const OzParams& p, int mode) {
@@ -82,6 +89,34 @@ __device__ __forceinline__ int oz_groups(const OzParams& p, int mode) {
     if (!p.planes_dev) return p.nslices;
     const int v = __ldg(p.planes_dev);
     return v < 1 ? 1 : (v > p.nslices ? p.nslices : v);
+}
+
+// Even plane count s: the truncation set {p + q < s} would drop the pair (s/2, s/2), the product of two digits of EQUAL weight.
+// In the rank-k updates of a factorisation the k-th entries of two panel rows have similar magnitude (column k of the panel has a
+// characteristic scale), so their LEADING digits sit in the same plane and that pair is not noise: for a positive-definite update it
+// is a coherent, same-signed term of relative size 2^(-8 s) per entry that adds up over K and over the block steps (measured:
+// 14x the residual of the factor, 40x the MLL gradient error at cond 3e6: profiles/r02_radix256.md).  One extra product of
+// order s restores the error level of an odd count; all other dropped pairs multiply a leading digit by a trailing (sign-random) one.
+__device__ __host__ __forceinline__ bool oz_has_diag(int groups) { return groups >= 2 && (groups & 1) == 0; }
+
+// K-blocks [kb0, kb1) a tile has to visit: the structural zeros of a triangular operand are skipped (v3).  All roles call this
+// with the same arguments, so producer, issuer and epilogue stay in lock step.  n0 / m0: first column / row of the tile.
+__device__ __forceinline__ void oz_krange(const OzParams& p, long long m0, long long n0, int bm, int& kb0, int& kb1) {
+    kb0 = 0;
+    kb1 = p.kblocks;
+    if (p.krange == KR_B_LOWER) {         // B(n,k) == 0 for k > n + off
+        long long e = (n0 + OZ_BN - 1 + p.kr_off) / OZ_BK + 1;
+        kb1 = e < 1 ? 1 : (e < p.kblocks ? (int)e : p.kblocks);
+    } else if (p.krange == KR_B_UPPER) {  // B(n,k) == 0 for k < n + off
+        long long b = (n0 + p.kr_off) / OZ_BK;
+        kb0 = b < 0 ? 0 : (b < p.kblocks ? (int)b : p.kblocks - 1);
+    } else if (p.krange == KR_A_LOWER) {  // A(m,k) == 0 for k > m + off
+        long long e = (m0 + bm - 1 + p.kr_off) / OZ_BK + 1;
+        kb1 = e < 1 ? 1 : (e < p.kblocks ? (int)e : p.kblocks);
+    } else if (p.krange == KR_A_UPPER) {  // A(m,k) == 0 for k < m + off
+        long long b = (m0 + p.kr_off) / OZ_BK;
+        kb0 = b < 0 ? 0 : (b < p.kblocks ? (int)b : p.kblocks - 1);
+    }
 }
 
 // ---- tile enumeration shared by the three roles: column chunks -> tile rows -> tile columns, dead tiles of the lower
@@ -98,9 +133,10 @@ struct TileWalk {
         return e < p.ntn ? (int)e : p.ntn;
     }
     __device__ int live_begin(const OzParams& p, int tm_) const {  // first live tile column of tile row tm_
-        if (p.mask != 2) return 0;
+        if (p.mask != 2 && p.mask != 3) return 0;
         long long rb = (p.row0 + (long long)tm_ * p.bm) / p.mask_nb;     // block of the tile's FIRST row (smallest)
-        long long need = (rb + 1) * p.mask_nb - (p.bn - 1) - p.col0;     // col0 + tn*BN + BN-1 >= (rb+1)*nb
+        // mask 2: col0 + tn*BN + BN-1 >= (rb+1)*nb;  mask 3 (diagonal blocks live too): ... >= rb*nb
+        long long need = (rb + (p.mask == 2 ? 1 : 0)) * p.mask_nb - (p.bn - 1) - p.col0;
         if (need <= 0) return 0;
         long long b = (need + p.bn - 1) / p.bn;
         return b < p.ntn ? (int)b : p.ntn;
@@ -200,6 +236,17 @@ __device__ __forceinline__ void tc_ld32(unsigned taddr, unsigned (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_ld16(unsigned taddr, unsigned (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+
 // K-major operand tile in shared memory: rows of 128 bytes, 8-row groups 1024 bytes apart, 128-byte swizzle
 // (what TMA SWIZZLE_128B writes for a {128 B, rows} box into a 1024-byte aligned buffer).
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(unsigned saddr) {
@@ -218,7 +265,7 @@ __device__ __forceinline__ double exact_i2d(int v) {  // exact int32 -> fp64 on 
     return __hiloint2double(0x43300000, (int)((unsigned)v ^ 0x80000000u)) - 4503601774854144.0;  // 2^52 + 2^31
 }
 
-// MODE 0: Ci = A B^T (raw int32, test / building block); MODE 1: C += alpha * 2^(ea+eb) * sum_t 2^(-7(t+2)) P_t
+// MODE 0: Ci = A B^T (raw int32, test / building block); MODE 1: C += alpha * 2^(ea+eb) * sum_t 2^(-8(t+2)) P_t
 template <int MODE>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const OzParams p) {
@@ -405,7 +452,7 @@ ozaki_i8_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             for (int t = 0; t < groups; ++t) {
                 mbar_wait_bounded(&tfull[acc], aphase);
                 tc_fence_after();
-                const double sc = __hiloint2double((1023 - OZ_BETA * (t + 2)) << 20, 0);  // 2^(-7 (t+2))
+                const double sc = __hiloint2double((1023 - OZ_BETA * (t + 2)) << 20, 0);  // 2^(-8 (t+2))
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     unsigned r[32];
@@ -615,7 +662,7 @@ ozaki_i8_kernel_v2(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 unsigned r[32];
                 tc_ld32(tmem_base + ((unsigned)(q4 * 32) << 16) + (unsigned)(t * O2_BN + h * 32), r);
                 if (MODE == 1) {
-                    const double sc = __hiloint2double((1023 - OZ_BETA * (t + 2)) << 20, 0);  // 2^(-7 (t+2))
+                    const double sc = __hiloint2double((1023 - OZ_BETA * (t + 2)) << 20, 0);  // 2^(-8 (t+2))
 #pragma unroll
                     for (int j = 0; j < 32; ++j) accd[j] = fma(exact_i2d((int)r[j]), sc, accd[j]);
                 } else if (row < p.m) {
@@ -720,6 +767,36 @@ __device__ __forceinline__ void tc_mma_i8_cg2(unsigned tmem_d, uint64_t adesc, u
         : "memory");
 }
 
+// fp64 write-out of one thread's 64 running sums (row `row`, tile columns [col0, col0 + 64)): C (+)= alpha 2^(ea+eb) acc, masked
+__device__ __forceinline__ void oz_store_row(const OzParams& p, const double (&accd)[64], int row, int col0) {
+    const double sr = p.alpha * __ldg(p.sa + row);
+    const long long grow = p.row0 + row;
+    double* crow = p.C + (long long)row * p.ldc;  // indexed by the local column
+    long long cshift = 0;
+    bool diag_blk = false;
+    if (p.mask == 3) {  // a 64-column slab lies inside one column block (mask_nb is a multiple of 128)
+        const long long rb = grow / p.mask_nb, cb = (p.col0 + col0) / p.mask_nb;
+        diag_blk = rb == cb;
+        if (diag_blk) {  // dense diagonal block rb of C2, addressed by (row, column) inside the block
+            crow = p.C2 + rb * p.mask_nb * p.mask_nb + (grow - rb * p.mask_nb) * p.mask_nb;
+            cshift = p.col0 - cb * p.mask_nb;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        const int col = col0 + j;
+        bool live = col < p.n;
+        if (p.mask == 1) live = live && (grow >= p.col0 + col);
+        else if (p.mask == 2) live = live && (grow / p.mask_nb < (p.col0 + col) / p.mask_nb);
+        else if (p.mask == 3) live = live && (diag_blk || grow / p.mask_nb < (p.col0 + col) / p.mask_nb);
+        if (live) {
+            const double v = accd[j] * (sr * __ldg(p.sb + col));
+            double* dst = crow + col + cshift;
+            *dst = p.beta0 ? v : *dst + v;
+        }
+    }
+}
+
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1)
 ozaki_i8_kernel_cg2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const OzParams p) {
@@ -764,12 +841,14 @@ ozaki_i8_kernel_cg2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int tm, tn;
             for (long long idx = pair; w.seek(p, idx, tm, tn); idx += npairs) {
                 const int m0 = tm * C2_BM + (int)rank * OZ_BM, n0 = tn * OZ_BN + (int)rank * C2_BNH;
+                int kb0, kb1;
+                oz_krange(p, (long long)tm * C2_BM, (long long)tn * OZ_BN, C2_BM, kb0, kb1);
                 for (int t = 0; t < groups;) {
                     const bool paired = p.pair && ((groups - t) & 1) == 0;  // odd plane count: order 0 runs unpaired
                     // paired: slot i of a K-block holds (A_i, B_{t+1-i}), i = 0..t+1; unpaired: (A_pa, B_{t-pa}), pa = 0..t
                     const int nsl = paired ? t + 2 : t + 1;
                     const int bsum = paired ? t + 1 : t;
-                    for (int kb = 0; kb < p.kblocks; ++kb) {
+                    for (int kb = kb0; kb < kb1; ++kb) {
                         for (int i = 0; i < nsl; ++i) {
                             mbar_wait_bounded(&empty[stage], phase ^ 1u);
                             uint8_t* sA = smem + stage * C2_SLOT_BYTES;
@@ -789,6 +868,25 @@ ozaki_i8_kernel_cg2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     }
                     t += paired ? 2 : 1;
                 }
+                if (oz_has_diag(groups)) {  // even plane count: the equal-plane product A_h B_h^T of order `groups`
+                    const int hp = groups >> 1;
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait_bounded(&empty[stage], phase ^ 1u);
+                        uint8_t* sA = smem + stage * C2_SLOT_BYTES;
+                        if (elect_one()) {
+                            if (p.noload) {
+                                if (rank == 0) mbar_arrive(&full[stage]);
+                            } else {
+                                if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * C2_SLOT_BYTES);
+                                const unsigned fb = mapa_u32(&full[stage], 0);
+                                tma_load_2d_cg2(sA, &tmA, fb, hp * p.pstride + kb * OZ_BK, m0);
+                                tma_load_2d_cg2(sA + C2_A_BYTES, &tmB, fb, hp * p.pstride + kb * OZ_BK, n0);
+                            }
+                        }
+                        __syncwarp();
+                        if (++stage == C2_RING) { stage = 0; phase ^= 1u; }
+                    }
+                }
             }
         }
     } else if (warp == 1) {
@@ -798,6 +896,8 @@ ozaki_i8_kernel_cg2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int acc = 0; unsigned aphase = 0;
             int tm, tn;
             for (long long idx = pair; w.seek(p, idx, tm, tn); idx += npairs) {
+                int kb0, kb1;
+                oz_krange(p, (long long)tm * C2_BM, (long long)tn * OZ_BN, C2_BM, kb0, kb1);
                 for (int t = 0; t < groups;) {
                     if (p.pair && ((groups - t) & 1) == 0) {
                         const int a_lo = acc; const unsigned ph_lo = aphase;
@@ -809,7 +909,7 @@ ozaki_i8_kernel_cg2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         tc_fence_after();
                         const unsigned d_lo = tmem_base + (unsigned)(a_lo * OZ_BN), d_hi = tmem_base + (unsigned)(a_hi * OZ_BN);
                         int prev = 0;
-                        for (int kb = 0; kb < p.kblocks; ++kb) {
+                        for (int kb = kb0; kb < kb1; ++kb) {
                             for (int i = 0; i <= t + 1; ++i) {
                                 mbar_wait_bounded(&full[stage], phase);
                                 tc_fence_after();
@@ -819,18 +919,19 @@ ozaki_i8_kernel_cg2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     const uint64_t da = umma_desc_k_sw128(sA), db = umma_desc_k_sw128(sA + C2_A_BYTES);
 #pragma unroll
                                     for (int kk = 0; kk < OZ_BK / 32; ++kk)
-                                        tc_mma_i8_cg2(d_hi, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), C2_IDESC, (kb | i | kk) != 0);
+                                        tc_mma_i8_cg2(d_hi, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), C2_IDESC,
+                                                      ((kb - kb0) | i | kk) != 0);
                                     if (i >= 1) {
                                         const uint64_t dp = umma_desc_k_sw128(sP);
 #pragma unroll
                                         for (int kk = 0; kk < OZ_BK / 32; ++kk)
                                             tc_mma_i8_cg2(d_lo, dp + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), C2_IDESC,
-                                                          !(kb == 0 && i == 1 && kk == 0));
+                                                          !(kb == kb0 && i == 1 && kk == 0));
                                         tc_commit_cg2(&empty[prev]);
                                     }
                                     if (i == t + 1) {
                                         tc_commit_cg2(&empty[stage]);
-                                        if (kb == p.kblocks - 1) { tc_commit_cg2(&tfull[a_lo]); tc_commit_cg2(&tfull[a_hi]); }
+                                        if (kb == kb1 - 1) { tc_commit_cg2(&tfull[a_lo]); tc_commit_cg2(&tfull[a_hi]); }
                                     }
                                 }
                                 __syncwarp();
@@ -844,7 +945,7 @@ ozaki_i8_kernel_cg2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     mbar_wait_bounded(&tempty[acc], aphase ^ 1u);
                     tc_fence_after();
                     const unsigned d_tmem = tmem_base + (unsigned)(acc * OZ_BN);
-                    const int nkb = (t + 1) * p.kblocks;
+                    const int nkb = (t + 1) * (kb1 - kb0);
                     for (int kb = 0; kb < nkb; ++kb) {
                         mbar_wait_bounded(&full[stage], phase);
                         tc_fence_after();
@@ -863,6 +964,27 @@ ozaki_i8_kernel_cg2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (++acc == OZ_ACC_STAGES) { acc = 0; aphase ^= 1u; }
                     ++t;
                 }
+                if (oz_has_diag(groups)) {
+                    mbar_wait_bounded(&tempty[acc], aphase ^ 1u);
+                    tc_fence_after();
+                    const unsigned d_tmem = tmem_base + (unsigned)(acc * OZ_BN);
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        mbar_wait_bounded(&full[stage], phase);
+                        tc_fence_after();
+                        const unsigned sA = smem_u32(smem + stage * C2_SLOT_BYTES);
+                        if (elect_one()) {
+                            const uint64_t da = umma_desc_k_sw128(sA), db = umma_desc_k_sw128(sA + C2_A_BYTES);
+#pragma unroll
+                            for (int kk = 0; kk < OZ_BK / 32; ++kk)
+                                tc_mma_i8_cg2(d_tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), C2_IDESC, ((kb - kb0) | kk) != 0);
+                            tc_commit_cg2(&empty[stage]);
+                            if (kb == kb1 - 1) tc_commit_cg2(&tfull[acc]);
+                        }
+                        __syncwarp();
+                        if (++stage == C2_RING) { stage = 0; phase ^= 1u; }
+                    }
+                    if (++acc == OZ_ACC_STAGES) { acc = 0; aphase ^= 1u; }
+                }
             }
         }
     } else if (warp >= OZ_EPI_WARP0) {
@@ -879,10 +1001,11 @@ ozaki_i8_kernel_cg2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < 64; ++j) accd[j] = 0.0;
             }
-            for (int t = 0; t < groups; ++t) {
+            const int norders = groups + (oz_has_diag(groups) ? 1 : 0);  // the diagonal group is the single product of order `groups`
+            for (int t = 0; t < norders; ++t) {
                 mbar_wait_bounded(&tfull[acc], aphase);
                 tc_fence_after();
-                const double sc = __hiloint2double((1023 - OZ_BETA * (t + 2)) << 20, 0);  // 2^(-7 (t+2))
+                const double sc = __hiloint2double((1023 - OZ_BETA * (t + 2)) << 20, 0);  // 2^(-8 (t+2))
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     unsigned r[32];
@@ -904,21 +1027,8 @@ ozaki_i8_kernel_cg2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty[acc], 0));  // the leader's barrier counts both CTAs
                 if (++acc == OZ_ACC_STAGES) { acc = 0; aphase ^= 1u; }
             }
-            if (MODE == 1 && row < p.m) {
-                const double sr = p.alpha * __ldg(p.sa + row);
-                double* crow = p.C + (long long)row * p.ldc;
-                const long long grow = p.row0 + row;
-#pragma unroll
-                for (int j = 0; j < 64; ++j) {
-                    const int col = col0 + j;
-                    bool live = col < p.n;
-                    if (p.mask == 1) live = live && (grow >= p.col0 + col);
-                    else if (p.mask == 2) live = live && (grow / p.mask_nb < (p.col0 + col) / p.mask_nb);
-                    if (live) {
-                        const double v = accd[j] * (sr * __ldg(p.sb + col));
-                        crow[col] = p.beta0 ? v : crow[col] + v;
-                    }
-                }
+            if constexpr (MODE == 1) {
+                if (row < p.m) oz_store_row(p, accd, row, col0);
             }
         }
     }
@@ -932,14 +1042,275 @@ ozaki_i8_kernel_cg2(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
 }
 
+// ---- variant 4 (default): CTA pairs, ORDER PAIRS SIDE BY SIDE IN ONE N = 256 INSTRUCTION ---------------------------------------
+// Variants 1-3 are paced by the operand bytes an instruction pulls out of shared memory (~56 B/clk/SM: M128 x N128 x K32 reads 8 KB
+// -> ~145 clk for 64 clk of int8 math; the CTA-pair N = 128 form reads 6 KB -> ~130 clk).  The only lever is more MACs per operand
+// byte, i.e. N = 256 -- but a 256-column output tile would need 2 x 128 x 256 fp64 running sums per SM (the whole register file).
+// This variant keeps the 256 x 128 output tile of a CTA pair and widens N across the ORDER instead: for the order pair (t, t+1)
+//      [ acc_t | acc_{t+1} ] += A_i * [ B_{t-i} ; B_{t+1-i} ]^T ,   i = 0..t,
+// one tcgen05.mma.cta_group::2 (M = 256, N = 256) per 32 digits: in a CTA pair the N rows of the B operand are split between the
+// two CTAs, so the leader stages the 128 rows of plane t-i and its peer the 128 rows of plane t+1-i of the SAME output columns,
+// and both SMs receive the 256-column accumulator [order t | order t+1] for their own 128 rows.  Per SM and instruction that is
+// 8 KB of operand reads for 128 clk of math (was 6 KB for 64).  The one product of order t+1 this leaves out, A_{t+1} B_0^T, is an
+// N = 128 instruction into the right half (each CTA stages 64 rows of B_0, as in variant 3); an odd plane count runs order 0
+// (a single product) the same way, and so does the equal-plane product an even plane count appends (oz_has_diag).  6 planes:
+// 9 wide + 4 narrow slot visits per K-block instead of 22 narrow ones.
+//   * ring of 6 slots x 32 KB (A 16 KB + B 16 KB; a narrow slot uses 24 KB); every slot is consumed by exactly one instruction
+//     group, so there is no "previous slot" coupling as in the paired schedule of variants 1 / 3;
+//   * TMEM: 2 buffers x 256 columns [lo | hi]; the epilogue drains buffer b (both orders) while the MMAs fill buffer b^1;
+//   * barriers / cluster protocol / tile walk / masks / K-ranges exactly as variant 3.
+constexpr int W4_B_BYTES = OZ_BN * OZ_BK;                 // 16 KB: a full 128-row plane tile
+constexpr int W4_SLOT_BYTES = C2_A_BYTES + W4_B_BYTES;    // 32 KB
+constexpr int W4_RING = 6;
+constexpr int W4_ACC = 2;                                 // x 256 TMEM columns
+constexpr int W4_SMEM_BYTES = W4_RING * W4_SLOT_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+// instruction descriptor: D = s32, A = B = signed int8, both K-major, N = 256, M = 256 (cta_group::2)
+constexpr unsigned W4_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(256 >> 3) << 17) | ((unsigned)(C2_BM >> 4) << 24);
+static_assert(W4_SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
+
+// Order groups of one output tile, enumerated identically by the three roles.  `cursor` runs over the orders t = 0..groups-1:
+// a WIDE group covers the order pair (t, t+1) when (groups - t) is even (an odd plane count runs order 0 alone as a single-order
+// group).  After the last order an EVEN plane count appends the DIAGONAL group: the one product A_h B_h^T, h = groups / 2, of
+// order `groups` (see oz_has_diag).  Every group owns one TMEM buffer.
+struct OzGroup {
+    int t;        // first order of the group (scale 2^(-8 (t + 2)))
+    int wide;     // 1: orders (t, t+1) side by side in N = 256 instructions
+    int diag;     // 1: the single product (A_t/2, B_t/2), t == groups
+    int nslots;   // ring slots per K-block
+    int norders;  // accumulator halves the epilogue drains
+};
+__device__ __forceinline__ bool oz_next_group(int groups, int& cursor, OzGroup& g) {
+    if (cursor < groups) {
+        g.t = cursor;
+        g.wide = ((groups - cursor) & 1) == 0;
+        g.diag = 0;
+        g.nslots = g.wide ? cursor + 2 : cursor + 1;
+        g.norders = g.wide ? 2 : 1;
+        cursor += g.norders;
+        return true;
+    }
+    if (cursor == groups && oz_has_diag(groups)) {
+        g.t = groups; g.wide = 0; g.diag = 1; g.nslots = 1; g.norders = 1;
+        cursor = groups + 1;
+        return true;
+    }
+    return false;
+}
+
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1)
+ozaki_i8_kernel_w4(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const OzParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const unsigned raw = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);  // identical offset in both CTAs of the pair
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + W4_RING * W4_SLOT_BYTES);
+    uint64_t* full = bars;                   // [6]   TMA (both CTAs) -> MMA; only the leader's copies are used
+    uint64_t* empty = bars + W4_RING;        // [6]   MMA -> TMA, multicast to both CTAs
+    uint64_t* tfull = bars + 2 * W4_RING;    // [2]   MMA -> epilogue, multicast to both CTAs
+    uint64_t* tempty = tfull + W4_ACC;       // [2]   epilogue (both CTAs) -> MMA; only the leader's copies are used
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty + W4_ACC);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];\n" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < W4_RING; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < W4_ACC; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * OZ_EPI_WARPS); }
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const unsigned tmem_base = *tmem_slot;
+
+    const int groups = oz_groups(p, MODE);
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own 128 rows of A; wide slot: all 128 rows of ITS plane of B; narrow slot: own 64 rows =====
+        TileWalk w; w.init(p);
+        int stage = 0; unsigned phase = 0;
+        int tm, tn;
+        for (long long idx = pair; w.seek(p, idx, tm, tn); idx += npairs) {
+            const int m0 = tm * C2_BM + (int)rank * OZ_BM, n0 = tn * OZ_BN;
+            int kb0, kb1;
+            oz_krange(p, (long long)tm * C2_BM, (long long)tn * OZ_BN, C2_BM, kb0, kb1);
+            OzGroup g;
+            for (int cursor = 0; oz_next_group(groups, cursor, g);) {
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    for (int i = 0; i < g.nslots; ++i) {
+                        const bool wslot = g.wide && i <= g.t;
+                        mbar_wait_bounded(&empty[stage], phase ^ 1u);
+                        uint8_t* sA = smem + stage * W4_SLOT_BYTES;
+                        if (elect_one()) {
+                            if (p.noload) {
+                                if (rank == 0) mbar_arrive(&full[stage]);
+                            } else {
+                                const unsigned fb = mapa_u32(&full[stage], 0);
+                                const int xk = kb * OZ_BK;
+                                if (wslot) {
+                                    if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * W4_SLOT_BYTES);
+                                    const int pb = g.t - i + (int)rank;  // leader: plane t-i (order t), peer: plane t+1-i (order t+1)
+                                    tma_load_2d_cg2(sA, &tmA, fb, i * p.pstride + xk, m0);
+                                    tma_load_2d_cg2(sA + C2_A_BYTES, &tmB, fb, pb * p.pstride + xk, n0);
+                                    tma_load_2d_cg2(sA + C2_A_BYTES + C2_B_BYTES, &tmB, fb, pb * p.pstride + xk, n0 + C2_BNH);
+                                } else {
+                                    if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * C2_SLOT_BYTES);
+                                    // wide group: the product A_{t+1} B_0 the side-by-side slots leave out; diagonal group: A_h B_h;
+                                    // single order: A_i B_{t-i}
+                                    const int pa = g.diag ? (g.t >> 1) : (g.wide ? g.t + 1 : i);
+                                    const int pb = g.diag ? (g.t >> 1) : (g.wide ? 0 : g.t - i);
+                                    tma_load_2d_cg2(sA, &tmA, fb, pa * p.pstride + xk, m0);
+                                    tma_load_2d_cg2(sA + C2_A_BYTES, &tmB, fb, pb * p.pstride + xk, n0 + (int)rank * C2_BNH);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        if (++stage == W4_RING) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {  // ===== MMA issuer: leader CTA only, one elected lane =====
+            TileWalk w; w.init(p);
+            int stage = 0; unsigned phase = 0;
+            int acc = 0; unsigned aphase = 0;
+            int tm, tn;
+            for (long long idx = pair; w.seek(p, idx, tm, tn); idx += npairs) {
+                int kb0, kb1;
+                oz_krange(p, (long long)tm * C2_BM, (long long)tn * OZ_BN, C2_BM, kb0, kb1);
+                OzGroup g;
+                for (int cursor = 0; oz_next_group(groups, cursor, g);) {
+                    mbar_wait_bounded(&tempty[acc], aphase ^ 1u);
+                    tc_fence_after();
+                    const unsigned d_lo = tmem_base + (unsigned)(acc * 256), d_hi = d_lo + 128u;
+                    for (int kb = kb0; kb < kb1; ++kb) {
+                        for (int i = 0; i < g.nslots; ++i) {
+                            const bool wslot = g.wide && i <= g.t;
+                            mbar_wait_bounded(&full[stage], phase);
+                            tc_fence_after();
+                            const unsigned sA = smem_u32(smem + stage * W4_SLOT_BYTES);
+                            if (elect_one()) {
+                                const uint64_t da = umma_desc_k_sw128(sA), db = umma_desc_k_sw128(sA + C2_A_BYTES);
+                                if (wslot) {
+#pragma unroll
+                                    for (int kk = 0; kk < OZ_BK / 32; ++kk)
+                                        tc_mma_i8_cg2(d_lo, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), W4_IDESC,
+                                                      ((kb - kb0) | i | kk) != 0);
+                                } else {
+                                    // wide group: the right half, already written by slot 0 of this K-block; otherwise the left half,
+                                    // first written at (kb0, i = 0)
+                                    const unsigned d = g.wide ? d_hi : d_lo;
+#pragma unroll
+                                    for (int kk = 0; kk < OZ_BK / 32; ++kk)
+                                        tc_mma_i8_cg2(d, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), C2_IDESC,
+                                                      g.wide ? 1u : (unsigned)(((kb - kb0) | i | kk) != 0));
+                                }
+                                tc_commit_cg2(&empty[stage]);
+                                if (kb == kb1 - 1 && i == g.nslots - 1) tc_commit_cg2(&tfull[acc]);
+                            }
+                            __syncwarp();
+                            if (++stage == W4_RING) { stage = 0; phase ^= 1u; }
+                        }
+                    }
+                    if (++acc == W4_ACC) { acc = 0; aphase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp >= OZ_EPI_WARP0) {
+        // ===== epilogue (both CTAs): warp (4 + 4 h + q) owns TMEM lanes [32 q, 32 q + 32) and tile columns [64 h, 64 h + 64) =====
+        const int q = warp & 3, h = (warp - OZ_EPI_WARP0) >> 2;
+        TileWalk w; w.init(p);
+        int acc = 0; unsigned aphase = 0;
+        int tm, tn;
+        for (long long idx = pair; w.seek(p, idx, tm, tn); idx += npairs) {
+            const int row = tm * C2_BM + (int)rank * OZ_BM + q * 32 + lane;
+            const int col0 = tn * OZ_BN + h * 64;
+            double accd[MODE == 1 ? 64 : 1];
+            if (MODE == 1) {
+#pragma unroll
+                for (int j = 0; j < 64; ++j) accd[j] = 0.0;
+            }
+            OzGroup g;
+            for (int cursor = 0; oz_next_group(groups, cursor, g);) {
+                mbar_wait_bounded(&tfull[acc], aphase);
+                tc_fence_after();
+                for (int o = 0; o < g.norders; ++o) {
+                    const double sc = __hiloint2double((1023 - OZ_BETA * (g.t + o + 2)) << 20, 0);  // 2^(-8 (order + 2))
+                    const unsigned tcol = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(acc * 256 + o * 128 + h * 64);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        unsigned r[16];
+                        tc_ld16(tcol + (unsigned)(c * 16), r);
+                        if (MODE == 1) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) accd[c * 16 + j] = fma(exact_i2d((int)r[j]), sc, accd[c * 16 + j]);
+                        } else {
+                            if (row < p.m) {
+                                int* dst = p.Ci + (long long)row * p.ldci + col0 + c * 16;
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (col0 + c * 16 + j < p.n) dst[j] = (int)r[j];
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty[acc], 0));  // the leader's barrier counts both CTAs
+                if (++acc == W4_ACC) { acc = 0; aphase ^= 1u; }
+            }
+            if constexpr (MODE == 1) {
+                if (row < p.m) oz_store_row(p, accd, row, col0);
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
 // ---- digit extraction ----------------------------------------------------------------------------------------------
-// one CTA per row: exponent from the row maximum, then `s` rounds of  R <- 128 R;  q = rint(R);  R <- R - q  (all exact)
+// Balanced radix-256 digits of R = x 2^-e (|R| <= OZ_RMAX): ONE rounding to the last plane, I = rint(R 2^(8 s)) (|I| < 2^55 for
+// s <= 7, exact in int64), then the digits are peeled from the least significant end with a carry,
+//      d = ((I + 128) mod 256) - 128  in [-128, 127],      I <- (I - d) / 256,
+// so every plane uses the whole int8 range and sum_p d_p 256^(s-1-p) == I exactly.  The top digit stays inside int8 because
+// the row exponent leaves |R| <= 0.494 < (127 - 128/255) / 256.  Truncating the planes after the first s' < s leaves a remainder of
+// at most 0.502 units of plane s' (the device-side plane guard uses a prefix of the extracted planes).
+constexpr double OZ_RMAX = 0.494;
+__device__ __forceinline__ int oz_row_exponent(double mx) {  // mx finite and > 0
+    int e = ilogb(mx) + 2;                   // mx 2^-e in [1/4, 1/2)
+    if (scalbn(mx, -e) > OZ_RMAX) ++e;       // mantissa above 1.976: one more bit of head room for the carry into the top digit
+    return e;
+}
+__device__ __forceinline__ long long oz_fixed_point(double R, int nslices) {
+    return __double2ll_rn(R * __hiloint2double((1023 + OZ_BETA * nslices) << 20, 0));
+}
+// one CTA per row: exponent from the row maximum, then the digits of every entry
 __global__ void __launch_bounds__(128) ozaki_slice_kernel(long long rows, int k, int kplane, const double* __restrict__ X,
                                                           long long ldx, int nslices, signed char* __restrict__ Q,
-                                                          long long ldq, double* __restrict__ scale) {
+                                                          long long ldq, double* __restrict__ scale,
+                                                          const int* __restrict__ nslices_dev) {
     __shared__ double red[4];
     const long long r = blockIdx.x;
     if (r >= rows) return;
+    if (nslices_dev) {  // the plane count the product will use: round THERE (uniform across the grid)
+        const int v = __ldg(nslices_dev);
+        nslices = v < 1 ? 1 : (v < nslices ? v : nslices);
+    }
     const double* x = X + r * ldx;
     double mx = 0.0;
     bool bad = false;
@@ -965,18 +1336,18 @@ __global__ void __launch_bounds__(128) ozaki_slice_kernel(long long rows, int k,
     } else if (mx == 0.0) {
         sc = 1.0;
     } else {
-        e = ilogb(mx) + 2;  // |x| 2^-e < 1/2
+        e = oz_row_exponent(mx);  // |x| 2^-e <= 0.494
         sc = scalbn(1.0, e);
     }
     if (threadIdx.x == 0) scale[r] = sc;
     signed char* qrow = Q + r * ldq;
     for (int c = threadIdx.x; c < kplane; c += 128) {
-        double R = (mx != mx || c >= k) ? 0.0 : scalbn(x[c], -e);  // columns [k, kplane) are zero padding
-        for (int p = 0; p < nslices; ++p) {
-            R *= 128.0;
-            double d = rint(R);
-            qrow[(long long)p * kplane + c] = (signed char)(int)d;
-            R -= d;
+        const double R = (mx != mx || c >= k) ? 0.0 : scalbn(x[c], -e);  // columns [k, kplane) are zero padding
+        long long I = oz_fixed_point(R, nslices);
+        for (int p = nslices - 1; p >= 0; --p) {
+            const int d = (int)((I + 128) & 255) - 128;
+            qrow[(long long)p * kplane + c] = (signed char)d;
+            I = (I - d) >> 8;
         }
     }
 }
@@ -1009,7 +1380,7 @@ __global__ void __launch_bounds__(256) ozaki_slice_t_kernel(long long rows, int 
                                                             long long ldx, int nslices, signed char* __restrict__ Qt, long long ldq,
                                                             const unsigned long long* __restrict__ colmax_bits,
                                                             double* __restrict__ scale) {
-    __shared__ signed char dig[8][32][128 + 16];
+    __shared__ signed char dig[OZ_PLANES_MAX][32][128 + 16];
     const int c0 = blockIdx.x * 32;
     const long long r0 = (long long)blockIdx.y * 128;
     const int lc = threadIdx.x & 31;
@@ -1020,18 +1391,18 @@ __global__ void __launch_bounds__(256) ozaki_slice_t_kernel(long long rows, int 
     if (c < cols) {
         mx = __longlong_as_double((long long)colmax_bits[c]);
         nanrow = !(mx <= 1.7976931348623157e308);
-        if (!nanrow && mx != 0.0) e = ilogb(mx) + 2;
+        if (!nanrow && mx != 0.0) e = oz_row_exponent(mx);
         if (blockIdx.y == 0 && threadIdx.x < 32)
             scale[c] = nanrow ? __longlong_as_double(0x7ff8000000000000LL) : (mx == 0.0 ? 1.0 : scalbn(1.0, e));
     }
     for (int lr = threadIdx.x >> 5; lr < 128; lr += 8) {
         const long long r = r0 + lr;
-        double R = (c < cols && r < rows && !nanrow) ? scalbn(X[r * ldx + c], -e) : 0.0;
-        for (int p = 0; p < nslices; ++p) {
-            R *= 128.0;
-            double d = rint(R);
-            dig[p][lc][lr] = (signed char)(int)d;
-            R -= d;
+        const double R = (c < cols && r < rows && !nanrow) ? scalbn(X[r * ldx + c], -e) : 0.0;
+        long long I = oz_fixed_point(R, nslices);
+        for (int p = nslices - 1; p >= 0; --p) {
+            const int d = (int)((I + 128) & 255) - 128;
+            dig[p][lc][lr] = (signed char)d;
+            I = (I - d) >> 8;
         }
     }
     __syncthreads();
@@ -1117,13 +1488,14 @@ int sm_count() {  // per device: one process may drive several GPUs (XLA's per-d
     }
     return n[dev];
 }
-// kernel variant: 3 = CTA pairs / cta_group::2 (default), 1 = one CTA per tile (round-1 kernel), 2 = plane-resident 128 x 64 tiles.
-// GPB_OZ_KERNEL selects 1 / 2 for measurements (profiles/r02_ozaki_cg2.md); read once, the value never changes afterwards.
+// kernel variant: 4 = CTA pairs with order pairs side by side in N = 256 instructions (default), 3 = CTA pairs / N = 128 (round-2
+// first half), 1 = one CTA per tile (round-1 kernel), 2 = plane-resident 128 x 64 tiles.  GPB_OZ_KERNEL selects 1 / 2 / 3 for
+// measurements (profiles/r02_ozaki_cg2.md, r02_ozaki_w4.md); read once, the value never changes afterwards.
 int variant() {
     static const int v = [] {
         const char* e = std::getenv("GPB_OZ_KERNEL");
-        const int x = e ? std::atoi(e) : 3;
-        return (x >= 1 && x <= 3) ? x : 3;
+        const int x = e ? std::atoi(e) : 4;
+        return (x >= 1 && x <= 4) ? x : 4;
     }();
     return v;
 }
@@ -1132,17 +1504,18 @@ int launch(stream_t s, const void* A, int64_t rowsA, int64_t lda, const void* B,
            OzParams& p) {
     const int v = variant();
     // cudaFuncSetAttribute is per device: remember it per (device, variant), never per process
-    static bool attr_set[GPB_MAX_DEVICES][4] = {};
+    static bool attr_set[GPB_MAX_DEVICES][5] = {};
     const int dev = current_device();
     if (!attr_set[dev][v]) {
         cudaError_t e = v == 1   ? cudaFuncSetAttribute(ozaki_i8_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, OZ_SMEM_BYTES)
                         : v == 2 ? cudaFuncSetAttribute(ozaki_i8_kernel_v2<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, O2_SMEM_BYTES)
-                                 : cudaFuncSetAttribute(ozaki_i8_kernel_cg2<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES);
+                        : v == 3 ? cudaFuncSetAttribute(ozaki_i8_kernel_cg2<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES)
+                                 : cudaFuncSetAttribute(ozaki_i8_kernel_w4<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, W4_SMEM_BYTES);
         if (e != cudaSuccess) return GPB_ERR_LAUNCH;
         attr_set[dev][v] = true;
     }
     p.bn = v == 2 ? O2_BN : OZ_BN;
-    p.bm = v == 3 ? C2_BM : OZ_BM;
+    p.bm = v >= 3 ? C2_BM : OZ_BM;
     p.kbs = (p.kblocks % OZ_KBS_MAX == 0 && !std::getenv("GPB_OZ_KBS1")) ? OZ_KBS_MAX : 1;
     {
         static int pair = [] { const char* e = std::getenv("GPB_OZ_PAIR"); return (e && std::atoi(e) == 0) ? 0 : 1; }();
@@ -1160,13 +1533,14 @@ int launch(stream_t s, const void* A, int64_t rowsA, int64_t lda, const void* B,
     CUtensorMap ta, tb;
     int rc = make_map(&ta, A, rowsA, width, lda, OZ_BM);
     if (rc) return rc;
-    rc = make_map(&tb, B, rowsB, width, ldb, v == 3 ? C2_BNH : p.bn);
+    rc = make_map(&tb, B, rowsB, width, ldb, v >= 3 ? C2_BNH : p.bn);
     if (rc) return rc;
     p.ntm = (p.m + p.bm - 1) / p.bm;
     p.ntn = (p.n + p.bn - 1) / p.bn;
     long long tiles = (long long)p.ntm * p.ntn;  // upper bound on the live tiles; CTAs beyond the live count exit at once
-    const int ctas_per_tile = v == 3 ? 2 : 1;
-    const int units = sm_count() / ctas_per_tile;  // v3: one CTA pair per TPC
+    const int ctas_per_tile = v >= 3 ? 2 : 1;
+    int units = sm_count() / ctas_per_tile;  // v3 / v4: one CTA pair per TPC
+    if (p.max_ctas > 0 && p.max_ctas / ctas_per_tile < units) units = p.max_ctas / ctas_per_tile > 0 ? p.max_ctas / ctas_per_tile : 1;
     int grid = (int)(tiles < units ? tiles : units) * ctas_per_tile;
     if (grid <= 0) return GPB_OK;
     const bool prof = profile_enabled();
@@ -1177,19 +1551,36 @@ int launch(stream_t s, const void* A, int64_t rowsA, int64_t lda, const void* B,
             if (p.mask == 1) {
                 c = p.row0 + i - p.col0 + 1;
                 c = c < 0 ? 0 : (c > p.n ? p.n : c);
-            } else if (p.mask == 2) {
-                long long first = ((p.row0 + i) / p.mask_nb + 1) * p.mask_nb - p.col0;
+            } else if (p.mask == 2 || p.mask == 3) {
+                long long first = ((p.row0 + i) / p.mask_nb + (p.mask == 2 ? 1 : 0)) * p.mask_nb - p.col0;
                 first = first < 0 ? 0 : (first > p.n ? p.n : first);
                 c = p.n - first;
             }
             live += (double)c;
         }
         const int S = MODE == 0 ? 1 : p.nslices;
-        profile_ozaki_begin(s, 2.0 * live * (double)p.kblocks * OZ_BK * (S * (S + 1) / 2));
+        double kfrac = 1.0;  // triangular K-range: fraction of the K-blocks an average tile visits
+        if (p.krange != KR_FULL && p.kblocks > 0) {
+            const bool on_b = p.krange == KR_B_LOWER || p.krange == KR_B_UPPER;
+            const int nt = on_b ? p.ntn : p.ntm, step = on_b ? OZ_BN : p.bm;
+            double acc = 0.0;
+            for (int t = 0; t < nt; ++t) {
+                long long lo = 0, hi = p.kblocks;
+                const long long x0 = (long long)t * step;
+                if (p.krange == KR_B_LOWER || p.krange == KR_A_LOWER) hi = (x0 + step - 1 + p.kr_off) / OZ_BK + 1;
+                else lo = (x0 + p.kr_off) / OZ_BK;
+                lo = lo < 0 ? 0 : (lo > p.kblocks - 1 ? p.kblocks - 1 : lo);
+                hi = hi < 1 ? 1 : (hi > p.kblocks ? p.kblocks : hi);
+                acc += (double)(hi - lo);
+            }
+            kfrac = acc / ((double)nt * p.kblocks);
+        }
+        profile_ozaki_begin(s, 2.0 * live * kfrac * (double)p.kblocks * OZ_BK * (S * (S + 1) / 2 + (v >= 3 && oz_has_diag(S) ? 1 : 0)));
     }
     if (v == 1) ozaki_i8_kernel<MODE><<<grid, OZ_THREADS, OZ_SMEM_BYTES, to_stream(s)>>>(ta, tb, p);
     else if (v == 2) ozaki_i8_kernel_v2<MODE><<<grid, OZ_THREADS, O2_SMEM_BYTES, to_stream(s)>>>(ta, tb, p);
-    else ozaki_i8_kernel_cg2<MODE><<<grid, OZ_THREADS, C2_SMEM_BYTES, to_stream(s)>>>(ta, tb, p);
+    else if (v == 3) ozaki_i8_kernel_cg2<MODE><<<grid, OZ_THREADS, C2_SMEM_BYTES, to_stream(s)>>>(ta, tb, p);
+    else ozaki_i8_kernel_w4<MODE><<<grid, OZ_THREADS, W4_SMEM_BYTES, to_stream(s)>>>(ta, tb, p);
     if (prof) profile_gemm_end(s);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
@@ -1198,19 +1589,19 @@ int launch(stream_t s, const void* A, int64_t rowsA, int64_t lda, const void* B,
 }  // namespace
 
 int ozaki_slice(stream_t s, int64_t rows, int64_t k, int64_t kplane, const double* X, int64_t ldx, int nslices, int8_t* Q,
-                int64_t ldq, double* scale) {
-    if (rows < 0 || k <= 0 || kplane < k || nslices < 1 || nslices > 8 || !X || !Q || !scale || ldq < (int64_t)nslices * kplane)
+                int64_t ldq, double* scale, const int* nslices_dev) {
+    if (rows < 0 || k <= 0 || kplane < k || nslices < 1 || nslices > OZ_PLANES_MAX || !X || !Q || !scale || ldq < (int64_t)nslices * kplane)
         return GPB_ERR_INVALID;
     if (rows == 0) return GPB_OK;
     ozaki_slice_kernel<<<(unsigned)rows, 128, 0, to_stream(s)>>>(rows, (int)k, (int)kplane, X, ldx, nslices,
-                                                                 reinterpret_cast<signed char*>(Q), ldq, scale);
+                                                                 reinterpret_cast<signed char*>(Q), ldq, scale, nslices_dev);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
 }
 
 int ozaki_slice_t(stream_t s, int64_t rows, int64_t cols, int64_t kplane, const double* X, int64_t ldx, int nslices, int8_t* Qt,
                   int64_t ldq, double* scale, double* colmax_scratch) {
-    if (rows <= 0 || cols <= 0 || kplane < rows || kplane % 128 || nslices < 1 || nslices > 8 || !X || !Qt || !scale ||
+    if (rows <= 0 || cols <= 0 || kplane < rows || kplane % 128 || nslices < 1 || nslices > OZ_PLANES_MAX || !X || !Qt || !scale ||
         !colmax_scratch || ldq < (int64_t)nslices * kplane || (ldq & 3) || (reinterpret_cast<uintptr_t>(Qt) & 3))
         return GPB_ERR_INVALID;
     if (cudaMemsetAsync(colmax_scratch, 0, (size_t)cols * sizeof(double), to_stream(s)) != cudaSuccess) return GPB_ERR_LAUNCH;
@@ -1248,15 +1639,22 @@ int igemm_i8(stream_t s, int64_t m, int64_t n, int64_t k, const int8_t* A, int64
 }
 
 int ozaki_gemm(stream_t s, const OzakiGemmDesc& d) {
-    if (d.M < 0 || d.N < 0 || d.K <= 0 || d.nslices < 1 || d.nslices > 8 || !d.Qa || !d.Qb || !d.sa || !d.sb || !d.C)
+    if (d.M < 0 || d.N < 0 || d.K <= 0 || d.nslices < 1 || d.nslices > OZ_PLANES_MAX || !d.Qa || !d.Qb || !d.sa || !d.sb || !d.C)
         return GPB_ERR_INVALID;
-    // int32 accumulator headroom of the deepest order: nslices * K * 64^2 must stay below 2^31
-    if (d.K % OZ_BK || (int64_t)d.nslices * d.K * 4096 >= (1ll << 31)) return GPB_ERR_UNSUPPORTED;
-    if (d.mask != MASK_NONE && d.mask != MASK_LOWER && d.mask != MASK_BLOCK_STRICT_UPPER) return GPB_ERR_UNSUPPORTED;
+    // int32 accumulator headroom of the deepest order: nslices * K * 128^2 must stay below 2^31
+    if (d.K % OZ_BK || (int64_t)d.nslices * d.K * OZ_DIGIT_SQ_MAX >= (1ll << 31)) return GPB_ERR_UNSUPPORTED;
+    if (d.mask != MASK_NONE && d.mask != MASK_LOWER && d.mask != MASK_BLOCK_STRICT_UPPER && d.mask != MASK_BLOCK_UPPER_DIAG_TO_C2)
+        return GPB_ERR_UNSUPPORTED;
+    const bool ext = d.krange != KR_FULL || d.mask == MASK_BLOCK_UPPER_DIAG_TO_C2;
+    if (ext && !ozaki_supports_extensions()) return GPB_ERR_UNSUPPORTED;
+    if (d.mask == MASK_BLOCK_UPPER_DIAG_TO_C2 && (!d.C2 || d.mask_nb <= 0 || d.mask_nb % 128 || d.mask_col0 % 128)) return GPB_ERR_INVALID;
+    if (d.krange < KR_FULL || d.krange > KR_A_UPPER) return GPB_ERR_INVALID;
     if (d.M == 0 || d.N == 0) return GPB_OK;
     OzParams p = {};
     p.m = (int)d.M; p.n = (int)d.N; p.kblocks = (int)(d.K / OZ_BK); p.nslices = d.nslices;
-    p.mask = d.mask == MASK_LOWER ? 1 : (d.mask == MASK_BLOCK_STRICT_UPPER ? 2 : 0); p.row0 = d.mask_row0; p.col0 = d.mask_col0; p.mask_nb = d.mask_nb > 0 ? d.mask_nb : 1;
+    p.mask = d.mask == MASK_LOWER ? 1 : (d.mask == MASK_BLOCK_STRICT_UPPER ? 2 : (d.mask == MASK_BLOCK_UPPER_DIAG_TO_C2 ? 3 : 0));
+    p.row0 = d.mask_row0; p.col0 = d.mask_col0; p.mask_nb = d.mask_nb > 0 ? d.mask_nb : 1;
+    p.C2 = d.C2; p.krange = d.krange; p.kr_off = d.kr_off; p.max_ctas = d.max_ctas;
     p.C = d.C; p.ldc = d.ldc; p.sa = d.sa; p.sb = d.sb; p.alpha = d.alpha; p.beta0 = d.beta0; p.planes_dev = d.nslices_dev;
     const int64_t ps = d.plane_stride > 0 ? d.plane_stride : d.K;
     if (ps < d.K || ps % 16) return GPB_ERR_INVALID;
@@ -1265,17 +1663,18 @@ int ozaki_gemm(stream_t s, const OzakiGemmDesc& d) {
 }
 
 bool ozaki_available() { return encode_tiled() != nullptr; }
+bool ozaki_supports_extensions() { return variant() >= 3; }
 
 namespace {
 __global__ void ozaki_choose_planes_kernel(int requested, double n, const double* __restrict__ variance,
                                            const double* __restrict__ obs_stddev, double jitter, int* __restrict__ out) {
     int planes = requested;
     if (requested == OZ_AUTO) {
-        planes = 8;
+        planes = OZ_AUTO_PLANES_HI;
         if (variance && obs_stddev) {
             const double s = obs_stddev[0] * obs_stddev[0] + jitter;
-            const double bound = (n * fabs(variance[0]) + s) / s;  // NaN / s == 0 compare false -> 8 planes
-            if (bound <= OZ_AUTO_COND_LIMIT) planes = 7;
+            const double bound = (n * fabs(variance[0]) + s) / s;  // NaN / s == 0 compare false -> the larger plane count
+            if (bound <= OZ_AUTO_COND_LIMIT) planes = OZ_AUTO_PLANES_LO;
         }
     }
     out[0] = planes;
@@ -1284,7 +1683,7 @@ __global__ void ozaki_choose_planes_kernel(int requested, double n, const double
 
 int ozaki_choose_planes(stream_t s, int requested, int64_t N, const double* variance, const double* obs_stddev, double jitter,
                         int* planes_out) {
-    if (!planes_out || N < 0 || !(requested == OZ_AUTO || (requested >= 1 && requested <= 8))) return GPB_ERR_INVALID;
+    if (!planes_out || N < 0 || !(requested == OZ_AUTO || (requested >= 1 && requested <= OZ_PLANES_MAX))) return GPB_ERR_INVALID;
     ozaki_choose_planes_kernel<<<1, 1, 0, to_stream(s)>>>(requested, (double)N, variance, obs_stddev, jitter, planes_out);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
@@ -1293,7 +1692,7 @@ int ozaki_choose_planes(stream_t s, int requested, int64_t N, const double* vari
 int ozaki_auto_planes_host(int64_t N, double variance, double obs_stddev, double jitter) {
     const double s = obs_stddev * obs_stddev + jitter;
     const double bound = ((double)N * (variance < 0 ? -variance : variance) + s) / s;
-    return bound <= OZ_AUTO_COND_LIMIT ? 7 : 8;
+    return bound <= OZ_AUTO_COND_LIMIT ? OZ_AUTO_PLANES_LO : OZ_AUTO_PLANES_HI;
 }
 
 }  // namespace gpb

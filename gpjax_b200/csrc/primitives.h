@@ -46,7 +46,11 @@ enum Mask {
     MASK_LOWER = 1,               // r >= c
     MASK_UPPER = 2,               // r <= c
     MASK_BLOCK_STRICT_UPPER = 3,  // r / mask_nb <  c / mask_nb
-    MASK_BLOCK_STRICT_LOWER = 4   // r / mask_nb >  c / mask_nb
+    MASK_BLOCK_STRICT_LOWER = 4,  // r / mask_nb >  c / mask_nb
+    // ozaki_gemm only: blocks with r / mask_nb <= c / mask_nb are live; a DIAGONAL block b is not written to C but to the dense
+    // mask_nb x mask_nb matrix at C2 + b * mask_nb^2 (the exact path keeps L in the diagonal blocks of its N x N buffer and the
+    // diagonal blocks of Sigma^-1 in the workspace)
+    MASK_BLOCK_UPPER_DIAG_TO_C2 = 5
 };
 
 // K-range restriction exploiting triangular operands (zeros are never read).
@@ -252,13 +256,18 @@ int svgp_scalar_grads(stream_t s, const double* sc, const double* dots, const do
                       const double* obs_stddev, double jitter, double* g_var, double* g_obs, double* g_mean);
 
 // ---- FP64 rank-k updates on the INT8 tensor pipe (Ozaki scheme; ozaki_i8.cu) ---------------------------------------
-// x_ik = scale_i * sum_p Q[i, p*k + c] * 2^(-7 (p+1)),  scale_i = 2^e_i,  |Q| <= 64: `nslices` signed 7-bit digit planes
-// per entry, plane p stored at columns [p*k, (p+1)*k) of the int8 matrix Q (row stride ldq >= nslices*k bytes, multiple
-// of 16; Q 16-byte aligned).  Exact (no rounding) while nslices*7 covers the mantissa; a NaN/Inf row gets scale = NaN.
+// x_ik = scale_i * sum_p Q[i, p*k + c] * 2^(-8 (p+1)),  scale_i = 2^e_i,  -128 <= Q <= 127: `nslices` balanced radix-256 digit
+// planes per entry (8 bits per plane, rounded ONCE to the last plane), plane p stored at columns [p*k, (p+1)*k) of the int8
+// matrix Q (row stride ldq >= nslices*k bytes, multiple of 16; Q 16-byte aligned).  |x_ik| <= 0.494 scale_i.  Exact (no rounding)
+// for entries whose last mantissa bit lies above 2^(-8 nslices) scale_i; a NaN/Inf row gets scale = NaN.
 // Plane stride `kplane` >= k (columns [k, kplane) of every plane are written as zero digits, so a ragged K can be padded
 // to the multiple of 128 the product kernel needs).
+// nslices_dev (optional DEVICE word, the guard of ozaki_choose_planes): when given, min(nslices, *nslices_dev) planes are extracted
+// and the ONE rounding happens at the last plane the product will use -- a prefix of a longer digit string would be a truncation,
+// whose error has a non-zero mean (balanced digits in [-128, 127] average -1/2) that adds up coherently over K and over the
+// block steps of a factorisation.
 int ozaki_slice(stream_t s, int64_t rows, int64_t k, int64_t kplane, const double* X, int64_t ldx, int nslices, int8_t* Q,
-                int64_t ldq, double* scale);
+                int64_t ldq, double* scale, const int* nslices_dev = nullptr);
 // Same digits for the COLUMNS of a rows x cols block (contraction over the rows): Qt[c, p*kplane + r], scale[c] from the column
 // maxima; rows [rows, kplane) are zero digits (kplane multiple of 128); colmax_scratch: cols doubles.
 int ozaki_slice_t(stream_t s, int64_t rows, int64_t cols, int64_t kplane, const double* X, int64_t ldx, int nslices, int8_t* Qt,
@@ -267,9 +276,12 @@ int ozaki_slice_t(stream_t s, int64_t rows, int64_t cols, int64_t kplane, const 
 // scratch: 2 * ceil(rows / 1024) * cols doubles
 int col_weighted_sums(stream_t s, int64_t rows, int64_t cols, const double* X, int64_t ldx, const double* w, double* scratch,
                       double* out_w, double* out_1);
+constexpr int OZ_DIGIT_BITS = 8;             // radix 256
+constexpr int OZ_DIGIT_SQ_MAX = 128 * 128;   // largest digit-pair product: int32 headroom is nslices * K * 2^14 < 2^31
+constexpr int OZ_PLANES_MAX = 7;             // 56 bits >= the fp64 mantissa (and 8 * 7 + 7 < 63: the fixed-point form fits int64)
 struct OzakiGemmDesc {
     int64_t M = 0, N = 0, K = 0;  // K = digits per plane (multiple of 128)
-    int nslices = 7;              // digit planes present in Qa / Qb (and used, unless nslices_dev overrides it)
+    int nslices = 6;              // digit planes present in Qa / Qb (and used, unless nslices_dev overrides it)
     const int* nslices_dev = nullptr;  // optional DEVICE word: planes to use, 1..nslices (the guard of ozaki_choose_planes);
                                        // read by the kernel, so the host never synchronises on the decision
     const int8_t* Qa = nullptr;   // [M, nslices*K]
@@ -283,20 +295,29 @@ struct OzakiGemmDesc {
     int64_t plane_stride = 0;     // digits between consecutive planes of one row (0 -> K): lets one launch cover a K sub-range
     int64_t ldc = 0;
     double alpha = 1.0;
-    int mask = MASK_NONE;         // MASK_NONE, MASK_LOWER or MASK_BLOCK_STRICT_UPPER (same meaning as GemmDesc::mask)
+    int mask = MASK_NONE;         // MASK_NONE, MASK_LOWER, MASK_BLOCK_STRICT_UPPER (as GemmDesc::mask) or MASK_BLOCK_UPPER_DIAG_TO_C2
     int64_t mask_row0 = 0, mask_col0 = 0, mask_nb = 1;
+    double* C2 = nullptr;         // MASK_BLOCK_UPPER_DIAG_TO_C2: the diagonal blocks (mask_nb multiple of 128)
+    int krange = KR_FULL;         // triangular operand: its structural zeros are never multiplied (K-blocks of 128 digits skipped)
+    int64_t kr_off = 0;
+    int max_ctas = 0;             // > 0: leave SMs free for a concurrent latency-bound chain on another stream (look-ahead)
 };
 int ozaki_gemm(stream_t s, const OzakiGemmDesc& d);
+// krange / MASK_BLOCK_UPPER_DIAG_TO_C2 / max_ctas need the CTA-pair kernel (the default; GPB_OZ_KERNEL=1|2 select older variants)
+bool ozaki_supports_extensions();
 // Digit planes of the int8 trailing updates of an N x N covariance factorisation, decided ON THE DEVICE (no host read):
-//   requested in 5..8        -> planes_out[0] = requested;
-//   requested == OZ_AUTO (-1)-> 7 if the hyper-parameters PROVE cond(Sigma) <= OZ_AUTO_COND_LIMIT, else 8, with the bound
+//   requested in 1..7        -> planes_out[0] = requested;
+//   requested == OZ_AUTO (-1)-> 6 if the hyper-parameters PROVE cond(Sigma) <= OZ_AUTO_COND_LIMIT, else 7, with the bound
 //                               cond(K + s I) <= (N * variance + s) / s,  s = obs_stddev^2 + jitter   (|k(x,y)| <= variance =>
 //                               lambda_max(K) <= N variance by Gershgorin; lambda_min(Sigma) >= s);
-//                               variance == nullptr (a bare matrix, nothing known about it) -> 8.
-// Calibration (profiles/r02_cond_sweep_n8192.jsonl): 8 planes = the FP64 DMMA path's own error level at every cond; 7 planes
-// ~ 5e-17 * cond relative error in the MLL gradient, i.e. <= 1e-9 while cond <= 1e7.
+//                               variance == nullptr (a bare matrix, nothing known about it) -> 7.
+// Calibration (profiles/r02_cond_sweep_n8192.jsonl, radix-128 digits: 8 planes = 56 bits, 7 planes = 49 bits): 56 bits = the FP64
+// DMMA path's own error level at every cond; 49 bits ~ 5e-17 * cond relative error in the MLL gradient.  Six radix-256 planes
+// (48 bits, dropped orders 7 * 2^-50 vs 8 * 2^-51) are 1.75x coarser: ~ 9e-17 * cond, i.e. <= 5e-10 while cond <= 5e6
+// (re-measured in profiles/r02_cond_sweep_radix256.jsonl).
 constexpr int OZ_AUTO = -1;
-constexpr double OZ_AUTO_COND_LIMIT = 1e7;
+constexpr int OZ_AUTO_PLANES_LO = 6, OZ_AUTO_PLANES_HI = 7;
+constexpr double OZ_AUTO_COND_LIMIT = 5e6;
 int ozaki_choose_planes(stream_t s, int requested, int64_t N, const double* variance, const double* obs_stddev, double jitter,
                         int* planes_out);
 // the same rule on the host, for reporting (bench.py) and tests; never used to steer a launch

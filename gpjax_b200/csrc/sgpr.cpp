@@ -51,7 +51,7 @@ Lay layout(int64_t M, int D, int64_t Bs) {
     int64_t p1 = gram_bwd_partials_count(Bs, M, D), p2 = gram_bwd_partials_count(M, M, D);
     L.gpart = take(p1 > p2 ? p1 : p2);
     L.info = take(8);
-    // pass-2 digit planes: OZ_MAX_SLICES planes of kplane int8 digits per row == kplane doubles per row
+    // pass-2 digit planes: OZ_MAX_SLICES (<= 8) planes of kplane int8 digits per row fit kplane doubles per row
     L.with_oz = Bs >= OZ_MIN_ROWS && M >= 256;
     L.oz_kplane = align_up(M + 2, 128);
     L.oz_kplane1 = align_up(Bs, 128);
@@ -194,12 +194,12 @@ int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug) {
         // The output has only ~(M/128)*(M/64)/2 tiles, so K (= rows) is split into SPLITK slices that run as
         // one batched launch into separate partial sums (summed after the block loop).
         if (planes1 && rows >= OZ_MIN_ROWS) {
-            // int8 route: K_b^T K_b (M x M, lower) from COLUMN digit planes of the block (8 planes: the raw statistics are later
+            // int8 route: K_b^T K_b (M x M, lower) from COLUMN digit planes of the block (all 7 planes, 56 bits: the raw statistics are later
             // whitened, which amplifies their rounding by cond(Kzz)); the two augmented rows [d ; 1]^T [K_b | d | 1] are GEMVs.
             const int64_t kp1 = align_up(rows, 128), ldq1 = OZ_MAX_SLICES * ws.oz_kplane1;
             GPB_TRY(ozaki_slice_t(s, rows, M, kp1, ws.T2, ld, planes1, ws.oz_qt, ldq1, ws.oz_s1, ws.oz_colmax));
-            // int32 headroom: (t+1) K 64^2 < 2^31  ->  split K so that planes * Ksub * 4096 stays below it
-            const int64_t kmax = ((int64_t)((1ll << 31) - 1) / ((int64_t)planes1 * 4096)) / 256 * 256;
+            // int32 headroom: (t+1) K 128^2 < 2^31  ->  split K so that planes * Ksub * 2^14 stays below it
+            const int64_t kmax = ((int64_t)((1ll << 31) - 1) / ((int64_t)planes1 * OZ_DIGIT_SQ_MAX)) / 256 * 256;
             const int64_t nsplit = (kp1 + kmax - 1) / kmax;
             const int64_t ksub = align_up((kp1 + nsplit - 1) / nsplit, 128);
             for (int64_t k0 = 0; k0 < kp1; k0 += ksub) {

@@ -254,8 +254,8 @@ OZAKI_AUTO = -1
 def set_ozaki_slices(nslices: int) -> None:
     """Arithmetic of the large rank-NB trailing updates of ``lower_cholesky`` / the inverse (process-wide switch):
     ``OZAKI_AUTO`` (-1, library default): exact int8 digit-plane products (``tcgen05.mma kind::i8``) whose plane count is chosen
-    on the device per call -- 8 planes (fp64-rounding-level) unless the hyper-parameters of a fused objective bound
-    cond(Sigma) by 1e7, then 7; 5..8: that many planes everywhere; 0: FP64 DMMA everywhere.
+    on the device per call -- 7 radix-256 planes (56 bits, fp64-rounding-level) unless the hyper-parameters of a fused
+    objective bound cond(Sigma) by 5e6, then 6; 4..7: that many planes everywhere; 0: FP64 DMMA everywhere.
     ``GPB_OZAKI`` in the environment sets the initial value."""
     lib().gpb_set_ozaki_slices(int(nslices))
 

@@ -119,27 +119,28 @@ int gpb_gemm(void* stream, int64_t M, int64_t N, int64_t K, double alpha, const 
 /* ---- FP64 rank-k updates on the INT8 tensor pipe (Ozaki scheme; tcgen05.mma kind::i8) --------------------------
  * Building blocks of gpb_potrf_lower / gpb_potri_lower, i.e. still jnp.linalg.cholesky (gpjax/linalg/operations.py:54-55)
  * and the inverse its reverse mode needs -- there is no separate reference function.  An fp64 operand row is split
- * exactly into `nslices` signed 7-bit digit planes after a power-of-two row scaling (gpb_ozaki_slice); every
- * digit-pair product is an exact int8 x int8 -> int32 GEMM on the tcgen05 pipe and gpb_ozaki_gemm recombines the
- * orders p+q < nslices in fp64:  C += alpha * A B^T  up to a truncation error of (nslices+1) 2^(-7 nslices) K relative
- * to the row maxima (nslices = 7: below fp64 rounding of a K = 1024 product).
+ * into `nslices` (1..7) balanced radix-256 digit planes (every plane uses the whole int8 range, 8 bits per plane) after a
+ * power-of-two row scaling (gpb_ozaki_slice); every digit-pair product is an exact int8 x int8 -> int32 GEMM on the tcgen05 pipe
+ * and gpb_ozaki_gemm recombines the orders p+q < nslices in fp64:  C += alpha * A B^T  up to a truncation error of
+ * 16 (nslices+1) 2^(-8 nslices) K relative to the row maxima (nslices = 7: below fp64 rounding of a K = 1024 product).
  *   Q        : int8 [rows, nslices*K], plane p at columns [p*K, (p+1)*K); 16-byte aligned, ldq multiple of 16
  *   scale    : fp64 [rows], 2^e_i (NaN for a row holding NaN/Inf -> NaN output, JAX semantics)
- *   K        : multiple of 128, and nslices * K * 4096 < 2^31 (int32 headroom of the deepest order; GPB_ERR_UNSUPPORTED beyond --
+ *   K        : multiple of 128, and nslices * K * 16384 < 2^31 (int32 headroom of the deepest order; GPB_ERR_UNSUPPORTED beyond --
  *              callers split K, as the SGPR statistics do for K = 65,536)
  * gpb_igemm_i8 exposes the raw integer product (C int32 = A B^T) for bit-exact testing.
- * gpb_set_ozaki_slices(s): s in {-1 (auto, default), 0, 5..8}; 0 keeps every blocked algorithm on the FP64 DMMA pipe, otherwise
+ * gpb_set_ozaki_slices(s): s in {-1 (auto, default), 0, 4..7}; 0 keeps every blocked algorithm on the FP64 DMMA pipe, otherwise
  * the rank-NB trailing updates (>= 2048 output rows) of potrf / trtri / lauum run through gpb_ozaki_gemm, and the two streamed
- * products of gpb_sgpr_stats(_raw) / gpb_sgpr_grad_local (blocks of >= 2048 rows, M >= 256) with 8 planes.
+ * products of gpb_sgpr_stats(_raw) / gpb_sgpr_grad_local (blocks of >= 2048 rows, M >= 256) with all 7 planes (56 bits).
  * Plane count of the exact-GP updates in auto mode -- the conditioning guard -- is decided per call ON THE DEVICE (a one-thread
  * kernel writes it into the workspace, the product kernels read it: no host synchronisation):
- *   gpb_potrf_lower / gpb_potri_lower (a bare matrix, nothing known about it): 8 planes = fp64-rounding-level products;
- *   gpb_mll_forward / gpb_mll_backward: 7 planes iff the hyper-parameters PROVE cond(Sigma) <= 1e7 through
- *     cond(K + s I) <= (N variance + s) / s, s = obs_stddev^2 + jitter  (|k| <= variance), else 8.
- * Measured against the CPU oracle (profiles/r02_cond_sweep_n8192.jsonl): 8 planes equal the FP64 path's own error at every
- * conditioning; 7 planes carry ~5e-17 cond relative error in the gradient (<= 1e-9 under the guard; contract 1e-8).
+ *   gpb_potrf_lower / gpb_potri_lower (a bare matrix, nothing known about it): 7 planes = fp64-rounding-level products;
+ *   gpb_mll_forward / gpb_mll_backward: 6 planes iff the hyper-parameters PROVE cond(Sigma) <= 5e6 through
+ *     cond(K + s I) <= (N variance + s) / s, s = obs_stddev^2 + jitter  (|k| <= variance), else 7.
+ * Measured against the CPU oracle (profiles/r02_cond_sweep_n8192.jsonl, r02_cond_sweep_radix256.jsonl): 56 bits equal the FP64
+ * path's own error at every conditioning; 48 bits carry ~9e-17 cond relative error in the gradient (<= 5e-10 under the guard;
+ * contract 1e-8).
  * gpb_ozaki_auto_planes is the same rule evaluated on host values, for reporting and tests only.
- * Environment variable GPB_OZAKI ("auto", 0, 5..8) sets the initial value of the switch; the switch is an atomic
+ * Environment variable GPB_OZAKI ("auto", 0, 4..7) sets the initial value of the switch; the switch is an atomic
  * process-wide configuration word, not meant to change while calls are in flight. */
 int gpb_ozaki_available(void);
 void gpb_set_ozaki_slices(int nslices);

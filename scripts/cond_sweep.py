@@ -6,7 +6,7 @@ trailing updates go before they leave the 1e-8 contract?
 
 For every (kernel, obs_stddev, lengthscale) cell it records cond_2(Sigma) (eigvalsh), the oracle's own noise floor
 (LU value vs Cholesky value -- two float64 routes to the same number) and, for each arithmetic of the CUDA path
-(`planes` = 0: FP64 DMMA everywhere, 7 / 8: int8 digit planes, "auto": the library default), the relative error of the
+(`planes` = 0: FP64 DMMA everywhere, 5 / 6 / 7: int8 radix-256 digit planes, "auto": the library default), the relative error of the
 value and of every gradient.  Measurement script: its output under profiles/ is what tests/test_gpu_conditioning.py
 and DESIGN section 5 quote.
 """
@@ -40,7 +40,7 @@ def gpu_eval(kind, X, y, ell, var, sn, planes):
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
-    plane_list = [0, 7, 8]
+    plane_list = [0, 5, 6, 7]  # radix-256 digit planes: 40 / 48 / 56 bits below the row maximum
     d = 8
     rng = np.random.default_rng(8192)
     X = rng.uniform(-2.0, 2.0, (n, d))

@@ -1,3 +1,4 @@
+#include <cstdlib>
 // HOST MODEL of gpjax_b200/csrc/primitives.h -- TEST INFRASTRUCTURE ONLY.
 //
 // Plain C++ loops with the same argument semantics as the CUDA launchers, operating on host
@@ -459,10 +460,17 @@ int sgpr_scalar_grads(stream_t, const double* sc, const double* dots, const doub
 
 // ---- Ozaki (int8 digit plane) primitives: exact integer model of ozaki_i8.cu ------------------------------------
 namespace gpb {
+static bool getenv_no_diag() { static const bool v = std::getenv("HOSTSIM_NO_DIAG") != nullptr; return v; }
+static int oz_row_exponent_host(double mx) {
+    int e = std::ilogb(mx) + 2;
+    if (std::scalbn(mx, -e) > 0.494) ++e;
+    return e;
+}
 int ozaki_slice(stream_t, int64_t rows, int64_t k, int64_t kplane, const double* X, int64_t ldx, int nslices, int8_t* Q,
-                int64_t ldq, double* scale) {
-    if (rows < 0 || k <= 0 || kplane < k || nslices < 1 || nslices > 8 || !X || !Q || !scale || ldq < (int64_t)nslices * kplane)
+                int64_t ldq, double* scale, const int* nslices_dev) {
+    if (rows < 0 || k <= 0 || kplane < k || nslices < 1 || nslices > OZ_PLANES_MAX || !X || !Q || !scale || ldq < (int64_t)nslices * kplane)
         return GPB_ERR_INVALID;
+    if (nslices_dev) nslices = std::min(std::max(nslices_dev[0], 1), nslices);
     for (int64_t r = 0; r < rows; ++r) {
         double mx = 0.0;
         bool bad = false;
@@ -474,22 +482,23 @@ int ozaki_slice(stream_t, int64_t rows, int64_t k, int64_t kplane, const double*
         int e = 0;
         if (bad) scale[r] = std::numeric_limits<double>::quiet_NaN();
         else if (mx == 0.0) scale[r] = 1.0;
-        else { e = std::ilogb(mx) + 2; scale[r] = std::scalbn(1.0, e); }
+        else { e = oz_row_exponent_host(mx); scale[r] = std::scalbn(1.0, e); }
         for (int64_t c = 0; c < kplane; ++c) {
-            double R = (bad || c >= k) ? 0.0 : std::scalbn(X[r * ldx + c], -e);
-            for (int p = 0; p < nslices; ++p) {
-                R *= 128.0;
-                double d = std::nearbyint(R);
-                Q[r * ldq + (int64_t)p * kplane + c] = (int8_t)(int)d;
-                R -= d;
+            const double R = (bad || c >= k) ? 0.0 : std::scalbn(X[r * ldx + c], -e);
+            long long I = std::llrint(std::scalbn(R, OZ_DIGIT_BITS * nslices));
+            for (int p = nslices - 1; p >= 0; --p) {
+                const int d = (int)((I + 128) & 255) - 128;
+                Q[r * ldq + (int64_t)p * kplane + c] = (int8_t)d;
+                I = (I - d) >> 8;
             }
+            if (I != 0) return GPB_ERR_INVALID;  // the exponent rule keeps the top digit inside int8
         }
     }
     return GPB_OK;
 }
 int ozaki_slice_t(stream_t, int64_t rows, int64_t cols, int64_t kplane, const double* X, int64_t ldx, int nslices, int8_t* Qt,
                   int64_t ldq, double* scale, double* colmax_scratch) {
-    if (rows <= 0 || cols <= 0 || kplane < rows || kplane % 128 || nslices < 1 || nslices > 8 || !X || !Qt || !scale || !colmax_scratch ||
+    if (rows <= 0 || cols <= 0 || kplane < rows || kplane % 128 || nslices < 1 || nslices > OZ_PLANES_MAX || !X || !Qt || !scale || !colmax_scratch ||
         ldq < (int64_t)nslices * kplane)
         return GPB_ERR_INVALID;
     for (int64_t c = 0; c < cols; ++c) {
@@ -504,15 +513,16 @@ int ozaki_slice_t(stream_t, int64_t rows, int64_t cols, int64_t kplane, const do
         int e = 0;
         if (bad) scale[c] = std::numeric_limits<double>::quiet_NaN();
         else if (mx == 0.0) scale[c] = 1.0;
-        else { e = std::ilogb(mx) + 2; scale[c] = std::scalbn(1.0, e); }
+        else { e = oz_row_exponent_host(mx); scale[c] = std::scalbn(1.0, e); }
         for (int64_t r = 0; r < kplane; ++r) {
-            double R = (bad || r >= rows) ? 0.0 : std::scalbn(X[r * ldx + c], -e);
-            for (int p = 0; p < nslices; ++p) {
-                R *= 128.0;
-                double d = std::nearbyint(R);
-                Qt[c * ldq + (int64_t)p * kplane + r] = (int8_t)(int)d;
-                R -= d;
+            const double R = (bad || r >= rows) ? 0.0 : std::scalbn(X[r * ldx + c], -e);
+            long long I = std::llrint(std::scalbn(R, OZ_DIGIT_BITS * nslices));
+            for (int p = nslices - 1; p >= 0; --p) {
+                const int d = (int)((I + 128) & 255) - 128;
+                Qt[c * ldq + (int64_t)p * kplane + r] = (int8_t)d;
+                I = (I - d) >> 8;
             }
+            if (I != 0) return GPB_ERR_INVALID;
         }
     }
     return GPB_OK;
@@ -529,29 +539,52 @@ int col_weighted_sums(stream_t, int64_t rows, int64_t cols, const double* X, int
     return GPB_OK;
 }
 int ozaki_gemm(stream_t, const OzakiGemmDesc& d) {
-    if (d.M < 0 || d.N < 0 || d.K <= 0 || d.nslices < 1 || d.nslices > 8 || !d.Qa || !d.Qb || !d.sa || !d.sb || !d.C)
+    if (d.M < 0 || d.N < 0 || d.K <= 0 || d.nslices < 1 || d.nslices > OZ_PLANES_MAX || !d.Qa || !d.Qb || !d.sa || !d.sb || !d.C)
         return GPB_ERR_INVALID;
-    if (d.K % 128) return GPB_ERR_UNSUPPORTED;
+    if (d.K % 128 || (int64_t)d.nslices * d.K * OZ_DIGIT_SQ_MAX >= (1ll << 31)) return GPB_ERR_UNSUPPORTED;
+    if (d.mask == MASK_BLOCK_UPPER_DIAG_TO_C2 && (!d.C2 || d.mask_nb <= 0 || d.mask_nb % 128 || d.mask_col0 % 128)) return GPB_ERR_INVALID;
+    const int planes = d.nslices_dev ? std::min(std::max(d.nslices_dev[0], 1), d.nslices) : d.nslices;
+    const int64_t ps = d.plane_stride > 0 ? d.plane_stride : d.K;
     for (int64_t i = 0; i < d.M; ++i)
         for (int64_t j = 0; j < d.N; ++j) {
-            if (d.mask == MASK_LOWER && d.mask_row0 + i < d.mask_col0 + j) continue;
-            if (d.mask == MASK_BLOCK_STRICT_UPPER && !((d.mask_row0 + i) / d.mask_nb < (d.mask_col0 + j) / d.mask_nb)) continue;
+            const int64_t gr = d.mask_row0 + i, gc = d.mask_col0 + j;
+            if (d.mask == MASK_LOWER && gr < gc) continue;
+            if (d.mask == MASK_BLOCK_STRICT_UPPER && !(gr / d.mask_nb < gc / d.mask_nb)) continue;
+            if (d.mask == MASK_BLOCK_UPPER_DIAG_TO_C2 && !(gr / d.mask_nb <= gc / d.mask_nb)) continue;
+            // triangular operand: the kernel skips whole 128-digit K-blocks of structural zeros; the digits there ARE zero, so the
+            // model may sum the full range -- but it must not read garbage, hence the same element-level range as GemmDesc::krange
+            int64_t c0 = 0, c1 = d.K;
+            if (d.krange == KR_B_LOWER) c1 = std::min<int64_t>(d.K, std::max<int64_t>(0, j + d.kr_off + 1));
+            else if (d.krange == KR_B_UPPER) c0 = std::min<int64_t>(d.K, std::max<int64_t>(0, j + d.kr_off));
+            else if (d.krange == KR_A_LOWER) c1 = std::min<int64_t>(d.K, std::max<int64_t>(0, i + d.kr_off + 1));
+            else if (d.krange == KR_A_UPPER) c0 = std::min<int64_t>(d.K, std::max<int64_t>(0, i + d.kr_off));
             double acc = 0.0;
-            const int planes = d.nslices_dev ? std::min(std::max(d.nslices_dev[0], 1), d.nslices) : d.nslices;
             for (int t = 0; t < planes; ++t) {
                 int64_t P = 0;
-                const int64_t ps = d.plane_stride > 0 ? d.plane_stride : d.K;
                 for (int p = 0; p <= t; ++p) {
                     const int8_t* a = d.Qa + i * d.ldqa + (int64_t)p * ps;
                     const int8_t* b = d.Qb + j * d.ldqb + (int64_t)(t - p) * ps;
                     int32_t part = 0;
-                    for (int64_t c = 0; c < d.K; ++c) part += (int32_t)a[c] * (int32_t)b[c];
+                    for (int64_t c = c0; c < c1; ++c) part += (int32_t)a[c] * (int32_t)b[c];
                     P += part;
                 }
-                acc = std::fma((double)P, std::scalbn(1.0, -7 * (t + 2)), acc);
+                acc = std::fma((double)P, std::scalbn(1.0, -OZ_DIGIT_BITS * (t + 2)), acc);
+            }
+            if (planes % 2 == 0 && !getenv_no_diag()) {  // even plane count: the one order-`planes` pair of EQUAL planes (see ozaki_i8.cu: coherent term)
+                const int h = planes / 2;
+                const int8_t* a = d.Qa + i * d.ldqa + (int64_t)h * ps;
+                const int8_t* b = d.Qb + j * d.ldqb + (int64_t)h * ps;
+                int32_t part = 0;
+                for (int64_t c = c0; c < c1; ++c) part += (int32_t)a[c] * (int32_t)b[c];
+                acc = std::fma((double)part, std::scalbn(1.0, -OZ_DIGIT_BITS * (planes + 2)), acc);
             }
             const double v = acc * (d.alpha * d.sa[i] * d.sb[j]);
-            d.C[i * d.ldc + j] = d.beta0 ? v : d.C[i * d.ldc + j] + v;
+            double* dst = &d.C[i * d.ldc + j];
+            if (d.mask == MASK_BLOCK_UPPER_DIAG_TO_C2 && gr / d.mask_nb == gc / d.mask_nb) {
+                const int64_t b = gr / d.mask_nb;
+                dst = d.C2 + b * d.mask_nb * d.mask_nb + (gr - b * d.mask_nb) * d.mask_nb + (gc - b * d.mask_nb);
+            }
+            *dst = d.beta0 ? v : *dst + v;
         }
     return GPB_OK;
 }
@@ -566,15 +599,16 @@ int igemm_i8(stream_t, int64_t m, int64_t n, int64_t k, const int8_t* A, int64_t
     return GPB_OK;
 }
 bool ozaki_available() { return true; }
+bool ozaki_supports_extensions() { return true; }
 int ozaki_auto_planes_host(int64_t N, double variance, double obs_stddev, double jitter) {
     const double s = obs_stddev * obs_stddev + jitter;
-    return ((double)N * std::fabs(variance) + s) / s <= OZ_AUTO_COND_LIMIT ? 7 : 8;
+    return ((double)N * std::fabs(variance) + s) / s <= OZ_AUTO_COND_LIMIT ? OZ_AUTO_PLANES_LO : OZ_AUTO_PLANES_HI;
 }
 int ozaki_choose_planes(stream_t, int requested, int64_t N, const double* variance, const double* obs_stddev, double jitter,
                         int* planes_out) {
-    if (!planes_out || N < 0 || !(requested == OZ_AUTO || (requested >= 1 && requested <= 8))) return GPB_ERR_INVALID;
+    if (!planes_out || N < 0 || !(requested == OZ_AUTO || (requested >= 1 && requested <= OZ_PLANES_MAX))) return GPB_ERR_INVALID;
     if (requested != OZ_AUTO) planes_out[0] = requested;
-    else planes_out[0] = (variance && obs_stddev) ? ozaki_auto_planes_host(N, variance[0], obs_stddev[0], jitter) : 8;
+    else planes_out[0] = (variance && obs_stddev) ? ozaki_auto_planes_host(N, variance[0], obs_stddev[0], jitter) : OZ_AUTO_PLANES_HI;
     return GPB_OK;
 }
 }  // namespace gpb
