@@ -63,10 +63,11 @@ int gpb_potrf_lower(void* stream, int64_t N, double* A, int64_t lda, int zero_up
     FactorWs w;
     int rc = carve(ws, ws_bytes, ws_n, ws_d, ws_potri, &w);
     if (rc) return rc;
-    if ((rc = factor_set_planes(stream, w, N, nullptr, nullptr, 0.0))) return rc;  // bare matrix: 8 planes unless forced
+    if ((rc = factor_set_planes(stream, w, N, nullptr, nullptr, 0.0))) return rc;  // bare matrix: 7 planes unless forced
+    if ((zero_upper & 2) && (rc = symmetrize_average_lower(stream, N, A, lda))) return rc;
     rc = potrf_lower(stream, N, A, lda, w, info);
     if (rc) return rc;
-    if (zero_upper) return zero_triangle(stream, N, A, lda, 2);
+    if (zero_upper & 1) return zero_triangle(stream, N, A, lda, 2);
     return GPB_OK;
 }
 

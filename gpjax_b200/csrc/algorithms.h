@@ -21,14 +21,15 @@ inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 // ---- process-wide switch: arithmetic of the rank-NB trailing updates (>= OZ_MIN_ROWS output rows) ------------------------
 //   OZ_AUTO (-1, default): int8 digit planes on tcgen05 (balanced radix-256 digits, 8 bits per plane), plane count decided per
 //                          call ON THE DEVICE by ozaki_choose_planes: the fused objectives use 6 planes (48 bits) only when the
-//                          hyper-parameters bound cond(Sigma) by 5e6, else 7 (56 bits);
+//                          hyper-parameters bound cond(Sigma) by 2e6, else 7 (56 bits);
 //                          a bare matrix (gpb_potrf_lower / gpb_potri_lower: nothing known about it) always gets 7;
 //   4..7                 : that many planes everywhere (measurement / opt-in);
 //   0                    : FP64 DMMA everywhere (also switches the SGPR / SVGP int8 products off).
 // Why 7 unless proven benign (profiles/r02_cond_sweep_n8192.jsonl + r02_cond_sweep_radix256.jsonl, tests/test_gpu_conditioning.py,
 // N = 8192, cond 1e3 .. 3e8): 56 bits below the row maximum are indistinguishable from the FP64 DMMA path against the CPU oracle
-// at every conditioning, and the triangular solves agree element-wise to 2e-10; 48-49 bits sit 10-50x above the DMMA path's
-// error (~5e-17 .. 9e-17 cond relative in the gradient) and ~3e-8 element-wise in the solves.
+// at every conditioning, and the triangular solves agree element-wise to 2e-10; 48 bits (+ the equal-plane term) sit 10-300x
+// above the DMMA path's error: at most 1.4e-15 x (the guard's bound) relative in the most sensitive gradient, ~3e-8 element-wise
+// in the solves.
 // Read from the environment variable GPB_OZAKI ("auto", 0, 4..7) at first use, overridable through set_ozaki_slices; the
 // value is a std::atomic configuration word -- it is not meant to change while calls are in flight.
 #ifndef GPB_OZ_DEFAULT

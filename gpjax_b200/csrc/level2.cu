@@ -128,6 +128,23 @@ __global__ void symmetrize_kernel(int64_t n, double* __restrict__ A, int64_t lda
     }
 }
 
+// lower triangle <- (A + A^T) / 2 (what jnp.linalg.cholesky does to its input before factorising: symmetrize_input=True);
+// tile (bi, bj), bi >= bj: the mirrored upper tile is read row-wise and transposed through shared memory
+__global__ void sym_average_lower_kernel(int64_t n, double* __restrict__ A, int64_t lda) {
+    __shared__ double t[32][33];
+    const int64_t bi = blockIdx.y, bj = blockIdx.x;
+    if (bj > bi) return;
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {  // upper tile (bj, bi)
+        const int64_t r = bj * 32 + k, c = bi * 32 + threadIdx.x;
+        if (r < n && c < n) t[k][threadIdx.x] = A[r * lda + c];
+    }
+    __syncthreads();
+    for (int k = threadIdx.y; k < 32; k += blockDim.y) {  // lower tile (bi, bj)
+        const int64_t r = bi * 32 + k, c = bj * 32 + threadIdx.x;
+        if (r < n && c < r) A[r * lda + c] = 0.5 * (A[r * lda + c] + t[threadIdx.x][k]);
+    }
+}
+
 __global__ void mll_value_kernel(int64_t n, const double* half_logdet, const double* quad, const int* info,
                                  double* out) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -208,6 +225,14 @@ int symmetrize(stream_t s, int64_t n, double* A, int64_t lda, int from_lower) {
     if (n <= 0) return GPB_OK;
     unsigned t = (unsigned)((n + 31) / 32);
     symmetrize_kernel<<<dim3(t, t), dim3(32, 8), 0, to_stream(s)>>>(n, A, lda, from_lower);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+int symmetrize_average_lower(stream_t s, int64_t n, double* A, int64_t lda) {
+    if (n <= 0) return GPB_OK;
+    unsigned t = (unsigned)((n + 31) / 32);
+    sym_average_lower_kernel<<<dim3(t, t), dim3(32, 8), 0, to_stream(s)>>>(n, A, lda);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
 }

@@ -82,7 +82,22 @@ struct OzParams {
     int bm;               // output tile height the walk enumerates (128: v1 / v2; 256: v3, one tile per CTA pair)
     const int* planes_dev;  // optional device word overriding nslices (1..nslices): the conditioning guard, read in-kernel
     int max_ctas;         // > 0: launch at most this many CTAs (SMs left free for a concurrent look-ahead chain)
+    int fx_bits;          // v4: fractional bits F of the int64 fixed-point recombination (see oz_fx_bits)
+    int use_red;          // v4: C += v through red.global.add.f64 (no load in the epilogue); 0: load / add / store
 };
+// v4 recombines the orders EXACTLY in a 64-bit integer instead of an fp64 FMA chain: acc = sum_t P_t 2^(F - 8 t), one unit =
+// 2^(-F - 16) 2^(ea + eb).  |P_t| <= (t + 1) K 2^14, so order 0 dominates and F = 61 - ceil(log2(K 2^14)) keeps |acc| < 2^62; orders
+// with 8 t > F are rounded to the unit (2^-54 of the scale product at K = 1024: below the fp64 rounding of the result).  Why: the
+// plain FP64 pipe of sm_100 issues one warp instruction per ~16 clk per scheduler (measured: profiles/r02_ozaki_epilogue.md), the
+// 2 x 7 DADD / DFMA per output of the FMA chain made the EPILOGUE the pacing role (the MMA warp waited for a free accumulator 45 %
+// of the time); IMAD.WIDE does the same accumulation on the integer pipe in one instruction per order.
+__host__ __device__ __forceinline__ int oz_fx_bits(long long K) {
+    int lg = 0;
+    while ((1ll << lg) < K * OZ_DIGIT_SQ_MAX) ++lg;
+    int F = 61 - lg;
+    if ((F & 7) == 7) --F;  // no order may need the multiplier 2^31 (not an int32)
+    return F;
+}
 // planes actually used by this launch (uniform across the grid: every role of every CTA reads the same word)
 __device__ __forceinline__ int oz_groups(const OzParams& p, int mode) {
     if (mode == 0) return 1;
@@ -1068,6 +1083,48 @@ constexpr int W4_SMEM_BYTES = W4_RING * W4_SLOT_BYTES + 1024 /*align slack*/ + 2
 constexpr unsigned W4_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(256 >> 3) << 17) | ((unsigned)(C2_BM >> 4) << 24);
 static_assert(W4_SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
 
+// write-out of one thread's 64 fixed-point sums: exact int64 -> fp64 (two exact halves, ONE rounding), scaled by
+// alpha 2^(ea + eb - F - 16), then C (+)= v -- through red.global.add.f64 when p.use_red: every output entry receives exactly one
+// add per launch from exactly one thread, so the result is deterministic and no epilogue warp ever waits for a load of C
+__device__ __forceinline__ void oz_store_row_fx(const OzParams& p, const long long (&accq)[64], int row, int col0) {
+    const double sr = p.alpha * __ldg(p.sa + row) * __hiloint2double((1023 - p.fx_bits - 2 * OZ_BETA) << 20, 0);
+    const long long grow = p.row0 + row;
+    double* crow = p.C + (long long)row * p.ldc;  // indexed by the local column
+    long long cshift = 0;
+    bool diag_blk = false;
+    if (p.mask == 3) {  // a 64-column slab lies inside one column block (mask_nb is a multiple of 128)
+        const long long rb = grow / p.mask_nb, cb = (p.col0 + col0) / p.mask_nb;
+        diag_blk = rb == cb;
+        if (diag_blk) {  // dense diagonal block rb of C2, addressed by (row, column) inside the block
+            crow = p.C2 + rb * p.mask_nb * p.mask_nb + (grow - rb * p.mask_nb) * p.mask_nb;
+            cshift = p.col0 - cb * p.mask_nb;
+        }
+    }
+    // live column range of this row inside the slab (all masks are intervals in the column index)
+    int jlo = 0, jhi = p.n - col0 < 64 ? p.n - col0 : 64;
+    if (p.mask == 1) {
+        const long long last = grow - p.col0 - col0;  // col <= grow - col0
+        jhi = last + 1 < jhi ? (int)(last + 1 < 0 ? 0 : last + 1) : jhi;
+    } else if ((p.mask == 2 || p.mask == 3) && !diag_blk) {
+        const long long first = (grow / p.mask_nb + 1) * p.mask_nb - p.col0 - col0;  // first column of the next block
+        jlo = first > 0 ? (first < 64 ? (int)first : 64) : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        if (j >= jlo && j < jhi) {
+            const int hi = (int)(accq[j] >> 32);
+            const unsigned lo = (unsigned)accq[j];
+            const double dh = __hiloint2double(0x43300000, (int)((unsigned)hi ^ 0x80000000u)) - 4503601774854144.0;  // exact
+            const double dl = __hiloint2double(0x43300000, (int)lo) - 4503599627370496.0;                           // exact
+            const double v = fma(dh, 4294967296.0, dl) * (sr * __ldg(p.sb + col0 + j));
+            double* dst = crow + col0 + j + cshift;
+            if (p.beta0) *dst = v;
+            else if (p.use_red) asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(dst), "d"(v) : "memory");
+            else *dst += v;
+        }
+    }
+}
+
 // Order groups of one output tile, enumerated identically by the three roles.  `cursor` runs over the orders t = 0..groups-1:
 // a WIDE group covers the order pair (t, t+1) when (groups - t) is even (an odd plane count runs order 0 alone as a single-order
 // group).  After the last order an EVEN plane count appends the DIAGONAL group: the one product A_h B_h^T, h = groups / 2, of
@@ -1235,25 +1292,36 @@ ozaki_i8_kernel_w4(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (long long idx = pair; w.seek(p, idx, tm, tn); idx += npairs) {
             const int row = tm * C2_BM + (int)rank * OZ_BM + q * 32 + lane;
             const int col0 = tn * OZ_BN + h * 64;
-            double accd[MODE == 1 ? 64 : 1];
+            long long accq[MODE == 1 ? 64 : 1];  // exact fixed-point running sums (see oz_fx_bits)
             if (MODE == 1) {
 #pragma unroll
-                for (int j = 0; j < 64; ++j) accd[j] = 0.0;
+                for (int j = 0; j < 64; ++j) accq[j] = 0;
             }
             OzGroup g;
             for (int cursor = 0; oz_next_group(groups, cursor, g);) {
                 mbar_wait_bounded(&tfull[acc], aphase);
                 tc_fence_after();
                 for (int o = 0; o < g.norders; ++o) {
-                    const double sc = __hiloint2double((1023 - OZ_BETA * (g.t + o + 2)) << 20, 0);  // 2^(-8 (order + 2))
+                    const int sh = p.fx_bits - OZ_BETA * (g.t + o);  // weight 2^sh of this order (warp-uniform)
                     const unsigned tcol = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(acc * 256 + o * 128 + h * 64);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         unsigned r[16];
                         tc_ld16(tcol + (unsigned)(c * 16), r);
                         if (MODE == 1) {
+                            if (sh >= 32) {  // order 0: lands in the high word
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) accd[c * 16 + j] = fma(exact_i2d((int)r[j]), sc, accd[c * 16 + j]);
+                                for (int j = 0; j < 16; ++j)
+                                    accq[c * 16 + j] += (long long)((unsigned long long)(unsigned)((int)r[j] << (sh - 32)) << 32);
+                            } else if (sh >= 0) {  // one IMAD.WIDE per value
+                                const int mul = 1 << sh;
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) accq[c * 16 + j] += (long long)(int)r[j] * (long long)mul;
+                            } else {  // below the unit: round to nearest
+                                const int rs = -sh, half = 1 << (rs - 1);
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) accq[c * 16 + j] += (long long)(((int)r[j] + half) >> rs);
+                            }
                         } else {
                             if (row < p.m) {
                                 int* dst = p.Ci + (long long)row * p.ldci + col0 + c * 16;
@@ -1270,7 +1338,7 @@ ozaki_i8_kernel_w4(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 if (++acc == W4_ACC) { acc = 0; aphase ^= 1u; }
             }
             if constexpr (MODE == 1) {
-                if (row < p.m) oz_store_row(p, accd, row, col0);
+                if (row < p.m) oz_store_row_fx(p, accq, row, col0);
             }
         }
     }
@@ -1529,6 +1597,9 @@ int launch(stream_t s, const void* A, int64_t rowsA, int64_t lda, const void* B,
     {
         static int noload = [] { const char* e = std::getenv("GPB_OZ_NOLOAD"); return (e && std::atoi(e) == 1) ? 1 : 0; }();
         p.noload = noload;
+        static int red = [] { const char* e = std::getenv("GPB_OZ_RED"); return (e && std::atoi(e) == 0) ? 0 : 1; }();
+        p.use_red = red;
+        p.fx_bits = oz_fx_bits((long long)p.kblocks * OZ_BK);
     }
     CUtensorMap ta, tb;
     int rc = make_map(&ta, A, rowsA, width, lda, OZ_BM);

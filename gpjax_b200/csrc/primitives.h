@@ -138,6 +138,8 @@ int fill2d(stream_t s, int64_t rows, int64_t cols, double* p, int64_t ld, double
 int zero_triangle(stream_t s, int64_t n, double* A, int64_t lda, int uplo);
 // mirror: A[c,r] = A[r,c] for r > c (from_lower=1) or A[r,c] = A[c,r] for r > c (from_lower=0)
 int symmetrize(stream_t s, int64_t n, double* A, int64_t lda, int from_lower);
+// lower triangle <- (A + A^T) / 2, strict upper untouched (jnp.linalg.cholesky symmetrises its input first)
+int symmetrize_average_lower(stream_t s, int64_t n, double* A, int64_t lda);
 
 // out[0] = -0.5*(n*log(2*pi) + 2*half_logdet[0] + quad[0]); NaN if *info != 0.
 int mll_value(stream_t s, int64_t n, const double* half_logdet, const double* quad, const int* info,
@@ -311,13 +313,13 @@ bool ozaki_supports_extensions();
 //                               cond(K + s I) <= (N * variance + s) / s,  s = obs_stddev^2 + jitter   (|k(x,y)| <= variance =>
 //                               lambda_max(K) <= N variance by Gershgorin; lambda_min(Sigma) >= s);
 //                               variance == nullptr (a bare matrix, nothing known about it) -> 7.
-// Calibration (profiles/r02_cond_sweep_n8192.jsonl, radix-128 digits: 8 planes = 56 bits, 7 planes = 49 bits): 56 bits = the FP64
-// DMMA path's own error level at every cond; 49 bits ~ 5e-17 * cond relative error in the MLL gradient.  Six radix-256 planes
-// (48 bits, dropped orders 7 * 2^-50 vs 8 * 2^-51) are 1.75x coarser: ~ 9e-17 * cond, i.e. <= 5e-10 while cond <= 5e6
-// (re-measured in profiles/r02_cond_sweep_radix256.jsonl).
+// Calibration (profiles/r02_cond_sweep_radix256.jsonl, N = 8192, 24 cells, cond 1e3 .. 3e8): 7 planes (56 bits) sit at the FP64 DMMA
+// path's own error level at every cond; 6 planes (48 bits + the equal-plane term) carry at most 1.4e-15 * BOUND relative error in the
+// most sensitive output (the mean-constant gradient 1^T Sigma^-1 (y - m) of a very smooth kernel), i.e. <= 2.8e-9 under the guard
+// (contract 1e-8); BOUND over-estimates cond(Sigma) by 3x in that cell and by 10-300x in the others.
 constexpr int OZ_AUTO = -1;
 constexpr int OZ_AUTO_PLANES_LO = 6, OZ_AUTO_PLANES_HI = 7;
-constexpr double OZ_AUTO_COND_LIMIT = 5e6;
+constexpr double OZ_AUTO_COND_LIMIT = 2e6;
 int ozaki_choose_planes(stream_t s, int requested, int64_t N, const double* variance, const double* obs_stddev, double jitter,
                         int* planes_out);
 // the same rule on the host, for reporting (bench.py) and tests; never used to steer a launch

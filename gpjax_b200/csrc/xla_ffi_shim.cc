@@ -88,7 +88,7 @@ static ffi::Error PotrfImpl(cudaStream_t stream, F64 A, ffi::Result<F64> L, ffi:
     const int64_t N = A.dimensions()[0];
     GPB_RETURN_IF_ERROR(adopt(stream, A, L));
     cudaMemsetAsync(info->typed_data(), 0, sizeof(int32_t), stream);
-    return to_error(gpb_potrf_lower(stream, N, L->typed_data(), N, 1, ws->typed_data(), (int64_t)ws->size_bytes(), N, 1, with_potri,
+    return to_error(gpb_potrf_lower(stream, N, L->typed_data(), N, 3 /* zero upper + symmetrize_input */, ws->typed_data(), (int64_t)ws->size_bytes(), N, 1, with_potri,
                                     info->typed_data()),
                     "gpb_potrf_lower");
 }

@@ -19,11 +19,12 @@ from .operators import Dense, Diagonal, Identity, LinearOperator, Triangular
 
 
 def _factor(A: torch.Tensor):
-    """Cholesky of a dense SPD tensor -> (L storage with zero upper, workspace)."""
+    """Cholesky of a dense tensor -> (L storage with zero upper, workspace).  As jnp.linalg.cholesky, the factor is that of
+    (A + A^T) / 2: a Dense that is not exactly symmetric gives the same L as the reference."""
     n = A.shape[0]
     L = A.detach().clone().contiguous()
     ws = ops.FactorWorkspace(n, 1, potri=False, device=A.device)
-    ops.potrf_lower_(L, ws, zero_upper=True)
+    ops.potrf_lower_(L, ws, zero_upper=True, symmetrize=True)
     return L, ws
 
 
@@ -35,7 +36,7 @@ def lower_cholesky(A: LinearOperator) -> LinearOperator:
     if isinstance(A, Triangular):
         if A.lower:
             return A
-        raise ValueError("lower_cholesky of an upper-triangular operator is not defined")
+        return lower_cholesky(Dense(A.to_dense()))  # operations.py:40-43: cholesky of the (symmetrised) dense upper factor
     if isinstance(A, Dense):
         if A.array.requires_grad and torch.is_grad_enabled():
             return Triangular(ops.CholeskyFunction.apply(A.array.contiguous()), lower=True)

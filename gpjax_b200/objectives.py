@@ -31,10 +31,15 @@ def _kernel_args(kernel):
     """(kind, lengthscale, [variance(, shape)]) of a kernel with a fused epilogue."""
     if getattr(kernel, "_b200_kind", None) is None:
         raise NotImplementedError(
-            f"{type(kernel).__name__}: the fused sparse objectives take a single stationary kernel with a fused "
-            "sm_100a epilogue (sum / product kernels are supported by conjugate_mll and conjugate_loocv only)"
+            f"{type(kernel).__name__}: the fused objectives take a single stationary kernel with a fused sm_100a epilogue"
         )
     return kernel._b200_kind, kernel.lengthscale.value, kernel.kernel_scalars()
+
+
+def _dist_world() -> int:
+    import torch.distributed as dist
+
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
 def _is_fused(kernel) -> bool:
@@ -90,6 +95,81 @@ def conjugate_loocv(posterior, data: Dataset) -> torch.Tensor:
     return ops.LoocvFunction.apply(Sigma, d)
 
 
+def _has_fused_sparse_path(kernel) -> bool:
+    """The streamed SGPR / SVGP kernels (csrc/sgpr.cpp) evaluate K_b tiles of ONE stationary kernel whose clamp-free diagonal is
+    its variance.  Sum / product kernels, PoweredExponential (clamped diagonal) and user engines take the composable route."""
+    return _is_fused(kernel) and kernel._b200_kind in sgpr_ops.FUSED_SPARSE_KINDS
+
+
+def _collapsed_elbo_composable(q, data: Dataset) -> torch.Tensor:
+    """objectives.py:342-416 evaluated operation by operation for kernels without a streamed sparse path (sums / products of
+    kernels, PoweredExponential): every matrix product, factorisation and solve is a launch of this library's CUDA kernels
+    (differentiable Gram tiles per part, DMMA GEMM, blocked Cholesky, triangular solves), the graph is torch autograd's.  Dense in
+    N x M -- sized for one GPU's memory, not streamed, not sharded."""
+    from .linalg import Dense, Triangular, lower_cholesky, psd, solve
+
+    x, y = data.X, data.y
+    n = x.shape[0]
+    post = q.posterior
+    kernel, mean_function = post.prior.kernel, post.prior.mean_function
+    m = q.num_inducing
+    sn = post.likelihood.obs_stddev.value.reshape(()).to(x.device)
+    noise = sn * sn
+    z = q.inducing_inputs.value
+    eye = torch.eye(m, dtype=torch.float64, device=x.device)
+    Kzz = kernel.gram(z).to_dense() + float(q.jitter) * eye
+    Kzx = kernel.cross_covariance(z, x)                                   # [m, n]
+    kxx = kernel.diagonal(x).diagonal                                     # k(x_i, x_i)
+    diff = y.reshape(n, 1) - mean_function(x).reshape(n, 1)
+    Lz = lower_cholesky(psd(Dense(Kzz)))
+    A = solve(Lz, Kzx) / sn                                               # Lz^-1 Kzx / sigma
+    AAT = ops.matmul_nt(A, A)                                             # [m, m]
+    L = lower_cholesky(Dense(eye + AAT))
+    log_det_B = 2.0 * torch.sum(torch.log(torch.diagonal(L.to_dense())))
+    Ad = ops.matmul_nt(A, diff.reshape(1, n))                             # A (y - mu)   [m, 1]
+    c = solve(L, Ad)
+    quad = (torch.sum(diff * diff) - torch.sum(c * c)) / noise
+    two_log_prob = -n * torch.log(2.0 * torch.pi * noise) - log_det_B - quad
+    two_trace = torch.sum(kxx) / noise - torch.trace(AAT)
+    return ((two_log_prob - two_trace) / 2.0).reshape(())
+
+
+def _elbo_composable(q, data: Dataset) -> torch.Tensor:
+    """objectives.py:241-318 with the Gaussian likelihood's analytical integrator (integrators.py:151-158) and the moments of
+    variational_families.py:234-285 at the batch points, operation by operation (see _collapsed_elbo_composable)."""
+    from .linalg import Dense, lower_cholesky, psd, solve
+
+    x, y = data.X, data.y
+    n = x.shape[0]
+    post = q.posterior
+    kernel, mean_function = post.prior.kernel, post.prior.mean_function
+    m = q.num_inducing
+    sn = post.likelihood.obs_stddev.value.reshape(()).to(x.device)
+    noise = sn * sn
+    z = q.inducing_inputs.value
+    eye = torch.eye(m, dtype=torch.float64, device=x.device)
+    Lz = lower_cholesky(psd(Dense(kernel.gram(z).to_dense() + float(q.jitter) * eye)))
+    W = torch.tril(q.variational_root_covariance.value)
+    mu_t = (q.variational_mean.value.reshape(m, 1) - mean_function(z).reshape(m, 1))
+    # KL[N(mu, W W^T) || N(mu_z, Kzz)]  (variational_families.py:169-210)
+    LiW = solve(Lz, W)
+    Lim = solve(Lz, mu_t)
+    Lzd = Lz.to_dense()
+    kl = 0.5 * (torch.sum(LiW * LiW) + torch.sum(Lim * Lim) - m
+                + 2.0 * torch.sum(torch.log(torch.diagonal(Lzd))) - 2.0 * torch.sum(torch.log(torch.abs(torch.diagonal(W)))))
+    # moments of q(f(x_i))
+    Kzx = kernel.cross_covariance(z, x)                                   # [m, n]
+    A = solve(Lz, Kzx)                                                    # Lz^-1 Kzx
+    KiK = solve(Lz.T, A)                                                  # Kzz^-1 Kzx
+    R = ops.matmul_nt(KiK, W, a_layout=1, b_layout=1)                     # (Kzz^-1 Kzx)^T W   [n, m]
+    mean = mean_function(x).reshape(n, 1) + ops.matmul_nt(KiK, mu_t.reshape(1, m), a_layout=1)
+    var = kernel.diagonal(x).diagonal - torch.sum(A * A, dim=0) + torch.sum(R * R, dim=1) + float(q.jitter)
+    err = y.reshape(n, 1) - mean
+    expectation = -0.5 * (torch.log(torch.tensor(2.0 * torch.pi, dtype=torch.float64, device=x.device)) + torch.log(noise)
+                          + (err.reshape(-1) ** 2 + var) / noise)
+    return (torch.sum(expectation) * float(post.likelihood.num_datapoints) / n - kl).reshape(())
+
+
 def collapsed_elbo(variational_family, data: Dataset, *, block_rows: int = sgpr_ops.DEFAULT_BLOCK_ROWS,
                    group=None, statistics: str = "auto") -> torch.Tensor:
     """Collapsed (Titsias) evidence lower bound (objectives.py:342-416).
@@ -101,6 +181,10 @@ def collapsed_elbo(variational_family, data: Dataset, *, block_rows: int = sgpr_
     x, y = data.X, data.y
     post = variational_family.posterior
     kernel = post.prior.kernel
+    if not _has_fused_sparse_path(kernel):
+        if group is not None or _dist_world() > 1:
+            raise NotImplementedError("the composable collapsed_elbo (sum / product kernels) is single-GPU: it is not row-sharded")
+        return _collapsed_elbo_composable(variational_family, data)
     kind, ell, var = _kernel_args(kernel)
     xs = kernel.slice_input(x)
     xs = xs if xs.is_contiguous() else xs.contiguous()
@@ -125,6 +209,10 @@ def elbo(variational_family, data: Dataset, *, block_rows: int = sgpr_ops.DEFAUL
     if not isinstance(post.likelihood, Gaussian):
         raise NotImplementedError("the fused ELBO covers the Gaussian likelihood (analytical integrator) only")
     kernel = post.prior.kernel
+    if not _has_fused_sparse_path(kernel):
+        if group is not None or _dist_world() > 1:
+            raise NotImplementedError("the composable elbo (sum / product kernels) is single-GPU: it is not data-parallel")
+        return _elbo_composable(q, data)
     kind, ell, var = _kernel_args(kernel)
     xs = kernel.slice_input(data.X)
     xs = xs if xs.is_contiguous() else xs.contiguous()

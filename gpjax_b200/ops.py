@@ -169,12 +169,15 @@ class FactorWorkspace:
         return _p(self.buf), self.nbytes, self.n, self.d, self.potri
 
 
-def potrf_lower_(A: torch.Tensor, ws: FactorWorkspace, zero_upper: bool = True) -> torch.Tensor:
-    """In-place lower Cholesky of the lower triangle of A.  Returns the device `info` word."""
+def potrf_lower_(A: torch.Tensor, ws: FactorWorkspace, zero_upper: bool = True, symmetrize: bool = False) -> torch.Tensor:
+    """In-place lower Cholesky of the lower triangle of A.  Returns the device `info` word.  ``symmetrize`` first replaces
+    the lower triangle by (A + A^T) / 2, the ``symmetrize_input=True`` default of ``jnp.linalg.cholesky``
+    (gpjax/linalg/operations.py:54-55 calls it on whatever dense array it is given)."""
     _check_mat(A, "A")
     n = A.shape[0]
     info = torch.zeros(1, dtype=torch.int32, device=A.device)
-    rc = lib().gpb_potrf_lower(_stream(), n, _p(A), A.stride(0), int(zero_upper), *ws.args(), _p(info))
+    rc = lib().gpb_potrf_lower(_stream(), n, _p(A), A.stride(0), int(bool(zero_upper)) | (2 if symmetrize else 0), *ws.args(),
+                               _p(info))
     _abi.check(rc, "gpb_potrf_lower")
     return info
 
@@ -255,7 +258,7 @@ def set_ozaki_slices(nslices: int) -> None:
     """Arithmetic of the large rank-NB trailing updates of ``lower_cholesky`` / the inverse (process-wide switch):
     ``OZAKI_AUTO`` (-1, library default): exact int8 digit-plane products (``tcgen05.mma kind::i8``) whose plane count is chosen
     on the device per call -- 7 radix-256 planes (56 bits, fp64-rounding-level) unless the hyper-parameters of a fused
-    objective bound cond(Sigma) by 5e6, then 6; 4..7: that many planes everywhere; 0: FP64 DMMA everywhere.
+    objective bound cond(Sigma) by 2e6, then 6; 4..7: that many planes everywhere; 0: FP64 DMMA everywhere.
     ``GPB_OZAKI`` in the environment sets the initial value."""
     lib().gpb_set_ozaki_slices(int(nslices))
 
@@ -505,7 +508,7 @@ class CholeskyFunction(torch.autograd.Function):
         n = A.shape[0]
         L = A.detach().clone().contiguous()
         ws = FactorWorkspace(n, 1, potri=False, device=A.device)
-        potrf_lower_(L, ws, zero_upper=True)
+        potrf_lower_(L, ws, zero_upper=True, symmetrize=True)
         ctx.ws = ws
         ctx.save_for_backward(L)
         return L
@@ -520,6 +523,37 @@ class CholeskyFunction(torch.autograd.Function):
         Y = trsm_lower_left_(L, P.contiguous(), ws, trans=True)             # L^-T Phi
         St = trsm_lower_left_(L, Y.T.contiguous(), ws, trans=True)          # (Y L^-1)^T
         return 0.5 * (St + St.T)
+
+
+class GemmFunction(torch.autograd.Function):
+    """C = op(A) op(B)^T on the DMMA pipe, differentiable (layout 0: the tensor is [rows, K]; 1: it is [K, rows]) -- the
+    jnp.matmul of the composable objectives.  Backward: d op(A) = G op(B), d op(B) = G^T op(A), two more launches."""
+
+    @staticmethod
+    def forward(ctx, A, B, a_layout, b_layout):
+        ctx.layouts = (int(a_layout), int(b_layout))
+        A, B = A.detach().contiguous(), B.detach().contiguous()
+        ctx.save_for_backward(A, B)
+        return gemm(A, B, a_layout=a_layout, b_layout=b_layout)
+
+    @staticmethod
+    def backward(ctx, G):
+        A, B = ctx.saved_tensors
+        al, bl = ctx.layouts
+        G = G.contiguous()
+        gA = gB = None
+        if ctx.needs_input_grad[0]:
+            gA = gemm(G, B, a_layout=0, b_layout=1 - bl) if al == 0 else gemm(B, G, a_layout=1 - bl, b_layout=0)
+        if ctx.needs_input_grad[1]:
+            gB = gemm(G, A, a_layout=1, b_layout=1 - al) if bl == 0 else gemm(A, G, a_layout=1 - al, b_layout=1)
+        return gA, gB, None, None
+
+
+def matmul_nt(A: torch.Tensor, B: torch.Tensor, a_layout: int = 0, b_layout: int = 0) -> torch.Tensor:
+    """op(A) op(B)^T through GemmFunction when either operand requires grad, else one plain launch."""
+    if torch.is_grad_enabled() and (A.requires_grad or B.requires_grad):
+        return GemmFunction.apply(A, B, a_layout, b_layout)
+    return gemm(A.contiguous(), B.contiguous(), a_layout=a_layout, b_layout=b_layout)
 
 
 class TriangularSolveFunction(torch.autograd.Function):

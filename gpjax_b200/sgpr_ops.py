@@ -18,6 +18,9 @@ from ._lib import lib
 from .ops import _check_mat, _ell_args, _kscalars, _no_data_grad, _p, _scalar, _stream, next_generation, require_cuda
 
 DEFAULT_BLOCK_ROWS = 32768
+# kernel kinds the streamed sparse path evaluates (csrc/sgpr.cpp check_args: every fused stationary kernel except PoweredExponential,
+# whose clamped diagonal k(x, x) != variance)
+FUSED_SPARSE_KINDS = frozenset({0, 1, 2, 3, 4, 6, 7})
 
 
 def _world(group) -> int:

@@ -51,6 +51,10 @@ class CollapsedVariationalGaussian(AbstractVariationalGaussian):
 
         post = self.posterior
         kern = post.prior.kernel
+        from .objectives import _has_fused_sparse_path
+
+        if not _has_fused_sparse_path(kern):
+            return self._predict_composable(test_inputs, train_data)
         kind = kern.compute_engine._kind(kern)
         x = kern.slice_input(train_data.X).contiguous()
         t = kern.slice_input(test_inputs).contiguous()
@@ -93,6 +97,34 @@ class CollapsedVariationalGaussian(AbstractVariationalGaussian):
         return GaussianDistribution(torch.atleast_1d(mu), Dense(cov))
 
 
+    def _predict_composable(self, test_inputs, train_data):
+        """variational_families.py:766-870 operation by operation (sum / product kernels, PoweredExponential): dense in N x M."""
+        from . import ops
+        from .distributions import GaussianDistribution
+        from .linalg import Dense, lower_cholesky, psd, solve
+
+        post = self.posterior
+        kern, mean_fn = post.prior.kernel, post.prior.mean_function
+        x, y, t = train_data.X, train_data.y, test_inputs
+        z = self.inducing_inputs.value
+        n, m, T = x.shape[0], z.shape[0], t.shape[0]
+        sn = post.likelihood.obs_stddev.value.reshape(()).to(x.device)
+        eye = torch.eye(m, dtype=torch.float64, device=x.device)
+        Lz = lower_cholesky(psd(Dense(kern.gram(z).to_dense() + float(self.jitter) * eye)))
+        Kzx = kern.cross_covariance(z, x)
+        A = solve(Lz, Kzx) / sn                                            # Lz^-1 Kzx / sigma
+        L = lower_cholesky(Dense(eye + ops.matmul_nt(A, A)))               # L L^T = I + A A^T
+        diff = (y.reshape(n, 1) - mean_fn(x).reshape(n, 1))
+        Ad = ops.matmul_nt(A, diff.reshape(1, n)) * sn                     # Lz^-1 Kzx (y - mu)
+        v = solve(L.T, solve(L, Ad))                                       # B^-1 Lz^-1 Kzx diff
+        At = solve(Lz, kern.cross_covariance(z, t))                        # Lz^-1 Kzt   [m, T]
+        mean = mean_fn(t).reshape(-1) + ops.matmul_nt(At, (v / (sn * sn)).reshape(1, m), a_layout=1).reshape(-1)
+        LAt = solve(L, At)
+        cov = kern.gram(t).to_dense() - ops.matmul_nt(At, At, a_layout=1, b_layout=1) \
+            + ops.matmul_nt(LAt, LAt, a_layout=1, b_layout=1) + float(self.jitter) * torch.eye(T, dtype=torch.float64, device=x.device)
+        return GaussianDistribution(torch.atleast_1d(mean), Dense(cov))
+
+
 class VariationalGaussian(AbstractVariationalGaussian):
     """q(u) = N(mu, S), S = sqrt sqrt^T (gpjax/variational_families.py:134-285).  `prior_kl` and the
     per-point moments of `predict` are consumed by `gpjax_b200.objectives.elbo`, which evaluates them through
@@ -122,6 +154,10 @@ class VariationalGaussian(AbstractVariationalGaussian):
         from .linalg import Dense
 
         kern = self.posterior.prior.kernel
+        from .objectives import _is_fused
+
+        if not _is_fused(kern):
+            return self._predict_composable(test_inputs)
         kind = kern.compute_engine._kind(kern)
         z = kern.slice_input(self.inducing_inputs.value).contiguous()
         t = kern.slice_input(test_inputs).contiguous()
@@ -141,4 +177,25 @@ class VariationalGaussian(AbstractVariationalGaussian):
         cov = ops.gram_forward(kind, t, t, ell, var, diag_add=self.jitter)
         ops.gemm(A, A, cov, alpha=-1.0, beta=1.0, a_layout=1, b_layout=1)   # - A^T A
         ops.gemm(R, R, cov, alpha=1.0, beta=1.0)                            # + R R^T
+        return GaussianDistribution(torch.atleast_1d(mean), Dense(cov))
+
+    def _predict_composable(self, test_inputs):
+        """variational_families.py:234-285 operation by operation, for kernels assembled from several Gram launches."""
+        from . import ops
+        from .distributions import GaussianDistribution
+        from .linalg import Dense, lower_cholesky, psd, solve
+
+        kern, mean_fn = self.posterior.prior.kernel, self.posterior.prior.mean_function
+        z, t = self.inducing_inputs.value, test_inputs
+        m, T = z.shape[0], t.shape[0]
+        dev = z.device
+        Lz = lower_cholesky(psd(Dense(kern.gram(z).to_dense() + float(self.jitter) * torch.eye(m, dtype=torch.float64, device=dev))))
+        A = solve(Lz, kern.cross_covariance(z, t))                          # Lz^-1 Kzt
+        KiK = solve(Lz.T, A)                                                # Kzz^-1 Kzt
+        W = torch.tril(self.variational_root_covariance.value).contiguous()
+        R = ops.matmul_nt(KiK, W, a_layout=1, b_layout=1)                   # (Kzz^-1 Kzt)^T W
+        mu_t = (self.variational_mean.value.reshape(-1) - mean_fn(z).reshape(-1)).contiguous()
+        mean = mean_fn(t).reshape(-1) + ops.matmul_nt(KiK, mu_t.reshape(1, m), a_layout=1).reshape(-1)
+        cov = kern.gram(t).to_dense() - ops.matmul_nt(A, A, a_layout=1, b_layout=1) + ops.matmul_nt(R, R) \
+            + float(self.jitter) * torch.eye(T, dtype=torch.float64, device=dev)
         return GaussianDistribution(torch.atleast_1d(mean), Dense(cov))

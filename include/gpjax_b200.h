@@ -87,8 +87,10 @@ int gpb_gram_bwd(void* stream, int kind, int64_t N, int64_t M, int D, const doub
 
 /* ---- K2..K5: Cholesky / triangular solves / log-determinant -------------------------------------
  * gpb_potrf_lower  : lower_cholesky(Dense) -> jnp.linalg.cholesky (gpjax/linalg/operations.py:54-55);
- *                    in place, reads the lower triangle only; zero_upper=1 zeroes the strict upper
- *                    triangle as JAX returns it.
+ *                    in place; `zero_upper` is a flag word: bit 0 zeroes the strict upper triangle as JAX returns
+ *                    it, bit 1 first replaces the lower triangle by (A + A^T) / 2 -- jnp.linalg.cholesky's
+ *                    symmetrize_input=True default; without bit 1 only the lower triangle is read (the fused
+ *                    objectives build Sigma symmetric by construction and never set it).
  * gpb_diag_inverses: prepares the workspace for solves against a factor that was not produced by
  *                    gpb_potrf_lower (a user-built Triangular).
  * gpb_trsv_lower / gpb_trsm_lower_left : solve(Triangular, b) -> jsp.linalg.solve_triangular
@@ -134,11 +136,11 @@ int gpb_gemm(void* stream, int64_t M, int64_t N, int64_t K, double alpha, const 
  * Plane count of the exact-GP updates in auto mode -- the conditioning guard -- is decided per call ON THE DEVICE (a one-thread
  * kernel writes it into the workspace, the product kernels read it: no host synchronisation):
  *   gpb_potrf_lower / gpb_potri_lower (a bare matrix, nothing known about it): 7 planes = fp64-rounding-level products;
- *   gpb_mll_forward / gpb_mll_backward: 6 planes iff the hyper-parameters PROVE cond(Sigma) <= 5e6 through
+ *   gpb_mll_forward / gpb_mll_backward: 6 planes iff the hyper-parameters PROVE cond(Sigma) <= 2e6 through
  *     cond(K + s I) <= (N variance + s) / s, s = obs_stddev^2 + jitter  (|k| <= variance), else 7.
  * Measured against the CPU oracle (profiles/r02_cond_sweep_n8192.jsonl, r02_cond_sweep_radix256.jsonl): 56 bits equal the FP64
- * path's own error at every conditioning; 48 bits carry ~9e-17 cond relative error in the gradient (<= 5e-10 under the guard;
- * contract 1e-8).
+ * path's own error at every conditioning; 48 bits carry at most 1.4e-15 x bound relative error in the most sensitive gradient
+ * (<= 2.8e-9 under the guard; contract 1e-8).
  * gpb_ozaki_auto_planes is the same rule evaluated on host values, for reporting and tests only.
  * Environment variable GPB_OZAKI ("auto", 0, 4..7) sets the initial value of the switch; the switch is an atomic
  * process-wide configuration word, not meant to change while calls are in flight. */

@@ -62,13 +62,38 @@ __all__ = [
     "conjugate_loocv",
     "conjugate_loocv_value_and_grad_autodiff",
     "SHAPE_KINDS",
+    "kernel_diagonal",
 ]
 
 
-def _kind_id(kind) -> int:
+def _kind_id(kind):
+    """Kernel selector: a name / integer id of a stationary kernel, or a COMBINATION spec
+    ``("sum" | "prod", [(kind, lengthscale, variance), ...])`` (gpjax/kernels/base.py:246-339: the parts' values are summed /
+    multiplied pair by pair); for a combination the ``lengthscale`` / ``variance`` arguments of the callers are ignored."""
+    if isinstance(kind, tuple):
+        return kind
     if isinstance(kind, str):
         return KINDS[kind.lower()]
     return int(kind)
+
+
+def _combine(kind, fn):
+    op, parts = kind
+    out = None
+    for (k, ell, var) in parts:
+        m = fn(k, ell, var)
+        out = m if out is None else (out + m if op == "sum" else out * m)
+    return out
+
+
+def kernel_diagonal(kind, x, lengthscale, variance) -> np.ndarray:
+    """``vmap(kernel, in_axes=(0, 0))(x, x)`` (objectives.py:356) INCLUDING the 1e-36 distance clamp of utils.py:67, i.e.
+    variance * exp(-(1e-18)^power) for PoweredExponential."""
+    kind = _kind_id(kind)
+    x = np.atleast_2d(np.asarray(x, np.float64))
+    if isinstance(kind, tuple):
+        return _combine(kind, lambda k, ell, var: kernel_diagonal(k, x, ell, var))
+    return np.array([kernel_pair(kind, xi, xi, lengthscale, variance) for xi in x], np.float64)
 
 
 # ----------------------------------------------------------------------------------------
@@ -139,6 +164,8 @@ def cross_covariance(kind, x, z, lengthscale, variance) -> np.ndarray:
     kind = _kind_id(kind)
     x = np.atleast_2d(np.asarray(x, np.float64))
     z = np.atleast_2d(np.asarray(z, np.float64))
+    if isinstance(kind, tuple):
+        return _combine(kind, lambda k, ell, var: cross_covariance(k, x, z, ell, var))
     if kind == 6:
         ell = np.broadcast_to(np.asarray(lengthscale, np.float64), (x.shape[1],))
         r2 = np.zeros((x.shape[0], z.shape[0]), np.float64)
@@ -357,9 +384,7 @@ def collapsed_elbo(kind, X, y, Z, lengthscale, variance, obs_stddev, mean_const=
     noise = obs_stddev**2
     Kzz = add_jitter(gram(kind, Z, lengthscale, variance), jitter)  # :352-354
     Kzx = cross_covariance(kind, Z, X, lengthscale, variance)  # :355
-    Kxx_diag = np.array(
-        [_profile(kind, np.float64(0.0), variance) for _ in range(1)]
-    ).repeat(n)  # :356 (k(x,x) = variance for every stationary kernel here)
+    Kxx_diag = kernel_diagonal(kind, X, lengthscale, variance)  # :356
     mux = np.ones((n, 1)) * mean_const  # :357
     Lz = np.linalg.cholesky(Kzz)  # :359
     A = sla.solve_triangular(Lz, Kzx, lower=True) / np.sqrt(noise)  # :387
@@ -701,7 +726,7 @@ def svgp_elbo(kind, X, y, Z, lengthscale, variance, obs_stddev, mean_const, var_
     Kzz_inv_Kzt = sla.solve_triangular(Lz.T, Lz_inv_Kzt, lower=False)
     Ktz_Kzz_inv_sqrt = Kzz_inv_Kzt.T @ W
     mean = mean_const + Kzz_inv_Kzt.T @ (mu - mean_const)
-    var = variance - np.sum(Lz_inv_Kzt**2, axis=0) + np.sum(Ktz_Kzz_inv_sqrt**2, axis=1) + jitter
+    var = kernel_diagonal(kind, X, lengthscale, variance) - np.sum(Lz_inv_Kzt**2, axis=0) + np.sum(Ktz_Kzz_inv_sqrt**2, axis=1) + jitter
     # integrators.py:151-158
     ell = -0.5 * np.sum(np.log(2.0 * np.pi) + np.log(s) + ((y - mean) ** 2 + var) / s)
     return float(ell * num_datapoints / b - kl)

@@ -274,6 +274,11 @@ int symmetrize(stream_t, int64_t n, double* A, int64_t lda, int from_lower) {
         }
     return GPB_OK;
 }
+int symmetrize_average_lower(stream_t, int64_t n, double* A, int64_t lda) {
+    for (int64_t r = 0; r < n; ++r)
+        for (int64_t c = 0; c < r; ++c) A[r * lda + c] = 0.5 * (A[r * lda + c] + A[c * lda + r]);
+    return GPB_OK;
+}
 int mll_value(stream_t, int64_t n, const double* half_logdet, const double* quad, const int* info, double* out) {
     double v = -0.5 * ((double)n * std::log(2.0 * M_PI) + 2.0 * half_logdet[0] + quad[0]);
     if (info && info[0] != 0) v = std::numeric_limits<double>::quiet_NaN();
@@ -460,7 +465,6 @@ int sgpr_scalar_grads(stream_t, const double* sc, const double* dots, const doub
 
 // ---- Ozaki (int8 digit plane) primitives: exact integer model of ozaki_i8.cu ------------------------------------
 namespace gpb {
-static bool getenv_no_diag() { static const bool v = std::getenv("HOSTSIM_NO_DIAG") != nullptr; return v; }
 static int oz_row_exponent_host(double mx) {
     int e = std::ilogb(mx) + 2;
     if (std::scalbn(mx, -e) > 0.494) ++e;
@@ -558,7 +562,17 @@ int ozaki_gemm(stream_t, const OzakiGemmDesc& d) {
             else if (d.krange == KR_B_UPPER) c0 = std::min<int64_t>(d.K, std::max<int64_t>(0, j + d.kr_off));
             else if (d.krange == KR_A_LOWER) c1 = std::min<int64_t>(d.K, std::max<int64_t>(0, i + d.kr_off + 1));
             else if (d.krange == KR_A_UPPER) c0 = std::min<int64_t>(d.K, std::max<int64_t>(0, i + d.kr_off));
-            double acc = 0.0;
+            // exact int64 fixed-point recombination, as the default kernel (ozaki_i8.cu: oz_fx_bits / oz_store_row_fx)
+            int lg = 0;
+            while ((1ll << lg) < d.K * OZ_DIGIT_SQ_MAX) ++lg;
+            int F = 61 - lg;
+            if ((F & 7) == 7) --F;
+            long long accq = 0;
+            auto add_order = [&](int order, long long P) {
+                const int sh = F - OZ_DIGIT_BITS * order;
+                if (sh >= 0) accq += P * (1ll << sh);
+                else accq += (P + (1ll << (-sh - 1))) >> (-sh);
+            };
             for (int t = 0; t < planes; ++t) {
                 int64_t P = 0;
                 for (int p = 0; p <= t; ++p) {
@@ -568,17 +582,18 @@ int ozaki_gemm(stream_t, const OzakiGemmDesc& d) {
                     for (int64_t c = c0; c < c1; ++c) part += (int32_t)a[c] * (int32_t)b[c];
                     P += part;
                 }
-                acc = std::fma((double)P, std::scalbn(1.0, -OZ_DIGIT_BITS * (t + 2)), acc);
+                add_order(t, P);
             }
-            if (planes % 2 == 0 && !getenv_no_diag()) {  // even plane count: the one order-`planes` pair of EQUAL planes (see ozaki_i8.cu: coherent term)
+            if (planes >= 2 && planes % 2 == 0) {  // even plane count: the one order-`planes` pair of EQUAL planes (oz_has_diag)
                 const int h = planes / 2;
                 const int8_t* a = d.Qa + i * d.ldqa + (int64_t)h * ps;
                 const int8_t* b = d.Qb + j * d.ldqb + (int64_t)h * ps;
                 int32_t part = 0;
                 for (int64_t c = c0; c < c1; ++c) part += (int32_t)a[c] * (int32_t)b[c];
-                acc = std::fma((double)part, std::scalbn(1.0, -OZ_DIGIT_BITS * (planes + 2)), acc);
+                add_order(planes, part);
             }
-            const double v = acc * (d.alpha * d.sa[i] * d.sb[j]);
+            const double sr = d.alpha * d.sa[i] * std::scalbn(1.0, -F - 2 * OZ_DIGIT_BITS);
+            const double v = (double)accq * (sr * d.sb[j]);
             double* dst = &d.C[i * d.ldc + j];
             if (d.mask == MASK_BLOCK_UPPER_DIAG_TO_C2 && gr / d.mask_nb == gc / d.mask_nb) {
                 const int64_t b = gr / d.mask_nb;

@@ -85,6 +85,31 @@ def test_linalg_dispatch(n):
     assert abs(logdet(Diagonal(d)).item() - float(torch.log(d).sum())) < 1e-12
 
 
+@pytest.mark.parametrize("n", [3, 700, 2500])
+def test_lower_cholesky_symmetrises_a_dense_input_like_jnp_cholesky(n):
+    """jnp.linalg.cholesky(symmetrize_input=True) -- what gpjax/linalg/operations.py:54-55 calls -- factors (A + A^T) / 2; an
+    upper Triangular goes through the same dense route (operations.py:40-43)."""
+    from gpjax_b200.linalg import Dense, Triangular, lower_cholesky
+
+    rng = np.random.default_rng(n)
+    X = rng.uniform(-2, 2, (n, 2))
+    S = o.gram("rbf", X, np.array([0.9, 1.1]), 1.0) + 0.3 * np.eye(n)
+    A0 = S + np.triu(1e-3 * rng.standard_normal((n, n)), 1)
+    L = lower_cholesky(Dense(dev(A0))).to_dense().cpu().numpy()
+    ref = np.linalg.cholesky(0.5 * (A0 + A0.T))
+    assert np.max(np.abs(L - ref)) <= 1e-11 * np.abs(ref).max()
+    assert np.max(np.abs(L - np.linalg.cholesky(S))) > 1e-7
+    Ad = dev(A0).requires_grad_(True)  # differentiable route: same factor, symmetric gradient
+    Lg = lower_cholesky(Dense(Ad)).to_dense()
+    assert np.max(np.abs(Lg.detach().cpu().numpy() - ref)) <= 1e-11 * np.abs(ref).max()
+    Lg.sum().backward()
+    assert torch.allclose(Ad.grad, Ad.grad.T)
+    U = Triangular(dev(np.triu(S)), lower=False)
+    Lu = lower_cholesky(U).to_dense().cpu().numpy()
+    Ud = np.triu(S)
+    assert np.max(np.abs(Lu - np.linalg.cholesky(0.5 * (Ud + Ud.T)))) <= 1e-11
+
+
 @pytest.mark.parametrize("kname", list(NAMES))
 @pytest.mark.parametrize("n,d", [(1, 1), (2, 2), (10, 3), (200, 2)])
 def test_conjugate_mll_api(kname, n, d):

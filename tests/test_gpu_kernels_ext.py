@@ -182,15 +182,22 @@ def test_collapsed_elbo_fused(cls, kind, name, skw, sv):
     assert np.max(np.abs(pred.covariance().cpu().numpy() - cref)) <= 1e-8 * max(np.max(np.abs(cref)), 1.0)
 
 
-def test_powered_exponential_is_refused_by_the_sparse_objectives():
+def test_powered_exponential_runs_the_composable_sparse_route():
+    """The streamed SGPR statistics assume k(x, x) = variance; PoweredExponential's clamped diagonal is variance * exp(-(1e-18)^power)
+    (stationary/utils.py:67), visibly smaller for power = 0.5, so it takes the composable route -- and matches the oracle, whose
+    trace term evaluates the kernel at (x, x) pair by pair as objectives.py:356 does."""
     import gpjax_b200 as gpx
 
-    X, y = data(100, 2, 1)
-    k = gpx.kernels.PoweredExponential(power=0.5)
-    post = gpx.gps.Prior(mean_function=gpx.mean_functions.Zero(), kernel=k) * gpx.likelihoods.Gaussian(num_datapoints=100)
-    q = gpx.variational_families.CollapsedVariationalGaussian(posterior=post, inducing_inputs=dev(X[:10]))
-    with pytest.raises((NotImplementedError, RuntimeError)):
-        gpx.objectives.collapsed_elbo(q, gpx.Dataset(X=dev(X), y=dev(y)))
+    n = 300
+    X, y = data(n, 2, 1)
+    k = gpx.kernels.PoweredExponential(lengthscale=[0.9, 1.2], variance=1.3, power=0.5)
+    post = gpx.gps.Prior(mean_function=gpx.mean_functions.Zero(), kernel=k) * gpx.likelihoods.Gaussian(num_datapoints=n, obs_stddev=0.4)
+    q = gpx.variational_families.CollapsedVariationalGaussian(posterior=post, inducing_inputs=dev(X[:20] + 0.01))
+    val = gpx.objectives.collapsed_elbo(q, gpx.Dataset(X=dev(X), y=dev(y)))
+    ref = o.collapsed_elbo("powered_exponential", X, y, X[:20] + 0.01, np.array([0.9, 1.2]), np.array([1.3, 0.5]), 0.4, 0.0)
+    assert abs(val.item() - ref) <= 1e-8 * abs(ref)
+    # had the trace term used k(x, x) = variance, the value would differ by n * variance * (1 - exp(-1e-9)) / (2 sigma^2) ~ 1e-6
+    assert abs(n * 1.3 * (1.0 - math.exp(-1e-9)) / (2 * 0.16)) > 1e-8 * abs(ref)
 
 
 # ---- combination kernels (kernels/base.py:150-339) ---------------------------------------------------------------
@@ -278,17 +285,133 @@ def test_combination_kernels(op):
     assert np.max(np.abs(pred.covariance().cpu().numpy() - cref)) <= 1e-8 * max(np.max(np.abs(cref)), 1.0)
 
 
-def test_combination_rejects_non_kernels_and_sparse_objectives():
+def test_combination_rejects_non_kernels():
     import gpjax_b200 as gpx
 
     with pytest.raises(TypeError):
         gpx.kernels.SumKernel(kernels=[gpx.kernels.RBF(), 3.0])
-    k = gpx.kernels.RBF() + gpx.kernels.Matern52()
-    X, y = data(50, 1, 2)
-    post = gpx.gps.Prior(mean_function=gpx.mean_functions.Zero(), kernel=k) * gpx.likelihoods.Gaussian(num_datapoints=50)
-    q = gpx.variational_families.CollapsedVariationalGaussian(posterior=post, inducing_inputs=dev(X[:5]))
-    with pytest.raises(NotImplementedError):
-        gpx.objectives.collapsed_elbo(q, gpx.Dataset(X=dev(X), y=dev(y)))
+
+
+def _t_collapsed_elbo(Kzz, Kzx, kdiag, diff, sn, jitter):
+    """objectives.py:342-416 in torch-CPU float64 on given matrices (autodiff reference for the combination kernels)."""
+    m, n = Kzx.shape
+    Lz = torch.linalg.cholesky(Kzz + jitter * torch.eye(m, dtype=torch.float64))
+    A = torch.linalg.solve_triangular(Lz, Kzx, upper=False) / sn
+    AAT = A @ A.T
+    L = torch.linalg.cholesky(torch.eye(m, dtype=torch.float64) + AAT)
+    c = torch.linalg.solve_triangular(L, (A @ diff).reshape(-1, 1), upper=False)
+    quad = (torch.sum(diff**2) - torch.sum(c**2)) / sn**2
+    two_log_prob = -n * torch.log(2 * math.pi * sn**2) - 2.0 * torch.sum(torch.log(torch.diagonal(L))) - quad
+    return (two_log_prob - (torch.sum(kdiag) / sn**2 - torch.trace(AAT))) / 2.0
+
+
+def _t_svgp_elbo(Kzz, Kzx, kdiag, y, mean_c, sn, mu, W, num_datapoints, jitter):
+    """objectives.py:241-318 + variational_families.py:169-285 + integrators.py:151-158 in torch-CPU float64."""
+    m, n = Kzx.shape
+    Lz = torch.linalg.cholesky(Kzz + jitter * torch.eye(m, dtype=torch.float64))
+    W = torch.tril(W)
+    LiW = torch.linalg.solve_triangular(Lz, W, upper=False)
+    Lim = torch.linalg.solve_triangular(Lz, (mu - mean_c).reshape(-1, 1), upper=False)
+    kl = 0.5 * (torch.sum(LiW**2) + torch.sum(Lim**2) - m + 2 * torch.sum(torch.log(torch.diagonal(Lz)))
+                - 2 * torch.sum(torch.log(torch.abs(torch.diagonal(W)))))
+    A = torch.linalg.solve_triangular(Lz, Kzx, upper=False)
+    KiK = torch.linalg.solve_triangular(Lz.T, A, upper=True)
+    R = KiK.T @ W
+    mean = mean_c + KiK.T @ (mu - mean_c)
+    var = kdiag - torch.sum(A**2, 0) + torch.sum(R**2, 1) + jitter
+    ell = -0.5 * torch.sum(math.log(2 * math.pi) + torch.log(sn**2) + ((y - mean) ** 2 + var) / sn**2)
+    return ell * num_datapoints / n - kl
+
+
+@pytest.mark.parametrize("op", ["sum", "prod", "mixed"])
+def test_sparse_objectives_and_predictions_accept_combination_kernels(op):
+    """collapsed_elbo / elbo take ANY kernel in the reference (objectives.py:352-356 only call kernel.gram / cross_covariance /
+    __call__).  Sums and products have no single streamed epilogue here, so they run the composable route: value, every gradient
+    (kernel parts, noise, mean, inducing inputs, variational parameters) and both predictive distributions against CPU autodiff."""
+    import gpjax_b200 as gpx
+    from gpjax_b200.parameters import Real
+
+    n, m = 600, 40
+    X, y = data(n, 2, 41)
+    Z0 = np.ascontiguousarray(X[:m] + (0.0 if op == "sum" else 0.01))  # op == "sum": coincident points exercise the White part
+    T = data(25, 2, 42)[0]
+    Xt, yt, Tt = torch.tensor(X), torch.tensor(y).reshape(-1), torch.tensor(T)
+
+    def build():
+        k, parts = _combo(op)
+        post = gpx.gps.Prior(mean_function=gpx.mean_functions.Constant(Real(0.2)), kernel=k) * gpx.likelihoods.Gaussian(
+            num_datapoints=5 * n, obs_stddev=0.4)
+        return k, parts, post
+
+    def check(val, ref, pairs):
+        assert abs(val.item() - ref.item()) <= 1e-8 * abs(ref.item()), (val.item(), ref.item())
+        floor = 1e-6 * abs(ref.item())
+        for mine, theirs in pairs:
+            b = theirs.grad.numpy()
+            a = mine.value.grad.cpu().numpy().reshape(b.shape)
+            assert np.max(np.abs(a - b)) <= 1e-8 * max(np.max(np.abs(b)), floor), (a, b)
+
+    D = gpx.Dataset(X=dev(X), y=dev(y))
+    t = lambda a: torch.tensor(np.asarray(a, np.float64), requires_grad=True)
+    # ---- collapsed_elbo + CollapsedVariationalGaussian.predict
+    k, parts, post = build()
+    q = gpx.variational_families.CollapsedVariationalGaussian(posterior=post, inducing_inputs=dev(Z0))
+    for p in dict(q.named_parameters()).values():
+        p.value.requires_grad_(True)
+    val = gpx.objectives.collapsed_elbo(q, D)
+    val.backward()
+    P, Zt, sn, c = _combo_params(), t(Z0), t(0.4), t(0.2)
+    ref = _t_collapsed_elbo(_combo_t(op, Zt, Zt, P), _combo_t(op, Zt, Xt, P), torch.diagonal(_combo_t(op, Xt, Xt, P)), yt - c, sn, 1e-6)
+    ref.backward()
+    pairs = [(parts[0].lengthscale, P["l1"]), (parts[0].variance, P["v1"]), (parts[1].lengthscale, P["l2"]),
+             (parts[1].variance, P["v2"]), (post.likelihood.obs_stddev, sn), (post.prior.mean_function.constant, c),
+             (q.inducing_inputs, Zt)]
+    if op != "prod":
+        pairs.append((parts[2].variance, P["v3"]))
+    check(val, ref, pairs)
+    pred = q.predict(dev(T), D)
+    with torch.no_grad():
+        Pd = {kk: v.detach() for kk, v in P.items()}
+        Kzz = _combo_t(op, Zt.detach(), Zt.detach(), Pd).numpy() + 1e-6 * np.eye(m)
+        Kzx = _combo_t(op, Zt.detach(), Xt, Pd).numpy()
+        Kzt = _combo_t(op, Zt.detach(), Tt, Pd).numpy()
+        Ktt = _combo_t(op, Tt, Tt, Pd).numpy()
+    Lz = np.linalg.cholesky(Kzz)
+    A = np.linalg.solve(Lz, Kzx) / 0.4
+    Bm = np.eye(m) + A @ A.T
+    At = np.linalg.solve(Lz, Kzt)
+    v = np.linalg.solve(Bm, A @ (y.reshape(-1) - 0.2)) * 0.4
+    mref = 0.2 + At.T @ v / 0.16
+    cref = Ktt - At.T @ At + At.T @ np.linalg.solve(Bm, At) + 1e-6 * np.eye(25)
+    assert np.max(np.abs(pred.mean().cpu().numpy() - mref)) <= 1e-8 * max(np.max(np.abs(mref)), 1.0)
+    assert np.max(np.abs(pred.covariance().cpu().numpy() - cref)) <= 1e-8 * max(np.max(np.abs(cref)), 1.0)
+    # ---- elbo (SVGP) + VariationalGaussian.predict
+    k, parts, post = build()
+    rng = np.random.default_rng(7)
+    mu0 = 0.3 * rng.standard_normal((m, 1))
+    W0 = np.tril(0.1 * rng.standard_normal((m, m))) + 0.8 * np.eye(m)
+    q = gpx.variational_families.VariationalGaussian(posterior=post, inducing_inputs=dev(Z0), variational_mean=dev(mu0),
+                                                     variational_root_covariance=dev(W0))
+    for p in dict(q.named_parameters()).values():
+        p.value.requires_grad_(True)
+    val = gpx.objectives.elbo(q, D)
+    val.backward()
+    P, Zt, sn, c, mu, W = _combo_params(), t(Z0), t(0.4), t(0.2), t(mu0.reshape(-1)), t(W0)
+    ref = _t_svgp_elbo(_combo_t(op, Zt, Zt, P), _combo_t(op, Zt, Xt, P), torch.diagonal(_combo_t(op, Xt, Xt, P)), yt, c, sn, mu, W,
+                       5.0 * n, 1e-6)
+    ref.backward()
+    pairs = [(parts[0].lengthscale, P["l1"]), (parts[0].variance, P["v1"]), (parts[1].lengthscale, P["l2"]),
+             (parts[1].variance, P["v2"]), (post.likelihood.obs_stddev, sn), (post.prior.mean_function.constant, c),
+             (q.inducing_inputs, Zt), (q.variational_mean, mu)]
+    check(val, ref, pairs)
+    gW = q.variational_root_covariance.value.grad.cpu().numpy()
+    assert np.max(np.abs(np.tril(gW) - np.tril(W.grad.numpy()))) <= 1e-8 * np.max(np.abs(W.grad.numpy()))
+    pred = q.predict(dev(T))
+    KiK = np.linalg.solve(Kzz, Kzt)
+    mref = 0.2 + KiK.T @ (mu0.reshape(-1) - 0.2)
+    cref = Ktt - At.T @ At + (KiK.T @ W0) @ (KiK.T @ W0).T + 1e-6 * np.eye(25)
+    assert np.max(np.abs(pred.mean().cpu().numpy() - mref)) <= 1e-8 * max(np.max(np.abs(mref)), 1.0)
+    assert np.max(np.abs(pred.covariance().cpu().numpy() - cref)) <= 1e-8 * max(np.max(np.abs(cref)), 1.0)
 
 
 # ---- conjugate_loocv (objectives.py:110-178) -----------------------------------------------------------------------

@@ -292,6 +292,28 @@ def test_svgp_elbo_value_and_gradient(lib, kind, name, N, M, D, iso, block, shar
         assert np.max(np.abs(a - b)) <= 1e-7 * max(np.max(np.abs(b)), 1e-8 * abs(ref)), k
 
 
+def test_potrf_flag_word_symmetrises_the_input_like_jnp_cholesky(lib):
+    """jnp.linalg.cholesky factors (A + A^T) / 2 (symmetrize_input=True; gpjax/linalg/operations.py:54-55 passes whatever dense
+    array it holds).  Bit 1 of gpb_potrf_lower's flag word does the same; without it only the lower triangle is read."""
+    N = 300
+    X, _ = data(N, 2, N)
+    S = o.gram("rbf", X, np.array([0.9, 1.1]), 1.0) + 0.3 * np.eye(N)
+    E = 1e-3 * np.random.default_rng(1).standard_normal((N, N))
+    A0 = S + np.triu(E, 1)  # not symmetric: the strict upper triangle is perturbed
+    nbytes = lib.gpb_factor_workspace_bytes(N, 2, 0)
+    info = np.zeros(1, np.int32)
+    out = {}
+    for flags in (1, 3):
+        ws = np.zeros(nbytes // 8 + 8)
+        A = A0.copy()
+        assert lib.gpb_potrf_lower(None, N, p(A), N, flags, p(ws), nbytes, N, 2, 0, p(info)) == 0 and info[0] == 0
+        assert np.all(np.triu(A, 1) == 0.0)
+        out[flags] = A
+    assert np.max(np.abs(out[1] - np.linalg.cholesky(S))) <= 1e-12
+    assert np.max(np.abs(out[3] - np.linalg.cholesky(0.5 * (A0 + A0.T)))) <= 1e-12
+    assert np.max(np.abs(out[1] - out[3])) > 1e-6
+
+
 # ---- Ozaki (int8 digit plane) trailing updates: orchestration, workspace carving, double buffering ---------------------
 @pytest.mark.parametrize("N,planes", [(700, 6), (1024, 7), (900, 4)])
 def test_potrf_with_int8_digit_plane_updates(lib, N, planes):
@@ -393,15 +415,16 @@ def test_mll_value_and_gradient_with_int8_digit_plane_updates(lib, N):
 
 def test_auto_mode_guard_picks_planes_from_the_hyperparameters(lib):
     """OZ_AUTO (-1): the plane count of the int8 updates is written into the workspace by ozaki_choose_planes -- 7 for a bare
-    matrix (gpb_potrf_lower), 6 only while (N variance + s) / s <= 5e6, s = obs_stddev^2 + jitter, for the fused objective --
+    matrix (gpb_potrf_lower), 6 only while (N variance + s) / s <= 2e6, s = obs_stddev^2 + jitter, for the fused objective --
     and the product kernels read it from there.  The host model's workspace is host memory, so the word can be inspected."""
     N, D = 700, 3
     X, y = data(N, D, N)
     ell, c = np.linspace(0.8, 1.6, D), np.array([0.0])
     assert lib.gpb_ozaki_auto_planes(50000, 1.0, 0.3, 1e-6) == 6       # the benchmark's hyper-parameters: bound 5.6e5
     assert lib.gpb_ozaki_auto_planes(100000, 1.0, 0.3, 1e-6) == 6      # config 3: 1.1e6
-    assert lib.gpb_ozaki_auto_planes(8192, 1.0, 0.05, 1e-6) == 6       # 3.3e6
-    assert lib.gpb_ozaki_auto_planes(8192, 1.0, 0.03, 1e-6) == 7       # 9.1e6 > 5e6
+    assert lib.gpb_ozaki_auto_planes(8192, 1.0, 0.1, 1e-6) == 6        # 8.2e5
+    assert lib.gpb_ozaki_auto_planes(8192, 1.0, 0.05, 1e-6) == 7       # 3.3e6 > 2e6
+    assert lib.gpb_ozaki_auto_planes(8192, 1.0, 0.03, 1e-6) == 7       # 9.1e6
     assert lib.gpb_ozaki_auto_planes(8192, 1.0, 0.003, 1e-6) == 7      # 8.2e8
     assert lib.gpb_ozaki_auto_planes(50000, 1.0, 0.0, 0.0) == 7        # s = 0 -> inf -> 7
     nbytes = lib.gpb_mll_workspace_bytes(N, D)
