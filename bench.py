@@ -373,26 +373,29 @@ def bench_exact(D: Dist, args):
     dmma = {"kernel": "gemm_f64_kernel (FP64 DMMA.8x8x4)", "launches_per_step": gemm_n.value / args.steps,
             "time_over_step_time": gemm_ms.value * 1e-3 / t}
     if planes and oz_n.value > 0:
-        # Dominant kernel: ozaki_i8_kernel_cg2 (tcgen05.mma.cta_group::2.kind::i8).  `achieved` = algorithmic int8 operations of
-        # its launches (live output entries x K x s(s+1)/2 digit pairs x 2) / summed launch durations (CUDA events on the
-        # launching stream).  The launcher counts with the 7 planes present in the digit buffers; the device-side guard used
-        # `planes` of them, hence the s(s+1)/56 factor.
-        oz_ops_used = oz_ops.value * (planes * (planes + 1) / 2) / 28.0
+        # Dominant kernel: ozaki_i8_kernel_w4 (tcgen05.mma.cta_group::2.kind::i8).  `achieved` = algorithmic int8 operations of
+        # its launches (live output entries x K x digit pairs x 2) / summed launch durations (CUDA events on the launching
+        # stream).  Digit pairs of s planes: s(s+1)/2, plus the equal-plane pair (s/2, s/2) when s is even (csrc/ozaki_i8.cu:
+        # oz_has_diag).  The launcher counts with the 7 planes the digit buffers are laid out for (28 pairs); the device-side
+        # guard used `planes` of them.
+        pairs = lambda q: q * (q + 1) // 2 + (1 if (q >= 2 and q % 2 == 0) else 0)
+        oz_ops_used = oz_ops.value * pairs(planes) / 28.0
         achieved = oz_ops_used / (oz_ms.value * 1e-3) / 1e12
         # MEASURED_PEAKS.json has no int8 entry: the ceiling is measured live in this process (cuBLASLt IGEMM, torch._int_mm):
         # `peak` = the SUSTAINED figure (the kernel is timed inside a seconds-long step under the 1 kW cap), burst alongside.
         i8 = measure_int8_ceiling(D)
         mp = measured_peaks() or {}
         bf16 = float(mp.get("bf16_tflops_sustained") or mp.get("bf16_tflops") or 1414.5)
-        ncu = ncu_capture("profiles/r02_ozaki_cg2_ncu.json")
+        ncu = ncu_capture("profiles/r02_ozaki_w4_ncu.json")
         roof = {"bound": "tensor",
-                "kernel": "ozaki_i8_kernel_cg2 (tcgen05.mma.cta_group::2.kind::i8, M256 x N128 per CTA pair, int8 x int8 -> int32 in TMEM)",
+                "kernel": "ozaki_i8_kernel_w4 (tcgen05.mma.cta_group::2.kind::i8, M256 x N256 per CTA pair = two digit-pair orders side by side, "
+                          "int8 x int8 -> int32 in TMEM, int64 fixed-point recombination, red.global.add.f64 write-out)",
                 "achieved": achieved, "peak": i8["sustained_tops"], "unit": "TFLOP/s", "frac": achieved / i8["sustained_tops"],
                 "peak_source": "measured live in this process: torch._int_mm (cuBLASLt IGEMM) 8192^3 back to back for >= 2 s "
                                "(sustained, power-capped); unit is int8 Top/s (2 x MAC)",
                 "int8_ceiling_measured": i8, "frac_of_int8_burst": achieved / i8["burst_tops"],
                 "frac_of_2x_bf16_sustained": achieved / (2.0 * bf16),
-                "digit_planes": planes, "digit_plane_mode": "auto (device-side conditioning guard)" if mode == -1 else "forced",
+                "digit_planes": planes, "digit_bits_per_plane": 8, "digit_pair_products": pairs(planes), "digit_plane_mode": "auto (device-side conditioning guard)" if mode == -1 else "forced",
                 "int8_ops_per_eval": oz_ops_used / args.steps,
                 "launches_per_step": oz_n.value / args.steps, "time_over_step_time": oz_ms.value * 1e-3 / t,
                 "algorithmic_flop_per_eval": flops_per_eval,

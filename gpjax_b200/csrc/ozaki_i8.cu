@@ -87,10 +87,10 @@ struct OzParams {
 };
 // v4 recombines the orders EXACTLY in a 64-bit integer instead of an fp64 FMA chain: acc = sum_t P_t 2^(F - 8 t), one unit =
 // 2^(-F - 16) 2^(ea + eb).  |P_t| <= (t + 1) K 2^14, so order 0 dominates and F = 61 - ceil(log2(K 2^14)) keeps |acc| < 2^62; orders
-// with 8 t > F are rounded to the unit (2^-54 of the scale product at K = 1024: below the fp64 rounding of the result).  Why: the
-// plain FP64 pipe of sm_100 issues one warp instruction per ~16 clk per scheduler (measured: profiles/r02_ozaki_epilogue.md), the
-// 2 x 7 DADD / DFMA per output of the FMA chain made the EPILOGUE the pacing role (the MMA warp waited for a free accumulator 45 %
-// of the time); IMAD.WIDE does the same accumulation on the integer pipe in one instruction per order.
+// with 8 t > F are rounded to the unit (2^-54 of the scale product at K = 1024: below the fp64 rounding of the result).  Why: one
+// rounding per output entry instead of one per order, and one IMAD.WIDE per value on the integer pipe instead of a DADD + DFMA
+// pair on the FP64 pipe the write-out also needs (profiles/r02_ozaki_epilogue.md; the time of the kernel did not change with it --
+// what paced the epilogue was the load of C and of the column scales in the write-out, see oz_store_row_fx).
 __host__ __device__ __forceinline__ int oz_fx_bits(long long K) {
     int lg = 0;
     while ((1ll << lg) < K * OZ_DIGIT_SQ_MAX) ++lg;
@@ -760,6 +760,11 @@ __device__ __forceinline__ unsigned mapa_u32(const void* p, unsigned rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(unsigned cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
 }
+// same without the release fence: the accumulator hand-back orders TMEM reads (tcgen05.wait::ld + fence::before_thread_sync), not
+// global memory -- a release here would wait for every outstanding red.global of the previous tile's write-out
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(unsigned cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
 // TMA load of a CTA pair: data lands in THIS CTA's shared memory, the transaction bytes are signalled on the mbarrier at the
 // shared::cluster address `bar_cluster` (the leader's `full` barrier)
 __device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* map, unsigned bar_cluster, int x, int y) {
@@ -1078,27 +1083,89 @@ constexpr int W4_B_BYTES = OZ_BN * OZ_BK;                 // 16 KB: a full 128-r
 constexpr int W4_SLOT_BYTES = C2_A_BYTES + W4_B_BYTES;    // 32 KB
 constexpr int W4_RING = 6;
 constexpr int W4_ACC = 2;                                 // x 256 TMEM columns
-constexpr int W4_SMEM_BYTES = W4_RING * W4_SLOT_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int W4_SB_STAGE_BYTES = OZ_EPI_WARPS * 64 * (8 + 4);  // per epilogue warp: the 64 column scales of its slab + their exponents
+constexpr int W4_SMEM_BYTES = W4_RING * W4_SLOT_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + W4_SB_STAGE_BYTES;
 // instruction descriptor: D = s32, A = B = signed int8, both K-major, N = 256, M = 256 (cta_group::2)
 constexpr unsigned W4_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(256 >> 3) << 17) | ((unsigned)(C2_BM >> 4) << 24);
 static_assert(W4_SMEM_BYTES <= 232448, "exceeds the 227 KB dynamic shared memory of sm_100");
 
 // write-out of one thread's 64 fixed-point sums: exact int64 -> fp64 (two exact halves, ONE rounding), scaled by
 // alpha 2^(ea + eb - F - 16), then C (+)= v -- through red.global.add.f64 when p.use_red: every output entry receives exactly one
-// add per launch from exactly one thread, so the result is deterministic and no epilogue warp ever waits for a load of C
-__device__ __forceinline__ void oz_store_row_fx(const OzParams& p, const long long (&accq)[64], int row, int col0) {
+// add per launch from exactly one thread, so the result is deterministic and no epilogue warp ever waits for a load of C.
+// `sbs`: the 64 column scales of the slab, staged in shared memory by the warp (a per-element __ldg of sb cost one exposed L2
+// round trip per output entry: 38 % of the MMA warp's time went into waiting for this loop, profiles/r02_ozaki_epilogue.md).
+template <int STORE>  // 0: C = v (beta0), 1: red.global.add, 2: load / add / store
+__device__ __forceinline__ void oz_store_row_fx_impl(const long long (&accq)[64], double* crow, const double* sbs, double sr,
+                                                      int jlo, int jhi) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        if (j >= jlo && j < jhi) {
+            const int hi = (int)(accq[j] >> 32);
+            const unsigned lo = (unsigned)accq[j];
+            const double dh = __hiloint2double(0x43300000, (int)((unsigned)hi ^ 0x80000000u)) - 4503601774854144.0;  // exact
+            const double dl = __hiloint2double(0x43300000, (int)lo) - 4503599627370496.0;                           // exact
+            const double v = fma(dh, 4294967296.0, dl) * (sr * sbs[j]);
+            double* dst = crow + j;
+            if (STORE == 0) *dst = v;
+            else if (STORE == 1) asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(dst), "d"(v) : "memory");
+            else *dst += v;
+        }
+    }
+}
+// Exponent of a scale that is an exact power of two (what the slice kernels produce), or a marker:
+//   OZ_E_POISON  : NaN / Inf scale (a poisoned row: the output entry becomes NaN, JAX semantics for a failed factorisation)
+//   OZ_E_GENERIC : anything else (zero, negative, denormal, a mantissa) -> the warp takes the FP64 write-out
+constexpr int OZ_E_POISON = 0x40000000, OZ_E_GENERIC = 0x40000001;
+__device__ __forceinline__ int oz_scale_exp(double s) {
+    const int hi = __double2hiint(s), lo = __double2loint(s);
+    const int field = (hi >> 20) & 0x7FF;
+    if (field == 0x7FF) return OZ_E_POISON;
+    if (hi < 0 || field == 0 || ((hi & 0xFFFFF) | lo) != 0) return OZ_E_GENERIC;
+    return field - 1023;
+}
+// INTEGER-ONLY write-out: round-to-nearest-even int64 -> binary64 built by hand, the power-of-two scales applied as an exponent
+// add.  Why no FP64 instruction at all: while the tensor pipe runs UTCIMMA the FP64 pipe of the same SM is throttled -- the 5 FP64
+// operations per output entry of the FP64 write-out kept the epilogue warps in `stall_math` for a quarter of their time whether the
+// kernel issued 17 or 5 of them per entry (profiles/r02_ozaki_epilogue.md section 3), and the MMA warp waited for them.
+template <int STORE>  // 0: C = v (beta0), 1: red.global.add, 2: load / add / store
+__device__ __forceinline__ void oz_store_row_int_impl(const long long (&accq)[64], double* crow, const int* sbe, int er, int neg,
+                                                       int jlo, int jhi) {
+#pragma unroll
+    for (int j = 0; j < 64; ++j) {
+        if (j >= jlo && j < jhi) {
+            const long long x = accq[j];
+            const unsigned long long a = (unsigned long long)(x < 0 ? -x : x);
+            const int ec = sbe[j];
+            const int lz = __clzll((long long)a);
+            const unsigned long long nrm = a << (lz & 63);          // leading one at bit 63 (a != 0)
+            unsigned long long mant = nrm >> 11;                     // 53 bits, implicit one included
+            const unsigned rem = (unsigned)nrm & 0x7FFu;
+            mant += (rem > 0x400u || (rem == 0x400u && (mant & 1ull))) ? 1ull : 0ull;
+            const int E = 63 - lz + 1023 + er + ec;                  // biased exponent of the scaled value
+            unsigned long long bits = ((unsigned long long)(unsigned)(E - 1) << 52) + mant;  // a carry out of mant bumps the exponent
+            if (a == 0ull || E <= 0) bits = 0ull;                    // zero / below the normal range: flush
+            if (E >= 2047) bits = 0x7FF0000000000000ull;
+            bits |= (unsigned long long)(unsigned)((x < 0) != (neg != 0)) << 63;
+            if (er == OZ_E_POISON || ec == OZ_E_POISON) bits = 0x7FF8000000000000ull;
+            const double v = __longlong_as_double((long long)bits);
+            double* dst = crow + j;
+            if (STORE == 0) *dst = v;
+            else if (STORE == 1) asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(dst), "d"(v) : "memory");
+            else *dst += v;
+        }
+    }
+}
+__device__ __forceinline__ void oz_store_row_fx(const OzParams& p, const long long (&accq)[64], int row, int col0, const double* sbs,
+                                                const int* sbe, bool generic) {
     const double sr = p.alpha * __ldg(p.sa + row) * __hiloint2double((1023 - p.fx_bits - 2 * OZ_BETA) << 20, 0);
     const long long grow = p.row0 + row;
-    double* crow = p.C + (long long)row * p.ldc;  // indexed by the local column
-    long long cshift = 0;
+    double* crow = p.C + (long long)row * p.ldc + col0;  // indexed by the column inside the slab
     bool diag_blk = false;
     if (p.mask == 3) {  // a 64-column slab lies inside one column block (mask_nb is a multiple of 128)
         const long long rb = grow / p.mask_nb, cb = (p.col0 + col0) / p.mask_nb;
         diag_blk = rb == cb;
-        if (diag_blk) {  // dense diagonal block rb of C2, addressed by (row, column) inside the block
-            crow = p.C2 + rb * p.mask_nb * p.mask_nb + (grow - rb * p.mask_nb) * p.mask_nb;
-            cshift = p.col0 - cb * p.mask_nb;
-        }
+        if (diag_blk)  // dense diagonal block rb of C2, addressed by (row, column) inside the block
+            crow = p.C2 + rb * p.mask_nb * p.mask_nb + (grow - rb * p.mask_nb) * p.mask_nb + (p.col0 + col0 - cb * p.mask_nb);
     }
     // live column range of this row inside the slab (all masks are intervals in the column index)
     int jlo = 0, jhi = p.n - col0 < 64 ? p.n - col0 : 64;
@@ -1109,20 +1176,17 @@ __device__ __forceinline__ void oz_store_row_fx(const OzParams& p, const long lo
         const long long first = (grow / p.mask_nb + 1) * p.mask_nb - p.col0 - col0;  // first column of the next block
         jlo = first > 0 ? (first < 64 ? (int)first : 64) : 0;
     }
-#pragma unroll
-    for (int j = 0; j < 64; ++j) {
-        if (j >= jlo && j < jhi) {
-            const int hi = (int)(accq[j] >> 32);
-            const unsigned lo = (unsigned)accq[j];
-            const double dh = __hiloint2double(0x43300000, (int)((unsigned)hi ^ 0x80000000u)) - 4503601774854144.0;  // exact
-            const double dl = __hiloint2double(0x43300000, (int)lo) - 4503599627370496.0;                           // exact
-            const double v = fma(dh, 4294967296.0, dl) * (sr * __ldg(p.sb + col0 + j));
-            double* dst = crow + col0 + j + cshift;
-            if (p.beta0) *dst = v;
-            else if (p.use_red) asm volatile("red.global.add.f64 [%0], %1;\n" ::"l"(dst), "d"(v) : "memory");
-            else *dst += v;
-        }
+    const int er = oz_scale_exp(fabs(sr));
+    if (generic || er == OZ_E_GENERIC) {  // scales that are not powers of two (never produced by the slice kernels): FP64 write-out
+        if (p.beta0) oz_store_row_fx_impl<0>(accq, crow, sbs, sr, jlo, jhi);
+        else if (p.use_red) oz_store_row_fx_impl<1>(accq, crow, sbs, sr, jlo, jhi);
+        else oz_store_row_fx_impl<2>(accq, crow, sbs, sr, jlo, jhi);
+        return;
     }
+    const int neg = sr < 0.0;
+    if (p.beta0) oz_store_row_int_impl<0>(accq, crow, sbe, er, neg, jlo, jhi);
+    else if (p.use_red) oz_store_row_int_impl<1>(accq, crow, sbe, er, neg, jlo, jhi);
+    else oz_store_row_int_impl<2>(accq, crow, sbe, er, neg, jlo, jhi);
 }
 
 // Order groups of one output tile, enumerated identically by the three roles.  `cursor` runs over the orders t = 0..groups-1:
@@ -1166,6 +1230,7 @@ ozaki_i8_kernel_w4(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint64_t* tfull = bars + 2 * W4_RING;    // [2]   MMA -> epilogue, multicast to both CTAs
     uint64_t* tempty = tfull + W4_ACC;       // [2]   epilogue (both CTAs) -> MMA; only the leader's copies are used
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(tempty + W4_ACC);
+    double* sb_stage = reinterpret_cast<double*>(smem + W4_RING * W4_SLOT_BYTES + 256);  // [8 epilogue warps][64]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned rank = cluster_ctarank();
@@ -1293,9 +1358,20 @@ ozaki_i8_kernel_w4(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const int row = tm * C2_BM + (int)rank * OZ_BM + q * 32 + lane;
             const int col0 = tn * OZ_BN + h * 64;
             long long accq[MODE == 1 ? 64 : 1];  // exact fixed-point running sums (see oz_fx_bits)
+            double* sbs = sb_stage + (warp - OZ_EPI_WARP0) * 64;
+            int* sbe = reinterpret_cast<int*>(sb_stage + OZ_EPI_WARPS * 64) + (warp - OZ_EPI_WARP0) * 64;
+            bool generic = false;  // warp-uniform: some column scale of the slab is not a power of two
             if (MODE == 1) {
 #pragma unroll
                 for (int j = 0; j < 64; ++j) accq[j] = 0;
+                __syncwarp();  // the previous tile's write-out has read its scales
+                const double s0 = col0 + lane < p.n ? __ldg(p.sb + col0 + lane) : 1.0;
+                const double s1 = col0 + 32 + lane < p.n ? __ldg(p.sb + col0 + 32 + lane) : 1.0;
+                const int e0 = oz_scale_exp(s0), e1 = oz_scale_exp(s1);
+                sbs[lane] = s0; sbs[32 + lane] = s1;
+                sbe[lane] = e0; sbe[32 + lane] = e1;
+                generic = __any_sync(0xffffffffu, e0 == OZ_E_GENERIC || e1 == OZ_E_GENERIC) != 0;
+                __syncwarp();
             }
             OzGroup g;
             for (int cursor = 0; oz_next_group(groups, cursor, g);) {
@@ -1334,11 +1410,11 @@ ozaki_i8_kernel_w4(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty[acc], 0));  // the leader's barrier counts both CTAs
+                if (lane == 0) mbar_arrive_cluster_relaxed(mapa_u32(&tempty[acc], 0));  // the leader's barrier counts both CTAs
                 if (++acc == W4_ACC) { acc = 0; aphase ^= 1u; }
             }
             if constexpr (MODE == 1) {
-                if (row < p.m) oz_store_row_fx(p, accq, row, col0);
+                if (row < p.m) oz_store_row_fx(p, accq, row, col0, sbs, sbe, generic);
             }
         }
     }

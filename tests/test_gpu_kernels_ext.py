@@ -184,20 +184,20 @@ def test_collapsed_elbo_fused(cls, kind, name, skw, sv):
 
 def test_powered_exponential_runs_the_composable_sparse_route():
     """The streamed SGPR statistics assume k(x, x) = variance; PoweredExponential's clamped diagonal is variance * exp(-(1e-18)^power)
-    (stationary/utils.py:67), visibly smaller for power = 0.5, so it takes the composable route -- and matches the oracle, whose
+    (stationary/utils.py:67), visibly smaller for power = 0.3, so it takes the composable route -- and matches the oracle, whose
     trace term evaluates the kernel at (x, x) pair by pair as objectives.py:356 does."""
     import gpjax_b200 as gpx
 
     n = 300
     X, y = data(n, 2, 1)
-    k = gpx.kernels.PoweredExponential(lengthscale=[0.9, 1.2], variance=1.3, power=0.5)
+    k = gpx.kernels.PoweredExponential(lengthscale=[0.9, 1.2], variance=1.3, power=0.3)
     post = gpx.gps.Prior(mean_function=gpx.mean_functions.Zero(), kernel=k) * gpx.likelihoods.Gaussian(num_datapoints=n, obs_stddev=0.4)
     q = gpx.variational_families.CollapsedVariationalGaussian(posterior=post, inducing_inputs=dev(X[:20] + 0.01))
     val = gpx.objectives.collapsed_elbo(q, gpx.Dataset(X=dev(X), y=dev(y)))
-    ref = o.collapsed_elbo("powered_exponential", X, y, X[:20] + 0.01, np.array([0.9, 1.2]), np.array([1.3, 0.5]), 0.4, 0.0)
+    ref = o.collapsed_elbo("powered_exponential", X, y, X[:20] + 0.01, np.array([0.9, 1.2]), np.array([1.3, 0.3]), 0.4, 0.0)
     assert abs(val.item() - ref) <= 1e-8 * abs(ref)
-    # had the trace term used k(x, x) = variance, the value would differ by n * variance * (1 - exp(-1e-9)) / (2 sigma^2) ~ 1e-6
-    assert abs(n * 1.3 * (1.0 - math.exp(-1e-9)) / (2 * 0.16)) > 1e-8 * abs(ref)
+    # had the trace term used k(x, x) = variance, the value would be off by n variance (1 - exp(-(1e-18)^0.3)) / (2 sigma^2) ~ 5e-3
+    assert abs(n * 1.3 * (1.0 - math.exp(-(1e-18 ** 0.3))) / (2 * 0.16)) > 100 * 1e-8 * abs(ref)
 
 
 # ---- combination kernels (kernels/base.py:150-339) ---------------------------------------------------------------

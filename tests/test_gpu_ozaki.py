@@ -104,6 +104,46 @@ def test_recombined_product_meets_truncation_bound(s, tol, m, n, k, lower):
     assert float(((C - ref).abs() / (A.norm(dim=1).max() * B.norm(dim=1).max())).max()) <= tol
 
 
+def test_write_out_paths_agree_power_of_two_scales_generic_scales_and_poisoned_rows():
+    """The default write-out builds the fp64 result with integer instructions (power-of-two scales = an exponent add).  Scales
+    that are not powers of two (possible through the C ABI) take the FP64 write-out; a NaN scale poisons its row / column only."""
+    from gpjax_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(11)
+    m, n, k, s = 600, 500, 256, 6
+    A = torch.randn(m, k, dtype=torch.float64, device="cuda", generator=g) * torch.exp(
+        4 * torch.randn(m, 1, dtype=torch.float64, device="cuda", generator=g))
+    B = torch.randn(n, k, dtype=torch.float64, device="cuda", generator=g)
+    Qa, sa = ops.ozaki_slice(A, s)
+    Qb, sb = ops.ozaki_slice(B, s)
+    C0 = torch.randn(m, n, dtype=torch.float64, device="cuda", generator=g)
+    C1 = C0.clone()
+    ops.ozaki_gemm_(C1, Qa, sa, Qb, sb, k, s, alpha=-1.0)
+    ref = C0 - A @ B.T
+    scale = A.abs().amax(1)[:, None] * B.abs().amax(1)[None, :] * k
+    assert float(((C1 - ref).abs() / scale).max()) <= 1e-12
+    # generic scales: 3 sa and sb / 3 give the same product up to the roundings of the FP64 write-out
+    C2 = C0.clone()
+    ops.ozaki_gemm_(C2, Qa, 3.0 * sa, Qb, sb / 3.0, k, s, alpha=-1.0)
+    assert float(((C2 - C1).abs() / scale).max()) <= 1e-15
+    # alpha that is not a power of two
+    C3 = C0.clone()
+    ops.ozaki_gemm_(C3, Qa, sa, Qb, sb, k, s, alpha=-0.3)
+    assert float(((C3 - (C0 - 0.3 * (A @ B.T))).abs() / scale).max()) <= 1e-12
+    # poisoned row and column
+    sa2, sb2 = sa.clone(), sb.clone()
+    sa2[17] = float("nan")
+    sb2[401] = float("nan")
+    C4 = C0.clone()
+    ops.ozaki_gemm_(C4, Qa, sa2, Qb, sb2, k, s, alpha=-1.0)
+    bad = torch.isnan(C4)
+    expect = torch.zeros_like(bad)
+    expect[17, :] = True
+    expect[:, 401] = True
+    assert torch.equal(bad, expect)
+    assert torch.equal(C4[~bad], C1[~bad])
+
+
 @pytest.mark.parametrize("n", [4096, 5000])
 def test_cholesky_on_the_int8_pipe_matches_the_dmma_factor(n):
     from gpjax_b200 import ops
