@@ -195,7 +195,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "evals/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"exact_gp_conjugate_mll_value_and_grad_N{n}_D{d}_RBF_ARD", "N": n, "D": d},
+            "config": {"workload": f"exact_gp_conjugate_mll_value_and_grad_N{n}_D{d}_RBF_ARD", "N": n, "D": d,
+                       "timed_sample_N": s["n_sample"],
+                       "extrapolation": f"each step times the reference formulation at N={s['n_sample']} and scales by (N/N_sample)^3 "
+                                        f"to N={n}: the full size would take ~80 min per step on these host cores"},
             "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)

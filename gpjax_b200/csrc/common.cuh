@@ -31,6 +31,18 @@ struct PerDeviceOnce {
     void mark(int dev) { done[dev].store(1, std::memory_order_release); }  // setting the attribute twice is harmless
 };
 
+// ---- balanced radix-256 digit planes (ozaki_i8.cu, gram.cu) ------------------------------------------------------------
+constexpr int OZ_BETA = OZ_DIGIT_BITS;  // 8: radix-256 digits
+constexpr double OZ_RMAX = 0.494;
+__device__ __forceinline__ int oz_row_exponent(double mx) {  // mx finite and > 0
+    int e = ilogb(mx) + 2;                   // mx 2^-e in [1/4, 1/2)
+    if (scalbn(mx, -e) > OZ_RMAX) ++e;       // mantissa above 1.976: one more bit of head room for the carry into the top digit
+    return e;
+}
+__device__ __forceinline__ long long oz_fixed_point(double R, int nslices) {
+    return __double2ll_rn(R * __hiloint2double((1023 + OZ_BETA * nslices) << 20, 0));
+}
+
 // ---- cp.async (LDGSTS) with zero-fill -------------------------------------------------------
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
     unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem));

@@ -146,6 +146,198 @@ __global__ void __launch_bounds__(GT, 2) gram_kernel(const GramParams p) {
     }
 }
 
+// ---- fused Gram tile -> digit planes (GramDigitsDesc) --------------------------------------------------------------------
+struct GramDigitsParams {
+    GramParams g;
+    int cols_mode, nslices;
+    signed char* Q; int64_t ldq, kplane;
+    double* scale;
+    const double* y; const double* mean_const;
+    double* part;
+};
+// staged digits of one tile: [plane][64 rows][row stride] bytes; row stride 128 in mode 0 (16-byte vector reads along the
+// columns), 132 in mode 1 (the write-out gathers 16 ROWS per column: +4 bytes per row spreads them over the banks)
+constexpr int GD_STRIDE0 = TC, GD_STRIDE1 = TC + 4;
+constexpr int GD_DIG_BYTES = OZ_PLANES_MAX * TR * GD_STRIDE1;
+
+// All s balanced radix-256 digits of I at once: with C = 0x80 in each of the s low bytes, the unsigned bytes of I + C are
+// d_p + 128 (unique base-256 representation of a non-negative number), so (I + C) ^ C holds the digits as signed bytes;
+// plane p (most significant first) is byte s - 1 - p.
+__device__ __forceinline__ unsigned long long oz_digit_bytes(long long I, unsigned long long C) {
+    return ((unsigned long long)I + C) ^ C;
+}
+
+template <int KIND, int DC>
+__global__ void __launch_bounds__(GT, 2) gram_digits_kernel(const GramDigitsParams q) {
+    extern __shared__ __align__(16) double sm[];
+    const GramParams& p = q.g;
+    const int Dp = pad_dim(p.D, DC);
+    double* Xs = sm;               // [TR][Dp]
+    double* Zs = sm + TR * Dp;     // [Dp][TC]
+    double* ell_s = Zs + Dp * TC;  // [Dp]  (periodic only)
+    double* red = ell_s + Dp;      // [2][4][TC]  (mode 1: partial column sums per ty group)
+    signed char* dig = reinterpret_cast<signed char*>(red + 2 * 4 * TC);
+    constexpr bool PER = (KIND == KIND_PERIODIC);
+    constexpr bool SHP = (KIND == KIND_RATQUAD || KIND == KIND_POWEXP || KIND == KIND_PERIODIC);
+    const int64_t tr = blockIdx.x / p.tiles_c, tc = blockIdx.x % p.tiles_c;
+    const int64_t r0 = tr * TR, c0 = tc * TC;
+    const bool kernel_tile = c0 < p.M;  // the tile holds at least one genuine kernel column
+    if (kernel_tile) {
+        load_scaled<true, PER>(Xs, p.X, p.ldx, r0, p.N, TR, p.D, Dp, p.ell, p.ell_is_scalar);
+        load_scaled<false, PER>(Zs, p.Z, p.ldz, c0, p.M, TC, p.D, Dp, p.ell, p.ell_is_scalar);
+        if (PER) load_ell(ell_s, p.ell, p.ell_is_scalar, p.D, Dp);
+    }
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const double var = p.variance[0];
+    const double shp = SHP ? p.variance[1] : 0.0;
+    const double mean = q.mean_const ? q.mean_const[0] : 0.0;
+    constexpr int ns = OZ_PLANES_MAX;  // the streamed sparse passes always use all 7 planes (host checks nslices == 7)
+    const double avar = fabs(var);
+    const bool var_bad = !(avar <= 1.7976931348623157e308);
+    const int e_var = (!var_bad && avar > 0.0) ? oz_row_exponent(avar) : 0;
+    // per-row multiplier 2^(8 s - e_r) (0 for a poisoned row), computed ONCE per row: mode 0 scales a row by the bound
+    // max(|variance|, 1, |d_r|), mode 1 every column by |variance|
+    double* mul_s = red;  // [TR] (mode 0; `red` is only used by mode 1)
+    if (!q.cols_mode && threadIdx.x < TR) {
+        const int64_t r = r0 + threadIdx.x;
+        double m_ = 0.0;
+        if (r < p.N) {
+            const double dr = q.y[r] - mean;
+            const double mx = fmax(fmax(avar, 1.0), fabs(dr));
+            const bool bad = var_bad || !(mx <= 1.7976931348623157e308);
+            const int e = bad ? 0 : oz_row_exponent(mx);
+            if (!bad) m_ = scalbn(1.0, OZ_BETA * ns - e);
+            if (tc == 0) q.scale[r] = bad ? __longlong_as_double(0x7ff8000000000000LL) : scalbn(1.0, e);
+        }
+        mul_s[threadIdx.x] = m_;
+    }
+    __syncthreads();
+    double r2[RPT][2];
+    if (kernel_tile) tile_r2<DC, PER>(Xs, Zs, Dp, tx, ty, r2, ell_s, PER ? (3.141592653589793 / shp) : 0.0);
+    const int64_t c = c0 + 2 * tx;
+    const int stride = q.cols_mode ? GD_STRIDE1 : GD_STRIDE0;
+    const unsigned long long C = 0x0080808080808080ull;
+    const double mul_c = var_bad ? 0.0 : scalbn(1.0, OZ_BETA * ns - e_var);
+    double sw[2] = {0.0, 0.0}, s1[2] = {0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int lr = ty + 4 * i;
+        const int64_t r = r0 + lr;
+        const bool rok = r < p.N;
+        const double dr = rok ? q.y[r] - mean : 0.0;
+        double v[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int64_t cc = c + h;
+            double val = 0.0;
+            if (rok) {
+                if (cc < p.M) val = kprofile<KIND>(r2[i][h], var, shp);
+                else if (cc == p.M) val = dr;
+                else if (cc == p.M + 1) val = 1.0;
+            }
+            v[h] = val;
+        }
+        if (q.cols_mode) {
+            sw[0] = fma(dr, v[0], sw[0]); sw[1] = fma(dr, v[1], sw[1]);
+            s1[0] += v[0]; s1[1] += v[1];
+        }
+        // x 2^(8 s - e): exact power-of-two scaling, then ONE rounding to the last plane; a zero multiplier poisons / blanks
+        const double mul = q.cols_mode ? mul_c : mul_s[lr];
+        unsigned long long J[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const bool live = q.cols_mode ? (c + h < p.M) : true;
+            J[h] = oz_digit_bytes(live ? __double2ll_rn(v[h] * mul) : 0ll, C);
+        }
+        // plane pl = byte 6 - pl of J: one PRMT pairs the two columns, one 16-bit store per plane
+        const unsigned lo0 = (unsigned)J[0], hi0 = (unsigned)(J[0] >> 32), lo1 = (unsigned)J[1], hi1 = (unsigned)(J[1] >> 32);
+        signed char* drow = dig + lr * stride + 2 * tx;
+        const int ps = TR * stride;
+        *reinterpret_cast<unsigned short*>(drow + 0 * ps) = (unsigned short)__byte_perm(hi0, hi1, 0x0062);
+        *reinterpret_cast<unsigned short*>(drow + 1 * ps) = (unsigned short)__byte_perm(hi0, hi1, 0x0051);
+        *reinterpret_cast<unsigned short*>(drow + 2 * ps) = (unsigned short)__byte_perm(hi0, hi1, 0x0040);
+        *reinterpret_cast<unsigned short*>(drow + 3 * ps) = (unsigned short)__byte_perm(lo0, lo1, 0x0073);
+        *reinterpret_cast<unsigned short*>(drow + 4 * ps) = (unsigned short)__byte_perm(lo0, lo1, 0x0062);
+        *reinterpret_cast<unsigned short*>(drow + 5 * ps) = (unsigned short)__byte_perm(lo0, lo1, 0x0051);
+        *reinterpret_cast<unsigned short*>(drow + 6 * ps) = (unsigned short)__byte_perm(lo0, lo1, 0x0040);
+    }
+    if (q.cols_mode) {
+        red[(0 * 4 + ty) * TC + 2 * tx] = sw[0]; red[(0 * 4 + ty) * TC + 2 * tx + 1] = sw[1];
+        red[(1 * 4 + ty) * TC + 2 * tx] = s1[0]; red[(1 * 4 + ty) * TC + 2 * tx + 1] = s1[1];
+        if (tr == 0 && ty == 0) {  // column scales: the same fixed exponent for every genuine column
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (c + h < p.M) q.scale[c + h] = var_bad ? __longlong_as_double(0x7ff8000000000000LL) : (avar > 0.0 ? scalbn(1.0, e_var) : 1.0);
+        }
+    }
+    __syncthreads();
+    if (q.cols_mode) {
+        // partial sums of this tile row for the M + 2 columns [K_b | d | 1], ty groups added in a fixed order
+        if (threadIdx.x < TC) {
+            const int64_t cc = c0 + threadIdx.x;
+            if (cc < p.M + 2) {
+                double a = 0.0, b = 0.0;
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) { a += red[(0 * 4 + g4) * TC + threadIdx.x]; b += red[(1 * 4 + g4) * TC + threadIdx.x]; }
+                q.part[(tr * 2 + 0) * (p.M + 2) + cc] = a;
+                q.part[(tr * 2 + 1) * (p.M + 2) + cc] = b;
+            }
+        }
+        // transposing write-out: a warp takes one (plane, group of 8 columns); lane = (column in the group, 16-row chunk); every
+        // lane gathers its 16 rows byte by byte (2-way bank conflicts at most with the 132-byte row stride) and stores 16 bytes:
+        // the four chunks of a column are 64 contiguous bytes of Qt
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int lc = lane & 7, ch = lane >> 3;
+        for (int task = warp; task < ns * (TC / 8); task += GT / 32) {
+            const int pl = task / (TC / 8), cg = task % (TC / 8);
+            const int cc = cg * 8 + lc;
+            const signed char* src = dig + (pl * TR + ch * 16) * GD_STRIDE1 + cc;
+            unsigned wv[4];
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+                unsigned x = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) x |= (unsigned)(unsigned char)src[(k4 * 4 + k) * GD_STRIDE1] << (8 * k);
+                wv[k4] = x;
+            }
+            if (c0 + cc < p.M)
+                *reinterpret_cast<uint4*>(q.Q + (c0 + cc) * q.ldq + (int64_t)pl * q.kplane + r0 + ch * 16) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        }
+    } else {
+        const int total = ns * TR * (TC / 16);
+        for (int w = threadIdx.x; w < total; w += GT) {
+            const int pl = w / (TR * (TC / 16)), rem = w % (TR * (TC / 16)), lr = rem / (TC / 16), ch = rem % (TC / 16);
+            if (r0 + lr < p.N)
+                *reinterpret_cast<uint4*>(q.Q + (r0 + lr) * q.ldq + (int64_t)pl * q.kplane + c0 + ch * 16) =
+                    *reinterpret_cast<const uint4*>(dig + (pl * TR + lr) * GD_STRIDE0 + ch * 16);
+        }
+    }
+}
+
+template <int KIND>
+int launch_gram_digits(cudaStream_t st, const GramDigitsParams& q, int64_t ntiles) {
+    const int D = q.g.D;
+    int DC = D <= 2 ? 2 : (D <= 4 ? 4 : 8);
+    int Dp = pad_dim(D, DC);
+    size_t smem = sizeof(double) * ((size_t)(TR + TC) * Dp + Dp + 2 * 4 * TC) + GD_DIG_BYTES;
+    dim3 grid((unsigned)ntiles);
+    static PerDeviceOnce once[3];
+    const int dev = current_device();
+#define GPB_GD_LAUNCH(DCV, SLOT)                                                                     \
+    {                                                                                                \
+        auto kern = gram_digits_kernel<KIND, DCV>;                                                   \
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return GPB_ERR_LAUNCH; \
+        kern<<<grid, GT, smem, st>>>(q);                                                             \
+    }
+    (void)once; (void)dev;
+    if (DC == 2) GPB_GD_LAUNCH(2, 0)
+    else if (DC == 4) GPB_GD_LAUNCH(4, 1)
+    else GPB_GD_LAUNCH(8, 2)
+#undef GPB_GD_LAUNCH
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
 template <int KIND>
 int launch_gram(cudaStream_t st, const GramParams& p, int64_t ntiles) {
     int DC = p.D <= 2 ? 2 : (p.D <= 4 ? 4 : 8);
@@ -519,6 +711,41 @@ int gram(stream_t s, const GramDesc& d) {
         case KIND_PERIODIC: return launch_gram<KIND_PERIODIC>(st, p, ntiles);
         case KIND_WHITE: return launch_gram<KIND_WHITE>(st, p, ntiles);
         default: return GPB_ERR_INVALID;
+    }
+}
+
+int gram_digits(stream_t s, const GramDigitsDesc& d) {
+    const GramDesc& g = d.g;
+    if (g.N <= 0 || g.M <= 0 || g.D <= 0 || d.nslices < 1 || d.nslices > OZ_PLANES_MAX) return GPB_ERR_INVALID;
+    if (g.D > MAX_D || d.nslices != OZ_PLANES_MAX) return GPB_ERR_UNSUPPORTED;  // the kernel extracts all 7 planes (what the sparse passes use)
+    if (!g.X || !g.Z || !g.ell || !g.variance || !d.Q || !d.scale || !d.y) return GPB_ERR_INVALID;
+    if (d.kplane % 128 || d.ldq < (int64_t)d.nslices * d.kplane || (d.ldq & 15) || (reinterpret_cast<uintptr_t>(d.Q) & 15))
+        return GPB_ERR_INVALID;
+    if (d.cols_mode ? (d.kplane < g.N || !d.part) : (d.kplane < g.M + 2)) return GPB_ERR_INVALID;
+    GramDigitsParams q;
+    GramParams& p = q.g;
+    p.N = g.N; p.M = g.M; p.D = g.D;
+    p.X = g.X; p.ldx = g.ldx; p.Z = g.Z; p.ldz = g.ldz;
+    p.ell = g.ell; p.ell_is_scalar = g.ell_is_scalar; p.variance = g.variance;
+    p.K = nullptr; p.ldk = 0; p.lower_only = 0; p.diag_add = 0.0; p.diag_add_sq = nullptr; p.row0 = 0; p.col0 = 0; p.k_vec16 = 0;
+    q.cols_mode = d.cols_mode; q.nslices = d.nslices;
+    q.Q = reinterpret_cast<signed char*>(d.Q); q.ldq = d.ldq; q.kplane = d.kplane;
+    q.scale = d.scale; q.y = d.y; q.mean_const = d.mean_const; q.part = d.part;
+    // mode 0: tiles cover kplane columns (zero digits beyond M + 2) x N rows; mode 1: M + 2 columns x kplane rows (zero beyond N)
+    p.tiles_c = d.cols_mode ? (g.M + 2 + TC - 1) / TC : d.kplane / TC;
+    const int64_t tiles_r = d.cols_mode ? d.kplane / TR : (g.N + TR - 1) / TR;
+    const int64_t ntiles = tiles_r * p.tiles_c;
+    if (ntiles > 2147483647LL) return GPB_ERR_UNSUPPORTED;
+    cudaStream_t st = to_stream(s);
+    switch (g.kind) {
+        case KIND_RBF: return launch_gram_digits<KIND_RBF>(st, q, ntiles);
+        case KIND_MATERN32: return launch_gram_digits<KIND_MATERN32>(st, q, ntiles);
+        case KIND_MATERN52: return launch_gram_digits<KIND_MATERN52>(st, q, ntiles);
+        case KIND_MATERN12: return launch_gram_digits<KIND_MATERN12>(st, q, ntiles);
+        case KIND_RATQUAD: return launch_gram_digits<KIND_RATQUAD>(st, q, ntiles);
+        case KIND_PERIODIC: return launch_gram_digits<KIND_PERIODIC>(st, q, ntiles);
+        case KIND_WHITE: return launch_gram_digits<KIND_WHITE>(st, q, ntiles);
+        default: return GPB_ERR_UNSUPPORTED;  // PoweredExponential: k(x, x) != variance, not on the streamed sparse path
     }
 }
 

@@ -52,7 +52,7 @@ constexpr int OZ_THREADS = 384;
 constexpr int OZ_EPI_WARP0 = 4, OZ_EPI_WARPS = 8;
 constexpr int OZ_CHUNK_TILES = 32;  // output tile columns walked together so their B digits stay L2-resident
 constexpr int OZ_SMEM_BYTES = OZ_STAGES * OZ_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int OZ_BETA = OZ_DIGIT_BITS;  // 8: radix-256 digits
+// OZ_BETA (= OZ_DIGIT_BITS = 8), oz_row_exponent and oz_fixed_point live in common.cuh (shared with the fused Gram -> digits kernel)
 
 struct OzParams {
     int m, n;             // output extents
@@ -1434,15 +1434,6 @@ ozaki_i8_kernel_w4(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // so every plane uses the whole int8 range and sum_p d_p 256^(s-1-p) == I exactly.  The top digit stays inside int8 because
 // the row exponent leaves |R| <= 0.494 < (127 - 128/255) / 256.  Truncating the planes after the first s' < s leaves a remainder of
 // at most 0.502 units of plane s' (the device-side plane guard uses a prefix of the extracted planes).
-constexpr double OZ_RMAX = 0.494;
-__device__ __forceinline__ int oz_row_exponent(double mx) {  // mx finite and > 0
-    int e = ilogb(mx) + 2;                   // mx 2^-e in [1/4, 1/2)
-    if (scalbn(mx, -e) > OZ_RMAX) ++e;       // mantissa above 1.976: one more bit of head room for the carry into the top digit
-    return e;
-}
-__device__ __forceinline__ long long oz_fixed_point(double R, int nslices) {
-    return __double2ll_rn(R * __hiloint2double((1023 + OZ_BETA * nslices) << 20, 0));
-}
 // one CTA per row: exponent from the row maximum, then the digits of every entry
 __global__ void __launch_bounds__(128) ozaki_slice_kernel(long long rows, int k, int kplane, const double* __restrict__ X,
                                                           long long ldx, int nslices, signed char* __restrict__ Q,
@@ -1771,6 +1762,13 @@ int col_weighted_sums(stream_t s, int64_t rows, int64_t cols, const double* X, i
     col_wsum_partial_kernel<<<g, 256, 0, to_stream(s)>>>(rows, (int)cols, X, ldx, w, scratch);
     GPB_LAUNCH_CHECK();
     col_wsum_reduce_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, to_stream(s)>>>(chunks, (int)cols, scratch, out_w, out_1);
+    GPB_LAUNCH_CHECK();
+    return GPB_OK;
+}
+
+int col_partials_reduce(stream_t s, int64_t chunks, int64_t cols, const double* part, double* out_w, double* out_1) {
+    if (chunks <= 0 || cols <= 0 || !part || !out_w || !out_1) return GPB_ERR_INVALID;
+    col_wsum_reduce_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, to_stream(s)>>>((int)chunks, (int)cols, part, out_w, out_1);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
 }

@@ -281,6 +281,29 @@ int col_weighted_sums(stream_t s, int64_t rows, int64_t cols, const double* X, i
 constexpr int OZ_DIGIT_BITS = 8;             // radix 256
 constexpr int OZ_DIGIT_SQ_MAX = 128 * 128;   // largest digit-pair product: int32 headroom is nslices * K * 2^14 < 2^31
 constexpr int OZ_PLANES_MAX = 7;             // 56 bits >= the fp64 mantissa (and 8 * 7 + 7 < 63: the fixed-point form fits int64)
+// Fused Gram tile -> digit planes (SGPR / SVGP streamed passes): the K_b block is never written as fp64.  Scales are FIXED from
+// the bound |k(x, z)| <= variance instead of measured maxima (no pass over the block is needed for them):
+//   cols_mode 0 (pass 2): Q[r, p*kplane + c] = digit p of the row [K_b | d | 1 | 0..] (c < kplane), d_r = y_r - mean;
+//                         scale[r] = 2^e, e from max(|variance|, 1, |d_r|)
+//   cols_mode 1 (pass 1): Qt[c, p*kplane + r] = digit p of K_b[r, c] (c < M; rows >= N up to kplane are zero digits),
+//                         scale[c] = 2^e(|variance|); part[(t*2 + 0)*(M+2) + c] = sum over the 64 rows of tile row t of
+//                         d_r * v_rc, part[(t*2 + 1)*(M+2) + c] = sum v_rc, for the M + 2 columns v = [K_b | d | 1]
+//                         (reduced in tile-row order by col_partials_reduce: deterministic)
+struct GramDigitsDesc {
+    GramDesc g;                 // kind, N (rows of the block), M, D, X, Z, ell, variance; K / ldk unused
+    int cols_mode = 0;
+    int nslices = OZ_PLANES_MAX;
+    int8_t* Q = nullptr;
+    int64_t ldq = 0, kplane = 0;   // kplane: multiple of 128, >= M + 2 (mode 0) / >= N (mode 1)
+    double* scale = nullptr;
+    const double* y = nullptr;           // [N]
+    const double* mean_const = nullptr;  // device scalar or null (zero mean)
+    double* part = nullptr;              // mode 1: 2 * gram_digits_tile_rows(kplane) * (M + 2) doubles
+};
+int gram_digits(stream_t s, const GramDigitsDesc& d);
+inline int64_t gram_digits_tile_rows(int64_t kplane) { return (kplane + 63) / 64; }
+// out_w[c] += sum_t part[(t*2+0)*cols + c], out_1[c] += sum_t part[(t*2+1)*cols + c]   (t ascending)
+int col_partials_reduce(stream_t s, int64_t chunks, int64_t cols, const double* part, double* out_w, double* out_1);
 struct OzakiGemmDesc {
     int64_t M = 0, N = 0, K = 0;  // K = digits per plane (multiple of 128)
     int nslices = 6;              // digit planes present in Qa / Qb (and used, unless nslices_dev overrides it)

@@ -10,6 +10,8 @@
 // beyond one block.
 #include "sgpr.h"
 
+#include <cstdlib>
+
 namespace gpb {
 
 #define GPB_TRY(expr)                    \
@@ -118,6 +120,28 @@ static int check_args(const SgprArgs& a) {
     return GPB_OK;
 }
 
+// K_b^T K_b (M x M, lower) += from the column digit planes in ws.oz_qt; K = kp1 block rows are split so that the int32
+// accumulators keep their head room: (t+1) K 128^2 < 2^31  ->  planes * Ksub * 2^14 stays below it
+static int sgpr_stats_syrk_int8(stream_t s, const SgprWs& ws, int64_t M, int64_t ld, int64_t kp1, int64_t ldq1, int planes1) {
+    const int64_t kmax = ((int64_t)((1ll << 31) - 1) / ((int64_t)planes1 * OZ_DIGIT_SQ_MAX)) / 256 * 256;
+    const int64_t nsplit = (kp1 + kmax - 1) / kmax;
+    const int64_t ksub = align_up((kp1 + nsplit - 1) / nsplit, 128);
+    for (int64_t k0 = 0; k0 < kp1; k0 += ksub) {
+        OzakiGemmDesc g;
+        g.M = M; g.N = M; g.K = (kp1 - k0) < ksub ? (kp1 - k0) : ksub; g.nslices = planes1;
+        g.Qa = ws.oz_qt + k0; g.ldqa = ldq1; g.sa = ws.oz_s1; g.Qb = g.Qa; g.ldqb = ldq1; g.sb = ws.oz_s1;
+        g.plane_stride = kp1;
+        g.C = ws.Ppart; g.ldc = ld; g.alpha = 1.0; g.mask = MASK_LOWER;
+        GPB_TRY(ozaki_gemm(s, g));
+    }
+    return GPB_OK;
+}
+// GPB_SGPR_FUSED=0 keeps the round-1 route (fp64 K_b block, then col_absmax / ozaki_slice_t / col_weighted_sums / ozaki_slice)
+static bool sgpr_fused_digits() {
+    static const bool v = [] { const char* e = std::getenv("GPB_SGPR_FUSED"); return !(e && std::atoi(e) == 0); }();
+    return v;
+}
+
 static GramDesc gram_desc(const SgprArgs& a, const double* X, int64_t ldx, int64_t rows, double* K, int64_t ldk) {
     GramDesc g;
     g.kind = a.kind; g.N = rows; g.M = a.M; g.D = a.D;
@@ -179,6 +203,20 @@ int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug) {
     const int planes1 = (ws.oz_qt && ozaki_available() && get_ozaki_slices() != 0) ? OZ_MAX_SLICES : 0;
     for (int64_t r0 = 0; r0 < a.Nloc; r0 += a.block_rows) {
         const int64_t rows = (a.Nloc - r0) < a.block_rows ? (a.Nloc - r0) : a.block_rows;
+        if (raw && planes1 && rows >= OZ_MIN_ROWS && sgpr_fused_digits()) {
+            // Fused route: the Gram tiles of the block are turned into COLUMN digit planes (fixed scale from |k| <= variance) and into
+            // per-tile-row partial sums of the two augmented statistics rows inside ONE kernel -- K_b never exists as fp64.
+            const int64_t kp1 = align_up(rows, 128), ldq1 = OZ_MAX_SLICES * ws.oz_kplane1;
+            GramDigitsDesc gd;
+            gd.g = gram_desc(a, a.X + r0 * a.ldx, a.ldx, rows, nullptr, 0);
+            gd.cols_mode = 1; gd.nslices = planes1;
+            gd.Q = ws.oz_qt; gd.ldq = ldq1; gd.kplane = kp1; gd.scale = ws.oz_s1;
+            gd.y = a.y + r0; gd.mean_const = a.mean_const; gd.part = ws.T1;
+            GPB_TRY(gram_digits(s, gd));
+            GPB_TRY(sgpr_stats_syrk_int8(s, ws, M, ld, kp1, ldq1, planes1));
+            GPB_TRY(col_partials_reduce(s, gram_digits_tile_rows(kp1), ld, ws.T1, ws.Ppart + M * ld, ws.Ppart + (M + 1) * ld));
+            continue;
+        }
         // K_b^T = k(X_b, Z)   (objectives.py:355, one row block)
         GPB_TRY(gram(s, gram_desc(a, a.X + r0 * a.ldx, a.ldx, rows, raw ? ws.T2 : ws.T1, ld)));
         if (!raw) {
@@ -198,18 +236,7 @@ int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug) {
             // whitened, which amplifies their rounding by cond(Kzz)); the two augmented rows [d ; 1]^T [K_b | d | 1] are GEMVs.
             const int64_t kp1 = align_up(rows, 128), ldq1 = OZ_MAX_SLICES * ws.oz_kplane1;
             GPB_TRY(ozaki_slice_t(s, rows, M, kp1, ws.T2, ld, planes1, ws.oz_qt, ldq1, ws.oz_s1, ws.oz_colmax));
-            // int32 headroom: (t+1) K 128^2 < 2^31  ->  split K so that planes * Ksub * 2^14 stays below it
-            const int64_t kmax = ((int64_t)((1ll << 31) - 1) / ((int64_t)planes1 * OZ_DIGIT_SQ_MAX)) / 256 * 256;
-            const int64_t nsplit = (kp1 + kmax - 1) / kmax;
-            const int64_t ksub = align_up((kp1 + nsplit - 1) / nsplit, 128);
-            for (int64_t k0 = 0; k0 < kp1; k0 += ksub) {
-                OzakiGemmDesc g;
-                g.M = M; g.N = M; g.K = (kp1 - k0) < ksub ? (kp1 - k0) : ksub; g.nslices = planes1;
-                g.Qa = ws.oz_qt + k0; g.ldqa = ldq1; g.sa = ws.oz_s1; g.Qb = g.Qa; g.ldqb = ldq1; g.sb = ws.oz_s1;
-                g.plane_stride = kp1;
-                g.C = ws.Ppart; g.ldc = ld; g.alpha = 1.0; g.mask = MASK_LOWER;
-                GPB_TRY(ozaki_gemm(s, g));
-            }
+            GPB_TRY(sgpr_stats_syrk_int8(s, ws, M, ld, kp1, ldq1, planes1));
             // rows M, M+1 of the statistics: [d ; 1]^T [K_b | d | 1]   (T1 is free here in both routes: scratch)
             GPB_TRY(sub_scalar(s, rows, a.y + r0, a.mean_const, ws.oz_st));
             GPB_TRY(col_weighted_sums(s, rows, ld, ws.T2, ld, ws.oz_st, ws.T1, ws.Ppart + M * ld, ws.Ppart + (M + 1) * ld));
@@ -308,11 +335,21 @@ int sgpr_grad_local(stream_t s, const SgprArgs& a, const SgprWs& ws, double* g_Z
     if (planes) GPB_TRY(ozaki_slice(s, M, ld, kp, ws.Caug, ld, planes, ws.oz_qc, ldq, ws.oz_sc));
     for (int64_t r0 = 0; r0 < a.Nloc; r0 += a.block_rows) {
         const int64_t rows = (a.Nloc - r0) < a.block_rows ? (a.Nloc - r0) : a.block_rows;
-        GPB_TRY(gram(s, gram_desc(a, a.X + r0 * a.ldx, a.ldx, rows, ws.T1, ld)));
-        GPB_TRY(sgpr_aug_columns(s, rows, ws.T1, ld, M, a.y + r0, a.mean_const));
+        const bool fused = planes && rows >= OZ_MIN_ROWS && sgpr_fused_digits();
+        if (fused) {  // Gram tiles -> ROW digit planes of [K_b^T | d_b | 1] directly (scale from max(|variance|, 1, |d_r|))
+            GramDigitsDesc gd;
+            gd.g = gram_desc(a, a.X + r0 * a.ldx, a.ldx, rows, nullptr, 0);
+            gd.cols_mode = 0; gd.nslices = planes;
+            gd.Q = ws.oz_qt; gd.ldq = ldq; gd.kplane = kp; gd.scale = ws.oz_st;
+            gd.y = a.y + r0; gd.mean_const = a.mean_const;
+            GPB_TRY(gram_digits(s, gd));
+        } else {
+            GPB_TRY(gram(s, gram_desc(a, a.X + r0 * a.ldx, a.ldx, rows, ws.T1, ld)));
+            GPB_TRY(sgpr_aug_columns(s, rows, ws.T1, ld, M, a.y + r0, a.mean_const));
+        }
         // dK_b^T = [K_b^T | d_b | 1] Caug^T   (= K_b^T C + d_b cvec^T)
         if (planes && rows >= OZ_MIN_ROWS) {
-            GPB_TRY(ozaki_slice(s, rows, ld, kp, ws.T1, ld, planes, ws.oz_qt, ldq, ws.oz_st));
+            if (!fused) GPB_TRY(ozaki_slice(s, rows, ld, kp, ws.T1, ld, planes, ws.oz_qt, ldq, ws.oz_st));
             OzakiGemmDesc g;
             g.M = rows; g.N = M; g.K = kp; g.nslices = planes;
             g.Qa = ws.oz_qt; g.ldqa = ldq; g.sa = ws.oz_st; g.Qb = ws.oz_qc; g.ldqb = ldq; g.sb = ws.oz_sc;

@@ -603,6 +603,78 @@ int ozaki_gemm(stream_t, const OzakiGemmDesc& d) {
         }
     return GPB_OK;
 }
+int gram_digits(stream_t, const GramDigitsDesc& d) {
+    const GramDesc& g = d.g;
+    if (g.N <= 0 || g.M <= 0 || g.D <= 0 || d.nslices < 1 || d.nslices > OZ_PLANES_MAX) return GPB_ERR_INVALID;
+    if (!g.X || !g.Z || !g.ell || !g.variance || !d.Q || !d.scale || !d.y) return GPB_ERR_INVALID;
+    if (d.kplane % 128 || d.ldq < (int64_t)d.nslices * d.kplane) return GPB_ERR_INVALID;
+    if (d.cols_mode ? (d.kplane < g.N || !d.part) : (d.kplane < g.M + 2)) return GPB_ERR_INVALID;
+    if (g.kind == KIND_POWEXP || !kind_valid(g.kind)) return GPB_ERR_UNSUPPORTED;
+    const double mean = d.mean_const ? d.mean_const[0] : 0.0;
+    const double avar = std::fabs(g.variance[0]);
+    const bool var_bad = !(avar <= std::numeric_limits<double>::max());
+    const int e_var = (!var_bad && avar > 0.0) ? oz_row_exponent_host(avar) : 0;
+    auto value = [&](int64_t r, int64_t c) -> double {
+        if (r >= g.N) return 0.0;
+        if (c < g.M) {
+            PairOut po;
+            pair_eval(g.kind, g.X + r * g.ldx, g.Z + c * g.ldz, g.D, g.ell, g.ell_is_scalar, g.variance, po);
+            return po.k;
+        }
+        if (c == g.M) return d.y[r] - mean;
+        if (c == g.M + 1) return 1.0;
+        return 0.0;
+    };
+    auto digits = [&](double v, int e, bool bad, int8_t* out, int64_t stride) {
+        long long I = bad ? 0 : std::llrint(std::scalbn(v, -e + OZ_DIGIT_BITS * d.nslices));
+        for (int p = d.nslices - 1; p >= 0; --p) {
+            const int dg = (int)((I + 128) & 255) - 128;
+            out[(int64_t)p * stride] = (int8_t)dg;
+            I = (I - dg) >> 8;
+        }
+        return I == 0;
+    };
+    if (!d.cols_mode) {
+        for (int64_t r = 0; r < g.N; ++r) {
+            const double dr = d.y[r] - mean;
+            const double mx = std::max(std::max(avar, 1.0), std::fabs(dr));
+            const bool bad = var_bad || !(mx <= std::numeric_limits<double>::max());
+            const int e = bad ? 0 : oz_row_exponent_host(mx);
+            d.scale[r] = bad ? std::numeric_limits<double>::quiet_NaN() : std::scalbn(1.0, e);
+            for (int64_t c = 0; c < d.kplane; ++c)
+                if (!digits(value(r, c), e, bad, d.Q + r * d.ldq + c, d.kplane)) return GPB_ERR_INVALID;
+        }
+        return GPB_OK;
+    }
+    const int64_t cols = g.M + 2, tiles = gram_digits_tile_rows(d.kplane);
+    for (int64_t c = 0; c < g.M; ++c) {
+        d.scale[c] = var_bad ? std::numeric_limits<double>::quiet_NaN() : (avar > 0.0 ? std::scalbn(1.0, e_var) : 1.0);
+        for (int64_t r = 0; r < d.kplane; ++r)
+            if (!digits(value(r, c), e_var, var_bad, d.Q + c * d.ldq + r, d.kplane)) return GPB_ERR_INVALID;
+    }
+    for (int64_t t = 0; t < tiles; ++t)
+        for (int64_t c = 0; c < cols; ++c) {
+            double sw = 0.0, s1 = 0.0;
+            for (int64_t r = t * 64; r < std::min<int64_t>((t + 1) * 64, g.N); ++r) {
+                const double v = value(r, c);
+                sw += (d.y[r] - mean) * v;
+                s1 += v;
+            }
+            d.part[(t * 2 + 0) * cols + c] = sw;
+            d.part[(t * 2 + 1) * cols + c] = s1;
+        }
+    return GPB_OK;
+}
+int col_partials_reduce(stream_t, int64_t chunks, int64_t cols, const double* part, double* out_w, double* out_1) {
+    if (chunks <= 0 || cols <= 0 || !part || !out_w || !out_1) return GPB_ERR_INVALID;
+    for (int64_t c = 0; c < cols; ++c) {
+        double sw = 0.0, s1 = 0.0;
+        for (int64_t k = 0; k < chunks; ++k) { sw += part[(k * 2 + 0) * cols + c]; s1 += part[(k * 2 + 1) * cols + c]; }
+        out_w[c] += sw;
+        out_1[c] += s1;
+    }
+    return GPB_OK;
+}
 int igemm_i8(stream_t, int64_t m, int64_t n, int64_t k, const int8_t* A, int64_t lda, const int8_t* B, int64_t ldb, int32_t* C,
              int64_t ldc) {
     for (int64_t i = 0; i < m; ++i)
