@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(GT, 2) gram_digits_kernel(const GramDigitsPara
     double* Zs = sm + TR * Dp;     // [Dp][TC]
     double* ell_s = Zs + Dp * TC;  // [Dp]  (periodic only)
     double* red = ell_s + Dp;      // [2][4][TC]  (mode 1: partial column sums per ty group)
-    signed char* dig = reinterpret_cast<signed char*>(red + 2 * 4 * TC);
+    double* aux = red + 2 * 4 * TC;  // [2][TR]: per-row multiplier (mode 0) and d_r = y_r - mean
+    signed char* dig = reinterpret_cast<signed char*>(aux + 2 * TR);
     constexpr bool PER = (KIND == KIND_PERIODIC);
     constexpr bool SHP = (KIND == KIND_RATQUAD || KIND == KIND_POWEXP || KIND == KIND_PERIODIC);
     const int64_t tr = blockIdx.x / p.tiles_c, tc = blockIdx.x % p.tiles_c;
@@ -197,19 +198,23 @@ __global__ void __launch_bounds__(GT, 2) gram_digits_kernel(const GramDigitsPara
     const int e_var = (!var_bad && avar > 0.0) ? oz_row_exponent(avar) : 0;
     // per-row multiplier 2^(8 s - e_r) (0 for a poisoned row), computed ONCE per row: mode 0 scales a row by the bound
     // max(|variance|, 1, |d_r|), mode 1 every column by |variance|
-    double* mul_s = red;  // [TR] (mode 0; `red` is only used by mode 1)
-    if (!q.cols_mode && threadIdx.x < TR) {
+    double* mul_s = aux;
+    double* dr_s = aux + TR;
+    if (threadIdx.x < TR) {
         const int64_t r = r0 + threadIdx.x;
-        double m_ = 0.0;
+        double m_ = 0.0, dr = 0.0;
         if (r < p.N) {
-            const double dr = q.y[r] - mean;
-            const double mx = fmax(fmax(avar, 1.0), fabs(dr));
-            const bool bad = var_bad || !(mx <= 1.7976931348623157e308);
-            const int e = bad ? 0 : oz_row_exponent(mx);
-            if (!bad) m_ = scalbn(1.0, OZ_BETA * ns - e);
-            if (tc == 0) q.scale[r] = bad ? __longlong_as_double(0x7ff8000000000000LL) : scalbn(1.0, e);
+            dr = q.y[r] - mean;
+            if (!q.cols_mode) {
+                const double mx = fmax(fmax(avar, 1.0), fabs(dr));
+                const bool bad = var_bad || !(mx <= 1.7976931348623157e308);
+                const int e = bad ? 0 : oz_row_exponent(mx);
+                if (!bad) m_ = scalbn(1.0, OZ_BETA * ns - e);
+                if (tc == 0) q.scale[r] = bad ? __longlong_as_double(0x7ff8000000000000LL) : scalbn(1.0, e);
+            }
         }
         mul_s[threadIdx.x] = m_;
+        dr_s[threadIdx.x] = dr;
     }
     __syncthreads();
     double r2[RPT][2];
@@ -224,7 +229,7 @@ __global__ void __launch_bounds__(GT, 2) gram_digits_kernel(const GramDigitsPara
         const int lr = ty + 4 * i;
         const int64_t r = r0 + lr;
         const bool rok = r < p.N;
-        const double dr = rok ? q.y[r] - mean : 0.0;
+        const double dr = dr_s[lr];
         double v[2];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -319,7 +324,7 @@ int launch_gram_digits(cudaStream_t st, const GramDigitsParams& q, int64_t ntile
     const int D = q.g.D;
     int DC = D <= 2 ? 2 : (D <= 4 ? 4 : 8);
     int Dp = pad_dim(D, DC);
-    size_t smem = sizeof(double) * ((size_t)(TR + TC) * Dp + Dp + 2 * 4 * TC) + GD_DIG_BYTES;
+    size_t smem = sizeof(double) * ((size_t)(TR + TC) * Dp + Dp + 2 * 4 * TC + 2 * TR) + GD_DIG_BYTES;
     dim3 grid((unsigned)ntiles);
     static PerDeviceOnce once[3];
     const int dev = current_device();
@@ -373,7 +378,7 @@ int launch_gram(cudaStream_t st, const GramParams& p, int64_t ntiles) {
 template <int DC, bool WANT_X, bool WANT_Z, bool PER = false>
 __device__ __forceinline__ void contract_dims(const double* __restrict__ Xs, const double* __restrict__ Zs,
                                               int Dp, int tx, int ty, const double (&G)[RPT][2],
-                                              double* __restrict__ ell_acc /*[Dp] smem, atomically added*/,
+                                              double* __restrict__ ell_acc /*[GT/32][Dp] smem: one slot row per warp, summed in a fixed order by the caller*/,
                                               double* __restrict__ gx_s /*[TR][Dp] smem*/,
                                               double* __restrict__ gz_s /*[Dp][TC] smem*/,
                                               const double* __restrict__ ell_s = nullptr, double pc = 0.0,
@@ -427,7 +432,7 @@ __device__ __forceinline__ void contract_dims(const double* __restrict__ Xs, con
 #pragma unroll
         for (int d = 0; d < DC; ++d) {
             double v = warp_sum(acc[d]);
-            if ((threadIdx.x & 31) == 0) atomicAdd(ell_acc + d0 + d, v);
+            if ((threadIdx.x & 31) == 0) ell_acc[(threadIdx.x >> 5) * Dp + d0 + d] = v;  // every (warp, d) is written exactly once
             if (WANT_Z) {
                 atomicAdd(gz_s + (d0 + d) * TC + 2 * tx, gz0[d]);
                 atomicAdd(gz_s + (d0 + d) * TC + 2 * tx + 1, gz1[d]);
@@ -458,8 +463,8 @@ __global__ void __launch_bounds__(GT, (WANT_X || WANT_Z) ? 1 : 2) gram_bwd_kerne
     const int Dp = pad_dim(p.D, DC);
     double* Xs = sm;                     // [TR][Dp]
     double* Zs = Xs + TR * Dp;           // [Dp][TC]
-    double* ell_acc = Zs + Dp * TC;      // [Dp]
-    double* red = ell_acc + Dp;          // [32]
+    double* ell_acc = Zs + Dp * TC;      // [GT/32][Dp]: per-warp sums, added in warp order (deterministic)
+    double* red = ell_acc + (GT / 32) * Dp;  // [32]
     double* ell_s = red + 32;            // [Dp]       (periodic only)
     double* gx_s = ell_s + Dp;           // [TR][Dp]   (WANT_X)
     double* gz_s = gx_s + (WANT_X ? TR * Dp : 0);  // [Dp][TC]   (WANT_Z)
@@ -470,7 +475,7 @@ __global__ void __launch_bounds__(GT, (WANT_X || WANT_Z) ? 1 : 2) gram_bwd_kerne
     load_scaled<true, PER>(Xs, p.X, p.ldx, r0, p.N, TR, p.D, Dp, p.ell, p.ell_is_scalar);
     load_scaled<false, PER>(Zs, p.Z, p.ldz, c0, p.M, TC, p.D, Dp, p.ell, p.ell_is_scalar);
     if (PER) load_ell(ell_s, p.ell, p.ell_is_scalar, p.D, Dp);
-    for (int i = threadIdx.x; i < Dp; i += GT) ell_acc[i] = 0.0;
+    for (int i = threadIdx.x; i < (GT / 32) * Dp; i += GT) ell_acc[i] = 0.0;
     if (WANT_X)
         for (int i = threadIdx.x; i < TR * Dp; i += GT) gx_s[i] = 0.0;
     if (WANT_Z)
@@ -503,7 +508,12 @@ __global__ void __launch_bounds__(GT, (WANT_X || WANT_Z) ? 1 : 2) gram_bwd_kerne
     double s2 = SHP ? block_sum(wshp, red) : 0.0;
     double* out = p.partials + (int64_t)blockIdx.x * (Dp + 2);
     if (threadIdx.x == 0) { out[Dp] = s; out[Dp + 1] = s2; }
-    for (int i = threadIdx.x; i < Dp; i += GT) out[i] = ell_acc[i];
+    for (int i = threadIdx.x; i < Dp; i += GT) {
+        double a = 0.0;
+#pragma unroll
+        for (int w = 0; w < GT / 32; ++w) a += ell_acc[w * Dp + i];
+        out[i] = a;
+    }
     {
         // dr2/dx_d = 2 (xs_d - zs_d) / l_d ; dr2/dz_d = -2 (xs_d - zs_d) / l_d
         if (WANT_X && p.g_X) {
@@ -579,8 +589,8 @@ __global__ void __launch_bounds__(GT, 2) mll_bwd_kernel(const MllBwdParams p) {
     const int Dp = pad_dim(p.D, DC);
     double* Xs = sm;
     double* Zs = Xs + TR * Dp;
-    double* ell_acc = Zs + Dp * TC;
-    double* red = ell_acc + Dp;
+    double* ell_acc = Zs + Dp * TC;  // [GT/32][Dp]: per-warp sums, added in warp order (deterministic)
+    double* red = ell_acc + (GT / 32) * Dp;
     double* ell_s = red + 32;  // [Dp] (periodic only)
     constexpr bool PER = (KIND == KIND_PERIODIC);
     constexpr bool SHP = (KIND == KIND_RATQUAD || KIND == KIND_POWEXP || KIND == KIND_PERIODIC);
@@ -595,7 +605,7 @@ __global__ void __launch_bounds__(GT, 2) mll_bwd_kernel(const MllBwdParams p) {
     load_scaled<true, PER>(Xs, p.X, p.ldx, r0, p.N, TR, p.D, Dp, p.ell, p.ell_is_scalar);
     load_scaled<false, PER>(Zs, p.X, p.ldx, c0, p.N, TC, p.D, Dp, p.ell, p.ell_is_scalar);
     if (PER) load_ell(ell_s, p.ell, p.ell_is_scalar, p.D, Dp);
-    for (int i = threadIdx.x; i < Dp; i += GT) ell_acc[i] = 0.0;
+    for (int i = threadIdx.x; i < (GT / 32) * Dp; i += GT) ell_acc[i] = 0.0;
     __syncthreads();
     const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
     const double var = p.variance[0];
@@ -636,7 +646,12 @@ __global__ void __launch_bounds__(GT, 2) mll_bwd_kernel(const MllBwdParams p) {
     double s2 = block_sum(trw, red);
     double s3 = SHP ? block_sum(wshp, red) : 0.0;
     if (threadIdx.x == 0) { out[Dp] = s1; out[Dp + 1] = s2; out[Dp + 2] = s3; }
-    for (int i = threadIdx.x; i < Dp; i += GT) out[i] = ell_acc[i];
+    for (int i = threadIdx.x; i < Dp; i += GT) {
+        double a = 0.0;
+#pragma unroll
+        for (int w = 0; w < GT / 32; ++w) a += ell_acc[w * Dp + i];
+        out[i] = a;
+    }
 }
 
 __global__ void mll_bwd_reduce_kernel(const double* __restrict__ partials, int64_t ntiles, int Dp, int D,
@@ -757,7 +772,7 @@ int64_t gram_bwd_partials_count(int64_t N, int64_t M, int D) {
 template <int KIND, int DCV, bool WX, bool WZ>
 static int launch_gram_bwd_one(cudaStream_t st, const GramBwdParams& p, int64_t ntiles) {
     int Dp = pad_dim(p.D, DCV);
-    size_t smem = sizeof(double) * ((size_t)(TR + TC) * Dp + (WX ? TR * Dp : 0) + (WZ ? TC * Dp : 0) + 2 * Dp + 32);
+    size_t smem = sizeof(double) * ((size_t)(TR + TC) * Dp + (WX ? TR * Dp : 0) + (WZ ? TC * Dp : 0) + (GT / 32 + 1) * Dp + 32);
     auto kern = gram_bwd_kernel<KIND, DCV, WX, WZ>;
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -829,7 +844,7 @@ template <int KIND>
 static int launch_mll_bwd(cudaStream_t st, const MllBwdParams& p, int64_t ntiles) {
     int DC = pick_dc(p.D);
     int Dp = pad_dim(p.D, DC);
-    size_t smem = sizeof(double) * ((size_t)(TR + TC) * Dp + 2 * Dp + 32);
+    size_t smem = sizeof(double) * ((size_t)(TR + TC) * Dp + (GT / 32 + 1) * Dp + 32);
     dim3 grid((unsigned)ntiles);
 #define GPB_MLL_LAUNCH(DCV)                                                                          \
     {                                                                                                \

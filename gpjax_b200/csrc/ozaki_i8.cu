@@ -1585,6 +1585,25 @@ __global__ void col_wsum_reduce_kernel(int chunks, int cols, const double* __res
     out_1[c] += s1;
 }
 
+// same reduction for many chunks (the fused Gram -> digits kernel leaves one partial per 64-row tile row: 1024 per block): eight
+// row groups walk interleaved chunk subsets, then a fixed-order sum of the eight -- deterministic, 8x the parallelism
+__global__ void __launch_bounds__(256) col_partials_reduce_kernel(int chunks, int cols, const double* __restrict__ part,
+                                                                  double* __restrict__ out_w, double* __restrict__ out_1) {
+    __shared__ double red[2][8][32];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    double sw = 0.0, s1 = 0.0;
+    if (c < cols)
+        for (int k = threadIdx.y; k < chunks; k += 8) { sw += part[((long long)k * 2 + 0) * cols + c]; s1 += part[((long long)k * 2 + 1) * cols + c]; }
+    red[0][threadIdx.y][threadIdx.x] = sw;
+    red[1][threadIdx.y][threadIdx.x] = s1;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < cols) {
+        for (int i = 1; i < 8; ++i) { sw += red[0][i][threadIdx.x]; s1 += red[1][i][threadIdx.x]; }
+        out_w[c] += sw;
+        out_1[c] += s1;
+    }
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1768,7 +1787,7 @@ int col_weighted_sums(stream_t s, int64_t rows, int64_t cols, const double* X, i
 
 int col_partials_reduce(stream_t s, int64_t chunks, int64_t cols, const double* part, double* out_w, double* out_1) {
     if (chunks <= 0 || cols <= 0 || !part || !out_w || !out_1) return GPB_ERR_INVALID;
-    col_wsum_reduce_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, to_stream(s)>>>((int)chunks, (int)cols, part, out_w, out_1);
+    col_partials_reduce_kernel<<<(unsigned)((cols + 31) / 32), dim3(32, 8), 0, to_stream(s)>>>((int)chunks, (int)cols, part, out_w, out_1);
     GPB_LAUNCH_CHECK();
     return GPB_OK;
 }
