@@ -103,7 +103,7 @@ __device__ __forceinline__ int oz_groups(const OzParams& p, int mode) {
     if (mode == 0) return 1;
     if (!p.planes_dev) return p.nslices;
     const int v = __ldg(p.planes_dev);
-    return v < 1 ? 1 : (v > p.nslices ? p.nslices : v);
+    return (v < 1 || v > p.nslices) ? p.nslices : v;  // a word nobody set (zero / garbage) means every plane, never fewer
 }
 
 // Even plane count s: the truncation set {p + q < s} would drop the pair (s/2, s/2), the product of two digits of EQUAL weight.
@@ -1444,7 +1444,7 @@ __global__ void __launch_bounds__(128) ozaki_slice_kernel(long long rows, int k,
     if (r >= rows) return;
     if (nslices_dev) {  // the plane count the product will use: round THERE (uniform across the grid)
         const int v = __ldg(nslices_dev);
-        nslices = v < 1 ? 1 : (v < nslices ? v : nslices);
+        nslices = (v < 1 || v > nslices) ? nslices : v;
     }
     const double* x = X + r * ldx;
     double mx = 0.0;

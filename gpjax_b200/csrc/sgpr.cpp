@@ -185,6 +185,9 @@ int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug) {
     gz.lower_only = 1; gz.diag_add = a.jitter;
     GPB_TRY(gram(s, gz));
     GPB_TRY(fill2d(s, 1, 2, reinterpret_cast<double*>(ws.info2), 2, 0.0));  // clears both info words (bit pattern 0)
+    // M >= 3072 crosses the int8 threshold of the blocked factorisation: the device word the digit kernels read must be set
+    // (a bare M x M matrix: all 7 planes) -- it is part of the workspace and starts out uninitialised
+    GPB_TRY(factor_set_planes(s, ws.fz, M, nullptr, nullptr, 0.0));
     GPB_TRY(potrf_lower(s, M, ws.Lz, M, ws.fz, ws.info2));
     GPB_TRY(zero_triangle(s, M, ws.Lz, M, 2));
     // explicit inverse factor (lower, physically zero above the diagonal)
@@ -288,6 +291,7 @@ int sgpr_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const double* P
     GPB_TRY(sgpr_prepare(s, M, Paug, ld, a.obs_stddev, ws.Bmat, ws.psi, ws.a1, ws.sc));
     // L L^T = I + A A^T   (objectives.py:393-396)
     GPB_TRY(copy2d(s, M, M, ws.Bmat, M, ws.LB, M));
+    GPB_TRY(factor_set_planes(s, ws.fb, M, nullptr, nullptr, 0.0));
     GPB_TRY(potrf_lower(s, M, ws.LB, M, ws.fb, ws.info2 + 1));
     GPB_TRY(sum_log_diag(s, M, ws.LB, M, hl));              // :399
     GPB_TRY(copy2d(s, 1, M, ws.psi, M, ws.w, M));

@@ -53,6 +53,8 @@ __all__ = [
     "conjugate_predict",
     "gram_longdouble",
     "conjugate_mll_longdouble",
+    "collapsed_elbo_longdouble",
+    "collapsed_elbo_grad_longdouble_fd",
     "reference_cpu_mll_value_and_grad",
     "reference_cpu_elbo_value_and_grad",
     "svgp_elbo",
@@ -647,6 +649,114 @@ def conjugate_mll_longdouble(kind, X, y, lengthscale, variance, obs_stddev, mean
         w[i] = (d[i] - L[i, :i] @ w[:i]) / L[i, i]
     val = ld(-0.5) * (n * np.log(2 * ld(np.pi)) + 2 * np.sum(np.log(np.diag(L))) + w @ w)
     return val
+
+
+def _chol_longdouble(S):
+    n = S.shape[0]
+    L = np.zeros_like(S)
+    for j in range(n):
+        v = S[j:, j] - L[j:, :j] @ L[j, :j]
+        L[j, j] = np.sqrt(v[0])
+        L[j + 1 :, j] = v[1:] / L[j, j]
+    return L
+
+
+def _trsm_longdouble(L, B):
+    """L^-1 B by forward substitution, 80-bit."""
+    X = np.zeros_like(B)
+    for i in range(L.shape[0]):
+        X[i] = (B[i] - L[i, :i] @ X[:i]) / L[i, i]
+    return X
+
+
+def collapsed_elbo_longdouble(kind, X, y, Z, lengthscale, variance, obs_stddev, mean_const=0.0, jitter=1e-6):
+    """gpjax/objectives.py:342-416 in 80-bit arithmetic (unblocked Cholesky / substitution; M <= ~100, N <= ~1000): the
+    adjudicator for disagreements between two float64 evaluation orders of the collapsed bound."""
+    ld = np.longdouble
+    X = np.asarray(X, np.float64)
+    Z = np.asarray(Z, np.float64)
+    n, m = X.shape[0], Z.shape[0]
+    noise = ld(obs_stddev) ** 2
+    Kzz = gram_longdouble(kind, Z, Z, lengthscale, variance) + np.eye(m, dtype=ld) * ld(jitter)
+    Kzx = gram_longdouble(kind, Z, X, lengthscale, variance)
+    diff = np.asarray(y, np.float64).reshape(-1).astype(ld) - ld(mean_const)
+    Lz = _chol_longdouble(Kzz)
+    A = _trsm_longdouble(Lz, Kzx) / np.sqrt(noise)
+    AAT = A @ A.T
+    L = _chol_longdouble(np.eye(m, dtype=ld) + AAT)
+    c = _trsm_longdouble(L, (A @ diff).reshape(-1, 1)).reshape(-1)
+    quad = (diff @ diff - c @ c) / noise
+    two_log_prob = -n * np.log(2 * ld(np.pi) * noise) - 2 * np.sum(np.log(np.diag(L))) - quad
+    two_trace = n * ld(variance) / noise - np.trace(AAT)  # k(x, x) = variance for the kernels gram_longdouble covers
+    return (two_log_prob - two_trace) / 2
+
+
+def collapsed_elbo_grad_longdouble_fd(kind, X, y, Z, lengthscale, variance, obs_stddev, mean_const=0.0, jitter=1e-6, h=1e-6):
+    """Central differences of the 80-bit value (step h: truncation ~h^2, round-off ~1e-19 / h -> ~1e-12 relative): gradient with
+    respect to lengthscale (vector), variance, obs_stddev, mean_const and the inducing inputs, as a dict like the autodiff oracle's."""
+    ld = np.longdouble
+    ell = np.atleast_1d(np.asarray(lengthscale, np.float64)).astype(ld)
+    Zl = np.asarray(Z, np.float64).astype(ld)
+
+    def f(ell_, var_, sn_, c_, Z_):
+        return collapsed_elbo_longdouble_raw(kind, X, y, Z_, ell_, var_, sn_, c_, jitter)
+
+    base = (ell, ld(variance), ld(obs_stddev), ld(mean_const), Zl)
+    out = {}
+    g = np.zeros(ell.shape[0])
+    for i in range(ell.shape[0]):
+        e = np.zeros_like(ell); e[i] = ld(h)
+        g[i] = float((f(ell + e, *base[1:]) - f(ell - e, *base[1:])) / (2 * ld(h)))
+    out["lengthscale"] = g
+    out["variance"] = float((f(ell, base[1] + ld(h), *base[2:]) - f(ell, base[1] - ld(h), *base[2:])) / (2 * ld(h)))
+    out["obs_stddev"] = float((f(ell, base[1], base[2] + ld(h), base[3], Zl) - f(ell, base[1], base[2] - ld(h), base[3], Zl)) / (2 * ld(h)))
+    out["mean_const"] = float((f(ell, base[1], base[2], base[3] + ld(h), Zl) - f(ell, base[1], base[2], base[3] - ld(h), Zl)) / (2 * ld(h)))
+    gz = np.zeros(Zl.shape)
+    for a in range(Zl.shape[0]):
+        for b in range(Zl.shape[1]):
+            E = np.zeros_like(Zl); E[a, b] = ld(h)
+            gz[a, b] = float((f(ell, base[1], base[2], base[3], Zl + E) - f(ell, base[1], base[2], base[3], Zl - E)) / (2 * ld(h)))
+    out["inducing_inputs"] = gz
+    return out
+
+
+def collapsed_elbo_longdouble_raw(kind, X, y, Z, ell, variance, obs_stddev, mean_const, jitter):
+    """collapsed_elbo_longdouble with 80-bit PARAMETERS (the finite differences perturb them below float64 resolution)."""
+    ld = np.longdouble
+    kind = _kind_id(kind)
+    Xl = np.asarray(X, np.float64).astype(ld)
+    n, m = Xl.shape[0], Z.shape[0]
+
+    def gram_ld(a, b):
+        xs, zs = a / ell, b / ell
+        r2 = np.zeros((a.shape[0], b.shape[0]), ld)
+        for k in range(a.shape[1]):
+            dd = xs[:, k : k + 1] - zs[:, k][None, :]
+            r2 += dd * dd
+        if kind == 0:
+            return variance * np.exp(ld(-0.5) * r2)
+        tau = np.sqrt(np.maximum(r2, ld(1e-36)))
+        if kind == 3:
+            return variance * np.exp(-tau)
+        if kind == 1:
+            s3 = np.sqrt(ld(3.0))
+            return variance * (1 + s3 * tau) * np.exp(-s3 * tau)
+        s5 = np.sqrt(ld(5.0))
+        return variance * (1 + s5 * tau + ld(5.0) / ld(3.0) * tau * tau) * np.exp(-s5 * tau)
+
+    noise = obs_stddev * obs_stddev
+    Kzz = gram_ld(Z, Z) + np.eye(m, dtype=ld) * ld(jitter)
+    Kzx = gram_ld(Z, Xl)
+    diff = np.asarray(y, np.float64).reshape(-1).astype(ld) - mean_const
+    Lz = _chol_longdouble(Kzz)
+    A = _trsm_longdouble(Lz, Kzx) / np.sqrt(noise)
+    AAT = A @ A.T
+    L = _chol_longdouble(np.eye(m, dtype=ld) + AAT)
+    c = _trsm_longdouble(L, (A @ diff).reshape(-1, 1)).reshape(-1)
+    quad = (diff @ diff - c @ c) / noise
+    two_log_prob = -n * np.log(2 * ld(np.pi) * noise) - 2 * np.sum(np.log(np.diag(L))) - quad
+    two_trace = n * variance / noise - np.trace(AAT)
+    return (two_log_prob - two_trace) / 2
 
 
 # ----------------------------------------------------------------------------------------

@@ -474,7 +474,7 @@ int ozaki_slice(stream_t, int64_t rows, int64_t k, int64_t kplane, const double*
                 int64_t ldq, double* scale, const int* nslices_dev) {
     if (rows < 0 || k <= 0 || kplane < k || nslices < 1 || nslices > OZ_PLANES_MAX || !X || !Q || !scale || ldq < (int64_t)nslices * kplane)
         return GPB_ERR_INVALID;
-    if (nslices_dev) nslices = std::min(std::max(nslices_dev[0], 1), nslices);
+    if (nslices_dev) nslices = (nslices_dev[0] < 1 || nslices_dev[0] > nslices) ? nslices : nslices_dev[0];
     for (int64_t r = 0; r < rows; ++r) {
         double mx = 0.0;
         bool bad = false;
@@ -547,7 +547,7 @@ int ozaki_gemm(stream_t, const OzakiGemmDesc& d) {
         return GPB_ERR_INVALID;
     if (d.K % 128 || (int64_t)d.nslices * d.K * OZ_DIGIT_SQ_MAX >= (1ll << 31)) return GPB_ERR_UNSUPPORTED;
     if (d.mask == MASK_BLOCK_UPPER_DIAG_TO_C2 && (!d.C2 || d.mask_nb <= 0 || d.mask_nb % 128 || d.mask_col0 % 128)) return GPB_ERR_INVALID;
-    const int planes = d.nslices_dev ? std::min(std::max(d.nslices_dev[0], 1), d.nslices) : d.nslices;
+    const int planes = d.nslices_dev ? ((d.nslices_dev[0] < 1 || d.nslices_dev[0] > d.nslices) ? d.nslices : d.nslices_dev[0]) : d.nslices;
     const int64_t ps = d.plane_stride > 0 ? d.plane_stride : d.K;
     for (int64_t i = 0; i < d.M; ++i)
         for (int64_t j = 0; j < d.N; ++j) {

@@ -190,3 +190,39 @@ def test_bench_route_auto_statistics_int8_block_65536_vs_oracle_fixture():
     check(v2, g2, ref, gref)
     assert v1 != v2  # two different evaluation orders really ran
     sgpr_ops.release_buffers()
+
+
+def test_gradient_against_the_40_digit_adjudicator_in_the_ill_conditioned_regime():
+    """cond(Kzz) = 8.8e6: value and gradient of the CUDA path (reference order "whitened" and the cheaper "raw" statistics) against
+    tests/golden/sgpr_adjudicator.json (40-digit mpmath, see tests/test_oracle_goldens.py for what the oracle's two float64 routes
+    do there; measured record: profiles/r02_sgpr_adjudication.json).  Asserted: value 1e-8; kernel / noise gradients 1e-7 of their
+    own size; the inducing-input gradient within 2e4 x cond x eps of max|g_Z| -- the two-pass algorithm's measured floor -- for the whiten-first route."""
+    import json
+    import os
+    import sys
+
+    from gpjax_b200.sgpr_ops import collapsed_elbo_fused
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    from make_sgpr_adjudicator_fixture import make_inputs
+
+    F = json.load(open(os.path.join(here, "sgpr_adjudicator.json")))
+    X, y, Z = make_inputs()
+    assert float(X.sum()) == F["x_checksum"]
+    h = F["hyper"]
+    eps = np.finfo(np.float64).eps
+    for route in ("whitened", "raw"):
+        p = [dev(Z).requires_grad_(True), dev(np.array([h["lengthscale"]])).requires_grad_(True), dev(h["variance"]).requires_grad_(True),
+             dev(h["obs_stddev"]).requires_grad_(True), dev(h["mean_const"]).requires_grad_(True)]
+        v = collapsed_elbo_fused(0, dev(X), dev(y), p[0], p[1], p[2], p[3], p[4], h["jitter"], 64, None, route)
+        v.backward()
+        got = dict(inducing_inputs=p[0].grad, lengthscale=p[1].grad, variance=p[2].grad, obs_stddev=p[3].grad, mean_const=p[4].grad)
+        err = {k: float(np.max(np.abs(got[k].cpu().numpy().reshape(-1) - np.asarray(b).reshape(-1))) / np.max(np.abs(b)))
+               for k, b in F["grad"].items()}
+        verr = abs(v.item() - F["value"]) / abs(F["value"])
+        amp = 1.0 if route == "whitened" else F["cond_kzz"] / 1e3  # raw statistics: documented cond-amplified route (opt-in / auto-guarded)
+        assert verr <= 1e-8 * amp, (route, verr)
+        assert max(err[k] for k in ("lengthscale", "variance", "obs_stddev")) <= 1e-7 * amp, (route, err)
+        assert err["inducing_inputs"] <= 2e4 * F["cond_kzz"] * eps * amp, (route, err)  # measured 2.4e-5 (oracle's two-pass closed form: 1.3e-5)
+

@@ -47,6 +47,32 @@ def test_svgp_elbo_vs_autodiff_oracle(kind, name, n, m, d, iso, block):
         assert np.max(np.abs(a - b)) <= tol_g * max(np.max(np.abs(b)), 1e-6 * abs(ref)), (k, cond)
 
 
+def test_svgp_elbo_at_the_benchmarked_inducing_count():
+    """BASELINE config 5's M = 4096 (D = 16, Matern32) on a 2 x 4096-row minibatch: the statistics SYRK and the pass-2 product run
+    on the int8 pipe (7 planes), the replicated M x M finish is the 4096-point one the benchmark times.  Value and every gradient
+    against the oracle's autodiff (~25 s of host time)."""
+    from gpjax_b200.svgp_ops import svgp_elbo_fused
+
+    n, m, d = 8192, 4096, 16
+    X, y, Z, mu, _ = make(n, m, d, 5)
+    # a well-conditioned root covariance: a random unit-lower-triangular factor with O(1) row sums is exponentially ill-conditioned in
+    # M (with make()'s 0.05 off-diagonals the W^-T term of dELBO/dW differs by 7e-7 between ANY two float64 evaluations at M = 4096)
+    W = np.tril(np.random.default_rng(6).standard_normal((m, m)) * 0.002) + 0.6 * np.eye(m)
+    ell = np.linspace(0.8, 1.6, d) * 2.0
+    ref, gref = o.svgp_elbo_value_and_grad_autodiff("matern32", X, y, Z, ell, 1.0, 0.3, 0.1, mu, W, 5e7)
+    p = {k: dev(v).requires_grad_(True) for k, v in dict(Z=Z, ell=ell, var=1.0, sn=0.3, c=0.1, mu=mu, W=W).items()}
+    val = svgp_elbo_fused(1, dev(X), dev(y), p["Z"], p["ell"], p["var"], p["sn"], p["c"], p["mu"], p["W"], 5e7, 1e-6, 4096)
+    val.backward()
+    assert abs(val.item() - ref) <= TOL * abs(ref)
+    got = dict(inducing_inputs=p["Z"].grad, lengthscale=p["ell"].grad, variance=p["var"].grad, obs_stddev=p["sn"].grad,
+               mean_const=p["c"].grad, variational_mean=p["mu"].grad.reshape(-1), variational_root_covariance=p["W"].grad)
+    cond = float(np.linalg.cond(o.gram("matern32", Z, ell, 1.0) + 1e-6 * np.eye(m)))
+    tol_g = TOL * max(1.0, cond / 1e4)
+    for k, b in gref.items():
+        a, b = got[k].cpu().numpy().reshape(np.shape(b)), np.asarray(b)
+        assert np.max(np.abs(a - b)) <= tol_g * max(np.max(np.abs(b)), 1e-6 * abs(ref)), (k, cond)
+
+
 def test_svgp_api_fit_minibatch_and_predict():
     import gpjax_b200 as gpx
 

@@ -201,3 +201,40 @@ def test_extended_kernel_autodiff_matches_finite_differences(name, s):
     em[1] -= h
     fd = (o.conjugate_mll(name, X, y, ep, np.array(s), 0.4, 0.2) - o.conjugate_mll(name, X, y, em, np.array(s), 0.4, 0.2)) / (2 * h)
     assert abs(fd - g["lengthscale"][1]) <= 1e-5 * max(abs(fd), 1.0)
+
+
+def test_collapsed_elbo_gradient_adjudicated_at_40_digits():
+    """cond(Kzz + jitter I) = 8.8e6 (the regime of examples/collapsed_vi.py).  tests/golden/sgpr_adjudicator.json holds the bound
+    and its gradient from a 40-digit mpmath evaluation (generator committed next to it).  Which float64 side is closer?  The
+    reference's evaluation order differentiated by reverse mode (the oracle's autodiff) stays within 3e-8 of the truth in every
+    parameter group; the two-pass closed form -- the algorithm the CUDA path implements -- is as good for the kernel / noise
+    parameters but loses ~1e3 x cond x eps in the inducing-input gradient (1.3e-5 of max|g_Z|, 3e-10 of the gradient's largest
+    component).  This is why the SGPR GPU tests scale their gradient tolerance with cond(Kzz) (tests/test_gpu_sgpr.py::check)."""
+    import json
+    import os
+    import sys
+
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, here)
+    from make_sgpr_adjudicator_fixture import make_inputs
+
+    F = json.load(open(os.path.join(here, "sgpr_adjudicator.json")))
+    X, y, Z = make_inputs()
+    assert float(X.sum()) == F["x_checksum"] and float(y.sum()) == F["y_checksum"]
+    h = F["hyper"]
+    args = ("rbf", X, y, Z, np.array([h["lengthscale"]]), h["variance"], h["obs_stddev"], h["mean_const"])
+    assert abs(o.collapsed_elbo(*args) - F["value"]) <= 1e-12 * abs(F["value"])
+    va, ga = o.collapsed_elbo_value_and_grad_autodiff(*args)
+    gc = o.collapsed_elbo_grad_closed_form(*args)
+    gc = gc[1] if isinstance(gc, tuple) else gc
+    err = {}
+    for k, b in F["grad"].items():
+        b = np.asarray(b)
+        sc = np.max(np.abs(b))
+        err[k] = (float(np.max(np.abs(np.asarray(ga[k]).reshape(b.shape) - b)) / sc),
+                  float(np.max(np.abs(np.asarray(gc[k]).reshape(b.shape) - b)) / sc))
+    assert max(e[0] for e in err.values()) <= 1e-7, err            # reference order + autodiff: the accurate side
+    assert err["inducing_inputs"][0] < err["inducing_inputs"][1], err
+    assert max(err[k][1] for k in ("lengthscale", "variance", "obs_stddev")) <= 1e-8, err
+    assert err["inducing_inputs"][1] <= 1e4 * F["cond_kzz"] * np.finfo(np.float64).eps, err  # 2e-5 here
+
