@@ -332,6 +332,46 @@ def measure_int8_ceiling(D: Dist, n=8192, sustain_s=2.0):
             "sm_mhz_sustained": clk.get("sm_mhz"), "power_w_max": clk.get("power_w_max"), "reasons": clk.get("reasons")}
 
 
+def measure_hbm_kernels(D: Dist, n, d, X, ell, var):
+    """HBM rooflines of the epilogue / solve kernels the north-star names, against MEASURED_PEAKS.json's copy bandwidth:
+    gram_kernel (lower triangle of Sigma written once: 8 B per entry; ~40 FP64 instructions per entry make it FP64-issue bound
+    before it is HBM bound) and the GEMV of the blocked triangular solve (8 B per factor entry read once)."""
+    torch = D.torch
+    from gpjax_b200 import ops
+
+    mp = measured_peaks() or {}
+    peak = float(mp.get("hbm_gbs") or 6456.2)
+    st = ops._mll_state(n, d, X.device)  # the step's own N x N buffer (holds Sigma^-1 / L after the last backward)
+    def ev_ms(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+    out = {"peak": peak, "unit": "GB/s", "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)"}
+    with torch.no_grad():
+        t_gram = ev_ms(lambda: ops.gram_forward(0, X, X, ell.detach(), var.detach(), diag_add=1e-6 + 0.09, lower_only=True, out=st.sigma))
+        live = n * (n + 1) / 2 + n * 64  # entries of the 64 x 128 tiles that touch the lower triangle (upper bound: + one tile row)
+        out["gram_kernel"] = {"ms": t_gram, "algorithmic_bytes": 8.0 * n * (n + 1) / 2, "achieved": 8.0 * live / t_gram / 1e6,
+                              "frac": 8.0 * live / t_gram / 1e6 / peak,
+                              "note": "FP64-issue bound (exp + direct differences, ~40 FP64 instructions per entry) at this D"}
+        # blocked triangular solve L w = d (gemv_n / gemv_t kernels + the stored diagonal-block inverses): reads the factor once
+        ws = ops.FactorWorkspace(n, d, potri=False, device=X.device)
+        ops.potrf_lower_(st.sigma, ws, zero_upper=False)
+        v = torch.ones(n, dtype=torch.float64, device=X.device)
+        for trans, name in ((False, "trsv_forward"), (True, "trsv_transposed")):
+            t_s = ev_ms(lambda: ops.trsv_lower_(st.sigma, v.clone(), ws, trans=trans))
+            out[name] = {"ms": t_s, "algorithmic_bytes": 8.0 * n * (n + 1) / 2, "achieved": 8.0 * n * (n + 1) / 2 / t_s / 1e6,
+                         "frac": 8.0 * n * (n + 1) / 2 / t_s / 1e6 / peak,
+                         "note": "gemv_n / gemv_t over the off-diagonal panels + one GEMV per stored diagonal-block inverse"}
+        del ws
+    return out
+
+
 def bench_exact(D: Dist, args):
     torch = D.torch
     import gpjax_b200 as gpx
@@ -430,6 +470,9 @@ def bench_exact(D: Dist, args):
                 "traffic": 1.646e12 if (n == 50000 and L.gpb_block_size() == 1024) else None,
                 "traffic_unit": "bytes per evaluation (all GEMM launches)",
                 "algorithmic_bytes": 3 * 16 * float(n) ** 3 / (6 * L.gpb_block_size())}
+
+    # ---- bandwidth-class kernels of the path, each timed alone on the benched shape (CUDA events on the launching stream) -------
+    roof["roofline_hbm"] = measure_hbm_kernels(D, n, d, X, ell, var)
 
     # ---- e2e: the public API with HOST buffers (pinned), H2D + D2H inside the timed region -------------------
     prior = gpx.gps.Prior(mean_function=gpx.mean_functions.Constant(Real(HYPER["mean_const"])),

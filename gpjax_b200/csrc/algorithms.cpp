@@ -184,6 +184,18 @@ static int diag_block(stream_t s, int n, double* Ablk, int64_t lda, double* D, d
     return GPB_OK;
 }
 
+// SMs left to the look-ahead chain during the big int8 update of a potrf step (GPB_LOOKAHEAD_FREE_SMS, default 4; 0 = none)
+constexpr int64_t LOOKAHEAD_MIN_ROWS = 12288;
+static int lookahead_ctas() {
+    static const int free_sms = [] {
+        const char* e = std::getenv("GPB_LOOKAHEAD_FREE_SMS");
+        const int v = e ? std::atoi(e) : 4;
+        return v < 0 ? 0 : (v > 64 ? 64 : v);
+    }();
+    if (free_sms == 0) return 0;
+    return device_sm_count() - free_sms;
+}
+
 // Right-looking blocked Cholesky with one-step LOOKAHEAD: the trailing update of step k is split into
 // the next block column (U1) and the rest (U2); as soon as U1 is done the latency-bound chain of step
 // k+1 (diagonal-block factorisation + inverse, panel X = P inv(L)^T) runs on a high-priority side stream
@@ -253,6 +265,10 @@ int potrf_lower(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& w
                 v.Qa = qcur + nb1 * ldq; v.ldqa = ldq; v.sa = scur + nb1;
                 v.Qb = v.Qa; v.ldqb = ldq; v.sb = v.sa;
                 v.C = A + (j1 + nb1) * lda + (j1 + nb1); v.ldc = lda; v.alpha = -1.0; v.mask = MASK_LOWER;
+                // A persistent launch on every SM would leave nothing for the look-ahead chain on the side stream (its kernels
+                // cannot co-reside with a 198 KB / 64 K-register CTA), i.e. no overlap at all: keep a few SMs free while the update
+                // is long enough to cover the chain (diagonal-block recursion ~2 ms).
+                if (rest >= LOOKAHEAD_MIN_ROWS && ozaki_supports_extensions()) v.max_ctas = lookahead_ctas();
                 GPB_TRY(ozaki_gemm(s, v));
             } else {
                 GemmDesc v;

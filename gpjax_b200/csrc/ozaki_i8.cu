@@ -1828,6 +1828,7 @@ int ozaki_gemm(stream_t s, const OzakiGemmDesc& d) {
 }
 
 bool ozaki_available() { return encode_tiled() != nullptr; }
+int device_sm_count() { return sm_count(); }
 bool ozaki_supports_extensions() { return variant() >= 3; }
 
 namespace {

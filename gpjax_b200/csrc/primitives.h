@@ -328,6 +328,8 @@ struct OzakiGemmDesc {
     int max_ctas = 0;             // > 0: leave SMs free for a concurrent latency-bound chain on another stream (look-ahead)
 };
 int ozaki_gemm(stream_t s, const OzakiGemmDesc& d);
+// SMs of the current device (148 on B200), for callers that size OzakiGemmDesc::max_ctas
+int device_sm_count();
 // krange / MASK_BLOCK_UPPER_DIAG_TO_C2 / max_ctas need the CTA-pair kernel (the default; GPB_OZ_KERNEL=1|2 select older variants)
 bool ozaki_supports_extensions();
 // Digit planes of the int8 trailing updates of an N x N covariance factorisation, decided ON THE DEVICE (no host read):

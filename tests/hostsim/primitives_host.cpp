@@ -686,6 +686,7 @@ int igemm_i8(stream_t, int64_t m, int64_t n, int64_t k, const int8_t* A, int64_t
     return GPB_OK;
 }
 bool ozaki_available() { return true; }
+int device_sm_count() { return 148; }
 bool ozaki_supports_extensions() { return true; }
 int ozaki_auto_planes_host(int64_t N, double variance, double obs_stddev, double jitter) {
     const double s = obs_stddev * obs_stddev + jitter;
