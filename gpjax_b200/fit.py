@@ -141,11 +141,12 @@ def fit_scipy(*, model: Module, objective, train_data: Dataset, trainable=Parame
 def fit_lbfgs(*, model: Module, objective, train_data: Dataset, params_bijection: tp.Optional[dict] = DEFAULT_BIJECTION,
               trainable=Parameter, max_iters: int = 100, safe: bool = True, max_linesearch_steps: int = 32,
               gtol: float = 1e-5):
-    """fit.py:259-361.  The reference drives optax's L-BFGS (zoom line search) inside a lax.while_loop; the
-    optimiser is host-side glue here as well: SciPy's L-BFGS-B on the raveled unconstrained parameters with the
-    same stopping knobs.  Returns (optimised model, final loss)."""
+    """fit.py:259-361.  The reference drives optax's L-BFGS (memory 10, zoom line search from step 1) inside a lax.while_loop
+    that runs while  n == 0 or (n < max_iters and |grad|_2 >= gtol);  the same optimiser is restated as host glue in
+    optim.lbfgs_minimize on the raveled unconstrained parameters.  Returns (optimised model, final loss)."""
     import numpy as np
-    from scipy.optimize import minimize
+
+    from .optim import lbfgs_minimize
 
     if safe:
         _check_model(model)
@@ -171,10 +172,9 @@ def fit_lbfgs(*, model: Module, objective, train_data: Dataset, params_bijection
         return float(val), np.concatenate([g[k].reshape(-1).cpu().numpy() for k in keys])
 
     x0 = np.concatenate([u0[k].reshape(-1).cpu().numpy() for k in keys])
-    result = minimize(fun=wrapper, x0=x0, jac=True, method="L-BFGS-B",
-                      options={"maxiter": max_iters, "maxls": max_linesearch_steps, "gtol": gtol})
-    loss.commit(unravel(result.x))
-    return model, torch.as_tensor(result.fun, dtype=torch.float64)
+    x, fval, _, _ = lbfgs_minimize(wrapper, x0, max_iters=max_iters, max_linesearch_steps=max_linesearch_steps, gtol=gtol)
+    loss.commit(unravel(x))
+    return model, torch.as_tensor(fval, dtype=torch.float64)
 
 
 def _check_model(model) -> None:

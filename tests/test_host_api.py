@@ -249,3 +249,60 @@ def test_kernel_algebra_builds_flattened_combinations():
     with pytest.raises(NotImplementedError):  # a combination has no single fused epilogue: the sparse objectives refuse
         from gpjax_b200.objectives import _kernel_args
         _kernel_args(s)
+
+
+def test_lbfgs_minimize_zoom_linesearch_reaches_the_scipy_optimum():
+    """optim.lbfgs_minimize restates the optimiser gpjax/fit.py:259-361 assembles from optax (L-BFGS memory 10 + strong-Wolfe zoom
+    search from step 1, loop `n == 0 or (n < max_iters and |g| >= gtol)`).  Checked on Rosenbrock (curved valley: the line search
+    must bracket and zoom), an ill-conditioned quadratic (the two-loop recursion must pick up curvature) and a softplus-transformed
+    GP-like objective; SciPy's L-BFGS-B is the independent reference for the optimum."""
+    from scipy.optimize import minimize
+
+    from gpjax_b200.optim import lbfgs_minimize
+
+    def rosen(x):
+        f = float(np.sum(100.0 * (x[1:] - x[:-1] ** 2) ** 2 + (1 - x[:-1]) ** 2))
+        g = np.zeros_like(x)
+        g[:-1] = -400.0 * x[:-1] * (x[1:] - x[:-1] ** 2) - 2 * (1 - x[:-1])
+        g[1:] += 200.0 * (x[1:] - x[:-1] ** 2)
+        return f, g
+
+    x, f, g, n = lbfgs_minimize(rosen, np.array([-1.2, 1.0, -0.5, 0.8]), max_iters=200, gtol=1e-8)
+    assert np.allclose(x, 1.0, atol=1e-6) and f < 1e-14 and np.linalg.norm(g) < 1e-8 and n < 120
+
+    A = np.diag(np.logspace(0, 3, 12))
+    Q = np.linalg.qr(np.random.default_rng(0).standard_normal((12, 12)))[0]
+    H = Q @ A @ Q.T
+    b = np.arange(12.0)
+    quad = lambda x: (float(0.5 * x @ H @ x - b @ x), H @ x - b)
+    x, f, g, n = lbfgs_minimize(quad, np.zeros(12), max_iters=300, gtol=1e-7)
+    # float64 stops resolving the sufficient-decrease test around |g| ~ 1e-6 here (f ~ -30): the search then returns step 0 and the loop ends
+    assert np.linalg.norm(x - np.linalg.solve(H, b)) <= 1e-6 * np.linalg.norm(np.linalg.solve(H, b)) and np.linalg.norm(g) < 1e-5
+
+    rng = np.random.default_rng(1)
+    Xs = np.sort(rng.uniform(-3, 3, 60))
+    ys = np.sin(Xs) + 0.1 * rng.standard_normal(60)
+
+    def nll(u):  # exact GP negative MLL in softplus-unconstrained (lengthscale, variance, noise), numerical gradient-free check below
+        sp = np.log1p(np.exp(u))
+        ell, var, sn = sp
+        r2 = (Xs[:, None] - Xs[None, :]) ** 2 / ell**2
+        K = var * np.exp(-0.5 * r2)
+        S = K + (sn**2 + 1e-6) * np.eye(60)
+        L = np.linalg.cholesky(S)
+        a = np.linalg.solve(S, ys)
+        f = 0.5 * ys @ a + np.sum(np.log(np.diag(L))) + 30 * np.log(2 * np.pi)
+        Si = np.linalg.inv(S)
+        Wm = 0.5 * (Si - np.outer(a, a))
+        dS = [K * r2 / ell, K / var, 2 * sn * np.eye(60)]
+        g = np.array([np.sum(Wm * d) for d in dS]) * (1.0 / (1.0 + np.exp(-u)))
+        return float(f), g
+
+    u0 = np.log(np.expm1(np.array([1.0, 1.0, 1.0])))
+    x, f, g, n = lbfgs_minimize(nll, u0, max_iters=100, gtol=1e-6)
+    ref = minimize(nll, u0, jac=True, method="L-BFGS-B", options={"gtol": 1e-9, "ftol": 1e-15})
+    assert abs(f - ref.fun) <= 1e-8 * abs(ref.fun) and np.linalg.norm(g) < 1e-5 and n <= 100
+    # the loop condition of the reference: at least one iteration even when the gradient is already below gtol
+    x1, f1, g1, n1 = lbfgs_minimize(quad, np.linalg.solve(H, b), max_iters=5, gtol=1e3)
+    assert n1 == 1
+
