@@ -49,6 +49,36 @@ int get_ozaki_slices() {
 static bool oz_on(const FactorWs& ws, int64_t rows) {
     return get_ozaki_slices() != 0 && ws.oz_q && ws.oz_planes && rows >= OZ_MIN_ROWS && NB % 128 == 0 && ozaki_available();
 }
+// Panel x inverse-block products (X = P inv(L_kk)^T and friends: M x NB x NB with a triangular NB x NB operand) on the int8 pipe as
+// well: GPB_OZ_PANELS=0 keeps them on the DMMA pipe.  Same predicate as the rank-NB update next to each of them (oz_on), full
+// blocks only; the inverse block is sliced like any other operand (power-of-two row scales), its structural zeros are skipped by
+// the kernel's K-range.
+static bool oz_panels_on(const FactorWs& ws, int64_t rows, int64_t nbk) {
+    static const bool on = [] {
+        const char* e = std::getenv("GPB_OZ_PANELS");
+        return !e || std::atoi(e) != 0;
+    }();
+    return on && nbk == NB && oz_on(ws, rows) && ozaki_supports_extensions();
+}
+// C[0:M, 0:NB] = alpha * A T^T with A's digit planes at (qa, sa) and the triangular block T (NB x NB, row stride NB) sliced into
+// (qt, st): NB rows of scratch planes.  krange says where T's zeros are (KR_B_*), or, with swap, T is the LEFT operand:
+// C[0:NB, 0:M] = alpha * T A^T (KR_A_*).
+static int oz_tri_product(stream_t s, const FactorWs& ws, int64_t M, const int8_t* qa, const double* sa, const double* T, int8_t* qt,
+                          double* st, double* C, int64_t ldc, double alpha, int krange, bool swap) {
+    const int64_t ldq = OZ_MAX_SLICES * NB;
+    GPB_TRY(ozaki_slice(s, NB, NB, NB, T, NB, OZ_MAX_SLICES, qt, ldq, st, ws.oz_planes));
+    OzakiGemmDesc g;
+    g.K = NB; g.nslices = OZ_MAX_SLICES; g.nslices_dev = ws.oz_planes;
+    if (!swap) {
+        g.M = M; g.N = NB; g.Qa = qa; g.sa = sa; g.Qb = qt; g.sb = st;
+    } else {
+        g.M = NB; g.N = M; g.Qa = qt; g.sa = st; g.Qb = qa; g.sb = sa;
+    }
+    g.ldqa = ldq; g.ldqb = ldq;
+    g.C = C; g.ldc = ldc; g.alpha = alpha; g.beta0 = 1; g.krange = krange;
+    return ozaki_gemm(s, g);
+}
+
 int factor_set_planes(stream_t s, const FactorWs& ws, int64_t N, const double* variance, const double* obs_stddev, double jitter) {
     const int req = get_ozaki_slices();
     if (req == 0 || !ws.oz_planes || !ozaki_available()) return GPB_OK;
@@ -209,11 +239,17 @@ static int potrf_panel(stream_t s, int64_t N, double* A, int64_t lda, const Fact
     const int64_t rows = N - j0 - nbk;
     if (rows <= 0) return GPB_OK;
     double* P = A + (j0 + nbk) * lda + j0;
-    GemmDesc g;  // X = P * inv(L_kk)^T -> contiguous copy, then back in place
-    g.M = rows; g.N = nbk; g.K = nbk;
-    g.A = P; g.lda = lda; g.B = Dk; g.ldb = NB; g.C = panel; g.ldc = NB;
-    g.krange = KR_B_LOWER;
-    GPB_TRY(gemm(s, g));
+    if (oz_panels_on(ws, rows, nbk)) {  // X = P * inv(L_kk)^T on the int8 pipe: planes of P in rows [0, rows) of this step's digit
+        const int64_t ldq = OZ_MAX_SLICES * NB;  // buffer (X's planes replace them below), planes of inv(L_kk) in the NB rows after
+        GPB_TRY(ozaki_slice(s, rows, NB, NB, P, lda, OZ_MAX_SLICES, oz_q, ldq, oz_scale, ws.oz_planes));
+        GPB_TRY(oz_tri_product(s, ws, rows, oz_q, oz_scale, Dk, oz_q + rows * ldq, oz_scale + rows, panel, NB, 1.0, KR_B_LOWER, false));
+    } else {
+        GemmDesc g;  // X = P * inv(L_kk)^T -> contiguous copy, then back in place
+        g.M = rows; g.N = nbk; g.K = nbk;
+        g.A = P; g.lda = lda; g.B = Dk; g.ldb = NB; g.C = panel; g.ldc = NB;
+        g.krange = KR_B_LOWER;
+        GPB_TRY(gemm(s, g));
+    }
     GPB_TRY(copy2d(s, rows, nbk, panel, NB, P, lda));
     // Ozaki path: digit planes of the panel, extracted on the stream that produced it (the side stream under lookahead)
     if (nbk == NB && oz_on(ws, rows))  // ws.oz_planes[0] planes are extracted (rounded at the last one) and used by the product
@@ -384,13 +420,21 @@ int trtri_into_upper(stream_t s, int64_t N, double* A, int64_t lda, const Factor
         const int64_t nbk = (N - j0) < NB ? (N - j0) : NB;
         const double* Dk = ws.Dinv + k * NB * NB;
         const double* DTk = ws.DinvT + k * NB * NB;
+        const bool tri8 = j0 > 0 && oz_panels_on(ws, j0, nbk);  // scratch planes: the second digit buffer (potrf's double buffer)
+        const int64_t ldq = OZ_MAX_SLICES * NB;
         if (j0 > 0) {
             // W[0:j0, k] = -Acc * inv(L_kk)^T
-            GemmDesc g;
-            g.M = j0; g.N = nbk; g.K = nbk;
-            g.A = A + j0; g.lda = lda; g.B = Dk; g.ldb = NB; g.C = Wp; g.ldc = NB;
-            g.alpha = -1.0; g.krange = KR_B_LOWER;
-            GPB_TRY(gemm(s, g));
+            if (tri8) {
+                GPB_TRY(ozaki_slice(s, j0, NB, NB, A + j0, lda, OZ_MAX_SLICES, ws.oz_q2 + NB * ldq, ldq, ws.oz_scale2 + NB, ws.oz_planes));
+                GPB_TRY(oz_tri_product(s, ws, j0, ws.oz_q2 + NB * ldq, ws.oz_scale2 + NB, Dk, ws.oz_q2, ws.oz_scale2, Wp, NB, -1.0,
+                                       KR_B_LOWER, false));
+            } else {
+                GemmDesc g;
+                g.M = j0; g.N = nbk; g.K = nbk;
+                g.A = A + j0; g.lda = lda; g.B = Dk; g.ldb = NB; g.C = Wp; g.ldc = NB;
+                g.alpha = -1.0; g.krange = KR_B_LOWER;
+                GPB_TRY(gemm(s, g));
+            }
             GPB_TRY(copy2d(s, j0, nbk, Wp, NB, A + j0, lda));
         }
         const int64_t right = N - j0 - nbk;
@@ -401,7 +445,6 @@ int trtri_into_upper(stream_t s, int64_t N, double* A, int64_t lda, const Factor
             // Acc[0:j0, k+1:] += W[0:j0,k] * L[k+1:,k]^T   (nbk == NB here: block k is not the last one)
             if (oz_on(ws, j0)) {  // digit planes indexed by GLOBAL row: W rows [0, j0), L rows [j0 + nbk, N)
                 const int planes = OZ_MAX_SLICES;
-                const int64_t ldq = OZ_MAX_SLICES * NB;
                 GPB_TRY(ozaki_slice(s, j0, NB, NB, Wp, NB, planes, ws.oz_q, ldq, ws.oz_scale, ws.oz_planes));
                 GPB_TRY(ozaki_slice(s, right, NB, NB, Lp, lda, planes, ws.oz_q + (j0 + nbk) * ldq, ldq, ws.oz_scale + j0 + nbk, ws.oz_planes));
                 OzakiGemmDesc u;
@@ -418,12 +461,18 @@ int trtri_into_upper(stream_t s, int64_t N, double* A, int64_t lda, const Factor
                 GPB_TRY(gemm(s, u));
             }
         }
-        GemmDesc v;  // Acc[k, k+1:] = W_kk * L[k+1:,k]^T   (first write of that block row)
-        v.M = nbk; v.N = right; v.K = nbk;
-        v.A = Wp + j0 * NB; v.lda = NB; v.B = Lp; v.ldb = lda;
-        v.C = A + j0 * lda + (j0 + nbk); v.ldc = lda; v.beta = 0.0;
-        v.krange = KR_A_UPPER;
-        GPB_TRY(gemm(s, v));
+        // Acc[k, k+1:] = W_kk * L[k+1:,k]^T   (first write of that block row)
+        if (tri8 && right >= OZ_MIN_ROWS) {  // L's planes are the ones the update above sliced (rows j0 + nbk .. N of the first buffer)
+            GPB_TRY(oz_tri_product(s, ws, right, ws.oz_q + (j0 + nbk) * ldq, ws.oz_scale + j0 + nbk, DTk, ws.oz_q2, ws.oz_scale2,
+                                   A + j0 * lda + (j0 + nbk), lda, 1.0, KR_A_UPPER, true));
+        } else {
+            GemmDesc v;
+            v.M = nbk; v.N = right; v.K = nbk;
+            v.A = Wp + j0 * NB; v.lda = NB; v.B = Lp; v.ldb = lda;
+            v.C = A + j0 * lda + (j0 + nbk); v.ldc = lda; v.beta = 0.0;
+            v.krange = KR_A_UPPER;
+            GPB_TRY(gemm(s, v));
+        }
     }
     return GPB_OK;
 }
@@ -467,11 +516,15 @@ int lauum_upper(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& w
                 GPB_TRY(gemm(s, b));
             }
             // S[0:j0, k] = W[0:j0,k] * inv(L_kk)          (B operand = DinvT_k, upper triangular)
-            GemmDesc c;
-            c.M = j0; c.N = nbk; c.K = nbk;
-            c.A = P; c.lda = lda; c.B = DTk; c.ldb = NB; c.C = ws.panel; c.ldc = NB;
-            c.krange = KR_B_UPPER;
-            GPB_TRY(gemm(s, c));
+            if (oz_panels_on(ws, j0, nbk)) {  // P's planes are still in the first digit buffer (sliced for P P^T above)
+                GPB_TRY(oz_tri_product(s, ws, j0, ws.oz_q, ws.oz_scale, DTk, ws.oz_q2, ws.oz_scale2, ws.panel, NB, 1.0, KR_B_UPPER, false));
+            } else {
+                GemmDesc c;
+                c.M = j0; c.N = nbk; c.K = nbk;
+                c.A = P; c.lda = lda; c.B = DTk; c.ldb = NB; c.C = ws.panel; c.ldc = NB;
+                c.krange = KR_B_UPPER;
+                GPB_TRY(gemm(s, c));
+            }
             GPB_TRY(copy2d(s, j0, nbk, ws.panel, NB, P, lda));
         }
         // S_kk = inv(L_kk)^T inv(L_kk)

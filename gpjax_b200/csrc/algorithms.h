@@ -18,7 +18,8 @@ constexpr int64_t LEAFN = 128; // leaf size handled by potrf_leaf
 inline int64_t nblocks(int64_t n) { return (n + NB - 1) / NB; }
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
-// ---- process-wide switch: arithmetic of the rank-NB trailing updates (>= OZ_MIN_ROWS output rows) ------------------------
+// ---- process-wide switch: arithmetic of the rank-NB trailing updates (>= OZ_MIN_ROWS output rows) and of the panel x inverse-
+// diagonal-block products next to them (those also obey GPB_OZ_PANELS=0 -> DMMA; profiles/r02_cond_sweep_panels_{dmma,int8}.jsonl)
 //   OZ_AUTO (-1, default): int8 digit planes on tcgen05 (balanced radix-256 digits, 8 bits per plane), plane count decided per
 //                          call ON THE DEVICE by ozaki_choose_planes: the fused objectives use 6 planes (48 bits) only when the
 //                          hyper-parameters bound cond(Sigma) by 2e6, else 7 (56 bits);

@@ -131,14 +131,15 @@ int gpb_gemm(void* stream, int64_t M, int64_t N, int64_t K, double alpha, const 
  *              callers split K, as the SGPR statistics do for K = 65,536)
  * gpb_igemm_i8 exposes the raw integer product (C int32 = A B^T) for bit-exact testing.
  * gpb_set_ozaki_slices(s): s in {-1 (auto, default), 0, 4..7}; 0 keeps every blocked algorithm on the FP64 DMMA pipe, otherwise
- * the rank-NB trailing updates (>= 2048 output rows) of potrf / trtri / lauum run through gpb_ozaki_gemm, and the two streamed
+ * the rank-NB trailing updates (>= 2048 output rows) of potrf / trtri / lauum and the panel x inverse-diagonal-block products next
+ * to them (environment variable GPB_OZ_PANELS=0 keeps those on the DMMA pipe) run through gpb_ozaki_gemm, and the two streamed
  * products of gpb_sgpr_stats(_raw) / gpb_sgpr_grad_local (blocks of >= 2048 rows, M >= 256) with all 7 planes (56 bits).
  * Plane count of the exact-GP updates in auto mode -- the conditioning guard -- is decided per call ON THE DEVICE (a one-thread
  * kernel writes it into the workspace, the product kernels read it: no host synchronisation):
  *   gpb_potrf_lower / gpb_potri_lower (a bare matrix, nothing known about it): 7 planes = fp64-rounding-level products;
  *   gpb_mll_forward / gpb_mll_backward: 6 planes iff the hyper-parameters PROVE cond(Sigma) <= 2e6 through
  *     cond(K + s I) <= (N variance + s) / s, s = obs_stddev^2 + jitter  (|k| <= variance), else 7.
- * Measured against the CPU oracle (profiles/r02_cond_sweep_n8192.jsonl, r02_cond_sweep_radix256.jsonl): 56 bits equal the FP64
+ * Measured against the CPU oracle (profiles/r02_cond_sweep_n8192.jsonl, r02_cond_sweep_radix256.jsonl, r02_cond_sweep_panels_int8.jsonl): 56 bits equal the FP64
  * path's own error at every conditioning; 48 bits carry at most 1.4e-15 x bound relative error in the most sensitive gradient
  * (<= 2.8e-9 under the guard; contract 1e-8).
  * gpb_ozaki_auto_planes is the same rule evaluated on host values, for reporting and tests only.
