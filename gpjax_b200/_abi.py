@@ -18,6 +18,7 @@ PROTOTYPES = {
     "gpb_version": (C.c_char_p, []),
     "gpb_max_input_dim": (i32, []),
     "gpb_block_size": (i64, []),
+    "gpb_block_size_for": (i64, [i64]),
     "gpb_profile_reset": (None, [i32]),
     "gpb_debug_set_gemm_variant": (None, [i32]),
     "gpb_profile_read": (i32, [vp, vp, vp]),

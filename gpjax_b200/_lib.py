@@ -7,7 +7,8 @@ import os
 from . import _abi
 
 _LIB = None
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgpjax_b200.so")
+# GPB_LIB_PATH: measurement hook (a build with another block size, GPB_NB=... scripts/nb_sweep.py); never a fallback
+LIB_PATH = os.environ.get("GPB_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libgpjax_b200.so")
 
 
 class ExtensionMissingError(RuntimeError):

@@ -15,7 +15,8 @@ extern "C" {
 
 const char* gpb_version(void) { return "gpjax_b200 0.1.0 (sm_100a, fp64 DMMA)"; }
 int gpb_max_input_dim(void) { return max_input_dim(); }
-int64_t gpb_block_size(void) { return NB; }
+int64_t gpb_block_size(void) { return block_size_for(0); }
+int64_t gpb_block_size_for(int64_t ws_n) { return block_size_for(ws_n); }
 void gpb_profile_reset(int enable) { profile_reset(enable); }
 void gpb_debug_set_gemm_variant(int v) { debug_set_gemm_variant(v); }
 int gpb_profile_read(double* gemm_ms, int64_t* gemm_launches, int64_t* all_launches) {
@@ -112,7 +113,7 @@ int gpb_potri_lower(void* stream, int64_t N, double* A, int64_t lda, double* out
     if ((rc = factor_set_planes(stream, w, N, nullptr, nullptr, 0.0))) return rc;
     if ((rc = trtri_into_upper(stream, N, A, lda, w))) return rc;
     if ((rc = lauum_upper(stream, N, A, lda, w))) return rc;
-    const int64_t nblk = nblocks(N);
+    const int64_t NB = w.nb, nblk = nblocks(N, NB);
     for (int64_t k = 0; k < nblk; ++k) {
         const int64_t j0 = k * NB;
         const int64_t nbk = (N - j0) < NB ? (N - j0) : NB;

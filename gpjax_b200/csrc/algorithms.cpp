@@ -28,6 +28,28 @@ namespace gpb {
     } while (0)
 
 // -------------------------------------------------------------------------------------------
+// block size rule (algorithms.h)
+// -------------------------------------------------------------------------------------------
+int64_t block_size_for(int64_t ws_n) {
+#ifdef GPB_NB
+    (void)ws_n;
+    return GPB_NB;
+#else
+    static const int64_t large = [] {
+        const char* e = std::getenv("GPB_NB_LARGE");
+        const long long v = e ? std::atoll(e) : NB_LARGE;
+        return (v >= 128 && v <= 8192 && v % 128 == 0) ? (int64_t)v : NB_LARGE;
+    }();
+    static const int64_t min_rows = [] {
+        const char* e = std::getenv("GPB_NB_LARGE_MIN_ROWS");
+        const long long v = e ? std::atoll(e) : NB_LARGE_MIN_ROWS;
+        return v > 0 ? (int64_t)v : NB_LARGE_MIN_ROWS;
+    }();
+    return ws_n >= min_rows ? large : NB_SMALL;
+#endif
+}
+
+// -------------------------------------------------------------------------------------------
 // Ozaki switch
 // -------------------------------------------------------------------------------------------
 namespace {
@@ -47,7 +69,7 @@ int get_ozaki_slices() {
 }
 // does a rank-NB update with `rows` output rows run on the int8 pipe?  (plane count: ws.oz_planes, decided on the device)
 static bool oz_on(const FactorWs& ws, int64_t rows) {
-    return get_ozaki_slices() != 0 && ws.oz_q && ws.oz_planes && rows >= OZ_MIN_ROWS && NB % 128 == 0 && ozaki_available();
+    return get_ozaki_slices() != 0 && ws.oz_q && ws.oz_planes && rows >= OZ_MIN_ROWS && ws.nb % 128 == 0 && ozaki_available();
 }
 // Panel x inverse-block products (X = P inv(L_kk)^T and friends: M x NB x NB with a triangular NB x NB operand) on the int8 pipe as
 // well: GPB_OZ_PANELS=0 keeps them on the DMMA pipe.  Same predicate as the rank-NB update next to each of them (oz_on), full
@@ -58,13 +80,14 @@ static bool oz_panels_on(const FactorWs& ws, int64_t rows, int64_t nbk) {
         const char* e = std::getenv("GPB_OZ_PANELS");
         return !e || std::atoi(e) != 0;
     }();
-    return on && nbk == NB && oz_on(ws, rows) && ozaki_supports_extensions();
+    return on && nbk == ws.nb && oz_on(ws, rows) && ozaki_supports_extensions();
 }
 // C[0:M, 0:NB] = alpha * A T^T with A's digit planes at (qa, sa) and the triangular block T (NB x NB, row stride NB) sliced into
 // (qt, st): NB rows of scratch planes.  krange says where T's zeros are (KR_B_*), or, with swap, T is the LEFT operand:
 // C[0:NB, 0:M] = alpha * T A^T (KR_A_*).
 static int oz_tri_product(stream_t s, const FactorWs& ws, int64_t M, const int8_t* qa, const double* sa, const double* T, int8_t* qt,
                           double* st, double* C, int64_t ldc, double alpha, int krange, bool swap) {
+    const int64_t NB = ws.nb;
     const int64_t ldq = OZ_MAX_SLICES * NB;
     GPB_TRY(ozaki_slice(s, NB, NB, NB, T, NB, OZ_MAX_SLICES, qt, ldq, st, ws.oz_planes));
     OzakiGemmDesc g;
@@ -97,7 +120,8 @@ struct WsLayout {
 };
 WsLayout ws_layout(int64_t N, int D, int with_potri) {
     WsLayout L;
-    const int64_t blk = nblocks(N) * NB * NB;
+    const int64_t NB = block_size_for(N);
+    const int64_t blk = nblocks(N, NB) * NB * NB;
     int64_t o = 0;
     auto take = [&](int64_t n) {
         int64_t r = o;
@@ -137,6 +161,7 @@ int factor_ws_carve(void* buf, int64_t bytes, int64_t N, int D, int with_potri, 
     WsLayout L = ws_layout(N, D, with_potri);
     if (bytes < L.total * (int64_t)sizeof(double)) return GPB_ERR_WORKSPACE;
     double* b = static_cast<double*>(buf);
+    ws->nb = block_size_for(N);
     ws->Dinv = b + L.off_dinv;
     ws->DinvT = b + L.off_dinvt;
     ws->Sdiag = with_potri ? b + L.off_sdiag : nullptr;
@@ -163,7 +188,7 @@ int factor_ws_carve(void* buf, int64_t bytes, int64_t N, int D, int with_potri, 
 // scratch per recursion level (h = 256, 128), laid out back to back.
 // -------------------------------------------------------------------------------------------
 static int diag_block(stream_t s, int n, double* Ablk, int64_t lda, double* D, double* DT, double* small,
-                      int* info, int64_t row0, int factor) {
+                      int* info, int64_t row0, int factor, int64_t NB) {
     if (n <= LEAFN) return potrf_leaf(s, n, Ablk, lda, D, NB, DT, NB, info, row0, factor);
     int h = (int)LEAFN;
     while (2 * h < n) h *= 2;  // largest power-of-two multiple of LEAFN strictly below n
@@ -175,7 +200,7 @@ static int diag_block(stream_t s, int n, double* Ablk, int64_t lda, double* D, d
     double* A22 = A21 + n1;
     double* D22 = D + (int64_t)n1 * NB + n1;
     double* DT22 = DT + (int64_t)n1 * NB + n1;
-    GPB_TRY(diag_block(s, n1, Ablk, lda, D, DT, next_small, info, row0, factor));
+    GPB_TRY(diag_block(s, n1, Ablk, lda, D, DT, next_small, info, row0, factor, NB));
     GemmDesc g;
     if (factor) {
         // L21 = A21 * inv(L11)^T
@@ -194,7 +219,7 @@ static int diag_block(stream_t s, int n, double* Ablk, int64_t lda, double* D, d
     } else {
         GPB_TRY(copy2d(s, n2, n1, A21, lda, t21, h));
     }
-    GPB_TRY(diag_block(s, n2, A22, lda, D22, DT22, next_small, info, row0 + n1, factor));
+    GPB_TRY(diag_block(s, n2, A22, lda, D22, DT22, next_small, info, row0 + n1, factor, NB));
     // tt = L21 * inv(L11)          (B operand = inv(L11)^T, upper triangular)
     g = GemmDesc();
     g.M = n2; g.N = n1; g.K = n1;
@@ -232,10 +257,11 @@ static int lookahead_ctas() {
 // while U2 -- >95 % of the step's flops -- keeps the SMs busy on the caller's stream.
 static int potrf_panel(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& ws, int* info, int64_t k,
                        double* panel, int8_t* oz_q, double* oz_scale) {
+    const int64_t NB = ws.nb;
     const int64_t j0 = k * NB;
     const int nbk = (int)((N - j0) < NB ? (N - j0) : NB);
     double* Dk = ws.Dinv + k * NB * NB;
-    GPB_TRY(diag_block(s, nbk, A + j0 * lda + j0, lda, Dk, ws.DinvT + k * NB * NB, ws.small, info, j0, 1));
+    GPB_TRY(diag_block(s, nbk, A + j0 * lda + j0, lda, Dk, ws.DinvT + k * NB * NB, ws.small, info, j0, 1, NB));
     const int64_t rows = N - j0 - nbk;
     if (rows <= 0) return GPB_OK;
     double* P = A + (j0 + nbk) * lda + j0;
@@ -259,7 +285,8 @@ static int potrf_panel(stream_t s, int64_t N, double* A, int64_t lda, const Fact
 
 int potrf_lower(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& ws, int* info) {
     if (N < 0 || (N > 0 && !A)) return GPB_ERR_INVALID;
-    const int64_t nblk = nblocks(N);
+    const int64_t NB = ws.nb;
+    const int64_t nblk = nblocks(N, NB);
     if (nblk == 0) return GPB_OK;
     stream_t side = side_stream(s, 0);
     double* pcur = ws.panel;
@@ -326,18 +353,20 @@ int potrf_lower(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& w
 }
 
 int diag_inverses(stream_t s, int64_t N, const double* L, int64_t lda, const FactorWs& ws) {
-    const int64_t nblk = nblocks(N);
+    const int64_t NB = ws.nb;
+    const int64_t nblk = nblocks(N, NB);
     for (int64_t k = 0; k < nblk; ++k) {
         const int64_t j0 = k * NB;
         const int nbk = (int)((N - j0) < NB ? (N - j0) : NB);
         GPB_TRY(diag_block(s, nbk, const_cast<double*>(L) + j0 * lda + j0, lda, ws.Dinv + k * NB * NB,
-                           ws.DinvT + k * NB * NB, ws.small, nullptr, j0, 0));
+                           ws.DinvT + k * NB * NB, ws.small, nullptr, j0, 0, NB));
     }
     return GPB_OK;
 }
 
 int trsv_lower(stream_t s, int64_t N, const double* L, int64_t lda, const FactorWs& ws, double* x, int trans) {
-    const int64_t nblk = nblocks(N);
+    const int64_t NB = ws.nb;
+    const int64_t nblk = nblocks(N, NB);
     double* t = ws.vec + 2 * align_up(N, NB);  // [NB] scratch
     if (!trans) {
         for (int64_t k = 0; k < nblk; ++k) {
@@ -363,7 +392,8 @@ int trsv_lower(stream_t s, int64_t N, const double* L, int64_t lda, const Factor
 int trsm_lower_left(stream_t s, int64_t N, int64_t T, const double* L, int64_t lda, const FactorWs& ws, double* B,
                     int64_t ldb, int trans) {
     if (N <= 0 || T <= 0) return GPB_OK;
-    const int64_t nblk = nblocks(N);
+    const int64_t NB = ws.nb;
+    const int64_t nblk = nblocks(N, NB);
     double* Xk = ws.panel;  // [NB x T], row stride T
     if (!trans) {
         for (int64_t k = 0; k < nblk; ++k) {
@@ -413,7 +443,8 @@ int trsm_lower_left(stream_t s, int64_t N, int64_t T, const double* L, int64_t l
 }
 
 int trtri_into_upper(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& ws) {
-    const int64_t nblk = nblocks(N);
+    const int64_t NB = ws.nb;
+    const int64_t nblk = nblocks(N, NB);
     double* Wp = ws.panel;  // block column k of W, rows 0 .. j0+nbk, ld NB
     for (int64_t k = 0; k < nblk; ++k) {
         const int64_t j0 = k * NB;
@@ -478,7 +509,8 @@ int trtri_into_upper(stream_t s, int64_t N, double* A, int64_t lda, const Factor
 }
 
 int lauum_upper(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& ws) {
-    const int64_t nblk = nblocks(N);
+    const int64_t NB = ws.nb;
+    const int64_t nblk = nblocks(N, NB);
     for (int64_t k = 0; k < nblk; ++k) {
         const int64_t j0 = k * NB;
         const int64_t nbk = (N - j0) < NB ? (N - j0) : NB;
@@ -543,7 +575,7 @@ int mll_forward(stream_t s, const MllArgs& a, const FactorWs& ws, double* value_
     if (a.N <= 0 || a.D <= 0 || !a.X || !a.y || !a.ell || !a.variance || !a.obs_stddev || !a.Sigma || !value_out ||
         !alpha_out || !info)
         return GPB_ERR_INVALID;
-    const int64_t N = a.N;
+    const int64_t N = a.N, NB = ws.nb;
     double* dvec = ws.vec;                        // d = y - m
     double* wvec = ws.vec + align_up(N, NB);      // w = L^-1 d
     double* half_logdet = ws.scal;
@@ -575,7 +607,7 @@ int mll_backward(stream_t s, const MllArgs& a, const FactorWs& ws, const double*
     GPB_TRY(trtri_into_upper(s, a.N, a.Sigma, a.lds, ws));
     GPB_TRY(lauum_upper(s, a.N, a.Sigma, a.lds, ws));
     MllBwdDesc d;
-    d.kind = a.kind; d.N = a.N; d.D = a.D; d.nb = NB;
+    d.kind = a.kind; d.N = a.N; d.D = a.D; d.nb = ws.nb;
     d.X = a.X; d.ldx = a.ldx; d.alpha = alpha;
     d.S = a.Sigma; d.lds = a.lds; d.Sdiag = ws.Sdiag;
     d.ell = a.ell; d.ell_is_scalar = a.ell_is_scalar; d.variance = a.variance; d.obs_stddev = a.obs_stddev;

@@ -7,15 +7,20 @@
 
 namespace gpb {
 
-// Measured on B200 (scripts/nb_sweep.py, value + gradient of conjugate_mll): N=50k  512: 3.93 s, 1024: 3.84 s, 2048: 3.82 s;
-// N=20k 285 / 283 / 291 ms; N=10k 53.0 / 54.6 / 58.4 ms.  1024 doubles K of every trailing update (fewer passes over C).
-#ifndef GPB_NB
-#define GPB_NB 1024
-#endif
-constexpr int64_t NB = GPB_NB;  // block size of every blocked algorithm (power-of-two multiple of 128)
+// Block size NB of every blocked algorithm (a multiple of 128): a function of the order the WORKSPACE was sized for, fixed when
+// the workspace is carved (FactorWs::nb), so every call that shares a workspace -- the factorisation and the solves / inverse that
+// reuse its diagonal-block inverses -- agrees on it.  Measured on B200 (scripts/nb_sweep.py, value + gradient of conjugate_mll):
+//   round 1, FP64 DMMA path: N=50k  512: 3.93 s, 1024: 3.84 s, 2048: 3.82 s; N=20k 285 / 283 / 291 ms; N=10k 53.0 / 54.6 / 58.4 ms;
+//   round 2, int8 path     : N=50k 1024: 1495 ms, 2048: 1305 ms; N=20k 136.6 / 132.5 ms; N=10k 37.6 / 38.7 ms
+// (K of every trailing update doubles with NB: half the passes over C and half the write-outs per int8 product -- the write-out is
+// what paces that kernel -- against a longer latency-bound diagonal-block chain, which the look-ahead hides only for large N).
+// -DGPB_NB=... (build.py: GPB_NB=...) forces one block size for every order: the host model of the CPU tests (256) and sweeps.
+// GPB_NB_LARGE / GPB_NB_LARGE_MIN_ROWS (environment, read once): measurement hooks for the large-order rule (scripts/nb_sweep.py).
+constexpr int64_t NB_SMALL = 1024, NB_LARGE = 2048, NB_LARGE_MIN_ROWS = 16384;
+int64_t block_size_for(int64_t ws_n);
 constexpr int64_t LEAFN = 128; // leaf size handled by potrf_leaf
 
-inline int64_t nblocks(int64_t n) { return (n + NB - 1) / NB; }
+inline int64_t nblocks(int64_t n, int64_t nb) { return (n + nb - 1) / nb; }
 inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 // ---- process-wide switch: arithmetic of the rank-NB trailing updates (>= OZ_MIN_ROWS output rows) and of the panel x inverse-
@@ -47,6 +52,7 @@ constexpr int64_t OZ_MIN_ROWS = GPB_OZ_MIN_ROWS;  // smaller updates stay on the
 
 // ---- workspace for the exact-GP factorisation family --------------------------------------
 struct FactorWs {
+    int64_t nb = 0;           // block size NB of every call on this workspace: block_size_for(the order it was carved for)
     double* Dinv = nullptr;   // nblk blocks [NB x NB], inverse of the diagonal blocks of L
     double* DinvT = nullptr;  // their transposes
     double* Sdiag = nullptr;  // nblk blocks [NB x NB], diagonal blocks of Sigma^-1 (potri only)

@@ -306,7 +306,7 @@ int sgpr_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const double* P
     GPB_TRY(trtri_into_upper(s, M, ws.LB, M, ws.fb));
     GPB_TRY(lauum_upper(s, M, ws.LB, M, ws.fb));
     {   // assemble the full symmetric inverse
-        const int64_t nblk = nblocks(M);
+        const int64_t NB = ws.fb.nb, nblk = nblocks(M, NB);
         for (int64_t k = 0; k < nblk; ++k) {
             const int64_t j0 = k * NB;
             const int64_t nbk = (M - j0) < NB ? (M - j0) : NB;

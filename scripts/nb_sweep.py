@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from gpjax_b200 import ops
 from gpjax_b200._lib import lib
 dev = "cuda"
-print("NB =", lib().gpb_block_size())
+print("NB =", lib().gpb_block_size(), "(small orders),", lib().gpb_block_size_for(50000), "(N = 50,000)")
 for n in [int(a) for a in sys.argv[1:]] or (2000, 5000, 10000, 20000, 30000):
     d = 8
     rng = np.random.default_rng(123)

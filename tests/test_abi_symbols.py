@@ -49,6 +49,7 @@ def test_cuda_library_loads_and_answers_queries(cuda_lib_path):
     lib = _abi.declare(ctypes.CDLL(cuda_lib_path))
     assert b"sm_100a" in lib.gpb_version()
     assert lib.gpb_block_size() in (256, 512, 1024)
+    assert lib.gpb_block_size_for(50_000) in (256, 512, 1024, 2048) and lib.gpb_block_size_for(100) == lib.gpb_block_size()
     assert lib.gpb_max_input_dim() >= 16
     assert lib.gpb_mll_workspace_bytes(50000, 8) > 0
     assert lib.gpb_factor_workspace_bytes(1000, 1, 0) < lib.gpb_factor_workspace_bytes(1000, 1, 1)
