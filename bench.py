@@ -35,6 +35,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "exact-GP MLL+grad evals/s @N=50k fp64; SGPR ELBO points/s at 1/2/4/8 GPU"
+NOMINAL_8BIT_TOPS = 4500.0  # dense fp8 / int8-class tensor peak of B200 (B200_PROFILING.md: 4.5 PFLOP/s dense fp8)
 NOMINAL_FP64_TFLOPS = 128 * 148 * 1.965e9 / 1e12  # 128 flop/clk/SM x 148 SMs x 1.965 GHz = 37.2
 
 
@@ -449,6 +450,10 @@ def bench_exact(D: Dist, args):
                 "peak_source": "measured live in this process: torch._int_mm (cuBLASLt IGEMM) 8192^3 back to back for >= 2 s "
                                "(sustained, power-capped); unit is int8 Top/s (2 x MAC)",
                 "int8_ceiling_measured": i8, "frac_of_int8_burst": achieved / i8["burst_tops"],
+                "frac_of_nominal_dense_8bit_peak": achieved / NOMINAL_8BIT_TOPS,
+                "note": "frac > 1 against the sustained library figure means this kernel sustains more int8 Top/s than cuBLASLt's IGEMM "
+                        "under the same 1 kW power cap (sw_power_cap is the limiter of both); the pipe-limited comparison is "
+                        "frac_of_int8_burst",
                 "frac_of_2x_bf16_sustained": achieved / (2.0 * bf16),
                 "digit_planes": planes, "digit_bits_per_plane": 8, "digit_pair_products": pairs(planes), "digit_plane_mode": "auto (device-side conditioning guard)" if mode == -1 else "forced",
                 "int8_ops_per_eval": oz_ops_used / args.steps,
@@ -582,6 +587,7 @@ def bench_sgpr(D: Dist, args, steps=None, warmup=None):
                 "kernel": "ozaki_i8_kernel (tcgen05.mma kind::i8, 7 radix-256 digit planes): K_b^T K_b statistics + dK_b = [K_b|d|1] Caug^T",
                 "achieved": a8, "peak": peak8, "unit": "TFLOP/s", "frac": a8 / peak8, "peak_source": peak_src,
                 "int8_ceiling_measured": i8, "frac_of_int8_sustained": a8 / i8["sustained_tops"], "frac_of_2x_bf16_sustained": a8 / bf16x2,
+                "frac_of_nominal_dense_8bit_peak": a8 / NOMINAL_8BIT_TOPS,
                 "int8_ops_per_point": oz_ops.value / steps / (hi - lo), "time_over_step_time": oz_ms.value * 1e-3 / t,
                 "launches_per_step": oz_n.value / steps,
                 "algorithmic_flop_per_point": fpp, "reference_formulation_flop_per_point": 4.0 * m * m,
@@ -692,6 +698,7 @@ def bench_svgp(D: Dist, args):
         roof = {"bound": "tensor", "kernel": "ozaki_i8_kernel (tcgen05.mma kind::i8, 7 radix-256 digit planes)", "achieved": a8, "peak": peak8,
                 "unit": "TFLOP/s", "frac": a8 / peak8, "peak_source": peak_src,
                 "int8_ceiling_measured": i8, "frac_of_int8_sustained": a8 / i8["sustained_tops"], "frac_of_2x_bf16_sustained": a8 / bf16x2,
+                "frac_of_nominal_dense_8bit_peak": a8 / NOMINAL_8BIT_TOPS,
                 "time_over_step_time": oz_ms.value * 1e-3 / t, "algorithmic_flop_per_step": flops,
                 "whole_step_tflops_per_gpu": flops * steps / t / 1e12,
                 "remaining_dmma_gemms": {"time_over_step_time": gemm_ms.value * 1e-3 / t},

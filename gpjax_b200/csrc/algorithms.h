@@ -11,12 +11,13 @@ namespace gpb {
 // the workspace is carved (FactorWs::nb), so every call that shares a workspace -- the factorisation and the solves / inverse that
 // reuse its diagonal-block inverses -- agrees on it.  Measured on B200 (scripts/nb_sweep.py, value + gradient of conjugate_mll):
 //   round 1, FP64 DMMA path: N=50k  512: 3.93 s, 1024: 3.84 s, 2048: 3.82 s; N=20k 285 / 283 / 291 ms; N=10k 53.0 / 54.6 / 58.4 ms;
-//   round 2, int8 path     : N=50k 1024: 1495 ms, 2048: 1305 ms; N=20k 136.6 / 132.5 ms; N=10k 37.6 / 38.7 ms
+//   round 2, int8 path     : N=50k 1024: 1495 ms, 2048: 1305 ms, 4096: 1375 ms; N=20k 136.6 / 132.5 ms; N=16,384 88.3 / 85.2 ms;
+//                            N=12,288 51.8 / 50.9 ms; N=10k 37.6 / 38.7 ms; N=8192 26.5 / 27.0 ms  (profiles/r02_nb_rule_sweeps.log)
 // (K of every trailing update doubles with NB: half the passes over C and half the write-outs per int8 product -- the write-out is
 // what paces that kernel -- against a longer latency-bound diagonal-block chain, which the look-ahead hides only for large N).
 // -DGPB_NB=... (build.py: GPB_NB=...) forces one block size for every order: the host model of the CPU tests (256) and sweeps.
 // GPB_NB_LARGE / GPB_NB_LARGE_MIN_ROWS (environment, read once): measurement hooks for the large-order rule (scripts/nb_sweep.py).
-constexpr int64_t NB_SMALL = 1024, NB_LARGE = 2048, NB_LARGE_MIN_ROWS = 16384;
+constexpr int64_t NB_SMALL = 1024, NB_LARGE = 2048, NB_LARGE_MIN_ROWS = 12288;
 int64_t block_size_for(int64_t ws_n);
 constexpr int64_t LEAFN = 128; // leaf size handled by potrf_leaf
 

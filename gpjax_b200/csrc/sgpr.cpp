@@ -105,6 +105,13 @@ int sgpr_ws_carve(void* buf, int64_t bytes, int64_t M, int D, int64_t block_rows
     ws->oz_colmax = L.with_oz ? b + L.oz_colmax : nullptr;
     ws->oz_ones = L.with_oz ? b + L.oz_ones : nullptr;
     ws->oz_kplane1 = L.oz_kplane1;
+    if (L.with_oz) {
+        const int64_t need2 = block_rows * L.oz_kplane, need1 = M * L.oz_kplane1;
+        ws->oz_qt_bytes = 8 * (need2 > need1 ? need2 : need1);
+        ws->oz_qc_bytes = 8 * M * L.oz_kplane;
+        ws->oz_st_len = block_rows;
+        ws->oz_sc_len = M;
+    }
     return GPB_OK;
 }
 
@@ -151,6 +158,44 @@ static GramDesc gram_desc(const SgprArgs& a, const double* X, int64_t ldx, int64
     return g;
 }
 
+// -------------------------------------------------------------------------------------------
+// Dense products of the replicated M x M finish (V = Lz^-1 W, V V^T, Phi Ttil, Linv^T G Linv, ...: ~11 M^3 MACs per SVGP step,
+// 38 % of a config-5 step as FP64 DMMA GEMMs at M = 4096) on the int8 pipe: both operands are sliced into all 7 digit planes
+// (56 bits below the row / column maximum: the products are at fp64-rounding level, as in the streamed passes) and multiplied by
+// the same tcgen05 kernel.  Operands that are K-contiguous are sliced by rows (ozaki_slice), MN-layout operands -- the product
+// contracts over their ROWS -- by columns (ozaki_slice_t).  The digit buffers of the streamed passes are free between pass 1 and
+// pass 2, which is exactly where the finish runs.  GPB_SGPR_FINISH_INT8=0 keeps the DMMA GEMMs; so do small products
+// (any extent < 2048), batched ones and operands that do not fit the borrowed buffers.
+// -------------------------------------------------------------------------------------------
+constexpr int64_t MM_INT8_MIN = 2048;
+static bool mm_int8_on() {
+    static const bool v = [] { const char* e = std::getenv("GPB_SGPR_FINISH_INT8"); return !(e && std::atoi(e) == 0); }();
+    return v;
+}
+static int mm_gemm(stream_t s, const SgprWs& ws, const GemmDesc& g) {
+    const int64_t kp = align_up(g.K, 128), ldq = (int64_t)OZ_MAX_SLICES * kp;
+    const bool fits = ws.oz_qt && ws.oz_qc && g.M * ldq <= ws.oz_qt_bytes && g.N * ldq <= ws.oz_qc_bytes && g.M <= ws.oz_st_len &&
+                      g.N <= ws.oz_sc_len && (g.a_layout == LAYOUT_K || g.M <= ws.oz_sc_len) &&
+                      (int64_t)OZ_MAX_SLICES * kp * OZ_DIGIT_SQ_MAX < (1ll << 31);
+    const bool route = mm_int8_on() && fits && g.batch <= 1 && g.M >= MM_INT8_MIN && g.N >= MM_INT8_MIN && g.K >= MM_INT8_MIN &&
+                       (g.beta == 0.0 || g.beta == 1.0) && (g.mask == MASK_NONE || g.mask == MASK_LOWER) &&
+                       get_ozaki_slices() != 0 && ozaki_available() && ozaki_supports_extensions();
+    if (!route) return gemm(s, g);
+    const int planes = OZ_MAX_SLICES;
+    // column scratch of ozaki_slice_t: oz_colmax holds M entries; the B operand's scale vector doubles as A's scratch and vice versa
+    if (g.a_layout == LAYOUT_K) GPB_TRY(ozaki_slice(s, g.M, g.K, kp, g.A, g.lda, planes, ws.oz_qt, ldq, ws.oz_st));
+    else GPB_TRY(ozaki_slice_t(s, g.K, g.M, kp, g.A, g.lda, planes, ws.oz_qt, ldq, ws.oz_st, ws.oz_colmax));
+    if (g.b_layout == LAYOUT_K) GPB_TRY(ozaki_slice(s, g.N, g.K, kp, g.B, g.ldb, planes, ws.oz_qc, ldq, ws.oz_sc));
+    else GPB_TRY(ozaki_slice_t(s, g.K, g.N, kp, g.B, g.ldb, planes, ws.oz_qc, ldq, ws.oz_sc, ws.oz_colmax));
+    OzakiGemmDesc o;
+    o.M = g.M; o.N = g.N; o.K = kp; o.nslices = planes;
+    o.Qa = ws.oz_qt; o.ldqa = ldq; o.sa = ws.oz_st; o.Qb = ws.oz_qc; o.ldqb = ldq; o.sb = ws.oz_sc;
+    o.C = g.C; o.ldc = g.ldc; o.alpha = g.alpha; o.beta0 = g.beta == 0.0 ? 1 : 0;
+    o.mask = g.mask; o.mask_row0 = g.mask_row0; o.mask_col0 = g.mask_col0;
+    o.krange = g.krange; o.kr_off = g.kr_off;
+    return ozaki_gemm(s, o);
+}
+
 
 // Caug = [Linv^T G1 Linv | Linv^T uvec | 0]  (M x (M+2), row stride M+2): pass 2 forms dK_b^T = [K_b^T|d|1] Caug^T.
 // dKzz = Linv^T G2 Linv.
@@ -160,19 +205,19 @@ static int build_pass2_adjoints(stream_t s, int64_t M, const SgprWs& ws, const d
     GemmDesc t;
     t.M = M; t.N = M; t.K = M;
     t.A = G1; t.lda = M; t.B = ws.Linv; t.ldb = M; t.b_layout = LAYOUT_MN; t.C = ws.Tmp; t.ldc = M;
-    GPB_TRY(gemm(s, t));
+    GPB_TRY(mm_gemm(s, ws, t));
     GemmDesc c;
     c.M = M; c.N = M; c.K = M;
     c.A = ws.Linv; c.lda = M; c.a_layout = LAYOUT_MN; c.B = ws.Tmp; c.ldb = M; c.b_layout = LAYOUT_MN;
     c.C = ws.Caug; c.ldc = ld;
-    GPB_TRY(gemm(s, c));
+    GPB_TRY(mm_gemm(s, ws, c));
     GPB_TRY(gemv(s, M, M, ws.Linv, M, 1, uvec, ws.cvec, 1.0, 0.0));
     GPB_TRY(copy2d(s, M, 1, ws.cvec, 1, ws.Caug + M, ld));
     GPB_TRY(fill2d(s, M, 1, ws.Caug + M + 1, ld, 0.0));
     t.A = G2;
-    GPB_TRY(gemm(s, t));
+    GPB_TRY(mm_gemm(s, ws, t));
     c.C = ws.dKzz; c.ldc = M;
-    GPB_TRY(gemm(s, c));
+    GPB_TRY(mm_gemm(s, ws, c));
     return GPB_OK;
 }
 
@@ -269,13 +314,13 @@ int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug) {
     g.M = ld; g.N = M; g.K = M;
     g.A = Praw; g.lda = ld; g.B = ws.Linv; g.ldb = M; g.C = W1; g.ldc = ld;
     g.krange = KR_B_LOWER;
-    GPB_TRY(gemm(s, g));
+    GPB_TRY(mm_gemm(s, ws, g));
     // Phi = Lz^-1 W1[:M] = (W1[:M]^T Lz^-T)^T, symmetric: the lower triangle of the product is what is kept
     GemmDesc h;
     h.M = M; h.N = M; h.K = M;
     h.A = W1; h.lda = ld; h.a_layout = LAYOUT_MN; h.B = ws.Linv; h.ldb = M; h.C = Paug; h.ldc = ld;
     h.krange = KR_B_LOWER; h.mask = MASK_LOWER;
-    GPB_TRY(gemm(s, h));
+    GPB_TRY(mm_gemm(s, ws, h));
     GPB_TRY(copy2d(s, 2, M, W1 + M * ld, ld, Paug + M * ld, ld));
     GPB_TRY(copy2d(s, 2, 2, Praw + M * ld + M, ld, Paug + M * ld + M, ld));
     return GPB_OK;
@@ -429,10 +474,10 @@ int svgp_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const double* P
     g.M = M; g.N = M; g.K = M;
     g.A = ws.Linv; g.lda = M; g.B = ws.Wc; g.ldb = M; g.b_layout = LAYOUT_MN; g.C = V; g.ldc = M;
     g.krange = KR_A_LOWER;
-    GPB_TRY(gemm(s, g));
+    GPB_TRY(mm_gemm(s, ws, g));
     g = GemmDesc();                                                         // Ttil = V V^T + u u^T
     g.M = M; g.N = M; g.K = M; g.A = V; g.lda = M; g.B = V; g.ldb = M; g.C = Tt; g.ldc = M;
-    GPB_TRY(gemm(s, g));
+    GPB_TRY(mm_gemm(s, ws, g));
     g = GemmDesc();
     g.M = M; g.N = M; g.K = 1; g.A = uvec; g.lda = 1; g.B = uvec; g.ldb = 1; g.C = Tt; g.ldc = M; g.beta = 1.0;
     GPB_TRY(gemm(s, g));
@@ -447,14 +492,14 @@ int svgp_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const double* P
     if (!need_grad) return GPB_OK;
     g = GemmDesc();                                                         // PT = Phi Ttil
     g.M = M; g.N = M; g.K = M; g.A = Phi; g.lda = M; g.B = Tt; g.ldb = M; g.C = ws.Tmp; g.ldc = M;
-    GPB_TRY(gemm(s, g));
+    GPB_TRY(mm_gemm(s, ws, g));
     GPB_TRY(svgp_adjoints(s, M, Phi, Tt, ws.Tmp, uvec, ws.psi, ws.sc, ws.G1, ws.G2));
     GPB_TRY(gemv(s, M, M, Phi, M, 0, uvec, ws.phiu, 1.0, 0.0));
     GPB_TRY(svgp_vectors(s, M, ws.psi, ws.phiu, uvec, ws.sc, ws.tvec, ws.u));
     GPB_TRY(dot(s, M, uvec, ws.a1, dots + 8));
     g = GemmDesc();                                                         // H = coef Phi V + V
     g.M = M; g.N = M; g.K = M; g.A = Phi; g.lda = M; g.B = V; g.ldb = M; g.b_layout = LAYOUT_MN; g.C = ws.X3; g.ldc = M;
-    GPB_TRY(gemm(s, g));
+    GPB_TRY(mm_gemm(s, ws, g));
     GPB_TRY(svgp_h(s, M, ws.X3, V, ws.sc, ws.H));
     GPB_TRY(build_pass2_adjoints(s, M, ws, ws.G1, ws.G2, ws.u));            // clobbers ws.Tmp (PT no longer needed)
     return GPB_OK;
@@ -483,7 +528,7 @@ int svgp_grad_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const doub
         g.M = M; g.N = M; g.K = M;
         g.A = ws.Linv; g.lda = M; g.a_layout = LAYOUT_MN; g.B = ws.H; g.ldb = M; g.b_layout = LAYOUT_MN;
         g.C = g_W; g.ldc = ldgw; g.alpha = -1.0; g.mask = MASK_LOWER;
-        GPB_TRY(gemm(s, g));
+        GPB_TRY(mm_gemm(s, ws, g));
         GPB_TRY(svgp_gw_diag(s, M, W, ldw, g_W, ldgw));
     }
     if (gout) {

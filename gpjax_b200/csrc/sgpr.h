@@ -39,6 +39,9 @@ struct SgprWs {
     // pass 1 (statistics SYRK, contraction over the block rows): column digit planes share oz_qt; plane = block rows rounded to 128
     double *oz_s1 = nullptr, *oz_colmax = nullptr, *oz_ones = nullptr;
     int64_t oz_kplane1 = 0;
+    // capacities of the digit buffers (bytes) and of the scale vectors (entries): the dense M x M x M products of the replicated
+    // finish borrow them between the two streamed passes (mm_gemm in sgpr.cpp)
+    int64_t oz_qt_bytes = 0, oz_qc_bytes = 0, oz_st_len = 0, oz_sc_len = 0;
 };
 
 int64_t sgpr_ws_bytes(int64_t M, int D, int64_t block_rows);

@@ -55,7 +55,7 @@ extern "C" {
 const char* gpb_version(void);
 int gpb_max_input_dim(void); /* largest D the compiled kernels accept */
 int64_t gpb_block_size(void); /* NB of the blocked algorithms for small orders (= gpb_block_size_for(0)) */
-/* NB used by every call that shares a workspace sized for order ws_n (1024 below 16,384 rows, 2048 from there on; measured in
+/* NB used by every call that shares a workspace sized for order ws_n (1024 below 12,288 rows, 2048 from there on; measured in
  * gpjax_b200/csrc/algorithms.h).  Reporting only: callers never pass a block size. */
 int64_t gpb_block_size_for(int64_t ws_n);
 
