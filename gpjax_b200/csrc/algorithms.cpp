@@ -563,6 +563,7 @@ int lauum_upper(stream_t s, int64_t N, double* A, int64_t lda, const FactorWs& w
         GemmDesc d;
         d.M = nbk; d.N = nbk; d.K = nbk;
         d.A = DTk; d.lda = NB; d.B = DTk; d.ldb = NB; d.C = ws.Sdiag + k * NB * NB; d.ldc = NB;
+        d.krange = KR_A_UPPER;  // inv(L_kk)^T is upper triangular: row m of the left operand starts at column m
         GPB_TRY(gemm(s, d));
     }
     return GPB_OK;
