@@ -115,6 +115,16 @@ int sgpr_ws_carve(void* buf, int64_t bytes, int64_t M, int D, int64_t block_rows
     return GPB_OK;
 }
 
+// Rows per streamed block: the shard is cut into ceil(Nloc / block_rows) blocks of EQUAL size (rounded up to 128 rows, never above
+// block_rows, which sized the workspace) instead of full blocks plus a ragged tail -- every block pays the same M x M write-out
+// in pass 1, so a 4,800-row tail (1.25 M rows per rank at 8 GPUs = 19.07 blocks of 65,536) cost almost a full block.
+static int64_t balanced_block_rows(int64_t nloc, int64_t block_rows) {
+    if (nloc <= block_rows) return block_rows;
+    const int64_t nb = (nloc + block_rows - 1) / block_rows;
+    const int64_t per = align_up((nloc + nb - 1) / nb, 128);
+    return per < block_rows ? per : block_rows;
+}
+
 static int check_args(const SgprArgs& a) {
     if (a.Nloc < 0 || a.M <= 0 || a.D <= 0 || a.block_rows <= 0) return GPB_ERR_INVALID;
     if (!a.Z || !a.ell || !a.variance || !a.obs_stddev) return GPB_ERR_INVALID;
@@ -249,8 +259,9 @@ int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug) {
     //    relative error of Phi ~ eps * sqrt(N) * cond(Kzz)); callers enable it for well-conditioned Kzz only.
     const bool raw = a.raw_stats != 0;
     const int planes1 = (ws.oz_qt && ozaki_available() && get_ozaki_slices() != 0) ? OZ_MAX_SLICES : 0;
-    for (int64_t r0 = 0; r0 < a.Nloc; r0 += a.block_rows) {
-        const int64_t rows = (a.Nloc - r0) < a.block_rows ? (a.Nloc - r0) : a.block_rows;
+    const int64_t block_step = balanced_block_rows(a.Nloc, a.block_rows);
+    for (int64_t r0 = 0; r0 < a.Nloc; r0 += block_step) {
+        const int64_t rows = (a.Nloc - r0) < block_step ? (a.Nloc - r0) : block_step;
         if (raw && planes1 && rows >= OZ_MIN_ROWS && sgpr_fused_digits()) {
             // Fused route: the Gram tiles of the block are turned into COLUMN digit planes (fixed scale from |k| <= variance) and into
             // per-tile-row partial sums of the two augmented statistics rows inside ONE kernel -- K_b never exists as fp64.
@@ -382,8 +393,9 @@ int sgpr_grad_local(stream_t s, const SgprArgs& a, const SgprWs& ws, double* g_Z
     const int planes = (ws.oz_qt && ozaki_available() && get_ozaki_slices() != 0) ? OZ_MAX_SLICES : 0;
     const int64_t kp = ws.oz_kplane, ldq = OZ_MAX_SLICES * kp;
     if (planes) GPB_TRY(ozaki_slice(s, M, ld, kp, ws.Caug, ld, planes, ws.oz_qc, ldq, ws.oz_sc));
-    for (int64_t r0 = 0; r0 < a.Nloc; r0 += a.block_rows) {
-        const int64_t rows = (a.Nloc - r0) < a.block_rows ? (a.Nloc - r0) : a.block_rows;
+    const int64_t block_step = balanced_block_rows(a.Nloc, a.block_rows);
+    for (int64_t r0 = 0; r0 < a.Nloc; r0 += block_step) {
+        const int64_t rows = (a.Nloc - r0) < block_step ? (a.Nloc - r0) : block_step;
         const bool fused = planes && rows >= OZ_MIN_ROWS && sgpr_fused_digits();
         if (fused) {  // Gram tiles -> ROW digit planes of [K_b^T | d_b | 1] directly (scale from max(|variance|, 1, |d_r|))
             GramDigitsDesc gd;

@@ -192,6 +192,8 @@ int gpb_mll_backward(void* stream, int kind, int64_t N, int D, const double* X, 
  *   5. all-reduce(sum) of those three
  *   6. gpb_sgpr_grad_finish (replicated)           -> adds the Kzz / scalar terms, applies *gout,
  *        writes g_obs_stddev and g_mean_const.
+ * block_rows bounds the rows streamed at a time (it sizes the workspace); the local rows are cut into ceil(Nloc / block_rows)
+ * blocks of equal size (multiples of 128 rows) rather than full blocks plus a ragged tail.
  * The same workspace must be passed to all calls of one evaluation.  info_out: int[2] =
  * {chol(Kzz) failure, chol(I + A A^T) failure} (0 = ok; value is NaN otherwise). */
 int64_t gpb_sgpr_workspace_bytes(int64_t M, int D, int64_t block_rows);
