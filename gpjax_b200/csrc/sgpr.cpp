@@ -139,7 +139,8 @@ static int check_args(const SgprArgs& a) {
 
 // K_b^T K_b (M x M, lower) += from the column digit planes in ws.oz_qt; K = kp1 block rows are split so that the int32
 // accumulators keep their head room: (t+1) K 128^2 < 2^31  ->  planes * Ksub * 2^14 stays below it
-static int sgpr_stats_syrk_int8(stream_t s, const SgprWs& ws, int64_t M, int64_t ld, int64_t kp1, int64_t ldq1, int planes1) {
+static int sgpr_stats_syrk_int8(stream_t s, const SgprWs& ws, int64_t M, int64_t ld, int64_t kp1, int64_t ldq1, int planes1,
+                                int max_ctas = 0) {
     const int64_t kmax = ((int64_t)((1ll << 31) - 1) / ((int64_t)planes1 * OZ_DIGIT_SQ_MAX)) / 256 * 256;
     const int64_t nsplit = (kp1 + kmax - 1) / kmax;
     const int64_t ksub = align_up((kp1 + nsplit - 1) / nsplit, 128);
@@ -148,7 +149,7 @@ static int sgpr_stats_syrk_int8(stream_t s, const SgprWs& ws, int64_t M, int64_t
         g.M = M; g.N = M; g.K = (kp1 - k0) < ksub ? (kp1 - k0) : ksub; g.nslices = planes1;
         g.Qa = ws.oz_qt + k0; g.ldqa = ldq1; g.sa = ws.oz_s1; g.Qb = g.Qa; g.ldqb = ldq1; g.sb = ws.oz_s1;
         g.plane_stride = kp1;
-        g.C = ws.Ppart; g.ldc = ld; g.alpha = 1.0; g.mask = MASK_LOWER;
+        g.C = ws.Ppart; g.ldc = ld; g.alpha = 1.0; g.mask = MASK_LOWER; g.max_ctas = max_ctas;
         GPB_TRY(ozaki_gemm(s, g));
     }
     return GPB_OK;
@@ -156,6 +157,12 @@ static int sgpr_stats_syrk_int8(stream_t s, const SgprWs& ws, int64_t M, int64_t
 // GPB_SGPR_FUSED=0 keeps the round-1 route (fp64 K_b block, then col_absmax / ozaki_slice_t / col_weighted_sums / ozaki_slice)
 static bool sgpr_fused_digits() {
     static const bool v = [] { const char* e = std::getenv("GPB_SGPR_FUSED"); return !(e && std::atoi(e) == 0); }();
+    return v;
+}
+
+// GPB_SGPR_OVERLAP_KZZ=0: factor Kzz on the caller's stream before the streamed loop (the order of the first half of round 2)
+static bool sgpr_overlap_kzz() {
+    static const bool v = [] { const char* e = std::getenv("GPB_SGPR_OVERLAP_KZZ"); return !(e && std::atoi(e) == 0); }();
     return v;
 }
 
@@ -235,19 +242,24 @@ int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug) {
     GPB_TRY(check_args(a));
     if (!Paug) return GPB_ERR_INVALID;
     const int64_t M = a.M, ld = M + 2;
-    // Kzz + jitter I = Lz Lz^T   (objectives.py:352-359)
+    // Kzz + jitter I = Lz Lz^T   (objectives.py:352-359) and the explicit inverse factor.  On the raw-statistics route nothing in
+    // the streamed loop needs them -- they enter only in the whitening after it -- so this latency-bound chain (~130 dependent
+    // launches, 6 ms at M = 2048, 12 ms at M = 4096; replicated on every rank) runs on a helper stream NEXT TO the first blocks.
+    const bool raw = a.raw_stats != 0;
+    stream_t kz = (raw && sgpr_overlap_kzz()) ? side_stream(s, 1) : s;
+    if (kz != s) GPB_TRY(stream_fork(s, kz));
     GramDesc gz = gram_desc(a, a.Z, a.ldz, M, ws.Lz, M);
     gz.lower_only = 1; gz.diag_add = a.jitter;
-    GPB_TRY(gram(s, gz));
-    GPB_TRY(fill2d(s, 1, 2, reinterpret_cast<double*>(ws.info2), 2, 0.0));  // clears both info words (bit pattern 0)
+    GPB_TRY(gram(kz, gz));
+    GPB_TRY(fill2d(kz, 1, 2, reinterpret_cast<double*>(ws.info2), 2, 0.0));  // clears both info words (bit pattern 0)
     // M >= 3072 crosses the int8 threshold of the blocked factorisation: the device word the digit kernels read must be set
     // (a bare M x M matrix: all 7 planes) -- it is part of the workspace and starts out uninitialised
-    GPB_TRY(factor_set_planes(s, ws.fz, M, nullptr, nullptr, 0.0));
-    GPB_TRY(potrf_lower(s, M, ws.Lz, M, ws.fz, ws.info2));
-    GPB_TRY(zero_triangle(s, M, ws.Lz, M, 2));
+    GPB_TRY(factor_set_planes(kz, ws.fz, M, nullptr, nullptr, 0.0));
+    GPB_TRY(potrf_lower(kz, M, ws.Lz, M, ws.fz, ws.info2));
+    GPB_TRY(zero_triangle(kz, M, ws.Lz, M, 2));
     // explicit inverse factor (lower, physically zero above the diagonal)
-    GPB_TRY(set_identity(s, M, ws.Linv, M));
-    GPB_TRY(trsm_lower_left(s, M, M, ws.Lz, M, ws.fz, ws.Linv, M, 0));
+    GPB_TRY(set_identity(kz, M, ws.Linv, M));
+    GPB_TRY(trsm_lower_left(kz, M, M, ws.Lz, M, ws.fz, ws.Linv, M, 0));
     GPB_TRY(fill2d(s, ld, ld, Paug, ld, 0.0));
     GPB_TRY(fill2d(s, SPLITK * ld, ld, ws.Ppart, ld, 0.0));
     // Two ways to the same row-additive statistics Paug = sum_b [A~_b ; d_b^T ; 1^T][..]^T, A~_b = Lz^-1 K_b:
@@ -257,9 +269,10 @@ int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug) {
     //    directly, Paug = T Praw T^T with T = blockdiag(Lz^-1, 1, 1) once at the end (two M^3 products).
     //    Forward N M^2 flop, but the rounding of Praw is amplified by cond(Kzz) (normal-equations-like:
     //    relative error of Phi ~ eps * sqrt(N) * cond(Kzz)); callers enable it for well-conditioned Kzz only.
-    const bool raw = a.raw_stats != 0;
     const int planes1 = (ws.oz_qt && ozaki_available() && get_ozaki_slices() != 0) ? OZ_MAX_SLICES : 0;
     const int64_t block_step = balanced_block_rows(a.Nloc, a.block_rows);
+    // while the Kzz chain is (probably) still running, the persistent int8 launches leave 8 SMs to it: the first three blocks
+    int overlap_blocks = kz != s ? 3 : 0;
     for (int64_t r0 = 0; r0 < a.Nloc; r0 += block_step) {
         const int64_t rows = (a.Nloc - r0) < block_step ? (a.Nloc - r0) : block_step;
         if (raw && planes1 && rows >= OZ_MIN_ROWS && sgpr_fused_digits()) {
@@ -272,7 +285,7 @@ int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug) {
             gd.Q = ws.oz_qt; gd.ldq = ldq1; gd.kplane = kp1; gd.scale = ws.oz_s1;
             gd.y = a.y + r0; gd.mean_const = a.mean_const; gd.part = ws.T1;
             GPB_TRY(gram_digits(s, gd));
-            GPB_TRY(sgpr_stats_syrk_int8(s, ws, M, ld, kp1, ldq1, planes1));
+            GPB_TRY(sgpr_stats_syrk_int8(s, ws, M, ld, kp1, ldq1, planes1, overlap_blocks-- > 0 ? device_sm_count() - 8 : 0));
             GPB_TRY(col_partials_reduce(s, gram_digits_tile_rows(kp1), ld, ws.T1, ws.Ppart + M * ld, ws.Ppart + (M + 1) * ld));
             continue;
         }
@@ -316,6 +329,7 @@ int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug) {
         for (int i = 0; i < SPLITK; ++i) GPB_TRY(axpy(s, ld * ld, 1.0, ws.Ppart + (int64_t)i * ld * ld, Paug));
         return GPB_OK;
     }
+    if (kz != s) GPB_TRY(stream_fork(kz, s));      // the whitening below is the first consumer of Lz^-1
     double* Praw = ws.Ppart;                       // slab 0 collects the sum
     double* W1 = ws.Ppart + (int64_t)ld * ld;      // slab 1 is scratch afterwards
     for (int i = 1; i < SPLITK; ++i) GPB_TRY(axpy(s, ld * ld, 1.0, ws.Ppart + (int64_t)i * ld * ld, Praw));
