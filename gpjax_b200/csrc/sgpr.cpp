@@ -271,8 +271,12 @@ int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug) {
     //    relative error of Phi ~ eps * sqrt(N) * cond(Kzz)); callers enable it for well-conditioned Kzz only.
     const int planes1 = (ws.oz_qt && ozaki_available() && get_ozaki_slices() != 0) ? OZ_MAX_SLICES : 0;
     const int64_t block_step = balanced_block_rows(a.Nloc, a.block_rows);
-    // while the Kzz chain is (probably) still running, the persistent int8 launches leave 8 SMs to it: the first three blocks
-    int overlap_blocks = kz != s ? 3 : 0;
+    // while the Kzz chain is (probably) still running -- the first three blocks -- the persistent int8 launches leave 8 SMs to it,
+    // but only when the SYRK has several waves of 256 x 128 output tiles: at M = 2048 its 72 lower tiles are ONE wave of the 74 CTA
+    // pairs (two pairs idle anyway), and capping the launch at 70 pairs made it two (measured: pass 1 of a 1.25 M-row shard
+    // 74.8 -> 78.3 ms with the cap)
+    const int64_t syrk_tiles = ((M + 255) / 256) * ((M + 127) / 128) / 2;
+    int overlap_blocks = (kz != s && syrk_tiles > 2 * (device_sm_count() / 2)) ? 3 : 0;
     for (int64_t r0 = 0; r0 < a.Nloc; r0 += block_step) {
         const int64_t rows = (a.Nloc - r0) < block_step ? (a.Nloc - r0) : block_step;
         if (raw && planes1 && rows >= OZ_MIN_ROWS && sgpr_fused_digits()) {
