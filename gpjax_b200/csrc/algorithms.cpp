@@ -1,13 +1,15 @@
 // Blocked right-looking algorithms (host orchestration only -- see algorithms.h).
 //
-// Storage convention for the exact-GP path (one N x N row-major buffer A, block size NB = GPB_NB = 1024):
+// Storage convention for the exact-GP path (one N x N row-major buffer A, block size NB = ws.nb: 1024 below 12,288 rows, 2048
+// from there on -- algorithms.h):
 //   * lower triangle incl. the diagonal blocks : Sigma, then its Cholesky factor L (in place)
 //   * blocks strictly above the block diagonal : W = L^-T (trtri), then Sigma^-1 = W W^T (lauum)
 //   * ws.Dinv / ws.DinvT                       : inverses of the diagonal blocks of L (and transposes)
 //   * ws.Sdiag                                 : diagonal blocks of Sigma^-1
 // so a single N x N buffer carries forward AND backward (N = 100k -> 80 GB of the 180 GB HBM) and
 // L survives the backward pass.  Every O(N^3) step is a rank-NB update C += A B^T (int8 digit planes on tcgen05 for updates
-// with >= 2048 rows -- csrc/ozaki_i8.cu -- FP64 DMMA GEMM otherwise):
+// with >= 2048 rows -- csrc/ozaki_i8.cu -- FP64 DMMA GEMM otherwise); the panel x inverse-block products next to them take the
+// same pipe (oz_tri_product):
 //   potrf : panel  X = P * inv(L_kk)^T,  trailing  A22 -= X X^T          (N^3/3)
 //   trtri : W[:,k] = -Acc * inv(L_kk)^T, Acc[:, k+1:] += W[:,k] L[k+1:,k]^T   (N^3/3)
 //   lauum : S[:k,:k] += W[:,k] W[:,k]^T, S[:,k] = W[:,k] inv(L_kk)       (N^3/3)
