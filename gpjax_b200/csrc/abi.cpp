@@ -230,6 +230,7 @@ int gpb_sgpr_stats_raw(void* stream, int kind, int64_t Nloc, int64_t M, int D, c
     SgprArgs a = sgpr_args(kind, Nloc, M, D, X, ldx, y, Z, ldz, lengthscale, lengthscale_is_scalar, variance, obs_stddev,
                            mean_const, jitter, block_rows);
     a.raw_stats = 1;
+    a.dense_int8 = 1;  // the whitening of the raw sums: same precondition as the route itself
     return sgpr_stats(stream, a, w, Paug);
 }
 
@@ -240,9 +241,10 @@ int gpb_sgpr_finish(void* stream, int kind, int64_t M, int D, const double* Z, i
     SgprWs w;
     int rc = sgpr_ws_carve(ws, ws_bytes, M, D, block_rows, &w);
     if (rc) return rc;
-    return sgpr_finish(stream, sgpr_args(kind, 0, M, D, nullptr, 0, nullptr, Z, ldz, lengthscale, lengthscale_is_scalar,
-                                         variance, obs_stddev, nullptr, 0.0, block_rows), w, Paug, need_grad, elbo_out,
-                       info_out);
+    SgprArgs a = sgpr_args(kind, 0, M, D, nullptr, 0, nullptr, Z, ldz, lengthscale, lengthscale_is_scalar, variance, obs_stddev,
+                           nullptr, 0.0, block_rows);
+    a.dense_int8 = (need_grad & GPB_FINISH_DENSE_INT8) ? 1 : 0;
+    return sgpr_finish(stream, a, w, Paug, need_grad & 1, elbo_out, info_out);
 }
 
 int gpb_sgpr_grad_local(void* stream, int kind, int64_t Nloc, int64_t M, int D, const double* X, int64_t ldx,
@@ -279,9 +281,10 @@ int gpb_svgp_finish(void* stream, int kind, int64_t M, int D, const double* Z, i
     SgprWs w;
     int rc = sgpr_ws_carve(ws, ws_bytes, M, D, block_rows, &w);
     if (rc) return rc;
-    return svgp_finish(stream, sgpr_args(kind, 0, M, D, nullptr, 0, nullptr, Z, ldz, lengthscale, lengthscale_is_scalar,
-                                         variance, obs_stddev, mean_const, jitter, block_rows), w, Paug, mu, W, ldw,
-                       num_datapoints, need_grad, elbo_out, info_out);
+    SgprArgs a = sgpr_args(kind, 0, M, D, nullptr, 0, nullptr, Z, ldz, lengthscale, lengthscale_is_scalar, variance, obs_stddev,
+                           mean_const, jitter, block_rows);
+    a.dense_int8 = (need_grad & GPB_FINISH_DENSE_INT8) ? 1 : 0;
+    return svgp_finish(stream, a, w, Paug, mu, W, ldw, num_datapoints, need_grad & 1, elbo_out, info_out);
 }
 
 int gpb_svgp_grad_finish(void* stream, int kind, int64_t M, int D, const double* Z, int64_t ldz,

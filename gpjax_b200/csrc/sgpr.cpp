@@ -183,18 +183,26 @@ static GramDesc gram_desc(const SgprArgs& a, const double* X, int64_t ldx, int64
 // contracts over their ROWS -- by columns (ozaki_slice_t).  The digit buffers of the streamed passes are free between pass 1 and
 // pass 2, which is exactly where the finish runs.  GPB_SGPR_FINISH_INT8=0 keeps the DMMA GEMMs; so do small products
 // (any extent < 2048), batched ones and operands that do not fit the borrowed buffers.
+// Precondition (SgprArgs::dense_int8, bit GPB_FINISH_DENSE_INT8 of the finish entry points' flag word): a WELL-CONDITIONED Kzz --
+// the same thing the raw-statistics route needs, and the public "auto" route sets both from one condition estimate.  Digits are
+// relative to the row / column maximum, and the rows of Lz^-1 span cond(Kzz) in magnitude: on the host model at M = 260 and
+// cond(Kzz) = 6e7 the 56-bit products put the variance / inducing-input gradients 9.6e-9 / 1.4e-8 from the oracle where the FP64
+// GEMMs sit at 2e-10 / 7e-10 (value and well-conditioned cases: indistinguishable), so an ill-conditioned Kzz keeps the DMMA GEMMs.
 // -------------------------------------------------------------------------------------------
-constexpr int64_t MM_INT8_MIN = 2048;
+#ifndef GPB_MM_INT8_MIN
+#define GPB_MM_INT8_MIN 2048  // the host model of the CPU tests builds with 256 so that its M = 260 cases take this route
+#endif
+constexpr int64_t MM_INT8_MIN = GPB_MM_INT8_MIN;
 static bool mm_int8_on() {
     static const bool v = [] { const char* e = std::getenv("GPB_SGPR_FINISH_INT8"); return !(e && std::atoi(e) == 0); }();
     return v;
 }
-static int mm_gemm(stream_t s, const SgprWs& ws, const GemmDesc& g) {
+static int mm_gemm(stream_t s, const SgprWs& ws, const GemmDesc& g, bool allow_int8) {
     const int64_t kp = align_up(g.K, 128), ldq = (int64_t)OZ_MAX_SLICES * kp;
     const bool fits = ws.oz_qt && ws.oz_qc && g.M * ldq <= ws.oz_qt_bytes && g.N * ldq <= ws.oz_qc_bytes && g.M <= ws.oz_st_len &&
                       g.N <= ws.oz_sc_len && (g.a_layout == LAYOUT_K || g.M <= ws.oz_sc_len) &&
                       (int64_t)OZ_MAX_SLICES * kp * OZ_DIGIT_SQ_MAX < (1ll << 31);
-    const bool route = mm_int8_on() && fits && g.batch <= 1 && g.M >= MM_INT8_MIN && g.N >= MM_INT8_MIN && g.K >= MM_INT8_MIN &&
+    const bool route = allow_int8 && mm_int8_on() && fits && g.batch <= 1 && g.M >= MM_INT8_MIN && g.N >= MM_INT8_MIN && g.K >= MM_INT8_MIN &&
                        (g.beta == 0.0 || g.beta == 1.0) && (g.mask == MASK_NONE || g.mask == MASK_LOWER) &&
                        get_ozaki_slices() != 0 && ozaki_available() && ozaki_supports_extensions();
     if (!route) return gemm(s, g);
@@ -217,24 +225,24 @@ static int mm_gemm(stream_t s, const SgprWs& ws, const GemmDesc& g) {
 // Caug = [Linv^T G1 Linv | Linv^T uvec | 0]  (M x (M+2), row stride M+2): pass 2 forms dK_b^T = [K_b^T|d|1] Caug^T.
 // dKzz = Linv^T G2 Linv.
 static int build_pass2_adjoints(stream_t s, int64_t M, const SgprWs& ws, const double* G1, const double* G2,
-                                const double* uvec) {
+                                const double* uvec, bool dense_int8) {
     const int64_t ld = M + 2;
     GemmDesc t;
     t.M = M; t.N = M; t.K = M;
     t.A = G1; t.lda = M; t.B = ws.Linv; t.ldb = M; t.b_layout = LAYOUT_MN; t.C = ws.Tmp; t.ldc = M;
-    GPB_TRY(mm_gemm(s, ws, t));
+    GPB_TRY(mm_gemm(s, ws, t, dense_int8));
     GemmDesc c;
     c.M = M; c.N = M; c.K = M;
     c.A = ws.Linv; c.lda = M; c.a_layout = LAYOUT_MN; c.B = ws.Tmp; c.ldb = M; c.b_layout = LAYOUT_MN;
     c.C = ws.Caug; c.ldc = ld;
-    GPB_TRY(mm_gemm(s, ws, c));
+    GPB_TRY(mm_gemm(s, ws, c, dense_int8));
     GPB_TRY(gemv(s, M, M, ws.Linv, M, 1, uvec, ws.cvec, 1.0, 0.0));
     GPB_TRY(copy2d(s, M, 1, ws.cvec, 1, ws.Caug + M, ld));
     GPB_TRY(fill2d(s, M, 1, ws.Caug + M + 1, ld, 0.0));
     t.A = G2;
-    GPB_TRY(mm_gemm(s, ws, t));
+    GPB_TRY(mm_gemm(s, ws, t, dense_int8));
     c.C = ws.dKzz; c.ldc = M;
-    GPB_TRY(mm_gemm(s, ws, c));
+    GPB_TRY(mm_gemm(s, ws, c, dense_int8));
     return GPB_OK;
 }
 
@@ -343,13 +351,13 @@ int sgpr_stats(stream_t s, const SgprArgs& a, const SgprWs& ws, double* Paug) {
     g.M = ld; g.N = M; g.K = M;
     g.A = Praw; g.lda = ld; g.B = ws.Linv; g.ldb = M; g.C = W1; g.ldc = ld;
     g.krange = KR_B_LOWER;
-    GPB_TRY(mm_gemm(s, ws, g));
+    GPB_TRY(mm_gemm(s, ws, g, a.dense_int8 != 0));
     // Phi = Lz^-1 W1[:M] = (W1[:M]^T Lz^-T)^T, symmetric: the lower triangle of the product is what is kept
     GemmDesc h;
     h.M = M; h.N = M; h.K = M;
     h.A = W1; h.lda = ld; h.a_layout = LAYOUT_MN; h.B = ws.Linv; h.ldb = M; h.C = Paug; h.ldc = ld;
     h.krange = KR_B_LOWER; h.mask = MASK_LOWER;
-    GPB_TRY(mm_gemm(s, ws, h));
+    GPB_TRY(mm_gemm(s, ws, h, a.dense_int8 != 0));
     GPB_TRY(copy2d(s, 2, M, W1 + M * ld, ld, Paug + M * ld, ld));
     GPB_TRY(copy2d(s, 2, 2, Praw + M * ld + M, ld, Paug + M * ld + M, ld));
     return GPB_OK;
@@ -394,7 +402,7 @@ int sgpr_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const double* P
     GPB_TRY(dot(s, M, ws.psi, ws.v, ws.dots + 0));
     GPB_TRY(dot(s, M, ws.v, ws.a1, ws.dots + 1));
     GPB_TRY(vec_sum(s, M, ws.rowsum, ws.dots + 2));
-    GPB_TRY(build_pass2_adjoints(s, M, ws, ws.G1, ws.G2, ws.u));
+    GPB_TRY(build_pass2_adjoints(s, M, ws, ws.G1, ws.G2, ws.u, a.dense_int8 != 0));
     return GPB_OK;
 }
 
@@ -504,10 +512,10 @@ int svgp_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const double* P
     g.M = M; g.N = M; g.K = M;
     g.A = ws.Linv; g.lda = M; g.B = ws.Wc; g.ldb = M; g.b_layout = LAYOUT_MN; g.C = V; g.ldc = M;
     g.krange = KR_A_LOWER;
-    GPB_TRY(mm_gemm(s, ws, g));
+    GPB_TRY(mm_gemm(s, ws, g, a.dense_int8 != 0));
     g = GemmDesc();                                                         // Ttil = V V^T + u u^T
     g.M = M; g.N = M; g.K = M; g.A = V; g.lda = M; g.B = V; g.ldb = M; g.C = Tt; g.ldc = M;
-    GPB_TRY(mm_gemm(s, ws, g));
+    GPB_TRY(mm_gemm(s, ws, g, a.dense_int8 != 0));
     g = GemmDesc();
     g.M = M; g.N = M; g.K = 1; g.A = uvec; g.lda = 1; g.B = uvec; g.ldb = 1; g.C = Tt; g.ldc = M; g.beta = 1.0;
     GPB_TRY(gemm(s, g));
@@ -522,16 +530,24 @@ int svgp_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const double* P
     if (!need_grad) return GPB_OK;
     g = GemmDesc();                                                         // PT = Phi Ttil
     g.M = M; g.N = M; g.K = M; g.A = Phi; g.lda = M; g.B = Tt; g.ldb = M; g.C = ws.Tmp; g.ldc = M;
-    GPB_TRY(mm_gemm(s, ws, g));
+    GPB_TRY(mm_gemm(s, ws, g, a.dense_int8 != 0));
     GPB_TRY(svgp_adjoints(s, M, Phi, Tt, ws.Tmp, uvec, ws.psi, ws.sc, ws.G1, ws.G2));
     GPB_TRY(gemv(s, M, M, Phi, M, 0, uvec, ws.phiu, 1.0, 0.0));
     GPB_TRY(svgp_vectors(s, M, ws.psi, ws.phiu, uvec, ws.sc, ws.tvec, ws.u));
     GPB_TRY(dot(s, M, uvec, ws.a1, dots + 8));
     g = GemmDesc();                                                         // H = coef Phi V + V
     g.M = M; g.N = M; g.K = M; g.A = Phi; g.lda = M; g.B = V; g.ldb = M; g.b_layout = LAYOUT_MN; g.C = ws.X3; g.ldc = M;
-    GPB_TRY(mm_gemm(s, ws, g));
+    GPB_TRY(mm_gemm(s, ws, g, a.dense_int8 != 0));
     GPB_TRY(svgp_h(s, M, ws.X3, V, ws.sc, ws.H));
-    GPB_TRY(build_pass2_adjoints(s, M, ws, ws.G1, ws.G2, ws.u));            // clobbers ws.Tmp (PT no longer needed)
+    // the dense part of dF/dW, tril(-Lz^-T H), is formed HERE (X3 is free again and survives pass 2): this entry point knows whether
+    // the dense products may take the int8 pipe, gpb_svgp_grad_finish has no flag word
+    GPB_TRY(fill2d(s, M, M, ws.X3, M, 0.0));
+    g = GemmDesc();
+    g.M = M; g.N = M; g.K = M;
+    g.A = ws.Linv; g.lda = M; g.a_layout = LAYOUT_MN; g.B = ws.H; g.ldb = M; g.b_layout = LAYOUT_MN;
+    g.C = ws.X3; g.ldc = M; g.alpha = -1.0; g.mask = MASK_LOWER;
+    GPB_TRY(mm_gemm(s, ws, g, a.dense_int8 != 0));
+    GPB_TRY(build_pass2_adjoints(s, M, ws, ws.G1, ws.G2, ws.u, a.dense_int8 != 0));            // clobbers ws.Tmp (PT no longer needed)
     return GPB_OK;
 }
 
@@ -552,13 +568,8 @@ int svgp_grad_finish(stream_t s, const SgprArgs& a, const SgprWs& ws, const doub
     GPB_TRY(gemv(s, M, M, ws.Linv, M, 1, ws.tvec, gmu, 1.0, 0.0));  // dF/dmu = Lz^-T [coef (psi - Phi u) - u]
     GPB_TRY(vec_sum(s, M, gmu, ws.dots + 9));                       // mu - mu_z: the mean constant sees -1^T dF/dmu
     GPB_TRY(svgp_scalar_grads(s, ws.sc, ws.dots, ws.dots + 8, a.variance, a.obs_stddev, a.jitter, g_var, g_obs, g_mean));
-    if (g_W) {  // tril( -Lz^-T (coef Phi + I) V + W^-T )
-        GPB_TRY(fill2d(s, M, M, g_W, ldgw, 0.0));
-        GemmDesc g;
-        g.M = M; g.N = M; g.K = M;
-        g.A = ws.Linv; g.lda = M; g.a_layout = LAYOUT_MN; g.B = ws.H; g.ldb = M; g.b_layout = LAYOUT_MN;
-        g.C = g_W; g.ldc = ldgw; g.alpha = -1.0; g.mask = MASK_LOWER;
-        GPB_TRY(mm_gemm(s, ws, g));
+    if (g_W) {  // tril( -Lz^-T (coef Phi + I) V + W^-T ): the dense part was left in ws.X3 by svgp_finish
+        GPB_TRY(copy2d(s, M, M, ws.X3, M, g_W, ldgw));
         GPB_TRY(svgp_gw_diag(s, M, W, ldw, g_W, ldgw));
     }
     if (gout) {

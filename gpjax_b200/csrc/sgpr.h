@@ -23,6 +23,8 @@ struct SgprArgs {
     double jitter = 1e-6;
     int64_t block_rows = 32768;  // rows per streamed block
     int raw_stats = 0;           // pass 1 accumulates raw [K_b^T|d|1] products and whitens once at the end (see sgpr.cpp)
+    int dense_int8 = 0;          // the caller vouches for a well-conditioned Kzz (the raw-statistics route's own precondition): the dense
+                                 // M x M x M products of the replicated finish may run as 7-plane int8 digit products (mm_gemm)
 };
 
 struct SgprWs {

@@ -192,6 +192,7 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(GpbSgprStats, SgprStatsImpl,
                                   .Ret<F64>().Ret<F64>()
                                   .Attr<int32_t>("kind").Attr<double>("jitter").Attr<int64_t>("block_rows").Attr<int32_t>("raw"));
 
+// need_grad is the flag word of include/gpjax_b200.h: bit 0 = prepare the gradient pass, bit 1 = GPB_FINISH_DENSE_INT8
 static ffi::Error SgprFinishImpl(cudaStream_t stream, F64 Z, F64 ell, F64 var, F64 sn, F64 Paug, F64 ws, ffi::Result<F64> elbo,
                                  ffi::Result<S32> info, ffi::Result<F64> ws_out, int32_t kind, int64_t block_rows, int32_t need_grad) {
     const int64_t M = Z.dimensions()[0], D = Z.dimensions()[1];

@@ -196,6 +196,16 @@ def _stats(L, raw: bool):
     return (L.gpb_sgpr_stats_raw, "gpb_sgpr_stats_raw") if raw else (L.gpb_sgpr_stats, "gpb_sgpr_stats")
 
 
+FINISH_DENSE_INT8 = 2  # include/gpjax_b200.h: GPB_FINISH_DENSE_INT8
+
+
+def finish_flags(need_grad, raw) -> int:
+    """Flag word of gpb_sgpr_finish / gpb_svgp_finish: bit 0 = prepare the gradient pass, bit 1 = Kzz is well conditioned (the
+    raw-statistics route was chosen: estimated cond <= RAW_STATISTICS_COND_LIMIT, or the caller asked for it), so the dense M^3
+    products of the replicated finish may run as int8 digit-plane products."""
+    return (1 if need_grad else 0) | (FINISH_DENSE_INT8 if raw else 0)
+
+
 def _forward_raw(st, kind, X, y, Z, ell_v, iso, var, sn, mean, jitter, block_rows, group, need_grad, raw=False):
     n_loc, D = X.shape
     M = Z.shape[0]
@@ -209,7 +219,7 @@ def _forward_raw(st, kind, X, y, Z, ell_v, iso, var, sn, mean, jitter, block_row
     val = torch.empty(1, dtype=torch.float64, device=Z.device)
     info = torch.zeros(2, dtype=torch.int32, device=Z.device)
     rc = L.gpb_sgpr_finish(_stream(), kind, M, D, _p(Z), Z.stride(0), _p(ell_v), iso, _p(var), _p(sn), block_rows,
-                           _p(st.ws), st.nbytes, _p(P), int(need_grad), _p(val), _p(info))
+                           _p(st.ws), st.nbytes, _p(P), finish_flags(need_grad, raw), _p(val), _p(info))
     _abi.check(rc, "gpb_sgpr_finish")
     st.generation = next_generation()
     return val, info
@@ -307,7 +317,7 @@ def profile_phases(kind, X, y, Z, ell, variance, obs_stddev, mean_const=None, ji
     _all_reduce(P, group)
     ev[2].record()
     _abi.check(L.gpb_sgpr_finish(_stream(), kind, M, D, _p(Z), Z.stride(0), _p(ell_v), iso, _p(var), _p(sn), block_rows,
-                                 _p(st.ws), st.nbytes, _p(P), 1, _p(val), _p(info)), "gpb_sgpr_finish")
+                                 _p(st.ws), st.nbytes, _p(P), finish_flags(True, raw), _p(val), _p(info)), "gpb_sgpr_finish")
     ev[3].record()
     _abi.check(L.gpb_sgpr_grad_local(_stream(), kind, n_loc, M, D, _p(X), X.stride(0) if n_loc else D, _p(y), _p(Z),
                                      Z.stride(0), _p(ell_v), iso, _p(var), _p(sn), _p(mean), block_rows, _p(st.ws), st.nbytes,

@@ -9,7 +9,7 @@ import torch
 from . import _abi
 from ._lib import lib
 from .ops import _check_mat, _ell_args, _kscalars, _no_data_grad, _p, _scalar, _stream, next_generation, require_cuda
-from .sgpr_ops import DEFAULT_BLOCK_ROWS, _all_reduce, _state, _stats, _use_raw_statistics
+from .sgpr_ops import DEFAULT_BLOCK_ROWS, _all_reduce, _state, _stats, _use_raw_statistics, finish_flags
 
 
 def _forward_raw(st, kind, X, y, Z, ell_v, iso, var, sn, mean, mu, W, ndata, jitter, block_rows, group, need_grad,
@@ -27,7 +27,7 @@ def _forward_raw(st, kind, X, y, Z, ell_v, iso, var, sn, mean, mu, W, ndata, jit
     info = torch.zeros(2, dtype=torch.int32, device=Z.device)
     rc = L.gpb_svgp_finish(_stream(), kind, M, D, _p(Z), Z.stride(0), _p(ell_v), iso, _p(var), _p(sn), _p(mean), _p(mu),
                            _p(W), W.stride(0), float(ndata), float(jitter), block_rows, _p(st.ws), st.nbytes, _p(P),
-                           int(need_grad), _p(val), _p(info))
+                           finish_flags(need_grad, raw), _p(val), _p(info))
     _abi.check(rc, "gpb_svgp_finish")
     st.generation = next_generation()
     return val

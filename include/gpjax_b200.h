@@ -40,6 +40,7 @@ extern "C" {
 #define GPB_ERR_UNSUPPORTED (-2)
 #define GPB_ERR_LAUNCH (-3)
 #define GPB_ERR_WORKSPACE (-4)
+#define GPB_FINISH_DENSE_INT8 2 /* flag bit of need_grad in gpb_sgpr_finish / gpb_svgp_finish (see there) */
 
 #define GPB_KIND_RBF 0
 #define GPB_KIND_MATERN32 1
@@ -192,6 +193,10 @@ int gpb_mll_backward(void* stream, int kind, int64_t N, int D, const double* X, 
  *   5. all-reduce(sum) of those three
  *   6. gpb_sgpr_grad_finish (replicated)           -> adds the Kzz / scalar terms, applies *gout,
  *        writes g_obs_stddev and g_mean_const.
+ * need_grad of gpb_sgpr_finish / gpb_svgp_finish is a flag word: bit 0 = prepare the gradient pass; bit 1 (GPB_FINISH_DENSE_INT8) =
+ * the caller vouches that Kzz is well conditioned (the precondition of gpb_sgpr_stats_raw; the Python "auto" route sets both from
+ * one condition estimate, cond <= 1e3), so the dense M x M x M products of this replicated step may run as 56-bit int8
+ * digit-plane products on the tcgen05 pipe (M >= 2048) instead of FP64 DMMA GEMMs.  Without the bit the arithmetic is FP64.
  * block_rows bounds the rows streamed at a time (it sizes the workspace); the local rows are cut into ceil(Nloc / block_rows)
  * blocks of equal size (multiples of 128 rows) rather than full blocks plus a ragged tail.
  * The same workspace must be passed to all calls of one evaluation.  info_out: int[2] =

@@ -170,8 +170,9 @@ def _sgpr_run(lib, kind, X, y, Z, ell, iso, var, sn, c, jitter, block_rows, shar
     vals = []
     for r in range(shards):
         val, info = np.zeros(1), np.zeros(2, np.int32)
+        # flag word: bit 0 = gradients, bit 1 (GPB_FINISH_DENSE_INT8) = well-conditioned Kzz, as the public route sets it with raw
         rc = lib.gpb_sgpr_finish(None, kind, M, D, p(Z), D, p(ellv), int(iso), p(var_a), p(sn_a), block_rows,
-                                 p(wss[r]), nbytes, p(Pall), 1, p(val), p(info))
+                                 p(wss[r]), nbytes, p(Pall), 1 | (2 if raw else 0), p(val), p(info))
         assert rc == 0 and not info.any()
         vals.append(val[0])
     assert len(set(vals)) == 1  # replicated finish is bit-identical on every rank
@@ -484,3 +485,57 @@ def test_sgpr_statistics_and_pass2_through_int8_digit_planes(lib, raw):
         assert np.max(np.abs(a - b)) <= 1e-7 * amp * max(np.max(np.abs(b)), 1e-8 * abs(ref)), k
         a0 = np.asarray(g0[k]).reshape(np.shape(gref[k]))
         assert np.max(np.abs(a - a0)) <= 1e-10 * max(amp, amp2) * max(np.max(np.abs(b)), 1e-8 * abs(ref)), (k, cond)
+
+
+def test_svgp_finish_dense_products_on_the_int8_model(lib):
+    """The dense M x M x M products of the replicated SVGP finish (V = Lz^-1 W, V V^T, Phi Ttil, Phi V, Linv^T G Linv,
+    -Linv^T H) as 7-plane digit products (mm_gemm in sgpr.cpp; the host model routes extents >= 256): row digit planes for
+    K-contiguous operands, column digit planes for MN-layout ones, triangular K-ranges, lower mask, beta = 0.  Well-conditioned Kzz
+    (cond ~ 4e1: the precondition bit 1 of the flag word states); flag 1 keeps every dense product on the FP64 GEMM model, and both
+    must sit far inside the oracle tolerance."""
+    N, M, D, block = 600, 260, 5, 300
+    X, y = data(N, D, N + M)
+    rng = np.random.default_rng(M)
+    Z = np.ascontiguousarray(rng.uniform(-2, 2, (M, D)))
+    mu = rng.standard_normal(M) * 0.3
+    W = np.ascontiguousarray(np.tril(rng.standard_normal((M, M)) * 0.02) + 0.7 * np.eye(M))
+    ell = np.full(D, 0.8)
+    var_a, sn_a, c_a = np.array([1.3]), np.array([0.4]), np.array([0.2])
+    ndata, jitter = 5000.0, 1e-6
+    assert np.linalg.cond(o.gram("rbf", Z, ell, 1.3) + jitter * np.eye(M)) < 1e3
+    ref, gref = o.svgp_elbo_value_and_grad_autodiff("rbf", X, y, Z, ell, 1.3, 0.4, 0.2, mu, np.tril(W), ndata, jitter)
+    nbytes = lib.gpb_sgpr_workspace_bytes(M, D, block)
+    out = {}
+    for flag in (1, 3):
+        ws, P = np.zeros(nbytes // 8 + 8), np.zeros(lib.gpb_sgpr_stats_count(M))
+        val, info = np.zeros(1), np.zeros(2, np.int32)
+        try:
+            lib.gpb_set_ozaki_slices(7)
+            assert lib.gpb_sgpr_stats(None, 0, N, M, D, p(X), D, p(y), p(Z), D, p(ell), 0, p(var_a), p(sn_a), p(c_a), jitter,
+                                      block, p(ws), nbytes, p(P)) == 0  # whitened statistics: identical input for both flags
+            assert lib.gpb_svgp_finish(None, 0, M, D, p(Z), D, p(ell), 0, p(var_a), p(sn_a), p(c_a), p(mu), p(W), M, ndata, jitter,
+                                       block, p(ws), nbytes, p(P), flag, p(val), p(info)) == 0 and not info.any()
+            f = np.zeros(M * D + D + 1)
+            assert lib.gpb_sgpr_grad_local(None, 0, N, M, D, p(X), D, p(y), p(Z), D, p(ell), 0, p(var_a), p(sn_a), p(c_a), block,
+                                           p(ws), nbytes, p(f[:M * D]), p(f[M * D:M * D + D]), p(f[M * D + D:])) == 0
+            gZ, gl, gv = f[:M * D].copy(), f[M * D:M * D + D].copy(), f[M * D + D:].copy()
+            gs, gc, gmu, gW = np.zeros(1), np.zeros(1), np.zeros(M), np.full((M, M), np.nan)
+            assert lib.gpb_svgp_grad_finish(None, 0, M, D, p(Z), D, p(ell), 0, p(var_a), p(sn_a), jitter, block, p(ws), nbytes, None,
+                                            p(W), M, p(gZ), p(gl), p(gv), p(gs), p(gc), p(gmu), p(gW), M) == 0
+        finally:
+            lib.gpb_set_ozaki_slices(0)
+        assert abs(val[0] - ref) <= 1e-10 * abs(ref)
+        got = dict(lengthscale=gl, variance=gv[0], obs_stddev=gs[0], mean_const=gc[0], inducing_inputs=gZ.reshape(M, D),
+                   variational_mean=gmu, variational_root_covariance=gW)
+        assert np.all(np.triu(gW, 1) == 0.0)
+        for k in gref:
+            a, b = np.asarray(got[k]).reshape(np.shape(gref[k])), np.asarray(gref[k])
+            assert np.max(np.abs(a - b)) <= 1e-9 * max(np.max(np.abs(b)), 1e-8 * abs(ref)), (k, flag)
+        out[flag] = got
+    # the flag really changes the arithmetic of the dense products (digit planes vs the FP64 GEMM model) ...
+    assert not np.array_equal(out[1]["variational_root_covariance"], out[3]["variational_root_covariance"])
+    assert not np.array_equal(out[1]["inducing_inputs"], out[3]["inducing_inputs"])
+    # ... and at this conditioning only at the 1e-12 level
+    for k in gref:
+        a, b = np.asarray(out[1][k]), np.asarray(out[3][k])
+        assert np.max(np.abs(a - b)) <= 1e-11 * max(np.max(np.abs(np.asarray(gref[k]))), 1e-8 * abs(ref)), k
