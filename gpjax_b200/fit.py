@@ -4,6 +4,7 @@ of every trainable Parameter)."""
 from __future__ import annotations
 
 import copy
+import os
 import typing as tp
 
 import torch
@@ -61,8 +62,18 @@ def get_batch(train_data: Dataset, batch_size: int, key) -> Dataset:
 
 def fit(*, model: Module, objective, train_data: Dataset, optim: GradientTransformation,
         params_bijection: tp.Optional[dict] = DEFAULT_BIJECTION, trainable=Parameter, key=42, num_iters: int = 100,
-        batch_size: int = -1, log_rate: int = 10, verbose: bool = True, unroll: int = 1, safe: bool = True):
-    """Minimises `objective(model, batch)`; returns (optimised copy of the model, history[num_iters])."""
+        batch_size: int = -1, log_rate: int = 10, verbose: bool = True, unroll: int = 1, safe: bool = True,
+        cuda_graph: tp.Optional[bool] = None):
+    """Minimises `objective(model, batch)`; returns (optimised copy of the model, history[num_iters]).
+
+    `cuda_graph` (not a reference argument; default: the environment switch GPB_FIT_CUDA_GRAPH, off when unset) plays the
+    part `jax.jit` + `lax.scan` play in the reference's loop (fit.py:160-170): after `_GRAPH_WARMUP` ordinary iterations one
+    optimisation step -- objective, its backward, the optimiser update, the history entry -- is captured once as a CUDA graph and
+    replayed for the remaining iterations, so a step costs one graph launch instead of a few hundred kernel launches from Python
+    (the launch-bound regime: N of a few thousand, BASELINE config 1).  Requirements, all checked or failing loudly at capture:
+    full batches (`batch_size == -1`), everything on one CUDA device, an objective whose evaluation only enqueues device work
+    (conjugate_mll, conjugate_loocv, and the sparse objectives with an explicit statistics route), and an optimiser whose state
+    is made of tensors (the optimisers in `gpjax_b200.optim` are)."""
     if safe:
         _check_model(model)
         _check_train_data(train_data)
@@ -87,16 +98,97 @@ def fit(*, model: Module, objective, train_data: Dataset, optim: GradientTransfo
             bar = trange(num_iters)
         except Exception:  # pragma: no cover
             bar = None
-    for it in (bar if bar is not None else range(num_iters)):
+    if cuda_graph is None:
+        cuda_graph = os.environ.get("GPB_FIT_CUDA_GRAPH", "0") not in ("", "0")
+    if cuda_graph:
+        if batch_size != -1:
+            raise NotImplementedError("fit(cuda_graph=True) replays one captured step: it needs full batches (batch_size=-1)")
+        if train_data.X.device.type != "cuda":
+            raise RuntimeError("fit(cuda_graph=True) needs the training data on a CUDA device")
+    n_eager = min(num_iters, _GRAPH_WARMUP) if cuda_graph else num_iters
+    it = 0
+    for it in range(n_eager):
         batch = get_batch(train_data, batch_size, gen) if batch_size != -1 else train_data
         val, grads = loss.value_and_grad(u, batch)
         updates, opt_state = optim.update(grads, opt_state, u)
         u = apply_updates(u, updates)
         history[it] = val
-        if bar is not None and it % log_rate == 0:
-            bar.set_postfix(Value=f"{val.item():.2f}")
+        if bar is not None:
+            bar.update(1)
+            if it % log_rate == 0:
+                bar.set_postfix(Value=f"{val.item():.2f}")
+    if n_eager < num_iters:
+        u = _replay_captured_steps(loss, optim, u, opt_state, train_data, history, n_eager, num_iters, bar, log_rate)
+    if bar is not None:
+        bar.close()
     loss.commit(u)
     return model, history
+
+
+_GRAPH_WARMUP = 3  # ordinary iterations before the capture: they size the cached workspaces and create the helper streams
+
+
+def _tree_tensors(old, new, where="optimiser state"):
+    """Pairs (old tensor, new tensor) of two optimiser states of equal structure; a host-side leaf that changes from step to step
+    (a Python step counter) cannot be replayed and is refused."""
+    if isinstance(old, torch.Tensor):
+        if not isinstance(new, torch.Tensor) or new.shape != old.shape or new.dtype != old.dtype:
+            raise TypeError(f"fit(cuda_graph=True): {where} changes type or shape between steps")
+        return [(old, new)]
+    if isinstance(old, dict):
+        if not isinstance(new, dict) or old.keys() != new.keys():
+            raise TypeError(f"fit(cuda_graph=True): {where} changes structure between steps")
+        return [pair for k in old for pair in _tree_tensors(old[k], new[k], f"{where}[{k!r}]")]
+    if isinstance(old, (tuple, list)):
+        if not isinstance(new, (tuple, list)) or len(old) != len(new):
+            raise TypeError(f"fit(cuda_graph=True): {where} changes structure between steps")
+        return [pair for i, (a, b) in enumerate(zip(old, new)) for pair in _tree_tensors(a, b, f"{where}[{i}]")]
+    if old != new:
+        raise TypeError(f"fit(cuda_graph=True): {where} holds a host-side value that changes every step ({old!r} -> {new!r}); "
+                        "keep optimiser state in device tensors")
+    return []
+
+
+def _tree_clone(t):
+    if isinstance(t, torch.Tensor):
+        return t.clone()
+    if isinstance(t, dict):
+        return {k: _tree_clone(v) for k, v in t.items()}
+    if isinstance(t, (tuple, list)):
+        return type(t)(_tree_clone(v) for v in t) if not hasattr(t, "_fields") else type(t)(*(_tree_clone(v) for v in t))
+    return t
+
+
+def _replay_captured_steps(loss, optim, u, opt_state, train_data, history, first, num_iters, bar, log_rate):
+    """Iterations first .. num_iters-1 as replays of ONE captured step.  The step reads and writes fixed buffers: the unconstrained
+    parameters `u`, the optimiser state, a device-side iteration index and `history`; the objective's own buffers (the cached
+    N x N workspace of ops._mll_state, the streamed SGPR state) were sized by the ordinary iterations and stay alive in their
+    caches while the graph exists."""
+    dev = train_data.X.device
+    with torch.cuda.device(dev):
+        u = {k: v.detach().clone() for k, v in u.items()}
+        opt_state = _tree_clone(opt_state)
+        slot = torch.full((1,), first, dtype=torch.int64, device=dev)
+        graph = torch.cuda.CUDAGraph()
+        torch.cuda.synchronize(dev)
+        with torch.cuda.graph(graph):
+            val, grads = loss.value_and_grad(u, train_data)
+            updates, new_state = optim.update(grads, opt_state, u)
+            new_u = apply_updates(u, updates)
+            history.index_copy_(0, slot, val.reshape(1).to(history.dtype))
+            slot.add_(1)
+            for k in u:
+                u[k].copy_(new_u[k])
+            for old, new in _tree_tensors(opt_state, new_state):
+                old.copy_(new)
+        for it in range(first, num_iters):
+            graph.replay()
+            if bar is not None:
+                bar.update(1)
+                if it % log_rate == 0:
+                    bar.set_postfix(Value=f"{history[it].item():.2f}")
+        torch.cuda.synchronize(dev)  # the graph (and its private pool) is released on return
+    return u
 
 
 def fit_scipy(*, model: Module, objective, train_data: Dataset, trainable=Parameter, max_iters: int = 500,

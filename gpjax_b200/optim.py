@@ -29,10 +29,14 @@ def sgd(learning_rate: float) -> GradientTransformation:
 
 def adam(learning_rate: float, b1: float = 0.9, b2: float = 0.999, eps: float = 1e-8,
          weight_decay: float = 0.0) -> GradientTransformation:
-    """optax.adam (weight_decay = 0) / optax.adamw semantics: bias-corrected moments, eps outside the sqrt."""
+    """optax.adam (weight_decay = 0) / optax.adamw semantics: bias-corrected moments, eps outside the sqrt.  The step count
+    lives on the parameters' device (a 0-d tensor, like optax's `count` array), so one update is a fixed sequence of device
+    operations that `fit(..., cuda_graph=True)` can capture and replay."""
 
     def init(params):
-        return {"count": 0, "mu": {k: torch.zeros_like(v) for k, v in params.items()},
+        ref = next(iter(params.values()), None)
+        count = torch.zeros((), dtype=torch.float64, device=None if ref is None else ref.device)
+        return {"count": count, "mu": {k: torch.zeros_like(v) for k, v in params.items()},
                 "nu": {k: torch.zeros_like(v) for k, v in params.items()}}
 
     def update(grads, state, params=None):

@@ -306,3 +306,31 @@ def test_lbfgs_minimize_zoom_linesearch_reaches_the_scipy_optimum():
     x1, f1, g1, n1 = lbfgs_minimize(quad, np.linalg.solve(H, b), max_iters=5, gtol=1e3)
     assert n1 == 1
 
+
+
+def test_fit_cuda_graph_argument_checks_on_cpu():
+    """fit(cuda_graph=True) refuses what it cannot replay before touching the GPU: minibatches and CPU data."""
+    post, opt = _toy_model(), gpx.optim.adam(0.1)
+    D = gpx.Dataset(X=torch.zeros((10, 1), dtype=torch.float64), y=torch.zeros((10, 1), dtype=torch.float64))
+    with pytest.raises(NotImplementedError):
+        gpx.fit(model=post, objective=_toy_objective, train_data=D, optim=opt, num_iters=4, batch_size=2, verbose=False,
+                cuda_graph=True)
+    with pytest.raises(RuntimeError):
+        gpx.fit(model=post, objective=_toy_objective, train_data=D, optim=opt, num_iters=4, verbose=False, cuda_graph=True)
+
+
+def test_fit_cuda_graph_state_pairing():
+    """The replayed step copies the new optimiser state over the old one leaf by leaf; a host-side leaf that moves is refused."""
+    from gpjax_b200.fit import _tree_clone, _tree_tensors
+
+    opt = gpx.optim.adam(0.1)
+    p = {"a": torch.zeros(3, dtype=torch.float64), "b": torch.ones((), dtype=torch.float64)}
+    st0 = opt.init(p)
+    _, st1 = opt.update({k: torch.ones_like(v) for k, v in p.items()}, st0, p)
+    pairs = _tree_tensors(st0, st1)
+    assert len(pairs) == 5 and all(a.shape == b.shape for a, b in pairs)  # count, mu x 2, nu x 2
+    c = _tree_clone(st1)
+    assert c["count"] is not st1["count"] and float(c["count"]) == 1.0 and torch.equal(c["mu"]["a"], st1["mu"]["a"])
+    with pytest.raises(TypeError):
+        _tree_tensors({"count": 0}, {"count": 1})
+    assert _tree_tensors((), ()) == []
