@@ -238,3 +238,78 @@ def test_collapsed_elbo_gradient_adjudicated_at_40_digits():
     assert max(err[k][1] for k in ("lengthscale", "variance", "obs_stddev")) <= 1e-8, err
     assert err["inducing_inputs"][1] <= 1e4 * F["cond_kzz"] * np.finfo(np.float64).eps, err  # 2e-5 here
 
+
+
+# ---- SVGP oracle: pinned on closed forms that involve none of its own linear algebra, and on the
+# collapsed bound, which is itself tied to the pinned MLL through ELBO(Z = X) = MLL above ---------------------------------------
+def _svgp_problem(kind, n, m, d, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-2.0, 2.0, (n, d))
+    y = np.sin(X[:, :1]) + 0.1 * rng.standard_normal((n, 1))
+    Z = rng.uniform(-2.0, 2.0, (m, d))
+    ell = np.linspace(0.8, 1.3, d)
+    return X, y, Z, ell, 1.4, 0.3, 0.2  # variance, obs_stddev, mean constant
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern32", "matern52"])
+@pytest.mark.parametrize("n,m,d,num_datapoints", [(1, 1, 1, 1), (40, 7, 2, 40), (64, 12, 3, 1000)])
+def test_svgp_elbo_with_q_equal_to_the_prior_is_the_expected_log_likelihood_under_the_prior(kind, n, m, d, num_datapoints):
+    """q(u) = p(u) (variational mean = prior mean at Z, root covariance = chol(Kzz + jitter I)): the KL term vanishes
+    (the reference's kl(q, q) = 0 identity, tests/test_gaussian_distribution.py) and q(f_i) = N(c, k(x_i, x_i) + jitter), so
+    the bound is  (N / B) * sum_i [ log N(y_i; c, s^2) - (k_ii + jitter) / (2 s^2) ]  -- no matrix enters the right-hand side."""
+    X, y, Z, ell, var, sn, c = _svgp_problem(kind, n, m, d, n + m)
+    jitter = 1e-6
+    W = np.linalg.cholesky(o.gram(kind, Z, ell, var) + jitter * np.eye(m))
+    got = o.svgp_elbo(kind, X, y, Z, ell, var, sn, c, np.full(m, c), W, num_datapoints, jitter)
+    kii = var  # stationary kernels: k(x, x) = variance
+    want = (num_datapoints / n) * np.sum(-0.5 * np.log(2 * np.pi * sn**2) - ((y.reshape(-1) - c) ** 2 + kii + jitter) / (2 * sn**2))
+    assert abs(got - want) <= 1e-9 * abs(want)
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern32", "matern52"])
+@pytest.mark.parametrize("n,m,d", [(30, 5, 1), (80, 16, 3)])
+def test_svgp_elbo_at_the_optimal_q_equals_the_collapsed_bound(kind, n, m, d):
+    """Titsias: maximising the uncollapsed bound over q(u) = N(mu, S) gives  S* = Kzz B^-1 Kzz,  mu* = mu_z + Kzz B^-1 Kzx (y - mu_x) / s^2,
+    B = Kzz + Kzx Kxz / s^2,  and the collapsed bound (objectives.py:342-416).  The reference's per-point predictive adds `jitter`
+    to every marginal variance (variational_families.py:281), which the collapsed bound does not: the two differ by exactly
+    N jitter / (2 s^2).  Ties svgp_elbo (KL with a general q included) to collapsed_elbo and through it to the pinned MLL."""
+    X, y, Z, ell, var, sn, c = _svgp_problem(kind, n, m, d, 3 * n + m)
+    jitter = 1e-6
+    Kzz = o.gram(kind, Z, ell, var) + jitter * np.eye(m)
+    Kzx = o.cross_covariance(kind, Z, X, ell, var)
+    B = Kzz + Kzx @ Kzx.T / sn**2
+    S = Kzz @ np.linalg.solve(B, Kzz)
+    mu = c + Kzz @ np.linalg.solve(B, Kzx @ (y.reshape(-1) - c)) / sn**2
+    W = np.linalg.cholesky(0.5 * (S + S.T))
+    got = o.svgp_elbo(kind, X, y, Z, ell, var, sn, c, mu, W, n, jitter)
+    want = o.collapsed_elbo(kind, X, y, Z, ell, var, sn, c, jitter) - n * jitter / (2 * sn**2)
+    assert abs(got - want) <= 1e-8 * abs(want)
+    # any other q is worse (the bound is tight only at the optimum)
+    assert o.svgp_elbo(kind, X, y, Z, ell, var, sn, c, mu + 0.05, W, n, jitter) < got
+    assert o.svgp_elbo(kind, X, y, Z, ell, var, sn, c, mu, 1.1 * W, n, jitter) < got
+    # the predictive distributions coincide too (variational_families.py:234-285 against :786-870)
+    T = np.random.default_rng(1).uniform(-2.0, 2.0, (9, d))
+    m1, c1 = o.svgp_predict(kind, T, Z, ell, var, c, mu, W, jitter)
+    m2, c2 = o.collapsed_predict(kind, X, y, T, Z, ell, var, sn, c, jitter)
+    assert np.max(np.abs(m1 - m2)) <= 1e-8 * max(1.0, np.max(np.abs(m2)))
+    assert np.max(np.abs(c1 - c2)) <= 1e-8
+
+
+def test_svgp_autodiff_oracle_vanishing_gradient_at_the_optimal_q():
+    """At (mu*, S*) the gradient of the bound with respect to the variational parameters is zero; the torch-autodiff restatement
+    (the oracle the GPU gradients are compared with) must see that stationary point, and must agree in value with the NumPy one."""
+    kind, n, m, d = "rbf", 60, 9, 2
+    X, y, Z, ell, var, sn, c = _svgp_problem(kind, n, m, d, 17)
+    jitter = 1e-6
+    Kzz = o.gram(kind, Z, ell, var) + jitter * np.eye(m)
+    Kzx = o.cross_covariance(kind, Z, X, ell, var)
+    B = Kzz + Kzx @ Kzx.T / sn**2
+    S = Kzz @ np.linalg.solve(B, Kzz)
+    mu = c + Kzz @ np.linalg.solve(B, Kzx @ (y.reshape(-1) - c)) / sn**2
+    W = np.linalg.cholesky(0.5 * (S + S.T))
+    val, g = o.svgp_elbo_value_and_grad_autodiff(kind, X, y, Z, ell, var, sn, c, mu, W, n, jitter)
+    assert abs(val - o.svgp_elbo(kind, X, y, Z, ell, var, sn, c, mu, W, n, jitter)) <= 1e-10 * abs(val)
+    # scale: the gradient a unit away from the optimum
+    _, g_off = o.svgp_elbo_value_and_grad_autodiff(kind, X, y, Z, ell, var, sn, c, mu + 1.0, 2.0 * W, n, jitter)
+    assert np.max(np.abs(g["variational_mean"])) <= 1e-6 * np.max(np.abs(g_off["variational_mean"]))
+    assert np.max(np.abs(g["variational_root_covariance"])) <= 1e-6 * np.max(np.abs(g_off["variational_root_covariance"]))
