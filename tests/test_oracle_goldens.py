@@ -313,3 +313,19 @@ def test_svgp_autodiff_oracle_vanishing_gradient_at_the_optimal_q():
     _, g_off = o.svgp_elbo_value_and_grad_autodiff(kind, X, y, Z, ell, var, sn, c, mu + 1.0, 2.0 * W, n, jitter)
     assert np.max(np.abs(g["variational_mean"])) <= 1e-6 * np.max(np.abs(g_off["variational_mean"]))
     assert np.max(np.abs(g["variational_root_covariance"])) <= 1e-6 * np.max(np.abs(g_off["variational_root_covariance"]))
+
+
+@pytest.mark.parametrize("kind", ["rbf", "matern52"])
+def test_collapsed_predict_with_z_equal_to_x_is_the_exact_posterior(kind):
+    """Z = X makes the Nystroem term exact up to the jitter on Kzz, so CollapsedVariationalGaussian.predict
+    (variational_families.py:786-870) must reproduce ConjugatePosterior.predict (gps.py:443-526), whose oracle is pinned on the
+    stored predictive sums of examples/regression.py -- the predictive twin of the reference's ELBO(Z = X) = MLL test."""
+    rng = np.random.default_rng(5)
+    X = rng.uniform(-2.0, 2.0, (25, 2))
+    y = np.sin(X[:, :1]) + 0.1 * rng.standard_normal((25, 1))
+    T = rng.uniform(-2.0, 2.0, (11, 2))
+    ell, var, sn, c = np.array([0.9, 1.2]), 1.3, 0.4, 0.1
+    m1, c1 = o.collapsed_predict(kind, X, y, T, X, ell, var, sn, c)
+    m2, c2 = o.conjugate_predict(kind, X, y, T, ell, var, sn, c)
+    # approximate by construction (the jitter on Kzz, amplified by cond(Kxx)): observed 1.6e-5 (RBF) / 6e-7 (Matern52)
+    assert np.max(np.abs(m1 - m2)) <= 1e-4 and np.max(np.abs(c1 - c2)) <= 1e-4
