@@ -98,8 +98,9 @@ def fit(*, model: Module, objective, train_data: Dataset, optim: GradientTransfo
             bar = trange(num_iters)
         except Exception:  # pragma: no cover
             bar = None
-    if cuda_graph is None:
-        cuda_graph = os.environ.get("GPB_FIT_CUDA_GRAPH", "0") not in ("", "0")
+    if cuda_graph is None:  # the environment default only applies where a step can be captured; an explicit True is strict
+        cuda_graph = (os.environ.get("GPB_FIT_CUDA_GRAPH", "0") not in ("", "0") and batch_size == -1
+                      and train_data.X.device.type == "cuda")
     if cuda_graph:
         if batch_size != -1:
             raise NotImplementedError("fit(cuda_graph=True) replays one captured step: it needs full batches (batch_size=-1)")
