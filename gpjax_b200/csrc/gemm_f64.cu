@@ -25,6 +25,7 @@
 //     and live columns are walked in chunks of 64 tiles (blockIdx.z) so the B rows of a chunk stay
 //     L2-resident while all tile rows sweep them (DRAM reads of a 44.5k^2 rank-512 update: 41 GB -> 10 GB).
 //   * Triangular K-range skipping for operands with physically-zero triangles (explicit inverses).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace gpb {
@@ -517,6 +518,10 @@ int launch_gemm(cudaStream_t st, const GemmParams& p, int batch) {
 }  // namespace
 
 static int g_variant = 2;
+static const bool g_small_tiles = [] {
+    const char* e = std::getenv("GPB_GEMM_SMALL_TILES");
+    return !(e && e[0] == '0');
+}();
 void debug_set_gemm_variant(int v) { g_variant = v; }
 
 template <int BM, int BN, int WM, int WN, int STAGES, int MINB, bool SWZ, bool BULK>
@@ -570,6 +575,15 @@ int gemm(stream_t s, const GemmDesc& d) {
     if (g_variant == 0) return dispatch_layouts<128, 64, 32, 32, 3, 2, false, false>(st, p, d);
     if (g_variant == 8) return dispatch_layouts<128, 64, 32, 64, 4, 2, true, false>(st, p, d);
     if (g_variant == 9) return dispatch_layouts<128, 64, 32, 64, 3, 2, false, true>(st, p, d);  // TMA bulk-copy staging
+    // Few-tile products (the recursion of the diagonal blocks, the replicated M x M finishes, everything at N of a few thousand):
+    // a 128 x 64 tile keeps one SM's DMMA pipe busy for ~1.1 us per 16-wide K step, so a launch of <= 16 such CTAs runs at the
+    // speed of ONE SM's pipe for K / 16 steps (31-44 us each at K = 128..512, 56 % of a value + gradient at N = 1000:
+    // profiles/r02_mll1000_launches.md) while the other SMs idle.  Quarter tiles (64 x 32, two warps of 32 x 32) put the same
+    // product on four times as many SMs; used while the quarter-tile grid still fits one wave.  GPB_GEMM_SMALL_TILES=0 disables.
+    if (g_small_tiles) {
+        const int64_t t128 = ((d.M + 127) / 128) * ((d.N + 63) / 64) * (int64_t)d.batch;
+        if (4 * t128 <= device_sm_count()) return dispatch_layouts<64, 32, 32, 32, 3, 4, false, false>(st, p, d);
+    }
     return dispatch_layouts<128, 64, 32, 64, 3, 2, false, false>(st, p, d);
 }
 
