@@ -62,6 +62,11 @@ def test_cuda_library_is_sm100a_with_dmma(cuda_lib_path):
     obj = os.path.join(os.path.dirname(cuda_lib_path), "obj", "gemm_f64.o")
     sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
     assert sass.count("DMMA.8x8x4") >= 64 and "LDGSTS" in sass
+    # both tile shapes are in the binary, for all four operand layouts: the full 128 x 64 tile and the quarter tile that few-tile
+    # launches use (gemm_f64.cu: gemm())
+    funcs = re.findall(r"Function : (\S*gemm_f64_kernel\S*)", sass)
+    assert sum("ILi128ELi64ELi32ELi64ELi3ELi2ELb0ELb0E" in f for f in funcs) == 4
+    assert sum("ILi64ELi32ELi32ELi32ELi3ELi4ELb0ELb0E" in f for f in funcs) == 4
 
 
 def test_int8_kernel_is_tcgen05_with_tma_and_tmem(cuda_lib_path):
