@@ -11,7 +11,8 @@
 //   * CTA tile 128x64, 4 warps (4x1), warp tile 32x64 -> 32 DMMA accumulator tiles per warp (12 fragment
 //     loads per 32 DMMAs), ~230 regs, TWO CTAs resident per SM with independent barriers: one CTA's C
 //     read-modify-write epilogue and chunk barriers overlap the other's main loop.  (8 warps x 32x32:
-//     -4 %; a 128x128 CTA with one CTA/SM: -8 %.)
+//     -4 %; a 128x128 CTA with one CTA/SM: -8 %.)  Launches of a few tiles only (<= 37 such CTAs) take the same kernel
+//     instantiated with quarter tiles (64x32, two warps of 32x32): see gemm() at the end of the file.
 //   * K is consumed in 16-wide chunks through a 3-stage cp.async (LDGSTS) shared-memory ring; interior
 //     tiles use a precomputed-pointer fast path (3 instructions per 16-byte copy), edge tiles a fully
 //     predicated path whose zero-fill comes from the copy's src-size operand.
