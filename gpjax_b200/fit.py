@@ -72,8 +72,9 @@ def fit(*, model: Module, objective, train_data: Dataset, optim: GradientTransfo
     replayed for the remaining iterations, so a step costs one graph launch instead of a few hundred kernel launches from Python
     (the launch-bound regime: N of a few thousand, BASELINE config 1).  Requirements, all checked or failing loudly at capture:
     full batches (`batch_size == -1`), everything on one CUDA device, an objective whose evaluation only enqueues device work
-    (conjugate_mll, conjugate_loocv, and the sparse objectives with an explicit statistics route), and an optimiser whose state
-    is made of tensors (the optimisers in `gpjax_b200.optim` are)."""
+    (conjugate_mll, conjugate_loocv, and the sparse objectives: their statistics="auto" route decision needs a host poll, so a
+    captured step takes the reference's whitened order unless a route is named), and an optimiser whose state is made of
+    tensors (the optimisers in `gpjax_b200.optim` are)."""
     if safe:
         _check_model(model)
         _check_train_data(train_data)

@@ -167,6 +167,10 @@ def _use_raw_statistics(mode: str, kind, Z, ell_v, var, jitter) -> bool:
         return True
     if mode != "auto":
         raise ValueError("statistics must be 'auto', 'whitened' or 'raw'")
+    if torch.cuda.is_current_stream_capturing():
+        # fit(cuda_graph=True): a captured step cannot poll an event or re-estimate cond(Kzz) as training moves Z, and a decision
+        # frozen at capture time would outlive its guard -- a replayed step takes the reference's order unless told otherwise
+        return False
     key = (Z.device.index, kind, Z.shape[0], Z.shape[1], float(jitter))
     slot = _ROUTE_CACHE.get(key)
     if slot is None:
