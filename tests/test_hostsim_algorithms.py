@@ -539,3 +539,50 @@ def test_svgp_finish_dense_products_on_the_int8_model(lib):
     for k in gref:
         a, b = np.asarray(out[1][k]), np.asarray(out[3][k])
         assert np.max(np.abs(a - b)) <= 1e-11 * max(np.max(np.abs(np.asarray(gref[k]))), 1e-8 * abs(ref)), k
+
+
+@pytest.mark.parametrize("raw", [False, True])
+def test_sgpr_empty_row_shard(lib, raw):
+    """A rank that holds no rows (N not divisible into non-empty shards, or a minibatch drawn elsewhere) passes N = 0 and null data
+    pointers through the protocol: its statistics and local gradient are exact zeros (every word written, none left as it was), and
+    the reduced result is the full-data ELBO / gradient."""
+    rng = np.random.default_rng(3)
+    N, M, D, block = 90, 12, 2, 32
+    X, y = data(N, D, 5)
+    Z = np.ascontiguousarray(rng.uniform(-2, 2, (M, D)))
+    ell, var, sn, c = np.linspace(0.8, 1.4, D), np.array([1.3]), np.array([0.4]), np.array([0.2])
+    nbytes = lib.gpb_sgpr_workspace_bytes(M, D, block)
+    stats = lib.gpb_sgpr_stats_raw if raw else lib.gpb_sgpr_stats
+    shards = [(np.ascontiguousarray(X), np.ascontiguousarray(y)), (None, None)]
+    wss = [np.zeros(nbytes // 8 + 8) for _ in shards]
+    Ps = []
+    for (Xr, yr), ws in zip(shards, wss):
+        P = np.full(lib.gpb_sgpr_stats_count(M), np.nan)
+        assert stats(None, 0, 0 if Xr is None else len(Xr), M, D, p(Xr), D, p(yr), p(Z), D, p(ell), 0, p(var), p(sn), p(c), 1e-6,
+                     block, p(ws), nbytes, p(P)) == 0
+        Ps.append(P)
+    assert not np.isnan(Ps[1]).any() and np.all(Ps[1] == 0.0)
+    Pall = Ps[0] + Ps[1]
+    val, info = np.zeros(1), np.zeros(2, np.int32)
+    for ws in wss:
+        Pc = Pall.copy()
+        assert lib.gpb_sgpr_finish(None, 0, M, D, p(Z), D, p(ell), 0, p(var), p(sn), block, p(ws), nbytes, p(Pc),
+                                   1 | (2 if raw else 0), p(val), p(info)) == 0
+    ref, gref = o.collapsed_elbo_value_and_grad_autodiff("rbf", X, y, Z, ell, 1.3, 0.4, 0.2)
+    assert abs(val[0] - ref) <= 1e-9 * abs(ref)
+    tot = np.zeros(M * D + D + 1)
+    for (Xr, yr), ws in zip(shards, wss):
+        f = np.full(M * D + D + 1, np.nan)
+        assert lib.gpb_sgpr_grad_local(None, 0, 0 if Xr is None else len(Xr), M, D, p(Xr), D, p(yr), p(Z), D, p(ell), 0, p(var),
+                                       p(sn), p(c), block, p(ws), nbytes, p(f[:M * D]), p(f[M * D:M * D + D]), p(f[M * D + D:])) == 0
+        if Xr is None:
+            assert np.all(f == 0.0)
+        tot += f
+    gZ, gl, gv = tot[:M * D].copy(), tot[M * D:M * D + D].copy(), tot[M * D + D:].copy()
+    gs, gc = np.zeros(1), np.zeros(1)
+    assert lib.gpb_sgpr_grad_finish(None, 0, M, D, p(Z), D, p(ell), 0, p(var), p(sn), block, p(wss[1]), nbytes, None, p(gZ), p(gl),
+                                    p(gv), p(gs), p(gc)) == 0
+    got = dict(lengthscale=gl, variance=gv[0], obs_stddev=gs[0], mean_const=gc[0], inducing_inputs=gZ.reshape(M, D))
+    for k in got:
+        a, b = np.asarray(got[k]).reshape(np.shape(gref[k])), np.asarray(gref[k])
+        assert np.max(np.abs(a - b)) <= 1e-7 * max(np.max(np.abs(b)), 1e-8 * abs(ref)), k
